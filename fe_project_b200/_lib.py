@@ -1,0 +1,84 @@
+"""ctypes loader of the in-tree CUDA library (fe_project_b200/libfedg.so).
+
+There is no Python or CPU fallback: if the library is missing or does not export every
+symbol of include/fedg.h, importing fails loudly.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libfedg.so")
+
+# every extern "C" symbol declared in include/fedg.h
+ABI_SYMBOLS = (
+    "fedg_last_error", "fedg_version", "fedg_create", "fedg_destroy", "fedg_dyn_init",
+    "fedg_set_prog", "fedg_get_prog", "fedg_set_aux", "fedg_set_phyd_hgrad", "fedg_set_coriolis",
+    "fedg_dyn_update", "fedg_dyn_update_host", "fedg_cal_tend_ex", "fedg_get_pres",
+    "fedg_exchange_halo", "fedg_monitor", "fedg_rk_info", "fedg_rk_coef", "fedg_elem_op",
+    "fedg_last_timing", "fedg_comm_unique_id", "fedg_comm_init",
+)
+
+
+class MeshDesc(C.Structure):
+    _fields_ = (
+        [("polyorder", C.c_int)] + [(n, C.c_int) for n in ("Ne", "NeA", "NeX", "NeY", "NeZ", "Ne2D", "Nhalo")]
+        + [(n, C.c_void_p) for n in ("D1D", "Lift", "VPOrdM1", "IntWeight_lgl", "Escale", "Fscale", "normal_fn",
+                                     "J", "Gsqrt", "GI3", "GsqrtH", "zlev", "VMapM", "VMapP", "VMapB", "EMap3Dto2D")]
+        + [("nbr_rank", C.c_int * 6), ("nbr_face", C.c_int * 6), ("my_rank", C.c_int), ("vel_bc", C.c_int * 6)]
+        + [(n, C.c_double) for n in ("GRAV", "Rdry", "CPdry", "CVdry", "PRES00", "OHM")]
+    )
+
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a). fe_project_b200 has no CPU fallback.")
+    L = C.CDLL(LIB_PATH)
+    missing = [s for s in ABI_SYMBOLS if not hasattr(L, s)]
+    if missing:
+        raise ImportError(f"{LIB_PATH} lacks ABI symbols: {missing}")
+    vp, ci, cd = C.c_void_p, C.c_int, C.c_double
+    L.fedg_last_error.restype = C.c_char_p
+    L.fedg_create.argtypes = [C.POINTER(MeshDesc), C.POINTER(vp)]
+    L.fedg_destroy.argtypes = [vp]
+    L.fedg_destroy.restype = None
+    L.fedg_dyn_init.argtypes = [vp, C.c_char_p, C.c_char_p, cd, ci, vp, vp]
+    L.fedg_set_prog.argtypes = [vp] * 6
+    L.fedg_get_prog.argtypes = [vp] * 6
+    L.fedg_set_aux.argtypes = [vp] * 7
+    L.fedg_set_phyd_hgrad.argtypes = [vp] * 3
+    L.fedg_set_coriolis.argtypes = [vp] * 2
+    L.fedg_dyn_update.argtypes = [vp, ci]
+    L.fedg_dyn_update_host.argtypes = [vp] * 6 + [ci]
+    L.fedg_cal_tend_ex.argtypes = [vp] * 6
+    L.fedg_get_pres.argtypes = [vp] * 3
+    L.fedg_exchange_halo.argtypes = [vp, ci]
+    L.fedg_monitor.argtypes = [vp, vp]
+    L.fedg_rk_info.argtypes = [C.c_char_p] + [vp] * 4
+    L.fedg_rk_coef.argtypes = [C.c_char_p] + [vp] * 6
+    L.fedg_elem_op.argtypes = [vp, C.c_char_p, vp, vp, ci]
+    L.fedg_last_timing.argtypes = [vp, vp, vp, vp]
+    L.fedg_comm_unique_id.argtypes = [vp]
+    L.fedg_comm_init.argtypes = [vp, vp, ci, ci]
+    _lib = L
+    return L
+
+
+class FedgError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"fedg error {code}: {msg}")
+        self.code = code
+
+
+def check(rc: int):
+    if rc != 0:
+        raise FedgError(rc, load().fedg_last_error().decode(errors="replace"))

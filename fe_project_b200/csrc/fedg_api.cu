@@ -1,0 +1,611 @@
+// C-ABI layer + host-side driver of the dynamics step (see include/fedg.h).
+//
+// The host side mirrors AtmDynDGMDriver_nonhydro3d%Update
+// (FElib/src/fluid_dyn_solver/scale_atm_dyn_dgm_driver_nonhydro3d.F90:614-963): per RK stage a halo
+// fill (+ boundary condition) and ONE fused stage kernel; the prognostic state ping-pongs between
+// device buffers so that neighbours always read the stage-input state.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "fedg_internal.h"
+#include "rk_tables.h"
+
+using namespace fedg;
+
+namespace {
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg) { g_err = msg; return code; }
+
+#define CUDA_TRY(expr)                                                                              \
+  do {                                                                                              \
+    cudaError_t e__ = (expr);                                                                       \
+    if (e__ != cudaSuccess)                                                                         \
+      return fail(FEDG_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__));              \
+  } while (0)
+
+struct DevBuf {
+  double* p = nullptr;
+  size_t n = 0;
+  cudaError_t alloc(size_t n_) {
+    release();
+    n = n_;
+    cudaError_t e = cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(double));
+    if (e == cudaSuccess) e = cudaMemset(p, 0, std::max<size_t>(n, 1) * sizeof(double));
+    return e;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+};
+}  // namespace
+
+struct fedg_ctx {
+  int np = 0, Np = 0, Nfp = 0, NfpTot = 0;
+  int Ne = 0, NeA = 0, NeX = 0, NeY = 0, NeZ = 0, Ne2D = 0, Nhalo = 0;
+  size_t nint = 0, nall = 0;  // Np*Ne, Np*Ne + Nhalo
+  bool terrain = false, moist = false, has_cor = false, has_phyd = false;
+  bool dyn_ready = false, aux_ready = false;
+  PhysConst c{};
+  double OHM = 0;
+  ElemTables tab{};
+  RKTable rk;
+  std::vector<RKStage> stages;
+  bool vt_used = false, hevi = false, modalfilter = false;
+  double dt = 0;
+  int my_rank = 0, nbr_rank[6], nbr_face[6], vel_bc[6];
+  int face_off[7];
+  cudaStream_t stream = nullptr;
+  // device data
+  DevBuf prog[3][NVAR], vt[NVAR], tendbuf[NVAR];
+  DevBuf dens_hyd, pres_hyd, therm_hyd, rtot, cvtot, cptot, gsqrt, g13, g23, gsqrtH, dphydx, dphydy, coriolis;
+  DevBuf escale, fscale, pres, dpres, w3, Jac, zlev, mon;
+  int* d_vmapP = nullptr; int* d_emap2d = nullptr; int* d_vmapB = nullptr; int* d_halo_src = nullptr;
+  int cur = 0;
+  // timing
+  bool profile = true;
+  std::vector<cudaEvent_t> ev;
+  double last_ms_total = 0, last_ms_stage = 0; long last_launches = 0;
+  ~fedg_ctx() {
+    for (auto& e : ev) cudaEventDestroy(e);
+    if (d_vmapP) cudaFree(d_vmapP);
+    if (d_emap2d) cudaFree(d_emap2d);
+    if (d_vmapB) cudaFree(d_vmapB);
+    if (d_halo_src) cudaFree(d_halo_src);
+    for (auto& s : prog) for (auto& b : s) b.release();
+    for (auto& b : vt) b.release();
+    for (auto& b : tendbuf) b.release();
+    for (DevBuf* b : {&dens_hyd, &pres_hyd, &therm_hyd, &rtot, &cvtot, &cptot, &gsqrt, &g13, &g23, &gsqrtH, &dphydx, &dphydy,
+                      &coriolis, &escale, &fscale, &pres, &dpres, &w3, &Jac, &zlev, &mon})
+      b->release();
+    if (stream) cudaStreamDestroy(stream);
+  }
+};
+
+static ElemTables g_loaded_tab{};
+static bool g_tab_valid = false;
+static void ensure_tables(fedg_ctx* c) {
+  if (!g_tab_valid || std::memcmp(&g_loaded_tab, &c->tab, sizeof(ElemTables)) != 0) {
+    upload_tables(c->tab, c->stream);
+    g_loaded_tab = c->tab;
+    g_tab_valid = true;
+  }
+}
+
+static int upload(fedg_ctx* c, DevBuf& b, const double* host, size_t n) {
+  if (b.n < n) CUDA_TRY(b.alloc(n));
+  CUDA_TRY(cudaMemcpyAsync(b.p, host, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  return FEDG_OK;
+}
+
+extern "C" {
+
+const char* fedg_last_error(void) { return g_err.c_str(); }
+int fedg_version(void) { return 100; }
+
+int fedg_create(const fedg_mesh_desc* d, fedg_ctx** out) {
+  if (!d || !out) return fail(FEDG_ERR_ARG, "null argument");
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t ce = cudaGetDeviceCount(&ndev);
+  if (ce != cudaSuccess || ndev == 0)
+    return fail(FEDG_ERR_CUDA, std::string("no CUDA device: ") + cudaGetErrorString(ce) + " (this library has no CPU fallback)");
+  const int np = d->polyorder + 1;
+  if (np != 8 && np != 4) return fail(FEDG_ERR_UNSUPPORTED, "polyorder must be 7 or 3 in this build");
+  if (d->Ne != d->NeX * d->NeY * d->NeZ || d->Ne2D != d->NeX * d->NeY) return fail(FEDG_ERR_ARG, "Ne / NeX*NeY*NeZ mismatch");
+  for (const void* p : {(const void*)d->D1D, (const void*)d->Lift, (const void*)d->VPOrdM1, (const void*)d->IntWeight_lgl,
+                        (const void*)d->Escale, (const void*)d->Fscale, (const void*)d->normal_fn, (const void*)d->J,
+                        (const void*)d->Gsqrt, (const void*)d->GI3, (const void*)d->GsqrtH, (const void*)d->zlev,
+                        (const void*)d->VMapM, (const void*)d->VMapP, (const void*)d->VMapB, (const void*)d->EMap3Dto2D})
+    if (!p) return fail(FEDG_ERR_ARG, "null array in fedg_mesh_desc");
+
+  std::unique_ptr<fedg_ctx> c(new fedg_ctx);
+  c->np = np; c->Nfp = np * np; c->Np = np * np * np; c->NfpTot = 6 * np * np;
+  c->Ne = d->Ne; c->NeA = d->NeA; c->NeX = d->NeX; c->NeY = d->NeY; c->NeZ = d->NeZ; c->Ne2D = d->Ne2D; c->Nhalo = d->Nhalo;
+  const int Np = c->Np, Nfp = c->Nfp, NfpTot = c->NfpTot, Ne = c->Ne;
+  c->nint = size_t(Np) * Ne; c->nall = c->nint + size_t(c->Nhalo);
+  if (size_t(Np) * d->NeA < c->nall) return fail(FEDG_ERR_ARG, "NeA too small for Nhalo");
+  const int fsz[6] = {c->NeX * c->NeZ, c->NeY * c->NeZ, c->NeX * c->NeZ, c->NeY * c->NeZ, c->NeX * c->NeY, c->NeX * c->NeY};
+  c->face_off[0] = 0;
+  for (int f = 0; f < 6; ++f) c->face_off[f + 1] = c->face_off[f] + fsz[f] * Nfp;
+  if (c->face_off[6] != c->Nhalo) return fail(FEDG_ERR_ARG, "Nhalo does not match the tile face sizes");
+  c->c.GRAV = d->GRAV; c->c.Rdry = d->Rdry; c->c.CPdry = d->CPdry; c->c.CVdry = d->CVdry; c->c.PRES00 = d->PRES00;
+  c->c.rP0 = 1.0 / d->PRES00; c->c.gamm = d->CPdry / d->CVdry; c->c.CPovCV = d->CPdry / d->CVdry; c->OHM = d->OHM;
+  c->my_rank = d->my_rank;
+  for (int f = 0; f < 6; ++f) {
+    c->nbr_rank[f] = d->nbr_rank[f]; c->nbr_face[f] = d->nbr_face[f] - 1; c->vel_bc[f] = d->vel_bc[f];
+    if (c->nbr_face[f] < 0 || c->nbr_face[f] > 5) return fail(FEDG_ERR_ARG, "nbr_face must be 1..6");
+    if (fsz[f] != fsz[c->nbr_face[f]]) return fail(FEDG_ERR_ARG, "neighbour face size mismatch");
+  }
+
+  // ---- element tables
+  ElemTables& T = c->tab;
+  std::memset(&T, 0, sizeof(T));
+  T.np = np;
+  for (int i = 0; i < np; ++i)
+    for (int l = 0; l < np; ++l) {
+      T.D[i * np + l] = d->D1D[i + l * np];
+      T.VP[i * np + l] = d->VPOrdM1[i + l * np];
+      T.Fh[i * np + l] = T.Fv[i * np + l] = (i == l) ? 1.0 : 0.0;
+    }
+  auto LiftAt = [&](int n, int col) { return d->Lift[size_t(n) + size_t(col) * Np]; };
+  for (int m = 0; m < np; ++m) {
+    T.Lw[m * 2] = LiftAt(m, 3 * Nfp);                // x- face, face node (j=0,k=0), volume node (m,0,0)
+    T.Lw[m * 2 + 1] = LiftAt(m, 1 * Nfp);            // x+ face
+  }
+  {  // the lifting matrix must have the tensor-product structure the TensorProd3D operator assumes
+    double scale = 0.0, dev = 0.0, offmax = 0.0;
+    for (int m = 0; m < 2 * np; ++m) scale = std::max(scale, std::fabs(T.Lw[m]));
+    for (int k = 0; k < np; ++k) for (int j = 0; j < np; ++j) for (int i = 0; i < np; ++i) {
+      int n = i + j * np + k * np * np;
+      const int cols[6] = {i + k * np, Nfp + j + k * np, 2 * Nfp + i + k * np, 3 * Nfp + j + k * np, 4 * Nfp + i + j * np, 5 * Nfp + i + j * np};
+      const double w[6] = {T.Lw[j * 2], T.Lw[i * 2 + 1], T.Lw[j * 2 + 1], T.Lw[i * 2], T.Lw[k * 2], T.Lw[k * 2 + 1]};
+      for (int f = 0; f < 6; ++f) dev = std::max(dev, std::fabs(LiftAt(n, cols[f]) - w[f]));
+      // one off-pattern probe per node
+      int colx = (cols[0] + 1) % Nfp;
+      if (colx != cols[0]) offmax = std::max(offmax, std::fabs(LiftAt(n, colx)));
+    }
+    if (dev > 1e-9 * scale || offmax > 1e-9 * scale)
+      return fail(FEDG_ERR_UNSUPPORTED, "elem%Lift is not of tensor-product (I x I x invM1D e_face) form");
+  }
+
+  // ---- geometry: compress what is constant per element / per element face on MeshCubeDom3D
+  std::vector<double> esc(size_t(3) * Ne), fsc(size_t(6) * Ne);
+  for (int ke = 0; ke < Ne; ++ke) {
+    for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) {
+      const double* E = d->Escale + (size_t(a) + 3 * size_t(b)) * size_t(Np) * Ne + size_t(ke) * Np;
+      double v0 = E[0];
+      for (int p = 1; p < Np; ++p)
+        if (std::fabs(E[p] - v0) > 1e-12 * std::fabs(v0)) return fail(FEDG_ERR_UNSUPPORTED, "Escale varies inside an element");
+      if (a == b) esc[size_t(a) * Ne + ke] = v0;
+      else if (v0 != 0.0) return fail(FEDG_ERR_UNSUPPORTED, "Escale has off-diagonal entries");
+    }
+    for (int f = 0; f < 6; ++f) {
+      const double* F = d->Fscale + size_t(ke) * NfpTot + f * Nfp;
+      for (int p = 1; p < Nfp; ++p)
+        if (std::fabs(F[p] - F[0]) > 1e-12 * std::fabs(F[0])) return fail(FEDG_ERR_UNSUPPORTED, "Fscale varies on a face");
+      fsc[size_t(f) * Ne + ke] = F[0];
+      const int ax = (f == 1 || f == 3) ? 0 : (f == 0 || f == 2) ? 1 : 2;
+      const double sg = (f == 1 || f == 2 || f == 5) ? 1.0 : -1.0;
+      for (int p = 0; p < Nfp; ++p)
+        for (int a = 0; a < 3; ++a) {
+          double nv = d->normal_fn[size_t(a) * NfpTot * Ne + size_t(ke) * NfpTot + f * Nfp + p];
+          if (nv != (a == ax ? sg : 0.0)) return fail(FEDG_ERR_UNSUPPORTED, "normal_fn is not axis aligned");
+        }
+    }
+  }
+  bool terrain = false;
+  for (size_t n = 0; n < c->nall && !terrain; ++n)
+    if (d->Gsqrt[n] != 1.0 || d->GI3[n] != 0.0 || d->GI3[size_t(Np) * d->NeA + n] != 0.0) terrain = true;
+  for (size_t n = 0; n < size_t(Nfp) * c->Ne2D && !terrain; ++n) if (d->GsqrtH[n] != 1.0) terrain = true;
+  c->terrain = terrain;
+
+  // ---- connectivity (to 0-based) and the same-rank halo source map
+  std::vector<int> vP(size_t(NfpTot) * Ne), e2(Ne), vB(std::max(c->Nhalo, 1)), src(std::max(c->Nhalo, 1));
+  for (int ke = 0; ke < Ne; ++ke) {
+    e2[ke] = d->EMap3Dto2D[ke] - 1;
+    if (e2[ke] < 0 || e2[ke] >= c->Ne2D) return fail(FEDG_ERR_ARG, "EMap3Dto2D out of range");
+    for (int f = 0; f < 6; ++f) for (int p = 0; p < Nfp; ++p) {
+      size_t q = size_t(ke) * NfpTot + f * Nfp + p;
+      int nloc;
+      switch (f) {
+        case 0: nloc = (p % np) + (p / np) * Nfp; break;
+        case 1: nloc = (np - 1) + (p % np) * np + (p / np) * Nfp; break;
+        case 2: nloc = (p % np) + (np - 1) * np + (p / np) * Nfp; break;
+        case 3: nloc = (p % np) * np + (p / np) * Nfp; break;
+        case 4: nloc = p; break;
+        default: nloc = p + (np - 1) * Nfp; break;
+      }
+      if (d->VMapM[q] - 1 != ke * Np + nloc) return fail(FEDG_ERR_UNSUPPORTED, "VMapM does not follow the hexahedral Fmask order");
+      long vp = long(d->VMapP[q]) - 1;
+      if (vp < 0 || vp >= long(c->nall)) return fail(FEDG_ERR_ARG, "VMapP out of range");
+      vP[q] = int(vp);
+    }
+  }
+  for (int h = 0; h < c->Nhalo; ++h) {
+    vB[h] = d->VMapB[h] - 1;
+    if (vB[h] < 0 || size_t(vB[h]) >= c->nint) return fail(FEDG_ERR_ARG, "VMapB out of range");
+  }
+  for (int f = 0; f < 6; ++f) {
+    const int fo = c->nbr_face[f];
+    const bool local = c->nbr_rank[f] == c->my_rank;
+    for (int m = 0; m < fsz[f] * Nfp; ++m) src[c->face_off[f] + m] = local ? vB[c->face_off[fo] + m] : -1;
+  }
+
+  CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  CUDA_TRY(cudaMalloc(&c->d_vmapP, vP.size() * sizeof(int)));
+  CUDA_TRY(cudaMalloc(&c->d_emap2d, e2.size() * sizeof(int)));
+  CUDA_TRY(cudaMalloc(&c->d_vmapB, vB.size() * sizeof(int)));
+  CUDA_TRY(cudaMalloc(&c->d_halo_src, src.size() * sizeof(int)));
+  CUDA_TRY(cudaMemcpy(c->d_vmapP, vP.data(), vP.size() * sizeof(int), cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(c->d_emap2d, e2.data(), e2.size() * sizeof(int), cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(c->d_vmapB, vB.data(), vB.size() * sizeof(int), cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(c->d_halo_src, src.data(), src.size() * sizeof(int), cudaMemcpyHostToDevice));
+  fedg_ctx* cc = c.get();
+  int rc;
+  if ((rc = upload(cc, c->escale, esc.data(), esc.size()))) return rc;
+  if ((rc = upload(cc, c->fscale, fsc.data(), fsc.size()))) return rc;
+  if ((rc = upload(cc, c->w3, d->IntWeight_lgl, Np))) return rc;
+  if ((rc = upload(cc, c->Jac, d->J, c->nint))) return rc;
+  if ((rc = upload(cc, c->zlev, d->zlev, c->nint))) return rc;
+  if (terrain) {
+    if ((rc = upload(cc, c->gsqrt, d->Gsqrt, c->nall))) return rc;
+    if ((rc = upload(cc, c->g13, d->GI3, c->nall))) return rc;
+    if ((rc = upload(cc, c->g23, d->GI3 + size_t(Np) * d->NeA, c->nall))) return rc;
+    if ((rc = upload(cc, c->gsqrtH, d->GsqrtH, size_t(Nfp) * c->Ne2D))) return rc;
+  }
+  for (auto& s : c->prog) for (auto& b : s) CUDA_TRY(b.alloc(c->nall));
+  for (DevBuf* b : {&c->dens_hyd, &c->pres_hyd, &c->therm_hyd, &c->pres, &c->dpres}) CUDA_TRY(b->alloc(c->nall));
+  CUDA_TRY(c->mon.alloc(8));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  *out = c.release();
+  return FEDG_OK;
+}
+
+void fedg_destroy(fedg_ctx* ctx) { delete ctx; }
+
+int fedg_rk_info(const char* scheme, int* nstage, int* tend_buf_size, int* low_storage, int* imex) {
+  RKTable t;
+  if (!scheme || !t.init(scheme)) return fail(FEDG_ERR_ARG, std::string("unsupported RK scheme ") + (scheme ? scheme : "(null)"));
+  *nstage = t.nstage; *tend_buf_size = t.tend_buf_size; *low_storage = t.low_storage; *imex = t.imex;
+  return FEDG_OK;
+}
+int fedg_rk_coef(const char* scheme, double* a_ex, double* b_ex, double* a_im, double* b_im, double* sig, double* gam) {
+  RKTable t;
+  if (!scheme || !t.init(scheme)) return fail(FEDG_ERR_ARG, "unsupported RK scheme");
+  std::memcpy(a_ex, t.a_ex.data(), t.a_ex.size() * 8); std::memcpy(b_ex, t.b_ex.data(), t.b_ex.size() * 8);
+  std::memcpy(a_im, t.a_im.data(), t.a_im.size() * 8); std::memcpy(b_im, t.b_im.data(), t.b_im.size() * 8);
+  std::memcpy(sig, t.sig.data(), t.sig.size() * 8); std::memcpy(gam, t.gam.data(), t.gam.size() * 8);
+  return FEDG_OK;
+}
+
+// Stage coefficients of the fused update from the scheme tables
+// (rk_advance_low_storage2D scale_timeint_rk.F90:1182-1266, rk_advance_general2D :2201-2355).
+static void build_stages(fedg_ctx* c) {
+  const RKTable& t = c->rk;
+  const int s = t.nstage;
+  const double EPS = 2.220446e-16, dt = c->dt;
+  c->stages.assign(s, RKStage{});
+  c->vt_used = false;
+  if (t.low_storage) {
+    for (int n = 0; n < s - 1; ++n)
+      if (std::fabs(t.sg(s, n)) > EPS || std::fabs(t.gm(s, n)) > EPS) c->vt_used = true;
+    for (int n = 0; n < s; ++n) {
+      RKStage& r = c->stages[n];
+      const double sig_ss = t.sg(n + 1, n), gam_ss = dt * t.gm(n + 1, n);
+      r.c_q = sig_ss; r.c_k = gam_ss;
+      if (n == s - 1) { r.add_vt = c->vt_used; continue; }
+      r.c_q0 = 1.0 - sig_ss; r.use_q0 = (r.c_q0 != 0.0);
+      const double sig_Ns = t.sg(s, n), gam_Ns = dt * t.gm(s, n);
+      const bool upd = std::fabs(sig_Ns) > EPS || std::fabs(t.gm(s, n)) > EPS;
+      if (c->vt_used && (upd || n == 0)) {
+        r.vt_update = 1; r.vt_init = (n == 0); r.vt_init_q = 0.0;
+        r.vt_q = upd ? sig_Ns : 0.0; r.vt_k = upd ? gam_Ns : 0.0;
+      }
+    }
+  } else {  // general explicit scheme with tend_buf_size == 1
+    for (int n = 0; n < s; ++n) {
+      RKStage& r = c->stages[n];
+      if (s == 1) { r.c_q = 1.0; r.c_k = dt * t.b_ex[0]; continue; }
+      c->vt_used = true;
+      if (n == s - 1) { r.add_vt = 1; r.c_q = 0.0; r.c_k = dt * t.b_ex[n]; continue; }
+      r.use_q0 = 1; r.c_q0 = 1.0; r.c_q = 0.0; r.c_k = dt * t.aex(n + 1, n);
+      r.vt_update = 1; r.vt_init = (n == 0); r.vt_init_q = 1.0; r.vt_q = 0.0; r.vt_k = dt * t.b_ex[n];
+    }
+  }
+}
+
+int fedg_dyn_init(fedg_ctx* c, const char* eqs_type, const char* tinteg_type, double dt, int modalfilter_flag,
+                  const double* filter_h1D, const double* filter_v1D) {
+  if (!c || !eqs_type || !tinteg_type) return fail(FEDG_ERR_ARG, "null argument");
+  std::string eqs(eqs_type);
+  if (eqs == "NONHYDRO3D_HEVE") c->hevi = false;
+  else return fail(FEDG_ERR_UNSUPPORTED, "EQS_TYPE " + eqs + " is not available in this build (NONHYDRO3D_HEVE only)");
+  if (!c->rk.init(tinteg_type)) return fail(FEDG_ERR_ARG, std::string("unsupported TINTEG_TYPE ") + tinteg_type);
+  if (c->rk.imex) return fail(FEDG_ERR_ARG, "HEVE needs an explicit RK scheme");
+  if (c->rk.tend_buf_size != 1) return fail(FEDG_ERR_UNSUPPORTED, "explicit schemes with several tendency buffers are not supported");
+  if (!(dt > 0.0)) return fail(FEDG_ERR_ARG, "dt must be positive");
+  c->dt = dt;
+  build_stages(c);
+  if (c->vt_used) for (auto& b : c->vt) if (b.n < c->nall) CUDA_TRY(b.alloc(c->nall));
+  c->modalfilter = modalfilter_flag != 0;
+  const int np = c->np;
+  for (int i = 0; i < np; ++i)
+    for (int l = 0; l < np; ++l) {
+      c->tab.Fh[i * np + l] = c->modalfilter ? 0.0 : (i == l ? 1.0 : 0.0);
+      c->tab.Fv[i * np + l] = c->tab.Fh[i * np + l];
+    }
+  if (c->modalfilter) {
+    if (!filter_h1D || !filter_v1D) return fail(FEDG_ERR_ARG, "modal filter matrices missing");
+    for (int i = 0; i < np; ++i)
+      for (int l = 0; l < np; ++l) { c->tab.Fh[i * np + l] = filter_h1D[i + l * np]; c->tab.Fv[i * np + l] = filter_v1D[i + l * np]; }
+  }
+  c->dyn_ready = true;
+  return FEDG_OK;
+}
+
+int fedg_set_prog(fedg_ctx* c, const double* DDENS, const double* MOMX, const double* MOMY, const double* MOMZ, const double* DRHOT) {
+  if (!c || !DDENS || !MOMX || !MOMY || !MOMZ || !DRHOT) return fail(FEDG_ERR_ARG, "null argument");
+  const double* h[NVAR] = {DDENS, MOMX, MOMY, MOMZ, DRHOT};
+  for (int v = 0; v < NVAR; ++v)
+    CUDA_TRY(cudaMemcpyAsync(c->prog[c->cur][v].p, h[v], c->nall * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  return FEDG_OK;
+}
+
+int fedg_get_prog(fedg_ctx* c, double* DDENS, double* MOMX, double* MOMY, double* MOMZ, double* DRHOT) {
+  if (!c || !DDENS || !MOMX || !MOMY || !MOMZ || !DRHOT) return fail(FEDG_ERR_ARG, "null argument");
+  double* h[NVAR] = {DDENS, MOMX, MOMY, MOMZ, DRHOT};
+  for (int v = 0; v < NVAR; ++v)
+    CUDA_TRY(cudaMemcpyAsync(h[v], c->prog[c->cur][v].p, c->nall * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  return FEDG_OK;
+}
+
+// gather own-face values into the halo slots of an auxiliary field (same-rank faces)
+static int fill_aux_halo(fedg_ctx* c, double* field);
+
+int fedg_set_aux(fedg_ctx* c, const double* DENS_hyd, const double* PRES_hyd, const double* THERM_hyd, const double* Rtot,
+                 const double* CVtot, const double* CPtot) {
+  if (!c || !DENS_hyd || !PRES_hyd || !Rtot || !CVtot || !CPtot) return fail(FEDG_ERR_ARG, "null argument");
+  int rc;
+  if ((rc = upload(c, c->dens_hyd, DENS_hyd, c->nint))) return rc;
+  if ((rc = upload(c, c->pres_hyd, PRES_hyd, c->nint))) return rc;
+  if (THERM_hyd) { if ((rc = upload(c, c->therm_hyd, THERM_hyd, c->nint))) return rc; }
+  else launch_calc_rhot_hyd(c->pres_hyd.p, c->c, c->therm_hyd.p, long(c->nint), c->stream);
+  bool moist = false;
+  for (size_t n = 0; n < c->nint && !moist; ++n)
+    if (Rtot[n] != c->c.Rdry || CVtot[n] != c->c.CVdry || CPtot[n] != c->c.CPdry) moist = true;
+  c->moist = moist;
+  if (moist) {
+    for (DevBuf* b : {&c->rtot, &c->cvtot, &c->cptot}) if (b->n < c->nall) CUDA_TRY(b->alloc(c->nall));
+    if ((rc = upload(c, c->rtot, Rtot, c->nint))) return rc;
+    if ((rc = upload(c, c->cvtot, CVtot, c->nint))) return rc;
+    if ((rc = upload(c, c->cptot, CPtot, c->nint))) return rc;
+  }
+  for (DevBuf* b : {&c->dens_hyd, &c->pres_hyd, &c->therm_hyd}) if ((rc = fill_aux_halo(c, b->p))) return rc;
+  if (moist) for (DevBuf* b : {&c->rtot, &c->cvtot, &c->cptot}) if ((rc = fill_aux_halo(c, b->p))) return rc;
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  c->aux_ready = true;
+  return FEDG_OK;
+}
+
+int fedg_set_phyd_hgrad(fedg_ctx* c, const double* DPhydDx, const double* DPhydDy) {
+  if (!c) return fail(FEDG_ERR_ARG, "null argument");
+  c->has_phyd = false;
+  if (!DPhydDx || !DPhydDy) return FEDG_OK;
+  bool nz = false;
+  for (size_t n = 0; n < c->nint && !nz; ++n) if (DPhydDx[n] != 0.0 || DPhydDy[n] != 0.0) nz = true;
+  if (!nz) return FEDG_OK;
+  int rc;
+  if ((rc = upload(c, c->dphydx, DPhydDx, c->nint))) return rc;
+  if ((rc = upload(c, c->dphydy, DPhydDy, c->nint))) return rc;
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  c->has_phyd = true;
+  return FEDG_OK;
+}
+
+int fedg_set_coriolis(fedg_ctx* c, const double* cor) {
+  if (!c) return fail(FEDG_ERR_ARG, "null argument");
+  c->has_cor = false;
+  if (!cor) return FEDG_OK;
+  const size_t n2 = size_t(c->Nfp) * c->Ne2D;
+  bool nz = false;
+  for (size_t n = 0; n < n2 && !nz; ++n) if (cor[n] != 0.0) nz = true;
+  if (!nz) return FEDG_OK;
+  int rc;
+  if ((rc = upload(c, c->coriolis, cor, n2))) return rc;
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  c->has_cor = true;
+  return FEDG_OK;
+}
+
+}  // extern "C"
+
+// ---- host-side stage sequencing ------------------------------------------------------------
+namespace {
+
+__global__ void aux_halo_kernel(double* q, const int* src, int nint, int nhalo) {
+  int h = blockIdx.x * blockDim.x + threadIdx.x;
+  if (h < nhalo && src[h] >= 0) q[size_t(nint) + h] = q[src[h]];
+}
+
+void fill_halo(fedg_ctx* c, int buf, bool apply_bc) {
+  HaloParams H{};
+  for (int v = 0; v < NVAR; ++v) H.q[v] = c->prog[buf][v].p;
+  H.src = c->d_halo_src; H.vmapB = c->d_vmapB;
+  H.gsqrt = c->gsqrt.p; H.g13 = c->g13.p; H.g23 = c->g23.p; H.gsqrtH = c->gsqrtH.p; H.emap2d = c->d_emap2d;
+  for (int f = 0; f < 7; ++f) H.face_off[f] = c->face_off[f];
+  for (int f = 0; f < 6; ++f) {
+    // a face carries the BC only when its neighbour is the tile itself with the same face (bnd_Init_lc)
+    bool phys = c->nbr_rank[f] == c->my_rank && c->nbr_face[f] == f;
+    H.bc[f] = (apply_bc && phys) ? c->vel_bc[f] : FEDG_BND_NOSPEC;
+  }
+  H.Np = c->Np; H.Ne = c->Ne; H.Nfp = c->Nfp; H.np = c->np; H.Nhalo = c->Nhalo; H.terrain = c->terrain;
+  launch_halo_fill(H, c->stream);
+}
+
+void fill_stage_params(fedg_ctx* c, StageParams& P, int in, int out, int q0) {
+  for (int v = 0; v < NVAR; ++v) {
+    P.qin[v] = c->prog[in][v].p; P.qout[v] = c->prog[out][v].p; P.q0[v] = c->prog[q0][v].p;
+    P.vt[v] = c->vt[v].p; P.tend_out[v] = nullptr;
+  }
+  P.dens_hyd = c->dens_hyd.p; P.pres_hyd = c->pres_hyd.p; P.therm_hyd = c->therm_hyd.p;
+  P.rtot = c->rtot.p; P.cvtot = c->cvtot.p; P.cptot = c->cptot.p;
+  P.gsqrt = c->gsqrt.p; P.g13 = c->g13.p; P.g23 = c->g23.p; P.gsqrtH = c->gsqrtH.p;
+  P.dphydx = c->dphydx.p; P.dphydy = c->dphydy.p; P.coriolis = c->coriolis.p;
+  P.escale = c->escale.p; P.fscale = c->fscale.p; P.vmapP = c->d_vmapP; P.emap2d = c->d_emap2d;
+  P.pres_out = c->pres.p; P.dpres_out = c->dpres.p;
+  P.c = c->c; P.Ne = c->Ne; P.Ne2D = c->Ne2D;
+  P.has_cor = c->has_cor; P.has_phyd = c->has_phyd; P.do_filter = 0; P.write_pres = 0;
+}
+
+int run_steps(fedg_ctx* c, int nsteps) {
+  if (!c->dyn_ready || !c->aux_ready) return fail(FEDG_ERR_STATE, "fedg_dyn_init and fedg_set_aux must be called before the update");
+  ensure_tables(c);
+  const int ns = c->rk.nstage;
+  const size_t need_ev = 2 + (c->profile ? size_t(2) * ns * nsteps : 0);
+  while (c->ev.size() < need_ev) { cudaEvent_t e; CUDA_TRY(cudaEventCreate(&e)); c->ev.push_back(e); }
+  CUDA_TRY(cudaEventRecord(c->ev[0], c->stream));
+  size_t iev = 2;
+  long launches = 0;
+  for (int step = 0; step < nsteps; ++step) {
+    const int i0 = c->cur;
+    int in = i0;
+    for (int s = 0; s < ns; ++s) {
+      int out;
+      if (s == ns - 1) out = (ns == 1) ? (i0 + 1) % 3 : i0;
+      else { out = (in + 1) % 3; if (out == i0) out = (out + 1) % 3; }
+      fill_halo(c, in, true);
+      StageParams P{};
+      fill_stage_params(c, P, in, out, i0);
+      P.rk = c->stages[s];
+      if (s == ns - 1) { P.do_filter = c->modalfilter; P.write_pres = 1; }
+      if (c->profile) CUDA_TRY(cudaEventRecord(c->ev[iev++], c->stream));
+      launch_heve_stage(P, c->np, c->terrain, c->moist, c->stream);
+      if (c->profile) CUDA_TRY(cudaEventRecord(c->ev[iev++], c->stream));
+      launches += 2;
+      in = out;
+    }
+    c->cur = in;
+  }
+  CUDA_TRY(cudaEventRecord(c->ev[1], c->stream));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  CUDA_TRY(cudaGetLastError());
+  float ms = 0;
+  CUDA_TRY(cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]));
+  c->last_ms_total = ms; c->last_ms_stage = 0; c->last_launches = launches;
+  if (c->profile)
+    for (size_t k = 2; k + 1 < iev; k += 2) { float m2 = 0; CUDA_TRY(cudaEventElapsedTime(&m2, c->ev[k], c->ev[k + 1])); c->last_ms_stage += m2; }
+  return FEDG_OK;
+}
+}  // namespace
+
+static int fill_aux_halo(fedg_ctx* c, double* field) {
+  if (c->Nhalo > 0) aux_halo_kernel<<<(c->Nhalo + 255) / 256, 256, 0, c->stream>>>(field, c->d_halo_src, int(c->nint), c->Nhalo);
+  CUDA_TRY(cudaGetLastError());
+  return FEDG_OK;
+}
+
+extern "C" {
+
+int fedg_dyn_update(fedg_ctx* c, int nsteps) {
+  if (!c || nsteps < 0) return fail(FEDG_ERR_ARG, "bad argument");
+  return run_steps(c, nsteps);
+}
+
+int fedg_dyn_update_host(fedg_ctx* c, double* DDENS, double* MOMX, double* MOMY, double* MOMZ, double* DRHOT, int nsteps) {
+  int rc;
+  if ((rc = fedg_set_prog(c, DDENS, MOMX, MOMY, MOMZ, DRHOT))) return rc;
+  if ((rc = run_steps(c, nsteps))) return rc;
+  return fedg_get_prog(c, DDENS, MOMX, MOMY, MOMZ, DRHOT);
+}
+
+int fedg_exchange_halo(fedg_ctx* c, int apply_bc) {
+  if (!c) return fail(FEDG_ERR_ARG, "null argument");
+  fill_halo(c, c->cur, apply_bc != 0);
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  CUDA_TRY(cudaGetLastError());
+  return FEDG_OK;
+}
+
+int fedg_cal_tend_ex(fedg_ctx* c, double* DENS_dt, double* MOMX_dt, double* MOMY_dt, double* MOMZ_dt, double* RHOT_dt) {
+  if (!c || !DENS_dt || !MOMX_dt || !MOMY_dt || !MOMZ_dt || !RHOT_dt) return fail(FEDG_ERR_ARG, "null argument");
+  if (!c->dyn_ready || !c->aux_ready) return fail(FEDG_ERR_STATE, "fedg_dyn_init and fedg_set_aux must be called first");
+  ensure_tables(c);
+  for (auto& b : c->tendbuf) if (b.n < c->nint) CUDA_TRY(b.alloc(c->nint));
+  fill_halo(c, c->cur, true);
+  StageParams P{};
+  fill_stage_params(c, P, c->cur, c->cur, c->cur);
+  for (int v = 0; v < NVAR; ++v) P.tend_out[v] = c->tendbuf[v].p;
+  launch_heve_stage(P, c->np, c->terrain, c->moist, c->stream);
+  double* h[NVAR] = {DENS_dt, MOMX_dt, MOMY_dt, MOMZ_dt, RHOT_dt};
+  for (int v = 0; v < NVAR; ++v)
+    CUDA_TRY(cudaMemcpyAsync(h[v], c->tendbuf[v].p, c->nint * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  CUDA_TRY(cudaGetLastError());
+  return FEDG_OK;
+}
+
+int fedg_get_pres(fedg_ctx* c, double* PRES, double* DPRES) {
+  if (!c || !PRES || !DPRES) return fail(FEDG_ERR_ARG, "null argument");
+  if (!c->aux_ready) return fail(FEDG_ERR_STATE, "fedg_set_aux must be called first");
+  launch_calc_pres(c->prog[c->cur][V_DRHOT].p, c->pres_hyd.p, c->therm_hyd.p, c->rtot.p, c->cvtot.p, c->cptot.p, c->moist, c->c,
+                   c->pres.p, c->dpres.p, long(c->nint), c->stream);
+  CUDA_TRY(cudaMemcpyAsync(PRES, c->pres.p, c->nint * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(cudaMemcpyAsync(DPRES, c->dpres.p, c->nint * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  CUDA_TRY(cudaGetLastError());
+  return FEDG_OK;
+}
+
+int fedg_monitor(fedg_ctx* c, double* out) {
+  if (!c || !out) return fail(FEDG_ERR_ARG, "null argument");
+  if (!c->aux_ready) return fail(FEDG_ERR_STATE, "fedg_set_aux must be called first");
+  launch_calc_pres(c->prog[c->cur][V_DRHOT].p, c->pres_hyd.p, c->therm_hyd.p, c->rtot.p, c->cvtot.p, c->cptot.p, c->moist, c->c,
+                   c->pres.p, c->dpres.p, long(c->nint), c->stream);
+  const double* q[NVAR];
+  for (int v = 0; v < NVAR; ++v) q[v] = c->prog[c->cur][v].p;
+  launch_monitor(q, c->dens_hyd.p, c->pres.p, c->rtot.p, c->moist, c->w3.p, c->Jac.p, c->gsqrt.p, c->terrain, c->zlev.p, c->c,
+                 c->Np, c->Ne, c->mon.p, c->stream);
+  CUDA_TRY(cudaMemcpyAsync(out, c->mon.p, 5 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  CUDA_TRY(cudaGetLastError());
+  return FEDG_OK;
+}
+
+int fedg_elem_op(fedg_ctx* c, const char* name, const double* in, double* out, int nelem) {
+  if (!c || !name || !in || !out || nelem <= 0) return fail(FEDG_ERR_ARG, "bad argument");
+  static const char* names[6] = {"Dx", "Dy", "Dz", "Lift", "VFilterPM1", "ModalFilter"};
+  int op = -1;
+  for (int k = 0; k < 6; ++k) if (std::strcmp(name, names[k]) == 0) op = k;
+  if (op < 0) return fail(FEDG_ERR_ARG, std::string("unknown element operation ") + name);
+  ensure_tables(c);
+  const size_t nin = size_t(op == 3 ? c->NfpTot : c->Np) * nelem, nout = size_t(c->Np) * nelem;
+  DevBuf a, b;
+  CUDA_TRY(a.alloc(nin)); CUDA_TRY(b.alloc(nout));
+  CUDA_TRY(cudaMemcpyAsync(a.p, in, nin * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  launch_elem_op(op, a.p, b.p, nelem, c->np, c->stream);
+  CUDA_TRY(cudaMemcpyAsync(out, b.p, nout * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  cudaError_t e = cudaGetLastError();
+  a.release(); b.release();
+  if (e != cudaSuccess) return fail(FEDG_ERR_CUDA, cudaGetErrorString(e));
+  return FEDG_OK;
+}
+
+int fedg_last_timing(fedg_ctx* c, double* ms_total, double* ms_stage_kernels, long* n_launches) {
+  if (!c) return fail(FEDG_ERR_ARG, "null argument");
+  if (ms_total) *ms_total = c->last_ms_total;
+  if (ms_stage_kernels) *ms_stage_kernels = c->last_ms_stage;
+  if (n_launches) *n_launches = c->last_launches;
+  return FEDG_OK;
+}
+
+int fedg_comm_unique_id(void*) { return fail(FEDG_ERR_UNSUPPORTED, "NCCL halo exchange is not built yet"); }
+int fedg_comm_init(fedg_ctx*, const void*, int, int) { return fail(FEDG_ERR_UNSUPPORTED, "NCCL halo exchange is not built yet"); }
+
+}  // extern "C"

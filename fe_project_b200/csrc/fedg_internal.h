@@ -1,0 +1,87 @@
+// Internal declarations shared by the C-ABI layer and the CUDA kernels (sm_100a, FP64).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "../../include/fedg.h"
+
+namespace fedg {
+
+constexpr int NVAR = 5;
+// internal variable order of the per-variable pointer arrays
+enum { V_DDENS = 0, V_MOMX = 1, V_MOMY = 2, V_MOMZ = 3, V_DRHOT = 4 };
+
+constexpr int MAXNP = 8;  // nodes per direction supported by the kernels (p <= 7)
+
+// Element operator tables, uploaded to __constant__ memory (uniform indices become constant-bank
+// operands of DFMA; per-thread rows are fetched once per kernel).
+struct ElemTables {
+  double D[MAXNP * MAXNP];    // D1D[i][l], row-major
+  double Lw[MAXNP * 2];       // lift1d[m][side]
+  double VP[MAXNP * MAXNP];   // VPOrdM1[k][l]
+  double Fh[MAXNP * MAXNP];   // horizontal modal filter [i][l]
+  double Fv[MAXNP * MAXNP];   // vertical modal filter [k][l]
+  int np;
+  int pad;
+};
+
+// Coefficients of one explicit RK stage in the fused update
+//   q_new  = c_q0*q0 + c_q*q + c_k*k  (+ varTmp when add_vt)
+//   varTmp = (vt_init ? vt_init_q*q : varTmp) + vt_q*q + vt_k*k   (when vt_update)
+struct RKStage {
+  double c_q0, c_q, c_k;
+  double vt_init_q, vt_q, vt_k;
+  int use_q0, add_vt, vt_update, vt_init;
+};
+
+struct PhysConst {
+  double GRAV, Rdry, CPdry, CVdry, PRES00, rP0, gamm, CPovCV;
+};
+
+struct StageParams {
+  const double* qin[NVAR];
+  double* qout[NVAR];
+  const double* q0[NVAR];
+  double* vt[NVAR];
+  double* tend_out[NVAR];  // when non-null: write the tendency instead of the updated state
+  const double *dens_hyd, *pres_hyd, *therm_hyd, *rtot, *cvtot, *cptot;
+  const double *gsqrt, *g13, *g23, *gsqrtH;
+  const double *dphydx, *dphydy, *coriolis;
+  const double* escale;  // [3][Ne]
+  const double* fscale;  // [6][Ne]
+  const int* vmapP;      // (NfpTot,Ne) 0-based
+  const int* emap2d;     // (Ne) 0-based
+  double *pres_out, *dpres_out;
+  RKStage rk;
+  PhysConst c;
+  int Ne, Ne2D;
+  int has_cor, has_phyd, do_filter, write_pres;
+};
+
+struct HaloParams {
+  double* q[NVAR];
+  const int* src;        // (Nhalo) interior flat index feeding each halo slot (same-rank faces), -1 = remote
+  const int* vmapB;      // (Nhalo) own face node of each halo slot
+  const double *gsqrt, *g13, *g23, *gsqrtH;
+  const int* emap2d;
+  int face_off[7];
+  int bc[6];
+  int Np, Ne, Nfp, np, Nhalo, terrain;
+};
+
+void upload_tables(const ElemTables& t, cudaStream_t s);
+void launch_heve_stage(const StageParams& p, int np, bool terrain, bool moist, cudaStream_t s);
+void launch_halo_fill(const HaloParams& p, cudaStream_t s);
+void launch_calc_pres(const double* drhot, const double* pres_hyd, const double* therm_hyd, const double* rtot,
+                      const double* cvtot, const double* cptot, bool moist, PhysConst c, double* pres, double* dpres,
+                      long n, cudaStream_t s);
+void launch_calc_rhot_hyd(const double* pres_hyd, PhysConst c, double* therm_hyd, long n, cudaStream_t s);
+void launch_monitor(const double* const q[NVAR], const double* dens_hyd, const double* pres, const double* rtot,
+                    bool moist, const double* w3, const double* Jac, const double* gsqrt, bool terrain,
+                    const double* zlev, PhysConst c, int Np, int Ne, double* out5, cudaStream_t s);
+void launch_elem_op(int op, const double* in, double* out, int nelem, int np, cudaStream_t s);
+
+}  // namespace fedg

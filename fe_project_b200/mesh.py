@@ -1,0 +1,211 @@
+"""Host-side local mesh of a regional cube domain (one tile of `MeshCubeDom3D`).
+
+Builds the arrays the dynamics kernels read from `LocalMesh3D`
+(FElib/src/mesh/scale_localmesh_3d.F90:31-68): `Escale, Fscale, normal_fn, Gsqrt,
+GI3, GsqrtH, J, VMapM, VMapP, VMapB, EMap3Dto2D, pos_en`, with the same element
+numbering (`ke = i + (j-1)*NeX + (k-1)*NeX*NeY`), the same face order
+(y-, x+, y+, x-, z-, z+) and the same halo ordering as
+`MeshUtil3D_genPatchBoundaryMap` (FElib/src/mesh/scale_meshutil_3d.F90:478-641):
+halo slots are face nodes, grouped by tile face 1..6, elements ascending inside a
+face.  Geometry follows `MeshCubeDom3D_coord_conv` / `MeshBase3D_setGeometricInfo`
+(scale_mesh_cubedom3d.F90:545-602, scale_mesh_base3d.F90:175-331).
+
+The tile graph (`tile_neighbors`) restates `MeshUtil3D_buildGlobalMap`
+(scale_meshutil_3d.F90:750-877): a face with no neighbour points back to the tile
+itself with the same face id, which is what makes the halo exchange copy a tile's
+own boundary values into its halo at a physical boundary.
+
+Index maps are produced 0-based for numpy and exported 1-based (Fortran) through
+`LocalMeshCube.abi_*` for the C ABI, which takes the reference's conventions.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from .element import HexElement
+
+# tile face ids, 0-based here: 0 y-, 1 x+, 2 y+, 3 x-, 4 z-, 5 z+
+OPPOSITE_FACE = (2, 3, 0, 1, 5, 4)
+
+BND_NOSPEC, BND_PERIODIC, BND_SLIP, BND_NOSLIP = 0, 1, 2, 3   # scale_mesh_bndinfo.F90:48-54
+
+
+class LocalMeshCube:
+    def __init__(self, elem: HexElement, NeX: int, NeY: int, NeZ: int,
+                 xmin: float, xmax: float, ymin: float, ymax: float,
+                 zmin: float, zmax: float, FZ: np.ndarray | None = None,
+                 periodic=(False, False, False),
+                 NprcX: int = 1, NprcY: int = 1, pi: int = 0, pj: int = 0):
+        """One tile (pi, pj) of an NprcX x NprcY horizontal decomposition; NeX/NeY/NeZ are per tile."""
+        self.elem = elem
+        self.NeX, self.NeY, self.NeZ = NeX, NeY, NeZ
+        self.NprcX, self.NprcY, self.pi, self.pj = NprcX, NprcY, pi, pj
+        self.periodic = tuple(bool(b) for b in periodic)
+        n = elem.np1
+        Np, Nfp = elem.Np, elem.Nfp
+        self.Ne = Ne = NeX * NeY * NeZ
+        self.Ne2D = NeX * NeY
+        self.NeA = Ne + 2 * (NeX + NeY) * NeZ + 2 * NeX * NeY
+        self.Ne2DA = NeX * NeY + 2 * (NeX + NeY)
+        delx = (xmax - xmin) / NprcX
+        dely = (ymax - ymin) / NprcY
+        self.xmin, self.xmax = xmin + pi * delx, xmin + (pi + 1) * delx
+        self.ymin, self.ymax = ymin + pj * dely, ymin + (pj + 1) * dely
+        if FZ is None:
+            FZ = zmin + (zmax - zmin) * np.arange(NeZ + 1) / NeZ
+        self.FZ = np.asarray(FZ, dtype=np.float64)
+        assert self.FZ.size == NeZ + 1
+        self.zmin, self.zmax = self.FZ[0], self.FZ[-1]
+
+        # vertex coordinates exactly as MeshUtil3D_genCubeDomain computes them
+        vx = (self.xmax - self.xmin) * np.arange(NeX + 1) / NeX + self.xmin
+        vy = (self.ymax - self.ymin) * np.arange(NeY + 1) / NeY + self.ymin
+        vz = self.FZ
+
+        ez, ey, ex = np.meshgrid(np.arange(NeZ), np.arange(NeY), np.arange(NeX), indexing="ij")
+        ex, ey, ez = ex.reshape(-1), ey.reshape(-1), ez.reshape(-1)
+        self.ex, self.ey, self.ez = ex, ey, ez
+        self.EMap3Dto2D = ex + ey * NeX
+
+        x0, x1 = vx[ex], vx[ex + 1]
+        y0, y1 = vy[ey], vy[ey + 1]
+        z0, z1 = vz[ez], vz[ez + 1]
+        self.pos_en = np.empty((3, Ne, Np))
+        self.pos_en[0] = x0[:, None] + 0.5 * (elem.x1[None, :] + 1.0) * (x1 - x0)[:, None]
+        self.pos_en[1] = y0[:, None] + 0.5 * (elem.x2[None, :] + 1.0) * (y1 - y0)[:, None]
+        self.pos_en[2] = z0[:, None] + 0.5 * (elem.x3[None, :] + 1.0) * (z1 - z0)[:, None]
+
+        xX, yY, zZ = 0.5 * (x1 - x0), 0.5 * (y1 - y0), 0.5 * (z1 - z0)
+        J = xX * yY * zZ
+        self.J = np.repeat(J[:, None], Np, axis=1)
+        # Escale(:,ke,d,d): only the diagonal is non-zero for this mapping
+        self.Escale = np.zeros((3, 3, Ne, Np))
+        self.Escale[0, 0] = ((yY * zZ) / J)[:, None]
+        self.Escale[1, 1] = ((xX * zZ) / J)[:, None]
+        self.Escale[2, 2] = ((xX * yY) / J)[:, None]
+
+        # normals / Fscale (MeshCubeDom3D_calc_normal + setGeometricInfo)
+        self.normal_fn = np.zeros((3, Ne, elem.NfpTot))
+        self.Fscale = np.empty((Ne, elem.NfpTot))
+        self.sJ = np.empty((Ne, elem.NfpTot))
+        e11, e22, e33 = self.Escale[0, 0, :, 0], self.Escale[1, 1, :, 0], self.Escale[2, 2, :, 0]
+        for f, (d, sgn, esc) in enumerate(((1, -1.0, e22), (0, 1.0, e11), (1, 1.0, e22),
+                                           (0, -1.0, e11), (2, -1.0, e33), (2, 1.0, e33))):
+            sl = slice(f * Nfp, (f + 1) * Nfp)
+            nvec = sgn * esc
+            sj = np.sqrt(nvec ** 2)
+            self.normal_fn[d, :, sl] = (nvec / sj)[:, None]
+            self.sJ[:, sl] = (sj * J)[:, None]
+            self.Fscale[:, sl] = ((sj * J) / J)[:, None]
+
+        # metric factors of the (flat) terrain-following map: defaults of setGeometricInfo
+        self.Gsqrt = np.ones((self.NeA, Np))
+        self.GI3 = np.zeros((2, self.NeA, Np))
+        self.GsqrtH = np.ones((self.Ne2D, Nfp))
+        self.gam = np.ones((self.NeA, Np))
+        self.zlev = self.pos_en[2].copy()
+
+        self._build_maps()
+        self._build_tile_graph()
+
+    # ------------------------------------------------------------------
+    def _build_maps(self):
+        e = self.elem
+        NeX, NeY, NeZ, Ne = self.NeX, self.NeY, self.NeZ, self.Ne
+        Np, Nfp, NfpTot = e.Np, e.Nfp, e.NfpTot
+        ke = np.arange(Ne)
+        ex, ey, ez = self.ex, self.ey, self.ez
+        vmapM = np.empty((Ne, NfpTot), dtype=np.int64)
+        vmapP = np.empty((Ne, NfpTot), dtype=np.int64)
+        for f in range(6):
+            vmapM[:, f * Nfp:(f + 1) * Nfp] = ke[:, None] * Np + e.Fmask[f][None, :]
+        # interior connections: the matching node of the neighbour's opposite face
+        nb = [
+            (ey > 0, ke - NeX), (ex < NeX - 1, ke + 1), (ey < NeY - 1, ke + NeX),
+            (ex > 0, ke - 1), (ez > 0, ke - NeX * NeY), (ez < NeZ - 1, ke + NeX * NeY),
+        ]
+        on_bnd = []
+        for f, (has, kn) in enumerate(nb):
+            fo = OPPOSITE_FACE[f]
+            sl = slice(f * Nfp, (f + 1) * Nfp)
+            kn_ = np.where(has, kn, ke)
+            fo_ = np.where(has, fo, f)
+            vmapP[:, sl] = kn_[:, None] * Np + e.Fmask[fo_]
+            on_bnd.append(~has)
+        # tile-boundary faces -> halo slots (genPatchBoundaryMap ordering)
+        sizes = np.array([NeX * NeZ, NeY * NeZ, NeX * NeZ, NeY * NeZ, NeX * NeY, NeX * NeY]) * Nfp
+        self.halo_face_size = sizes
+        self.halo_face_off = np.concatenate([[0], np.cumsum(sizes)[:-1]])
+        self.Nhalo = int(sizes.sum())
+        rank = [ex + ez * NeX, ey + ez * NeY, ex + ez * NeX, ey + ez * NeY, ex + ey * NeX, ex + ey * NeX]
+        vmapB = np.empty(self.Nhalo, dtype=np.int64)
+        for f in range(6):
+            sel = np.nonzero(on_bnd[f])[0]                 # ascending ke
+            r = rank[f][sel]
+            assert np.array_equal(np.sort(r), r)
+            base = self.halo_face_off[f] + r * Nfp
+            sl = slice(f * Nfp, (f + 1) * Nfp)
+            vmapP[sel, sl] = Np * Ne + base[:, None] + np.arange(Nfp)[None, :]
+            vmapB[(base[:, None] + np.arange(Nfp)[None, :]).reshape(-1)] = \
+                (sel[:, None] * Np + e.Fmask[f][None, :]).reshape(-1)
+        self.VMapM, self.VMapP, self.VMapB = vmapM, vmapP, vmapB
+
+    def _build_tile_graph(self):
+        """(neighbour tile (pi,pj), neighbour face) per tile face; self+same face when none."""
+        px, py = self.periodic[0], self.periodic[1]
+        pi, pj, NX, NY = self.pi, self.pj, self.NprcX, self.NprcY
+        nbr = []
+        for f, (di, dj) in enumerate(((0, -1), (1, 0), (0, 1), (-1, 0))):
+            qi, qj = pi + di, pj + dj
+            if 0 <= qi < NX and 0 <= qj < NY:
+                nbr.append(((qi, qj), OPPOSITE_FACE[f]))
+            elif (di != 0 and px) or (dj != 0 and py):
+                nbr.append(((qi % NX, qj % NY), OPPOSITE_FACE[f]))
+            else:
+                nbr.append(((pi, pj), f))
+        for f in (4, 5):
+            nbr.append(((pi, pj), OPPOSITE_FACE[f] if self.periodic[2] else f))
+        self.tile_neighbors = nbr
+
+    # ------------------------------------------------------------------
+    def halo_bc_types(self, vel_bc: dict | None = None) -> np.ndarray:
+        """Per tile face velocity BC id (bnd_Init_lc, scale_atm_dyn_dgm_bnd.F90:788-838).
+
+        vel_bc maps 'south','east','north','west','btm','top' -> BND_* id.  Only faces whose
+        neighbour is the tile itself with the same face id receive the BC; others stay NOSPEC.
+        """
+        names = ("south", "east", "north", "west", "btm", "top")
+        out = np.zeros(6, dtype=np.int32)
+        vel_bc = vel_bc or {}
+        for f, nm in enumerate(names):
+            (qi, qj), fo = self.tile_neighbors[f]
+            if (qi, qj) == (self.pi, self.pj) and fo == f:
+                out[f] = vel_bc.get(nm, BND_NOSPEC)
+        return out
+
+    def self_exchange_src(self) -> np.ndarray:
+        """For a single-tile run: interior node index feeding each halo slot (0-based).
+
+        Restates Put/Exchange/Get of MeshFieldCommCubeDom3D for same-rank neighbours
+        (scale_meshfieldcomm_base.F90 exchange_core same-rank copy): halo slots of face f
+        receive the sender's VMapB-ordered data of face f' = tile_neighbors[f].face.
+        """
+        src = np.empty(self.Nhalo, dtype=np.int64)
+        for f in range(6):
+            (qi, qj), fo = self.tile_neighbors[f]
+            assert (qi, qj) == (self.pi, self.pj), "self_exchange_src needs a single-tile graph"
+            assert self.halo_face_size[f] == self.halo_face_size[fo]
+            o, oo, s = self.halo_face_off[f], self.halo_face_off[fo], self.halo_face_size[f]
+            src[o:o + s] = self.VMapB[oo:oo + s]
+        return src
+
+    def exchange_halo_numpy(self, q: np.ndarray) -> None:
+        """In-place single-tile halo fill of a (NeA*Np,) or (NeA, Np) field."""
+        flat = q.reshape(-1)
+        flat[self.Ne * self.elem.Np: self.Ne * self.elem.Np + self.Nhalo] = flat[self.self_exchange_src()]
+
+    # ---- exports in the reference's conventions (Fortran order, 1-based) ----
+    def abi_vmapM(self): return (self.VMapM + 1).astype(np.int32)
+    def abi_vmapP(self): return (self.VMapP + 1).astype(np.int32)
+    def abi_vmapB(self): return (self.VMapB + 1).astype(np.int32)
+    def abi_emap3dto2d(self): return (self.EMap3Dto2D + 1).astype(np.int32)

@@ -1,0 +1,169 @@
+/* fedg.h -- C ABI of the B200-native DG dynamics hot path (drop-in for FE-Project's
+ * atm_dyn_dgm_nonhydro3d dynamics step).
+ *
+ * The reference has no C/FFI boundary: its plug-in seams are Fortran type-bound procedures and
+ * procedure pointers.  Each entry point below names the reference interface it stands behind
+ * (paths relative to FE-Project's FElib/src); INTEGRATION.md shows the ISO_C_BINDING interface
+ * block a maintainer adds on the Fortran side.
+ *
+ * Conventions (same as the reference, so a Fortran caller passes its arrays unchanged):
+ *   - all arrays are column-major with the node index fastest: field(Np, NeA);
+ *   - index maps (VMapM, VMapP, VMapB, EMap3Dto2D) are 1-based;
+ *   - real(RP) is double; -DSINGLE builds of the reference are not supported;
+ *   - host pointers are only read/written during the call that receives them: the context copies
+ *     what it needs to the device, the caller keeps ownership;
+ *   - one context per (MPI rank, local mesh) <-> one GPU; calls on one context come from one thread;
+ *   - every function returns FEDG_OK or an error code; fedg_last_error() gives the message.  The
+ *     Fortran shim turns a non-zero status into LOG_ERROR + PRC_abort, which is how the reference
+ *     reports errors.
+ * There is no CPU fallback: without a CUDA device fedg_create() fails with FEDG_ERR_CUDA.
+ */
+#ifndef FEDG_H_
+#define FEDG_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct fedg_ctx fedg_ctx;
+
+enum {
+  FEDG_OK = 0,
+  FEDG_ERR_ARG = 1,         /* bad argument / inconsistent sizes */
+  FEDG_ERR_CUDA = 2,        /* CUDA runtime failure (message holds cudaGetErrorString) */
+  FEDG_ERR_UNSUPPORTED = 3, /* configuration outside what the kernels implement */
+  FEDG_ERR_STATE = 4,       /* call order violated (e.g. update before dyn_init) */
+  FEDG_ERR_COMM = 5         /* NCCL failure */
+};
+
+/* boundary-condition ids, mesh/scale_mesh_bndinfo.F90:48-54 */
+enum { FEDG_BND_NOSPEC = 0, FEDG_BND_PERIODIC = 1, FEDG_BND_SLIP = 2, FEDG_BND_NOSLIP = 3 };
+
+/* Reference element + local mesh of one tile.
+ * Replaces reading LocalMesh3D / ElementBase3D components inside the tendency routines:
+ *   mesh/scale_localmesh_3d.F90:31-68, mesh/scale_localmesh_base.F90:31-75,
+ *   element/scale_element_base.F90:111-145,
+ *   element/scale_element_operation_tensorprod3D.F90.erb:66-80 (D1D, Lift_mat, IntrpMat_VPOrdM1). */
+typedef struct fedg_mesh_desc {
+  int polyorder;            /* PolyOrder_h == PolyOrder_v (TensorProd3D requirement, tensorprod3D.F90.erb:112) */
+  int Ne, NeA, NeX, NeY, NeZ, Ne2D;
+  int Nhalo;                /* size(VMapB) */
+  /* reference element */
+  const double* D1D;            /* (np,np)   elem1D%Dx1                                     */
+  const double* Lift;           /* (Np,NfpTot) elem3D%Lift                                  */
+  const double* VPOrdM1;        /* (np,np)   1D IntrpMat_VPOrdM1 (V * invV with last row 0) */
+  const double* IntWeight_lgl;  /* (Np)                                                     */
+  /* geometry */
+  const double* Escale;     /* (Np,Ne,3,3)   */
+  const double* Fscale;     /* (NfpTot,Ne)   */
+  const double* normal_fn;  /* (NfpTot,Ne,3) */
+  const double* J;          /* (Np,Ne)       */
+  const double* Gsqrt;      /* (Np,NeA)      */
+  const double* GI3;        /* (Np,NeA,2)    */
+  const double* GsqrtH;     /* (Nfp_v,Ne2D)  */
+  const double* zlev;       /* (Np,Ne)       */
+  /* connectivity, 1-based */
+  const int* VMapM;         /* (NfpTot,Ne) */
+  const int* VMapP;         /* (NfpTot,Ne) */
+  const int* VMapB;         /* (Nhalo)     */
+  const int* EMap3Dto2D;    /* (Ne)        */
+  /* tile graph seen from this tile, faces in the order y-, x+, y+, x-, z-, z+
+   * (MeshCubeDom3D%tileID_globalMap / tileFaceID_globalMap / PRCRank_globalMap,
+   *  mesh/scale_meshutil_3d.F90:750-877): rank owning the neighbour tile and the neighbour's
+   *  face id (1..6).  A face with no neighbour points to the own rank with the same face id. */
+  int nbr_rank[6];
+  int nbr_face[6];
+  int my_rank;
+  /* velocity boundary condition per tile face (FEDG_BND_*), applied only where the face has no
+   * neighbour (fluid_dyn_solver/scale_atm_dyn_dgm_bnd.F90:788-838) */
+  int vel_bc[6];
+  /* SCALE constants (scale_const), passed in: GRAV may be overridden by PARAM_CONST */
+  double GRAV, Rdry, CPdry, CVdry, PRES00, OHM;
+} fedg_mesh_desc;
+
+const char* fedg_last_error(void);
+int fedg_version(void);
+
+/* Create / destroy the device-resident context for one local mesh. */
+int fedg_create(const fedg_mesh_desc* desc, fedg_ctx** out);
+void fedg_destroy(fedg_ctx* ctx);
+
+/* AtmDynDGMDriver_nonhydro3d%Init: fluid_dyn_solver/scale_atm_dyn_dgm_driver_nonhydro3d.F90:355-594
+ * eqs_type: "NONHYDRO3D_HEVE" (| "NONHYDRO3D_HEVI" when built); tinteg_type: a timeint_rk scheme name
+ * (common/scale_timeint_rk_butcher_tab.F90:27-67).  filter_h1D / filter_v1D are the (np,np) matrices
+ * MFilter_h1D and MFilter_v1D of Setup_ModalFilter (tensorprod3D.F90.erb:160-181, 460-505); pass
+ * NULL when modalfilter_flag == 0. */
+int fedg_dyn_init(fedg_ctx* ctx, const char* eqs_type, const char* tinteg_type, double dt,
+                  int modalfilter_flag, const double* filter_h1D, const double* filter_v1D);
+
+/* MeshField3D%local(n)%val of the five prognostic variables, (Np,NeA) each, host <-> device. */
+int fedg_set_prog(fedg_ctx* ctx, const double* DDENS, const double* MOMX, const double* MOMY,
+                  const double* MOMZ, const double* DRHOT);
+int fedg_get_prog(fedg_ctx* ctx, double* DDENS, double* MOMX, double* MOMY, double* MOMZ, double* DRHOT);
+
+/* AUX_VARS used by the step (driver_nonhydro3d.F90:683-690).  THERM_hyd may be NULL: it is then
+ * computed as in atm_dyn_dgm_nonhydro3d_common_calc_RHOT_hyd (nonhydro3d_common.F90:584-619).
+ * Interior values only are required: the halo part is filled by a halo exchange, as the model
+ * does after reading a restart file (model mod_atmos_vars.F90:553-636). */
+int fedg_set_aux(fedg_ctx* ctx, const double* DENS_hyd, const double* PRES_hyd, const double* THERM_hyd,
+                 const double* Rtot, const double* CVtot, const double* CPtot);
+/* AUXDYNVARS3D DPhydDx, DPhydDy (driver_nonhydro3d.F90:323-326, 1060-1095); NULL = zero. */
+int fedg_set_phyd_hgrad(fedg_ctx* ctx, const double* DPhydDx, const double* DPhydDy);
+/* Coriolis parameter (Nfp_v, Ne2D); NULL = zero. */
+int fedg_set_coriolis(fedg_ctx* ctx, const double* coriolis);
+
+/* AtmDynDGMDriver_nonhydro3d%Update (driver_nonhydro3d.F90:614-963), nsteps times, state resident
+ * on the device. */
+int fedg_dyn_update(fedg_ctx* ctx, int nsteps);
+/* Same, called the way the reference driver calls Update: prognostic fields live in host arrays;
+ * they are copied to the device, advanced nsteps and copied back. */
+int fedg_dyn_update_host(fedg_ctx* ctx, double* DDENS, double* MOMX, double* MOMY, double* MOMZ,
+                         double* DRHOT, int nsteps);
+
+/* atm_dyn_nonhydro3d_cal_tend_ex seam (driver_nonhydro3d.F90:152-199, 815-828): explicit tendency of
+ * the state currently on the device, after halo exchange, pressure and boundary conditions, i.e.
+ * what the driver stores in tint%tend_buf2D_ex at one stage.  Outputs are host arrays (Np,Ne). */
+int fedg_cal_tend_ex(fedg_ctx* ctx, double* DENS_dt, double* MOMX_dt, double* MOMY_dt, double* MOMZ_dt,
+                     double* RHOT_dt);
+
+/* atm_dyn_dgm_nonhydro3d_common_calc_pressure (nonhydro3d_common.F90:350-393): PRES, DPRES (Np,Ne) of
+ * the state on the device. */
+int fedg_get_pres(fedg_ctx* ctx, double* PRES, double* DPRES);
+
+/* Halo exchange + boundary condition of the prognostic variables, exposed for conformance tests:
+ * MeshFieldComm_Exchange (model_framework/scale_model_var_manager.F90:458-487) followed by
+ * ApplyBC_PROGVARS_lc (scale_atm_dyn_dgm_bnd.F90:270-367).  After the call fedg_get_prog returns
+ * arrays whose halo part [Np*Ne, Np*Ne+Nhalo) is filled. */
+int fedg_exchange_halo(fedg_ctx* ctx, int apply_bc);
+
+/* Conservation monitors: sum(IntWeight_lgl * J * Gsqrt * f) for f = DDENS, ENGT, ENGK, ENGI, ENGP
+ * (file/scale_file_monitor_meshfield.F90:176-213; fields of model mod_atmos_vars_container.F90:1281-1357).
+ * Local-tile sums; out[5]. */
+int fedg_monitor(fedg_ctx* ctx, double* out);
+
+/* timeint_rk tables (common/scale_timeint_rk_butcher_tab.F90): sizes by fedg_rk_info, then coefficients
+ * row-major: a_ex,a_im (nstage*nstage), b_ex,b_im (nstage), sig,gam ((nstage+1)*nstage). */
+int fedg_rk_info(const char* scheme, int* nstage, int* tend_buf_size, int* low_storage, int* imex);
+int fedg_rk_coef(const char* scheme, double* a_ex, double* b_ex, double* a_im, double* b_im, double* sig,
+                 double* gam);
+
+/* ElementOperationBase3D conformance entry points (element/scale_element_operation_base.F90:33-193),
+ * host arrays, nelem elements at once; names: "Dx","Dy","Dz","Lift","VFilterPM1","ModalFilter".
+ * in: (Np,nelem) or (NfpTot,nelem) for Lift; out: (Np,nelem). */
+int fedg_elem_op(fedg_ctx* ctx, const char* name, const double* in, double* out, int nelem);
+
+/* Timing of the last fedg_dyn_update call measured with CUDA events on the context's stream:
+ * ms_total, and the summed duration of the stage kernels only. */
+int fedg_last_timing(fedg_ctx* ctx, double* ms_total, double* ms_stage_kernels, long* n_launches);
+
+/* Multi-GPU: NCCL communicator over the ranks of the tile graph.  The caller obtains the 128-byte
+ * unique id on rank 0 (fedg_comm_unique_id), broadcasts it with its own transport (MPI_Bcast in the
+ * reference, torch.distributed in the tests) and every rank calls fedg_comm_init.  Replaces
+ * MeshFieldCommBase Put/Exchange/Get over MPI (data/scale_meshfieldcomm_base.F90:58-139). */
+int fedg_comm_unique_id(void* id128);
+int fedg_comm_init(fedg_ctx* ctx, const void* id128, int rank, int nranks);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FEDG_H_ */

@@ -1,0 +1,63 @@
+"""Shared builders of synthetic cases for the parity tests (same inputs for oracle and CUDA path)."""
+from __future__ import annotations
+
+import numpy as np
+
+from fe_project_b200 import initcond
+from fe_project_b200.element import HexElement
+from fe_project_b200.mesh import LocalMeshCube
+
+C0 = initcond.SCALE_CONST
+SLIP6 = dict(south="SLIP", east="SLIP", north="SLIP", west="SLIP", btm="SLIP", top="SLIP")
+MF = dict(MF_ETAC_h=2.0 / 3.0, MF_ALPHA_h=1.0, MF_ORDER_h=16, MF_ETAC_v=2.0 / 3.0, MF_ALPHA_v=1.0, MF_ORDER_v=16)
+
+
+class DensityCurrentCase:
+    """Straka density current on NeX x NeY x NeZ elements of order p (config 3 of BASELINE.json, any size)."""
+
+    def __init__(self, p=7, NeX=8, NeY=2, NeZ=4, dom=(0.0, 25.6e3, 0.0, 6.4e3, 0.0, 6.4e3), dt=0.08,
+                 tinteg="ERK_SSP_4s3o", modalfilter=True, perturb=0.0, periodic=(False, True, False), intrp_order=11):
+        self.p, self.dom, self.dt, self.tinteg, self.modalfilter = p, dom, dt, tinteg, modalfilter
+        self.periodic = periodic
+        self.elem = HexElement(p)
+        self.mesh = LocalMeshCube(self.elem, NeX, NeY, NeZ, *dom, periodic=periodic)
+        self.fields = initcond.density_current(self.mesh, intrp_order=intrp_order)
+        if perturb:
+            # deterministic smooth 3D momentum perturbation so that every term of the tendency is exercised
+            x, y, z = (self.mesh.pos_en[d] for d in range(3))
+            Ne = self.mesh.Ne
+            kx, ky, kz = 2 * np.pi / (dom[1] - dom[0]), 2 * np.pi / (dom[3] - dom[2]), np.pi / (dom[5] - dom[4])
+            self.fields["MOMX"][:Ne] = perturb * np.sin(kx * x) * np.cos(ky * y) * np.cos(kz * z)
+            self.fields["MOMY"][:Ne] = perturb * 0.7 * np.sin(kx * x + 0.3) * np.sin(ky * y + 0.1) * np.cos(kz * z)
+            self.fields["MOMZ"][:Ne] = perturb * 0.5 * np.sin(kx * x) * np.cos(ky * y) * np.sin(kz * z)
+        self.vel_bc = SLIP6
+
+    def make_oracle(self):
+        from oracle_api import Oracle
+        m = self.mesh
+        o = Oracle(self.p, m.NeX, m.NeY, m.NeZ, self.dom, periodic=self.periodic)
+        o.set_consts(C0)
+        for k, v in self.fields.items():
+            o.arr(k)[:] = v.reshape(-1)
+        o.arr("Rtot")[:] = C0["Rdry"]; o.arr("CVtot")[:] = C0["CVdry"]; o.arr("CPtot")[:] = C0["CPdry"]
+        mf = (2.0 / 3.0, 1.0, 16, 2.0 / 3.0, 1.0, 16)
+        o.setup_dyn("NONHYDRO3D_HEVE", self.tinteg, self.dt, self.modalfilter, mf, (2, 2, 2, 2, 2, 2))
+        o.prepare()
+        return o
+
+    def make_driver(self, oracle=None):
+        from fe_project_b200.dyncore import AtmDynDGMDriver_nonhydro3d
+        d = AtmDynDGMDriver_nonhydro3d(self.elem, self.mesh, C0, vel_bc=self.vel_bc)
+        d.Init("NONHYDRO3D_HEVE", self.tinteg, self.dt, MODALFILTER_FLAG=self.modalfilter, **MF)
+        f = self.fields
+        d.set_aux(f["DENS_hyd"], f["PRES_hyd"])
+        if oracle is not None:  # DPhydDx/y are set-up products of the model (driver_nonhydro3d.F90:1060-1095)
+            d.set_phyd_hgrad(oracle.arr("DPhydDx"), oracle.arr("DPhydDy"))
+        d.set_prog(*(f[k] for k in ("DDENS", "MOMX", "MOMY", "MOMZ", "DRHOT")))
+        return d
+
+
+def rel_l2(a, b):
+    a = np.asarray(a).reshape(-1); b = np.asarray(b).reshape(-1)
+    nb = np.linalg.norm(b)
+    return np.linalg.norm(a - b) / (nb if nb > 0 else 1.0)

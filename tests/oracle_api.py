@@ -1,0 +1,193 @@
+"""ctypes binding of the CPU oracle (oracle/libfeoracle.so).  Test infrastructure only."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_ORACLE_DIR = os.path.join(os.path.dirname(_HERE), "oracle")
+_LIB = None
+
+
+def build_oracle():
+    so = os.path.join(_ORACLE_DIR, "libfeoracle.so")
+    srcs = [os.path.join(_ORACLE_DIR, f) for f in os.listdir(_ORACLE_DIR) if f.endswith((".cpp", ".hpp"))]
+    if (not os.path.exists(so)) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
+        subprocess.check_call(["make", "-s", "-j8", "-C", _ORACLE_DIR])
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        L = C.CDLL(build_oracle())
+        L.feo_create.restype = C.c_void_p
+        L.feo_create.argtypes = [C.c_int] * 5 + [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.feo_destroy.argtypes = [C.c_void_p]
+        L.feo_dims.argtypes = [C.c_void_p, C.c_void_p]
+        L.feo_array.restype = C.POINTER(C.c_double)
+        L.feo_array.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_long)]
+        L.feo_iarray.restype = C.POINTER(C.c_int)
+        L.feo_iarray.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_long)]
+        L.feo_set_consts.argtypes = [C.c_void_p, C.c_void_p]
+        L.feo_setup_dyn.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_double, C.c_int, C.c_void_p, C.c_void_p]
+        L.feo_prepare.argtypes = [C.c_void_p]
+        L.feo_update.argtypes = [C.c_void_p, C.c_int]
+        L.feo_monitor.argtypes = [C.c_void_p, C.c_void_p]
+        L.feo_stage_piece.argtypes = [C.c_void_p, C.c_char_p]
+        L.feo_elem_op.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.feo_lift_dense.argtypes = [C.c_void_p, C.c_void_p]
+        L.feo_dmat_dense.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.feo_sparsemat_matmul.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.feo_rk_info.argtypes = [C.c_char_p] + [C.c_void_p] * 4
+        L.feo_rk_coef.argtypes = [C.c_char_p] + [C.c_void_p] * 6
+        L.feo_rk_create.restype = C.c_void_p
+        L.feo_rk_create.argtypes = [C.c_char_p, C.c_double, C.c_int, C.c_long]
+        L.feo_rk_destroy.argtypes = [C.c_void_p]
+        L.feo_rk_tend.restype = C.POINTER(C.c_double)
+        L.feo_rk_tend.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
+        L.feo_rk_implicit_fac.restype = C.c_double
+        L.feo_rk_implicit_fac.argtypes = [C.c_void_p, C.c_int]
+        L.feo_rk_store_implicit.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+        L.feo_rk_advance.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+        L.feo_last_error.restype = C.c_char_p
+        _LIB = L
+    return _LIB
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+class Oracle:
+    """One single-tile regional run of the CPU restatement."""
+
+    def __init__(self, p, NeX, NeY, NeZ, dom, periodic=(False, False, False), lumped=False, FZ=None):
+        L = lib()
+        dom = np.asarray(dom, dtype=np.float64)
+        per = np.asarray(periodic, dtype=np.int32)
+        fz = None if FZ is None else np.ascontiguousarray(FZ, dtype=np.float64)
+        self.h = L.feo_create(p, int(lumped), NeX, NeY, NeZ, _p(dom), _p(fz), _p(per))
+        if not self.h:
+            raise RuntimeError(L.feo_last_error().decode())
+        d = np.zeros(8, dtype=np.int32)
+        L.feo_dims(self.h, _p(d))
+        self.Np, self.NfpTot, self.Ne, self.NeA, self.Nhalo, self.np1, self.Ne2D = (int(x) for x in d[:7])
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().feo_destroy(self.h)
+            self.h = None
+
+    def _chk(self, rc):
+        if rc:
+            raise RuntimeError(lib().feo_last_error().decode())
+
+    def arr(self, name) -> np.ndarray:
+        n = C.c_long()
+        ptr = lib().feo_array(self.h, name.encode(), C.byref(n))
+        if not ptr:
+            raise KeyError(name)
+        return np.ctypeslib.as_array(ptr, shape=(n.value,))
+
+    def iarr(self, name) -> np.ndarray:
+        n = C.c_long()
+        ptr = lib().feo_iarray(self.h, name.encode(), C.byref(n))
+        if not ptr:
+            raise KeyError(name)
+        return np.ctypeslib.as_array(ptr, shape=(n.value,))
+
+    def set_consts(self, c):
+        a = np.array([c["GRAV"], c["Rdry"], c["CPdry"], c["CVdry"], c["PRES00"], c.get("OHM", 7.292e-5)], dtype=np.float64)
+        lib().feo_set_consts(self.h, _p(a))
+
+    def setup_dyn(self, eqs, tinteg, dt, modalfilter=False, mf=(0, 0, 0, 0, 0, 0), vel_bc=(0,) * 6):
+        mf = np.asarray(mf, dtype=np.float64)
+        bc = np.asarray(vel_bc, dtype=np.int32)
+        self._chk(lib().feo_setup_dyn(self.h, eqs.encode(), tinteg.encode(), dt, int(modalfilter), _p(mf), _p(bc)))
+
+    def prepare(self):
+        self._chk(lib().feo_prepare(self.h))
+
+    def update(self, nsteps=1):
+        self._chk(lib().feo_update(self.h, nsteps))
+
+    def piece(self, what):
+        self._chk(lib().feo_stage_piece(self.h, what.encode()))
+
+    def monitor(self):
+        out = np.zeros(5)
+        lib().feo_monitor(self.h, _p(out))
+        return out
+
+    def elem_op(self, name, a, b=None, nout=None):
+        out = np.zeros(nout if nout is not None else self.Np)
+        a = np.ascontiguousarray(a, dtype=np.float64)
+        b = None if b is None else np.ascontiguousarray(b, dtype=np.float64)
+        self._chk(lib().feo_elem_op(self.h, name.encode(), _p(a), _p(b), _p(out)))
+        return out
+
+    def lift_dense(self):
+        out = np.zeros((self.Np, self.NfpTot))
+        lib().feo_lift_dense(self.h, _p(out))
+        return out
+
+    def dmat_dense(self, d):
+        out = np.zeros((self.Np, self.Np))
+        lib().feo_dmat_dense(self.h, d, _p(out))
+        return out
+
+
+def sparsemat_matmul(A, b, eps, ell):
+    A = np.ascontiguousarray(A, dtype=np.float64)
+    b = np.ascontiguousarray(b, dtype=np.float64)
+    M, N = A.shape
+    c = np.zeros(M)
+    g = np.zeros((M, N))
+    rc = lib().feo_sparsemat_matmul(_p(A), M, N, eps, int(ell), _p(b), _p(c), _p(g))
+    assert rc == 0
+    return c, g
+
+
+def rk_tables(name):
+    L = lib()
+    n = [C.c_int() for _ in range(4)]
+    rc = L.feo_rk_info(name.encode(), *[C.byref(x) for x in n])
+    if rc:
+        raise KeyError(name)
+    s = n[0].value
+    a_ex, a_im = np.zeros((s, s)), np.zeros((s, s))
+    b_ex, b_im = np.zeros(s), np.zeros(s)
+    sig, gam = np.zeros((s + 1, s)), np.zeros((s + 1, s))
+    L.feo_rk_coef(name.encode(), _p(a_ex), _p(b_ex), _p(a_im), _p(b_im), _p(sig), _p(gam))
+    return dict(nstage=s, tend_buf_size=n[1].value, low_storage=bool(n[2].value), imex=bool(n[3].value),
+                a_ex=a_ex, b_ex=b_ex, a_im=a_im, b_im=b_im, sig=sig, gam=gam)
+
+
+class OracleRK:
+    def __init__(self, name, dt, nvar, n=1):
+        self.h = lib().feo_rk_create(name.encode(), dt, nvar, n)
+        if not self.h:
+            raise RuntimeError(lib().feo_last_error().decode())
+        self.n = n
+        self.info = rk_tables(name)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().feo_rk_destroy(self.h)
+            self.h = None
+
+    def tend(self, im, var, stage):
+        return np.ctypeslib.as_array(lib().feo_rk_tend(self.h, int(im), var, stage), shape=(self.n,))
+
+    def implicit_fac(self, stage):
+        return lib().feo_rk_implicit_fac(self.h, stage)
+
+    def store_implicit(self, stage, q, var):
+        lib().feo_rk_store_implicit(self.h, stage, _p(q), var)
+
+    def advance(self, stage, q, var):
+        lib().feo_rk_advance(self.h, stage, _p(q), var)
