@@ -1,0 +1,255 @@
+#!/usr/bin/env python
+"""bench.py -- DG dynamics DOF-updates/s of the nonhydro3d p=7 hot path on B200.
+
+Contract: `python bench.py --gpus N --steps K --warmup W [--impl reference]` prints ONE JSON line
+(rank 0).  A "step" is one full dynamics time step (all RK stages, boundary conditions, modal filter,
+final pressure diagnostic) of the regional density-current configuration (BASELINE.json configs[2],
+32x32x16 elements, p=7, NONHYDRO3D_HEVE, ERK_SSP_4s3o) over the whole mesh.
+
+  value   : 5*Np*Ne_global*K / t, state resident in HBM, t from CUDA events on the launching stream
+  e2e     : the same metric through the host-buffer entry point (fedg_dyn_update_host): pinned host
+            arrays -> H2D -> step -> D2H inside the timed region, one step per call
+  roofline: fused stage kernel, algorithmic bytes (232 B/node/stage) / mean launch time
+  cpu_baseline / --impl reference: the CPU oracle (reference-equivalent restatement; the Fortran
+            reference cannot be built here) on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "tests")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import numpy as np  # noqa: E402
+
+METRIC = "DG dynamics DOF-updates/s (nonhydro3d p=7)"
+UNIT = "DOF-updates/s"
+ALG_BYTES_PER_NODE_STAGE = 232.0      # SURVEY.md 8(d), HEVE explicit stage fused with low-storage RK
+WORKLOAD = dict(name="atm_nonhydro3d regional density current", p=7, NeX=32, NeY=32, NeZ=16,
+                dom=(0.0, 25.6e3, 0.0, 25.6e3, 0.0, 6.4e3), dt=0.04, eqs="NONHYDRO3D_HEVE", tinteg="ERK_SSP_4s3o")
+
+
+def read_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.gpu = gpu_index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-i", str(self.gpu), "-lms", "50"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        out = dict(sm_mhz=None, sm_max_mhz=None, reasons=[], samples=0)
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        for line in self.f:
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1])); mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+        try:
+            os.unlink(self.f.name)
+        except OSError:
+            pass
+        return out
+
+
+def oracle_sample(threads=None, target_s=12.0):
+    """Times the CPU oracle on a bounded sample: same equations/scheme/filter, 16x8x8 p=7 elements."""
+    from cases import DensityCurrentCase
+    if threads:
+        os.environ["OMP_NUM_THREADS"] = str(threads)
+    case = DensityCurrentCase(p=7, NeX=16, NeY=8, NeZ=8, dom=(0.0, 12.8e3, 0.0, 6.4e3, 0.0, 3.2e3), dt=WORKLOAD["dt"],
+                              tinteg=WORKLOAD["tinteg"], modalfilter=True)
+    o = case.make_oracle()
+    o.update(1)
+    t0 = time.perf_counter(); o.update(2); t1 = (time.perf_counter() - t0) / 2
+    nsteps = int(max(3, min(200, target_s / max(t1, 1e-6))))
+    t0 = time.perf_counter(); o.update(nsteps); dt = time.perf_counter() - t0
+    dof = 5 * case.elem.Np * case.mesh.Ne
+    return dict(value=dof * nsteps / dt, steps=nsteps, seconds=dt,
+                sample=f"density current 16x8x8 elements p=7 ({dof} DOF), {nsteps} steps of ERK_SSP_4s3o + modal filter")
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    vals = []
+    for _ in range(max(1, args.warmup and 1)):
+        pass
+    K = max(1, min(args.steps, 3))
+    for _ in range(K):
+        vals.append(oracle_sample(threads=cores, target_s=8.0))
+    best = max(vals, key=lambda r: r["value"])
+    line = dict(metric=METRIC, value=best["value"], unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
+                ms_per_step=1e3 * best["seconds"] / best["steps"], higher_is_better=True, scaling="weak", vs_baseline=None,
+                dtype="f64", data="synthetic", impl="reference",
+                config=dict(workload=f"{WORKLOAD['name']} (bounded sample of 32x32x16 p=7, HEVE, ERK_SSP_4s3o)"),
+                cpu_baseline=dict(value=best["value"], unit=UNIT, cores=cores, kind="port", sample=best["sample"]),
+                e2e=dict(value=best["value"], unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+                note="CPU oracle = reference-equivalent C++ restatement (g++ -O3 -fopenmp); the Fortran reference "
+                     "needs gfortran+MPI+SCALE 5.5.5, none of which exist in this image")
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=400)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--nex", type=int, default=WORKLOAD["NeX"])
+    ap.add_argument("--ney", type=int, default=WORKLOAD["NeY"])
+    ap.add_argument("--nez", type=int, default=WORKLOAD["NeZ"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_
+        dist = dist_
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    from cases import DensityCurrentCase
+    from fe_project_b200.setup_aux import calc_phyd_hgrad
+    from fe_project_b200.dyncore import PROG_NAMES
+
+    W = max(3, args.warmup)
+    K = args.steps
+    if world > 1:
+        raise SystemExit("multi-GPU tiles need the NCCL halo exchange (not in this build yet)")
+    case = DensityCurrentCase(p=WORKLOAD["p"], NeX=args.nex, NeY=args.ney, NeZ=args.nez, dom=WORKLOAD["dom"],
+                              dt=WORKLOAD["dt"], tinteg=WORKLOAD["tinteg"], modalfilter=True)
+    d = case.make_driver(None)
+    gx, gy = calc_phyd_hgrad(case.elem, case.mesh, case.fields["PRES_hyd"])
+    d.set_phyd_hgrad(gx, gy)
+    Np, Ne = case.elem.Np, case.mesh.Ne
+    dof = 5 * Np * Ne * world
+
+    d.Update(W)
+    torch.cuda.synchronize()
+    if dist:
+        dist.barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    time.sleep(0.12)
+    d.Update(K)
+    torch.cuda.synchronize()
+    tm = d.last_timing()
+    clocks = sampler.stop()
+    if dist:
+        dist.barrier()
+    ms_total = tm["ms_total"]
+    if dist:
+        t = torch.tensor([ms_total], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    value = dof * K / (ms_total * 1e-3)
+    n_stage_launch = tm["launches"] // 2
+    ms_stage = tm["ms_stage_kernels"] / max(1, n_stage_launch)
+    peak, peak_src = read_peaks()
+    alg_bytes = ALG_BYTES_PER_NODE_STAGE * Np * Ne
+    achieved = alg_bytes / (ms_stage * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "heve_stage_traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            traffic = json.load(f).get("dram_bytes_per_launch")
+    state = d.get_prog()
+    finite = all(np.isfinite(state[k][:Np * Ne]).all() for k in PROG_NAMES)
+
+    # ---- e2e: host buffers in, host buffers out, one step per call
+    nall = d.n_field
+    pinned = {k: torch.empty(nall, dtype=torch.float64).pin_memory() for k in PROG_NAMES}
+    host = {k: pinned[k].numpy() for k in PROG_NAMES}
+    for k in PROG_NAMES:
+        host[k][:] = case.fields[k].reshape(-1)
+    d.Update_host(host, 1)
+    ne2e = 5
+    t0 = time.perf_counter()
+    for _ in range(ne2e):
+        d.Update_host(host, 1)
+    torch.cuda.synchronize()
+    t_e2e = (time.perf_counter() - t0) / ne2e
+    if dist:
+        t = torch.tensor([t_e2e], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t_e2e = float(t.item())
+    nbytes = 5 * (Np * Ne + case.mesh.Nhalo) * 8
+    e2e = dict(value=dof / t_e2e, unit=UNIT, h2d_bytes_per_step=nbytes, d2h_bytes_per_step=nbytes, steps_per_call=1)
+
+    if rank == 0:
+        cpu = None
+        if not args.no_cpu_baseline:
+            r = oracle_sample(threads=os.cpu_count(), target_s=12.0)
+            cpu = dict(value=r["value"], unit=UNIT, cores=os.cpu_count(), kind="port", sample=r["sample"])
+        line = dict(
+            metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=K, warmup=W, ms_per_step=ms_total / K,
+            higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64", data="synthetic",
+            config=dict(workload=f"{WORKLOAD['name']}, {args.nex}x{args.ney}x{args.nez} elements p=7, {WORKLOAD['eqs']}, "
+                                 f"{WORKLOAD['tinteg']}, dt={WORKLOAD['dt']}, modal filter on, slip walls x/z, periodic y",
+                        dof=dof, l2_policy="inputs larger than L2 (67 MB per field, >1 GB touched per stage)",
+                        specialisation="flat mesh (Gsqrt=1, GI3=0) and dry thermodynamics detected at registration; "
+                                       "roofline uses the unspecialised 232 B/node/stage"),
+            clocks=clocks, e2e=e2e, gpu_launches=tm["launches"],
+            roofline=dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak, traffic=traffic,
+                          kernel="heve_stage_kernel<8,1,flat,dry>", ms_per_launch=ms_stage,
+                          algorithmic_bytes_per_launch=alg_bytes, peak_source=peak_src),
+            cpu_baseline=cpu, finite=bool(finite))
+        print(json.dumps(line))
+    if dist:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
