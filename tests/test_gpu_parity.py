@@ -1,0 +1,194 @@
+"""Parity of the CUDA path (through the C ABI, libfedg.so) against the CPU oracle on identical seeded inputs.
+Bar (BASELINE.json north_star): relative L2 error of every prognostic variable <= 1e-10 after N steps in FP64."""
+import numpy as np
+import pytest
+
+from cases import DensityCurrentCase, rel_l2, C0
+
+pytestmark = pytest.mark.gpu
+TOL = 1.0e-10
+PROG = ("DDENS", "MOMX", "MOMY", "MOMZ", "DRHOT")
+# oracle variable order in tend_ex: DENS, RHOT, MOMZ, MOMX, MOMY
+TEND = (("DENS_dt", 0), ("RHOT_dt", 1), ("MOMZ_dt", 2), ("MOMX_dt", 3), ("MOMY_dt", 4))
+
+
+@pytest.fixture(scope="module")
+def small_case():
+    case = DensityCurrentCase(p=7, NeX=4, NeY=2, NeZ=3, perturb=2.0)
+    return case
+
+
+def test_library_is_the_cuda_one():
+    from fe_project_b200 import _lib
+    L = _lib.load()
+    assert L.fedg_version() >= 100
+    maps = open("/proc/self/maps").read()
+    assert "libfedg.so" in maps and "libcudart" in maps
+
+
+@pytest.mark.parametrize("p", [3, 7])
+def test_elem_ops(p):
+    """ElementOperationBase3D conformance entry points vs oracle (and hence vs the reference's known answers)."""
+    case = DensityCurrentCase(p=p, NeX=2, NeY=1, NeZ=1, intrp_order=p)
+    o = case.make_oracle()
+    d = case.make_driver(o)
+    e = case.elem
+    rng = np.random.default_rng(5)
+    nelem = 3
+    q = rng.standard_normal((nelem, e.Np))
+    for name in ("Dx", "Dy", "Dz", "VFilterPM1", "ModalFilter"):
+        out = d.elem_op(name, q, nelem).reshape(nelem, e.Np)
+        for k in range(nelem):
+            ref = o.elem_op(name, q[k])
+            assert np.abs(out[k] - ref).max() <= 1e-12 * max(1.0, np.abs(ref).max()), name
+    f = rng.standard_normal((nelem, e.NfpTot))
+    out = d.elem_op("Lift", f, nelem).reshape(nelem, e.Np)
+    for k in range(nelem):
+        ref = o.elem_op("Lift", f[k])
+        assert np.abs(out[k] - ref).max() <= 1e-12 * np.abs(ref).max()
+    # reference known answer: Dx of 4x^p+3y^p+2z^p (test_element_operation_hexahedral.f90:97-144)
+    dat = 4.0 * e.x1 ** p + 3.0 * e.x2 ** p + 2.0 * e.x3 ** p
+    out = d.elem_op("Dx", dat, 1)
+    assert np.sum((out - 4.0 * p * e.x1 ** (p - 1)) ** 2) <= 1e-15
+
+
+def test_pressure(small_case):
+    o = small_case.make_oracle()
+    d = small_case.make_driver(o)
+    P, D = d.get_pres()
+    n = small_case.mesh.Ne * small_case.elem.Np
+    assert rel_l2(P, o.arr("PRES")[:n]) <= 1e-14
+    assert np.abs(D - o.arr("DPRES")[:n]).max() <= 1e-14 * 1e5 * 4
+
+
+def test_halo_and_bc(small_case):
+    o = small_case.make_oracle()
+    d = small_case.make_driver(o)
+    o.piece("exchange"); o.piece("bc")
+    d.exchange_halo(apply_bc=True)
+    g = d.get_prog()
+    n = small_case.mesh.Ne * small_case.elem.Np + small_case.mesh.Nhalo
+    for nm in PROG:
+        assert np.array_equal(g[nm][:n], o.arr(nm)[:n]), nm
+
+
+@pytest.mark.parametrize("p,dims", [(7, (4, 2, 3)), (3, (5, 3, 4))])
+def test_tendency(p, dims):
+    """cal_tend_ex seam: halo + pressure + BC + Rusanov flux + Div_var5 + tendency assembly."""
+    case = DensityCurrentCase(p=p, NeX=dims[0], NeY=dims[1], NeZ=dims[2], perturb=2.0, intrp_order=min(11, p + 4))
+    o = case.make_oracle()
+    d = case.make_driver(o)
+    for w in ("exchange", "pressure", "bc", "tend_ex"):
+        o.piece(w)
+    t = d.cal_tend_ex()
+    n = case.mesh.Ne * case.elem.Np
+    te = o.arr("tend_ex").reshape(5, -1)[:, :n]
+    for nm, iv in TEND:
+        assert rel_l2(t[nm], te[iv]) <= 1e-12, nm
+
+
+@pytest.mark.parametrize("tinteg", ["ERK_SSP_4s3o", "ERK_SSP_3s3o", "ERK_4s4o", "ERK_SSP_10s4o_2N", "ERK_1s1o",
+                                    "ERK_SSP_2s2o", "ERK_SSP_5s3o_2N2*"])
+def test_steps_all_schemes(tinteg):
+    case = DensityCurrentCase(p=7, NeX=3, NeY=2, NeZ=2, perturb=2.0, tinteg=tinteg, dt=0.04)
+    o = case.make_oracle()
+    d = case.make_driver(o)
+    o.update(5); d.Update(5)
+    g = d.get_prog()
+    n = case.mesh.Ne * case.elem.Np
+    for nm in PROG:
+        assert rel_l2(g[nm][:n], o.arr(nm)[:n]) <= TOL, (tinteg, nm)
+
+
+@pytest.mark.parametrize("p,dims,mf,periodic", [(7, (4, 2, 3), True, (False, True, False)),
+                                                (7, (3, 3, 2), False, (False, False, False)),
+                                                (3, (6, 4, 4), True, (True, True, False)),
+                                                (7, (1, 1, 1), True, (False, True, False))])
+def test_steps_density_current(p, dims, mf, periodic):
+    """N = 20 steps of the full dynamics step (all stages, BC, modal filter, final pressure)."""
+    case = DensityCurrentCase(p=p, NeX=dims[0], NeY=dims[1], NeZ=dims[2], perturb=2.0, modalfilter=mf,
+                              periodic=periodic, intrp_order=min(11, p + 4), dt=0.08 if p == 7 else 0.2)
+    o = case.make_oracle()
+    d = case.make_driver(o)
+    o.update(20); d.Update(20)
+    g = d.get_prog()
+    n = case.mesh.Ne * case.elem.Np
+    for nm in PROG:
+        assert rel_l2(g[nm][:n], o.arr(nm)[:n]) <= TOL, nm
+    # conservation monitors match the oracle's (mass, total energy): north_star "to round-off"
+    mo, mg = o.monitor(), d.monitor()
+    vol = float(np.sum(np.tile(case.elem.IntWeight_lgl, case.mesh.Ne) * case.mesh.J.reshape(-1)))
+    assert abs(mo[0] - mg[0]) <= 1e-11 * vol
+    assert abs(mo[1] - mg[1]) <= 1e-12 * abs(mo[1])
+
+
+def test_update_host_roundtrip(small_case):
+    """fedg_dyn_update_host (the way the Fortran driver calls Update: host arrays in/out) == resident update."""
+    o = small_case.make_oracle()
+    d = small_case.make_driver(o)
+    host = {k: np.ascontiguousarray(small_case.fields[k].reshape(-1).copy()) for k in PROG}
+    d.Update_host(host, 3)
+    o.update(3)
+    n = small_case.mesh.Ne * small_case.elem.Np
+    for nm in PROG:
+        assert rel_l2(host[nm][:n], o.arr(nm)[:n]) <= TOL
+
+
+def test_moist_and_coriolis_paths():
+    """Non-dry Rtot/CVtot/CPtot fields and an f-plane Coriolis parameter exercise the un-specialised kernel."""
+    case = DensityCurrentCase(p=7, NeX=3, NeY=2, NeZ=2, perturb=2.0)
+    o = case.make_oracle()
+    m, e = case.mesh, case.elem
+    n = m.Ne * e.Np
+    x = m.pos_en[0].reshape(-1)
+    qv = 0.01 * (1.0 + 0.3 * np.sin(x / 3e3))
+    Rt = np.full(m.NeA * e.Np, C0["Rdry"]); Rt[:n] = C0["Rdry"] * (1 - qv) + 461.5 * qv
+    Cv = np.full(m.NeA * e.Np, C0["CVdry"]); Cv[:n] = C0["CVdry"] * (1 - qv) + 1390.0 * qv
+    Cp = Cv + Rt
+    o.arr("Rtot")[:] = Rt; o.arr("CVtot")[:] = Cv; o.arr("CPtot")[:] = Cp
+    cor = np.full((m.Ne2D, e.Nfp), 1.0e-4)
+    o.arr("CORIOLIS")[:] = cor.reshape(-1)
+    o.prepare()
+    d = case.make_driver(o)
+    d.set_aux(case.fields["DENS_hyd"], case.fields["PRES_hyd"], Rtot=Rt, CVtot=Cv, CPtot=Cp)
+    d.set_coriolis(cor)
+    o.update(5); d.Update(5)
+    g = d.get_prog()
+    for nm in PROG:
+        assert rel_l2(g[nm][:n], o.arr(nm)[:n]) <= TOL, nm
+
+
+def test_errors_are_reported():
+    from fe_project_b200 import _lib
+    case = DensityCurrentCase(p=3, NeX=2, NeY=1, NeZ=1, intrp_order=3)
+    d = case.make_driver(None)
+    with pytest.raises(_lib.FedgError):
+        d.Init("NONHYDRO3D_NOPE", "ERK_SSP_3s3o", 0.1)
+    with pytest.raises(_lib.FedgError):
+        d.Init("NONHYDRO3D_HEVE", "IMEX_ARK232", 0.1)
+
+
+@pytest.mark.parametrize("dims", [(32, 32, 16)])
+def test_full_size_properties(dims):
+    """BASELINE size (32x32x16, p=7; the oracle would take minutes): size-independent properties.
+    (i) closed box: DDENS integral conserved to round-off over steps; (ii) y-translation invariance: the density
+    current is y-independent (ry = 1e13), so every y-row of elements must hold the same values to round-off; (iii) a resting balanced
+    state stays at rest (|momentum| at pow-round-off level)."""
+    case = DensityCurrentCase(p=7, NeX=dims[0], NeY=dims[1], NeZ=dims[2], dom=(0.0, 25.6e3, 0.0, 25.6e3, 0.0, 6.4e3), dt=0.04)
+    d = case.make_driver(None)
+    m0 = d.monitor()
+    d.Update(10)
+    m1 = d.monitor()
+    vol = 25.6e3 * 25.6e3 * 6.4e3
+    assert abs(m1[0] - m0[0]) <= 1e-12 * vol
+    assert abs(m1[1] - m0[1]) <= 1e-9 * abs(m0[1])
+    g = d.get_prog()
+    Np, Ne = case.elem.Np, case.mesh.Ne
+    for nm in ("DDENS", "MOMX", "MOMZ", "DRHOT"):
+        a = g[nm][:Ne * Np].reshape(dims[2], dims[1], dims[0], 8, 8, 8)    # [ez, ey, ex, k, j, i]
+        assert np.isfinite(a).all()
+        sc = np.abs(a).max()
+        assert np.abs(a[:, 0] - a[:, dims[1] // 2]).max() <= 1e-9 * sc, nm
+        assert np.abs(a[:, :, :, :, 0, :] - a[:, :, :, :, 5, :]).max() <= 1e-9 * sc, nm
+    assert np.abs(g["MOMY"][:Ne * Np]).max() <= 1e-9 * np.abs(g["MOMX"][:Ne * Np]).max()
+    assert np.abs(g["MOMX"][:Ne * Np]).max() > 1e-3
