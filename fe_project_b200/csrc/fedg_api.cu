@@ -60,9 +60,12 @@ struct fedg_ctx {
   int face_off[7];
   cudaStream_t stream = nullptr;
   // device data
-  DevBuf prog[3][NVAR], vt[NVAR], tendbuf[NVAR];
+  DevBuf prog[3][NVAR], dp[3], vt[NVAR], tendbuf[NVAR];
+  bool dp_valid[3] = {false, false, false};  // dp[b] holds DPRES of prog[b] (interior)
+  ElemTables* d_tab = nullptr;
+  bool tab_dirty = true;
   DevBuf dens_hyd, pres_hyd, therm_hyd, rtot, cvtot, cptot, gsqrt, g13, g23, gsqrtH, dphydx, dphydy, coriolis;
-  DevBuf escale, fscale, pres, dpres, w3, Jac, zlev, mon;
+  DevBuf escale, fscale, pres, w3, Jac, zlev, mon;
   int* d_vmapP = nullptr; int* d_emap2d = nullptr; int* d_vmapB = nullptr; int* d_halo_src = nullptr;
   int cur = 0;
   // timing
@@ -75,11 +78,13 @@ struct fedg_ctx {
     if (d_emap2d) cudaFree(d_emap2d);
     if (d_vmapB) cudaFree(d_vmapB);
     if (d_halo_src) cudaFree(d_halo_src);
+    if (d_tab) cudaFree(d_tab);
+    for (auto& b : dp) b.release();
     for (auto& s : prog) for (auto& b : s) b.release();
     for (auto& b : vt) b.release();
     for (auto& b : tendbuf) b.release();
     for (DevBuf* b : {&dens_hyd, &pres_hyd, &therm_hyd, &rtot, &cvtot, &cptot, &gsqrt, &g13, &g23, &gsqrtH, &dphydx, &dphydy,
-                      &coriolis, &escale, &fscale, &pres, &dpres, &w3, &Jac, &zlev, &mon})
+                      &coriolis, &escale, &fscale, &pres, &w3, &Jac, &zlev, &mon})
       b->release();
     if (stream) cudaStreamDestroy(stream);
   }
@@ -88,6 +93,11 @@ struct fedg_ctx {
 static ElemTables g_loaded_tab{};
 static bool g_tab_valid = false;
 static void ensure_tables(fedg_ctx* c) {
+  if (!c->d_tab) { cudaMalloc(&c->d_tab, sizeof(ElemTables)); c->tab_dirty = true; }
+  if (c->tab_dirty) {
+    cudaMemcpyAsync(c->d_tab, &c->tab, sizeof(ElemTables), cudaMemcpyHostToDevice, c->stream);  // pageable source: staged before return
+    c->tab_dirty = false;
+  }
   if (!g_tab_valid || std::memcmp(&g_loaded_tab, &c->tab, sizeof(ElemTables)) != 0) {
     upload_tables(c->tab, c->stream);
     g_loaded_tab = c->tab;
@@ -258,7 +268,8 @@ int fedg_create(const fedg_mesh_desc* d, fedg_ctx** out) {
     if ((rc = upload(cc, c->gsqrtH, d->GsqrtH, size_t(Nfp) * c->Ne2D))) return rc;
   }
   for (auto& s : c->prog) for (auto& b : s) CUDA_TRY(b.alloc(c->nall));
-  for (DevBuf* b : {&c->dens_hyd, &c->pres_hyd, &c->therm_hyd, &c->pres, &c->dpres}) CUDA_TRY(b->alloc(c->nall));
+  for (DevBuf* b : {&c->dens_hyd, &c->pres_hyd, &c->therm_hyd, &c->pres}) CUDA_TRY(b->alloc(c->nall));
+  for (auto& b : c->dp) CUDA_TRY(b.alloc(c->nall));
   CUDA_TRY(c->mon.alloc(8));
   CUDA_TRY(cudaStreamSynchronize(c->stream));
   *out = c.release();
@@ -343,6 +354,7 @@ int fedg_dyn_init(fedg_ctx* c, const char* eqs_type, const char* tinteg_type, do
     for (int i = 0; i < np; ++i)
       for (int l = 0; l < np; ++l) { c->tab.Fh[i * np + l] = filter_h1D[i + l * np]; c->tab.Fv[i * np + l] = filter_v1D[i + l * np]; }
   }
+  c->tab_dirty = true;
   c->dyn_ready = true;
   return FEDG_OK;
 }
@@ -353,6 +365,7 @@ int fedg_set_prog(fedg_ctx* c, const double* DDENS, const double* MOMX, const do
   for (int v = 0; v < NVAR; ++v)
     CUDA_TRY(cudaMemcpyAsync(c->prog[c->cur][v].p, h[v], c->nall * sizeof(double), cudaMemcpyHostToDevice, c->stream));
   CUDA_TRY(cudaStreamSynchronize(c->stream));
+  c->dp_valid[c->cur] = false;
   return FEDG_OK;
 }
 
@@ -390,6 +403,7 @@ int fedg_set_aux(fedg_ctx* c, const double* DENS_hyd, const double* PRES_hyd, co
   if (moist) for (DevBuf* b : {&c->rtot, &c->cvtot, &c->cptot}) if ((rc = fill_aux_halo(c, b->p))) return rc;
   CUDA_TRY(cudaStreamSynchronize(c->stream));
   c->aux_ready = true;
+  for (bool& v : c->dp_valid) v = false;
   return FEDG_OK;
 }
 
@@ -436,6 +450,7 @@ __global__ void aux_halo_kernel(double* q, const int* src, int nint, int nhalo) 
 void fill_halo(fedg_ctx* c, int buf, bool apply_bc) {
   HaloParams H{};
   for (int v = 0; v < NVAR; ++v) H.q[v] = c->prog[buf][v].p;
+  H.dp = c->dp[buf].p;
   H.src = c->d_halo_src; H.vmapB = c->d_vmapB;
   H.gsqrt = c->gsqrt.p; H.g13 = c->g13.p; H.g23 = c->g23.p; H.gsqrtH = c->gsqrtH.p; H.emap2d = c->d_emap2d;
   for (int f = 0; f < 7; ++f) H.face_off[f] = c->face_off[f];
@@ -458,9 +473,18 @@ void fill_stage_params(fedg_ctx* c, StageParams& P, int in, int out, int q0) {
   P.gsqrt = c->gsqrt.p; P.g13 = c->g13.p; P.g23 = c->g23.p; P.gsqrtH = c->gsqrtH.p;
   P.dphydx = c->dphydx.p; P.dphydy = c->dphydy.p; P.coriolis = c->coriolis.p;
   P.escale = c->escale.p; P.fscale = c->fscale.p; P.vmapP = c->d_vmapP; P.emap2d = c->d_emap2d;
-  P.pres_out = c->pres.p; P.dpres_out = c->dpres.p;
+  P.pres_out = c->pres.p; P.dpin = c->dp[in].p; P.dpout = c->dp[out].p; P.tab = c->d_tab;
   P.c = c->c; P.Ne = c->Ne; P.Ne2D = c->Ne2D;
   P.has_cor = c->has_cor; P.has_phyd = c->has_phyd; P.do_filter = 0; P.write_pres = 0;
+}
+
+// DPRES of prog[buf] (interior): produced by the stage kernel that wrote prog[buf]; computed here only after the
+// state was replaced from the host (calc_pressure, nonhydro3d_common.F90:350-393).
+void ensure_dp(fedg_ctx* c, int buf) {
+  if (c->dp_valid[buf]) return;
+  launch_calc_pres(c->prog[buf][V_DRHOT].p, c->pres_hyd.p, c->therm_hyd.p, c->rtot.p, c->cvtot.p, c->cptot.p, c->moist, c->c,
+                   c->pres.p, c->dp[buf].p, long(c->nint), c->stream);
+  c->dp_valid[buf] = true;
 }
 
 int run_steps(fedg_ctx* c, int nsteps) {
@@ -479,14 +503,16 @@ int run_steps(fedg_ctx* c, int nsteps) {
       int out;
       if (s == ns - 1) out = (ns == 1) ? (i0 + 1) % 3 : i0;
       else { out = (in + 1) % 3; if (out == i0) out = (out + 1) % 3; }
+      ensure_dp(c, in);
       fill_halo(c, in, true);
       StageParams P{};
       fill_stage_params(c, P, in, out, i0);
       P.rk = c->stages[s];
       if (s == ns - 1) { P.do_filter = c->modalfilter; P.write_pres = 1; }
       if (c->profile) CUDA_TRY(cudaEventRecord(c->ev[iev++], c->stream));
-      launch_heve_stage(P, c->np, c->terrain, c->moist, c->stream);
+      launch_stage(P, c->np, c->terrain, c->moist, false, c->stream);
       if (c->profile) CUDA_TRY(cudaEventRecord(c->ev[iev++], c->stream));
+      c->dp_valid[out] = true;
       launches += 2;
       in = out;
     }
@@ -537,11 +563,12 @@ int fedg_cal_tend_ex(fedg_ctx* c, double* DENS_dt, double* MOMX_dt, double* MOMY
   if (!c->dyn_ready || !c->aux_ready) return fail(FEDG_ERR_STATE, "fedg_dyn_init and fedg_set_aux must be called first");
   ensure_tables(c);
   for (auto& b : c->tendbuf) if (b.n < c->nint) CUDA_TRY(b.alloc(c->nint));
+  ensure_dp(c, c->cur);
   fill_halo(c, c->cur, true);
   StageParams P{};
   fill_stage_params(c, P, c->cur, c->cur, c->cur);
   for (int v = 0; v < NVAR; ++v) P.tend_out[v] = c->tendbuf[v].p;
-  launch_heve_stage(P, c->np, c->terrain, c->moist, c->stream);
+  launch_stage(P, c->np, c->terrain, c->moist, false, c->stream);
   double* h[NVAR] = {DENS_dt, MOMX_dt, MOMY_dt, MOMZ_dt, RHOT_dt};
   for (int v = 0; v < NVAR; ++v)
     CUDA_TRY(cudaMemcpyAsync(h[v], c->tendbuf[v].p, c->nint * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
@@ -554,9 +581,10 @@ int fedg_get_pres(fedg_ctx* c, double* PRES, double* DPRES) {
   if (!c || !PRES || !DPRES) return fail(FEDG_ERR_ARG, "null argument");
   if (!c->aux_ready) return fail(FEDG_ERR_STATE, "fedg_set_aux must be called first");
   launch_calc_pres(c->prog[c->cur][V_DRHOT].p, c->pres_hyd.p, c->therm_hyd.p, c->rtot.p, c->cvtot.p, c->cptot.p, c->moist, c->c,
-                   c->pres.p, c->dpres.p, long(c->nint), c->stream);
+                   c->pres.p, c->dp[c->cur].p, long(c->nint), c->stream);
+  c->dp_valid[c->cur] = true;
   CUDA_TRY(cudaMemcpyAsync(PRES, c->pres.p, c->nint * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-  CUDA_TRY(cudaMemcpyAsync(DPRES, c->dpres.p, c->nint * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(cudaMemcpyAsync(DPRES, c->dp[c->cur].p, c->nint * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   CUDA_TRY(cudaStreamSynchronize(c->stream));
   CUDA_TRY(cudaGetLastError());
   return FEDG_OK;
@@ -566,7 +594,8 @@ int fedg_monitor(fedg_ctx* c, double* out) {
   if (!c || !out) return fail(FEDG_ERR_ARG, "null argument");
   if (!c->aux_ready) return fail(FEDG_ERR_STATE, "fedg_set_aux must be called first");
   launch_calc_pres(c->prog[c->cur][V_DRHOT].p, c->pres_hyd.p, c->therm_hyd.p, c->rtot.p, c->cvtot.p, c->cptot.p, c->moist, c->c,
-                   c->pres.p, c->dpres.p, long(c->nint), c->stream);
+                   c->pres.p, c->dp[c->cur].p, long(c->nint), c->stream);
+  c->dp_valid[c->cur] = true;
   const double* q[NVAR];
   for (int v = 0; v < NVAR; ++v) q[v] = c->prog[c->cur][v].p;
   launch_monitor(q, c->dens_hyd.p, c->pres.p, c->rtot.p, c->moist, c->w3.p, c->Jac.p, c->gsqrt.p, c->terrain, c->zlev.p, c->c,

@@ -47,6 +47,9 @@ struct StageParams {
   const double* q0[NVAR];
   double* vt[NVAR];
   double* tend_out[NVAR];  // when non-null: write the tendency instead of the updated state
+  const double* dpin;      // DPRES of the stage-input state (interior + halo)
+  double* dpout;           // DPRES of the stage-output state (interior), written by the kernel
+  const ElemTables* tab;   // device copy of the operator tables
   const double *dens_hyd, *pres_hyd, *therm_hyd, *rtot, *cvtot, *cptot;
   const double *gsqrt, *g13, *g23, *gsqrtH;
   const double *dphydx, *dphydy, *coriolis;
@@ -54,7 +57,7 @@ struct StageParams {
   const double* fscale;  // [6][Ne]
   const int* vmapP;      // (NfpTot,Ne) 0-based
   const int* emap2d;     // (Ne) 0-based
-  double *pres_out, *dpres_out;
+  double* pres_out;
   RKStage rk;
   PhysConst c;
   int Ne, Ne2D;
@@ -63,6 +66,7 @@ struct StageParams {
 
 struct HaloParams {
   double* q[NVAR];
+  double* dp;            // DPRES travels with the prognostic variables
   const int* src;        // (Nhalo) interior flat index feeding each halo slot (same-rank faces), -1 = remote
   const int* vmapB;      // (Nhalo) own face node of each halo slot
   const double *gsqrt, *g13, *g23, *gsqrtH;
@@ -73,7 +77,7 @@ struct HaloParams {
 };
 
 void upload_tables(const ElemTables& t, cudaStream_t s);
-void launch_heve_stage(const StageParams& p, int np, bool terrain, bool moist, cudaStream_t s);
+void launch_stage(const StageParams& p, int np, bool terrain, bool moist, bool hevi, cudaStream_t s);
 void launch_halo_fill(const HaloParams& p, cudaStream_t s);
 void launch_calc_pres(const double* drhot, const double* pres_hyd, const double* therm_hyd, const double* rtot,
                       const double* cvtot, const double* cptot, bool moist, PhysConst c, double* pres, double* dpres,

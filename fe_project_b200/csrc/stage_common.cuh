@@ -1,0 +1,104 @@
+// Device helpers shared by the stage kernels: equation of state, TMA bulk copy + mbarrier, Rusanov flux.
+#pragma once
+#include <cstdint>
+
+#include "fedg_internal.h"
+
+namespace fedg {
+
+// PRES = P00 * (Rtot/P00 * RHOT)^(CPtot/CVtot)   (nonhydro3d_common.F90:467-474)
+__device__ __forceinline__ double eos_pres(double R, double rP0, double rhot, double cpovcv, double P00) {
+  return P00 * pow(R * rP0 * rhot, cpovcv);
+}
+
+// ---- TMA bulk copy + mbarrier (PTX ISA: cp.async.bulk, mbarrier)
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done = 0;
+  while (!done) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  }
+}
+
+// One side of a face node: Gsqrt-weighted state of rhot_heve_numflux.F90:1030-1069.
+struct FaceSide {
+  double gDD, gMX, gMY, gMZ, gDR, gDens, gRhot, Gs, RGv, G13, G23, Phyd, dp, Vel, Velh;
+};
+
+template <bool TERRAIN>
+__device__ __forceinline__ void make_side(FaceSide& s, double dd, double mx, double my, double mz, double dr, double dh, double ph,
+                                          double th, double dp, double Gs, double G13, double G23) {
+  s.Gs = Gs; s.RGv = TERRAIN ? 1.0 / Gs : 1.0; s.G13 = G13; s.G23 = G23;
+  s.gDD = Gs * dd; s.gMX = Gs * mx; s.gMY = Gs * my; s.gMZ = Gs * mz; s.gDR = Gs * dr;
+  s.gDens = s.gDD + Gs * dh;
+  s.gRhot = Gs * th + s.gDR;
+  s.Phyd = ph; s.dp = dp;
+}
+
+// contravariant normal velocity; Velh = horizontal part only (HEVI mass / theta fluxes)
+template <int AX, bool TERRAIN>
+__device__ __forceinline__ void face_velocity(FaceSide& s, double sgn) {
+  if (AX == 0) { s.Velh = (s.gMX * sgn) / s.gDens; s.Vel = s.Velh; }
+  else if (AX == 1) { s.Velh = (s.gMY * sgn) / s.gDens; s.Vel = s.Velh; }
+  else {
+    double w = TERRAIN ? (s.gMZ * s.RGv + s.G13 * s.gMX + s.G23 * s.gMY) : s.gMZ;
+    s.Velh = 0.0;
+    s.Vel = s.Velh + (w * sgn) / s.gDens;
+  }
+}
+
+// Rusanov flux jump of the five variables at one face node.
+//   HEVE: rhot_heve_numflux.F90:1071-1134.   HEVI: rhot_hevi_numflux.F90:363-411 (alpha *= 1 - nz^2; mass and
+//   theta fluxes advect with the horizontal velocity only; no vertical pressure term in MOMZ).
+template <int AX, bool TERRAIN, bool HEVI>
+__device__ __forceinline__ void rusanov(FaceSide& M, FaceSide& Q, double sgn, double gamm, double hf, double* out5) {
+  face_velocity<AX, TERRAIN>(M, sgn);
+  face_velocity<AX, TERRAIN>(Q, sgn);
+  double alpha;
+  if (HEVI) {
+    if (AX == 2) alpha = 0.0;
+    else alpha = fmax(sqrt(gamm * (M.Phyd + M.dp) * M.Gs / M.gDens) + fabs(M.Vel), sqrt(gamm * (Q.Phyd + Q.dp) * Q.Gs / Q.gDens) + fabs(Q.Vel));
+  } else {
+    double GnnM = 1.0, GnnP = 1.0;
+    if (AX == 2 && TERRAIN) {
+      GnnM = M.RGv * M.RGv + M.G13 * M.G13 + M.G23 * M.G23;
+      GnnP = Q.RGv * Q.RGv + Q.G13 * Q.G13 + Q.G23 * Q.G23;
+    }
+    alpha = fmax(sqrt(GnnM * gamm * (M.Phyd + M.dp) * M.Gs / M.gDens) + fabs(M.Vel),
+                 sqrt(GnnP * gamm * (Q.Phyd + Q.dp) * Q.Gs / Q.gDens) + fabs(Q.Vel));
+  }
+  const double vM = HEVI ? M.Velh : M.Vel, vQ = HEVI ? Q.Velh : Q.Vel;
+  out5[V_DDENS] = hf * (Q.gDens * vQ - M.gDens * vM - alpha * (Q.gDD - M.gDD));
+  out5[V_DRHOT] = hf * (Q.gRhot * vQ - M.gRhot * vM - alpha * (Q.gDR - M.gDR));
+  const double t3 = Q.Gs * Q.dp, t4 = M.Gs * M.dp;
+  double pz = 0.0, px = 0.0, py = 0.0;
+  if (AX == 2) {
+    if (!HEVI) pz = (t3 * Q.RGv - t4 * M.RGv) * sgn;
+    if (TERRAIN) { px = (Q.G13 * sgn) * t3 - (M.G13 * sgn) * t4; py = (Q.G23 * sgn) * t3 - (M.G23 * sgn) * t4; }
+  } else if (AX == 0) {
+    px = sgn * t3 - sgn * t4;
+  } else {
+    py = sgn * t3 - sgn * t4;
+  }
+  out5[V_MOMZ] = hf * (Q.gMZ * Q.Vel - M.gMZ * M.Vel + pz - alpha * (Q.gMZ - M.gMZ));
+  out5[V_MOMX] = hf * (Q.gMX * Q.Vel - M.gMX * M.Vel + px - alpha * (Q.gMX - M.gMX));
+  out5[V_MOMY] = hf * (Q.gMY * Q.Vel - M.gMY * M.Vel + py - alpha * (Q.gMY - M.gMY));
+}
+
+}  // namespace fedg

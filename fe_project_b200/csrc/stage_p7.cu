@@ -1,0 +1,374 @@
+// Fused explicit stage kernel for p = 7 elements (8x8x8 nodes), FP64 tensor-core contractions (sm_100a).
+//
+// Why tensor cores here: with one thread per node and the three 8-term contractions read as rows from shared
+// memory (stage_kernel<8,...> in heve_stage.cu) ncu shows the shared-memory data pipe as the binding unit
+// (l1tex__data_pipe_lsu_wavefronts 80 %, profiles/r01_v2_*): every node re-reads 3 x 64 B of flux rows plus 64 B of
+// D rows per variable.  mma.sync.m8n8k4.f64 (SASS DMMA.8x8x4, measured 37.1 TFLOP/s vs 34.1 for DFMA) shares the
+// operands inside the warp instead: each flux value is read from shared memory once per direction.
+//
+// Mapping (block = 256 threads = 8 warps, one element):  g = lane/4, t = lane%4
+//   warp w owns the plane k = w; lane (g,t) owns the two nodes (i = 2t, 2t+1 ; j = g ; k = w), i.e. the C fragment
+//   of the 8x8 tile  out^T[j][i]  of that plane.  With this orientation
+//     x-derivative   out^T = Fx^T * D^T      (A = data, B = D[i=g][l=t]  constant fragment)
+//     y-derivative   out^T += D * Fy^T       (A = D[j=g][l=t] constant,  B = data)
+//   accumulate in the same registers, and both data fragments come from the warp's own plane (no block barrier).
+//   The z-derivative uses tiles at fixed j = w:  out_j[k][i] = D * Fz_j  (A = D[k=g][l=t]); its C fragment belongs
+//   to other warps' nodes, so z-results cross through shared memory once (two block barriers per stage, batched
+//   over the five variables).  The lift is three more k=4 steps with (lift weights x face jumps) as operands.
+//   E11/E22/E33 (constant per element on MeshCubeDom3D) are folded into the constant fragments.
+#include <cstdint>
+#include <cstdlib>
+
+#include "fedg_internal.h"
+#include "stage_common.cuh"
+
+namespace fedg {
+
+namespace p7 {
+constexpr int NP = 8, N2 = 64, N3 = 512, NFT = 384;
+constexpr int KS_FZ = 68;   // k-stride of the z-staging layout  [k][j][i]: conflict-free B-fragment reads
+constexpr int KS_Z = 72;    // k-stride of the z-result layout   [k][j][i]: conflict-free 128-bit writes and reads
+constexpr int PLS = 12;     // row stride of the per-warp plane  [j][i]
+constexpr int TAB = 4 * 64 + 16;                       // D, Fh, Fv, VP, Lw
+constexpr int STASH = 9 * N3;
+constexpr int ZREG = NVAR * NP * KS_FZ + NVAR * NP * KS_Z;   // sFz + sZ alias the stash
+constexpr int REGA = STASH > ZREG ? STASH : ZREG;
+constexpr int PLANES = 8 * 2 * NP * PLS;
+constexpr int SM_DOUBLES = TAB + REGA + NVAR * NFT + PLANES;
+constexpr size_t SMEM_BYTES = size_t(SM_DOUBLES) * sizeof(double) + 16;
+}  // namespace p7
+
+__device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+template <bool TERRAIN, bool MOIST, bool HEVI>
+__global__ void __launch_bounds__(256, 3) stage_p7_kernel(const __grid_constant__ StageParams P) {
+  using namespace p7;
+  const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const int ke = blockIdx.x;
+  const size_t eb = size_t(ke) * N3;
+  const int n0 = 2 * t + 8 * g + 64 * w;     // own nodes n0, n0 + 1
+  const size_t gn = eb + n0;
+
+  extern __shared__ __align__(16) double smem[];
+  double* sTabD = smem;
+  double* sTabFh = smem + 64;
+  double* sTabFv = smem + 128;
+  double* sTabVP = smem + 192;
+  double* sTabLw = smem + 256;
+  double* sStash = smem + TAB;               // [9][512], dead after the face phase
+  double* sFz = smem + TAB;                  // [5][8*KS_FZ]   aliases the stash
+  double* sZ = sFz + NVAR * NP * KS_FZ;      // [5][8*KS_Z]
+  double* sDel = smem + TAB + REGA;          // [5][384]
+  double* sPx = sDel + NVAR * NFT + size_t(w) * 2 * NP * PLS;   // this warp's planes [j][i], row stride PLS
+  double* sPy = sPx + NP * PLS;
+  uint64_t* sBar = reinterpret_cast<uint64_t*>(smem + SM_DOUBLES);
+
+  // ---- phase 0: TMA bulk loads of the element's nine input fields
+  if (tid == 0) {
+    mbar_init(sBar, 1);
+    constexpr uint32_t BYTES = N3 * sizeof(double);
+    mbar_expect_tx(sBar, 9 * BYTES);
+    tma_load_1d(sStash + 0 * N3, P.qin[V_DDENS] + eb, BYTES, sBar);
+    tma_load_1d(sStash + 1 * N3, P.qin[V_MOMX] + eb, BYTES, sBar);
+    tma_load_1d(sStash + 2 * N3, P.qin[V_MOMY] + eb, BYTES, sBar);
+    tma_load_1d(sStash + 3 * N3, P.qin[V_MOMZ] + eb, BYTES, sBar);
+    tma_load_1d(sStash + 4 * N3, P.qin[V_DRHOT] + eb, BYTES, sBar);
+    tma_load_1d(sStash + 5 * N3, P.dens_hyd + eb, BYTES, sBar);
+    tma_load_1d(sStash + 6 * N3, P.pres_hyd + eb, BYTES, sBar);
+    tma_load_1d(sStash + 7 * N3, P.therm_hyd + eb, BYTES, sBar);
+    tma_load_1d(sStash + 8 * N3, P.dpin + eb, BYTES, sBar);
+  }
+  for (int m = tid; m < TAB; m += 256) {
+    double v;
+    if (m < 64) v = P.tab->D[m];
+    else if (m < 128) v = P.tab->Fh[m - 64];
+    else if (m < 192) v = P.tab->Fv[m - 128];
+    else if (m < 256) v = P.tab->VP[m - 192];
+    else v = P.tab->Lw[m - 256];
+    smem[m] = v;
+  }
+  const double E11 = P.escale[ke], E22 = P.escale[P.Ne + ke], E33 = P.escale[2 * size_t(P.Ne) + ke];
+  const int ke2d = P.emap2d[ke];
+  double2 cor = make_double2(0.0, 0.0), Gn = make_double2(1.0, 1.0), G13n = make_double2(0.0, 0.0), G23n = make_double2(0.0, 0.0),
+          gH = make_double2(1.0, 1.0);
+  if (P.has_cor) cor = *reinterpret_cast<const double2*>(P.coriolis + size_t(ke2d) * N2 + 2 * t + 8 * g);
+  if (TERRAIN) {
+    Gn = *reinterpret_cast<const double2*>(P.gsqrt + gn);
+    G13n = *reinterpret_cast<const double2*>(P.g13 + gn);
+    G23n = *reinterpret_cast<const double2*>(P.g23 + gn);
+    gH = *reinterpret_cast<const double2*>(P.gsqrtH + size_t(ke2d) * N2 + 2 * t + 8 * g);
+  }
+  __syncthreads();   // barrier init + tables visible
+  mbar_wait(sBar, 0);
+
+  // ---- phase 1: own-node values (two adjacent nodes per lane: 128-bit shared loads)
+  const double2 dd = *reinterpret_cast<const double2*>(sStash + 0 * N3 + n0);
+  const double2 mx = *reinterpret_cast<const double2*>(sStash + 1 * N3 + n0);
+  const double2 my = *reinterpret_cast<const double2*>(sStash + 2 * N3 + n0);
+  const double2 mz = *reinterpret_cast<const double2*>(sStash + 3 * N3 + n0);
+  const double2 dr = *reinterpret_cast<const double2*>(sStash + 4 * N3 + n0);
+  const double2 dp = *reinterpret_cast<const double2*>(sStash + 8 * N3 + n0);
+  double2 rdens, pt;
+  {
+    const double2 dh = *reinterpret_cast<const double2*>(sStash + 5 * N3 + n0);
+    const double2 th = *reinterpret_cast<const double2*>(sStash + 7 * N3 + n0);
+    rdens.x = 1.0 / (dd.x + dh.x); rdens.y = 1.0 / (dd.y + dh.y);
+    pt.x = (th.x + dr.x) * rdens.x; pt.y = (th.y + dr.y) * rdens.y;
+  }
+  double2 drho = make_double2(0.0, 0.0);
+  if (!HEVI) {  // VFilterPM1 of DDENS along the column (rhot_heve.F90:442-443), l ascending
+    const double* col = sStash + (n0 - 64 * w);
+#pragma unroll
+    for (int l = 0; l < NP; ++l) {
+      const double2 c = *reinterpret_cast<const double2*>(col + 64 * l);
+      const double vp = sTabVP[w * NP + l];
+      if (l == 0) { drho.x = c.x * vp; drho.y = c.y * vp; }
+      else { drho.x += c.x * vp; drho.y += c.y * vp; }
+    }
+  }
+
+  // ---- phase 2: face flux jumps (384 face nodes over 256 threads)
+  {
+    const double gamm = P.c.gamm;
+    const size_t fb = size_t(ke) * NFT;
+    for (int m = tid; m < NFT; m += 256) {
+      const int f = m >> 6, fp = m & 63, a = fp & 7, b = fp >> 3;
+      int nloc;
+      switch (f) {
+        case 0: nloc = a + b * N2; break;
+        case 1: nloc = (NP - 1) + a * NP + b * N2; break;
+        case 2: nloc = a + (NP - 1) * NP + b * N2; break;
+        case 3: nloc = a * NP + b * N2; break;
+        case 4: nloc = fp; break;
+        default: nloc = fp + (NP - 1) * N2; break;
+      }
+      const size_t iP = size_t(P.vmapP[fb + m]);
+      double GsM = 1.0, G13M = 0.0, G23M = 0.0, GsP = 1.0, G13P = 0.0, G23P = 0.0;
+      if (TERRAIN) {
+        GsM = P.gsqrt[eb + nloc]; G13M = P.g13[eb + nloc]; G23M = P.g23[eb + nloc];
+        GsP = P.gsqrt[iP]; G13P = P.g13[iP]; G23P = P.g23[iP];
+      }
+      FaceSide M, Q;
+      make_side<TERRAIN>(M, sStash[0 * N3 + nloc], sStash[1 * N3 + nloc], sStash[2 * N3 + nloc], sStash[3 * N3 + nloc],
+                         sStash[4 * N3 + nloc], sStash[5 * N3 + nloc], sStash[6 * N3 + nloc], sStash[7 * N3 + nloc],
+                         sStash[8 * N3 + nloc], GsM, G13M, G23M);
+      make_side<TERRAIN>(Q, P.qin[V_DDENS][iP], P.qin[V_MOMX][iP], P.qin[V_MOMY][iP], P.qin[V_MOMZ][iP], P.qin[V_DRHOT][iP],
+                         P.dens_hyd[iP], P.pres_hyd[iP], P.therm_hyd[iP], P.dpin[iP], GsP, G13P, G23P);
+      const double hf = P.fscale[size_t(f) * P.Ne + ke] * 0.5;
+      double o5[NVAR];
+      switch (f) {
+        case 0: rusanov<1, TERRAIN, HEVI>(M, Q, -1.0, gamm, hf, o5); break;
+        case 1: rusanov<0, TERRAIN, HEVI>(M, Q, 1.0, gamm, hf, o5); break;
+        case 2: rusanov<1, TERRAIN, HEVI>(M, Q, 1.0, gamm, hf, o5); break;
+        case 3: rusanov<0, TERRAIN, HEVI>(M, Q, -1.0, gamm, hf, o5); break;
+        case 4: rusanov<2, TERRAIN, HEVI>(M, Q, -1.0, gamm, hf, o5); break;
+        default: rusanov<2, TERRAIN, HEVI>(M, Q, 1.0, gamm, hf, o5); break;
+      }
+#pragma unroll
+      for (int v = 0; v < NVAR; ++v) sDel[v * NFT + m] = o5[v];
+    }
+  }
+
+  // per-node flux building blocks
+  double2 RGv = make_double2(1.0, 1.0), RGs = make_double2(1.0, 1.0);
+  if (TERRAIN) { RGv.x = 1.0 / (Gn.x / gH.x); RGv.y = 1.0 / (Gn.y / gH.y); RGs.x = 1.0 / Gn.x; RGs.y = 1.0 / Gn.y; }
+  const double2 fx0 = make_double2(Gn.x * mx.x, Gn.y * mx.y), fy0 = make_double2(Gn.x * my.x, Gn.y * my.y);
+  double2 fz0 = mz;
+  if (TERRAIN) {
+    fz0.x = Gn.x * (mz.x * RGv.x + G13n.x * mx.x + G23n.x * my.x);
+    fz0.y = Gn.y * (mz.y * RGv.y + G13n.y * mx.y + G23n.y * my.y);
+  }
+  const double2 GP = make_double2(Gn.x * dp.x, Gn.y * dp.y);
+  const double2 uu = make_double2(mx.x * rdens.x, mx.y * rdens.y), vv = make_double2(my.x * rdens.x, my.y * rdens.y),
+                ww = make_double2(mz.x * rdens.x, mz.y * rdens.y);
+  __syncthreads();   // stash dead (sFz / sZ alias it), sDel complete
+
+  // ---- phase 3: stage the vertical fluxes of all variables   sFz[v][k*KS_FZ + j*8 + i]
+  constexpr int order[NVAR] = {V_DDENS, V_DRHOT, V_MOMZ, V_MOMX, V_MOMY};
+  const int ownFz = 2 * t + 8 * g + KS_FZ * w;
+#pragma unroll
+  for (int iv = 0; iv < NVAR; ++iv) {
+    const int v = order[iv];
+    if (HEVI && (v == V_DDENS || v == V_DRHOT)) continue;   // vertical mass / theta fluxes are implicit (rhot_hevi.F90:440-452)
+    double2 Fz;
+    if (v == V_DDENS) Fz = fz0;
+    else if (v == V_DRHOT) Fz = make_double2(fz0.x * pt.x, fz0.y * pt.y);
+    else if (v == V_MOMZ) Fz = HEVI ? make_double2(fz0.x * ww.x, fz0.y * ww.y) : make_double2(fz0.x * ww.x + GP.x * RGv.x, fz0.y * ww.y + GP.y * RGv.y);
+    else if (v == V_MOMX) Fz = TERRAIN ? make_double2(fz0.x * uu.x + GP.x * G13n.x, fz0.y * uu.y + GP.y * G13n.y) : make_double2(fz0.x * uu.x, fz0.y * uu.y);
+    else Fz = TERRAIN ? make_double2(fz0.x * vv.x + GP.x * G23n.x, fz0.y * vv.y + GP.y * G23n.y) : make_double2(fz0.x * vv.x, fz0.y * vv.y);
+    *reinterpret_cast<double2*>(sFz + v * NP * KS_FZ + ownFz) = Fz;
+  }
+  // constant fragments: D[g][t], D[g][t+4] scaled by the element metric, lift weights Lw[g][s=t] (t < 2)
+  const double Dg0 = sTabD[g * NP + t], Dg1 = sTabD[g * NP + t + 4];
+  const double lwA = (t < 2) ? sTabLw[g * 2 + t] : 0.0;
+  __syncthreads();
+
+  // ---- phase 4: z-derivative + z-face lift, tile at fixed j = w:  out_j[k][i] = sum_l (E33 D)[k][l] Fz_j[l][i]
+  {
+    const double a0 = E33 * Dg0, a1 = E33 * Dg1;
+#pragma unroll
+    for (int iv = 0; iv < NVAR; ++iv) {
+      const int v = order[iv];
+      if (HEVI && (v == V_DDENS || v == V_DRHOT)) continue;
+      const double* src = sFz + v * NP * KS_FZ + g + 8 * w;
+      const double b0 = src[KS_FZ * t], b1 = src[KS_FZ * (t + 4)];
+      const double bl = (t < 2) ? sDel[v * NFT + (4 + t) * N2 + g + 8 * w] : 0.0;
+      double c0 = 0.0, c1 = 0.0;
+      dmma(c0, c1, a0, b0);
+      dmma(c0, c1, a1, b1);
+      dmma(c0, c1, lwA, bl);
+      *reinterpret_cast<double2*>(sZ + v * NP * KS_Z + 2 * t + 8 * w + KS_Z * g) = make_double2(c0, c1);
+    }
+  }
+  __syncthreads();
+
+  // ---- phase 5: per variable x/y-derivative + lateral lift on the own plane, tendency, RK update, filter passes x/y
+  const bool tend_mode = P.tend_out[0] != nullptr;
+  const double bx0 = E11 * Dg0, bx1 = E11 * Dg1, ay0 = E22 * Dg0, ay1 = E22 * Dg1;
+  const int ownP = PLS * g + 2 * t, ownZ = 2 * t + 8 * g + KS_Z * w;
+  double2 qnew[NVAR];
+#pragma unroll
+  for (int iv = 0; iv < NVAR; ++iv) {
+    const int v = order[iv];
+    double2 Fx, Fy, q;
+    if (v == V_DDENS) { Fx = fx0; Fy = fy0; q = dd; }
+    else if (v == V_DRHOT) { Fx = make_double2(fx0.x * pt.x, fx0.y * pt.y); Fy = make_double2(fy0.x * pt.x, fy0.y * pt.y); q = dr; }
+    else if (v == V_MOMZ) { Fx = make_double2(fx0.x * ww.x, fx0.y * ww.y); Fy = make_double2(fy0.x * ww.x, fy0.y * ww.y); q = mz; }
+    else if (v == V_MOMX) { Fx = make_double2(fx0.x * uu.x + GP.x, fx0.y * uu.y + GP.y); Fy = make_double2(fy0.x * uu.x, fy0.y * uu.y); q = mx; }
+    else { Fx = make_double2(fx0.x * vv.x, fx0.y * vv.y); Fy = make_double2(fy0.x * vv.x + GP.x, fy0.y * vv.y + GP.y); q = my; }
+    __syncwarp();   // previous variable's fragment reads of the planes are done
+    *reinterpret_cast<double2*>(sPx + ownP) = Fx;
+    *reinterpret_cast<double2*>(sPy + ownP) = Fy;
+    double c0 = 0.0, c1 = 0.0;
+    if (!(HEVI && (v == V_DDENS || v == V_DRHOT))) {
+      const double2 z = *reinterpret_cast<const double2*>(sZ + v * NP * KS_Z + ownZ);
+      c0 = z.x; c1 = z.y;
+    }
+    __syncwarp();
+    {
+      // x: out^T[j][i] += Fx^T[j][l] * (E11 D)[i][l]      A = Fx(i = t | t+4, j = g),  B = const
+      const double ax0 = sPx[PLS * g + t], ax1 = sPx[PLS * g + t + 4];
+      dmma(c0, c1, ax0, bx0);
+      dmma(c0, c1, ax1, bx1);
+      // y: out^T[j][i] += (E22 D)[j][l] * Fy^T[l][i]      A = const,  B = Fy(i = g, j = t | t+4)
+      const double by0 = sPy[PLS * t + g], by1 = sPy[PLS * (t + 4) + g];
+      dmma(c0, c1, ay0, by0);
+      dmma(c0, c1, ay1, by1);
+      // lift, x faces (3: x-, 1: x+): A = jump(j = g, k = w) for s = t < 2, B = Lw[i = g][s]
+      const double axl = (t < 2) ? sDel[v * NFT + (t == 0 ? 3 : 1) * N2 + g + 8 * w] : 0.0;
+      dmma(c0, c1, axl, lwA);
+      // lift, y faces (0: y-, 2: y+): A = Lw[j = g][s], B = jump(i = g, k = w)
+      const double byl = (t < 2) ? sDel[v * NFT + (t == 0 ? 0 : 2) * N2 + g + 8 * w] : 0.0;
+      dmma(c0, c1, lwA, byl);
+    }
+    const double2 div = make_double2(c0 * RGs.x, c1 * RGs.y);
+    double2 tend;
+    if (v == V_MOMZ) tend = HEVI ? make_double2(-div.x, -div.y) : make_double2(-div.x - P.c.GRAV * drho.x, -div.y - P.c.GRAV * drho.y);
+    else if (v == V_MOMX) {
+      double2 ph = make_double2(0.0, 0.0);
+      if (P.has_phyd) ph = *reinterpret_cast<const double2*>(P.dphydx + gn);
+      tend = make_double2((-ph.x + cor.x * my.x) - div.x, (-ph.y + cor.y * my.y) - div.y);
+    } else if (v == V_MOMY) {
+      double2 ph = make_double2(0.0, 0.0);
+      if (P.has_phyd) ph = *reinterpret_cast<const double2*>(P.dphydy + gn);
+      tend = make_double2((-ph.x - cor.x * mx.x) - div.x, (-ph.y - cor.y * mx.y) - div.y);
+    } else tend = make_double2(-div.x, -div.y);
+
+    if (tend_mode) {
+      *reinterpret_cast<double2*>(P.tend_out[v] + gn) = tend;
+      continue;
+    }
+    // RK stage update (scale_timeint_rk.F90:1182-1266 low storage, :2201-2355 general with one buffer)
+    double2 base = make_double2(0.0, 0.0);
+    if (P.rk.use_q0) { const double2 a = *reinterpret_cast<const double2*>(P.q0[v] + gn); base = make_double2(P.rk.c_q0 * a.x, P.rk.c_q0 * a.y); }
+    if (P.rk.add_vt) base = *reinterpret_cast<const double2*>(P.vt[v] + gn);
+    double2 r = make_double2(base.x + P.rk.c_q * q.x + P.rk.c_k * tend.x, base.y + P.rk.c_q * q.y + P.rk.c_k * tend.y);
+    if (P.rk.vt_update) {
+      double2 vb;
+      if (P.rk.vt_init) vb = make_double2(P.rk.vt_init_q * q.x, P.rk.vt_init_q * q.y);
+      else vb = *reinterpret_cast<const double2*>(P.vt[v] + gn);
+      *reinterpret_cast<double2*>(P.vt[v] + gn) =
+          make_double2(vb.x + P.rk.vt_q * q.x + P.rk.vt_k * tend.x, vb.y + P.rk.vt_q * q.y + P.rk.vt_k * tend.y);
+    }
+    if (P.do_filter) {
+      // modal filter of the Gsqrt-weighted variable (dyn_dgm_modalfilter.F90:49-130): x and y passes on the own plane
+      __syncwarp();
+      *reinterpret_cast<double2*>(sPx + ownP) = make_double2(Gn.x * r.x, Gn.y * r.y);
+      __syncwarp();
+      double f0 = 0.0, f1 = 0.0;
+      dmma(f0, f1, sPx[PLS * g + t], sTabFh[g * NP + t]);            // out^T[j][i] = g^T[j][l] Fh[i][l]
+      dmma(f0, f1, sPx[PLS * g + t + 4], sTabFh[g * NP + t + 4]);
+      *reinterpret_cast<double2*>(sPy + ownP) = make_double2(f0, f1);
+      __syncwarp();
+      double h0 = 0.0, h1 = 0.0;
+      dmma(h0, h1, sTabFh[g * NP + t], sPy[PLS * t + g]);            // out^T[j][i] = Fh[j][l] r1^T[l][i]
+      dmma(h0, h1, sTabFh[g * NP + t + 4], sPy[PLS * (t + 4) + g]);
+      // stage for the z pass (sFz[v] is free: phase 4 has completed for every warp)
+      *reinterpret_cast<double2*>(sFz + v * NP * KS_FZ + ownFz) = make_double2(h0, h1);
+    }
+    qnew[iv] = r;
+  }
+
+  if (tend_mode) return;
+
+  if (P.do_filter) {
+    __syncthreads();   // all planes staged; every warp has finished reading sZ
+    const double a0 = sTabFv[g * NP + t], a1 = sTabFv[g * NP + t + 4];
+#pragma unroll
+    for (int v = 0; v < NVAR; ++v) {
+      const double* src = sFz + v * NP * KS_FZ + g + 8 * w;
+      double c0 = 0.0, c1 = 0.0;
+      dmma(c0, c1, a0, src[KS_FZ * t]);                              // out_j[k][i] = Fv[k][l] r2_j[l][i]
+      dmma(c0, c1, a1, src[KS_FZ * (t + 4)]);
+      *reinterpret_cast<double2*>(sZ + v * NP * KS_Z + 2 * t + 8 * w + KS_Z * g) = make_double2(c0, c1);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int iv = 0; iv < NVAR; ++iv) {
+      const double2 z = *reinterpret_cast<const double2*>(sZ + order[iv] * NP * KS_Z + ownZ);
+      qnew[iv] = make_double2(z.x * (1.0 / Gn.x), z.y * (1.0 / Gn.y));
+    }
+  }
+#pragma unroll
+  for (int iv = 0; iv < NVAR; ++iv) *reinterpret_cast<double2*>(P.qout[order[iv]] + gn) = qnew[iv];
+
+  {  // pressure of the new state: next stage's DPRES; PRES diagnostic at the end of Update (driver:954-959)
+    const double2 ph = *reinterpret_cast<const double2*>(P.pres_hyd + gn), th = *reinterpret_cast<const double2*>(P.therm_hyd + gn);
+    double2 R = make_double2(P.c.Rdry, P.c.Rdry), e = make_double2(P.c.CPovCV, P.c.CPovCV);
+    if (MOIST) {
+      R = *reinterpret_cast<const double2*>(P.rtot + gn);
+      const double2 cp = *reinterpret_cast<const double2*>(P.cptot + gn), cv = *reinterpret_cast<const double2*>(P.cvtot + gn);
+      e = make_double2(cp.x / cv.x, cp.y / cv.y);
+    }
+    const double2 drn = qnew[1];   // order[1] == V_DRHOT
+    const double p0 = eos_pres(R.x, P.c.rP0, th.x + drn.x, e.x, P.c.PRES00), p1 = eos_pres(R.y, P.c.rP0, th.y + drn.y, e.y, P.c.PRES00);
+    *reinterpret_cast<double2*>(P.dpout + gn) = make_double2(p0 - ph.x, p1 - ph.y);
+    if (P.write_pres) *reinterpret_cast<double2*>(P.pres_out + gn) = make_double2(p0, p1);
+  }
+}
+
+void launch_stage_p7(const StageParams& p, bool terrain, bool moist, bool hevi, cudaStream_t s) {
+  const size_t shmem = p7::SMEM_BYTES;
+  dim3 grid(p.Ne), block(256);
+#define FEDG_LAUNCH(T, M, H)                                                                                  \
+  do {                                                                                                        \
+    static bool attr_set = false;                                                                             \
+    if (!attr_set) {                                                                                          \
+      cudaFuncSetAttribute(stage_p7_kernel<T, M, H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem); \
+      attr_set = true;                                                                                        \
+    }                                                                                                         \
+    stage_p7_kernel<T, M, H><<<grid, block, shmem, s>>>(p);                                                   \
+  } while (0)
+  if (hevi) {
+    if (terrain) { if (moist) FEDG_LAUNCH(true, true, true); else FEDG_LAUNCH(true, false, true); }
+    else { if (moist) FEDG_LAUNCH(false, true, true); else FEDG_LAUNCH(false, false, true); }
+  } else {
+    if (terrain) { if (moist) FEDG_LAUNCH(true, true, false); else FEDG_LAUNCH(true, false, false); }
+    else { if (moist) FEDG_LAUNCH(false, true, false); else FEDG_LAUNCH(false, false, false); }
+  }
+#undef FEDG_LAUNCH
+}
+
+}  // namespace fedg
