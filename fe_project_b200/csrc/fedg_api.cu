@@ -8,6 +8,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <memory>
 #include <string>
 #include <vector>
@@ -476,6 +477,7 @@ void fill_stage_params(fedg_ctx* c, StageParams& P, int in, int out, int q0) {
   P.pres_out = c->pres.p; P.dpin = c->dp[in].p; P.dpout = c->dp[out].p; P.tab = c->d_tab;
   P.c = c->c; P.Ne = c->Ne; P.Ne2D = c->Ne2D;
   P.has_cor = c->has_cor; P.has_phyd = c->has_phyd; P.do_filter = 0; P.write_pres = 0;
+  { static int fp = -1; if (fp < 0) { const char* e = getenv("FEDG_FAST_POW"); fp = (e && e[0] == '1') ? 1 : 0; } P.fast_pow = fp; }
 }
 
 // DPRES of prog[buf] (interior): produced by the stage kernel that wrote prog[buf]; computed here only after the

@@ -61,7 +61,7 @@ struct StageParams {
   RKStage rk;
   PhysConst c;
   int Ne, Ne2D;
-  int has_cor, has_phyd, do_filter, write_pres;
+  int has_cor, has_phyd, do_filter, write_pres, fast_pow;
 };
 
 struct HaloParams {

@@ -25,20 +25,24 @@ __device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t
                "l"(src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(done)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return done != 0;
+}
+// all lanes wait (each observes the phase completion itself: acquire of the async-proxy writes); back off
+// between polls so that waiting warps do not eat issue slots of the other resident blocks
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t done = 0;
-  while (!done) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-  }
+  while (!mbar_try_wait(bar, parity)) __nanosleep(64);
 }
 
 // One side of a face node: Gsqrt-weighted state of rhot_heve_numflux.F90:1030-1069.
 struct FaceSide {
-  double gDD, gMX, gMY, gMZ, gDR, gDens, gRhot, Gs, RGv, G13, G23, Phyd, dp, Vel, Velh;
+  double gDD, gMX, gMY, gMZ, gDR, gDens, rgDens, gRhot, Gs, RGv, G13, G23, Phyd, dp, Vel, Velh;
 };
 
 template <bool TERRAIN>
@@ -47,19 +51,32 @@ __device__ __forceinline__ void make_side(FaceSide& s, double dd, double mx, dou
   s.Gs = Gs; s.RGv = TERRAIN ? 1.0 / Gs : 1.0; s.G13 = G13; s.G23 = G23;
   s.gDD = Gs * dd; s.gMX = Gs * mx; s.gMY = Gs * my; s.gMZ = Gs * mz; s.gDR = Gs * dr;
   s.gDens = s.gDD + Gs * dh;
+  s.rgDens = 1.0 / s.gDens;   // one reciprocal per side instead of the reference's three divisions (<= 1 ulp apart)
   s.gRhot = Gs * th + s.gDR;
   s.Phyd = ph; s.dp = dp;
 }
 
+// raw exterior-side node values gathered from global memory through VMapP
+template <bool TERRAIN>
+struct RawSide {
+  double dd, mx, my, mz, dr, dh, ph, th, dp, Gs, G13, G23;
+  __device__ __forceinline__ void load(const StageParams& P, size_t iP) {
+    dd = P.qin[V_DDENS][iP]; mx = P.qin[V_MOMX][iP]; my = P.qin[V_MOMY][iP]; mz = P.qin[V_MOMZ][iP]; dr = P.qin[V_DRHOT][iP];
+    dh = P.dens_hyd[iP]; ph = P.pres_hyd[iP]; th = P.therm_hyd[iP]; dp = P.dpin[iP];
+    Gs = 1.0; G13 = 0.0; G23 = 0.0;
+    if (TERRAIN) { Gs = P.gsqrt[iP]; G13 = P.g13[iP]; G23 = P.g23[iP]; }
+  }
+};
+
 // contravariant normal velocity; Velh = horizontal part only (HEVI mass / theta fluxes)
 template <int AX, bool TERRAIN>
 __device__ __forceinline__ void face_velocity(FaceSide& s, double sgn) {
-  if (AX == 0) { s.Velh = (s.gMX * sgn) / s.gDens; s.Vel = s.Velh; }
-  else if (AX == 1) { s.Velh = (s.gMY * sgn) / s.gDens; s.Vel = s.Velh; }
+  if (AX == 0) { s.Velh = (s.gMX * sgn) * s.rgDens; s.Vel = s.Velh; }
+  else if (AX == 1) { s.Velh = (s.gMY * sgn) * s.rgDens; s.Vel = s.Velh; }
   else {
     double w = TERRAIN ? (s.gMZ * s.RGv + s.G13 * s.gMX + s.G23 * s.gMY) : s.gMZ;
     s.Velh = 0.0;
-    s.Vel = s.Velh + (w * sgn) / s.gDens;
+    s.Vel = s.Velh + (w * sgn) * s.rgDens;
   }
 }
 
@@ -73,15 +90,15 @@ __device__ __forceinline__ void rusanov(FaceSide& M, FaceSide& Q, double sgn, do
   double alpha;
   if (HEVI) {
     if (AX == 2) alpha = 0.0;
-    else alpha = fmax(sqrt(gamm * (M.Phyd + M.dp) * M.Gs / M.gDens) + fabs(M.Vel), sqrt(gamm * (Q.Phyd + Q.dp) * Q.Gs / Q.gDens) + fabs(Q.Vel));
+    else alpha = fmax(sqrt(gamm * (M.Phyd + M.dp) * M.Gs * M.rgDens) + fabs(M.Vel), sqrt(gamm * (Q.Phyd + Q.dp) * Q.Gs * Q.rgDens) + fabs(Q.Vel));
   } else {
     double GnnM = 1.0, GnnP = 1.0;
     if (AX == 2 && TERRAIN) {
       GnnM = M.RGv * M.RGv + M.G13 * M.G13 + M.G23 * M.G23;
       GnnP = Q.RGv * Q.RGv + Q.G13 * Q.G13 + Q.G23 * Q.G23;
     }
-    alpha = fmax(sqrt(GnnM * gamm * (M.Phyd + M.dp) * M.Gs / M.gDens) + fabs(M.Vel),
-                 sqrt(GnnP * gamm * (Q.Phyd + Q.dp) * Q.Gs / Q.gDens) + fabs(Q.Vel));
+    alpha = fmax(sqrt(GnnM * gamm * (M.Phyd + M.dp) * M.Gs * M.rgDens) + fabs(M.Vel),
+                 sqrt(GnnP * gamm * (Q.Phyd + Q.dp) * Q.Gs * Q.rgDens) + fabs(Q.Vel));
   }
   const double vM = HEVI ? M.Velh : M.Vel, vQ = HEVI ? Q.Velh : Q.Vel;
   out5[V_DDENS] = hf * (Q.gDens * vQ - M.gDens * vM - alpha * (Q.gDD - M.gDD));

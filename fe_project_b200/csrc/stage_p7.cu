@@ -100,6 +100,10 @@ __global__ void __launch_bounds__(256, 3) stage_p7_kernel(const __grid_constant_
     G23n = *reinterpret_cast<const double2*>(P.g23 + gn);
     gH = *reinterpret_cast<const double2*>(P.gsqrtH + size_t(ke2d) * N2 + 2 * t + 8 * g);
   }
+  // exterior-side gather of this thread's first face node, issued while the bulk copies are in flight
+  const size_t fb = size_t(ke) * NFT;
+  RawSide<TERRAIN> pre;
+  pre.load(P, size_t(P.vmapP[fb + tid]));
   __syncthreads();   // barrier init + tables visible
   mbar_wait(sBar, 0);
 
@@ -129,11 +133,13 @@ __global__ void __launch_bounds__(256, 3) stage_p7_kernel(const __grid_constant_
     }
   }
 
-  // ---- phase 2: face flux jumps (384 face nodes over 256 threads)
+  // ---- phase 2: face flux jumps (384 face nodes over 256 threads: one pass for all, a second one for warps 0-3)
   {
     const double gamm = P.c.gamm;
-    const size_t fb = size_t(ke) * NFT;
-    for (int m = tid; m < NFT; m += 256) {
+#pragma unroll
+    for (int pass = 0; pass < 2; ++pass) {
+      const int m = tid + 256 * pass;
+      if (m >= NFT) break;
       const int f = m >> 6, fp = m & 63, a = fp & 7, b = fp >> 3;
       int nloc;
       switch (f) {
@@ -144,18 +150,15 @@ __global__ void __launch_bounds__(256, 3) stage_p7_kernel(const __grid_constant_
         case 4: nloc = fp; break;
         default: nloc = fp + (NP - 1) * N2; break;
       }
-      const size_t iP = size_t(P.vmapP[fb + m]);
-      double GsM = 1.0, G13M = 0.0, G23M = 0.0, GsP = 1.0, G13P = 0.0, G23P = 0.0;
-      if (TERRAIN) {
-        GsM = P.gsqrt[eb + nloc]; G13M = P.g13[eb + nloc]; G23M = P.g23[eb + nloc];
-        GsP = P.gsqrt[iP]; G13P = P.g13[iP]; G23P = P.g23[iP];
-      }
+      RawSide<TERRAIN> ex;
+      if (pass == 0) ex = pre; else ex.load(P, size_t(P.vmapP[fb + m]));
+      double GsM = 1.0, G13M = 0.0, G23M = 0.0;
+      if (TERRAIN) { GsM = P.gsqrt[eb + nloc]; G13M = P.g13[eb + nloc]; G23M = P.g23[eb + nloc]; }
       FaceSide M, Q;
       make_side<TERRAIN>(M, sStash[0 * N3 + nloc], sStash[1 * N3 + nloc], sStash[2 * N3 + nloc], sStash[3 * N3 + nloc],
                          sStash[4 * N3 + nloc], sStash[5 * N3 + nloc], sStash[6 * N3 + nloc], sStash[7 * N3 + nloc],
                          sStash[8 * N3 + nloc], GsM, G13M, G23M);
-      make_side<TERRAIN>(Q, P.qin[V_DDENS][iP], P.qin[V_MOMX][iP], P.qin[V_MOMY][iP], P.qin[V_MOMZ][iP], P.qin[V_DRHOT][iP],
-                         P.dens_hyd[iP], P.pres_hyd[iP], P.therm_hyd[iP], P.dpin[iP], GsP, G13P, G23P);
+      make_side<TERRAIN>(Q, ex.dd, ex.mx, ex.my, ex.mz, ex.dr, ex.dh, ex.ph, ex.th, ex.dp, ex.Gs, ex.G13, ex.G23);
       const double hf = P.fscale[size_t(f) * P.Ne + ke] * 0.5;
       double o5[NVAR];
       switch (f) {
@@ -343,7 +346,14 @@ __global__ void __launch_bounds__(256, 3) stage_p7_kernel(const __grid_constant_
       e = make_double2(cp.x / cv.x, cp.y / cv.y);
     }
     const double2 drn = qnew[1];   // order[1] == V_DRHOT
-    const double p0 = eos_pres(R.x, P.c.rP0, th.x + drn.x, e.x, P.c.PRES00), p1 = eos_pres(R.y, P.c.rP0, th.y + drn.y, e.y, P.c.PRES00);
+    double p0, p1;
+    if (P.fast_pow) {  // tuning experiment (FEDG_FAST_POW=1): exp(e log x) instead of pow(x, e)
+      p0 = P.c.PRES00 * exp(e.x * log(R.x * P.c.rP0 * (th.x + drn.x)));
+      p1 = P.c.PRES00 * exp(e.y * log(R.y * P.c.rP0 * (th.y + drn.y)));
+    } else {
+      p0 = eos_pres(R.x, P.c.rP0, th.x + drn.x, e.x, P.c.PRES00);
+      p1 = eos_pres(R.y, P.c.rP0, th.y + drn.y, e.y, P.c.PRES00);
+    }
     *reinterpret_cast<double2*>(P.dpout + gn) = make_double2(p0 - ph.x, p1 - ph.y);
     if (P.write_pres) *reinterpret_cast<double2*>(P.pres_out + gn) = make_double2(p0, p1);
   }

@@ -20,3 +20,4 @@ if [ -n "$NCU" ]; then
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:stage -s 8 -c 1 -o gpurun_out/stage_full -f \
    python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1; echo "ncu-full rc=$?"
 fi
+if [ -n "$REPORT" ]; then python tools/parity_report.py; FEDG_FAST_POW=1 python tools/parity_report.py; FEDG_FAST_POW=1 run_bench fastpow; fi
