@@ -49,7 +49,7 @@ struct fedg_ctx {
   int Ne = 0, NeA = 0, NeX = 0, NeY = 0, NeZ = 0, Ne2D = 0, Nhalo = 0;
   size_t nint = 0, nall = 0;  // Np*Ne, Np*Ne + Nhalo
   bool terrain = false, moist = false, has_cor = false, has_phyd = false;
-  bool dyn_ready = false, aux_ready = false, zface_contig = false;
+  bool dyn_ready = false, aux_ready = false;
   PhysConst c{};
   double OHM = 0;
   ElemTables tab{};
@@ -235,16 +235,6 @@ int fedg_create(const fedg_mesh_desc* d, fedg_ctx** out) {
       if (vp < 0 || vp >= long(c->nall)) return fail(FEDG_ERR_ARG, "VMapP out of range");
       vP[q] = int(vp);
     }
-  }
-  {  // exterior z-face nodes consecutive and 16-byte aligned -> the stage kernel fetches them with bulk copies
-    bool ok = true;
-    for (int ke = 0; ke < Ne && ok; ++ke)
-      for (int f = 4; f < 6 && ok; ++f) {
-        const int* q = &vP[size_t(ke) * NfpTot + f * Nfp];
-        if (q[0] % 2 != 0) ok = false;
-        for (int p = 1; p < Nfp && ok; ++p) if (q[p] != q[0] + p) ok = false;
-      }
-    c->zface_contig = ok;
   }
   for (int h = 0; h < c->Nhalo; ++h) {
     vB[h] = d->VMapB[h] - 1;
@@ -486,7 +476,7 @@ void fill_stage_params(fedg_ctx* c, StageParams& P, int in, int out, int q0) {
   P.escale = c->escale.p; P.fscale = c->fscale.p; P.vmapP = c->d_vmapP; P.emap2d = c->d_emap2d;
   P.pres_out = c->pres.p; P.dpin = c->dp[in].p; P.dpout = c->dp[out].p; P.tab = c->d_tab;
   P.c = c->c; P.Ne = c->Ne; P.Ne2D = c->Ne2D;
-  P.has_cor = c->has_cor; P.has_phyd = c->has_phyd; P.do_filter = 0; P.write_pres = 0; P.zface_contig = c->zface_contig ? 1 : 0;
+  P.has_cor = c->has_cor; P.has_phyd = c->has_phyd; P.do_filter = 0; P.write_pres = 0;
   { static int fp = -1; if (fp < 0) { const char* e = getenv("FEDG_FAST_POW"); fp = (e && e[0] == '1') ? 1 : 0; } P.fast_pow = fp; }
 }
 

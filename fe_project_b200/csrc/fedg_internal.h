@@ -62,7 +62,6 @@ struct StageParams {
   PhysConst c;
   int Ne, Ne2D;
   int has_cor, has_phyd, do_filter, write_pres, fast_pow;
-  int zface_contig;      // VMapP of every z-face is 64 consecutive indices (16-byte aligned start)
 };
 
 struct HaloParams {

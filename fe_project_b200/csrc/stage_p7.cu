@@ -27,15 +27,14 @@ namespace fedg {
 namespace p7 {
 constexpr int NP = 8, N2 = 64, N3 = 512, NFT = 384;
 constexpr int KS_FZ = 68;   // k-stride of the z-staging layout  [k][j][i]: conflict-free B-fragment reads
-constexpr int KS_Z = 68;    // z-results are written in place (warp w reads and writes only the slab j = w)
-constexpr int NZF = 9 * 2 * N2;   // exterior values of the two z-faces (contiguous through VMapP): TMA-staged
+constexpr int KS_Z = 72;    // k-stride of the z-result layout   [k][j][i]: conflict-free 128-bit writes and reads
 constexpr int PLS = 12;     // row stride of the per-warp plane  [j][i]
 constexpr int TAB = 4 * 64 + 16;                       // D, Fh, Fv, VP, Lw
 constexpr int STASH = 9 * N3;
-constexpr int ZREG = NVAR * NP * KS_FZ;                      // sFz (= sZ, in place) aliases the stash
+constexpr int ZREG = NVAR * NP * KS_FZ + NVAR * NP * KS_Z;   // sFz + sZ alias the stash
 constexpr int REGA = STASH > ZREG ? STASH : ZREG;
 constexpr int PLANES = 8 * 2 * NP * PLS;
-constexpr int SM_DOUBLES = TAB + REGA + NZF + NVAR * NFT + PLANES;
+constexpr int SM_DOUBLES = TAB + REGA + NVAR * NFT + PLANES;
 constexpr size_t SMEM_BYTES = size_t(SM_DOUBLES) * sizeof(double) + 16;
 }  // namespace p7
 
@@ -60,16 +59,15 @@ __global__ void __launch_bounds__(256, 3) stage_p7_kernel(const __grid_constant_
   double* sTabLw = smem + 256;
   double* sStash = smem + TAB;               // [9][512], dead after the face phase
   double* sFz = smem + TAB;                  // [5][8*KS_FZ]   aliases the stash
-  double* sZ = sFz;                          // z-results overwrite the staged fluxes slab by slab
-  double* sZF = smem + TAB + REGA;           // [9][2][64] exterior side of the z-faces
-  double* sDel = sZF + NZF;                  // [5][384]
+  double* sZ = sFz + NVAR * NP * KS_FZ;      // [5][8*KS_Z]
+  double* sDel = smem + TAB + REGA;          // [5][384]
   double* sPx = sDel + NVAR * NFT + size_t(w) * 2 * NP * PLS;   // this warp's planes [j][i], row stride PLS
   double* sPy = sPx + NP * PLS;
   uint64_t* sBar = reinterpret_cast<uint64_t*>(smem + SM_DOUBLES);
 
   // ---- phase 0: TMA bulk loads of the element's nine input fields
   if (tid == 0) {
-    mbar_init(sBar, P.zface_contig ? 2 : 1);
+    mbar_init(sBar, 1);
     constexpr uint32_t BYTES = N3 * sizeof(double);
     mbar_expect_tx(sBar, 9 * BYTES);
     tma_load_1d(sStash + 0 * N3, P.qin[V_DDENS] + eb, BYTES, sBar);
@@ -81,24 +79,6 @@ __global__ void __launch_bounds__(256, 3) stage_p7_kernel(const __grid_constant_
     tma_load_1d(sStash + 6 * N3, P.pres_hyd + eb, BYTES, sBar);
     tma_load_1d(sStash + 7 * N3, P.therm_hyd + eb, BYTES, sBar);
     tma_load_1d(sStash + 8 * N3, P.dpin + eb, BYTES, sBar);
-    if (P.zface_contig) {   // exterior z-face nodes are 64 consecutive values (checked at fedg_create)
-      constexpr uint32_t FB = N2 * sizeof(double);
-      mbar_expect_tx(sBar, 18 * FB);
-      const size_t fbz = size_t(ke) * NFT + 4 * N2;
-#pragma unroll
-      for (int zf = 0; zf < 2; ++zf) {
-        const size_t src = size_t(P.vmapP[fbz + zf * N2]);
-        tma_load_1d(sZF + (0 * 2 + zf) * N2, P.qin[V_DDENS] + src, FB, sBar);
-        tma_load_1d(sZF + (1 * 2 + zf) * N2, P.qin[V_MOMX] + src, FB, sBar);
-        tma_load_1d(sZF + (2 * 2 + zf) * N2, P.qin[V_MOMY] + src, FB, sBar);
-        tma_load_1d(sZF + (3 * 2 + zf) * N2, P.qin[V_MOMZ] + src, FB, sBar);
-        tma_load_1d(sZF + (4 * 2 + zf) * N2, P.qin[V_DRHOT] + src, FB, sBar);
-        tma_load_1d(sZF + (5 * 2 + zf) * N2, P.dens_hyd + src, FB, sBar);
-        tma_load_1d(sZF + (6 * 2 + zf) * N2, P.pres_hyd + src, FB, sBar);
-        tma_load_1d(sZF + (7 * 2 + zf) * N2, P.therm_hyd + src, FB, sBar);
-        tma_load_1d(sZF + (8 * 2 + zf) * N2, P.dpin + src, FB, sBar);
-      }
-    }
   }
   for (int m = tid; m < TAB; m += 256) {
     double v;
@@ -171,13 +151,7 @@ __global__ void __launch_bounds__(256, 3) stage_p7_kernel(const __grid_constant_
         default: nloc = fp + (NP - 1) * N2; break;
       }
       RawSide<TERRAIN> ex;
-      if (pass == 0) ex = pre;
-      else if (P.zface_contig && !TERRAIN) {
-        const double* z = sZF + (f - 4) * N2 + fp;
-        ex.dd = z[0 * 2 * N2]; ex.mx = z[1 * 2 * N2]; ex.my = z[2 * 2 * N2]; ex.mz = z[3 * 2 * N2]; ex.dr = z[4 * 2 * N2];
-        ex.dh = z[5 * 2 * N2]; ex.ph = z[6 * 2 * N2]; ex.th = z[7 * 2 * N2]; ex.dp = z[8 * 2 * N2];
-        ex.Gs = 1.0; ex.G13 = 0.0; ex.G23 = 0.0;
-      } else ex.load(P, size_t(P.vmapP[fb + m]));
+      if (pass == 0) ex = pre; else ex.load(P, size_t(P.vmapP[fb + m]));
       double GsM = 1.0, G13M = 0.0, G23M = 0.0;
       if (TERRAIN) { GsM = P.gsqrt[eb + nloc]; G13M = P.g13[eb + nloc]; G23M = P.g23[eb + nloc]; }
       FaceSide M, Q;
@@ -255,8 +229,6 @@ __global__ void __launch_bounds__(256, 3) stage_p7_kernel(const __grid_constant_
 
   // ---- phase 5: per variable x/y-derivative + lateral lift on the own plane, tendency, RK update, filter passes x/y
   const bool tend_mode = P.tend_out[0] != nullptr;
-  // inputs of the final pressure evaluation: issued now, consumed after the variable loop
-  const double2 ph_e = *reinterpret_cast<const double2*>(P.pres_hyd + gn), th_e = *reinterpret_cast<const double2*>(P.therm_hyd + gn);
   const double bx0 = E11 * Dg0, bx1 = E11 * Dg1, ay0 = E22 * Dg0, ay1 = E22 * Dg1;
   const int ownP = PLS * g + 2 * t, ownZ = 2 * t + 8 * g + KS_Z * w;
   double2 qnew[NVAR];
@@ -281,20 +253,18 @@ __global__ void __launch_bounds__(256, 3) stage_p7_kernel(const __grid_constant_
     {
       // x: out^T[j][i] += Fx^T[j][l] * (E11 D)[i][l]      A = Fx(i = t | t+4, j = g),  B = const
       const double ax0 = sPx[PLS * g + t], ax1 = sPx[PLS * g + t + 4];
+      dmma(c0, c1, ax0, bx0);
+      dmma(c0, c1, ax1, bx1);
       // y: out^T[j][i] += (E22 D)[j][l] * Fy^T[l][i]      A = const,  B = Fy(i = g, j = t | t+4)
       const double by0 = sPy[PLS * t + g], by1 = sPy[PLS * (t + 4) + g];
+      dmma(c0, c1, ay0, by0);
+      dmma(c0, c1, ay1, by1);
       // lift, x faces (3: x-, 1: x+): A = jump(j = g, k = w) for s = t < 2, B = Lw[i = g][s]
       const double axl = (t < 2) ? sDel[v * NFT + (t == 0 ? 3 : 1) * N2 + g + 8 * w] : 0.0;
+      dmma(c0, c1, axl, lwA);
       // lift, y faces (0: y-, 2: y+): A = Lw[j = g][s], B = jump(i = g, k = w)
       const double byl = (t < 2) ? sDel[v * NFT + (t == 0 ? 0 : 2) * N2 + g + 8 * w] : 0.0;
-      double e0 = 0.0, e1 = 0.0;   // second, independent accumulation chain (halves the dependent DMMA depth)
-      dmma(c0, c1, ax0, bx0);
-      dmma(e0, e1, ay0, by0);
-      dmma(c0, c1, ax1, bx1);
-      dmma(e0, e1, ay1, by1);
-      dmma(c0, c1, axl, lwA);
-      dmma(e0, e1, lwA, byl);
-      c0 += e0; c1 += e1;
+      dmma(c0, c1, lwA, byl);
     }
     const double2 div = make_double2(c0 * RGs.x, c1 * RGs.y);
     double2 tend;
@@ -368,7 +338,7 @@ __global__ void __launch_bounds__(256, 3) stage_p7_kernel(const __grid_constant_
   for (int iv = 0; iv < NVAR; ++iv) *reinterpret_cast<double2*>(P.qout[order[iv]] + gn) = qnew[iv];
 
   {  // pressure of the new state: next stage's DPRES; PRES diagnostic at the end of Update (driver:954-959)
-    const double2 ph = ph_e, th = th_e;
+    const double2 ph = *reinterpret_cast<const double2*>(P.pres_hyd + gn), th = *reinterpret_cast<const double2*>(P.therm_hyd + gn);
     double2 R = make_double2(P.c.Rdry, P.c.Rdry), e = make_double2(P.c.CPovCV, P.c.CPovCV);
     if (MOIST) {
       R = *reinterpret_cast<const double2*>(P.rtot + gn);

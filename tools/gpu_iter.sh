@@ -15,7 +15,7 @@ except Exception as e:
 PY
 }
 run_bench default
-if [ -n "$AB" ]; then FEDG_STAGE_GENERIC=1 run_bench generic; fi
+if [ -n "$AB" ]; then FEDG_P7_MINB=2 run_bench minb2; fi
 if [ -n "$NCU" ]; then
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:stage -s 8 -c 1 -o gpurun_out/stage_full -f \
    python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1; echo "ncu-full rc=$?"
