@@ -122,6 +122,19 @@ int feo_update(void* hv, int nsteps) {
   return guard([&] { for (int n = 0; n < nsteps; ++n) h->d.update(); });
 }
 
+// vertical-implicit tendency (cal_vi seam) of the current state about var0; arrays (5, Np*NeA) in the oracle's
+// variable order DENS, RHOT, MOMZ, MOMX, MOMY
+int feo_cal_vi(void* hv, double impl_fac, double dt, const double* var0, double* out) {
+  auto* h = static_cast<Handle*>(hv);
+  return guard([&] {
+    auto& d = h->d;
+    const size_t n = size_t(d.elem.Np) * d.mesh.NeA;
+    const double* v0[5]; double* o[5];
+    for (int v = 0; v < 5; ++v) { v0[v] = var0 + size_t(v) * n; o[v] = out + size_t(v) * n; }
+    hevi_cal_vi(d.elem, d.mesh, d.cst, d.st, v0, impl_fac, dt, o);
+  });
+}
+
 void feo_monitor(void* hv, double* out) { monitor_sums(static_cast<Handle*>(hv)->d, out); }
 
 // single pieces of the step, for kernel-by-kernel parity tests

@@ -16,8 +16,10 @@ class DensityCurrentCase:
     """Straka density current on NeX x NeY x NeZ elements of order p (config 3 of BASELINE.json, any size)."""
 
     def __init__(self, p=7, NeX=8, NeY=2, NeZ=4, dom=(0.0, 25.6e3, 0.0, 6.4e3, 0.0, 6.4e3), dt=0.08,
-                 tinteg="ERK_SSP_4s3o", modalfilter=True, perturb=0.0, periodic=(False, True, False), intrp_order=11):
+                 tinteg="ERK_SSP_4s3o", modalfilter=True, perturb=0.0, periodic=(False, True, False), intrp_order=11,
+                 eqs="NONHYDRO3D_HEVE"):
         self.p, self.dom, self.dt, self.tinteg, self.modalfilter = p, dom, dt, tinteg, modalfilter
+        self.eqs = eqs
         self.periodic = periodic
         self.elem = HexElement(p)
         self.mesh = LocalMeshCube(self.elem, NeX, NeY, NeZ, *dom, periodic=periodic)
@@ -41,14 +43,14 @@ class DensityCurrentCase:
             o.arr(k)[:] = v.reshape(-1)
         o.arr("Rtot")[:] = C0["Rdry"]; o.arr("CVtot")[:] = C0["CVdry"]; o.arr("CPtot")[:] = C0["CPdry"]
         mf = (2.0 / 3.0, 1.0, 16, 2.0 / 3.0, 1.0, 16)
-        o.setup_dyn("NONHYDRO3D_HEVE", self.tinteg, self.dt, self.modalfilter, mf, (2, 2, 2, 2, 2, 2))
+        o.setup_dyn(self.eqs, self.tinteg, self.dt, self.modalfilter, mf, (2, 2, 2, 2, 2, 2))
         o.prepare()
         return o
 
     def make_driver(self, oracle=None):
         from fe_project_b200.dyncore import AtmDynDGMDriver_nonhydro3d
         d = AtmDynDGMDriver_nonhydro3d(self.elem, self.mesh, C0, vel_bc=self.vel_bc)
-        d.Init("NONHYDRO3D_HEVE", self.tinteg, self.dt, MODALFILTER_FLAG=self.modalfilter, **MF)
+        d.Init(self.eqs, self.tinteg, self.dt, MODALFILTER_FLAG=self.modalfilter, **MF)
         f = self.fields
         d.set_aux(f["DENS_hyd"], f["PRES_hyd"])
         if oracle is not None:  # DPhydDx/y are set-up products of the model (driver_nonhydro3d.F90:1060-1095)

@@ -37,6 +37,7 @@ def lib():
         L.feo_prepare.argtypes = [C.c_void_p]
         L.feo_update.argtypes = [C.c_void_p, C.c_int]
         L.feo_monitor.argtypes = [C.c_void_p, C.c_void_p]
+        L.feo_cal_vi.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_void_p, C.c_void_p]
         L.feo_stage_piece.argtypes = [C.c_void_p, C.c_char_p]
         L.feo_elem_op.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.feo_lift_dense.argtypes = [C.c_void_p, C.c_void_p]
@@ -117,6 +118,13 @@ class Oracle:
 
     def piece(self, what):
         self._chk(lib().feo_stage_piece(self.h, what.encode()))
+
+    def cal_vi(self, impl_fac, dt, var0):
+        """var0: (5, Np*NeA) in the order DENS, RHOT, MOMZ, MOMX, MOMY; returns the implicit tendencies, same shape."""
+        var0 = np.ascontiguousarray(var0, dtype=np.float64)
+        out = np.zeros_like(var0)
+        self._chk(lib().feo_cal_vi(self.h, float(impl_fac), float(dt), _p(var0), _p(out)))
+        return out
 
     def monitor(self):
         out = np.zeros(5)
