@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(_HERE, "libfedg.so")
 ABI_SYMBOLS = (
     "fedg_last_error", "fedg_version", "fedg_create", "fedg_destroy", "fedg_dyn_init",
     "fedg_set_prog", "fedg_get_prog", "fedg_set_aux", "fedg_set_phyd_hgrad", "fedg_set_coriolis",
-    "fedg_dyn_update", "fedg_dyn_update_host", "fedg_cal_tend_ex", "fedg_get_pres",
+    "fedg_dyn_update", "fedg_dyn_update_host", "fedg_cal_tend_ex", "fedg_cal_vi", "fedg_get_pres",
     "fedg_exchange_halo", "fedg_monitor", "fedg_rk_info", "fedg_rk_coef", "fedg_elem_op",
     "fedg_last_timing", "fedg_comm_unique_id", "fedg_comm_init",
 )
@@ -60,6 +60,7 @@ def load() -> C.CDLL:
     L.fedg_dyn_update.argtypes = [vp, ci]
     L.fedg_dyn_update_host.argtypes = [vp] * 6 + [ci]
     L.fedg_cal_tend_ex.argtypes = [vp] * 6
+    L.fedg_cal_vi.argtypes = [vp, cd] + [vp] * 10
     L.fedg_get_pres.argtypes = [vp] * 3
     L.fedg_exchange_halo.argtypes = [vp, ci]
     L.fedg_monitor.argtypes = [vp, vp]

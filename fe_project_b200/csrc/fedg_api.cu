@@ -67,6 +67,10 @@ struct fedg_ctx {
   bool tab_dirty = true;
   DevBuf dens_hyd, pres_hyd, therm_hyd, rtot, cvtot, cptot, gsqrt, g13, g23, gsqrtH, dphydx, dphydy, coriolis;
   DevBuf escale, fscale, pres, w3, Jac, zlev, mon;
+  // HEVI: stage tendencies k_ex / k_im [stage][var], var0-based IMEX combination, column-solver scratch
+  std::vector<DevBuf> kex, kim;
+  DevBuf rhot_hyd_vi, vi_scratch;
+  double last_ms_vi = 0;
   int* d_vmapP = nullptr; int* d_emap2d = nullptr; int* d_vmapB = nullptr; int* d_halo_src = nullptr;
   int cur = 0;
   // timing
@@ -84,6 +88,9 @@ struct fedg_ctx {
     for (auto& s : prog) for (auto& b : s) b.release();
     for (auto& b : vt) b.release();
     for (auto& b : tendbuf) b.release();
+    for (auto& b : kex) b.release();
+    for (auto& b : kim) b.release();
+    rhot_hyd_vi.release(); vi_scratch.release();
     for (DevBuf* b : {&dens_hyd, &pres_hyd, &therm_hyd, &rtot, &cvtot, &cptot, &gsqrt, &g13, &g23, &gsqrtH, &dphydx, &dphydy,
                       &coriolis, &escale, &fscale, &pres, &w3, &Jac, &zlev, &mon})
       b->release();
@@ -335,14 +342,28 @@ int fedg_dyn_init(fedg_ctx* c, const char* eqs_type, const char* tinteg_type, do
   if (!c || !eqs_type || !tinteg_type) return fail(FEDG_ERR_ARG, "null argument");
   std::string eqs(eqs_type);
   if (eqs == "NONHYDRO3D_HEVE") c->hevi = false;
-  else return fail(FEDG_ERR_UNSUPPORTED, "EQS_TYPE " + eqs + " is not available in this build (NONHYDRO3D_HEVE only)");
+  else if (eqs == "NONHYDRO3D_HEVI") c->hevi = true;
+  else return fail(FEDG_ERR_UNSUPPORTED, "EQS_TYPE " + eqs + " is not available in this build (NONHYDRO3D_HEVE, NONHYDRO3D_HEVI)");
   if (!c->rk.init(tinteg_type)) return fail(FEDG_ERR_ARG, std::string("unsupported TINTEG_TYPE ") + tinteg_type);
-  if (c->rk.imex) return fail(FEDG_ERR_ARG, "HEVE needs an explicit RK scheme");
-  if (c->rk.tend_buf_size != 1) return fail(FEDG_ERR_UNSUPPORTED, "explicit schemes with several tendency buffers are not supported");
   if (!(dt > 0.0)) return fail(FEDG_ERR_ARG, "dt must be positive");
   c->dt = dt;
-  build_stages(c);
-  if (c->vt_used) for (auto& b : c->vt) if (b.n < c->nall) CUDA_TRY(b.alloc(c->nall));
+  if (c->hevi) {
+    // driver_nonhydro3d.F90:437-452: the HEVI equation sets run with an IMEX scheme
+    if (!c->rk.imex) return fail(FEDG_ERR_ARG, "HEVI needs an IMEX scheme (IMEX_ARK232, IMEX_ARK324)");
+    if (c->np != 8) return fail(FEDG_ERR_UNSUPPORTED, "the vertical-implicit column kernel is built for p = 7 only");
+    if (c->terrain) return fail(FEDG_ERR_UNSUPPORTED, "terrain-following HEVI is not available in this build");
+    if (2 * c->rk.nstage > MAXTERM) return fail(FEDG_ERR_UNSUPPORTED, "too many IMEX stages");
+    c->kex.resize(size_t(c->rk.nstage) * NVAR); c->kim.resize(size_t(c->rk.nstage) * NVAR);
+    for (auto& b : c->kex) if (b.n < c->nint) CUDA_TRY(b.alloc(c->nint));
+    for (auto& b : c->kim) if (b.n < c->nint) CUDA_TRY(b.alloc(c->nint));
+    const size_t nscr = size_t(c->NeZ) * 120 * size_t(c->Ne2D) * 64;
+    if (c->vi_scratch.n < nscr) CUDA_TRY(c->vi_scratch.alloc(nscr));
+  } else {
+    if (c->rk.imex) return fail(FEDG_ERR_ARG, "HEVE needs an explicit RK scheme");
+    if (c->rk.tend_buf_size != 1) return fail(FEDG_ERR_UNSUPPORTED, "explicit schemes with several tendency buffers are not supported");
+    build_stages(c);
+    if (c->vt_used) for (auto& b : c->vt) if (b.n < c->nall) CUDA_TRY(b.alloc(c->nall));
+  }
   c->modalfilter = modalfilter_flag != 0;
   const int np = c->np;
   for (int i = 0; i < np; ++i)
@@ -390,6 +411,9 @@ int fedg_set_aux(fedg_ctx* c, const double* DENS_hyd, const double* PRES_hyd, co
   if ((rc = upload(c, c->pres_hyd, PRES_hyd, c->nint))) return rc;
   if (THERM_hyd) { if ((rc = upload(c, c->therm_hyd, THERM_hyd, c->nint))) return rc; }
   else launch_calc_rhot_hyd(c->pres_hyd.p, c->c, c->therm_hyd.p, long(c->nint), c->stream);
+  // the vertical-implicit solver recomputes RHOT_hyd from PRES_hyd with dry constants (hevi_common_2.F90:211-212, 1253-1254)
+  if (c->rhot_hyd_vi.n < c->nall) CUDA_TRY(c->rhot_hyd_vi.alloc(c->nall));
+  launch_calc_rhot_hyd(c->pres_hyd.p, c->c, c->rhot_hyd_vi.p, long(c->nint), c->stream);
   bool moist = false;
   for (size_t n = 0; n < c->nint && !moist; ++n)
     if (Rtot[n] != c->c.Rdry || CVtot[n] != c->c.CVdry || CPtot[n] != c->c.CPdry) moist = true;
@@ -489,6 +513,69 @@ void ensure_dp(fedg_ctx* c, int buf) {
   c->dp_valid[buf] = true;
 }
 
+void fill_vi_params(fedg_ctx* c, VIParams& V, int in, int out, int i0, int stage, double impl_fac) {
+  for (int v = 0; v < NVAR; ++v) {
+    V.qcur[v] = c->prog[in][v].p; V.q0[v] = c->prog[i0][v].p; V.qout[v] = c->prog[out][v].p;
+    V.kim[v] = c->kim[size_t(stage) * NVAR + v].p;
+  }
+  V.dpout = c->dp[out].p;
+  V.dens_hyd = c->dens_hyd.p; V.pres_hyd = c->pres_hyd.p; V.therm_hyd = c->therm_hyd.p; V.rhot_hyd_vi = c->rhot_hyd_vi.p;
+  V.rtot = c->rtot.p; V.cvtot = c->cvtot.p; V.cptot = c->cptot.p;
+  V.escale = c->escale.p; V.fscale = c->fscale.p; V.tab = c->d_tab; V.scratch = c->vi_scratch.p;
+  V.c = c->c; V.impl_fac = impl_fac; V.Ne = c->Ne; V.Ne2D = c->Ne2D; V.NeZ = c->NeZ;
+}
+
+// HEVI / IMEX step (driver_nonhydro3d.F90:703-763 + 769-921): per stage  cal_vi -> StoreImplicit -> halo + BC ->
+// explicit tendency -> Advance (general IMEX form, scale_timeint_rk.F90:2201-2355, accumulated from var0 in the
+// reference's term order); then the modal filter.
+int run_steps_hevi(fedg_ctx* c, int nsteps, size_t& iev, long& launches) {
+  const int ns = c->rk.nstage;
+  const RKTable& t = c->rk;
+  const double dt = c->dt;
+  for (int step = 0; step < nsteps; ++step) {
+    const int i0 = c->cur, bA = (i0 + 1) % 3, bB = (i0 + 2) % 3;
+    int in = i0;
+    for (int s = 0; s < ns; ++s) {
+      const int mid = (in == i0) ? bA : in;            // the column solve may update in place except on var0
+      const int nxt = (mid == bA) ? bB : bA;
+      VIParams V{};
+      fill_vi_params(c, V, in, mid, i0, s, t.aim(s, s) * dt);
+      cudaEvent_t e0 = nullptr, e1 = nullptr;
+      if (c->profile) { e0 = c->ev[iev++]; e1 = c->ev[iev++]; CUDA_TRY(cudaEventRecord(e0, c->stream)); }
+      launch_vi(V, c->moist, c->stream);
+      if (c->profile) CUDA_TRY(cudaEventRecord(e1, c->stream));
+      c->dp_valid[mid] = true;
+      fill_halo(c, mid, true);
+      StageParams P{};
+      fill_stage_params(c, P, mid, mid, i0);
+      for (int v = 0; v < NVAR; ++v) P.tend_out[v] = c->kex[size_t(s) * NVAR + v].p;
+      launch_stage(P, c->np, c->terrain, c->moist, true, c->stream);
+      LinCombParams L{};
+      L.n = c->nint; L.nterm = 0;
+      for (int v = 0; v < NVAR; ++v) { L.base[v] = c->prog[i0][v].p; L.out[v] = c->prog[nxt][v].p; }
+      for (int ss = 0; ss <= s; ++ss) {
+        const double ce = (s == ns - 1) ? dt * t.b_ex[ss] : dt * t.aex(s + 1, ss);
+        const double ci = (s == ns - 1) ? dt * t.b_im[ss] : dt * t.aim(s + 1, ss);
+        for (int v = 0; v < NVAR; ++v) { L.k[L.nterm][v] = c->kex[size_t(ss) * NVAR + v].p; L.k[L.nterm + 1][v] = c->kim[size_t(ss) * NVAR + v].p; }
+        L.coef[L.nterm] = ce; L.coef[L.nterm + 1] = ci;
+        L.nterm += 2;
+      }
+      launch_lincomb(L, c->stream);
+      c->dp_valid[nxt] = false;
+      launches += 4;
+      in = nxt;
+    }
+    if (c->modalfilter) {
+      double* q[NVAR];
+      for (int v = 0; v < NVAR; ++v) q[v] = c->prog[in][v].p;
+      launch_modal_filter5(q, c->gsqrt.p, c->terrain, c->Ne, c->np, c->stream);
+      launches += 1;
+    }
+    c->cur = in;
+  }
+  return FEDG_OK;
+}
+
 int run_steps(fedg_ctx* c, int nsteps) {
   if (!c->dyn_ready || !c->aux_ready) return fail(FEDG_ERR_STATE, "fedg_dyn_init and fedg_set_aux must be called before the update");
   ensure_tables(c);
@@ -498,6 +585,12 @@ int run_steps(fedg_ctx* c, int nsteps) {
   CUDA_TRY(cudaEventRecord(c->ev[0], c->stream));
   size_t iev = 2;
   long launches = 0;
+  c->last_ms_vi = 0;
+  if (c->hevi) {
+    int rc = run_steps_hevi(c, nsteps, iev, launches);
+    if (rc) return rc;
+    nsteps = 0;
+  }
   for (int step = 0; step < nsteps; ++step) {
     const int i0 = c->cur;
     int in = i0;
@@ -570,10 +663,32 @@ int fedg_cal_tend_ex(fedg_ctx* c, double* DENS_dt, double* MOMX_dt, double* MOMY
   StageParams P{};
   fill_stage_params(c, P, c->cur, c->cur, c->cur);
   for (int v = 0; v < NVAR; ++v) P.tend_out[v] = c->tendbuf[v].p;
-  launch_stage(P, c->np, c->terrain, c->moist, false, c->stream);
+  launch_stage(P, c->np, c->terrain, c->moist, c->hevi, c->stream);
   double* h[NVAR] = {DENS_dt, MOMX_dt, MOMY_dt, MOMZ_dt, RHOT_dt};
   for (int v = 0; v < NVAR; ++v)
     CUDA_TRY(cudaMemcpyAsync(h[v], c->tendbuf[v].p, c->nint * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  CUDA_TRY(cudaGetLastError());
+  return FEDG_OK;
+}
+
+int fedg_cal_vi(fedg_ctx* c, double impl_fac, const double* DDENS0, const double* MOMX0, const double* MOMY0, const double* MOMZ0,
+                const double* DRHOT0, double* DENS_dt, double* MOMX_dt, double* MOMY_dt, double* MOMZ_dt, double* RHOT_dt) {
+  if (!c || !DDENS0 || !MOMX0 || !MOMY0 || !MOMZ0 || !DRHOT0 || !DENS_dt || !MOMX_dt || !MOMY_dt || !MOMZ_dt || !RHOT_dt)
+    return fail(FEDG_ERR_ARG, "null argument");
+  if (!c->dyn_ready || !c->aux_ready || !c->hevi) return fail(FEDG_ERR_STATE, "fedg_dyn_init(NONHYDRO3D_HEVI) and fedg_set_aux must be called first");
+  ensure_tables(c);
+  const int cur = c->cur, b0 = (cur + 1) % 3, b1 = (cur + 2) % 3;
+  const double* h0[NVAR] = {DDENS0, MOMX0, MOMY0, MOMZ0, DRHOT0};
+  for (int v = 0; v < NVAR; ++v)
+    CUDA_TRY(cudaMemcpyAsync(c->prog[b0][v].p, h0[v], c->nint * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  VIParams V{};
+  fill_vi_params(c, V, cur, b1, b0, 0, impl_fac);
+  launch_vi(V, c->moist, c->stream);
+  c->dp_valid[b0] = c->dp_valid[b1] = false;
+  double* h[NVAR] = {DENS_dt, MOMX_dt, MOMY_dt, MOMZ_dt, RHOT_dt};
+  for (int v = 0; v < NVAR; ++v)
+    CUDA_TRY(cudaMemcpyAsync(h[v], c->kim[v].p, c->nint * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   CUDA_TRY(cudaStreamSynchronize(c->stream));
   CUDA_TRY(cudaGetLastError());
   return FEDG_OK;

@@ -76,6 +76,34 @@ struct HaloParams {
   int Np, Ne, Nfp, np, Nhalo, terrain;
 };
 
+// vertical-implicit column solve (vi_solver.cu)
+struct VIParams {
+  const double* qcur[NVAR];   // state entering the stage (DDENS_, MOMX_, ...)
+  const double* q0[NVAR];     // var0: state at the start of the step (Newton linearisation point)
+  double* kim[NVAR];          // out: implicit tendency of the stage
+  double* qout[NVAR];         // out: qcur + impl_fac * kim (may alias qcur when qcur != q0)
+  double* dpout;              // out: DPRES of qout
+  const double *dens_hyd, *pres_hyd, *therm_hyd, *rhot_hyd_vi, *rtot, *cvtot, *cptot;
+  const double *escale, *fscale;
+  const ElemTables* tab;
+  double* scratch;            // NeZ * 120 * (Ne2D*64) doubles
+  PhysConst c;
+  double impl_fac;
+  int Ne, Ne2D, NeZ;
+};
+constexpr int MAXTERM = 20;   // 2 * stages of the largest IMEX scheme supported
+struct LinCombParams {
+  const double* base[NVAR];
+  double* out[NVAR];
+  const double* k[MAXTERM][NVAR];
+  double coef[MAXTERM];
+  int nterm;
+  size_t n;
+};
+void launch_vi(const VIParams& p, bool moist, cudaStream_t s);
+void launch_lincomb(const LinCombParams& L, cudaStream_t s);
+void launch_modal_filter5(double* const q[NVAR], const double* gsqrt, bool terrain, int Ne, int np, cudaStream_t s);
+
 void upload_tables(const ElemTables& t, cudaStream_t s);
 void launch_stage(const StageParams& p, int np, bool terrain, bool moist, bool hevi, cudaStream_t s);
 void launch_halo_fill(const HaloParams& p, cudaStream_t s);

@@ -192,6 +192,41 @@ __global__ void elem_op_kernel(int op, const double* __restrict__ in, double* __
   }
   out[size_t(e) * N3 + n] = r;
 }
+// atm_dyn_dgm_modalfilter_apply stand-alone (scale_atm_dyn_dgm_modalfilter.F90:49-130), five variables in place; used by the
+// HEVI path (the HEVE path applies the filter inside its last stage kernel).  One block per element, one thread per node.
+__global__ void modal_filter5_kernel(double* q0, double* q1, double* q2, double* q3, double* q4, const double* __restrict__ gsqrt,
+                                     int terrain, int np) {
+  extern __shared__ double s[];
+  const int N2 = np * np, N3 = N2 * np;
+  double* w = s + N3;
+  const int e = blockIdx.x, n = threadIdx.x;
+  const int i = n % np, j = (n / np) % np, k = n / N2;
+  double* q[NVAR] = {q0, q1, q2, q3, q4};
+  const size_t gi = size_t(e) * N3 + n;
+  const double G = terrain ? gsqrt[gi] : 1.0;
+  for (int v = 0; v < NVAR; ++v) {
+    __syncthreads();
+    s[n] = G * q[v][gi];
+    __syncthreads();
+    double a = cT.Fh[i * np] * s[j * np + k * N2];
+    for (int l = 1; l < np; ++l) a += cT.Fh[i * np + l] * s[l + j * np + k * N2];
+    w[n] = a;
+    __syncthreads();
+    double b = w[i + k * N2] * cT.Fh[j * np];
+    for (int l = 1; l < np; ++l) b += w[i + l * np + k * N2] * cT.Fh[j * np + l];
+    __syncthreads();
+    s[n] = b;
+    __syncthreads();
+    double r = s[i + j * np] * cT.Fv[k * np];
+    for (int l = 1; l < np; ++l) r += s[i + j * np + l * N2] * cT.Fv[k * np + l];
+    q[v][gi] = r * (1.0 / G);
+  }
+}
+void launch_modal_filter5(double* const q[NVAR], const double* gsqrt, bool terrain, int Ne, int np, cudaStream_t s) {
+  const int N3 = np * np * np;
+  modal_filter5_kernel<<<Ne, N3, size_t(2) * N3 * sizeof(double), s>>>(q[0], q[1], q[2], q[3], q[4], gsqrt, terrain ? 1 : 0, np);
+}
+
 void launch_elem_op(int op, const double* in, double* out, int nelem, int np, cudaStream_t s) {
   int N3 = np * np * np;
   size_t sh = size_t(2) * (6 * np * np > N3 ? 6 * np * np : N3) * sizeof(double);

@@ -148,6 +148,13 @@ class AtmDynDGMDriver_nonhydro3d:
         _lib.check(self.L.fedg_cal_tend_ex(self.h, *[_ptr(a) for a in out]))
         return dict(zip(("DENS_dt", "MOMX_dt", "MOMY_dt", "MOMZ_dt", "RHOT_dt"), out))
 
+    def cal_vi(self, impl_fac: float, var0: dict):
+        """atm_dyn_nonhydro3d_cal_vi: implicit tendency of the device state about var0 ({name: (Np*NeA,) or (Np*Ne,)})."""
+        a = [_f64(var0[k]).reshape(-1)[: self.n_int].copy() for k in PROG_NAMES]
+        out = [np.zeros(self.n_int) for _ in range(5)]
+        _lib.check(self.L.fedg_cal_vi(self.h, float(impl_fac), *[_ptr(x) for x in a], *[_ptr(x) for x in out]))
+        return dict(zip(("DENS_dt", "MOMX_dt", "MOMY_dt", "MOMZ_dt", "RHOT_dt"), out))
+
     def get_pres(self):
         P, D = np.zeros(self.n_int), np.zeros(self.n_int)
         _lib.check(self.L.fedg_get_pres(self.h, _ptr(P), _ptr(D)))

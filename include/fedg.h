@@ -89,7 +89,7 @@ int fedg_create(const fedg_mesh_desc* desc, fedg_ctx** out);
 void fedg_destroy(fedg_ctx* ctx);
 
 /* AtmDynDGMDriver_nonhydro3d%Init: fluid_dyn_solver/scale_atm_dyn_dgm_driver_nonhydro3d.F90:355-594
- * eqs_type: "NONHYDRO3D_HEVE" (| "NONHYDRO3D_HEVI" when built); tinteg_type: a timeint_rk scheme name
+ * eqs_type: "NONHYDRO3D_HEVE" | "NONHYDRO3D_HEVI" (p = 7, flat mesh); tinteg_type: a timeint_rk scheme name
  * (common/scale_timeint_rk_butcher_tab.F90:27-67).  filter_h1D / filter_v1D are the (np,np) matrices
  * MFilter_h1D and MFilter_v1D of Setup_ModalFilter (tensorprod3D.F90.erb:160-181, 460-505); pass
  * NULL when modalfilter_flag == 0. */
@@ -125,6 +125,14 @@ int fedg_dyn_update_host(fedg_ctx* ctx, double* DDENS, double* MOMX, double* MOM
  * what the driver stores in tint%tend_buf2D_ex at one stage.  Outputs are host arrays (Np,Ne). */
 int fedg_cal_tend_ex(fedg_ctx* ctx, double* DENS_dt, double* MOMX_dt, double* MOMY_dt, double* MOMZ_dt,
                      double* RHOT_dt);
+
+/* atm_dyn_nonhydro3d_cal_vi seam (driver_nonhydro3d.F90:201-250, 738-753; rhot_hevi.F90:772-965): vertical-implicit
+ * tendency of the state on the device, one Newton iteration about var0 (host arrays (Np,Ne), the tint%var0_2D of the
+ * reference).  impl_fac = a_im(s,s)*dt; impl_fac == 0 evaluates the vertical operator explicitly.  Needs
+ * fedg_dyn_init("NONHYDRO3D_HEVI", ...).  Outputs are host arrays (Np,Ne). */
+int fedg_cal_vi(fedg_ctx* ctx, double impl_fac, const double* DDENS0, const double* MOMX0, const double* MOMY0,
+                const double* MOMZ0, const double* DRHOT0, double* DENS_dt, double* MOMX_dt, double* MOMY_dt,
+                double* MOMZ_dt, double* RHOT_dt);
 
 /* atm_dyn_dgm_nonhydro3d_common_calc_pressure (nonhydro3d_common.F90:350-393): PRES, DPRES (Np,Ne) of
  * the state on the device. */
