@@ -72,6 +72,9 @@ struct fedg_ctx {
   DevBuf rhot_hyd_vi, vi_scratch;
   double last_ms_vi = 0;
   int* d_vmapP = nullptr; int* d_emap2d = nullptr; int* d_vmapB = nullptr; int* d_halo_src = nullptr;
+  // multi-GPU: NCCL state and the interior / tile-boundary element lists used to overlap the exchange
+  CommState comm;
+  int* d_elem_inner = nullptr; int* d_elem_bnd = nullptr; int n_inner = 0, n_bnd = 0;
   int cur = 0;
   // timing
   bool profile = true;
@@ -84,6 +87,9 @@ struct fedg_ctx {
     if (d_vmapB) cudaFree(d_vmapB);
     if (d_halo_src) cudaFree(d_halo_src);
     if (d_tab) cudaFree(d_tab);
+    if (d_elem_inner) cudaFree(d_elem_inner);
+    if (d_elem_bnd) cudaFree(d_elem_bnd);
+    comm_destroy(comm);
     for (auto& b : dp) b.release();
     for (auto& s : prog) for (auto& b : s) b.release();
     for (auto& b : vt) b.release();
@@ -402,6 +408,8 @@ int fedg_get_prog(fedg_ctx* c, double* DDENS, double* MOMX, double* MOMY, double
 
 // gather own-face values into the halo slots of an auxiliary field (same-rank faces)
 static int fill_aux_halo(fedg_ctx* c, double* field);
+// halo of the auxiliary fields across ranks (AUX_VARS exchange after a restart is read, model mod_atmos_vars.F90:553-636)
+static int exchange_aux_remote(fedg_ctx* c);
 
 int fedg_set_aux(fedg_ctx* c, const double* DENS_hyd, const double* PRES_hyd, const double* THERM_hyd, const double* Rtot,
                  const double* CVtot, const double* CPtot) {
@@ -426,6 +434,7 @@ int fedg_set_aux(fedg_ctx* c, const double* DENS_hyd, const double* PRES_hyd, co
   }
   for (DevBuf* b : {&c->dens_hyd, &c->pres_hyd, &c->therm_hyd}) if ((rc = fill_aux_halo(c, b->p))) return rc;
   if (moist) for (DevBuf* b : {&c->rtot, &c->cvtot, &c->cptot}) if ((rc = fill_aux_halo(c, b->p))) return rc;
+  if ((rc = exchange_aux_remote(c))) return rc;
   CUDA_TRY(cudaStreamSynchronize(c->stream));
   c->aux_ready = true;
   for (bool& v : c->dp_valid) v = false;
@@ -513,6 +522,8 @@ void ensure_dp(fedg_ctx* c, int buf) {
   c->dp_valid[buf] = true;
 }
 
+int exchange_and_stage(fedg_ctx* c, StageParams& P, int buf, bool hevi);
+
 void fill_vi_params(fedg_ctx* c, VIParams& V, int in, int out, int i0, int stage, double impl_fac) {
   for (int v = 0; v < NVAR; ++v) {
     V.qcur[v] = c->prog[in][v].p; V.q0[v] = c->prog[i0][v].p; V.qout[v] = c->prog[out][v].p;
@@ -545,11 +556,10 @@ int run_steps_hevi(fedg_ctx* c, int nsteps, size_t& iev, long& launches) {
       launch_vi(V, c->moist, c->stream);
       if (c->profile) CUDA_TRY(cudaEventRecord(e1, c->stream));
       c->dp_valid[mid] = true;
-      fill_halo(c, mid, true);
       StageParams P{};
       fill_stage_params(c, P, mid, mid, i0);
       for (int v = 0; v < NVAR; ++v) P.tend_out[v] = c->kex[size_t(s) * NVAR + v].p;
-      launch_stage(P, c->np, c->terrain, c->moist, true, c->stream);
+      { int rc = exchange_and_stage(c, P, mid, true); if (rc) return rc; }
       LinCombParams L{};
       L.n = c->nint; L.nterm = 0;
       for (int v = 0; v < NVAR; ++v) { L.base[v] = c->prog[i0][v].p; L.out[v] = c->prog[nxt][v].p; }
@@ -576,6 +586,33 @@ int run_steps_hevi(fedg_ctx* c, int nsteps, size_t& iev, long& launches) {
   return FEDG_OK;
 }
 
+// MeshFieldComm_Exchange + boundary condition + stage kernel.  With remote neighbours: pack and ship the tile faces on
+// the communication stream, process the interior elements meanwhile, then the tile-boundary elements once the halo
+// has arrived (HIDE_MPI_COMM_FLAG path of the reference, driver_nonhydro3d.F90:859-895).
+int exchange_and_stage(fedg_ctx* c, StageParams& P, int buf, bool hevi) {
+  fill_halo(c, buf, true);    // faces whose neighbour is on this rank + physical boundaries
+  if (!c->comm.active || c->comm.nremote == 0) {
+    launch_stage(P, c->np, c->terrain, c->moist, hevi, c->stream);
+    return FEDG_OK;
+  }
+  double* q[NVAR];
+  for (int v = 0; v < NVAR; ++v) q[v] = c->prog[buf][v].p;
+  std::string err;
+  int rc = comm_exchange_start(c->comm, q, c->dp[buf].p, c->d_vmapB, c->nint, c->stream, err);
+  if (rc) return fail(rc, err);
+  if (c->n_inner > 0) {
+    P.elem_list = c->d_elem_inner; P.nelem = c->n_inner;
+    launch_stage(P, c->np, c->terrain, c->moist, hevi, c->stream);
+  }
+  comm_exchange_wait(c->comm, c->stream);
+  if (c->n_bnd > 0) {
+    P.elem_list = c->d_elem_bnd; P.nelem = c->n_bnd;
+    launch_stage(P, c->np, c->terrain, c->moist, hevi, c->stream);
+  }
+  P.elem_list = nullptr; P.nelem = 0;
+  return FEDG_OK;
+}
+
 int run_steps(fedg_ctx* c, int nsteps) {
   if (!c->dyn_ready || !c->aux_ready) return fail(FEDG_ERR_STATE, "fedg_dyn_init and fedg_set_aux must be called before the update");
   ensure_tables(c);
@@ -599,13 +636,12 @@ int run_steps(fedg_ctx* c, int nsteps) {
       if (s == ns - 1) out = (ns == 1) ? (i0 + 1) % 3 : i0;
       else { out = (in + 1) % 3; if (out == i0) out = (out + 1) % 3; }
       ensure_dp(c, in);
-      fill_halo(c, in, true);
       StageParams P{};
       fill_stage_params(c, P, in, out, i0);
       P.rk = c->stages[s];
       if (s == ns - 1) { P.do_filter = c->modalfilter; P.write_pres = 1; }
       if (c->profile) CUDA_TRY(cudaEventRecord(c->ev[iev++], c->stream));
-      launch_stage(P, c->np, c->terrain, c->moist, false, c->stream);
+      { int rc = exchange_and_stage(c, P, in, false); if (rc) return rc; }
       if (c->profile) CUDA_TRY(cudaEventRecord(c->ev[iev++], c->stream));
       c->dp_valid[out] = true;
       launches += 2;
@@ -624,6 +660,19 @@ int run_steps(fedg_ctx* c, int nsteps) {
   return FEDG_OK;
 }
 }  // namespace
+
+static int exchange_aux_remote(fedg_ctx* c) {
+  if (!c->comm.active || c->comm.nremote == 0) return FEDG_OK;
+  // the six-field exchange ships any six arrays: send the background fields in its slots
+  double* q[NVAR] = {c->dens_hyd.p, c->pres_hyd.p, c->therm_hyd.p, c->moist ? c->rtot.p : c->dens_hyd.p, c->moist ? c->cvtot.p : c->pres_hyd.p};
+  double* sixth = c->moist ? c->cptot.p : c->therm_hyd.p;
+  std::string err;
+  int rc = comm_exchange_start(c->comm, q, sixth, c->d_vmapB, c->nint, c->stream, err);
+  if (rc) return fail(rc, err);
+  comm_exchange_wait(c->comm, c->stream);
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  return FEDG_OK;
+}
 
 static int fill_aux_halo(fedg_ctx* c, double* field) {
   if (c->Nhalo > 0) aux_halo_kernel<<<(c->Nhalo + 255) / 256, 256, 0, c->stream>>>(field, c->d_halo_src, int(c->nint), c->Nhalo);
@@ -648,6 +697,15 @@ int fedg_dyn_update_host(fedg_ctx* c, double* DDENS, double* MOMX, double* MOMY,
 int fedg_exchange_halo(fedg_ctx* c, int apply_bc) {
   if (!c) return fail(FEDG_ERR_ARG, "null argument");
   fill_halo(c, c->cur, apply_bc != 0);
+  if (c->comm.active && c->comm.nremote > 0) {
+    ensure_dp(c, c->cur);
+    double* q[NVAR];
+    for (int v = 0; v < NVAR; ++v) q[v] = c->prog[c->cur][v].p;
+    std::string err;
+    int rc = comm_exchange_start(c->comm, q, c->dp[c->cur].p, c->d_vmapB, c->nint, c->stream, err);
+    if (rc) return fail(rc, err);
+    comm_exchange_wait(c->comm, c->stream);
+  }
   CUDA_TRY(cudaStreamSynchronize(c->stream));
   CUDA_TRY(cudaGetLastError());
   return FEDG_OK;
@@ -659,11 +717,10 @@ int fedg_cal_tend_ex(fedg_ctx* c, double* DENS_dt, double* MOMX_dt, double* MOMY
   ensure_tables(c);
   for (auto& b : c->tendbuf) if (b.n < c->nint) CUDA_TRY(b.alloc(c->nint));
   ensure_dp(c, c->cur);
-  fill_halo(c, c->cur, true);
   StageParams P{};
   fill_stage_params(c, P, c->cur, c->cur, c->cur);
   for (int v = 0; v < NVAR; ++v) P.tend_out[v] = c->tendbuf[v].p;
-  launch_stage(P, c->np, c->terrain, c->moist, c->hevi, c->stream);
+  { int rc = exchange_and_stage(c, P, c->cur, c->hevi); if (rc) return rc; }
   double* h[NVAR] = {DENS_dt, MOMX_dt, MOMY_dt, MOMZ_dt, RHOT_dt};
   for (int v = 0; v < NVAR; ++v)
     CUDA_TRY(cudaMemcpyAsync(h[v], c->tendbuf[v].p, c->nint * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
@@ -751,7 +808,40 @@ int fedg_last_timing(fedg_ctx* c, double* ms_total, double* ms_stage_kernels, lo
   return FEDG_OK;
 }
 
-int fedg_comm_unique_id(void*) { return fail(FEDG_ERR_UNSUPPORTED, "NCCL halo exchange is not built yet"); }
-int fedg_comm_init(fedg_ctx*, const void*, int, int) { return fail(FEDG_ERR_UNSUPPORTED, "NCCL halo exchange is not built yet"); }
+int fedg_comm_unique_id(void* id128) {
+  if (!id128) return fail(FEDG_ERR_ARG, "null argument");
+  std::string err;
+  int rc = comm_unique_id(id128, err);
+  return rc ? fail(rc, err) : FEDG_OK;
+}
+
+int fedg_comm_init(fedg_ctx* c, const void* id128, int rank, int nranks) {
+  if (!c || !id128 || nranks < 1 || rank < 0 || rank >= nranks) return fail(FEDG_ERR_ARG, "bad argument");
+  if (rank != c->my_rank) return fail(FEDG_ERR_ARG, "rank differs from fedg_mesh_desc.my_rank");
+  if (c->comm.active) return fail(FEDG_ERR_STATE, "communicator already initialised");
+  std::string err;
+  int rc = comm_init(c->comm, id128, rank, nranks, c->nbr_rank, c->nbr_face, c->face_off, err);
+  if (rc) return fail(rc, err);
+  // elements touching a face whose neighbour tile lives on another rank
+  const int fsz[6] = {c->NeX * c->NeZ, c->NeY * c->NeZ, c->NeX * c->NeZ, c->NeY * c->NeZ, c->NeX * c->NeY, c->NeX * c->NeY};
+  (void)fsz;
+  std::vector<char> is_bnd(c->Ne, 0);
+  for (int ke = 0; ke < c->Ne; ++ke) {
+    const int ix = ke % c->NeX, iy = (ke / c->NeX) % c->NeY;
+    if ((iy == 0 && c->nbr_rank[0] != rank) || (ix == c->NeX - 1 && c->nbr_rank[1] != rank) || (iy == c->NeY - 1 && c->nbr_rank[2] != rank) ||
+        (ix == 0 && c->nbr_rank[3] != rank))
+      is_bnd[ke] = 1;
+  }
+  if (c->nbr_rank[4] != rank || c->nbr_rank[5] != rank) return fail(FEDG_ERR_UNSUPPORTED, "vertical tile decomposition is not supported (NprcZ = 1 in the reference)");
+  std::vector<int> inner, bnd;
+  for (int ke = 0; ke < c->Ne; ++ke) (is_bnd[ke] ? bnd : inner).push_back(ke);
+  c->n_inner = int(inner.size()); c->n_bnd = int(bnd.size());
+  CUDA_TRY(cudaMalloc(&c->d_elem_inner, std::max<size_t>(inner.size(), 1) * sizeof(int)));
+  CUDA_TRY(cudaMalloc(&c->d_elem_bnd, std::max<size_t>(bnd.size(), 1) * sizeof(int)));
+  CUDA_TRY(cudaMemcpy(c->d_elem_inner, inner.data(), inner.size() * sizeof(int), cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(c->d_elem_bnd, bnd.data(), bnd.size() * sizeof(int), cudaMemcpyHostToDevice));
+  if (c->aux_ready) { int rc2 = exchange_aux_remote(c); if (rc2) return rc2; }
+  return FEDG_OK;
+}
 
 }  // extern "C"

@@ -61,6 +61,8 @@ struct StageParams {
   RKStage rk;
   PhysConst c;
   int Ne, Ne2D;
+  const int* elem_list;  // when non-null: process elements elem_list[0..nelem) (interior / tile-boundary split)
+  int nelem;
   int has_cor, has_phyd, do_filter, write_pres, fast_pow;
 };
 
@@ -103,6 +105,29 @@ struct LinCombParams {
 void launch_vi(const VIParams& p, bool moist, cudaStream_t s);
 void launch_lincomb(const LinCombParams& L, cudaStream_t s);
 void launch_modal_filter5(double* const q[NVAR], const double* gsqrt, bool terrain, int Ne, int np, cudaStream_t s);
+
+// halo exchange over NCCL (halo_comm.cu)
+struct RemoteFace {
+  int f = 0, peer = 0, peer_face = 0, off = 0, cnt = 0;   // own face id, neighbour rank, its face id, halo offset / node count
+  double* sendbuf = nullptr;                               // [6][cnt]
+};
+struct CommState {
+  bool active = false;
+  void* comm = nullptr;          // ncclComm_t
+  int rank = 0, nranks = 1, nremote = 0;
+  RemoteFace face[6];
+  int recv_order[6] = {0, 1, 2, 3, 4, 5};
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev_packed = nullptr, ev_done = nullptr;
+};
+int comm_unique_id(void* id128, std::string& err);
+int comm_init(CommState& cs, const void* id128, int rank, int nranks, const int nbr_rank[6], const int nbr_face[6], const int face_off[7],
+              std::string& err);
+void comm_destroy(CommState& cs);
+int comm_exchange_start(CommState& cs, double* const q[NVAR], double* dp, const int* d_vmapB, size_t nint, cudaStream_t compute,
+                        std::string& err);
+void comm_exchange_wait(CommState& cs, cudaStream_t compute);
+int comm_allreduce_sum(CommState& cs, double* d_inout, int n, cudaStream_t s, std::string& err);
 
 void upload_tables(const ElemTables& t, cudaStream_t s);
 void launch_stage(const StageParams& p, int np, bool terrain, bool moist, bool hevi, cudaStream_t s);

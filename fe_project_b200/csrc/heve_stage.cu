@@ -76,9 +76,11 @@ __global__ void __launch_bounds__(512, MINB) stage_kernel(const __grid_constant_
   const int tid = threadIdx.x;
   const int el = tid / N3, n = tid - el * N3;
   const int i = n % NP, j = (n / NP) % NP, k = n / N2;
-  int ke = blockIdx.x * EPB + el;
-  const bool live = ke < P.Ne;
-  if (!live) ke = P.Ne - 1;
+  const int nel = P.elem_list ? P.nelem : P.Ne;
+  int slot = blockIdx.x * EPB + el;
+  const bool live = slot < nel;
+  if (!live) slot = nel - 1;
+  const int ke = P.elem_list ? P.elem_list[slot] : slot;
   const size_t eb = size_t(ke) * N3;
   const size_t gn = eb + n;
 
@@ -277,7 +279,8 @@ template <int NP, bool HEVI, int MINB>
 static void launch_stage_np(const StageParams& p, bool terrain, bool moist, cudaStream_t s) {
   using G = StageGeo<NP>;
   const size_t shmem = G::SMEM_BYTES;
-  dim3 grid((p.Ne + G::EPB - 1) / G::EPB), block(512);
+  const int nel = p.elem_list ? p.nelem : p.Ne;
+  dim3 grid((nel + G::EPB - 1) / G::EPB), block(512);
 #define FEDG_LAUNCH(T, M)                                                                                             \
   do {                                                                                                                \
     static bool attr_set = false;                                                                                     \

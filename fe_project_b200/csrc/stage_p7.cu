@@ -46,7 +46,7 @@ template <bool TERRAIN, bool MOIST, bool HEVI>
 __global__ void __launch_bounds__(256, 3) stage_p7_kernel(const __grid_constant__ StageParams P) {
   using namespace p7;
   const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
-  const int ke = blockIdx.x;
+  const int ke = P.elem_list ? P.elem_list[blockIdx.x] : int(blockIdx.x);
   const size_t eb = size_t(ke) * N3;
   const int n0 = 2 * t + 8 * g + 64 * w;     // own nodes n0, n0 + 1
   const size_t gn = eb + n0;
@@ -361,7 +361,7 @@ __global__ void __launch_bounds__(256, 3) stage_p7_kernel(const __grid_constant_
 
 void launch_stage_p7(const StageParams& p, bool terrain, bool moist, bool hevi, cudaStream_t s) {
   const size_t shmem = p7::SMEM_BYTES;
-  dim3 grid(p.Ne), block(256);
+  dim3 grid(p.elem_list ? p.nelem : p.Ne), block(256);
 #define FEDG_LAUNCH(T, M, H)                                                                                  \
   do {                                                                                                        \
     static bool attr_set = false;                                                                             \

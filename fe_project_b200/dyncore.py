@@ -77,6 +77,17 @@ class AtmDynDGMDriver_nonhydro3d:
         self.n_field = mesh.NeA * elem.Np
         self.n_int = mesh.Ne * elem.Np
 
+    # ---- multi-GPU: NCCL communicator over the ranks of the tile graph ------------------------
+    def init_comm(self, rank: int, nranks: int, bcast):
+        """bcast(bytes_or_None) -> bytes: broadcasts rank 0's 128-byte NCCL unique id with the caller's transport
+        (MPI_Bcast in the Fortran driver, torch.distributed here)."""
+        buf = (C.c_ubyte * 128)()
+        if rank == 0:
+            _lib.check(self.L.fedg_comm_unique_id(buf))
+        raw = bcast(bytes(buf) if rank == 0 else None)
+        buf2 = (C.c_ubyte * 128).from_buffer_copy(raw)
+        _lib.check(self.L.fedg_comm_init(self.h, buf2, int(rank), int(nranks)))
+
     # ---- reference-style lifecycle -------------------------------------------------------
     def Init(self, EQS_TYPE: str, TINTEG_TYPE: str, TIME_DT: float, MODALFILTER_FLAG: bool = False,
              MF_ETAC_h=2.0 / 3.0, MF_ALPHA_h=1.0, MF_ORDER_h=16, MF_ETAC_v=2.0 / 3.0, MF_ALPHA_v=1.0, MF_ORDER_v=16):

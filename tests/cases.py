@@ -17,12 +17,14 @@ class DensityCurrentCase:
 
     def __init__(self, p=7, NeX=8, NeY=2, NeZ=4, dom=(0.0, 25.6e3, 0.0, 6.4e3, 0.0, 6.4e3), dt=0.08,
                  tinteg="ERK_SSP_4s3o", modalfilter=True, perturb=0.0, periodic=(False, True, False), intrp_order=11,
-                 eqs="NONHYDRO3D_HEVE"):
+                 eqs="NONHYDRO3D_HEVE", NprcX=1, NprcY=1, pi=0, pj=0):
+        """NeX, NeY, NeZ are per tile; dom is the whole domain; (pi, pj) selects the tile of an NprcX x NprcY decomposition."""
         self.p, self.dom, self.dt, self.tinteg, self.modalfilter = p, dom, dt, tinteg, modalfilter
         self.eqs = eqs
         self.periodic = periodic
+        self.NprcX, self.NprcY, self.pi, self.pj = NprcX, NprcY, pi, pj
         self.elem = HexElement(p)
-        self.mesh = LocalMeshCube(self.elem, NeX, NeY, NeZ, *dom, periodic=periodic)
+        self.mesh = LocalMeshCube(self.elem, NeX, NeY, NeZ, *dom, periodic=periodic, NprcX=NprcX, NprcY=NprcY, pi=pi, pj=pj)
         self.fields = initcond.density_current(self.mesh, intrp_order=intrp_order)
         if perturb:
             # deterministic smooth 3D momentum perturbation so that every term of the tendency is exercised
@@ -49,7 +51,9 @@ class DensityCurrentCase:
 
     def make_driver(self, oracle=None):
         from fe_project_b200.dyncore import AtmDynDGMDriver_nonhydro3d
-        d = AtmDynDGMDriver_nonhydro3d(self.elem, self.mesh, C0, vel_bc=self.vel_bc)
+        rank = self.pi + self.pj * self.NprcX
+        d = AtmDynDGMDriver_nonhydro3d(self.elem, self.mesh, C0, vel_bc=self.vel_bc, my_rank=rank,
+                                       tile_rank=lambda qi, qj: qi + qj * self.NprcX)
         d.Init(self.eqs, self.tinteg, self.dt, MODALFILTER_FLAG=self.modalfilter, **MF)
         f = self.fields
         d.set_aux(f["DENS_hyd"], f["PRES_hyd"])
