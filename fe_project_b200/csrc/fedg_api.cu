@@ -522,7 +522,7 @@ void ensure_dp(fedg_ctx* c, int buf) {
   c->dp_valid[buf] = true;
 }
 
-int exchange_and_stage(fedg_ctx* c, StageParams& P, int buf, bool hevi);
+int exchange_and_stage(fedg_ctx* c, StageParams& P, int buf, bool hevi, cudaEvent_t e0 = nullptr, cudaEvent_t e1 = nullptr);
 
 void fill_vi_params(fedg_ctx* c, VIParams& V, int in, int out, int i0, int stage, double impl_fac) {
   for (int v = 0; v < NVAR; ++v) {
@@ -589,8 +589,10 @@ int run_steps_hevi(fedg_ctx* c, int nsteps, size_t& iev, long& launches) {
 // MeshFieldComm_Exchange + boundary condition + stage kernel.  With remote neighbours: pack and ship the tile faces on
 // the communication stream, process the interior elements meanwhile, then the tile-boundary elements once the halo
 // has arrived (HIDE_MPI_COMM_FLAG path of the reference, driver_nonhydro3d.F90:859-895).
-int exchange_and_stage(fedg_ctx* c, StageParams& P, int buf, bool hevi) {
+int exchange_and_stage(fedg_ctx* c, StageParams& P, int buf, bool hevi, cudaEvent_t e0, cudaEvent_t e1) {
   fill_halo(c, buf, true);    // faces whose neighbour is on this rank + physical boundaries
+  if (e0) cudaEventRecord(e0, c->stream);   // the timed region brackets the stage kernel(s) (+ the exchange when there is one)
+  struct Rec { cudaEvent_t e; cudaStream_t s; ~Rec() { if (e) cudaEventRecord(e, s); } } rec{e1, c->stream};
   if (!c->comm.active || c->comm.nremote == 0) {
     launch_stage(P, c->np, c->terrain, c->moist, hevi, c->stream);
     return FEDG_OK;
@@ -640,9 +642,9 @@ int run_steps(fedg_ctx* c, int nsteps) {
       fill_stage_params(c, P, in, out, i0);
       P.rk = c->stages[s];
       if (s == ns - 1) { P.do_filter = c->modalfilter; P.write_pres = 1; }
-      if (c->profile) CUDA_TRY(cudaEventRecord(c->ev[iev++], c->stream));
-      { int rc = exchange_and_stage(c, P, in, false); if (rc) return rc; }
-      if (c->profile) CUDA_TRY(cudaEventRecord(c->ev[iev++], c->stream));
+      cudaEvent_t e0 = nullptr, e1 = nullptr;
+      if (c->profile) { e0 = c->ev[iev++]; e1 = c->ev[iev++]; }
+      { int rc = exchange_and_stage(c, P, in, false, e0, e1); if (rc) return rc; }
       c->dp_valid[out] = true;
       launches += 2;
       in = out;
