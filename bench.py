@@ -175,7 +175,7 @@ def main():
     dom = (x0, x0 + (x1 - x0) * NX, y0, y0 + (y1 - y0) * NY, z0, z1)
     hevi = args.eqs == "hevi"
     case = DensityCurrentCase(p=WORKLOAD["p"], NeX=args.nex, NeY=args.ney, NeZ=args.nez, dom=dom,
-                              dt=(1.0 if hevi else WORKLOAD["dt"]), tinteg=("IMEX_ARK324" if hevi else WORKLOAD["tinteg"]),
+                              dt=(2.0 * WORKLOAD["dt"] if hevi else WORKLOAD["dt"]), tinteg=("IMEX_ARK324" if hevi else WORKLOAD["tinteg"]),
                               modalfilter=True, NprcX=NX, NprcY=NY, pi=pi, pj=pj,
                               eqs=("NONHYDRO3D_HEVI" if hevi else "NONHYDRO3D_HEVE"))
     d = case.make_driver(None)

@@ -18,6 +18,8 @@ ABI_SYMBOLS = (
     "fedg_dyn_update", "fedg_dyn_update_host", "fedg_cal_tend_ex", "fedg_cal_vi", "fedg_get_pres",
     "fedg_exchange_halo", "fedg_monitor", "fedg_rk_info", "fedg_rk_coef", "fedg_elem_op",
     "fedg_last_timing", "fedg_comm_unique_id", "fedg_comm_init",
+    "fedg_sparsemat_matmul", "fedg_advect3d_init", "fedg_advect3d_set", "fedg_advect3d_get",
+    "fedg_advect3d_cal_tend", "fedg_advect3d_update",
 )
 
 
@@ -29,6 +31,10 @@ class MeshDesc(C.Structure):
         + [("nbr_rank", C.c_int * 6), ("nbr_face", C.c_int * 6), ("my_rank", C.c_int), ("vel_bc", C.c_int * 6)]
         + [(n, C.c_double) for n in ("GRAV", "Rdry", "CPdry", "CVdry", "PRES00", "OHM")]
     )
+
+
+class SparseMatDesc(C.Structure):
+    _fields_ = [("M", C.c_int), ("N", C.c_int), ("col_size", C.c_int), ("val", C.c_void_p), ("colIdx", C.c_void_p)]
 
 
 _lib = None
@@ -70,6 +76,13 @@ def load() -> C.CDLL:
     L.fedg_last_timing.argtypes = [vp, vp, vp, vp]
     L.fedg_comm_unique_id.argtypes = [vp]
     L.fedg_comm_init.argtypes = [vp, vp, ci, ci]
+    sp = C.POINTER(SparseMatDesc)
+    L.fedg_sparsemat_matmul.argtypes = [sp, vp, vp, ci]
+    L.fedg_advect3d_init.argtypes = [vp, C.c_char_p, cd, sp, sp, sp, sp]
+    L.fedg_advect3d_set.argtypes = [vp] * 5
+    L.fedg_advect3d_get.argtypes = [vp, vp]
+    L.fedg_advect3d_cal_tend.argtypes = [vp, vp]
+    L.fedg_advect3d_update.argtypes = [vp, ci]
     _lib = L
     return L
 

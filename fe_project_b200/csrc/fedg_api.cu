@@ -44,6 +44,28 @@ struct DevBuf {
 };
 }  // namespace
 
+// sample/advect3d run on the mesh of a context (fedg_advect3d_*)
+struct AdvectState {
+  bool ready = false;
+  RKTable rk;
+  std::vector<RKStage> stages;
+  bool vt_used = false;
+  double dt = 0;
+  DevBuf q[3], u, v, w, vt, tend, ellval[4];
+  int* ellcol[4] = {nullptr, nullptr, nullptr, nullptr};
+  int colsz[4] = {0, 0, 0, 0};
+  int cur = 0, epb = 1;
+  cudaGraphExec_t step_graph = nullptr;
+  void release() {
+    if (step_graph) { cudaGraphExecDestroy(step_graph); step_graph = nullptr; }
+    for (auto& b : q) b.release();
+    for (DevBuf* b : {&u, &v, &w, &vt, &tend}) b->release();
+    for (auto& b : ellval) b.release();
+    for (auto& p : ellcol) { if (p) cudaFree(p); p = nullptr; }
+    ready = false;
+  }
+};
+
 struct fedg_ctx {
   int np = 0, Np = 0, Nfp = 0, NfpTot = 0;
   int Ne = 0, NeA = 0, NeX = 0, NeY = 0, NeZ = 0, Ne2D = 0, Nhalo = 0;
@@ -76,6 +98,7 @@ struct fedg_ctx {
   CommState comm;
   int* d_elem_inner = nullptr; int* d_elem_bnd = nullptr; int n_inner = 0, n_bnd = 0;
   int cur = 0;
+  AdvectState adv;
   // timing
   bool profile = true;
   std::vector<cudaEvent_t> ev;
@@ -90,6 +113,7 @@ struct fedg_ctx {
     if (d_elem_inner) cudaFree(d_elem_inner);
     if (d_elem_bnd) cudaFree(d_elem_bnd);
     comm_destroy(comm);
+    adv.release();
     for (auto& b : dp) b.release();
     for (auto& s : prog) for (auto& b : s) b.release();
     for (auto& b : vt) b.release();
@@ -309,39 +333,40 @@ int fedg_rk_coef(const char* scheme, double* a_ex, double* b_ex, double* a_im, d
 
 // Stage coefficients of the fused update from the scheme tables
 // (rk_advance_low_storage2D scale_timeint_rk.F90:1182-1266, rk_advance_general2D :2201-2355).
-static void build_stages(fedg_ctx* c) {
-  const RKTable& t = c->rk;
+static void build_stage_coefs(const RKTable& t, double dt, std::vector<RKStage>& stages, bool& vt_used) {
   const int s = t.nstage;
-  const double EPS = 2.220446e-16, dt = c->dt;
-  c->stages.assign(s, RKStage{});
-  c->vt_used = false;
+  const double EPS = 2.220446e-16;
+  stages.assign(s, RKStage{});
+  vt_used = false;
   if (t.low_storage) {
     for (int n = 0; n < s - 1; ++n)
-      if (std::fabs(t.sg(s, n)) > EPS || std::fabs(t.gm(s, n)) > EPS) c->vt_used = true;
+      if (std::fabs(t.sg(s, n)) > EPS || std::fabs(t.gm(s, n)) > EPS) vt_used = true;
     for (int n = 0; n < s; ++n) {
-      RKStage& r = c->stages[n];
+      RKStage& r = stages[n];
       const double sig_ss = t.sg(n + 1, n), gam_ss = dt * t.gm(n + 1, n);
       r.c_q = sig_ss; r.c_k = gam_ss;
-      if (n == s - 1) { r.add_vt = c->vt_used; continue; }
+      if (n == s - 1) { r.add_vt = vt_used; continue; }
       r.c_q0 = 1.0 - sig_ss; r.use_q0 = (r.c_q0 != 0.0);
       const double sig_Ns = t.sg(s, n), gam_Ns = dt * t.gm(s, n);
       const bool upd = std::fabs(sig_Ns) > EPS || std::fabs(t.gm(s, n)) > EPS;
-      if (c->vt_used && (upd || n == 0)) {
+      if (vt_used && (upd || n == 0)) {
         r.vt_update = 1; r.vt_init = (n == 0); r.vt_init_q = 0.0;
         r.vt_q = upd ? sig_Ns : 0.0; r.vt_k = upd ? gam_Ns : 0.0;
       }
     }
   } else {  // general explicit scheme with tend_buf_size == 1
     for (int n = 0; n < s; ++n) {
-      RKStage& r = c->stages[n];
+      RKStage& r = stages[n];
       if (s == 1) { r.c_q = 1.0; r.c_k = dt * t.b_ex[0]; continue; }
-      c->vt_used = true;
+      vt_used = true;
       if (n == s - 1) { r.add_vt = 1; r.c_q = 0.0; r.c_k = dt * t.b_ex[n]; continue; }
       r.use_q0 = 1; r.c_q0 = 1.0; r.c_q = 0.0; r.c_k = dt * t.aex(n + 1, n);
       r.vt_update = 1; r.vt_init = (n == 0); r.vt_init_q = 1.0; r.vt_q = 0.0; r.vt_k = dt * t.b_ex[n];
     }
   }
 }
+
+static void build_stages(fedg_ctx* c) { build_stage_coefs(c->rk, c->dt, c->stages, c->vt_used); }
 
 int fedg_dyn_init(fedg_ctx* c, const char* eqs_type, const char* tinteg_type, double dt, int modalfilter_flag,
                   const double* filter_h1D, const double* filter_v1D) {
@@ -843,6 +868,177 @@ int fedg_comm_init(fedg_ctx* c, const void* id128, int rank, int nranks) {
   CUDA_TRY(cudaMemcpy(c->d_elem_inner, inner.data(), inner.size() * sizeof(int), cudaMemcpyHostToDevice));
   CUDA_TRY(cudaMemcpy(c->d_elem_bnd, bnd.data(), bnd.size() * sizeof(int), cudaMemcpyHostToDevice));
   if (c->aux_ready) { int rc2 = exchange_aux_remote(c); if (rc2) return rc2; }
+  return FEDG_OK;
+}
+
+}  // extern "C"
+
+// ---- sample/advect3d (config 1) --------------------------------------------------------------------------
+namespace {
+void fill_advect_params(fedg_ctx* c, AdvectParams& P, int in, int out, int i0) {
+  AdvectState& a = c->adv;
+  P.q = a.q[in].p; P.u = a.u.p; P.v = a.v.p; P.w = a.w.p;
+  P.qout = a.q[out].p; P.q0 = a.q[i0].p; P.vt = a.vt.p; P.tend_out = nullptr;
+  for (int k = 0; k < 4; ++k) { P.ellval[k] = a.ellval[k].p; P.ellcol[k] = a.ellcol[k]; P.colsz[k] = a.colsz[k]; }
+  P.escale = c->escale.p; P.fscale = c->fscale.p; P.vmapP = c->d_vmapP;
+  P.Np = c->Np; P.Nfp = c->Nfp; P.NfpTot = c->NfpTot; P.np = c->np; P.Ne = c->Ne; P.epb = a.epb;
+}
+
+// one time step of test_advect3d.f90:81-126 enqueued on the context's stream; ends with adv.cur unchanged
+int enqueue_advect_step(fedg_ctx* c) {
+  AdvectState& a = c->adv;
+  const int ns = a.rk.nstage, i0 = a.cur;
+  int in = i0;
+  for (int s = 0; s < ns; ++s) {
+    int out;
+    if (s == ns - 1) out = (ns == 1) ? (i0 + 1) % 3 : i0;
+    else { out = (in + 1) % 3; if (out == i0) out = (out + 1) % 3; }
+    launch_advect_halo(a.q[in].p, a.u.p, a.v.p, a.w.p, c->d_halo_src, c->nint, c->Nhalo, false, c->stream);
+    AdvectParams P{};
+    fill_advect_params(c, P, in, out, i0);
+    P.rk = a.stages[s];
+    CUDA_TRY(launch_advect_stage(P, c->stream));
+    in = out;
+  }
+  a.cur = in;
+  return FEDG_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int fedg_sparsemat_matmul(const fedg_sparsemat* A, const double* b, double* c, int nvec) {
+  if (!A || !A->val || !A->colIdx || !b || !c || nvec <= 0 || A->M <= 0 || A->N <= 0 || A->col_size <= 0)
+    return fail(FEDG_ERR_ARG, "bad argument");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(FEDG_ERR_CUDA, "no CUDA device (this library has no CPU fallback)");
+  const size_t nell = size_t(A->M) * A->col_size;
+  std::vector<int> col0(nell);
+  for (size_t l = 0; l < nell; ++l) {
+    col0[l] = A->colIdx[l] - 1;
+    if (col0[l] < 0 || col0[l] >= A->N) return fail(FEDG_ERR_ARG, "colIdx out of range (must be 1-based)");
+  }
+  DevBuf dv, db, dc; int* dcol = nullptr;
+  CUDA_TRY(dv.alloc(nell)); CUDA_TRY(db.alloc(size_t(A->N) * nvec)); CUDA_TRY(dc.alloc(size_t(A->M) * nvec));
+  CUDA_TRY(cudaMalloc(&dcol, nell * sizeof(int)));
+  cudaError_t e = cudaMemcpy(dv.p, A->val, nell * sizeof(double), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(dcol, col0.data(), nell * sizeof(int), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(db.p, b, size_t(A->N) * nvec * sizeof(double), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = launch_ell_spmv(A->M, A->N, A->col_size, dv.p, dcol, db.p, dc.p, nvec, nullptr);
+  if (e == cudaSuccess) e = cudaMemcpy(c, dc.p, size_t(A->M) * nvec * sizeof(double), cudaMemcpyDeviceToHost);
+  cudaFree(dcol); dv.release(); db.release(); dc.release();
+  if (e != cudaSuccess) return fail(FEDG_ERR_CUDA, cudaGetErrorString(e));
+  return FEDG_OK;
+}
+
+int fedg_advect3d_init(fedg_ctx* c, const char* tinteg_type, double dt, const fedg_sparsemat* Dx, const fedg_sparsemat* Dy,
+                       const fedg_sparsemat* Dz, const fedg_sparsemat* Lift) {
+  if (!c || !tinteg_type || !Dx || !Dy || !Dz || !Lift) return fail(FEDG_ERR_ARG, "null argument");
+  AdvectState& a = c->adv;
+  a.release();
+  if (!a.rk.init(tinteg_type)) return fail(FEDG_ERR_ARG, std::string("unsupported TINTEG_SCHEME_TYPE ") + tinteg_type);
+  if (a.rk.imex) return fail(FEDG_ERR_ARG, "advect3d needs an explicit RK scheme");
+  if (a.rk.tend_buf_size != 1) return fail(FEDG_ERR_UNSUPPORTED, "explicit schemes with several tendency buffers are not supported");
+  if (!(dt > 0.0)) return fail(FEDG_ERR_ARG, "dt must be positive");
+  if (c->comm.active && c->comm.nremote > 0) return fail(FEDG_ERR_UNSUPPORTED, "advect3d runs on a single tile");
+  a.dt = dt;
+  build_stage_coefs(a.rk, dt, a.stages, a.vt_used);
+  const fedg_sparsemat* mats[4] = {Dx, Dy, Dz, Lift};
+  for (int k = 0; k < 4; ++k) {
+    const fedg_sparsemat* m = mats[k];
+    if (m->M != c->Np || m->N != (k == 3 ? c->NfpTot : c->Np) || m->col_size <= 0 || !m->val || !m->colIdx)
+      return fail(FEDG_ERR_ARG, "sparsemat shape does not match the element (Dx,Dy,Dz: Np x Np; Lift: Np x NfpTot)");
+    if (k > 0 && k < 3 && m->col_size != Dx->col_size) return fail(FEDG_ERR_ARG, "Dx, Dy, Dz must share col_size");
+    const size_t nell = size_t(m->M) * m->col_size;
+    std::vector<int> col0(nell);
+    for (size_t l = 0; l < nell; ++l) {
+      col0[l] = m->colIdx[l] - 1;
+      if (col0[l] < 0 || col0[l] >= m->N) return fail(FEDG_ERR_ARG, "sparsemat colIdx out of range (must be 1-based)");
+    }
+    a.colsz[k] = m->col_size;
+    CUDA_TRY(a.ellval[k].alloc(nell));
+    CUDA_TRY(cudaMalloc(&a.ellcol[k], nell * sizeof(int)));
+    CUDA_TRY(cudaMemcpy(a.ellval[k].p, m->val, nell * sizeof(double), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(a.ellcol[k], col0.data(), nell * sizeof(int), cudaMemcpyHostToDevice));
+  }
+  a.epb = std::max(1, 256 / c->Np);
+  for (auto& b : a.q) CUDA_TRY(b.alloc(c->nall));
+  for (DevBuf* b : {&a.u, &a.v, &a.w, &a.vt}) CUDA_TRY(b->alloc(c->nall));
+  CUDA_TRY(a.tend.alloc(c->nint));
+  AdvectParams P{};
+  fill_advect_params(c, P, 0, 1, 0);
+  if (advect_smem_bytes(P) > 227 * 1024) return fail(FEDG_ERR_UNSUPPORTED, "operators do not fit in shared memory at this order");
+  a.cur = 0;
+  a.ready = true;
+  return FEDG_OK;
+}
+
+int fedg_advect3d_set(fedg_ctx* c, const double* q, const double* u, const double* v, const double* w) {
+  if (!c || !q || !u || !v || !w) return fail(FEDG_ERR_ARG, "null argument");
+  AdvectState& a = c->adv;
+  if (!a.ready) return fail(FEDG_ERR_STATE, "fedg_advect3d_init must be called first");
+  const double* h[4] = {q, u, v, w};
+  double* d[4] = {a.q[a.cur].p, a.u.p, a.v.p, a.w.p};
+  for (int k = 0; k < 4; ++k) CUDA_TRY(cudaMemcpyAsync(d[k], h[k], c->nall * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  launch_advect_halo(a.q[a.cur].p, a.u.p, a.v.p, a.w.p, c->d_halo_src, c->nint, c->Nhalo, true, c->stream);
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  CUDA_TRY(cudaGetLastError());
+  return FEDG_OK;
+}
+
+int fedg_advect3d_get(fedg_ctx* c, double* q) {
+  if (!c || !q) return fail(FEDG_ERR_ARG, "null argument");
+  if (!c->adv.ready) return fail(FEDG_ERR_STATE, "fedg_advect3d_init must be called first");
+  CUDA_TRY(cudaMemcpyAsync(q, c->adv.q[c->adv.cur].p, c->nall * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  return FEDG_OK;
+}
+
+int fedg_advect3d_cal_tend(fedg_ctx* c, double* dqdt) {
+  if (!c || !dqdt) return fail(FEDG_ERR_ARG, "null argument");
+  AdvectState& a = c->adv;
+  if (!a.ready) return fail(FEDG_ERR_STATE, "fedg_advect3d_init must be called first");
+  launch_advect_halo(a.q[a.cur].p, a.u.p, a.v.p, a.w.p, c->d_halo_src, c->nint, c->Nhalo, true, c->stream);
+  AdvectParams P{};
+  fill_advect_params(c, P, a.cur, a.cur, a.cur);
+  P.tend_out = a.tend.p;
+  CUDA_TRY(launch_advect_stage(P, c->stream));
+  CUDA_TRY(cudaMemcpyAsync(dqdt, a.tend.p, c->nint * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  CUDA_TRY(cudaGetLastError());
+  return FEDG_OK;
+}
+
+int fedg_advect3d_update(fedg_ctx* c, int nsteps) {
+  if (!c || nsteps < 0) return fail(FEDG_ERR_ARG, "bad argument");
+  AdvectState& a = c->adv;
+  if (!a.ready) return fail(FEDG_ERR_STATE, "fedg_advect3d_init must be called first");
+  while (c->ev.size() < 2) { cudaEvent_t e; CUDA_TRY(cudaEventCreate(&e)); c->ev.push_back(e); }
+  if (!a.step_graph && nsteps > 1 && a.rk.nstage > 1) {
+    // launch-bound at the sample's size (512 elements): capture one step (2 kernels per stage) and replay it
+    cudaGraph_t g = nullptr;
+    CUDA_TRY(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+    const int cur0 = a.cur;
+    int rc = enqueue_advect_step(c);
+    cudaError_t e = cudaStreamEndCapture(c->stream, &g);
+    if (rc) { if (g) cudaGraphDestroy(g); return rc; }
+    if (e != cudaSuccess) return fail(FEDG_ERR_CUDA, std::string("graph capture: ") + cudaGetErrorString(e));
+    if (a.cur != cur0) { cudaGraphDestroy(g); return fail(FEDG_ERR_STATE, "step does not return to its start buffer"); }
+    e = cudaGraphInstantiate(&a.step_graph, g, 0);
+    cudaGraphDestroy(g);
+    if (e != cudaSuccess) return fail(FEDG_ERR_CUDA, std::string("graph instantiate: ") + cudaGetErrorString(e));
+  }
+  CUDA_TRY(cudaEventRecord(c->ev[0], c->stream));
+  for (int n = 0; n < nsteps; ++n) {
+    if (a.step_graph) CUDA_TRY(cudaGraphLaunch(a.step_graph, c->stream));
+    else { int rc = enqueue_advect_step(c); if (rc) return rc; }
+  }
+  CUDA_TRY(cudaEventRecord(c->ev[1], c->stream));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  CUDA_TRY(cudaGetLastError());
+  float ms = 0;
+  CUDA_TRY(cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]));
+  c->last_ms_total = ms; c->last_ms_stage = 0; c->last_launches = long(nsteps) * a.rk.nstage * 2;
   return FEDG_OK;
 }
 

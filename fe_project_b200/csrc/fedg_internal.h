@@ -102,6 +102,29 @@ struct LinCombParams {
   int nterm;
   size_t n;
 };
+// sample/advect3d stage (advect3d.cu)
+struct AdvectParams {
+  const double *q, *u, *v, *w;   // stage input (Np*Ne + Nhalo), halo filled
+  double* qout;
+  const double* q0;
+  double* vt;
+  double* tend_out;              // when non-null: write dqdt instead of the updated q
+  const double* ellval[4];       // Dx, Dy, Dz, Lift in ELL storage (slot-major, M = Np)
+  const int* ellcol[4];          // 0-based columns
+  int colsz[4];
+  const double* escale;          // [3][Ne]
+  const double* fscale;          // [6][Ne]
+  const int* vmapP;              // (NfpTot,Ne) 0-based
+  RKStage rk;
+  int Np, Nfp, NfpTot, np, Ne, epb;
+};
+size_t advect_smem_bytes(const AdvectParams& P);
+cudaError_t launch_advect_stage(const AdvectParams& P, cudaStream_t s);
+void launch_advect_halo(double* q, double* u, double* v, double* w, const int* src, size_t nint, int nhalo, bool with_vel,
+                        cudaStream_t s);
+cudaError_t launch_ell_spmv(int M, int N, int col_size, const double* val, const int* col, const double* b, double* c, int nvec,
+                            cudaStream_t s);
+
 void launch_vi(const VIParams& p, bool moist, cudaStream_t s);
 void launch_lincomb(const LinCombParams& L, cudaStream_t s);
 void launch_modal_filter5(double* const q[NVAR], const double* gsqrt, bool terrain, int Ne, int np, cudaStream_t s);

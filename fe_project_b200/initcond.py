@@ -3,6 +3,7 @@
 Each function restates the analytic initial condition of a reference test case so that
 the CUDA path and the CPU oracle start from identical arrays:
 
+* sound wave (sample/euler3d_hevi/test_euler3d_hevi.f90:1106-1149): uniform background, cosine pulse in DRHOT.
 * density current (Straka et al. 1993):
   model/atm_nonhydro3d/test/case/density_current/mod_user.F90:154-254,
   model/atm_nonhydro3d/src/preprocess/mod_mkinit_util.F90:54-165 (cosine bell + L2 projection),
@@ -71,4 +72,19 @@ def density_current(mesh: LocalMeshCube, theta0=300.0, dtheta=-15.0, xc=0.0, yc=
     f["PRES_hyd"][:Ne] = pres_hyd
     f["DDENS"][:Ne] = DENS - dens_hyd
     f["DRHOT"][:Ne] = DENS * PT - dens_hyd * theta0
+    return f
+
+
+def sound_wave(mesh: LocalMeshCube, amplitude=1.0e-12, dens0=1.0, pres0=1.0e5):
+    """Initial state of sample/euler3d_hevi (set_initcond_lc, test_euler3d_hevi.f90:1106-1149): DENS_hyd = 1,
+    PRES_hyd = 1e5, zero momentum, DRHOT = A cos(pi r / 2) for |r| <= 1 with r = (z - z_mid) / (0.1 Lz).
+    The shipped amplitude is 1e-12."""
+    e = mesh.elem
+    Np, Ne, NeA = e.Np, mesh.Ne, mesh.NeA
+    z = mesh.pos_en[2]
+    r = (z - 0.5 * (mesh.zmax + mesh.zmin)) / ((mesh.zmax - mesh.zmin) * 0.1)
+    f = {k: np.zeros((NeA, Np)) for k in ("DDENS", "MOMX", "MOMY", "MOMZ", "DRHOT", "DENS_hyd", "PRES_hyd")}
+    f["DENS_hyd"][:Ne] = dens0
+    f["PRES_hyd"][:Ne] = pres0
+    f["DRHOT"][:Ne] = np.where(np.abs(r) <= 1.0, amplitude * np.cos(0.5 * np.pi * r), 0.0)
     return f

@@ -171,6 +171,33 @@ int fedg_last_timing(fedg_ctx* ctx, double* ms_total, double* ms_stage_kernels, 
 int fedg_comm_unique_id(void* id128);
 int fedg_comm_init(fedg_ctx* ctx, const void* id128, int rank, int nranks);
 
+/* ---- sample/advect3d (BASELINE config 1) --------------------------------------------------------------
+ * `sparsemat` in ELL storage as the reference holds it (common/scale_sparsemat.F90:33-55, 100-250):
+ * val(M*col_size), colIdx(M*col_size), slot-major l = i + (k-1)*M (:172), colIdx 1-based. */
+typedef struct fedg_sparsemat {
+  int M, N, col_size;
+  const double* val;
+  const int* colIdx;
+} fedg_sparsemat;
+
+/* sparsemat_matmul, ELL (common/scale_sparsemat.F90:439-474, 554-634): c(:,j) = A b(:,j) for nvec right-hand sides;
+ * b is (N,nvec), c is (M,nvec), host arrays. */
+int fedg_sparsemat_matmul(const fedg_sparsemat* A, const double* b, double* c, int nvec);
+
+/* Set-up of the advection run on the mesh of ctx: the four operators the sample passes to
+ * advect3d_kernel_cal_tend (sample/advect3d/mod_advect3d_kernel.f90:34-44) and the timeint_rk scheme and step of
+ * sample/advect3d/test_advect3d.f90 (TINTEG_SCHEME_TYPE, TIME_DT). */
+int fedg_advect3d_init(fedg_ctx* ctx, const char* tinteg_type, double dt, const fedg_sparsemat* Dx,
+                       const fedg_sparsemat* Dy, const fedg_sparsemat* Dz, const fedg_sparsemat* Lift);
+/* q, u, v, w: MeshField3D%local(n)%val (Np,NeA), host <-> device (halo part is filled by the exchange). */
+int fedg_advect3d_set(fedg_ctx* ctx, const double* q, const double* u, const double* v, const double* w);
+int fedg_advect3d_get(fedg_ctx* ctx, double* q);
+/* advect3d_kernel_cal_tend of the state on the device after the halo exchange: dqdt (Np,Ne), host array. */
+int fedg_advect3d_cal_tend(fedg_ctx* ctx, double* dqdt);
+/* nsteps passes of the stage loop of test_advect3d.f90:81-126 (exchange -> cal_tend -> Advance per stage),
+ * state resident on the device; one step is captured once as a CUDA graph and replayed. */
+int fedg_advect3d_update(fedg_ctx* ctx, int nsteps);
+
 #ifdef __cplusplus
 }
 #endif

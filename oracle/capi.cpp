@@ -35,6 +35,9 @@ void* feo_create(int p, int lumped, int NeX, int NeY, int NeZ, const double* dom
   return h;
 }
 void feo_destroy(void* hv) { delete static_cast<Handle*>(hv); }
+// element / mesh of a handle, for the sample restatements that live on the same mesh (advect3d.cpp)
+const void* feo_elem_ptr(void* hv) { return &static_cast<Handle*>(hv)->d.elem; }
+const void* feo_mesh_ptr(void* hv) { return &static_cast<Handle*>(hv)->d.mesh; }
 
 void feo_dims(void* hv, int* out) {
   auto& d = static_cast<Handle*>(hv)->d;

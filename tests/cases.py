@@ -35,15 +35,17 @@ class DensityCurrentCase:
             self.fields["MOMY"][:Ne] = perturb * 0.7 * np.sin(kx * x + 0.3) * np.sin(ky * y + 0.1) * np.cos(kz * z)
             self.fields["MOMZ"][:Ne] = perturb * 0.5 * np.sin(kx * x) * np.cos(ky * y) * np.sin(kz * z)
         self.vel_bc = SLIP6
+        self.consts = C0
 
     def make_oracle(self):
         from oracle_api import Oracle
         m = self.mesh
         o = Oracle(self.p, m.NeX, m.NeY, m.NeZ, self.dom, periodic=self.periodic)
-        o.set_consts(C0)
+        o.set_consts(self.consts)
         for k, v in self.fields.items():
             o.arr(k)[:] = v.reshape(-1)
-        o.arr("Rtot")[:] = C0["Rdry"]; o.arr("CVtot")[:] = C0["CVdry"]; o.arr("CPtot")[:] = C0["CPdry"]
+        c = self.consts
+        o.arr("Rtot")[:] = c["Rdry"]; o.arr("CVtot")[:] = c["CVdry"]; o.arr("CPtot")[:] = c["CPdry"]
         mf = (2.0 / 3.0, 1.0, 16, 2.0 / 3.0, 1.0, 16)
         o.setup_dyn(self.eqs, self.tinteg, self.dt, self.modalfilter, mf, (2, 2, 2, 2, 2, 2))
         o.prepare()
@@ -52,7 +54,7 @@ class DensityCurrentCase:
     def make_driver(self, oracle=None):
         from fe_project_b200.dyncore import AtmDynDGMDriver_nonhydro3d
         rank = self.pi + self.pj * self.NprcX
-        d = AtmDynDGMDriver_nonhydro3d(self.elem, self.mesh, C0, vel_bc=self.vel_bc, my_rank=rank,
+        d = AtmDynDGMDriver_nonhydro3d(self.elem, self.mesh, self.consts, vel_bc=self.vel_bc, my_rank=rank,
                                        tile_rank=lambda qi, qj: qi + qj * self.NprcX)
         d.Init(self.eqs, self.tinteg, self.dt, MODALFILTER_FLAG=self.modalfilter, **MF)
         f = self.fields
@@ -61,6 +63,27 @@ class DensityCurrentCase:
             d.set_phyd_hgrad(oracle.arr("DPhydDx"), oracle.arr("DPhydDy"))
         d.set_prog(*(f[k] for k in ("DDENS", "MOMX", "MOMY", "MOMZ", "DRHOT")))
         return d
+
+
+class SoundWaveCase(DensityCurrentCase):
+    """Vertical sound-wave pulse of sample/euler3d_hevi (config 2 of BASELINE.json): 10 km cube, uniform background
+    DENS_hyd = 1, PRES_hyd = 1e5, GRAV = 0 (PARAM_CONST of its test.conf), DRHOT = A cos(pi r / 2) for |r| <= 1 around
+    mid-height (test_euler3d_hevi.f90:1106-1149), run through the library HEVI path (rows a8-a12) with IMEX_ARK232.
+    The shipped amplitude 1e-12 sits at round-off of the background rho*theta, so parity runs
+    use a raised amplitude; horizontally periodic, slip walls at bottom and top."""
+
+    def __init__(self, p=7, NeX=1, NeY=1, NeZ=80, dt=10.0, tinteg="IMEX_ARK232", amplitude=1.0e-3, modalfilter=False,
+                 NprcX=1, NprcY=1, pi=0, pj=0):
+        self.p, self.dt, self.tinteg, self.modalfilter = p, dt, tinteg, modalfilter
+        self.dom = dom = (0.0, 10.0e3, 0.0, 10.0e3, 0.0, 10.0e3)
+        self.eqs = "NONHYDRO3D_HEVI"
+        self.periodic = (True, True, False)
+        self.NprcX, self.NprcY, self.pi, self.pj = NprcX, NprcY, pi, pj
+        self.elem = HexElement(p)
+        self.mesh = LocalMeshCube(self.elem, NeX, NeY, NeZ, *dom, periodic=self.periodic, NprcX=NprcX, NprcY=NprcY, pi=pi, pj=pj)
+        self.consts = dict(C0, GRAV=0.0)
+        self.fields = initcond.sound_wave(self.mesh, amplitude=amplitude)
+        self.vel_bc = SLIP6
 
 
 def rel_l2(a, b):

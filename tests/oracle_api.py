@@ -55,6 +55,14 @@ def lib():
         L.feo_rk_store_implicit.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
         L.feo_rk_advance.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
         L.feo_last_error.restype = C.c_char_p
+        L.feo_advect3d_create.restype = C.c_void_p
+        L.feo_advect3d_create.argtypes = [C.c_void_p, C.c_char_p, C.c_double, C.c_int]
+        L.feo_advect3d_destroy.argtypes = [C.c_void_p]
+        L.feo_advect3d_array.restype = C.POINTER(C.c_double)
+        L.feo_advect3d_array.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_long)]
+        L.feo_advect3d_sparsemat.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 5
+        L.feo_advect3d_cal_tend.argtypes = [C.c_void_p, C.c_void_p]
+        L.feo_advect3d_update.argtypes = [C.c_void_p, C.c_int]
         _LIB = L
     return _LIB
 
@@ -147,6 +155,44 @@ class Oracle:
         out = np.zeros((self.Np, self.Np))
         lib().feo_dmat_dense(self.h, d, _p(out))
         return out
+
+
+class OracleAdvect3D:
+    """sample/advect3d on the mesh of an Oracle (config 1): q, u, v, w (Np*NeA) + ERK integrator."""
+
+    def __init__(self, oracle: Oracle, scheme="ERK_4s4o", dt=0.008, ell=True):
+        self.o = oracle
+        self.h = lib().feo_advect3d_create(oracle.h, scheme.encode(), float(dt), int(ell))
+        if not self.h:
+            raise RuntimeError("feo_advect3d_create failed")
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().feo_advect3d_destroy(self.h)
+            self.h = None
+
+    def arr(self, name):
+        n = C.c_long()
+        ptr = lib().feo_advect3d_array(self.h, name.encode(), C.byref(n))
+        if not ptr:
+            raise KeyError(name)
+        return np.ctypeslib.as_array(ptr, shape=(n.value,))
+
+    def sparsemat(self, which):
+        """ELL arrays of Dx/Dy/Dz/Lift (which = 0..3): (M, N, col_size, val[M*col_size], colIdx 0-based)."""
+        M, N, cs = C.c_int(), C.c_int(), C.c_int()
+        val, col = C.POINTER(C.c_double)(), C.POINTER(C.c_int)()
+        lib().feo_advect3d_sparsemat(self.h, which, C.byref(M), C.byref(N), C.byref(cs), C.byref(val), C.byref(col))
+        n = M.value * cs.value
+        return M.value, N.value, cs.value, np.ctypeslib.as_array(val, shape=(n,)).copy(), np.ctypeslib.as_array(col, shape=(n,)).copy()
+
+    def cal_tend(self):
+        out = np.zeros(self.o.Np * self.o.Ne)
+        lib().feo_advect3d_cal_tend(self.h, _p(out))
+        return out
+
+    def update(self, nsteps=1):
+        lib().feo_advect3d_update(self.h, int(nsteps))
 
 
 def sparsemat_matmul(A, b, eps, ell):

@@ -3,7 +3,7 @@ Bar (BASELINE.json north_star): relative L2 error of every prognostic variable <
 import numpy as np
 import pytest
 
-from cases import DensityCurrentCase, rel_l2, C0
+from cases import DensityCurrentCase, SoundWaveCase, rel_l2, C0
 
 pytestmark = pytest.mark.gpu
 TOL = 1.0e-10
@@ -241,7 +241,8 @@ def test_hevi_cal_vi(impl_fac):
             # compare the Newton iterate q* itself, and the tendency against the scale of the state
             qcur = o.arr(k)[:n]
             qs_ref, qs_got = qcur + impl_fac * ref[i], qcur + impl_fac * got[OUT[k]]
-            assert rel_l2(qs_got, qs_ref) <= 1e-12, (k, impl_fac)
+            # (DRHOT is a perturbation of rho*theta ~ 350: round-off of the full field is ~1e-13 of the perturbation)
+            assert rel_l2(qs_got, qs_ref) <= 1e-11, (k, impl_fac)
             assert np.abs(got[OUT[k]] - ref[i]).max() <= 1e-10 * max(np.abs(var0[i]).max(), np.abs(ref[i]).max()) / impl_fac, (k, impl_fac)
 
 
@@ -270,3 +271,45 @@ def test_hevi_rejects_unsupported():
     d = case.make_driver(None)
     with pytest.raises(_lib.FedgError):
         d.Init("NONHYDRO3D_HEVI", "ERK_SSP_3s3o", 0.1)      # HEVI needs IMEX
+
+
+@pytest.mark.parametrize("NeZ,amplitude", [(80, 1.0e-3), (80, 1.0e-12), (16, 1.0)])
+def test_sound_wave_config2(NeZ, amplitude):
+    """BASELINE config 2: sample/euler3d_hevi sound wave on the shipped 1x1x80 column at p = 7, IMEX_ARK232, GRAV = 0,
+    24 steps of 0.25 s (the horizontal explicit part limits dt to ~0.3 s at p = 7 on the 10 km wide element; vertical
+    acoustic CFL ~ 12).  MOMX/MOMY are pure round-off noise here (pressure round-off eps*p0 differentiated), so they are
+    compared against the momentum scale rho*c_s; with the shipped amplitude 1e-12 the perturbation itself is at round-off
+    of the background rho*theta (348), so that run is judged on the full fields."""
+    case = SoundWaveCase(p=7, NeZ=NeZ, dt=0.25, amplitude=amplitude)
+    o = case.make_oracle()
+    d = case.make_driver(o)
+    o.update(24); d.Update(24)
+    g = d.get_prog()
+    n = case.mesh.Ne * case.elem.Np
+    cs, rhot_hyd = np.sqrt(1.4e5), 1.0e5 / C0["Rdry"]
+    if amplitude > 1e-6:
+        for nm in ("DDENS", "MOMZ", "DRHOT"):
+            assert rel_l2(g[nm][:n], o.arr(nm)[:n]) <= TOL, nm
+        for nm in ("MOMX", "MOMY"):
+            assert np.abs(g[nm][:n] - o.arr(nm)[:n]).max() <= TOL * cs, nm
+    else:
+        assert np.abs(g["DRHOT"][:n] - o.arr("DRHOT")[:n]).max() <= 1e-13 * rhot_hyd
+        assert np.abs(g["DDENS"][:n] - o.arr("DDENS")[:n]).max() <= 1e-13
+        for nm in ("MOMX", "MOMY", "MOMZ"):
+            assert np.abs(g[nm][:n] - o.arr(nm)[:n]).max() <= 1e-13 * cs
+
+
+def test_sound_wave_config2_3d_tile():
+    """Config 2's rate variant in small: 3x2x8 elements, the same pulse made three-dimensional so that the horizontal
+    explicit part takes part."""
+    case = SoundWaveCase(p=7, NeX=3, NeY=2, NeZ=8, dt=0.1, amplitude=1.0e-2)
+    m = case.mesh
+    x, y = m.pos_en[0], m.pos_en[1]
+    case.fields["DRHOT"][:m.Ne] *= (1.0 + 0.5 * np.sin(2 * np.pi * x / 1.0e4) * np.cos(2 * np.pi * y / 1.0e4))
+    o = case.make_oracle()
+    d = case.make_driver(o)
+    o.update(8); d.Update(8)
+    g = d.get_prog()
+    n = m.Ne * case.elem.Np
+    for nm in PROG:
+        assert rel_l2(g[nm][:n], o.arr(nm)[:n]) <= TOL, nm

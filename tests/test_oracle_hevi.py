@@ -98,3 +98,29 @@ def test_vertical_acoustic_cfl_above_one_is_stable():
     assert np.abs(o.arr("DRHOT")[:n]).max() < 2e-2 and np.abs(o.arr("MOMZ")[:n]).max() < 5.0
     assert abs(np.sum(w * o.arr("DRHOT")[:n]) - m0) < 1e-12 * w.sum() * 360.0
     assert np.abs(o.arr("MOMX")[:n]).max() < 1e-12
+
+
+def test_sound_wave_config2_speed_and_split():
+    """BASELINE config 2 (sample/euler3d_hevi sound wave, p = 7 column) through the library HEVI path: the DRHOT pulse
+    splits into two halves of amplitude A/2 travelling at c_s = sqrt(gamma p / rho) (linear acoustics), momentum stays
+    vertical, and the DRHOT integral is conserved."""
+    from cases import SoundWaveCase
+    A = 1.0e-3
+    case = SoundWaveCase(p=7, NeZ=40, dt=0.25, amplitude=A)   # horizontal explicit part: dt < ~0.3 s at p = 7 on a 10 km element
+    o = case.make_oracle()
+    Ne, Np = case.mesh.Ne, case.elem.Np
+    n = Ne * Np
+    w = np.tile(case.elem.IntWeight_lgl, Ne) * case.mesh.J.reshape(-1)
+    m0 = np.sum(w * o.arr("DRHOT")[:n])
+    nstep = 24
+    o.update(nstep)
+    z = case.mesh.pos_en[2].reshape(-1)
+    dr = o.arr("DRHOT")[:n]
+    cs = np.sqrt(C0["CPdry"] / C0["CVdry"] * 1.0e5 / 1.0)
+    up = z > 5.0e3
+    zpk = z[up][np.argmax(dr[up])]
+    assert abs(zpk - (5.0e3 + cs * nstep * case.dt)) < 60.0, zpk
+    assert abs(dr[up].max() - 0.5 * A) < 0.02 * A
+    assert abs(dr[~up].max() - 0.5 * A) < 0.02 * A
+    assert abs(np.sum(w * dr) - m0) < 1e-12 * w.sum() * 350.0
+    assert np.abs(o.arr("MOMX")[:n]).max() < 1e-8 * np.abs(o.arr("MOMZ")[:n]).max()
