@@ -30,6 +30,7 @@ class MeshDesc(C.Structure):
                                      "J", "Gsqrt", "GI3", "GsqrtH", "zlev", "VMapM", "VMapP", "VMapB", "EMap3Dto2D")]
         + [("nbr_rank", C.c_int * 6), ("nbr_face", C.c_int * 6), ("my_rank", C.c_int), ("vel_bc", C.c_int * 6)]
         + [(n, C.c_double) for n in ("GRAV", "Rdry", "CPdry", "CVdry", "PRES00", "OHM")]
+        + [(n, C.c_void_p) for n in ("GIJ", "gam", "pos2D")] + [("panelID", C.c_int)]
     )
 
 

@@ -71,6 +71,7 @@ struct fedg_ctx {
   int Ne = 0, NeA = 0, NeX = 0, NeY = 0, NeZ = 0, Ne2D = 0, Nhalo = 0;
   size_t nint = 0, nall = 0;  // Np*Ne, Np*Ne + Nhalo
   bool terrain = false, moist = false, has_cor = false, has_phyd = false;
+  bool global = false; int panel = 0;   // cubed-sphere panel tile (GLOBALNONHYDRO3D_HEVI)
   bool dyn_ready = false, aux_ready = false;
   PhysConst c{};
   double OHM = 0;
@@ -88,7 +89,7 @@ struct fedg_ctx {
   ElemTables* d_tab = nullptr;
   bool tab_dirty = true;
   DevBuf dens_hyd, pres_hyd, therm_hyd, rtot, cvtot, cptot, gsqrt, g13, g23, gsqrtH, dphydx, dphydy, coriolis;
-  DevBuf escale, fscale, pres, w3, Jac, zlev, mon;
+  DevBuf escale, fscale, pres, w3, Jac, zlev, mon, g2d;
   // HEVI: stage tendencies k_ex / k_im [stage][var], var0-based IMEX combination, column-solver scratch
   std::vector<DevBuf> kex, kim;
   DevBuf rhot_hyd_vi, vi_scratch;
@@ -122,7 +123,7 @@ struct fedg_ctx {
     for (auto& b : kim) b.release();
     rhot_hyd_vi.release(); vi_scratch.release();
     for (DevBuf* b : {&dens_hyd, &pres_hyd, &therm_hyd, &rtot, &cvtot, &cptot, &gsqrt, &g13, &g23, &gsqrtH, &dphydx, &dphydy,
-                      &coriolis, &escale, &fscale, &pres, &w3, &Jac, &zlev, &mon})
+                      &coriolis, &escale, &fscale, &pres, &w3, &Jac, &zlev, &mon, &g2d})
       b->release();
     if (stream) cudaStreamDestroy(stream);
   }
@@ -249,6 +250,38 @@ int fedg_create(const fedg_mesh_desc* d, fedg_ctx** out) {
   for (size_t n = 0; n < c->nall && !terrain; ++n)
     if (d->Gsqrt[n] != 1.0 || d->GI3[n] != 0.0 || d->GI3[size_t(Np) * d->NeA + n] != 0.0) terrain = true;
   for (size_t n = 0; n < size_t(Nfp) * c->Ne2D && !terrain; ++n) if (d->GsqrtH[n] != 1.0) terrain = true;
+  // ---- cubed-sphere panel tile: the horizontal Jacobian lives in 2D tables, the kernels take the flat-geometry path
+  if (d->panelID != 0) {
+    if (d->panelID < 1 || d->panelID > 6 || !d->GIJ || !d->gam || !d->pos2D) return fail(FEDG_ERR_ARG, "panelID set but GIJ / gam / pos2D missing");
+    if (np != 8) return fail(FEDG_ERR_UNSUPPORTED, "the global equation set is built for p = 7 only");
+    const size_t n2 = size_t(Nfp) * c->Ne2D;
+    for (int ke = 0; ke < Ne; ++ke)
+      for (int p = 0; p < Np; ++p) {
+        const size_t i = size_t(ke) * Np + p;
+        const double gh = d->GsqrtH[size_t(d->EMap3Dto2D[ke] - 1) * Nfp + (p % Nfp)];
+        if (d->gam[i] != 1.0 || d->GI3[i] != 0.0 || d->GI3[size_t(Np) * d->NeA + i] != 0.0 || d->Gsqrt[i] != gh)
+          return fail(FEDG_ERR_UNSUPPORTED, "global panel: only the shallow-atmosphere metric without topography is available (gam = 1, GI3 = 0, Gsqrt = GsqrtH)");
+      }
+    for (size_t h = c->nint; h < c->nall; ++h) {   // fill_halo_metric: halo metric = own face value
+      const long src = long(d->VMapB[h - c->nint]) - 1;
+      if (d->Gsqrt[h] != d->Gsqrt[src]) return fail(FEDG_ERR_UNSUPPORTED, "global panel: halo Gsqrt must equal the own face value");
+    }
+    std::vector<double> g2(6 * n2);
+    for (size_t i = 0; i < n2; ++i) {
+      g2[i] = d->GsqrtH[i];
+      g2[n2 + i] = d->GIJ[i];                 // (1,1)
+      g2[2 * n2 + i] = d->GIJ[2 * n2 + i];    // (1,2): Fortran (Nfp,Ne2D,2,2) -> offset ((j-1)*2 + (i-1)) * n2
+      g2[3 * n2 + i] = d->GIJ[3 * n2 + i];    // (2,2)
+      g2[4 * n2 + i] = std::tan(d->pos2D[i]);
+      g2[5 * n2 + i] = std::tan(d->pos2D[n2 + i]);
+      if (std::fabs(d->GIJ[n2 + i] - d->GIJ[2 * n2 + i]) > 1e-14 * std::fabs(d->GIJ[i])) return fail(FEDG_ERR_ARG, "GIJ is not symmetric");
+    }
+    c->global = true; c->panel = d->panelID;
+    terrain = false;
+    c->g2d.n = 0;
+    { cudaError_t e = c->g2d.alloc(g2.size()); if (e != cudaSuccess) return fail(FEDG_ERR_CUDA, cudaGetErrorString(e)); }
+    { cudaError_t e = cudaMemcpy(c->g2d.p, g2.data(), g2.size() * sizeof(double), cudaMemcpyHostToDevice); if (e != cudaSuccess) return fail(FEDG_ERR_CUDA, cudaGetErrorString(e)); }
+  }
   c->terrain = terrain;
 
   // ---- connectivity (to 0-based) and the same-rank halo source map
@@ -299,6 +332,7 @@ int fedg_create(const fedg_mesh_desc* d, fedg_ctx** out) {
   if ((rc = upload(cc, c->w3, d->IntWeight_lgl, Np))) return rc;
   if ((rc = upload(cc, c->Jac, d->J, c->nint))) return rc;
   if ((rc = upload(cc, c->zlev, d->zlev, c->nint))) return rc;
+  if (c->global) { if ((rc = upload(cc, c->gsqrt, d->Gsqrt, c->nall))) return rc; }   // weights of the modal filter / monitors
   if (terrain) {
     if ((rc = upload(cc, c->gsqrt, d->Gsqrt, c->nall))) return rc;
     if ((rc = upload(cc, c->g13, d->GI3, c->nall))) return rc;
@@ -374,7 +408,12 @@ int fedg_dyn_init(fedg_ctx* c, const char* eqs_type, const char* tinteg_type, do
   std::string eqs(eqs_type);
   if (eqs == "NONHYDRO3D_HEVE") c->hevi = false;
   else if (eqs == "NONHYDRO3D_HEVI") c->hevi = true;
-  else return fail(FEDG_ERR_UNSUPPORTED, "EQS_TYPE " + eqs + " is not available in this build (NONHYDRO3D_HEVE, NONHYDRO3D_HEVI)");
+  else if (eqs == "GLOBALNONHYDRO3D_HEVI") {
+    if (!c->global) return fail(FEDG_ERR_ARG, "GLOBALNONHYDRO3D_HEVI needs a cubed-sphere panel mesh (fedg_mesh_desc.panelID)");
+    c->hevi = true;
+  }
+  else return fail(FEDG_ERR_UNSUPPORTED, "EQS_TYPE " + eqs + " is not available in this build (NONHYDRO3D_HEVE, NONHYDRO3D_HEVI, GLOBALNONHYDRO3D_HEVI)");
+  if (c->global && eqs != "GLOBALNONHYDRO3D_HEVI") return fail(FEDG_ERR_ARG, "a cubed-sphere panel mesh runs GLOBALNONHYDRO3D_HEVI only");
   if (!c->rk.init(tinteg_type)) return fail(FEDG_ERR_ARG, std::string("unsupported TINTEG_TYPE ") + tinteg_type);
   if (!(dt > 0.0)) return fail(FEDG_ERR_ARG, "dt must be positive");
   c->dt = dt;
@@ -535,6 +574,7 @@ void fill_stage_params(fedg_ctx* c, StageParams& P, int in, int out, int q0) {
   P.pres_out = c->pres.p; P.dpin = c->dp[in].p; P.dpout = c->dp[out].p; P.tab = c->d_tab;
   P.c = c->c; P.Ne = c->Ne; P.Ne2D = c->Ne2D;
   P.has_cor = c->has_cor; P.has_phyd = c->has_phyd; P.do_filter = 0; P.write_pres = 0;
+  P.g2d = c->g2d.p; P.OHM = c->OHM; P.is_global = c->global; P.panel = c->panel;
   { static int fp = -1; if (fp < 0) { const char* e = getenv("FEDG_FAST_POW"); fp = (e && e[0] == '1') ? 1 : 0; } P.fast_pow = fp; }
 }
 
@@ -603,7 +643,7 @@ int run_steps_hevi(fedg_ctx* c, int nsteps, size_t& iev, long& launches) {
     if (c->modalfilter) {
       double* q[NVAR];
       for (int v = 0; v < NVAR; ++v) q[v] = c->prog[in][v].p;
-      launch_modal_filter5(q, c->gsqrt.p, c->terrain, c->Ne, c->np, c->stream);
+      launch_modal_filter5(q, c->gsqrt.p, c->terrain || c->global, c->Ne, c->np, c->stream);
       launches += 1;
     }
     c->cur = in;
@@ -799,7 +839,7 @@ int fedg_monitor(fedg_ctx* c, double* out) {
   c->dp_valid[c->cur] = true;
   const double* q[NVAR];
   for (int v = 0; v < NVAR; ++v) q[v] = c->prog[c->cur][v].p;
-  launch_monitor(q, c->dens_hyd.p, c->pres.p, c->rtot.p, c->moist, c->w3.p, c->Jac.p, c->gsqrt.p, c->terrain, c->zlev.p, c->c,
+  launch_monitor(q, c->dens_hyd.p, c->pres.p, c->rtot.p, c->moist, c->w3.p, c->Jac.p, c->gsqrt.p, c->terrain || c->global, c->zlev.p, c->c,
                  c->Np, c->Ne, c->mon.p, c->stream);
   CUDA_TRY(cudaMemcpyAsync(out, c->mon.p, 5 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   CUDA_TRY(cudaStreamSynchronize(c->stream));

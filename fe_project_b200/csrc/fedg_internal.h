@@ -64,6 +64,11 @@ struct StageParams {
   const int* elem_list;  // when non-null: process elements elem_list[0..nelem) (interior / tile-boundary split)
   int nelem;
   int has_cor, has_phyd, do_filter, write_pres, fast_pow;
+  // global (cubed-sphere panel) equation set: 2D metric tables [6][Ne2D*Nfp] = GsqrtH, G11, G12, G22, X = tan(alpha),
+  // Y = tan(beta); planetary rotation rate; panel id 1..6
+  const double* g2d;
+  double OHM;
+  int is_global, panel;
 };
 
 struct HaloParams {

@@ -42,7 +42,7 @@ __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b)
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
-template <bool TERRAIN, bool MOIST, bool HEVI>
+template <bool TERRAIN, bool MOIST, bool HEVI, bool GLOBAL>
 __global__ void __launch_bounds__(256, 3) stage_p7_kernel(const __grid_constant__ StageParams P) {
   using namespace p7;
   const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
@@ -100,6 +100,20 @@ __global__ void __launch_bounds__(256, 3) stage_p7_kernel(const __grid_constant_
     G23n = *reinterpret_cast<const double2*>(P.g23 + gn);
     gH = *reinterpret_cast<const double2*>(P.gsqrtH + size_t(ke2d) * N2 + 2 * t + 8 * g);
   }
+  // global equation set: horizontal metric of the own two nodes (2D tables, the same for every plane k)
+  double2 G11n = make_double2(1.0, 1.0), G12n = make_double2(0.0, 0.0), G22n = make_double2(1.0, 1.0), Xn = make_double2(0.0, 0.0),
+          Yn = make_double2(0.0, 0.0);
+  const size_t n2d = size_t(P.Ne2D) * N2;
+  if (GLOBAL) {
+    const size_t h = size_t(ke2d) * N2 + 2 * t + 8 * g;
+    Gn = *reinterpret_cast<const double2*>(P.g2d + h);
+    gH = Gn;
+    G11n = *reinterpret_cast<const double2*>(P.g2d + n2d + h);
+    G12n = *reinterpret_cast<const double2*>(P.g2d + 2 * n2d + h);
+    G22n = *reinterpret_cast<const double2*>(P.g2d + 3 * n2d + h);
+    Xn = *reinterpret_cast<const double2*>(P.g2d + 4 * n2d + h);
+    Yn = *reinterpret_cast<const double2*>(P.g2d + 5 * n2d + h);
+  }
   // exterior-side gather of this thread's first face node, issued while the bulk copies are in flight
   const size_t fb = size_t(ke) * NFT;
   RawSide<TERRAIN> pre;
@@ -154,6 +168,16 @@ __global__ void __launch_bounds__(256, 3) stage_p7_kernel(const __grid_constant_
       if (pass == 0) ex = pre; else ex.load(P, size_t(P.vmapP[fb + m]));
       double GsM = 1.0, G13M = 0.0, G23M = 0.0;
       if (TERRAIN) { GsM = P.gsqrt[eb + nloc]; G13M = P.g13[eb + nloc]; G23M = P.g23[eb + nloc]; }
+      double fG11 = 1.0, fG12 = 0.0, fG22 = 1.0;
+      if (GLOBAL) {
+        // Gsqrt of both sides: own 2D node; the neighbour's own value inside the tile, the own value in the halo
+        // (fill_halo_metric, mesh_cubedspheredom3d.F90:657-678)
+        const size_t h = size_t(ke2d) * N2 + (nloc & 63);
+        GsM = P.g2d[h]; fG11 = P.g2d[n2d + h]; fG12 = P.g2d[2 * n2d + h]; fG22 = P.g2d[3 * n2d + h];
+        const size_t iP = size_t(P.vmapP[fb + m]);
+        ex.Gs = GsM;
+        if (iP < size_t(P.Ne) * N3) ex.Gs = P.g2d[size_t(P.emap2d[iP >> 9]) * N2 + (iP & 63)];
+      }
       FaceSide M, Q;
       make_side<TERRAIN>(M, sStash[0 * N3 + nloc], sStash[1 * N3 + nloc], sStash[2 * N3 + nloc], sStash[3 * N3 + nloc],
                          sStash[4 * N3 + nloc], sStash[5 * N3 + nloc], sStash[6 * N3 + nloc], sStash[7 * N3 + nloc],
@@ -161,6 +185,16 @@ __global__ void __launch_bounds__(256, 3) stage_p7_kernel(const __grid_constant_
       make_side<TERRAIN>(Q, ex.dd, ex.mx, ex.my, ex.mz, ex.dr, ex.dh, ex.ph, ex.th, ex.dp, ex.Gs, ex.G13, ex.G23);
       const double hf = P.fscale[size_t(f) * P.Ne + ke] * 0.5;
       double o5[NVAR];
+      if (GLOBAL) {
+        switch (f) {
+          case 0: rusanov_global<1>(M, Q, -1.0, gamm, hf, fG11, fG12, fG22, o5); break;
+          case 1: rusanov_global<0>(M, Q, 1.0, gamm, hf, fG11, fG12, fG22, o5); break;
+          case 2: rusanov_global<1>(M, Q, 1.0, gamm, hf, fG11, fG12, fG22, o5); break;
+          case 3: rusanov_global<0>(M, Q, -1.0, gamm, hf, fG11, fG12, fG22, o5); break;
+          case 4: rusanov_global<2>(M, Q, -1.0, gamm, hf, fG11, fG12, fG22, o5); break;
+          default: rusanov_global<2>(M, Q, 1.0, gamm, hf, fG11, fG12, fG22, o5); break;
+        }
+      } else
       switch (f) {
         case 0: rusanov<1, TERRAIN, HEVI>(M, Q, -1.0, gamm, hf, o5); break;
         case 1: rusanov<0, TERRAIN, HEVI>(M, Q, 1.0, gamm, hf, o5); break;
@@ -177,8 +211,10 @@ __global__ void __launch_bounds__(256, 3) stage_p7_kernel(const __grid_constant_
   // per-node flux building blocks
   double2 RGv = make_double2(1.0, 1.0), RGs = make_double2(1.0, 1.0);
   if (TERRAIN) { RGv.x = 1.0 / (Gn.x / gH.x); RGv.y = 1.0 / (Gn.y / gH.y); RGs.x = 1.0 / Gn.x; RGs.y = 1.0 / Gn.y; }
+  if (GLOBAL) { RGs.x = 1.0 / Gn.x; RGs.y = 1.0 / Gn.y; }   // GsqrtV = 1: RGv stays 1
   const double2 fx0 = make_double2(Gn.x * mx.x, Gn.y * mx.y), fy0 = make_double2(Gn.x * my.x, Gn.y * my.y);
   double2 fz0 = mz;
+  if (GLOBAL) fz0 = make_double2(Gn.x * mz.x, Gn.y * mz.y);
   if (TERRAIN) {
     fz0.x = Gn.x * (mz.x * RGv.x + G13n.x * mx.x + G23n.x * my.x);
     fz0.y = Gn.y * (mz.y * RGv.y + G13n.y * mx.y + G23n.y * my.y);
@@ -239,8 +275,15 @@ __global__ void __launch_bounds__(256, 3) stage_p7_kernel(const __grid_constant_
     if (v == V_DDENS) { Fx = fx0; Fy = fy0; q = dd; }
     else if (v == V_DRHOT) { Fx = make_double2(fx0.x * pt.x, fx0.y * pt.y); Fy = make_double2(fy0.x * pt.x, fy0.y * pt.y); q = dr; }
     else if (v == V_MOMZ) { Fx = make_double2(fx0.x * ww.x, fx0.y * ww.y); Fy = make_double2(fy0.x * ww.x, fy0.y * ww.y); q = mz; }
-    else if (v == V_MOMX) { Fx = make_double2(fx0.x * uu.x + GP.x, fx0.y * uu.y + GP.y); Fy = make_double2(fy0.x * uu.x, fy0.y * uu.y); q = mx; }
-    else { Fx = make_double2(fx0.x * vv.x, fx0.y * vv.y); Fy = make_double2(fy0.x * vv.x + GP.x, fy0.y * vv.y + GP.y); q = my; }
+    else if (v == V_MOMX) {
+      if (GLOBAL) { Fx = make_double2(fx0.x * uu.x + G11n.x * GP.x, fx0.y * uu.y + G11n.y * GP.y); Fy = make_double2(fy0.x * uu.x + G12n.x * GP.x, fy0.y * uu.y + G12n.y * GP.y); }
+      else { Fx = make_double2(fx0.x * uu.x + GP.x, fx0.y * uu.y + GP.y); Fy = make_double2(fy0.x * uu.x, fy0.y * uu.y); }
+      q = mx;
+    } else {
+      if (GLOBAL) { Fx = make_double2(fx0.x * vv.x + G12n.x * GP.x, fx0.y * vv.y + G12n.y * GP.y); Fy = make_double2(fy0.x * vv.x + G22n.x * GP.x, fy0.y * vv.y + G22n.y * GP.y); }
+      else { Fx = make_double2(fx0.x * vv.x, fx0.y * vv.y); Fy = make_double2(fy0.x * vv.x + GP.x, fy0.y * vv.y + GP.y); }
+      q = my;
+    }
     __syncwarp();   // previous variable's fragment reads of the planes are done
     *reinterpret_cast<double2*>(sPx + ownP) = Fx;
     *reinterpret_cast<double2*>(sPy + ownP) = Fy;
@@ -269,7 +312,29 @@ __global__ void __launch_bounds__(256, 3) stage_p7_kernel(const __grid_constant_
     const double2 div = make_double2(c0 * RGs.x, c1 * RGs.y);
     double2 tend;
     if (v == V_MOMZ) tend = HEVI ? make_double2(-div.x, -div.y) : make_double2(-div.x - P.c.GRAV * drho.x, -div.y - P.c.GRAV * drho.y);
-    else if (v == V_MOMX) {
+    else if (GLOBAL && (v == V_MOMX || v == V_MOMY)) {
+      // pressure-gradient of the background, metric (Christoffel) and Coriolis terms, globalnonhydro3d_rhot_hevi.F90:535-566
+      double2 phx = make_double2(0.0, 0.0), phy = make_double2(0.0, 0.0);
+      if (P.has_phyd) { phx = *reinterpret_cast<const double2*>(P.dphydx + gn); phy = *reinterpret_cast<const double2*>(P.dphydy + gn); }
+      const double sg = (P.panel == 6) ? -1.0 : 1.0;
+      const bool p14 = P.panel <= 4;
+      double r[2];
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        const double X = c ? Xn.y : Xn.x, Y = c ? Yn.y : Yn.x, MX = c ? mx.y : mx.x, MY = c ? my.y : my.x;
+        const double u = c ? uu.y : uu.x, w_ = c ? vv.y : vv.x;
+        const double g11 = c ? G11n.y : G11n.x, g12 = c ? G12n.y : G12n.x, g22 = c ? G22n.y : G22n.x;
+        const double px = c ? phx.y : phx.x, py = c ? phy.y : phy.x;
+        const double two = 2.0 / (1.0 + X * X + Y * Y);
+        double cori;
+        if (v == V_MOMX) cori = sg * P.OHM * two * (-X * Y * MX + (1.0 + Y * Y) * MY);
+        else cori = sg * P.OHM * two * (-(1.0 + X * X) * MX + X * Y * MY);
+        if (p14) cori = sg * Y * cori;
+        if (v == V_MOMX) r[c] = -(g11 * px + g12 * py) - two * Y * (X * Y * u - (1.0 + Y * Y) * w_) * MX + cori;
+        else r[c] = -(g12 * px + g22 * py) - two * X * (-(1.0 + X * X) * u + X * Y * w_) * MY + cori;
+      }
+      tend = make_double2(r[0] - div.x, r[1] - div.y);
+    } else if (v == V_MOMX) {
       double2 ph = make_double2(0.0, 0.0);
       if (P.has_phyd) ph = *reinterpret_cast<const double2*>(P.dphydx + gn);
       tend = make_double2((-ph.x + cor.x * my.x) - div.x, (-ph.y + cor.y * my.y) - div.y);
@@ -362,21 +427,23 @@ __global__ void __launch_bounds__(256, 3) stage_p7_kernel(const __grid_constant_
 void launch_stage_p7(const StageParams& p, bool terrain, bool moist, bool hevi, cudaStream_t s) {
   const size_t shmem = p7::SMEM_BYTES;
   dim3 grid(p.elem_list ? p.nelem : p.Ne), block(256);
-#define FEDG_LAUNCH(T, M, H)                                                                                  \
-  do {                                                                                                        \
-    static bool attr_set = false;                                                                             \
-    if (!attr_set) {                                                                                          \
-      cudaFuncSetAttribute(stage_p7_kernel<T, M, H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem); \
-      attr_set = true;                                                                                        \
-    }                                                                                                         \
-    stage_p7_kernel<T, M, H><<<grid, block, shmem, s>>>(p);                                                   \
+#define FEDG_LAUNCH(T, M, H, G)                                                                                  \
+  do {                                                                                                           \
+    static bool attr_set = false;                                                                                \
+    if (!attr_set) {                                                                                             \
+      cudaFuncSetAttribute(stage_p7_kernel<T, M, H, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem); \
+      attr_set = true;                                                                                           \
+    }                                                                                                            \
+    stage_p7_kernel<T, M, H, G><<<grid, block, shmem, s>>>(p);                                                   \
   } while (0)
-  if (hevi) {
-    if (terrain) { if (moist) FEDG_LAUNCH(true, true, true); else FEDG_LAUNCH(true, false, true); }
-    else { if (moist) FEDG_LAUNCH(false, true, true); else FEDG_LAUNCH(false, false, true); }
+  if (p.is_global) {   // GLOBALNONHYDRO3D_HEVI (flat, shallow atmosphere: enforced at fedg_create / fedg_dyn_init)
+    if (moist) FEDG_LAUNCH(false, true, true, true); else FEDG_LAUNCH(false, false, true, true);
+  } else if (hevi) {
+    if (terrain) { if (moist) FEDG_LAUNCH(true, true, true, false); else FEDG_LAUNCH(true, false, true, false); }
+    else { if (moist) FEDG_LAUNCH(false, true, true, false); else FEDG_LAUNCH(false, false, true, false); }
   } else {
-    if (terrain) { if (moist) FEDG_LAUNCH(true, true, false); else FEDG_LAUNCH(true, false, false); }
-    else { if (moist) FEDG_LAUNCH(false, true, false); else FEDG_LAUNCH(false, false, false); }
+    if (terrain) { if (moist) FEDG_LAUNCH(true, true, false, false); else FEDG_LAUNCH(true, false, false, false); }
+    else { if (moist) FEDG_LAUNCH(false, true, false, false); else FEDG_LAUNCH(false, false, false, false); }
   }
 #undef FEDG_LAUNCH
 }

@@ -59,6 +59,11 @@ class AtmDynDGMDriver_nonhydro3d:
         keep["zlev"] = _f64(mesh.zlev)
         keep["VMapM"], keep["VMapP"] = mesh.abi_vmapM(), mesh.abi_vmapP()
         keep["VMapB"], keep["EMap3Dto2D"] = mesh.abi_vmapB(), mesh.abi_emap3dto2d()
+        if getattr(mesh, "panelID", 0):      # cubed-sphere panel tile: Fortran shapes (Nfp,Ne2D,2,2), (Np,NeA), (Nfp,Ne2D,2)
+            keep["GIJ"] = _f64(mesh.GIJ.transpose(1, 0, 2, 3))
+            keep["gam"] = _f64(mesh.gam)
+            keep["pos2D"] = _f64(mesh.pos2D)
+            d.panelID = int(mesh.panelID)
         for k, a in keep.items():
             setattr(d, k, a.ctypes.data_as(C.c_void_p))
         tile_rank = tile_rank or (lambda pi, pj: my_rank)

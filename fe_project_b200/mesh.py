@@ -209,3 +209,57 @@ class LocalMeshCube:
     def abi_vmapP(self): return (self.VMapP + 1).astype(np.int32)
     def abi_vmapB(self): return (self.VMapB + 1).astype(np.int32)
     def abi_emap3dto2d(self): return (self.EMap3Dto2D + 1).astype(np.int32)
+
+
+class LocalMeshCubedSpherePanel(LocalMeshCube):
+    """One whole panel of `MeshCubedSphereDom3D` as a single tile (shallow-atmosphere approximation, no topography).
+
+    In the reference a panel is a cube mesh in the central angles (alpha, beta) in [-pi/4, pi/4]^2 and z
+    (`MeshCubedSphereDom3D_coord_conv`, FElib/src/mesh/scale_mesh_cubedspheredom3d.F90:527-565), so everything of
+    `LocalMeshCube` carries over; on top of it come the horizontal metric of the equiangular gnomonic map
+    (`CubedSphereCoordCnv_GetMetric`, FElib/src/common/scale_cubedsphere_coord_cnv.F90:735-787) and
+    `MeshCubedSphereDom3D_set_metric` (scale_mesh_cubedspheredom3d.F90:599-655): `G_ij, GIJ, GsqrtH` on the 2D nodes,
+    `gam = 1`, `Gsqrt(:,ke) = GsqrtH(IndexH2Dto3D, ke2D)`, halo metric = own face value (`fill_halo_metric`, :657-678).
+    The lateral halo of the tile holds its own face values: the panel-edge exchange is not part of this class."""
+
+    def __init__(self, elem: HexElement, panelID: int, NeX: int, NeY: int, NeZ: int, ztop: float, RPlanet: float,
+                 FZ: np.ndarray | None = None):
+        q = 0.25 * np.pi
+        super().__init__(elem, NeX, NeY, NeZ, -q, q, -q, q, 0.0, ztop, FZ=FZ, periodic=(False, False, False))
+        assert 1 <= panelID <= 6
+        self.panelID, self.RPlanet = int(panelID), float(RPlanet)
+        Np, Nfp, Ne = elem.Np, elem.Nfp, self.Ne
+        # 2D nodes = bottom-layer elements, k = 0 plane
+        a = self.pos_en[0][: self.Ne2D, :Nfp]
+        b = self.pos_en[1][: self.Ne2D, :Nfp]
+        self.pos2D = np.stack([a, b])                     # (2, Ne2D, Nfp)
+        X, Y = np.tan(a), np.tan(b)
+        r2 = 1.0 + X ** 2 + Y ** 2
+        ox, oy = 1.0 + X ** 2, 1.0 + Y ** 2
+        fac = ox * oy * (RPlanet / r2) ** 2
+        self.G_ij = np.empty((2, 2, self.Ne2D, Nfp))
+        self.G_ij[0, 0], self.G_ij[0, 1], self.G_ij[1, 0], self.G_ij[1, 1] = fac * ox, -fac * (X * Y), -fac * (X * Y), fac * oy
+        self.GsqrtH = RPlanet ** 2 * ox * oy / (r2 * np.sqrt(r2))
+        f2 = 1.0 / self.GsqrtH ** 2
+        self.GIJ = np.empty((2, 2, self.Ne2D, Nfp))
+        self.GIJ[0, 0], self.GIJ[0, 1], self.GIJ[1, 0], self.GIJ[1, 1] = (f2 * self.G_ij[1, 1], -f2 * self.G_ij[0, 1],
+                                                                        -f2 * self.G_ij[1, 0], f2 * self.G_ij[0, 0])
+        self.gam = np.ones((self.NeA, Np))
+        self.Gsqrt = np.ones((self.NeA, Np))
+        self.Gsqrt[:Ne] = self.GsqrtH[self.EMap3Dto2D][:, elem.IndexH2Dto3D]
+        g = self.Gsqrt.reshape(-1)
+        halo = self.VMapP >= Ne * Np
+        g[self.VMapP[halo]] = g[self.VMapM[halo]]
+        if self.panelID <= 4:
+            # CubedSphereCoordCnv_CS2LonLatPos, equatorial panels (scale_cubedsphere_coord_cnv.F90:106-119)
+            self.lon2D = a + 0.5 * np.pi * (self.panelID - 1)
+            self.lat2D = np.arctan(np.tan(b) * np.cos(a))
+
+    def lonlat_to_cs_vec(self, u_lon, v_lat):
+        """CubedSphereCoordCnv_LonLat2CSVec for an equatorial panel (scale_cubedsphere_coord_cnv.F90:349-369), on the 2D
+        nodes: physical (zonal, meridional) components -> contravariant (alpha, beta) components, gam = 1."""
+        assert self.panelID <= 4
+        X, Y = np.tan(self.pos2D[0]), np.tan(self.pos2D[1])
+        del2 = 1.0 + X ** 2 + Y ** 2
+        uc = u_lon / np.cos(self.lat2D)
+        return uc / self.RPlanet, (X * Y * uc + del2 / np.sqrt(1.0 + X ** 2) * v_lat) / (self.RPlanet * (1.0 + Y ** 2))

@@ -79,6 +79,15 @@ typedef struct fedg_mesh_desc {
   int vel_bc[6];
   /* SCALE constants (scale_const), passed in: GRAV may be overridden by PARAM_CONST */
   double GRAV, Rdry, CPdry, CVdry, PRES00, OHM;
+  /* Cubed-sphere panel tile (MeshCubedSphereDom3D, mesh/scale_mesh_cubedspheredom3d.F90:599-678); all NULL / 0 for a
+   * regional mesh.  panelID 1..6; GIJ: lcmesh%GIJ (Nfp_v,Ne2D,2,2) contravariant horizontal metric; gam (Np,NeA);
+   * pos2D: lcmesh2D%pos_en (Nfp_v,Ne2D,2) = central angles (alpha, beta).  Gsqrt, GsqrtH above carry the horizontal
+   * Jacobian.  This build covers the shallow-atmosphere approximation without topography (gam = 1, GI3 = 0,
+   * Gsqrt = GsqrtH on the 3D nodes); anything else is rejected with FEDG_ERR_UNSUPPORTED. */
+  const double* GIJ;
+  const double* gam;
+  const double* pos2D;
+  int panelID;
 } fedg_mesh_desc;
 
 const char* fedg_last_error(void);
@@ -89,7 +98,9 @@ int fedg_create(const fedg_mesh_desc* desc, fedg_ctx** out);
 void fedg_destroy(fedg_ctx* ctx);
 
 /* AtmDynDGMDriver_nonhydro3d%Init: fluid_dyn_solver/scale_atm_dyn_dgm_driver_nonhydro3d.F90:355-594
- * eqs_type: "NONHYDRO3D_HEVE" | "NONHYDRO3D_HEVI" (p = 7, flat mesh); tinteg_type: a timeint_rk scheme name
+ * eqs_type: "NONHYDRO3D_HEVE" | "NONHYDRO3D_HEVI" (p = 7, flat mesh) | "GLOBALNONHYDRO3D_HEVI" (p = 7, cubed-sphere
+ * panel tile: fluid_dyn_solver/scale_atm_dyn_dgm_globalnonhydro3d_rhot_hevi.F90:337-583, 873-1066, flux
+ * scale_atm_dyn_dgm_nonhydro3d_rhot_hevi_numflux.F90:606-834); tinteg_type: a timeint_rk scheme name
  * (common/scale_timeint_rk_butcher_tab.F90:27-67).  filter_h1D / filter_v1D are the (np,np) matrices
  * MFilter_h1D and MFilter_v1D of Setup_ModalFilter (tensorprod3D.F90.erb:160-181, 460-505); pass
  * NULL when modalfilter_flag == 0. */

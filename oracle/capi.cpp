@@ -34,6 +34,18 @@ void* feo_create(int p, int lumped, int NeX, int NeY, int NeZ, const double* dom
   if (rc) { delete h; return nullptr; }
   return h;
 }
+// one cubed-sphere panel tile: (alpha, beta) in [-pi/4, pi/4]^2, z in [0, ztop] (or FZ), shallow-atmosphere metric
+void* feo_create_panel(int p, int lumped, int panelID, int NeX, int NeY, int NeZ, double ztop, const double* FZ, double radius, int shallow) {
+  Handle* h = nullptr;
+  int rc = guard([&] {
+    h = new Handle;
+    h->d.elem.init(p, lumped != 0);
+    h->d.mesh.init_cubedsphere_panel(h->d.elem, panelID, NeX, NeY, NeZ, FZ, ztop, radius, shallow != 0);
+    h->d.st.alloc(size_t(h->d.elem.Np) * h->d.mesh.NeA, size_t(h->d.elem.Nfp) * h->d.mesh.Ne2D);
+  });
+  if (rc) { delete h; return nullptr; }
+  return h;
+}
 void feo_destroy(void* hv) { delete static_cast<Handle*>(hv); }
 // element / mesh of a handle, for the sample restatements that live on the same mesh (advect3d.cpp)
 const void* feo_elem_ptr(void* hv) { return &static_cast<Handle*>(hv)->d.elem; }
@@ -61,6 +73,9 @@ double* feo_array(void* hv, const char* name, long* n) {
   else if (s == "nz") v = &d.mesh.nz; else if (s == "Fscale") v = &d.mesh.Fscale;
   else if (s == "Gsqrt") v = &d.mesh.Gsqrt; else if (s == "G13") v = &d.mesh.G13; else if (s == "G23") v = &d.mesh.G23;
   else if (s == "GsqrtH") v = &d.mesh.GsqrtH;
+  else if (s == "gam") v = &d.mesh.gam; else if (s == "alpha2D") v = &d.mesh.alpha2D; else if (s == "beta2D") v = &d.mesh.beta2D;
+  else if (s == "GIJ11") v = &d.mesh.GIJ11; else if (s == "GIJ12") v = &d.mesh.GIJ12; else if (s == "GIJ22") v = &d.mesh.GIJ22;
+  else if (s == "Gij11") v = &d.mesh.Gij11; else if (s == "Gij12") v = &d.mesh.Gij12; else if (s == "Gij22") v = &d.mesh.Gij22;
   else if (s == "DDENS") v = &d.st.DDENS; else if (s == "MOMX") v = &d.st.MOMX; else if (s == "MOMY") v = &d.st.MOMY;
   else if (s == "MOMZ") v = &d.st.MOMZ; else if (s == "DRHOT") v = &d.st.DRHOT;
   else if (s == "DENS_hyd") v = &d.st.DENS_hyd; else if (s == "PRES_hyd") v = &d.st.PRES_hyd;
@@ -96,8 +111,14 @@ int feo_setup_dyn(void* hv, const char* eqs, const char* tinteg, double dt, int 
   return guard([&] {
     auto& d = h->d;
     std::string e(eqs);
+    d.global = false;
     if (e == "NONHYDRO3D_HEVE") d.hevi = false; else if (e == "NONHYDRO3D_HEVI") d.hevi = true;
+    else if (e == "GLOBALNONHYDRO3D_HEVI") {
+      if (!d.mesh.is_global) throw std::runtime_error("GLOBALNONHYDRO3D_HEVI needs a cubed-sphere panel mesh");
+      d.hevi = true; d.global = true;
+    }
     else throw std::runtime_error("unsupported EQS_TYPE " + e);
+    if (d.mesh.is_global && !d.global) throw std::runtime_error("a cubed-sphere panel mesh needs GLOBALNONHYDRO3D_HEVI");
     d.tint.init(tinteg, dt, 5, size_t(d.elem.Np) * d.mesh.NeA);
     if (d.hevi != d.tint.sc.imex) throw std::runtime_error("HEVI needs an IMEX scheme and HEVE an explicit one");
     d.modalfilter = modalfilter != 0;
@@ -150,7 +171,8 @@ int feo_stage_piece(void* hv, const char* what) {
     else if (w == "bc") apply_bc_progvars(d.elem, d.mesh, d.bnd, d.st);
     else if (w == "tend_ex") {
       double* out[5]; for (int v = 0; v < 5; ++v) out[v] = d.tint.tend_ex_buf(v, 0);
-      if (d.hevi) hevi_cal_tend(d.elem, d.mesh, d.cst, d.st, out); else heve_cal_tend(d.elem, d.mesh, d.cst, d.st, out);
+      if (d.global) global_hevi_cal_tend(d.elem, d.mesh, d.cst, d.st, out);
+      else if (d.hevi) hevi_cal_tend(d.elem, d.mesh, d.cst, d.st, out); else heve_cal_tend(d.elem, d.mesh, d.cst, d.st, out);
     }
     else if (w == "modalfilter") modalfilter_apply(d.elem, d.mesh, d.st);
     else throw std::runtime_error("unknown piece " + w);

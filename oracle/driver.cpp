@@ -25,7 +25,9 @@ void Driver::update() {
     apply_bc_progvars(elem, mesh, bnd, st);                                            // :797
     double* out[5];
     for (int v = 0; v < 5; ++v) out[v] = tint.tend_ex_buf(v, ind);
-    if (hevi) hevi_cal_tend(elem, mesh, cst, st, out); else heve_cal_tend(elem, mesh, cst, st, out);  // :815
+    if (global) global_hevi_cal_tend(elem, mesh, cst, st, out);
+    else if (hevi) hevi_cal_tend(elem, mesh, cst, st, out);
+    else heve_cal_tend(elem, mesh, cst, st, out);                                       // :815
     for (int v : rkvar) tint.advance(stage, st.prog(v), v, 0, nint);                   // :920
   }
   if (modalfilter) modalfilter_apply(elem, mesh, st);                                  // :940-951

@@ -514,8 +514,11 @@ void hevi_cal_vi(const Element& e, const Mesh& m, const Consts& c, const DynStat
   w.GsqrtV.resize(nint);
   for (vec* x : {&w.DENS, &w.W, &w.WT, &w.POT, &w.DPDRHOT, &w.t_dens, &w.t_momz, &w.t_rhot, &w.t_momx, &w.t_momy}) x->assign(nint, 0.0);
   for (int ke = 0; ke < m.Ne; ++ke)
-    for (int p = 0; p < Np; ++p)
-      w.GsqrtV[size_t(ke) * Np + p] = m.Gsqrt[size_t(ke) * Np + p] / m.GsqrtH[(p % Nfp) + size_t(m.emap2d[ke]) * Nfp];
+    for (int p = 0; p < Np; ++p) {
+      // regional: Gsqrt / GsqrtH (rhot_hevi.F90:864); global: Gsqrt / (gam^2 GsqrtH) (globalnonhydro3d_rhot_hevi.F90:965)
+      const double g2 = m.is_global ? m.gam[size_t(ke) * Np + p] * m.gam[size_t(ke) * Np + p] : 1.0;
+      w.GsqrtV[size_t(ke) * Np + p] = m.Gsqrt[size_t(ke) * Np + p] / (g2 * m.GsqrtH[(p % Nfp) + size_t(m.emap2d[ke]) * Nfp]);
+    }
   const double* cur[5];
   cur[DENS_VID] = s.DDENS.data(); cur[RHOT_VID] = s.DRHOT.data(); cur[MOMZ_VID] = s.MOMZ.data();
   cur[MOMX_VID] = s.MOMX.data(); cur[MOMY_VID] = s.MOMY.data();

@@ -100,6 +100,14 @@ struct Mesh {
   void init_cube(const Element& e, int nex, int ney, int nez, double xmin, double xmax, double ymin,
                  double ymax, double zmin, double zmax, const double* FZ, const bool per[3]);
   void exchange_halo(const Element& e, double* field) const;  // single-tile Put/Exchange/Get
+  // cubed-sphere panel tile (mesh/scale_mesh_cubedspheredom3d.F90): cube mesh in (alpha, beta, z) + horizontal metric
+  bool is_global = false;
+  int panelID = 0;
+  double RPlanet = 0.0;
+  vec alpha2D, beta2D, Gij11, Gij12, Gij22, GIJ11, GIJ12, GIJ22;   // (Nfp,Ne2D)
+  vec gam;                                                           // (Np,NeA)
+  void init_cubedsphere_panel(const Element& e, int panel, int nex, int ney, int nez, const double* FZ, double ztop,
+                              double radius, bool shallow);
 };
 
 // ---------------------------------------------------------------- time integrator (a13)
@@ -163,6 +171,10 @@ void hevi_cal_tend(const Element& e, const Mesh& m, const Consts& c, const DynSt
 void hevi_cal_vi(const Element& e, const Mesh& m, const Consts& c, const DynState& s, const double* var0[5],
                  double impl_fac, double dt, double* dt5[5]);
 
+// global (cubed-sphere) HEVI: explicit part (dyn_global.cpp); the column solve is hevi_cal_vi
+void global_hevi_numflux_generalhvc(const Element& e, const Mesh& m, const Consts& c, const DynState& s, vec& del_flux);
+void global_hevi_cal_tend(const Element& e, const Mesh& m, const Consts& c, const DynState& s, double* dt5[5]);
+
 struct Driver {
   Element elem;
   Mesh mesh;
@@ -170,7 +182,7 @@ struct Driver {
   BndCfg bnd;
   DynState st;
   TimeIntRK tint;
-  bool hevi = false, modalfilter = false;
+  bool hevi = false, modalfilter = false, global = false;
   void update();  // fluid_dyn_solver/scale_atm_dyn_dgm_driver_nonhydro3d.F90:614-963
 };
 

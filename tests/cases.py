@@ -5,7 +5,7 @@ import numpy as np
 
 from fe_project_b200 import initcond
 from fe_project_b200.element import HexElement
-from fe_project_b200.mesh import LocalMeshCube
+from fe_project_b200.mesh import LocalMeshCube, LocalMeshCubedSpherePanel
 
 C0 = initcond.SCALE_CONST
 SLIP6 = dict(south="SLIP", east="SLIP", north="SLIP", west="SLIP", btm="SLIP", top="SLIP")
@@ -84,6 +84,70 @@ class SoundWaveCase(DensityCurrentCase):
         self.consts = dict(C0, GRAV=0.0)
         self.fields = initcond.sound_wave(self.mesh, amplitude=amplitude)
         self.vel_bc = SLIP6
+
+
+class GlobalPanelCase(DensityCurrentCase):
+    """One cubed-sphere panel (GLOBALNONHYDRO3D_HEVI, shallow atmosphere, no topography; BASELINE config 4 in small):
+    isothermal hydrostatic background, solid-body zonal flow u = u0 cos(lat) in gradient-wind balance on an equatorial
+    panel plus a smooth 3D perturbation, so that every metric, Coriolis and pressure-gradient term is exercised.  The
+    lateral halo of the tile holds its own face values (no panel-edge exchange in this scope)."""
+
+    def __init__(self, p=7, panelID=1, NeX=2, NeY=2, NeZ=3, ztop=30.0e3, dt=20.0, tinteg="IMEX_ARK324", modalfilter=True,
+                 u0=30.0, T0=300.0, perturb=1.0, OHM=None, balanced=True):
+        self.p, self.dt, self.tinteg, self.modalfilter = p, dt, tinteg, modalfilter
+        self.eqs = "GLOBALNONHYDRO3D_HEVI"
+        self.periodic = (False, False, False)
+        self.NprcX = self.NprcY = 1
+        self.pi = self.pj = 0
+        self.panelID, self.ztop = panelID, ztop
+        self.elem = HexElement(p)
+        self.consts = dict(C0) if OHM is None else dict(C0, OHM=OHM)
+        c = self.consts
+        self.mesh = m = LocalMeshCubedSpherePanel(self.elem, panelID, NeX, NeY, NeZ, ztop, c["RPlanet"])
+        Ne, Np, NeA = m.Ne, self.elem.Np, m.NeA
+        z = m.pos_en[2]
+        h2 = self.elem.IndexH2Dto3D
+        lat = m.lat2D[m.EMap3Dto2D][:, h2]
+        # background: isothermal, function of z only
+        H = c["Rdry"] * T0 / c["GRAV"]
+        pres_hyd = c["PRES00"] * np.exp(-z / H)
+        dens_hyd = pres_hyd / (c["Rdry"] * T0)
+        # balanced state: ln p = ln p_hyd(z) - (u0^2 + 2 a Omega u0) sin^2(lat) / (2 R T0), T = T0
+        amp = (u0 ** 2 + 2.0 * c["RPlanet"] * c["OHM"] * u0) / (2.0 * c["Rdry"] * T0) if balanced else 0.0
+        pres = pres_hyd * np.exp(-amp * np.sin(lat) ** 2)
+        dens = pres / (c["Rdry"] * T0)
+        theta = T0 * (c["PRES00"] / pres) ** (c["Rdry"] / c["CPdry"])
+        rhot_hyd = c["PRES00"] / c["Rdry"] * (pres_hyd / c["PRES00"]) ** (c["CVdry"] / c["CPdry"])
+        ua, ub = m.lonlat_to_cs_vec(u0 * np.cos(m.lat2D), np.zeros_like(m.lat2D))
+        f = {k: np.zeros((NeA, Np)) for k in ("DDENS", "MOMX", "MOMY", "MOMZ", "DRHOT", "DENS_hyd", "PRES_hyd")}
+        f["DENS_hyd"][:Ne] = dens_hyd
+        f["PRES_hyd"][:Ne] = pres_hyd
+        f["DDENS"][:Ne] = dens - dens_hyd
+        f["DRHOT"][:Ne] = dens * theta - rhot_hyd
+        f["MOMX"][:Ne] = dens * ua[m.EMap3Dto2D][:, h2]
+        f["MOMY"][:Ne] = dens * ub[m.EMap3Dto2D][:, h2]
+        if perturb:
+            a, b = m.pos_en[0], m.pos_en[1]
+            R = c["RPlanet"]
+            f["MOMX"][:Ne] += perturb * dens * (3.0 / R) * np.sin(3 * a) * np.cos(2 * b) * np.cos(np.pi * z / ztop)
+            f["MOMY"][:Ne] += perturb * dens * (2.0 / R) * np.cos(2 * a + 0.3) * np.sin(3 * b + 0.1) * np.cos(np.pi * z / ztop)
+            f["MOMZ"][:Ne] += perturb * dens * 0.05 * np.sin(2 * a) * np.cos(3 * b) * np.sin(np.pi * z / ztop)
+            f["DRHOT"][:Ne] += perturb * 0.5 * dens * np.cos(3 * a) * np.cos(2 * b) * np.sin(2 * np.pi * z / ztop)
+        self.fields = f
+        self.vel_bc = dict(btm="SLIP", top="SLIP")
+
+    def make_oracle(self):
+        from oracle_api import Oracle
+        m, c = self.mesh, self.consts
+        o = Oracle(self.p, m.NeX, m.NeY, m.NeZ, panel=dict(panelID=self.panelID, ztop=self.ztop, RPlanet=c["RPlanet"]))
+        o.set_consts(c)
+        for k, v in self.fields.items():
+            o.arr(k)[:] = v.reshape(-1)
+        o.arr("Rtot")[:] = c["Rdry"]; o.arr("CVtot")[:] = c["CVdry"]; o.arr("CPtot")[:] = c["CPdry"]
+        mf = (2.0 / 3.0, 1.0, 16, 2.0 / 3.0, 1.0, 16)
+        o.setup_dyn(self.eqs, self.tinteg, self.dt, self.modalfilter, mf, (0, 0, 0, 0, 2, 2))
+        o.prepare()
+        return o
 
 
 def rel_l2(a, b):

@@ -26,6 +26,8 @@ def lib():
         L = C.CDLL(build_oracle())
         L.feo_create.restype = C.c_void_p
         L.feo_create.argtypes = [C.c_int] * 5 + [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.feo_create_panel.restype = C.c_void_p
+        L.feo_create_panel.argtypes = [C.c_int] * 6 + [C.c_double, C.c_void_p, C.c_double, C.c_int]
         L.feo_destroy.argtypes = [C.c_void_p]
         L.feo_dims.argtypes = [C.c_void_p, C.c_void_p]
         L.feo_array.restype = C.POINTER(C.c_double)
@@ -74,12 +76,17 @@ def _p(a):
 class Oracle:
     """One single-tile regional run of the CPU restatement."""
 
-    def __init__(self, p, NeX, NeY, NeZ, dom, periodic=(False, False, False), lumped=False, FZ=None):
+    def __init__(self, p, NeX, NeY, NeZ, dom=None, periodic=(False, False, False), lumped=False, FZ=None, panel=None):
+        """panel = dict(panelID, ztop, RPlanet): one cubed-sphere panel tile instead of a regional cube."""
         L = lib()
-        dom = np.asarray(dom, dtype=np.float64)
-        per = np.asarray(periodic, dtype=np.int32)
         fz = None if FZ is None else np.ascontiguousarray(FZ, dtype=np.float64)
-        self.h = L.feo_create(p, int(lumped), NeX, NeY, NeZ, _p(dom), _p(fz), _p(per))
+        if panel is not None:
+            self.h = L.feo_create_panel(p, int(lumped), int(panel["panelID"]), NeX, NeY, NeZ, float(panel["ztop"]), _p(fz),
+                                        float(panel["RPlanet"]), 1)
+        else:
+            dom = np.asarray(dom, dtype=np.float64)
+            per = np.asarray(periodic, dtype=np.int32)
+            self.h = L.feo_create(p, int(lumped), NeX, NeY, NeZ, _p(dom), _p(fz), _p(per))
         if not self.h:
             raise RuntimeError(L.feo_last_error().decode())
         d = np.zeros(8, dtype=np.int32)
