@@ -23,6 +23,9 @@ import sys
 import tempfile
 import time
 
+# NCCL writes its banner / debug lines to stdout by default: the contract is ONE JSON line on stdout
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 for _p in (ROOT, os.path.join(ROOT, "tests")):
     if _p not in sys.path:
@@ -132,6 +135,64 @@ def run_reference(args, rank, world):
     print(json.dumps(line))
 
 
+def run_advect3d(args):
+    """configs[0]: sample/advect3d, 8x8x8 elements p=3, ERK_4s4o, dt 0.008 (test.conf); one variable."""
+    import torch
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    from fe_project_b200.advect3d import Advect3D, gaussian_hill
+    from fe_project_b200.element import HexElement
+    from fe_project_b200.mesh import LocalMeshCube
+    ne = (8, 8, 8)
+    e = HexElement(3)
+    mesh = LocalMeshCube(e, *ne, 0, 1, 0, 1, 0, 1, periodic=(True, True, True))
+    g = Advect3D(e, mesh, "ERK_4s4o", 0.008)
+    q = gaussian_hill(mesh)
+    u = np.zeros_like(q); u[:mesh.Ne] = 0.5
+    g.set(q, u, u, u)
+    W, K = max(3, args.warmup), args.steps
+    g.update(W)
+    sampler = ClockSampler(0); sampler.start(); time.sleep(0.12)
+    g.update(K)
+    tm = g.last_timing()
+    clocks = sampler.stop()
+    dof = e.Np * mesh.Ne
+    value = dof * K / (tm["ms_total"] * 1e-3)
+    # e2e: host q in, K2 steps, host q out per call (the sample keeps q on the host between history writes)
+    t0 = time.perf_counter()
+    for _ in range(5):
+        g.set(q, u, u, u); g.update(10); q2 = g.get()
+    t_e2e = (time.perf_counter() - t0) / 5
+    nbytes = 4 * q.size * 8
+    cpu = None
+    if not args.no_cpu_baseline:
+        from oracle_api import Oracle, OracleAdvect3D
+        o = Oracle(3, *ne, (0, 1, 0, 1, 0, 1), periodic=(True, True, True))
+        a = OracleAdvect3D(o, "ERK_4s4o", 0.008)
+        a.arr("q")[:] = q.reshape(-1)
+        for nm in "uvw":
+            a.arr(nm)[:] = u.reshape(-1)
+        a.update(10)
+        t0 = time.perf_counter(); a.update(2000); dtc = time.perf_counter() - t0
+        cpu = dict(value=dof * 2000 / dtc, unit=UNIT, cores=os.cpu_count(), kind="port", sample="the full case, 2000 steps")
+    # dominant kernel: advect_stage_kernel; algorithmic bytes per node and stage: q, u, v, w, q0, varTmp in + q, varTmp out
+    peak, peak_src = read_peaks()
+    alg = 8 * 8.0 * dof
+    ms_stage = tm["ms_total"] / (K * 4)
+    print(json.dumps(dict(
+        metric=METRIC.replace("nonhydro3d p=7", "advect3d p=3"), value=value, unit=UNIT, n_gpus=1, steps=K, warmup=W,
+        ms_per_step=tm["ms_total"] / K, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64", data="synthetic",
+        config=dict(workload="sample/advect3d 8x8x8 elements p=3, ERK_4s4o, dt=0.008, gaussian hill, u=v=w=0.5, triply periodic",
+                    dof=dof, l2_policy="the whole case (1 MB) is L2 resident by construction: launch-latency bound, one CUDA graph per step"),
+        clocks=clocks, e2e=dict(value=dof * 10 / t_e2e, unit=UNIT, h2d_bytes_per_step=nbytes // 10, d2h_bytes_per_step=q.size * 8 // 10, steps_per_call=10),
+        gpu_launches=tm["launches"],
+        roofline=dict(bound="hbm", achieved=alg / (ms_stage * 1e-3) / 1e9, peak=peak, unit="GB/s", frac=alg / (ms_stage * 1e-3) / 1e9 / peak,
+                      traffic=None, kernel="advect_stage_kernel (halo kernel + stage kernel per RK stage, graph replay)", ms_per_launch=ms_stage,
+                      algorithmic_bytes_per_launch=alg, peak_source=peak_src,
+                      note="512 elements = 128 blocks < 148 SMs: the case cannot fill the device; the number documents launch latency"),
+        cpu_baseline=cpu, finite=bool(np.isfinite(q2).all()))))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -143,12 +204,18 @@ def main():
     ap.add_argument("--nez", type=int, default=WORKLOAD["NeZ"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--eqs", default="heve", choices=["heve", "hevi"], help="hevi: NONHYDRO3D_HEVI + IMEX_ARK324 (extra, not the headline)")
+    ap.add_argument("--workload", default="density_current", choices=["density_current", "sound_wave", "global_panel", "advect3d"],
+                    help="density_current = BASELINE configs[2] (headline); the others are extra measurement lines: sound_wave = "
+                         "configs[1] rate variant 16x16x16, global_panel = one 32x32x12 panel of configs[3], advect3d = configs[0]")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         run_reference(args, rank, world)
+        return
+    if args.workload == "advect3d":
+        run_advect3d(args)
         return
 
     import torch
@@ -173,11 +240,25 @@ def main():
     pi, pj = rank % NX, rank // NX
     x0, x1, y0, y1, z0, z1 = WORKLOAD["dom"]
     dom = (x0, x0 + (x1 - x0) * NX, y0, y0 + (y1 - y0) * NY, z0, z1)
-    hevi = args.eqs == "hevi"
-    case = DensityCurrentCase(p=WORKLOAD["p"], NeX=args.nex, NeY=args.ney, NeZ=args.nez, dom=dom,
-                              dt=(2.0 * WORKLOAD["dt"] if hevi else WORKLOAD["dt"]), tinteg=("IMEX_ARK324" if hevi else WORKLOAD["tinteg"]),
-                              modalfilter=True, NprcX=NX, NprcY=NY, pi=pi, pj=pj,
-                              eqs=("NONHYDRO3D_HEVI" if hevi else "NONHYDRO3D_HEVE"))
+    hevi = args.eqs == "hevi" or args.workload != "density_current"
+    wl_name = WORKLOAD["name"]
+    if args.workload == "density_current":
+        case = DensityCurrentCase(p=WORKLOAD["p"], NeX=args.nex, NeY=args.ney, NeZ=args.nez, dom=dom,
+                                  dt=(2.0 * WORKLOAD["dt"] if hevi else WORKLOAD["dt"]), tinteg=("IMEX_ARK324" if hevi else WORKLOAD["tinteg"]),
+                                  modalfilter=True, NprcX=NX, NprcY=NY, pi=pi, pj=pj,
+                                  eqs=("NONHYDRO3D_HEVI" if hevi else "NONHYDRO3D_HEVE"))
+    else:
+        if world > 1:
+            raise SystemExit("the extra workloads are single-GPU measurement lines")
+        from cases import SoundWaveCase, GlobalPanelCase
+        if args.workload == "sound_wave":     # configs[1]: sample/euler3d_hevi, rate variant 16x16x16
+            args.nex = args.ney = args.nez = 16
+            case = SoundWaveCase(p=7, NeX=16, NeY=16, NeZ=16, dt=0.015, tinteg="IMEX_ARK232", amplitude=1.0e-3)
+            wl_name = "sample/euler3d_hevi sound wave (library HEVI path)"
+        else:                                  # configs[3]: one panel of the 6x32x32x12 cubed sphere
+            args.nex, args.ney, args.nez = 32, 32, 12
+            case = GlobalPanelCase(p=7, NeX=32, NeY=32, NeZ=12, dt=5.0, tinteg="IMEX_ARK324", modalfilter=True)
+            wl_name = "atm_nonhydro3d global, one cubed-sphere panel (lateral halo = own face values)"
     d = case.make_driver(None)
     if world > 1:
         def bcast(raw):
@@ -185,7 +266,7 @@ def main():
             dist.broadcast_object_list(obj, src=0)
             return obj[0]
         d.init_comm(rank, world, bcast)
-    if world == 1:   # horizontally uniform background: DPhydDx/y vanish to round-off; single tile keeps the set-up path exercised
+    if world == 1 and args.workload == "density_current":   # horizontally uniform background: DPhydDx/y vanish to round-off; single tile keeps the set-up path exercised
         gx, gy = calc_phyd_hgrad(case.elem, case.mesh, case.fields["PRES_hyd"])
         d.set_phyd_hgrad(gx, gy)
     Np, Ne = case.elem.Np, case.mesh.Ne
@@ -253,8 +334,8 @@ def main():
         line = dict(
             metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=K, warmup=W, ms_per_step=ms_total / K,
             higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64", data="synthetic",
-            config=dict(workload=f"{WORKLOAD['name']}, {args.nex}x{args.ney}x{args.nez} elements per GPU p=7, {case.eqs}, "
-                                 f"{case.tinteg}, dt={case.dt}, modal filter on, slip walls x/z, periodic y, tiles {NX}x{NY}",
+            config=dict(workload=f"{wl_name}, {args.nex}x{args.ney}x{args.nez} elements per GPU p=7, {case.eqs}, "
+                                 f"{case.tinteg}, dt={case.dt}, modal filter {'on' if case.modalfilter else 'off'}, tiles {NX}x{NY}",
                         dof=dof, l2_policy="inputs larger than L2 (67 MB per field, >1 GB touched per stage)",
                         specialisation="flat mesh (Gsqrt=1, GI3=0) and dry thermodynamics detected at registration; "
                                        "roofline uses the unspecialised 232 B/node/stage"),
@@ -264,11 +345,13 @@ def main():
                            algorithmic_bytes_per_launch=alg_bytes, peak_source=peak_src) if not hevi else
                       # vertical-implicit column solve: FP64 bound.  Algorithmic flops of the reference algorithm per
                       # column-element: 24x24 LU 9.2 kflop + 4 RHS substitutions 4.6 kflop + coupling
-                      # elimination 0.6 kflop + the 8x8 (u,v) system 0.7 kflop = 15.1 kflop
+                      # elimination 0.6 kflop + the 8x8 (u,v) system 0.7 kflop = 15.1 kflop.  The kernel eliminates DDENS
+                      # first and pivots on the 16x16 remainder: 11.0 kflop per column-element (reduced_flops_per_launch);
+                      # ms_per_launch averages the implicit stages and the explicit-evaluation stage of the scheme
                       dict(bound="fp64", achieved=15.1e3 * Ne * 64 / (ms_stage * 1e-3) / 1e12, peak=34.07, unit="TFLOP/s",
                            frac=15.1e3 * Ne * 64 / (ms_stage * 1e-3) / 1e12 / 34.07, traffic=None,
-                           kernel="vi_column_kernel (8-lane Gauss-Jordan block-Thomas)", ms_per_launch=ms_stage,
-                           algorithmic_flops_per_launch=15.1e3 * Ne * 64,
+                           kernel="vi_column_kernel (DDENS eliminated, 16x16 partial-pivot Gauss-Jordan, block-Thomas)", ms_per_launch=ms_stage,
+                           algorithmic_flops_per_launch=15.1e3 * Ne * 64, reduced_flops_per_launch=11.0e3 * Ne * 64,
                            peak_source="measured DFMA peak, profiles/r01_fp64_peak.txt")),
             cpu_baseline=cpu, finite=bool(finite))
         print(json.dumps(line))

@@ -635,16 +635,12 @@ int run_steps_hevi(fedg_ctx* c, int nsteps, size_t& iev, long& launches) {
         L.coef[L.nterm] = ce; L.coef[L.nterm + 1] = ci;
         L.nterm += 2;
       }
-      launch_lincomb(L, c->stream);
+      // the last stage's combination carries the modal filter of the step (driver_nonhydro3d.F90:940-951)
+      if (s == ns - 1 && c->modalfilter) launch_lincomb_filter(L, c->d_tab, c->gsqrt.p, c->terrain || c->global, c->Ne, c->np, c->stream);
+      else launch_lincomb(L, c->stream);
       c->dp_valid[nxt] = false;
       launches += 4;
       in = nxt;
-    }
-    if (c->modalfilter) {
-      double* q[NVAR];
-      for (int v = 0; v < NVAR; ++v) q[v] = c->prog[in][v].p;
-      launch_modal_filter5(q, c->gsqrt.p, c->terrain || c->global, c->Ne, c->np, c->stream);
-      launches += 1;
     }
     c->cur = in;
   }

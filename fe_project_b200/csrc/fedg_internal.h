@@ -132,12 +132,15 @@ cudaError_t launch_ell_spmv(int M, int N, int col_size, const double* val, const
 
 void launch_vi(const VIParams& p, bool moist, cudaStream_t s);
 void launch_lincomb(const LinCombParams& L, cudaStream_t s);
+void launch_lincomb_filter(const LinCombParams& L, const ElemTables* tab, const double* gsqrt, bool weighted, int Ne, int np,
+                           cudaStream_t s);
 void launch_modal_filter5(double* const q[NVAR], const double* gsqrt, bool terrain, int Ne, int np, cudaStream_t s);
 
 // halo exchange over NCCL (halo_comm.cu)
 struct RemoteFace {
   int f = 0, peer = 0, peer_face = 0, off = 0, cnt = 0;   // own face id, neighbour rank, its face id, halo offset / node count
   double* sendbuf = nullptr;                               // [6][cnt]
+  double* recvbuf = nullptr;                               // [6][cnt]
 };
 struct CommState {
   bool active = false;

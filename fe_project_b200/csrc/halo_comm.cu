@@ -1,12 +1,14 @@
 // Face-halo exchange between tiles on different GPUs: NCCL send/recv over NVLink (replaces MeshFieldCommBase
 // Put / Exchange / Get over MPI, FElib/src/data/scale_meshfieldcomm_base.F90:58-139, 870-884).
 //
-// Per exchange and remote tile face: one pack kernel gathers the face nodes of the six travelling fields (five
-// prognostic variables + DPRES) through VMapB into a contiguous device buffer (extract_bounddata,
-// scale_meshfieldcomm_base.F90:617-687); ncclSend ships it; the matching ncclRecv writes straight into the halo slots
-// of the receiver's field arrays (halo slots of a tile face are contiguous, scale_meshutil_3d.F90:570-602), so there
-// is no unpack kernel.  All sends and receives of one exchange form one NCCL group on a dedicated stream so that the
-// interior elements can be processed meanwhile (HIDE_MPI_COMM_FLAG semantics, driver_nonhydro3d.F90:859-895).
+// Per exchange: ONE pack kernel gathers, for every remote tile face, the face nodes of the six travelling fields (five
+// prognostic variables + DPRES) through VMapB into that face's contiguous send buffer (extract_bounddata,
+// scale_meshfieldcomm_base.F90:617-687); ONE ncclSend / ncclRecv pair per face ships the six fields as a single message
+// (the first version sent every field separately and wrote straight into the halo slots: 12 point-to-point operations
+// per face, whose latency -- about 60 us per face and stage at 8 GPUs -- was not hidden); ONE unpack kernel on the
+// communication stream scatters the receive buffers into the halo slots (set_bounddata, :690-760).  The group runs on
+// a dedicated high-priority stream while the interior elements are processed (HIDE_MPI_COMM_FLAG semantics,
+// driver_nonhydro3d.F90:859-895).
 //
 // NCCL point-to-point operations carry no tags (the reference tags messages with 10*tileID+faceID): messages between
 // one pair of ranks match in posting order.  Sends are posted in ascending order of the sender's face id, receives in
@@ -57,14 +59,35 @@ struct NcclApi {
 };
 NcclApi g_nccl;
 
-// gather the face nodes of six fields into buf[field][m]
-__global__ void pack_face_kernel(const double* q0, const double* q1, const double* q2, const double* q3, const double* q4, const double* dp,
-                                 const int* __restrict__ vmapB, int off, int cnt, double* __restrict__ buf) {
-  const int m = blockIdx.x * blockDim.x + threadIdx.x;
-  if (m >= cnt) return;
-  const int src = vmapB[off + m];
-  buf[m] = q0[src]; buf[cnt + m] = q1[src]; buf[2 * cnt + m] = q2[src]; buf[3 * cnt + m] = q3[src]; buf[4 * cnt + m] = q4[src];
-  buf[5 * size_t(cnt) + m] = dp[src];
+struct FaceSet {            // the remote faces of a tile (at most four lateral ones)
+  double* buf[6];
+  int off[6], cnt[6], start[7];   // halo offset / node count per face, prefix sum of cnt
+  int n;
+};
+struct SixFields { double* f[6]; };
+
+// gather the face nodes of six fields into sendbuf[face][field][m]
+__global__ void pack_faces_kernel(SixFields q, const int* __restrict__ vmapB, FaceSet fs) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= fs.start[fs.n]) return;
+  int i = 0;
+  while (g >= fs.start[i + 1]) ++i;
+  const int m = g - fs.start[i], cnt = fs.cnt[i];
+  const int src = vmapB[fs.off[i] + m];
+  double* buf = fs.buf[i];
+#pragma unroll
+  for (int v = 0; v < 6; ++v) buf[size_t(v) * cnt + m] = q.f[v][src];
+}
+// scatter recvbuf[face][field][m] into the halo slots of the six fields
+__global__ void unpack_faces_kernel(SixFields q, size_t nint, FaceSet fs) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= fs.start[fs.n]) return;
+  int i = 0;
+  while (g >= fs.start[i + 1]) ++i;
+  const int m = g - fs.start[i], cnt = fs.cnt[i];
+  const double* buf = fs.buf[i];
+#pragma unroll
+  for (int v = 0; v < 6; ++v) q.f[v][nint + fs.off[i] + m] = buf[size_t(v) * cnt + m];
 }
 }  // namespace
 
@@ -92,11 +115,16 @@ int comm_init(CommState& cs, const void* id128, int rank, int nranks, const int 
     RemoteFace& rf = cs.face[cs.nremote++];
     rf.f = f; rf.peer = nbr_rank[f]; rf.peer_face = nbr_face[f]; rf.off = face_off[f]; rf.cnt = face_off[f + 1] - face_off[f];
     if (cudaMalloc(&rf.sendbuf, size_t(6) * rf.cnt * sizeof(double)) != cudaSuccess) { err = "cudaMalloc(sendbuf)"; return FEDG_ERR_CUDA; }
+    if (cudaMalloc(&rf.recvbuf, size_t(6) * rf.cnt * sizeof(double)) != cudaSuccess) { err = "cudaMalloc(recvbuf)"; return FEDG_ERR_CUDA; }
   }
   // receive order: ascending face id of the sender
   for (int i = 0; i < cs.nremote; ++i) cs.recv_order[i] = i;
   std::sort(cs.recv_order, cs.recv_order + cs.nremote, [&](int a, int b) { return cs.face[a].peer_face < cs.face[b].peer_face; });
-  if (cudaStreamCreateWithFlags(&cs.stream, cudaStreamNonBlocking) != cudaSuccess) { err = "cudaStreamCreate(comm)"; return FEDG_ERR_CUDA; }
+  {  // highest priority: the few blocks of the exchange must not queue behind the interior-element grid
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    if (cudaStreamCreateWithPriority(&cs.stream, cudaStreamNonBlocking, hi) != cudaSuccess) { err = "cudaStreamCreate(comm)"; return FEDG_ERR_CUDA; }
+  }
   cudaEventCreateWithFlags(&cs.ev_packed, cudaEventDisableTiming);
   cudaEventCreateWithFlags(&cs.ev_done, cudaEventDisableTiming);
   cs.active = true;
@@ -105,7 +133,7 @@ int comm_init(CommState& cs, const void* id128, int rank, int nranks, const int 
 
 void comm_destroy(CommState& cs) {
   if (!cs.active) return;
-  for (int i = 0; i < cs.nremote; ++i) if (cs.face[i].sendbuf) cudaFree(cs.face[i].sendbuf);
+  for (int i = 0; i < cs.nremote; ++i) { if (cs.face[i].sendbuf) cudaFree(cs.face[i].sendbuf); if (cs.face[i].recvbuf) cudaFree(cs.face[i].recvbuf); }
   if (cs.comm) g_nccl.CommDestroy(static_cast<ncclComm_t>(cs.comm));
   if (cs.stream) cudaStreamDestroy(cs.stream);
   if (cs.ev_packed) cudaEventDestroy(cs.ev_packed);
@@ -118,29 +146,35 @@ void comm_destroy(CommState& cs) {
 int comm_exchange_start(CommState& cs, double* const q[NVAR], double* dp, const int* d_vmapB, size_t nint, cudaStream_t compute,
                         std::string& err) {
   if (!cs.active || cs.nremote == 0) return FEDG_OK;
+  FaceSet snd{}, rcv{};
+  snd.n = rcv.n = cs.nremote;
   for (int i = 0; i < cs.nremote; ++i) {
     const RemoteFace& rf = cs.face[i];
-    pack_face_kernel<<<(rf.cnt + 255) / 256, 256, 0, compute>>>(q[0], q[1], q[2], q[3], q[4], dp, d_vmapB, rf.off, rf.cnt, rf.sendbuf);
+    snd.buf[i] = rf.sendbuf; rcv.buf[i] = rf.recvbuf;
+    snd.off[i] = rcv.off[i] = rf.off; snd.cnt[i] = rcv.cnt[i] = rf.cnt;
+    snd.start[i + 1] = rcv.start[i + 1] = snd.start[i] + rf.cnt;
   }
+  SixFields six{};
+  for (int v = 0; v < NVAR; ++v) six.f[v] = q[v];
+  six.f[5] = dp;
+  const int ntot = snd.start[cs.nremote];
+  pack_faces_kernel<<<(ntot + 255) / 256, 256, 0, compute>>>(six, d_vmapB, snd);
   cudaEventRecord(cs.ev_packed, compute);
   cudaStreamWaitEvent(cs.stream, cs.ev_packed, 0);
   ncclComm_t comm = static_cast<ncclComm_t>(cs.comm);
   ncclResult_t r = g_nccl.GroupStart();
-  for (int i = 0; i < cs.nremote && r == ncclSuccess; ++i) {           // ascending own face id; six messages per face
+  for (int i = 0; i < cs.nremote && r == ncclSuccess; ++i) {           // ascending own face id; one message per face
     const RemoteFace& rf = cs.face[i];
-    for (int v = 0; v < 6 && r == ncclSuccess; ++v)
-      r = g_nccl.Send(rf.sendbuf + size_t(v) * rf.cnt, size_t(rf.cnt), ncclDouble, rf.peer, comm, cs.stream);
+    r = g_nccl.Send(rf.sendbuf, size_t(6) * rf.cnt, ncclDouble, rf.peer, comm, cs.stream);
   }
   for (int oi = 0; oi < cs.nremote && r == ncclSuccess; ++oi) {        // ascending face id of the sender
     const RemoteFace& rf = cs.face[cs.recv_order[oi]];
-    for (int v = 0; v < 6 && r == ncclSuccess; ++v) {
-      double* dst = (v < NVAR ? q[v] : dp) + nint + rf.off;            // halo slots of this face: contiguous
-      r = g_nccl.Recv(dst, size_t(rf.cnt), ncclDouble, rf.peer, comm, cs.stream);
-    }
+    r = g_nccl.Recv(rf.recvbuf, size_t(6) * rf.cnt, ncclDouble, rf.peer, comm, cs.stream);
   }
   ncclResult_t r2 = g_nccl.GroupEnd();
   if (r == ncclSuccess) r = r2;
   if (r != ncclSuccess) { err = std::string("NCCL halo exchange: ") + g_nccl.GetErrorString(r); return FEDG_ERR_COMM; }
+  unpack_faces_kernel<<<(ntot + 255) / 256, 256, 0, cs.stream>>>(six, nint, rcv);
   cudaEventRecord(cs.ev_done, cs.stream);
   return FEDG_OK;
 }

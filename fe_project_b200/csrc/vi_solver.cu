@@ -180,8 +180,10 @@ __device__ __forceinline__ double group_matvec_s(const double* __restrict__ sMT,
   return s;
 }
 
-template <bool MOIST>
-__global__ void __launch_bounds__(VI_THREADS, 3) vi_column_kernel(const __grid_constant__ VIParams P) {
+// IMPLICIT = false is the explicit evaluation k_im = -A_v(q) of a stage with a_im(s,s) = 0 (first stage of the ARK schemes): no
+// elimination code, a fraction of the registers, so it runs at the occupancy of a streaming kernel.
+template <bool MOIST, bool IMPLICIT>
+__global__ void __launch_bounds__(VI_THREADS, IMPLICIT ? 3 : 4) vi_column_kernel(const __grid_constant__ VIParams P) {
   const int tid = threadIdx.x, grp = tid >> 3, l8 = tid & 7;
   const int ncol = P.Ne2D * 64;
   const int col = blockIdx.x * (VI_THREADS / 8) + grp;     // grid is sized so that col < ncol (Ne2D*64 % 16 == 0)
@@ -272,7 +274,7 @@ __global__ void __launch_bounds__(VI_THREADS, 3) vi_column_kernel(const __grid_c
     const double t_w = -(E33 * dz_w + (lw0 * dl_w_b + lw1 * dl_w_t)) - P.c.GRAV * drho;
     const double t_u = -(lw0 * dl_u_b + lw1 * dl_u_t), t_v = -(lw0 * dl_v_b + lw1 * dl_v_t);
 
-    if (ifac == 0.0) {   // explicit evaluation only (first IMEX stage): k_im = -A_v(q)
+    if (!IMPLICIT) {   // explicit evaluation only (first IMEX stage): k_im = -A_v(q)
       P.kim[V_DDENS][n] = t_r; P.kim[V_MOMZ][n] = t_w; P.kim[V_DRHOT][n] = t_t; P.kim[V_MOMX][n] = t_u; P.kim[V_MOMY][n] = t_v;
       __syncwarp();
       if (l8 == 7) { sPrev[0] = q.rho0; sPrev[1] = q.w0; sPrev[2] = q.th0; sPrev[3] = q.pot; sPrev[4] = q.u0; sPrev[5] = q.v0;
@@ -467,7 +469,7 @@ __global__ void __launch_bounds__(VI_THREADS, 3) vi_column_kernel(const __grid_c
     const size_t n = node(kz);
     const double cr = P.qcur[V_DDENS][n], cw = P.qcur[V_MOMZ][n], ct = P.qcur[V_DRHOT][n], cu = P.qcur[V_MOMX][n], cv = P.qcur[V_MOMY][n];
     double qr = cr, qw = cw, qt = ct, qu = cu, qv = cv;
-    if (ifac != 0.0) {
+    if (IMPLICIT) {
       double d[3], gq[3][3];
 #pragma unroll
       for (int v = 0; v < 3; ++v) {
@@ -508,12 +510,15 @@ void launch_vi(const VIParams& p, bool moist, cudaStream_t s) {
   const size_t shmem = (144 + size_t(groups) * VI_SOL + size_t(VI_NQ) * VI_THREADS) * sizeof(double);
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(vi_column_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(shmem));
-    cudaFuncSetAttribute(vi_column_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(shmem));
+    cudaFuncSetAttribute(vi_column_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(shmem));
+    cudaFuncSetAttribute(vi_column_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(shmem));
+    cudaFuncSetAttribute(vi_column_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(shmem));
+    cudaFuncSetAttribute(vi_column_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(shmem));
     attr_set = true;
   }
-  if (moist) vi_column_kernel<true><<<grid, block, shmem, s>>>(p);
-  else vi_column_kernel<false><<<grid, block, shmem, s>>>(p);
+  const bool implicit = p.impl_fac != 0.0;
+  if (moist) { if (implicit) vi_column_kernel<true, true><<<grid, block, shmem, s>>>(p); else vi_column_kernel<true, false><<<grid, block, shmem, s>>>(p); }
+  else { if (implicit) vi_column_kernel<false, true><<<grid, block, shmem, s>>>(p); else vi_column_kernel<false, false><<<grid, block, shmem, s>>>(p); }
 }
 
 // IMEX / general stage combination  q = base + sum_m coef[m] * k[m]  (rk_advance_general2D, scale_timeint_rk.F90:2201-2355,
@@ -528,6 +533,63 @@ __global__ void lincomb_kernel(const __grid_constant__ LinCombParams L) {
     L.out[v][n] = r;
   }
 }
+// Last IMEX stage fused with the modal filter of the step (atm_dyn_dgm_modalfilter_apply, dyn_dgm_modalfilter.F90:49-130,
+// called at driver_nonhydro3d.F90:940-951):  q = F3D(Gsqrt (base + sum coef k)) / Gsqrt.  One block per element, one
+// thread per node, the five variables move through the three 1D passes together (three block barriers per element);
+// the filter tables sit in shared memory transposed so that the lanes of a warp read consecutive words.  Saves the
+// write + read of the unfiltered state and replaces the stand-alone filter kernel (1.04 ms -> inside a 0.5 ms pass).
+__global__ void lincomb_filter_kernel(const __grid_constant__ LinCombParams L, const ElemTables* __restrict__ tab,
+                                      const double* __restrict__ gsqrt, int weighted, int np) {
+  extern __shared__ double sm[];
+  const int N2 = np * np, N3 = N2 * np;
+  double* sFhT = sm;            // sFhT[l*np + i] = Fh[i][l]
+  double* sFvT = sm + N2;
+  double* A = sm + 2 * N2;      // [5][N3]
+  double* B = A + NVAR * N3;    // [5][N3]
+  const int n = threadIdx.x;
+  const int i = n % np, j = (n / np) % np, k = n / N2;
+  if (n < N2) { const int r = n / np, c = n % np; sFhT[c * np + r] = tab->Fh[n]; sFvT[c * np + r] = tab->Fv[n]; }
+  const size_t gi = size_t(blockIdx.x) * N3 + n;
+  const double G = weighted ? gsqrt[gi] : 1.0;
+#pragma unroll
+  for (int v = 0; v < NVAR; ++v) {
+    double r = L.base[v][gi];
+    for (int m = 0; m < L.nterm; ++m) r = r + L.coef[m] * L.k[m][v][gi];
+    A[v * N3 + n] = G * r;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int v = 0; v < NVAR; ++v) {
+    const double* s = A + v * N3 + j * np + k * N2;
+    double a = sFhT[i] * s[0];
+    for (int l = 1; l < np; ++l) a += sFhT[l * np + i] * s[l];
+    B[v * N3 + n] = a;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int v = 0; v < NVAR; ++v) {
+    const double* w = B + v * N3 + i + k * N2;
+    double b = w[0] * sFhT[j];
+    for (int l = 1; l < np; ++l) b += w[l * np] * sFhT[l * np + j];
+    A[v * N3 + n] = b;
+  }
+  __syncthreads();
+  const double rG = 1.0 / G;
+#pragma unroll
+  for (int v = 0; v < NVAR; ++v) {
+    const double* s = A + v * N3 + i + j * np;
+    double r = s[0] * sFvT[k];
+    for (int l = 1; l < np; ++l) r += s[l * N2] * sFvT[l * np + k];
+    L.out[v][gi] = r * rG;
+  }
+}
+void launch_lincomb_filter(const LinCombParams& L, const ElemTables* tab, const double* gsqrt, bool weighted, int Ne, int np,
+                           cudaStream_t s) {
+  const int N3 = np * np * np;
+  const size_t shmem = (size_t(2) * np * np + size_t(2) * NVAR * N3) * sizeof(double);
+  lincomb_filter_kernel<<<Ne, N3, shmem, s>>>(L, tab, gsqrt, weighted ? 1 : 0, np);
+}
+
 void launch_lincomb(const LinCombParams& L, cudaStream_t s) {
   const int block = 256;
   lincomb_kernel<<<unsigned((L.n + block - 1) / block), block, 0, s>>>(L);
