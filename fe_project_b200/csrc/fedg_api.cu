@@ -89,7 +89,8 @@ struct fedg_ctx {
   ElemTables* d_tab = nullptr;
   bool tab_dirty = true;
   DevBuf dens_hyd, pres_hyd, therm_hyd, rtot, cvtot, cptot, gsqrt, g13, g23, gsqrtH, dphydx, dphydy, coriolis;
-  DevBuf escale, fscale, pres, w3, Jac, zlev, mon, g2d;
+  DevBuf escale, fscale, pres, w3, Jac, zlev, mon, g2d, phyt[6];
+  bool has_phyt = false;
   // HEVI: stage tendencies k_ex / k_im [stage][var], var0-based IMEX combination, column-solver scratch
   std::vector<DevBuf> kex, kim;
   DevBuf rhot_hyd_vi, vi_scratch;
@@ -115,6 +116,7 @@ struct fedg_ctx {
     if (d_elem_bnd) cudaFree(d_elem_bnd);
     comm_destroy(comm);
     adv.release();
+    for (auto& b : phyt) b.release();
     for (auto& b : dp) b.release();
     for (auto& s : prog) for (auto& b : s) b.release();
     for (auto& b : vt) b.release();
@@ -520,6 +522,23 @@ int fedg_set_phyd_hgrad(fedg_ctx* c, const double* DPhydDx, const double* DPhydD
   return FEDG_OK;
 }
 
+int fedg_set_phy_tend(fedg_ctx* c, const double* DENS_tp, const double* MOMX_tp, const double* MOMY_tp, const double* MOMZ_tp,
+                      const double* RHOT_tp, const double* RHOH_p) {
+  if (!c) return fail(FEDG_ERR_ARG, "null argument");
+  c->has_phyt = false;
+  const double* h[6] = {DENS_tp, MOMX_tp, MOMY_tp, MOMZ_tp, RHOT_tp, RHOH_p};
+  for (const double* p : h) if (!p) return FEDG_OK;           // NULL: no physics tendencies
+  bool nz = false;                                            // all zero (dry dynamics-only run): skip the six extra reads
+  for (int k = 0; k < 6 && !nz; ++k)
+    for (size_t n = 0; n < c->nint && !nz; ++n) if (h[k][n] != 0.0) nz = true;
+  if (!nz) return FEDG_OK;
+  if (c->global) return fail(FEDG_ERR_UNSUPPORTED, "physics tendencies are not wired into the global equation set yet");
+  for (int k = 0; k < 6; ++k) { int rc = upload(c, c->phyt[k], h[k], c->nint); if (rc) return rc; }
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  c->has_phyt = true;
+  return FEDG_OK;
+}
+
 int fedg_set_coriolis(fedg_ctx* c, const double* cor) {
   if (!c) return fail(FEDG_ERR_ARG, "null argument");
   c->has_cor = false;
@@ -575,6 +594,8 @@ void fill_stage_params(fedg_ctx* c, StageParams& P, int in, int out, int q0) {
   P.c = c->c; P.Ne = c->Ne; P.Ne2D = c->Ne2D;
   P.has_cor = c->has_cor; P.has_phyd = c->has_phyd; P.do_filter = 0; P.write_pres = 0;
   P.g2d = c->g2d.p; P.OHM = c->OHM; P.is_global = c->global; P.panel = c->panel;
+  for (int k = 0; k < 6; ++k) P.phyt[k] = c->phyt[k].p;
+  P.has_phyt = c->has_phyt;
   { static int fp = -1; if (fp < 0) { const char* e = getenv("FEDG_FAST_POW"); fp = (e && e[0] == '1') ? 1 : 0; } P.fast_pow = fp; }
 }
 

@@ -69,6 +69,9 @@ struct StageParams {
   const double* g2d;
   double OHM;
   int is_global, panel;
+  // physics tendencies DENS_tp, MOMX_tp, MOMY_tp, MOMZ_tp, RHOT_tp, RHOH_p (add_phy_tend, driver_nonhydro3d.F90:1098-1178)
+  const double* phyt[6];
+  int has_phyt;
 };
 
 struct HaloParams {

@@ -344,6 +344,18 @@ __global__ void __launch_bounds__(256, 3) stage_p7_kernel(const __grid_constant_
       tend = make_double2((-ph.x - cor.x * mx.x) - div.x, (-ph.y - cor.y * mx.y) - div.y);
     } else tend = make_double2(-div.x, -div.y);
 
+    if (P.has_phyt) {   // add_phy_tend (driver_nonhydro3d.F90:1098-1178), non-conservative form: RHOT_tp + RHOH_p / (CP * EXNER)
+      const int pv = (v == V_DDENS) ? 0 : (v == V_MOMX) ? 1 : (v == V_MOMY) ? 2 : (v == V_MOMZ) ? 3 : 4;
+      const double2 tp = *reinterpret_cast<const double2*>(P.phyt[pv] + gn);
+      tend.x += tp.x; tend.y += tp.y;
+      if (v == V_DRHOT) {
+        const double2 hh = *reinterpret_cast<const double2*>(P.phyt[5] + gn), ph = *reinterpret_cast<const double2*>(P.pres_hyd + gn);
+        double2 R = make_double2(P.c.Rdry, P.c.Rdry), cp = make_double2(P.c.CPdry, P.c.CPdry);
+        if (MOIST) { R = *reinterpret_cast<const double2*>(P.rtot + gn); cp = *reinterpret_cast<const double2*>(P.cptot + gn); }
+        tend.x += hh.x / (cp.x * pow((ph.x + dp.x) * P.c.rP0, R.x / cp.x));
+        tend.y += hh.y / (cp.y * pow((ph.y + dp.y) * P.c.rP0, R.y / cp.y));
+      }
+    }
     if (tend_mode) {
       *reinterpret_cast<double2*>(P.tend_out[v] + gn) = tend;
       continue;

@@ -19,6 +19,7 @@
 // Scope of this kernel: flat MeshCubeDom3D geometry (GsqrtV = 1, G13 = G23 = 0), the configuration the regional
 // HEVI cases run on; terrain-following HEVI is rejected at fedg_dyn_init.
 #include <cstdint>
+#include <cstdlib>
 
 #include "fedg_internal.h"
 
@@ -29,33 +30,49 @@ constexpr unsigned FULL = 0xffffffffu;
 struct NodeQ {            // quantities of one node evaluated on var0 (the Newton linearisation point)
   double rho0, w0, th0, u0, v0;   // DDENS, MOMZ, DRHOT, MOMX, MOMY of var0
   double dens, rhot, pot, wt, dpd, dpres_vol, a;
+  double dpf;                     // face form of the pressure perturbation (vi_cal_del_flux_dyn :1262-1266: dens * pott instead of RHOT)
 };
 
+// raw inputs of one node: var0 (5), DENS_hyd, RHOT_hyd (dry, as the solver recomputes it), PRES_hyd, and for moist runs
+// Rtot, CPtot, CVtot
+struct RawQ {
+  double rho0, w0, th0, u0, v0, dh, rh, ph, R, cp, cv;
+};
 template <bool MOIST>
-__device__ __forceinline__ NodeQ node_q(const VIParams& P, size_t n) {
+__device__ __forceinline__ RawQ raw_load(const VIParams& P, size_t n) {
+  RawQ r;
+  r.rho0 = P.q0[V_DDENS][n]; r.w0 = P.q0[V_MOMZ][n]; r.th0 = P.q0[V_DRHOT][n]; r.u0 = P.q0[V_MOMX][n]; r.v0 = P.q0[V_MOMY][n];
+  r.dh = P.dens_hyd[n]; r.rh = P.rhot_hyd_vi[n]; r.ph = P.pres_hyd[n];
+  r.R = r.cp = r.cv = 0.0;
+  if (MOIST) { r.R = P.rtot[n]; r.cp = P.cptot[n]; r.cv = P.cvtot[n]; }
+  return r;
+}
+template <bool MOIST>
+__device__ __forceinline__ NodeQ node_q(const VIParams& P, const RawQ& r) {
   NodeQ q;
-  q.rho0 = P.q0[V_DDENS][n]; q.w0 = P.q0[V_MOMZ][n]; q.th0 = P.q0[V_DRHOT][n]; q.u0 = P.q0[V_MOMX][n]; q.v0 = P.q0[V_MOMY][n];
-  const double R = MOIST ? P.rtot[n] : P.c.Rdry;
-  const double gm = MOIST ? P.cptot[n] / P.cvtot[n] : P.c.CPovCV;
-  q.dens = P.dens_hyd[n] + q.rho0;
-  q.rhot = P.rhot_hyd_vi[n] + q.th0;
+  q.rho0 = r.rho0; q.w0 = r.w0; q.th0 = r.th0; q.u0 = r.u0; q.v0 = r.v0;
+  const double R = MOIST ? r.R : P.c.Rdry;
+  const double gm = MOIST ? r.cp / r.cv : P.c.CPovCV;
+  q.dens = r.dh + q.rho0;
+  q.rhot = r.rh + q.th0;
   q.pot = q.rhot / q.dens;
   const double ptot = P.c.PRES00 * pow(R * P.c.rP0 * q.rhot, gm);
-  q.dpres_vol = ptot - P.pres_hyd[n];
+  q.dpres_vol = ptot - r.ph;
   q.wt = q.w0 / q.dens;
   q.dpd = gm * ptot / q.rhot;
   const double rdens0 = 1.0 / q.dens;
   q.a = fabs(q.w0 * rdens0) + sqrt(P.c.gamm * ptot * rdens0);
+  q.dpf = P.c.PRES00 * pow(R * P.c.rP0 * q.dens * q.pot, gm) - r.ph;
   return q;
 }
 
-// face form of the pressure perturbation (vi_cal_del_flux_dyn :1262-1266: dens * pott instead of RHOT)
-template <bool MOIST>
-__device__ __forceinline__ double dpres_face(const VIParams& P, size_t n, const NodeQ& q) {
-  const double R = MOIST ? P.rtot[n] : P.c.Rdry;
-  const double gm = MOIST ? P.cptot[n] / P.cvtot[n] : P.c.CPovCV;
-  return P.c.PRES00 * pow(R * P.c.rP0 * q.dens * q.pot, gm) - P.pres_hyd[n];
+// 8-byte asynchronous global -> shared copy (LDGSTS): the forward sweep prefetches the inputs of the next element while
+// the current one is eliminated, without holding them in registers
+__device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst))), "l"(gsrc) : "memory");
 }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 __device__ __forceinline__ double sel3(int s, double a, double b, double c) { return s == 0 ? a : (s == 1 ? b : c); }
 
@@ -157,18 +174,19 @@ constexpr int VI_YROW = 14;       // eliminated DDENS row of a node: [W_0..7 | T
 // warp on distinct banks for the broadcast 128-bit loads
 constexpr int VI_SOL = 96 + 24 + 2 * PROW + VI_PREV + 8 * VI_YROW;
 static_assert(VI_SOL == 292, "bank layout");
-constexpr int VI_NQ = 12;         // doubles of a NodeQ parked in shared memory across the elimination
+constexpr int VI_NQ = 13;         // doubles of a NodeQ parked in shared memory across the elimination
+constexpr int VI_PF = 16;         // prefetch slots per thread: raw inputs of the node two elements up (11) + qcur of the next element (5)
 
 __device__ __forceinline__ void park(double* s, const NodeQ& q) {
   s[0 * VI_THREADS] = q.rho0; s[1 * VI_THREADS] = q.w0; s[2 * VI_THREADS] = q.th0; s[3 * VI_THREADS] = q.u0; s[4 * VI_THREADS] = q.v0;
   s[5 * VI_THREADS] = q.dens; s[6 * VI_THREADS] = q.rhot; s[7 * VI_THREADS] = q.pot; s[8 * VI_THREADS] = q.wt; s[9 * VI_THREADS] = q.dpd;
-  s[10 * VI_THREADS] = q.dpres_vol; s[11 * VI_THREADS] = q.a;
+  s[10 * VI_THREADS] = q.dpres_vol; s[11 * VI_THREADS] = q.a; s[12 * VI_THREADS] = q.dpf;
 }
 __device__ __forceinline__ NodeQ unpark(const double* s) {
   NodeQ q;
   q.rho0 = s[0 * VI_THREADS]; q.w0 = s[1 * VI_THREADS]; q.th0 = s[2 * VI_THREADS]; q.u0 = s[3 * VI_THREADS]; q.v0 = s[4 * VI_THREADS];
   q.dens = s[5 * VI_THREADS]; q.rhot = s[6 * VI_THREADS]; q.pot = s[7 * VI_THREADS]; q.wt = s[8 * VI_THREADS]; q.dpd = s[9 * VI_THREADS];
-  q.dpres_vol = s[10 * VI_THREADS]; q.a = s[11 * VI_THREADS];
+  q.dpres_vol = s[10 * VI_THREADS]; q.a = s[11 * VI_THREADS]; q.dpf = s[12 * VI_THREADS];
   return q;
 }
 
@@ -182,8 +200,8 @@ __device__ __forceinline__ double group_matvec_s(const double* __restrict__ sMT,
 
 // IMPLICIT = false is the explicit evaluation k_im = -A_v(q) of a stage with a_im(s,s) = 0 (first stage of the ARK schemes): no
 // elimination code, a fraction of the registers, so it runs at the occupancy of a streaming kernel.
-template <bool MOIST, bool IMPLICIT>
-__global__ void __launch_bounds__(VI_THREADS, IMPLICIT ? 3 : 4) vi_column_kernel(const __grid_constant__ VIParams P) {
+template <bool MOIST, bool IMPLICIT, int MINB>
+__global__ void __launch_bounds__(VI_THREADS, MINB) vi_column_kernel(const __grid_constant__ VIParams P) {
   const int tid = threadIdx.x, grp = tid >> 3, l8 = tid & 7;
   const int ncol = P.Ne2D * 64;
   const int col = blockIdx.x * (VI_THREADS / 8) + grp;     // grid is sized so that col < ncol (Ne2D*64 % 16 == 0)
@@ -201,6 +219,7 @@ __global__ void __launch_bounds__(VI_THREADS, IMPLICIT ? 3 : 4) vi_column_kernel
   double* sPrev = sRow + 2 * PROW;
   double* sY = sPrev + VI_PREV;
   double* sQ = smem + 144 + size_t(VI_THREADS / 8) * VI_SOL + tid;   // [VI_NQ][VI_THREADS]
+  double* sPF = sQ + size_t(VI_NQ) * VI_THREADS;                      // [VI_PF][VI_THREADS]
   for (int m = tid; m < 144; m += VI_THREADS) {
     if (m < 128) { const int r = (m & 63) >> 3, c = m & 7; smem[(m & 64) + c * 8 + r] = m < 64 ? P.tab->D[m] : P.tab->VP[m - 64]; }
     else smem[m] = P.tab->Lw[m - 128];
@@ -212,18 +231,49 @@ __global__ void __launch_bounds__(VI_THREADS, IMPLICIT ? 3 : 4) vi_column_kernel
   double* scr = P.scratch;   // var3: [kz][12][8][ncol], then uv: [kz][3][8][ncol]
   const size_t scr_uv = size_t(NeZ) * 96 * ncol;
 
-  NodeQ q = node_q<MOIST>(P, node(0));
+  // prefetch (asynchronous copies into this thread's slots of sPF): raw inputs of node(kr), qcur of node(kc)
+  auto prefetch = [&](int kr, int kc) {
+    if (kr < NeZ) {
+      const size_t m = node(kr);
+      cp_async8(sPF + 0 * VI_THREADS, P.q0[V_DDENS] + m); cp_async8(sPF + 1 * VI_THREADS, P.q0[V_MOMZ] + m);
+      cp_async8(sPF + 2 * VI_THREADS, P.q0[V_DRHOT] + m); cp_async8(sPF + 3 * VI_THREADS, P.q0[V_MOMX] + m);
+      cp_async8(sPF + 4 * VI_THREADS, P.q0[V_MOMY] + m); cp_async8(sPF + 5 * VI_THREADS, P.dens_hyd + m);
+      cp_async8(sPF + 6 * VI_THREADS, P.rhot_hyd_vi + m); cp_async8(sPF + 7 * VI_THREADS, P.pres_hyd + m);
+      if (MOIST) { cp_async8(sPF + 8 * VI_THREADS, P.rtot + m); cp_async8(sPF + 9 * VI_THREADS, P.cptot + m); cp_async8(sPF + 10 * VI_THREADS, P.cvtot + m); }
+    }
+    if (IMPLICIT && kc < NeZ) {
+      const size_t m = node(kc);
+      cp_async8(sPF + 11 * VI_THREADS, P.qcur[V_DDENS] + m); cp_async8(sPF + 12 * VI_THREADS, P.qcur[V_MOMZ] + m);
+      cp_async8(sPF + 13 * VI_THREADS, P.qcur[V_DRHOT] + m); cp_async8(sPF + 14 * VI_THREADS, P.qcur[V_MOMX] + m);
+      cp_async8(sPF + 15 * VI_THREADS, P.qcur[V_MOMY] + m);
+    }
+    cp_async_commit();
+  };
+  prefetch(1, 0);
+  NodeQ q = node_q<MOIST>(P, raw_load<MOIST>(P, node(0)));
 
   // ---------------- forward sweep
   for (int kz = 0; kz < NeZ; ++kz) {
     const int ke = ke2d + kz * Ne2D;
     const size_t n = node(kz);
     const bool bot_bc = (kz == 0), top_bc = (kz == NeZ - 1);
+    // inputs of this element arrived while the previous one was eliminated
+    cp_async_wait_all();
     NodeQ qn = q;                                // next element (lookahead); self when at the top
-    if (!top_bc) qn = node_q<MOIST>(P, node(kz + 1));
+    if (!top_bc) {
+      RawQ r;
+      r.rho0 = sPF[0 * VI_THREADS]; r.w0 = sPF[1 * VI_THREADS]; r.th0 = sPF[2 * VI_THREADS]; r.u0 = sPF[3 * VI_THREADS];
+      r.v0 = sPF[4 * VI_THREADS]; r.dh = sPF[5 * VI_THREADS]; r.rh = sPF[6 * VI_THREADS]; r.ph = sPF[7 * VI_THREADS];
+      r.R = r.cp = r.cv = 0.0;
+      if (MOIST) { r.R = sPF[8 * VI_THREADS]; r.cp = sPF[9 * VI_THREADS]; r.cv = sPF[10 * VI_THREADS]; }
+      qn = node_q<MOIST>(P, r);
+    }
+    double cr = 0.0, cw_ = 0.0, ct = 0.0, cu = 0.0, cv = 0.0;   // state entering the stage at the own node
+    if (IMPLICIT) { cr = sPF[11 * VI_THREADS]; cw_ = sPF[12 * VI_THREADS]; ct = sPF[13 * VI_THREADS]; cu = sPF[14 * VI_THREADS]; cv = sPF[15 * VI_THREADS]; }
+    prefetch(kz + 2, kz + 1);
     // face-form pressure of the own end nodes and of the node above
-    const double dpf_own = dpres_face<MOIST>(P, n, q);
-    const double dpf_next = top_bc ? 0.0 : dpres_face<MOIST>(P, node(kz + 1), qn);
+    const double dpf_own = q.dpf;
+    const double dpf_next = top_bc ? 0.0 : qn.dpf;
 
     const double E33 = P.escale[2 * size_t(P.Ne) + ke];
     const double Fs_b = P.fscale[4 * size_t(P.Ne) + ke], Fs_t = P.fscale[5 * size_t(P.Ne) + ke];
@@ -282,7 +332,6 @@ __global__ void __launch_bounds__(VI_THREADS, IMPLICIT ? 3 : 4) vi_column_kernel
       __syncwarp();
       q = qn;
     } else {
-      const double cr = P.qcur[V_DDENS][n], cw_ = P.qcur[V_MOMZ][n], ct = P.qcur[V_DRHOT][n], cu = P.qcur[V_MOMX][n], cv = P.qcur[V_MOMY][n];
       // ---- Jacobian block of this element (construct_matbnd :750-772), rows of the own node.  Unknowns are numbered
       // 3*node + {0: DDENS, 1: MOMZ, 2: DRHOT} in the reference.  The DDENS rows are the identity except in the columns
       // of the two face nodes, so DDENS is eliminated first with two static pivots (rows 0 and 7: the diagonal carries
@@ -291,7 +340,8 @@ __global__ void __launch_bounds__(VI_THREADS, IMPLICIT ? 3 : 4) vi_column_kernel
       // values per lane.  The solution is the reference's (same linear system) up to round-off.
       //   DDENS row l :  rho_l + ra0 rho_0 + ra7 rho_7 + sum_j rW[j] w_j + rT0 theta_0 = rR[0..3]
       //   A2[0] = MOMZ row, A2[1] = DRHOT row over the columns [w_0..7 | theta_0..7 | 4 RHS]; cw / cth = their DDENS columns
-      double ra0 = 0.0, ra7 = 0.0, rT0 = 0.0, rW[8], rR[4], A2[2][20], cw[8], cth[8];
+      double ra0 = 0.0, ra7 = 0.0, rT0 = 0.0, rW[8], rR[4], A2[2][20];
+      double cw0 = 0.0, cth0 = 0.0, cth7 = 0.0;   // face / coupling corrections of the DDENS columns of node 0 and node 7
       const double potl = q.pot, wtl = q.wt, dpdl = q.dpd;
       const double gfac = ifac * P.c.GRAV, dfac = E33 / 1.0 * ifac;
 #pragma unroll
@@ -300,8 +350,8 @@ __global__ void __launch_bounds__(VI_THREADS, IMPLICIT ? 3 : 4) vi_column_kernel
         const double id = (p2 == l8) ? 1.0 : 0.0;
         const double pot2 = __shfl_sync(FULL, potl, p2, 8), wt2 = __shfl_sync(FULL, wtl, p2, 8), dpd2 = __shfl_sync(FULL, dpdl, p2, 8);
         rW[p2] = fdz;
-        cw[p2] = gfac * sVPT[p2 * 8 + l8];  A2[0][p2] = id;         A2[0][8 + p2] = fdz * dpd2;
-        cth[p2] = -fdz * pot2 * wt2;        A2[1][p2] = fdz * pot2; A2[1][8 + p2] = id + fdz * wt2;
+        A2[0][p2] = id;         A2[0][8 + p2] = fdz * dpd2;     // DDENS columns: gfac * VP[l][p2] and -fdz * pot2 * wt2,
+        A2[1][p2] = fdz * pot2; A2[1][8 + p2] = id + fdz * wt2; // rebuilt where they are used (product loop below)
       }
       double Lm[3][3], Um[3][3];
 #pragma unroll
@@ -315,9 +365,9 @@ __global__ void __launch_bounds__(VI_THREADS, IMPLICIT ? 3 : 4) vi_column_kernel
       const double t1b = facb * fmax(alph_b, alph_b), t2b = facb * (-1.0);
       const double t1t = fact * fmax(alph_t, alph_t), t2t = fact * (1.0);
       if (bot_bc) {
-        cth[0] += 2.0 * t2b * pot0 * wt0; rW[0] -= 2.0 * t2b; A2[0][0] += 2.0 * t1b; A2[1][0] -= 2.0 * t2b * pot0; A2[1][8] -= 2.0 * t2b * wt0;
+        cth0 += 2.0 * t2b * pot0 * wt0; rW[0] -= 2.0 * t2b; A2[0][0] += 2.0 * t1b; A2[1][0] -= 2.0 * t2b * pot0; A2[1][8] -= 2.0 * t2b * wt0;
       } else {
-        ra0 += t1b; cth[0] += t2b * pot0 * wt0; rW[0] -= t2b; A2[0][0] += t1b; A2[1][0] -= t2b * pot0;
+        ra0 += t1b; cth0 += t2b * pot0 * wt0; rW[0] -= t2b; A2[0][0] += t1b; A2[1][0] -= t2b * pot0;
         A2[0][8] -= t2b * dpd0; A2[1][8] += t1b - t2b * wt0;
         const double potn = potn_b, wtn = wtn_b, dpdn = dpdn_b;
         Lm[0][0] = -t1b; Lm[1][0] = 0.0;         Lm[2][0] = -t2b * potn * wtn;
@@ -325,9 +375,9 @@ __global__ void __launch_bounds__(VI_THREADS, IMPLICIT ? 3 : 4) vi_column_kernel
         Lm[0][2] = 0.0;  Lm[1][2] = t2b * dpdn;  Lm[2][2] = -t1b + t2b * wtn;
       }
       if (top_bc) {
-        cth[7] += 2.0 * t2t * pot7 * wt7; rW[7] -= 2.0 * t2t; A2[0][7] += 2.0 * t1t; A2[1][7] -= 2.0 * t2t * pot7; A2[1][15] -= 2.0 * t2t * wt7;
+        cth7 += 2.0 * t2t * pot7 * wt7; rW[7] -= 2.0 * t2t; A2[0][7] += 2.0 * t1t; A2[1][7] -= 2.0 * t2t * pot7; A2[1][15] -= 2.0 * t2t * wt7;
       } else {
-        ra7 += t1t; cth[7] += t2t * pot7 * wt7; rW[7] -= t2t; A2[0][7] += t1t; A2[1][7] -= t2t * pot7;
+        ra7 += t1t; cth7 += t2t * pot7 * wt7; rW[7] -= t2t; A2[0][7] += t1t; A2[1][7] -= t2t * pot7;
         A2[0][15] -= t2t * dpd7; A2[1][15] += t1t - t2t * wt7;
         const double potn = __shfl_sync(FULL, qn.pot, 0, 8), wtn = __shfl_sync(FULL, qn.wt, 0, 8), dpdn = __shfl_sync(FULL, qn.dpd, 0, 8);
         Um[0][0] = -t1t; Um[1][0] = 0.0;         Um[2][0] = -t2t * potn * wtn;
@@ -354,11 +404,11 @@ __global__ void __launch_bounds__(VI_THREADS, IMPLICIT ? 3 : 4) vi_column_kernel
         rW[0] = rW[0] - Lm[0][0] * g21b.x - Lm[0][1] * g22b.x - Lm[0][2] * g23b.x;
         rT0 = rT0 - Lm[0][0] * g21b.y - Lm[0][1] * g22b.y - Lm[0][2] * g23b.y;
         rR[0] = rR[0] - Lm[0][0] * g21a.x - Lm[0][1] * g22a.x - Lm[0][2] * g23a.x;
-        cw[0] = cw[0] - Lm[1][0] * g21a.y - Lm[1][1] * g22a.y - Lm[1][2] * g23a.y;
+        cw0 = cw0 - Lm[1][0] * g21a.y - Lm[1][1] * g22a.y - Lm[1][2] * g23a.y;
         A2[0][0] = A2[0][0] - Lm[1][0] * g21b.x - Lm[1][1] * g22b.x - Lm[1][2] * g23b.x;
         A2[0][8] = A2[0][8] - Lm[1][0] * g21b.y - Lm[1][1] * g22b.y - Lm[1][2] * g23b.y;
         A2[0][16] = A2[0][16] - Lm[1][0] * g21a.x - Lm[1][1] * g22a.x - Lm[1][2] * g23a.x;
-        cth[0] = cth[0] - Lm[2][0] * g21a.y - Lm[2][1] * g22a.y - Lm[2][2] * g23a.y;
+        cth0 = cth0 - Lm[2][0] * g21a.y - Lm[2][1] * g22a.y - Lm[2][2] * g23a.y;
         A2[1][0] = A2[1][0] - Lm[2][0] * g21b.x - Lm[2][1] * g22b.x - Lm[2][2] * g23b.x;
         A2[1][8] = A2[1][8] - Lm[2][0] * g21b.y - Lm[2][1] * g22b.y - Lm[2][2] * g23b.y;
         A2[1][16] = A2[1][16] - Lm[2][0] * g21a.x - Lm[2][1] * g22a.x - Lm[2][2] * g23a.x;
@@ -416,7 +466,11 @@ __global__ void __launch_bounds__(VI_THREADS, IMPLICIT ? 3 : 4) vi_column_kernel
 #pragma unroll
       for (int m = 0; m < 8; ++m) {
         const double* y = sY + m * VI_YROW;
-        const double c0 = cw[m], c1 = cth[m];
+        // DDENS columns of the MOMZ / DRHOT rows (construct_matbnd :757, :763) + the corrections of the face nodes
+        const double potwt = __shfl_sync(FULL, potl * wtl, m, 8);
+        double c0 = gfac * sVPT[m * 8 + l8], c1 = -(dfac * sDT[m * 8 + l8]) * potwt;
+        if (m == 0) { c0 += cw0; c1 += cth0; }
+        if (m == 7) c1 += cth7;
 #pragma unroll
         for (int j = 0; j < 8; j += 2) {
           const double2 t = lds_pair(y + j);
@@ -463,43 +517,61 @@ __global__ void __launch_bounds__(VI_THREADS, IMPLICIT ? 3 : 4) vi_column_kernel
     }
   }
 
-  // ---------------- backward sweep, update, outputs
-  double nb_r = 0.0, nb_w = 0.0, nb_t = 0.0, nb_u = 0.0, nb_v = 0.0;   // solution at node 0 of the element above
-  for (int kz = NeZ - 1; kz >= 0; --kz) {
+  // ---------------- backward sweep, update, outputs.  The loads of element kz-1 are issued before element kz is processed
+  // (register double buffer): the sweep is a chain of short dependent steps and was bound by global-load latency.
+  struct BwdIn {
+    double c[5], q0[5], d[3], gq[3][3], du, dv, guv, th, ph, R, gm;
+  };
+  auto bwd_load = [&](int kz) {
+    BwdIn b;
     const size_t n = node(kz);
-    const double cr = P.qcur[V_DDENS][n], cw = P.qcur[V_MOMZ][n], ct = P.qcur[V_DRHOT][n], cu = P.qcur[V_MOMX][n], cv = P.qcur[V_MOMY][n];
-    double qr = cr, qw = cw, qt = ct, qu = cu, qv = cv;
+    b.c[0] = P.qcur[V_DDENS][n]; b.c[1] = P.qcur[V_MOMZ][n]; b.c[2] = P.qcur[V_DRHOT][n]; b.c[3] = P.qcur[V_MOMX][n]; b.c[4] = P.qcur[V_MOMY][n];
+    b.th = P.therm_hyd[n]; b.ph = P.pres_hyd[n];
+    b.R = MOIST ? P.rtot[n] : P.c.Rdry;
+    b.gm = MOIST ? P.cptot[n] / P.cvtot[n] : P.c.CPovCV;
     if (IMPLICIT) {
-      double d[3], gq[3][3];
+      b.q0[0] = P.q0[V_DDENS][n]; b.q0[1] = P.q0[V_MOMZ][n]; b.q0[2] = P.q0[V_DRHOT][n]; b.q0[3] = P.q0[V_MOMX][n]; b.q0[4] = P.q0[V_MOMY][n];
 #pragma unroll
       for (int v = 0; v < 3; ++v) {
-        d[v] = scr[((size_t(kz) * 12 + v * 4) * 8 + l8) * ncol + col];
+        b.d[v] = scr[((size_t(kz) * 12 + v * 4) * 8 + l8) * ncol + col];
 #pragma unroll
-        for (int r = 0; r < 3; ++r) gq[v][r] = scr[((size_t(kz) * 12 + v * 4 + 1 + r) * 8 + l8) * ncol + col];
+        for (int r = 0; r < 3; ++r) b.gq[v][r] = scr[((size_t(kz) * 12 + v * 4 + 1 + r) * 8 + l8) * ncol + col];
       }
-      double du = scr[scr_uv + ((size_t(kz) * 3 + 0) * 8 + l8) * ncol + col], dv = scr[scr_uv + ((size_t(kz) * 3 + 1) * 8 + l8) * ncol + col];
-      const double guv = scr[scr_uv + ((size_t(kz) * 3 + 2) * 8 + l8) * ncol + col];
+      b.du = scr[scr_uv + ((size_t(kz) * 3 + 0) * 8 + l8) * ncol + col];
+      b.dv = scr[scr_uv + ((size_t(kz) * 3 + 1) * 8 + l8) * ncol + col];
+      b.guv = scr[scr_uv + ((size_t(kz) * 3 + 2) * 8 + l8) * ncol + col];
+    }
+    return b;
+  };
+  double nb_r = 0.0, nb_w = 0.0, nb_t = 0.0, nb_u = 0.0, nb_v = 0.0;   // solution at node 0 of the element above
+  BwdIn nxt = bwd_load(NeZ - 1);
+  for (int kz = NeZ - 1; kz >= 0; --kz) {
+    const size_t n = node(kz);
+    const BwdIn in = nxt;
+    if (kz > 0) nxt = bwd_load(kz - 1);
+    const double cr = in.c[0], cw = in.c[1], ct = in.c[2], cu = in.c[3], cv = in.c[4];
+    double qr = cr, qw = cw, qt = ct, qu = cu, qv = cv;
+    if (IMPLICIT) {
+      double d[3] = {in.d[0], in.d[1], in.d[2]};
+      double du = in.du, dv = in.dv;
       if (kz < NeZ - 1) {   // solve :429-444, solve_uv :661-674
 #pragma unroll
-        for (int v = 0; v < 3; ++v) d[v] = d[v] - gq[v][0] * nb_r - gq[v][1] * nb_w - gq[v][2] * nb_t;
-        du = du - guv * nb_u;
-        dv = dv - guv * nb_v;
+        for (int v = 0; v < 3; ++v) d[v] = d[v] - in.gq[v][0] * nb_r - in.gq[v][1] * nb_w - in.gq[v][2] * nb_t;
+        du = du - in.guv * nb_u;
+        dv = dv - in.guv * nb_v;
       }
       nb_r = __shfl_sync(FULL, d[0], 0, 8); nb_w = __shfl_sync(FULL, d[1], 0, 8); nb_t = __shfl_sync(FULL, d[2], 0, 8);
       nb_u = __shfl_sync(FULL, du, 0, 8); nb_v = __shfl_sync(FULL, dv, 0, 8);
       // PROG_VARS = var0 + delta;  tendency = (PROG_VARS - q) / impl_fac  (rhot_hevi.F90:931-940); StoreImplicit: q += impl_fac * k
-      const double pr = P.q0[V_DDENS][n] + d[0], pw = P.q0[V_MOMZ][n] + d[1], pth = P.q0[V_DRHOT][n] + d[2];
-      const double pu = P.q0[V_MOMX][n] + du, pvv = P.q0[V_MOMY][n] + dv;
+      const double pr = in.q0[0] + d[0], pw = in.q0[1] + d[1], pth = in.q0[2] + d[2];
+      const double pu = in.q0[3] + du, pvv = in.q0[4] + dv;
       const double kr = (pr - cr) / ifac, kw = (pw - cw) / ifac, kt = (pth - ct) / ifac, ku = (pu - cu) / ifac, kv = (pvv - cv) / ifac;
       P.kim[V_DDENS][n] = kr; P.kim[V_MOMZ][n] = kw; P.kim[V_DRHOT][n] = kt; P.kim[V_MOMX][n] = ku; P.kim[V_MOMY][n] = kv;
       qr = cr + ifac * kr; qw = cw + ifac * kw; qt = ct + ifac * kt; qu = cu + ifac * ku; qv = cv + ifac * kv;
     }
     P.qout[V_DDENS][n] = qr; P.qout[V_MOMZ][n] = qw; P.qout[V_DRHOT][n] = qt; P.qout[V_MOMX][n] = qu; P.qout[V_MOMY][n] = qv;
-    {  // DPRES of the updated state for the explicit part of this stage (DRHOT2PRES, nonhydro3d_common.F90:467-474)
-      const double R = MOIST ? P.rtot[n] : P.c.Rdry;
-      const double gm = MOIST ? P.cptot[n] / P.cvtot[n] : P.c.CPovCV;
-      P.dpout[n] = P.c.PRES00 * pow(R * P.c.rP0 * (P.therm_hyd[n] + qt), gm) - P.pres_hyd[n];
-    }
+    // DPRES of the updated state for the explicit part of this stage (DRHOT2PRES, nonhydro3d_common.F90:467-474)
+    P.dpout[n] = P.c.PRES00 * pow(in.R * P.c.rP0 * (in.th + qt), in.gm) - in.ph;
   }
 }
 
@@ -507,18 +579,26 @@ void launch_vi(const VIParams& p, bool moist, cudaStream_t s) {
   const int ncol = p.Ne2D * 64;
   const int groups = VI_THREADS / 8;
   dim3 grid(ncol / groups), block(VI_THREADS);
-  const size_t shmem = (144 + size_t(groups) * VI_SOL + size_t(VI_NQ) * VI_THREADS) * sizeof(double);
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(vi_column_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(shmem));
-    cudaFuncSetAttribute(vi_column_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(shmem));
-    cudaFuncSetAttribute(vi_column_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(shmem));
-    cudaFuncSetAttribute(vi_column_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(shmem));
-    attr_set = true;
-  }
+  const size_t shmem = (144 + size_t(groups) * VI_SOL + size_t(VI_NQ + VI_PF) * VI_THREADS) * sizeof(double);
+  // resident blocks per SM the implicit kernel is compiled for: 2 (244 registers, no spills; default) or 3 (168 registers,
+  // 144 B of spills).  Measured at 32x32x16: 2.49 vs 2.68 ms per launch (average over the stages of IMEX_ARK324); local-memory
+  // traffic costs more than the fourth warp per scheduler brings.  FEDG_VI_MINB=3 selects the other build (A/B measurements).
+  static int minb = -1;
+  if (minb < 0) { const char* e = getenv("FEDG_VI_MINB"); minb = (e && e[0] == '3') ? 3 : 2; }
+#define FEDG_VI_LAUNCH(M, I, B)                                                                              \
+  do {                                                                                                       \
+    static bool attr_set = false;                                                                            \
+    if (!attr_set) {                                                                                         \
+      cudaFuncSetAttribute(vi_column_kernel<M, I, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(shmem)); \
+      attr_set = true;                                                                                       \
+    }                                                                                                        \
+    vi_column_kernel<M, I, B><<<grid, block, shmem, s>>>(p);                                                 \
+  } while (0)
   const bool implicit = p.impl_fac != 0.0;
-  if (moist) { if (implicit) vi_column_kernel<true, true><<<grid, block, shmem, s>>>(p); else vi_column_kernel<true, false><<<grid, block, shmem, s>>>(p); }
-  else { if (implicit) vi_column_kernel<false, true><<<grid, block, shmem, s>>>(p); else vi_column_kernel<false, false><<<grid, block, shmem, s>>>(p); }
+  if (!implicit) { if (moist) FEDG_VI_LAUNCH(true, false, 4); else FEDG_VI_LAUNCH(false, false, 4); }
+  else if (minb == 2) { if (moist) FEDG_VI_LAUNCH(true, true, 2); else FEDG_VI_LAUNCH(false, true, 2); }
+  else { if (moist) FEDG_VI_LAUNCH(true, true, 3); else FEDG_VI_LAUNCH(false, true, 3); }
+#undef FEDG_VI_LAUNCH
 }
 
 // IMEX / general stage combination  q = base + sum_m coef[m] * k[m]  (rk_advance_general2D, scale_timeint_rk.F90:2201-2355,

@@ -143,6 +143,11 @@ class AtmDynDGMDriver_nonhydro3d:
         b = None if DPhydDy is None else self._chk_field(DPhydDy)
         _lib.check(self.L.fedg_set_phyd_hgrad(self.h, _ptr(a), _ptr(b)))
 
+    def set_phy_tend(self, DENS_tp, MOMX_tp, MOMY_tp, MOMZ_tp, RHOT_tp, RHOH_p):
+        """Physics tendencies of add_phy_tend (driver_nonhydro3d.F90:1098-1178); None switches them off."""
+        a = [None if x is None else self._chk_field(x) for x in (DENS_tp, MOMX_tp, MOMY_tp, MOMZ_tp, RHOT_tp, RHOH_p)]
+        _lib.check(self.L.fedg_set_phy_tend(self.h, *[_ptr(x) for x in a]))
+
     def set_coriolis(self, cor):
         a = None if cor is None else _f64(cor).reshape(-1)
         _lib.check(self.L.fedg_set_coriolis(self.h, _ptr(a)))

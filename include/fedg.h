@@ -120,6 +120,11 @@ int fedg_set_aux(fedg_ctx* ctx, const double* DENS_hyd, const double* PRES_hyd, 
                  const double* Rtot, const double* CVtot, const double* CPtot);
 /* AUXDYNVARS3D DPhydDx, DPhydDy (driver_nonhydro3d.F90:323-326, 1060-1095); NULL = zero. */
 int fedg_set_phyd_hgrad(fedg_ctx* ctx, const double* DPhydDx, const double* DPhydDy);
+/* Physics tendencies handed to the dynamics step, (Np,NeA) each: DENS_tp, MOMX_tp, MOMY_tp, MOMZ_tp, RHOT_tp, RHOH_p of
+ * add_phy_tend (driver_nonhydro3d.F90:843-857, 1098-1178; ENTOT_CONSERVE_SCHEME_FLAG = .false. form).  They are added
+ * to the explicit tendency of every stage inside the stage kernel.  NULL or all-zero arrays switch the term off. */
+int fedg_set_phy_tend(fedg_ctx* ctx, const double* DENS_tp, const double* MOMX_tp, const double* MOMY_tp,
+                      const double* MOMZ_tp, const double* RHOT_tp, const double* RHOH_p);
 /* Coriolis parameter (Nfp_v, Ne2D); NULL = zero. */
 int fedg_set_coriolis(fedg_ctx* ctx, const double* coriolis);
 

@@ -84,6 +84,8 @@ double* feo_array(void* hv, const char* name, long* n) {
   else if (s == "PRES") v = &d.st.PRES; else if (s == "DPRES") v = &d.st.DPRES;
   else if (s == "DPhydDx") v = &d.st.DPhydDx; else if (s == "DPhydDy") v = &d.st.DPhydDy;
   else if (s == "CORIOLIS") v = &d.st.CORIOLIS;
+  else if (s == "DENS_tp") v = &d.st.DENS_tp; else if (s == "MOMX_tp") v = &d.st.MOMX_tp; else if (s == "MOMY_tp") v = &d.st.MOMY_tp;
+  else if (s == "MOMZ_tp") v = &d.st.MOMZ_tp; else if (s == "RHOT_tp") v = &d.st.RHOT_tp; else if (s == "RHOH_p") v = &d.st.RHOH_p;
   else if (s == "tend_ex") v = &d.tint.tend_ex; else if (s == "tend_im") v = &d.tint.tend_im;
   if (!v) { *n = 0; return nullptr; }
   *n = long(v->size());
@@ -141,6 +143,9 @@ int feo_prepare(void* hv) {
   });
 }
 
+// physics tendencies on / off (the arrays are DENS_tp ... RHOH_p of feo_array)
+void feo_set_phytend(void* hv, int on) { static_cast<Handle*>(hv)->d.phytend = on != 0; }
+
 int feo_update(void* hv, int nsteps) {
   auto* h = static_cast<Handle*>(hv);
   return guard([&] { for (int n = 0; n < nsteps; ++n) h->d.update(); });
@@ -173,6 +178,7 @@ int feo_stage_piece(void* hv, const char* what) {
       double* out[5]; for (int v = 0; v < 5; ++v) out[v] = d.tint.tend_ex_buf(v, 0);
       if (d.global) global_hevi_cal_tend(d.elem, d.mesh, d.cst, d.st, out);
       else if (d.hevi) hevi_cal_tend(d.elem, d.mesh, d.cst, d.st, out); else heve_cal_tend(d.elem, d.mesh, d.cst, d.st, out);
+      if (d.phytend) add_phy_tend(d.elem, d.mesh, d.cst, d.st, d.entot_conserve, out);
     }
     else if (w == "modalfilter") modalfilter_apply(d.elem, d.mesh, d.st);
     else throw std::runtime_error("unknown piece " + w);

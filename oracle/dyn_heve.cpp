@@ -8,9 +8,25 @@ namespace feo {
 
 void DynState::alloc(size_t n, size_t n2d) {
   for (vec* v : {&DDENS, &MOMX, &MOMY, &MOMZ, &DRHOT, &DENS_hyd, &PRES_hyd, &THERM_hyd, &PRES_hyd_ref, &Rtot,
-                 &CVtot, &CPtot, &PRES, &DPRES, &DPhydDx, &DPhydDy})
+                 &CVtot, &CPtot, &PRES, &DPRES, &DPhydDx, &DPhydDy, &DENS_tp, &MOMX_tp, &MOMY_tp, &MOMZ_tp, &RHOT_tp, &RHOH_p})
     v->assign(n, 0.0);
   CORIOLIS.assign(n2d, 0.0);
+}
+
+// fluid_dyn_solver/scale_atm_dyn_dgm_driver_nonhydro3d.F90:1098-1178 (add_phy_tend, CPU branch)
+void add_phy_tend(const Element& e, const Mesh& m, const Consts& c, const DynState& s, bool entot_conserve, double* dt5[5]) {
+  const double rP0 = 1.0 / c.PRES00;
+  const size_t n = size_t(e.Np) * m.Ne;
+#pragma omp parallel for
+  for (size_t i = 0; i < n; ++i) {
+    dt5[DENS_VID][i] = dt5[DENS_VID][i] + s.DENS_tp[i];
+    dt5[MOMZ_VID][i] = dt5[MOMZ_VID][i] + s.MOMZ_tp[i];
+    dt5[MOMX_VID][i] = dt5[MOMX_VID][i] + s.MOMX_tp[i];
+    dt5[MOMY_VID][i] = dt5[MOMY_VID][i] + s.MOMY_tp[i];
+    const double EXNER = std::pow(s.PRES[i] * rP0, s.Rtot[i] / s.CPtot[i]);
+    if (entot_conserve) dt5[THERM_VID][i] = dt5[THERM_VID][i] + s.RHOH_p[i] + (s.CPtot[i] * EXNER) * s.RHOT_tp[i];
+    else dt5[THERM_VID][i] = dt5[THERM_VID][i] + s.RHOT_tp[i] + s.RHOH_p[i] / (s.CPtot[i] * EXNER);
+  }
 }
 
 // fluid_dyn_solver/scale_atm_dyn_dgm_nonhydro3d_common.F90:428-479 (CPU branch)

@@ -150,6 +150,8 @@ struct DynState {
   // auxiliary
   vec DENS_hyd, PRES_hyd, THERM_hyd, PRES_hyd_ref, Rtot, CVtot, CPtot, PRES, DPRES, DPhydDx, DPhydDy;
   vec CORIOLIS;  // (Nfp, Ne2D)
+  // physics tendencies handed to the dynamics (driver_nonhydro3d.F90:843-857), (Np,NeA)
+  vec DENS_tp, MOMX_tp, MOMY_tp, MOMZ_tp, RHOT_tp, RHOH_p;
   double* prog(int v) {
     switch (v) { case DENS_VID: return DDENS.data(); case RHOT_VID: return DRHOT.data();
       case MOMZ_VID: return MOMZ.data(); case MOMX_VID: return MOMX.data(); default: return MOMY.data(); }
@@ -164,6 +166,7 @@ void apply_bc_progvars(const Element& e, const Mesh& m, const BndCfg& b, DynStat
 void heve_numflux_generalvc(const Element& e, const Mesh& m, const Consts& c, const DynState& s, vec& del_flux);
 void heve_cal_tend(const Element& e, const Mesh& m, const Consts& c, const DynState& s, double* dt5[5]);
 void modalfilter_apply(const Element& e, const Mesh& m, DynState& s);
+void add_phy_tend(const Element& e, const Mesh& m, const Consts& c, const DynState& s, bool entot_conserve, double* dt5[5]);
 
 // HEVI (a6, a8-a12)
 void hevi_numflux_generalvc(const Element& e, const Mesh& m, const Consts& c, const DynState& s, vec& del_flux);
@@ -182,7 +185,7 @@ struct Driver {
   BndCfg bnd;
   DynState st;
   TimeIntRK tint;
-  bool hevi = false, modalfilter = false, global = false;
+  bool hevi = false, modalfilter = false, global = false, phytend = false, entot_conserve = false;
   void update();  // fluid_dyn_solver/scale_atm_dyn_dgm_driver_nonhydro3d.F90:614-963
 };
 

@@ -38,6 +38,7 @@ def lib():
         L.feo_setup_dyn.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_double, C.c_int, C.c_void_p, C.c_void_p]
         L.feo_prepare.argtypes = [C.c_void_p]
         L.feo_update.argtypes = [C.c_void_p, C.c_int]
+        L.feo_set_phytend.argtypes = [C.c_void_p, C.c_int]
         L.feo_monitor.argtypes = [C.c_void_p, C.c_void_p]
         L.feo_cal_vi.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_void_p, C.c_void_p]
         L.feo_stage_piece.argtypes = [C.c_void_p, C.c_char_p]
@@ -124,6 +125,9 @@ class Oracle:
         mf = np.asarray(mf, dtype=np.float64)
         bc = np.asarray(vel_bc, dtype=np.int32)
         self._chk(lib().feo_setup_dyn(self.h, eqs.encode(), tinteg.encode(), dt, int(modalfilter), _p(mf), _p(bc)))
+
+    def set_phytend(self, on=True):
+        lib().feo_set_phytend(self.h, int(on))
 
     def prepare(self):
         self._chk(lib().feo_prepare(self.h))

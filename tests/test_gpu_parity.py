@@ -372,3 +372,32 @@ def test_global_panel_rejections():
     reg = DensityCurrentCase(p=7, NeX=2, NeY=1, NeZ=2).make_driver(None)
     with pytest.raises(_lib.FedgError):
         reg.Init("GLOBALNONHYDRO3D_HEVI", "IMEX_ARK232", 1.0)
+
+
+@pytest.mark.parametrize("p,eqs,tinteg,dt", [(7, "NONHYDRO3D_HEVE", "ERK_SSP_4s3o", 0.05), (3, "NONHYDRO3D_HEVE", "ERK_SSP_3s3o", 0.2),
+                                             (7, "NONHYDRO3D_HEVI", "IMEX_ARK232", 0.5)])
+def test_physics_tendencies_row_a17(p, eqs, tinteg, dt):
+    """add_phy_tend (driver_nonhydro3d.F90:1098-1178): DENS/MOM/RHOT tendencies and the heating RHOH_p / (CP EXNER) enter the
+    explicit tendency of every stage."""
+    case = DensityCurrentCase(p=p, NeX=3, NeY=2, NeZ=3, perturb=2.0, eqs=eqs, tinteg=tinteg, dt=dt, intrp_order=min(11, p + 4))
+    o = case.make_oracle()
+    d = case.make_driver(o)
+    m, e = case.mesh, case.elem
+    n, N = m.Ne * e.Np, m.NeA * e.Np
+    x, z = m.pos_en[0].reshape(-1), m.pos_en[2].reshape(-1)
+    tp = {"DENS_tp": 1e-4 * np.sin(x / 2e3), "MOMX_tp": 2e-2 * np.cos(z / 1e3), "MOMY_tp": -1e-2 * np.sin(z / 2e3),
+          "MOMZ_tp": 5e-3 * np.sin(x / 3e3) * np.sin(z / 1e3), "RHOT_tp": 3e-2 * np.cos(x / 4e3), "RHOH_p": 50.0 * np.exp(-((z - 2e3) / 1e3) ** 2)}
+    full = {}
+    for k, v in tp.items():
+        a = np.zeros(N); a[:n] = v
+        o.arr(k)[:] = a
+        full[k] = a
+    o.set_phytend(True)
+    d.set_phy_tend(*(full[k] for k in ("DENS_tp", "MOMX_tp", "MOMY_tp", "MOMZ_tp", "RHOT_tp", "RHOH_p")))
+    o.update(5); d.Update(5)
+    g = d.get_prog()
+    for nm in PROG:
+        assert rel_l2(g[nm][:n], o.arr(nm)[:n]) <= TOL, nm
+    # and they matter: switching them off changes the answer
+    d2 = case.make_driver(o); d2.Update(5)
+    assert rel_l2(d2.get_prog()["DRHOT"][:n], g["DRHOT"][:n]) > 1e-6
