@@ -193,6 +193,55 @@ def run_advect3d(args):
         cpu_baseline=cpu, finite=bool(np.isfinite(q2).all()))))
 
 
+def run_sphere(args):
+    """configs[3]: global cubed sphere 6 x 32 x 32 x 12 elements p=7, GLOBALNONHYDRO3D_HEVI + IMEX_ARK324, the six panels as six
+    local meshes on one GPU (fedg_group_update); synthetic state: balanced solid-body rotation + perturbations."""
+    import torch
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    from cases import GlobalSphereCase
+    from fe_project_b200.dyncore import PROG_NAMES
+    ne, nez = (args.nex if args.nex != WORKLOAD["NeX"] else 32), (args.nez if args.nez != WORKLOAD["NeZ"] else 12)
+    case = GlobalSphereCase(p=7, Ne=ne, NeZ=nez, dt=5.0 * 32 / ne, tinteg="IMEX_ARK324", modalfilter=True)
+    g = case.make_driver()
+    W, K = max(3, args.warmup), args.steps
+    g.Update(W)
+    sampler = ClockSampler(0); sampler.start(); time.sleep(0.12)
+    g.Update(K)
+    tm = g.last_timing()
+    clocks = sampler.stop()
+    Np = case.elem.Np
+    nel = sum(m.Ne for m in case.cs.panels)
+    dof = 5 * Np * nel
+    value = dof * K / (tm["ms_total"] * 1e-3)
+    states = [d.get_prog() for d in g.panels]
+    finite = all(np.isfinite(st[k][:Np * m.Ne]).all() for st, m in zip(states, case.cs.panels) for k in PROG_NAMES)
+    # e2e: host state of the six panels in, one step, host state out
+    t0 = time.perf_counter()
+    ne2e = 3
+    for _ in range(ne2e):
+        for d, st in zip(g.panels, states):
+            d.set_prog(*(st[k] for k in PROG_NAMES))
+        g.Update(1)
+        states = [d.get_prog() for d in g.panels]
+    t_e2e = (time.perf_counter() - t0) / ne2e
+    nbytes = sum(5 * d.n_field * 8 for d in g.panels)
+    nstage = 4
+    # vertical-implicit column solve dominates: same accounting as the regional HEVI line (15.1 kflop per column-element)
+    ms_vi = None
+    print(json.dumps(dict(
+        metric=METRIC, value=value, unit=UNIT, n_gpus=1, steps=K, warmup=W, ms_per_step=tm["ms_total"] / K, higher_is_better=True,
+        scaling="weak", vs_baseline=None, dtype="f64", data="synthetic",
+        config=dict(workload=f"atm_nonhydro3d global cubed sphere 6x{ne}x{ne}x{nez} elements p=7, GLOBALNONHYDRO3D_HEVI, IMEX_ARK324, "
+                             f"dt={case.dt}, modal filter on, six local meshes on one GPU with linked panel-edge halos",
+                    dof=dof, l2_policy="inputs larger than L2 (50 MB per field and panel)"),
+        clocks=clocks, e2e=dict(value=dof / t_e2e, unit=UNIT, h2d_bytes_per_step=nbytes, d2h_bytes_per_step=nbytes, steps_per_call=1),
+        gpu_launches=tm["launches"],
+        roofline=dict(bound="fp64", achieved=None, peak=34.07, unit="TFLOP/s", frac=None, traffic=None,
+                      kernel="vi_column_kernel (see the global_panel line for its per-launch figures)", ms_per_launch=ms_vi),
+        cpu_baseline=None, finite=bool(finite))))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -204,7 +253,7 @@ def main():
     ap.add_argument("--nez", type=int, default=WORKLOAD["NeZ"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--eqs", default="heve", choices=["heve", "hevi"], help="hevi: NONHYDRO3D_HEVI + IMEX_ARK324 (extra, not the headline)")
-    ap.add_argument("--workload", default="density_current", choices=["density_current", "sound_wave", "global_panel", "advect3d"],
+    ap.add_argument("--workload", default="density_current", choices=["density_current", "sound_wave", "global_panel", "global_sphere", "advect3d"],
                     help="density_current = BASELINE configs[2] (headline); the others are extra measurement lines: sound_wave = "
                          "configs[1] rate variant 16x16x16, global_panel = one 32x32x12 panel of configs[3], advect3d = configs[0]")
     args = ap.parse_args()
@@ -216,6 +265,9 @@ def main():
         return
     if args.workload == "advect3d":
         run_advect3d(args)
+        return
+    if args.workload == "global_sphere":
+        run_sphere(args)
         return
 
     import torch

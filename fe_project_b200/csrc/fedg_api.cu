@@ -101,6 +101,10 @@ struct fedg_ctx {
   int* d_elem_inner = nullptr; int* d_elem_bnd = nullptr; int n_inner = 0, n_bnd = 0;
   int cur = 0;
   AdvectState adv;
+  // halo faces filled from another local mesh on the same device (cubed-sphere panel edges): fedg_link_halo
+  struct HaloLink { fedg_ctx* src = nullptr; int* d_src = nullptr; double* d_rot = nullptr; int off = 0, cnt = 0; } link[6];
+  int xbuf = 0;                    // buffer that holds the state other local meshes gather from (stage input of the explicit part)
+  struct { int i0, in, mid, nxt; } hs{0, 0, 0, 0};   // buffer cursor of the HEVI stage pieces
   // timing
   bool profile = true;
   std::vector<cudaEvent_t> ev;
@@ -115,6 +119,7 @@ struct fedg_ctx {
     if (d_elem_inner) cudaFree(d_elem_inner);
     if (d_elem_bnd) cudaFree(d_elem_bnd);
     comm_destroy(comm);
+    for (auto& l : link) { if (l.d_src) cudaFree(l.d_src); if (l.d_rot) cudaFree(l.d_rot); }
     adv.release();
     for (auto& b : phyt) b.release();
     for (auto& b : dp) b.release();
@@ -460,6 +465,7 @@ int fedg_set_prog(fedg_ctx* c, const double* DDENS, const double* MOMX, const do
     CUDA_TRY(cudaMemcpyAsync(c->prog[c->cur][v].p, h[v], c->nall * sizeof(double), cudaMemcpyHostToDevice, c->stream));
   CUDA_TRY(cudaStreamSynchronize(c->stream));
   c->dp_valid[c->cur] = false;
+  c->xbuf = c->cur;
   return FEDG_OK;
 }
 
@@ -564,6 +570,35 @@ __global__ void aux_halo_kernel(double* q, const int* src, int nint, int nhalo) 
   if (h < nhalo && src[h] >= 0) q[size_t(nint) + h] = q[src[h]];
 }
 
+// halo slots of a face linked to another local mesh: gather the six fields, re-express (MOMX, MOMY) in the own basis
+// (2x2 matrix per node = LonLat2CSVec(own panel, own face node) o CS2LonLatVec(source panel, source node))
+struct LinkFields { const double* s[6]; double* d[6]; };
+__global__ void halo_link_kernel(LinkFields F, const int* __restrict__ src, const double* __restrict__ rot, size_t dst0, int cnt) {
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= cnt) return;
+  const int i = src[m];
+  const size_t o = dst0 + m;
+  F.d[V_DDENS][o] = F.s[V_DDENS][i]; F.d[V_MOMZ][o] = F.s[V_MOMZ][i]; F.d[V_DRHOT][o] = F.s[V_DRHOT][i]; F.d[5][o] = F.s[5][i];
+  const double sx = F.s[V_MOMX][i], sy = F.s[V_MOMY][i];
+  double r00 = 1.0, r01 = 0.0, r10 = 0.0, r11 = 1.0;
+  if (rot) { r00 = rot[4 * size_t(m)]; r01 = rot[4 * size_t(m) + 1]; r10 = rot[4 * size_t(m) + 2]; r11 = rot[4 * size_t(m) + 3]; }
+  F.d[V_MOMX][o] = r00 * sx + r01 * sy;
+  F.d[V_MOMY][o] = r10 * sx + r11 * sy;
+}
+
+void fill_halo(fedg_ctx* c, int buf, bool apply_bc);
+void fill_halo_links(fedg_ctx* c, int buf) {
+  for (int f = 0; f < 6; ++f) {
+    const auto& l = c->link[f];
+    if (!l.src) continue;
+    LinkFields F{};
+    const int sb = l.src->xbuf;
+    for (int v = 0; v < NVAR; ++v) { F.s[v] = l.src->prog[sb][v].p; F.d[v] = c->prog[buf][v].p; }
+    F.s[5] = l.src->dp[sb].p; F.d[5] = c->dp[buf].p;
+    halo_link_kernel<<<(l.cnt + 255) / 256, 256, 0, c->stream>>>(F, l.d_src, l.d_rot, c->nint + size_t(l.off), l.cnt);
+  }
+}
+
 void fill_halo(fedg_ctx* c, int buf, bool apply_bc) {
   HaloParams H{};
   for (int v = 0; v < NVAR; ++v) H.q[v] = c->prog[buf][v].p;
@@ -578,6 +613,7 @@ void fill_halo(fedg_ctx* c, int buf, bool apply_bc) {
   }
   H.Np = c->Np; H.Ne = c->Ne; H.Nfp = c->Nfp; H.np = c->np; H.Nhalo = c->Nhalo; H.terrain = c->terrain;
   launch_halo_fill(H, c->stream);
+  fill_halo_links(c, buf);
 }
 
 void fill_stage_params(fedg_ctx* c, StageParams& P, int in, int out, int q0) {
@@ -625,45 +661,63 @@ void fill_vi_params(fedg_ctx* c, VIParams& V, int in, int out, int i0, int stage
 // HEVI / IMEX step (driver_nonhydro3d.F90:703-763 + 769-921): per stage  cal_vi -> StoreImplicit -> halo + BC ->
 // explicit tendency -> Advance (general IMEX form, scale_timeint_rk.F90:2201-2355, accumulated from var0 in the
 // reference's term order); then the modal filter.
+// stage pieces (so that several local meshes on one device can be advanced stage by stage, fedg_group_update)
+void hevi_begin_step(fedg_ctx* c) { c->hs.i0 = c->cur; c->hs.in = c->cur; }
+int hevi_stage_vi(fedg_ctx* c, int s, cudaEvent_t e0, cudaEvent_t e1) {
+  const int i0 = c->hs.i0, bA = (i0 + 1) % 3, bB = (i0 + 2) % 3, in = c->hs.in;
+  const int mid = (in == i0) ? bA : in;            // the column solve may update in place except on var0
+  const int nxt = (mid == bA) ? bB : bA;
+  c->hs.mid = mid; c->hs.nxt = nxt;
+  VIParams V{};
+  fill_vi_params(c, V, in, mid, i0, s, c->rk.aim(s, s) * c->dt);
+  if (e0) CUDA_TRY(cudaEventRecord(e0, c->stream));
+  launch_vi(V, c->moist, c->stream);
+  if (e1) CUDA_TRY(cudaEventRecord(e1, c->stream));
+  c->dp_valid[mid] = true;
+  c->xbuf = mid;
+  return FEDG_OK;
+}
+int hevi_stage_ex(fedg_ctx* c, int s) {
+  StageParams P{};
+  fill_stage_params(c, P, c->hs.mid, c->hs.mid, c->hs.i0);
+  for (int v = 0; v < NVAR; ++v) P.tend_out[v] = c->kex[size_t(s) * NVAR + v].p;
+  return exchange_and_stage(c, P, c->hs.mid, true);
+}
+void hevi_stage_combine(fedg_ctx* c, int s) {
+  const RKTable& t = c->rk;
+  const int ns = t.nstage, i0 = c->hs.i0, nxt = c->hs.nxt;
+  const double dt = c->dt;
+  LinCombParams L{};
+  L.n = c->nint; L.nterm = 0;
+  for (int v = 0; v < NVAR; ++v) { L.base[v] = c->prog[i0][v].p; L.out[v] = c->prog[nxt][v].p; }
+  for (int ss = 0; ss <= s; ++ss) {
+    const double ce = (s == ns - 1) ? dt * t.b_ex[ss] : dt * t.aex(s + 1, ss);
+    const double ci = (s == ns - 1) ? dt * t.b_im[ss] : dt * t.aim(s + 1, ss);
+    for (int v = 0; v < NVAR; ++v) { L.k[L.nterm][v] = c->kex[size_t(ss) * NVAR + v].p; L.k[L.nterm + 1][v] = c->kim[size_t(ss) * NVAR + v].p; }
+    L.coef[L.nterm] = ce; L.coef[L.nterm + 1] = ci;
+    L.nterm += 2;
+  }
+  // the last stage's combination carries the modal filter of the step (driver_nonhydro3d.F90:940-951)
+  if (s == ns - 1 && c->modalfilter) launch_lincomb_filter(L, c->d_tab, c->gsqrt.p, c->terrain || c->global, c->Ne, c->np, c->stream);
+  else launch_lincomb(L, c->stream);
+  c->dp_valid[nxt] = false;
+  c->hs.in = nxt;
+}
+void hevi_end_step(fedg_ctx* c) { c->cur = c->hs.in; c->xbuf = c->cur; }
+
 int run_steps_hevi(fedg_ctx* c, int nsteps, size_t& iev, long& launches) {
   const int ns = c->rk.nstage;
-  const RKTable& t = c->rk;
-  const double dt = c->dt;
   for (int step = 0; step < nsteps; ++step) {
-    const int i0 = c->cur, bA = (i0 + 1) % 3, bB = (i0 + 2) % 3;
-    int in = i0;
+    hevi_begin_step(c);
     for (int s = 0; s < ns; ++s) {
-      const int mid = (in == i0) ? bA : in;            // the column solve may update in place except on var0
-      const int nxt = (mid == bA) ? bB : bA;
-      VIParams V{};
-      fill_vi_params(c, V, in, mid, i0, s, t.aim(s, s) * dt);
       cudaEvent_t e0 = nullptr, e1 = nullptr;
-      if (c->profile) { e0 = c->ev[iev++]; e1 = c->ev[iev++]; CUDA_TRY(cudaEventRecord(e0, c->stream)); }
-      launch_vi(V, c->moist, c->stream);
-      if (c->profile) CUDA_TRY(cudaEventRecord(e1, c->stream));
-      c->dp_valid[mid] = true;
-      StageParams P{};
-      fill_stage_params(c, P, mid, mid, i0);
-      for (int v = 0; v < NVAR; ++v) P.tend_out[v] = c->kex[size_t(s) * NVAR + v].p;
-      { int rc = exchange_and_stage(c, P, mid, true); if (rc) return rc; }
-      LinCombParams L{};
-      L.n = c->nint; L.nterm = 0;
-      for (int v = 0; v < NVAR; ++v) { L.base[v] = c->prog[i0][v].p; L.out[v] = c->prog[nxt][v].p; }
-      for (int ss = 0; ss <= s; ++ss) {
-        const double ce = (s == ns - 1) ? dt * t.b_ex[ss] : dt * t.aex(s + 1, ss);
-        const double ci = (s == ns - 1) ? dt * t.b_im[ss] : dt * t.aim(s + 1, ss);
-        for (int v = 0; v < NVAR; ++v) { L.k[L.nterm][v] = c->kex[size_t(ss) * NVAR + v].p; L.k[L.nterm + 1][v] = c->kim[size_t(ss) * NVAR + v].p; }
-        L.coef[L.nterm] = ce; L.coef[L.nterm + 1] = ci;
-        L.nterm += 2;
-      }
-      // the last stage's combination carries the modal filter of the step (driver_nonhydro3d.F90:940-951)
-      if (s == ns - 1 && c->modalfilter) launch_lincomb_filter(L, c->d_tab, c->gsqrt.p, c->terrain || c->global, c->Ne, c->np, c->stream);
-      else launch_lincomb(L, c->stream);
-      c->dp_valid[nxt] = false;
+      if (c->profile) { e0 = c->ev[iev++]; e1 = c->ev[iev++]; }
+      { int rc = hevi_stage_vi(c, s, e0, e1); if (rc) return rc; }
+      { int rc = hevi_stage_ex(c, s); if (rc) return rc; }
+      hevi_stage_combine(c, s);
       launches += 4;
-      in = nxt;
     }
-    c->cur = in;
+    hevi_end_step(c);
   }
   return FEDG_OK;
 }
@@ -1096,6 +1150,75 @@ int fedg_advect3d_update(fedg_ctx* c, int nsteps) {
   float ms = 0;
   CUDA_TRY(cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]));
   c->last_ms_total = ms; c->last_ms_stage = 0; c->last_launches = long(nsteps) * a.rk.nstage * 2;
+  return FEDG_OK;
+}
+
+}  // extern "C"
+
+// ---- several local meshes on one device (the reference's LOCAL_MESH_NUM > 1; cubed-sphere panels) ----------------
+extern "C" {
+
+int fedg_link_halo(fedg_ctx* c, int face, fedg_ctx* src, const int* src_index, const double* rot) {
+  if (!c || !src || !src_index || face < 1 || face > 6) return fail(FEDG_ERR_ARG, "bad argument");
+  const int f = face - 1, cnt = c->face_off[f + 1] - c->face_off[f];
+  if (src->Np != c->Np) return fail(FEDG_ERR_ARG, "linked meshes must share the element");
+  int dev_a = -1;
+  cudaGetDevice(&dev_a);
+  std::vector<int> idx(cnt);
+  for (int m = 0; m < cnt; ++m) {
+    idx[m] = src_index[m] - 1;
+    if (idx[m] < 0 || size_t(idx[m]) >= src->nint) return fail(FEDG_ERR_ARG, "src_index out of range (1-based interior index of the source mesh)");
+  }
+  auto& l = c->link[f];
+  if (l.d_src) cudaFree(l.d_src);
+  if (l.d_rot) cudaFree(l.d_rot);
+  l = fedg_ctx::HaloLink{};
+  CUDA_TRY(cudaMalloc(&l.d_src, size_t(std::max(cnt, 1)) * sizeof(int)));
+  CUDA_TRY(cudaMemcpy(l.d_src, idx.data(), size_t(cnt) * sizeof(int), cudaMemcpyHostToDevice));
+  if (rot) {
+    CUDA_TRY(cudaMalloc(&l.d_rot, size_t(std::max(cnt, 1)) * 4 * sizeof(double)));
+    CUDA_TRY(cudaMemcpy(l.d_rot, rot, size_t(cnt) * 4 * sizeof(double), cudaMemcpyHostToDevice));
+  }
+  l.src = src; l.off = c->face_off[f]; l.cnt = cnt;
+  return FEDG_OK;
+}
+
+int fedg_group_update(fedg_ctx** ctxs, int n, int nsteps) {
+  if (!ctxs || n < 1 || nsteps < 0) return fail(FEDG_ERR_ARG, "bad argument");
+  for (int i = 0; i < n; ++i) {
+    fedg_ctx* c = ctxs[i];
+    if (!c) return fail(FEDG_ERR_ARG, "null context");
+    if (!c->dyn_ready || !c->aux_ready) return fail(FEDG_ERR_STATE, "fedg_dyn_init and fedg_set_aux must be called on every mesh of the group");
+    if (!c->hevi) return fail(FEDG_ERR_UNSUPPORTED, "group stepping is implemented for the HEVI equation sets");
+    if (c->comm.active && c->comm.nremote > 0) return fail(FEDG_ERR_UNSUPPORTED, "group stepping and NCCL tiles cannot be combined yet");
+    if (c->rk.nstage != ctxs[0]->rk.nstage || c->dt != ctxs[0]->dt) return fail(FEDG_ERR_ARG, "the meshes of a group share scheme and step");
+  }
+  // one stream for the whole group: the order of the launches is the dependency order between the meshes
+  fedg_ctx* lead = ctxs[0];
+  std::vector<cudaStream_t> saved(n);
+  for (int i = 0; i < n; ++i) { CUDA_TRY(cudaStreamSynchronize(ctxs[i]->stream)); saved[i] = ctxs[i]->stream; ctxs[i]->stream = lead->stream; }
+  struct Restore { fedg_ctx** c; std::vector<cudaStream_t>& s; int n; ~Restore() { for (int i = 0; i < n; ++i) c[i]->stream = s[i]; } } restore{ctxs, saved, n};
+  for (int i = 0; i < n; ++i) { ensure_tables(ctxs[i]); ensure_dp(ctxs[i], ctxs[i]->cur); }
+  while (lead->ev.size() < 2) { cudaEvent_t e; CUDA_TRY(cudaEventCreate(&e)); lead->ev.push_back(e); }
+  CUDA_TRY(cudaEventRecord(lead->ev[0], lead->stream));
+  const int ns = lead->rk.nstage;
+  long launches = 0;
+  for (int step = 0; step < nsteps; ++step) {
+    for (int i = 0; i < n; ++i) hevi_begin_step(ctxs[i]);
+    for (int s = 0; s < ns; ++s) {
+      for (int i = 0; i < n; ++i) { int rc = hevi_stage_vi(ctxs[i], s, nullptr, nullptr); if (rc) return rc; }     // cal_vi + StoreImplicit
+      for (int i = 0; i < n; ++i) { int rc = hevi_stage_ex(ctxs[i], s); if (rc) return rc; }                        // exchange + cal_tend_ex
+      for (int i = 0; i < n; ++i) hevi_stage_combine(ctxs[i], s);                                                  // Advance
+      launches += 4L * n;
+    }
+    for (int i = 0; i < n; ++i) hevi_end_step(ctxs[i]);
+  }
+  CUDA_TRY(cudaEventRecord(lead->ev[1], lead->stream));
+  CUDA_TRY(cudaStreamSynchronize(lead->stream));
+  CUDA_TRY(cudaGetLastError());
+  float ms = 0;
+  CUDA_TRY(cudaEventElapsedTime(&ms, lead->ev[0], lead->ev[1]));
+  lead->last_ms_total = ms; lead->last_ms_stage = 0; lead->last_launches = launches;
   return FEDG_OK;
 }
 

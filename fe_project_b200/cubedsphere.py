@@ -1,0 +1,194 @@
+"""Host-side set-up of the cubed-sphere panel graph: which face of which panel fills a halo face, in which order, and
+how the horizontal momentum is re-expressed in the receiving panel's basis.
+
+Restates, for one tile per panel (the reference's `Nprc = 6` layout):
+
+* `MeshUtilCubedSphere2D_getPanelConnectivity` (FElib/src/mesh/scale_meshutil_cubedsphere2d.F90:251-290): neighbour
+  panel and *destination* face of every lateral panel face; a negative face id asks for the send buffer to be
+  reverted along the edge.
+* the same-rank path of `MeshFieldCommBase_exchange_core` (FElib/src/data/scale_meshfieldcomm_base.F90:870-895): the
+  boundary data of (tile T, face f) lands in the halo of face |s_faceID| of tile s_tileID.
+* `push_localsendbuf` / `revert_hori` (FElib/src/data/scale_meshfieldcomm_cubedspheredom3d.F90:492-540).
+* `CubedSphereCoordCnv_CS2LonLatVec`, `_LonLat2CSVec`, `_CS2CartPos`
+  (FElib/src/common/scale_cubedsphere_coord_cnv.F90:150-236, 314-401, 406-488) with `gam = 1` (shallow atmosphere):
+  the sender turns (MOMX, MOMY) into lon-lat components at its face nodes, the receiver turns them into its own
+  contravariant components at its own face nodes (`MeshFieldCommCubedSphereDom3D_exchange` :226-420).
+
+The product of the two conversions is a 2x2 matrix per halo node; the device only gathers and applies it
+(`fedg_link_halo`).  `cs2cart` gives an independent, purely geometric check of the tables (tests/test_cubedsphere.py).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from .mesh import LocalMeshCubedSpherePanel
+
+EPS = 2.220446e-16
+
+
+def panel_connectivity():
+    """(panel_connectivity, face_connectivity), 1-based ids, index [face-1][panel-1]."""
+    pc = np.zeros((4, 6), dtype=int)
+    fc = np.zeros((4, 6), dtype=int)
+    zonal = [4, 1, 2, 3, 4, 1]
+    for n in range(1, 5):
+        pc[0, n - 1] = 6
+        fc[0, n - 1] = zonal[4 - n] if zonal[4 - n] > 2 else -zonal[4 - n]
+        pc[1, n - 1] = zonal[n + 1]
+        fc[1, n - 1] = 4
+        pc[2, n - 1] = 5
+        fc[2, n - 1] = -n if n > 2 else n
+        pc[3, n - 1] = zonal[n - 1]
+        fc[3, n - 1] = 2
+    pc[:, 4] = (1, 2, 3, 4); fc[:, 4] = (3, 3, -3, -3)
+    pc[:, 5] = (3, 2, 1, 4); fc[:, 5] = (-1, -1, 1, 1)
+    return pc, fc
+
+
+def cs2cart(panel, a, b, R=1.0):
+    x1, x2 = np.tan(a), np.tan(b)
+    fac = R / np.sqrt(1.0 + x1 ** 2 + x2 ** 2)
+    if panel == 1: return np.stack([fac, fac * x1, fac * x2])
+    if panel == 2: return np.stack([-fac * x1, fac, fac * x2])
+    if panel == 3: return np.stack([-fac, -fac * x1, fac * x2])
+    if panel == 4: return np.stack([fac * x1, -fac, fac * x2])
+    if panel == 5: return np.stack([-fac * x2, fac * x1, fac])
+    return np.stack([fac * x2, fac * x1, -fac])
+
+
+def cs2lonlat(panel, a, b):
+    x, y, z = cs2cart(panel, a, b)
+    return np.arctan2(y, x), np.arcsin(np.clip(z, -1.0, 1.0))
+
+
+def _coslat(panel, X, Y, a, b):
+    if panel <= 4:
+        return np.cos(np.arctan(np.tan(b) * np.cos(a)))
+    s = 1.0 if panel == 5 else -1.0
+    return np.cos(np.arctan(s / np.maximum(np.sqrt(X ** 2 + Y ** 2), EPS)))
+
+
+def cs2lonlat_vec(panel, a, b, va, vb, R):
+    X, Y = np.tan(a), np.tan(b)
+    del2 = 1.0 + X ** 2 + Y ** 2
+    cl = _coslat(panel, X, Y, a, b)
+    if panel <= 4:
+        return va * cl * R, (-X * Y * va + (1.0 + Y ** 2) * vb) * R * np.sqrt(1.0 + X ** 2) / del2
+    r = R if panel == 5 else -R
+    h2 = np.maximum(X ** 2 + Y ** 2, EPS)
+    vlon = (-Y * (1.0 + X ** 2) * va + X * (1.0 + Y ** 2) * vb) * r / h2 * cl
+    vlat = (-X * (1.0 + X ** 2) * va - Y * (1.0 + Y ** 2) * vb) * r / (del2 * np.maximum(np.sqrt(X ** 2 + Y ** 2), EPS))
+    return vlon, vlat
+
+
+def lonlat2cs_vec(panel, a, b, vlon, vlat, R):
+    X, Y = np.tan(a), np.tan(b)
+    del2 = 1.0 + X ** 2 + Y ** 2
+    uc = vlon / _coslat(panel, X, Y, a, b)
+    if panel <= 4:
+        return uc / R, (X * Y * uc + del2 / np.sqrt(1.0 + X ** 2) * vlat) / (R * (1.0 + Y ** 2))
+    r = R if panel == 5 else -R
+    sq = np.sqrt(np.maximum(del2 - 1.0, EPS))
+    return ((-Y * uc - del2 * X / sq * vlat) / (r * (1.0 + X ** 2)),
+            (X * uc - del2 * Y / sq * vlat) / (r * (1.0 + Y ** 2)))
+
+
+def revert_hori(idx, np1, nv, nex, nez):
+    """revert_hori of push_localsendbuf: the face buffer is (Nnode_h1D, Nnode_v, NeX, NeZ), first index fastest."""
+    a = np.asarray(idx).reshape(nez, nex, nv, np1)
+    return a[:, ::-1, :, ::-1].reshape(-1)
+
+
+class CubedSphere:
+    """Six panel tiles + the halo links between them."""
+
+    def __init__(self, elem, Ne, NeZ, ztop, RPlanet, FZ=None):
+        self.elem, self.Ne_h, self.NeZ, self.R = elem, Ne, NeZ, RPlanet
+        self.panels = [LocalMeshCubedSpherePanel(elem, pid, Ne, Ne, NeZ, ztop, RPlanet, FZ=FZ) for pid in range(1, 7)]
+        self.links = self._build_links()
+
+    def _face_nodes(self, mesh, f):
+        """0-based flat interior indices of the boundary nodes of tile face f (0-based) in halo order."""
+        o, n = mesh.halo_face_off[f], mesh.halo_face_size[f]
+        return mesh.VMapB[o:o + n]
+
+    def _build_links(self):
+        """links[U][g] = (T, src_index (0-based into T's fields), rot (n,2,2)) for the four lateral faces g of panel U."""
+        pc, fc = panel_connectivity()
+        e = self.elem
+        npts, nv = e.np1, e.np1
+        links = [dict() for _ in range(6)]
+        for T in range(6):
+            mT = self.panels[T]
+            for f in range(4):
+                U = pc[f, T] - 1
+                g = abs(fc[f, T]) - 1
+                src = self._face_nodes(mT, f)
+                if fc[f, T] < 0:
+                    src = revert_hori(src, npts, nv, self.Ne_h, self.NeZ)
+                mU = self.panels[U]
+                own = self._face_nodes(mU, g)
+                assert own.size == src.size
+                # positions: horizontal coordinates of the 3D nodes
+                aT, bT = mT.pos_en[0].reshape(-1)[src], mT.pos_en[1].reshape(-1)[src]
+                aU, bU = mU.pos_en[0].reshape(-1)[own], mU.pos_en[1].reshape(-1)[own]
+                rot = np.empty((own.size, 2, 2))
+                for c, (va, vb) in enumerate(((1.0, 0.0), (0.0, 1.0))):
+                    vl, vt = cs2lonlat_vec(T + 1, aT, bT, np.full(own.size, va), np.full(own.size, vb), self.R)
+                    ua, ub = lonlat2cs_vec(U + 1, aU, bU, vl, vt, self.R)
+                    rot[:, 0, c], rot[:, 1, c] = ua, ub
+                assert g not in links[U], "two faces feed the same halo face"
+                links[U][g] = (T, src.copy(), rot)
+        for U in range(6):
+            assert sorted(links[U]) == [0, 1, 2, 3]
+        return links
+
+    def exchange_numpy(self, fields, vector_pairs=(("MOMX", "MOMY"),)):
+        """fields: list of 6 dicts name -> (NeA*Np,) arrays.  Fills the lateral halos (reference semantics) in place."""
+        vec = {n for pr in vector_pairs for n in pr}
+        for U in range(6):
+            mU = self.panels[U]
+            nint = mU.Ne * self.elem.Np
+            for g, (T, src, rot) in self.links[U].items():
+                o = mU.halo_face_off[g]
+                sl = slice(nint + o, nint + o + src.size)
+                for name, arr in fields[U].items():
+                    if name not in vec:
+                        arr[sl] = fields[T][name][src]
+                for nx_, ny_ in vector_pairs:
+                    if nx_ in fields[U]:
+                        sx, sy = fields[T][nx_][src], fields[T][ny_][src]
+                        fields[U][nx_][sl] = rot[:, 0, 0] * sx + rot[:, 0, 1] * sy
+                        fields[U][ny_][sl] = rot[:, 1, 0] * sx + rot[:, 1, 1] * sy
+
+
+class GlobalSphereDriver:
+    """The six local meshes of the global model on one GPU: one `AtmDynDGMDriver_nonhydro3d` per panel, linked halos,
+    stage-synchronous stepping (`fedg_group_update`), i.e. what `AtmDynDGMDriver_nonhydro3d%Update` does with
+    `LOCAL_MESH_NUM = 6` (fluid_dyn_solver/scale_atm_dyn_dgm_driver_nonhydro3d.F90:703-921)."""
+
+    def __init__(self, cs: CubedSphere, consts: dict, vel_bc=None):
+        import ctypes as C
+        from . import _lib
+        from .dyncore import AtmDynDGMDriver_nonhydro3d
+        self.cs, self.L = cs, _lib.load()
+        self.panels = [AtmDynDGMDriver_nonhydro3d(cs.elem, m, consts, vel_bc=vel_bc or dict(btm="SLIP", top="SLIP")) for m in cs.panels]
+        self._keep = []
+        for U, d in enumerate(self.panels):
+            for g, (T, src, rot) in cs.links[U].items():
+                idx = np.ascontiguousarray(src + 1, dtype=np.int32)
+                r = np.ascontiguousarray(rot.reshape(-1, 4), dtype=np.float64)        # [r00, r01, r10, r11] per node
+                self._keep += [idx, r]
+                _lib.check(self.L.fedg_link_halo(d.h, g + 1, self.panels[T].h, idx.ctypes.data_as(C.c_void_p), r.ctypes.data_as(C.c_void_p)))
+        self._h = (C.c_void_p * 6)(*[d.h for d in self.panels])
+
+    def Init(self, *a, **kw):
+        for d in self.panels:
+            d.Init(*a, **kw)
+
+    def Update(self, nsteps=1):
+        from . import _lib
+        _lib.check(self.L.fedg_group_update(self._h, 6, int(nsteps)))
+
+    def last_timing(self):
+        return self.panels[0].last_timing()

@@ -187,6 +187,21 @@ int fedg_last_timing(fedg_ctx* ctx, double* ms_total, double* ms_stage_kernels, 
 int fedg_comm_unique_id(void* id128);
 int fedg_comm_init(fedg_ctx* ctx, const void* id128, int rank, int nranks);
 
+/* ---- several local meshes on one device (LOCAL_MESH_NUM > 1; cubed-sphere panels) ------------------------------
+ * fedg_link_halo: the halo of tile face `face` (1..6) of `ctx` is filled from the interior of `src`, another local mesh on
+ * the same device -- the same-rank path of MeshFieldCommBase_exchange_core (data/scale_meshfieldcomm_base.F90:870-895).
+ * src_index(n): 1-based interior index (into the (Np,Ne) part of src's fields) feeding each halo slot of the face, in
+ * halo order; it encodes tileID_globalMap / tileFaceID_globalMap and, for a negative face id, revert_hori
+ * (data/scale_meshfieldcomm_cubedspheredom3d.F90:492-540).  rot(4,n) (may be NULL): per halo node the matrix
+ * [r00 r01; r10 r11] that turns the source's (MOMX, MOMY) into the receiver's components, i.e.
+ * LonLat2CSVec(own panel, own face node) o CS2LonLatVec(source panel, source node)
+ * (MeshFieldCommCubedSphereDom3D_exchange :226-420, common/scale_cubedsphere_coord_cnv.F90:150-236, 314-401). */
+int fedg_link_halo(fedg_ctx* ctx, int face, fedg_ctx* src, const int* src_index, const double* rot);
+/* AtmDynDGMDriver_nonhydro3d%Update over the local meshes of a rank (the `do n = 1, LOCAL_MESH_NUM` loops of
+ * driver_nonhydro3d.F90:703-921): every stage piece runs on all meshes before the next one starts, so that linked halos
+ * see the neighbours' stage state.  HEVI equation sets. */
+int fedg_group_update(fedg_ctx** ctxs, int n, int nsteps);
+
 /* ---- sample/advect3d (BASELINE config 1) --------------------------------------------------------------
  * `sparsemat` in ELL storage as the reference holds it (common/scale_sparsemat.F90:33-55, 100-250):
  * val(M*col_size), colIdx(M*col_size), slot-major l = i + (k-1)*M (:172), colIdx 1-based. */

@@ -146,6 +146,44 @@ int feo_prepare(void* hv) {
 // physics tendencies on / off (the arrays are DENS_tp ... RHOH_p of feo_array)
 void feo_set_phytend(void* hv, int on) { static_cast<Handle*>(hv)->d.phytend = on != 0; }
 
+// ---- whole cubed sphere: six panel handles (created with feo_create_panel, panel ids 1..6 in order)
+int feo_sphere_exchange(void** hv6, int with_dpres) {
+  return guard([&] {
+    Mesh* mesh[6]; std::vector<double*> sc[6]; double* u1[6]; double* u2[6];
+    for (int p = 0; p < 6; ++p) {
+      auto& d = static_cast<Handle*>(hv6[p])->d;
+      if (d.mesh.panelID != p + 1) throw std::runtime_error("panels must be passed in the order 1..6");
+      mesh[p] = &d.mesh;
+      for (int v = 0; v < 5; ++v) d.mesh.exchange_halo(d.elem, d.st.prog(v));
+      sc[p] = {d.st.DDENS.data(), d.st.DRHOT.data(), d.st.MOMZ.data()};
+      if (with_dpres) { d.mesh.exchange_halo(d.elem, d.st.DPRES.data()); sc[p].push_back(d.st.DPRES.data()); }
+      u1[p] = d.st.MOMX.data(); u2[p] = d.st.MOMY.data();
+    }
+    sphere_exchange(static_cast<Handle*>(hv6[0])->d.elem, mesh, sc, u1, u2);
+  });
+}
+// exchange of the background fields after set-up (scalars only)
+int feo_sphere_exchange_aux(void** hv6) {
+  return guard([&] {
+    Mesh* mesh[6]; std::vector<double*> sc[6]; double* u1[6]; double* u2[6];
+    for (int p = 0; p < 6; ++p) {
+      auto& d = static_cast<Handle*>(hv6[p])->d;
+      mesh[p] = &d.mesh;
+      sc[p] = {d.st.DENS_hyd.data(), d.st.PRES_hyd.data(), d.st.THERM_hyd.data(), d.st.PRES_hyd_ref.data(), d.st.Rtot.data(),
+               d.st.CVtot.data(), d.st.CPtot.data(), d.st.PRES.data(), d.st.DPRES.data()};
+      u1[p] = u2[p] = nullptr;
+    }
+    sphere_exchange(static_cast<Handle*>(hv6[0])->d.elem, mesh, sc, u1, u2);
+  });
+}
+int feo_sphere_update(void** hv6, int nsteps) {
+  return guard([&] {
+    Driver* d[6];
+    for (int p = 0; p < 6; ++p) { d[p] = &static_cast<Handle*>(hv6[p])->d; if (!d[p]->global) throw std::runtime_error("sphere needs GLOBALNONHYDRO3D_HEVI"); }
+    for (int n = 0; n < nsteps; ++n) sphere_update(d);
+  });
+}
+
 int feo_update(void* hv, int nsteps) {
   auto* h = static_cast<Handle*>(hv);
   return guard([&] { for (int n = 0; n < nsteps; ++n) h->d.update(); });

@@ -189,6 +189,10 @@ struct Driver {
   void update();  // fluid_dyn_solver/scale_atm_dyn_dgm_driver_nonhydro3d.F90:614-963
 };
 
+// whole cubed sphere (sphere.cpp): panel-edge exchange and the six-panel step
+void sphere_exchange(const Element& e, Mesh* const mesh[6], const std::vector<double*> scal[6], double* const u1[6], double* const u2[6]);
+void sphere_update(Driver* d[6]);
+
 // monitors: file/scale_file_monitor_meshfield.F90:176-213 + model mod_atmos_vars_container.F90:1281-1357
 void monitor_sums(const Driver& d, double out[5]);  // DDENS mass, ENGT, ENGK, ENGI, ENGP
 

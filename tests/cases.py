@@ -150,6 +150,78 @@ class GlobalPanelCase(DensityCurrentCase):
         return o
 
 
+class GlobalSphereCase:
+    """The whole cubed sphere, six panel tiles of Ne x Ne x NeZ elements (BASELINE config 4 in small): isothermal atmosphere in
+    solid-body rotation (gradient-wind balance) plus, when perturb != 0, a second solid-body rotation about a tilted axis
+    (smooth across every panel edge and both poles), a vertical-velocity pattern and a warm blob."""
+
+    def __init__(self, p=7, Ne=2, NeZ=2, ztop=30.0e3, dt=20.0, tinteg="IMEX_ARK324", modalfilter=True, u0=30.0, T0=300.0, perturb=1.0):
+        from fe_project_b200.cubedsphere import CubedSphere, cs2cart, cs2lonlat, lonlat2cs_vec
+        self.p, self.dt, self.tinteg, self.modalfilter, self.ztop = p, dt, tinteg, modalfilter, ztop
+        self.eqs = "GLOBALNONHYDRO3D_HEVI"
+        self.elem = HexElement(p)
+        self.consts = c = dict(C0)
+        self.cs = CubedSphere(self.elem, Ne, NeZ, ztop, c["RPlanet"])
+        self.vel_bc = dict(btm="SLIP", top="SLIP")
+        H = c["Rdry"] * T0 / c["GRAV"]
+        amp = (u0 ** 2 + 2.0 * c["RPlanet"] * c["OHM"] * u0) / (2.0 * c["Rdry"] * T0)
+        w2 = perturb * 8.0 / c["RPlanet"] * np.array([0.6, -0.3, 0.74])          # tilted rotation vector [1/s]
+        self.fields = []
+        for P, m in enumerate(self.cs.panels):
+            Np, NeA, Nel = self.elem.Np, m.NeA, m.Ne
+            a, b, z = m.pos_en[0], m.pos_en[1], m.pos_en[2]
+            lon, lat = cs2lonlat(P + 1, a, b)
+            pres_hyd = c["PRES00"] * np.exp(-z / H)
+            dens_hyd = pres_hyd / (c["Rdry"] * T0)
+            pres = pres_hyd * np.exp(-amp * np.sin(lat) ** 2)
+            x = cs2cart(P + 1, a, b)                                               # unit sphere
+            blob = perturb * 2.0 * np.exp(-((x[0] - 0.5) ** 2 + (x[1] - 0.6) ** 2 + (x[2] - 0.62) ** 2) / 0.3 ** 2) * np.sin(np.pi * z / ztop)
+            temp = T0 + blob
+            dens = pres / (c["Rdry"] * temp)
+            theta = temp * (c["PRES00"] / pres) ** (c["Rdry"] / c["CPdry"])
+            rhot_hyd = c["PRES00"] / c["Rdry"] * (pres_hyd / c["PRES00"]) ** (c["CVdry"] / c["CPdry"])
+            # wind: u0 cos(lat) zonal + w2 x r
+            v3 = np.stack([w2[1] * x[2] - w2[2] * x[1], w2[2] * x[0] - w2[0] * x[2], w2[0] * x[1] - w2[1] * x[0]]) * c["RPlanet"]
+            elon = np.stack([-np.sin(lon), np.cos(lon), np.zeros_like(lon)])
+            elat = np.stack([-np.sin(lat) * np.cos(lon), -np.sin(lat) * np.sin(lon), np.cos(lat)])
+            ul = u0 * np.cos(lat) + np.sum(v3 * elon, axis=0)
+            vl = np.sum(v3 * elat, axis=0)
+            ua, ub = lonlat2cs_vec(P + 1, a, b, ul, vl, c["RPlanet"])
+            f = {k: np.zeros((NeA, Np)) for k in ("DDENS", "MOMX", "MOMY", "MOMZ", "DRHOT", "DENS_hyd", "PRES_hyd")}
+            f["DENS_hyd"][:Nel] = dens_hyd; f["PRES_hyd"][:Nel] = pres_hyd
+            f["DDENS"][:Nel] = dens - dens_hyd
+            f["DRHOT"][:Nel] = dens * theta - rhot_hyd
+            f["MOMX"][:Nel] = dens * ua; f["MOMY"][:Nel] = dens * ub
+            f["MOMZ"][:Nel] = perturb * dens * 0.05 * x[0] * x[1] * np.sin(np.pi * z / ztop)
+            self.fields.append(f)
+
+    def make_oracle(self):
+        from oracle_api import Oracle, OracleSphere
+        c = self.consts
+        panels = []
+        for P, m in enumerate(self.cs.panels):
+            o = Oracle(self.p, m.NeX, m.NeY, m.NeZ, panel=dict(panelID=P + 1, ztop=self.ztop, RPlanet=c["RPlanet"]))
+            o.set_consts(c)
+            for k, v in self.fields[P].items():
+                o.arr(k)[:] = v.reshape(-1)
+            o.arr("Rtot")[:] = c["Rdry"]; o.arr("CVtot")[:] = c["CVdry"]; o.arr("CPtot")[:] = c["CPdry"]
+            o.setup_dyn(self.eqs, self.tinteg, self.dt, self.modalfilter, (2.0 / 3.0, 1.0, 16, 2.0 / 3.0, 1.0, 16), (0, 0, 0, 0, 2, 2))
+            o.prepare()
+            panels.append(o)
+        s = OracleSphere(panels)
+        s.exchange_aux()
+        return s
+
+    def make_driver(self):
+        from fe_project_b200.cubedsphere import GlobalSphereDriver
+        g = GlobalSphereDriver(self.cs, self.consts, vel_bc=self.vel_bc)
+        g.Init(self.eqs, self.tinteg, self.dt, MODALFILTER_FLAG=self.modalfilter, **MF)
+        for d, f in zip(g.panels, self.fields):
+            d.set_aux(f["DENS_hyd"], f["PRES_hyd"])
+            d.set_prog(*(f[k] for k in ("DDENS", "MOMX", "MOMY", "MOMZ", "DRHOT")))
+        return g
+
+
 def rel_l2(a, b):
     a = np.asarray(a).reshape(-1); b = np.asarray(b).reshape(-1)
     nb = np.linalg.norm(b)

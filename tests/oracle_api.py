@@ -39,6 +39,9 @@ def lib():
         L.feo_prepare.argtypes = [C.c_void_p]
         L.feo_update.argtypes = [C.c_void_p, C.c_int]
         L.feo_set_phytend.argtypes = [C.c_void_p, C.c_int]
+        L.feo_sphere_exchange.argtypes = [C.c_void_p, C.c_int]
+        L.feo_sphere_exchange_aux.argtypes = [C.c_void_p]
+        L.feo_sphere_update.argtypes = [C.c_void_p, C.c_int]
         L.feo_monitor.argtypes = [C.c_void_p, C.c_void_p]
         L.feo_cal_vi.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_void_p, C.c_void_p]
         L.feo_stage_piece.argtypes = [C.c_void_p, C.c_char_p]
@@ -166,6 +169,28 @@ class Oracle:
         out = np.zeros((self.Np, self.Np))
         lib().feo_dmat_dense(self.h, d, _p(out))
         return out
+
+
+class OracleSphere:
+    """Six panel oracles (GLOBALNONHYDRO3D_HEVI) + the panel-edge exchange and the six-panel step."""
+
+    def __init__(self, panels):
+        assert len(panels) == 6
+        self.panels = list(panels)
+        self._h = (C.c_void_p * 6)(*[p.h for p in self.panels])
+
+    def _chk(self, rc):
+        if rc:
+            raise RuntimeError(lib().feo_last_error().decode())
+
+    def exchange(self, with_dpres=True):
+        self._chk(lib().feo_sphere_exchange(self._h, int(with_dpres)))
+
+    def exchange_aux(self):
+        self._chk(lib().feo_sphere_exchange_aux(self._h))
+
+    def update(self, nsteps=1):
+        self._chk(lib().feo_sphere_update(self._h, int(nsteps)))
 
 
 class OracleAdvect3D:

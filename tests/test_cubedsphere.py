@@ -1,0 +1,95 @@
+"""Panel-edge exchange of the cubed sphere (row e, global part) and the six-panel step of the oracle.
+The tables of the reference (getPanelConnectivity, revert_hori, CS2LonLatVec / LonLat2CSVec) are restated twice
+(NumPy: fe_project_b200/cubedsphere.py, C++: oracle/sphere.cpp) and pinned geometrically: the source node of every
+halo slot is the same physical point as the receiver's own face node, and globally continuous scalar / vector fields
+come back from the exchange equal to the own-face values."""
+import numpy as np
+import pytest
+
+from cases import GlobalSphereCase
+from fe_project_b200.cubedsphere import CubedSphere, cs2cart, panel_connectivity
+from fe_project_b200.element import HexElement
+
+
+def test_connectivity_is_geometrically_consistent():
+    pc, fc = panel_connectivity()
+    for T in range(6):                         # the graph is symmetric
+        for f in range(4):
+            U, g = pc[f, T] - 1, abs(fc[f, T]) - 1
+            assert pc[g, U] - 1 == T and abs(fc[g, U]) - 1 == f
+    cs = CubedSphere(HexElement(3), 3, 2, 30.0e3, 6.37122e6)
+    for U in range(6):
+        mU = cs.panels[U]
+        for g, (T, src, rot) in cs.links[U].items():
+            mT = cs.panels[T]
+            own = cs._face_nodes(mU, g)
+            pU = cs2cart(U + 1, mU.pos_en[0].reshape(-1)[own], mU.pos_en[1].reshape(-1)[own])
+            pT = cs2cart(T + 1, mT.pos_en[0].reshape(-1)[src], mT.pos_en[1].reshape(-1)[src])
+            assert np.abs(pU - pT).max() <= 1e-14
+            assert np.abs(mU.pos_en[2].reshape(-1)[own] - mT.pos_en[2].reshape(-1)[src]).max() <= 1e-9
+            assert np.abs(np.linalg.det(rot)).min() > 0.3      # the basis change never degenerates on an edge
+
+
+def test_exchange_two_restatements_and_continuity():
+    case = GlobalSphereCase(p=3, Ne=3, NeZ=2)
+    s = case.make_oracle()
+    s.exchange(with_dpres=False)
+    Np = case.elem.Np
+    fields = [{k: f[k].reshape(-1).copy() for k in ("DDENS", "DRHOT", "MOMZ", "MOMX", "MOMY")} for f in case.fields]
+    case.cs.exchange_numpy(fields)
+    for P, m in enumerate(case.cs.panels):
+        nint = m.Ne * Np
+        lat = slice(nint, nint + m.halo_face_off[4])            # the four lateral faces
+        for k in ("DDENS", "DRHOT", "MOMZ", "MOMX", "MOMY"):
+            a = s.panels[P].arr(k)
+            sc = np.abs(a[:nint]).max()
+            assert np.abs(a[lat] - fields[P][k][lat]).max() <= 1e-13 * sc, (P, k)          # C++ == NumPy
+            own = a[m.VMapB[: m.halo_face_off[4]]]
+            assert np.abs(a[lat] - own).max() <= 1e-12 * sc, (P, k)                          # continuous field: halo == own face
+
+
+def _sphere_tend(case):
+    s = case.make_oracle()
+    for o in s.panels:
+        o.piece("pressure")
+    s.exchange(with_dpres=True)
+    out = []
+    for o, m in zip(s.panels, case.cs.panels):
+        o.piece("bc"); o.piece("tend_ex")
+        n, N = m.Ne * case.elem.Np, m.NeA * case.elem.Np
+        out.append(o.arr("tend_ex")[:5 * N].reshape(5, -1)[:, :n].copy())
+    return s, out
+
+
+def test_balanced_rotation_is_steady_on_the_whole_sphere():
+    """Including the polar panels and every panel edge: converges spectrally with p."""
+    cor = 2 * 7.292e-5 * 30.0 / 6.37122e6
+    errs = []
+    for p in (3, 5, 7):
+        _, te = _sphere_tend(GlobalSphereCase(p=p, Ne=2, NeZ=2, perturb=0.0))
+        errs.append(max(max(np.abs(t[3]).max(), np.abs(t[4]).max()) for t in te))
+    assert errs[0] < 0.2 * cor and errs[1] < 0.1 * errs[0] and errs[2] < 0.1 * errs[1], errs
+
+
+def test_mass_is_conserved_over_the_closed_sphere():
+    """Sum over the six panels of the DDENS tendency integral vanishes to round-off: the flux leaving a panel edge enters the
+    neighbour (it does not on a single panel, whose lateral halo mirrors its own values)."""
+    case = GlobalSphereCase(p=4, Ne=2, NeZ=2)
+    _, te = _sphere_tend(case)
+    tot, scale = 0.0, 0.0
+    for t, m in zip(te, case.cs.panels):
+        n = m.Ne * case.elem.Np
+        w = np.tile(case.elem.IntWeight_lgl, m.Ne) * m.J.reshape(-1) * m.Gsqrt.reshape(-1)[:n]
+        tot += np.sum(w * t[0]); scale += np.sum(w * np.abs(t[0]))
+    assert abs(tot) <= 1e-12 * scale, (tot, scale)
+
+
+def test_six_panel_steps_stay_finite():
+    case = GlobalSphereCase(p=5, Ne=2, NeZ=3, dt=30.0)
+    s = case.make_oracle()
+    s.update(4)
+    for o, m in zip(s.panels, case.cs.panels):
+        n = m.Ne * case.elem.Np
+        for k in ("DDENS", "MOMX", "MOMY", "MOMZ", "DRHOT"):
+            assert np.isfinite(o.arr(k)[:n]).all()
+        assert np.abs(o.arr("MOMZ")[:n]).max() < 2.0

@@ -3,7 +3,7 @@ Bar (BASELINE.json north_star): relative L2 error of every prognostic variable <
 import numpy as np
 import pytest
 
-from cases import DensityCurrentCase, GlobalPanelCase, SoundWaveCase, rel_l2, C0
+from cases import DensityCurrentCase, GlobalPanelCase, GlobalSphereCase, SoundWaveCase, rel_l2, C0
 
 pytestmark = pytest.mark.gpu
 TOL = 1.0e-10
@@ -401,3 +401,47 @@ def test_physics_tendencies_row_a17(p, eqs, tinteg, dt):
     # and they matter: switching them off changes the answer
     d2 = case.make_driver(o); d2.Update(5)
     assert rel_l2(d2.get_prog()["DRHOT"][:n], g["DRHOT"][:n]) > 1e-6
+
+
+# ------------------------------------------------------------------------------ whole cubed sphere: six linked local meshes
+def test_sphere_halo_links():
+    """fedg_link_halo: panel-edge halos (index reversal + basis change of (MOMX, MOMY)) == the oracle's exchange."""
+    case = GlobalSphereCase(p=7, Ne=2, NeZ=2)
+    s = case.make_oracle()
+    g = case.make_driver()
+    for o in s.panels:
+        o.piece("pressure")
+    s.exchange(with_dpres=True)
+    for d in g.panels:
+        d.get_pres()                       # DPRES of every panel on the device before the gathers
+    for P, (d, o, m) in enumerate(zip(g.panels, s.panels, case.cs.panels)):
+        d.exchange_halo(apply_bc=False)
+        got = d.get_prog()
+        n = m.Ne * case.elem.Np
+        for nm in PROG:
+            ref = o.arr(nm)
+            sc = np.abs(ref[:n]).max()
+            assert np.abs(got[nm][n:n + m.Nhalo] - ref[n:n + m.Nhalo]).max() <= 1e-13 * sc, (P, nm)
+
+
+@pytest.mark.parametrize("tinteg,dt,Ne,NeZ", [("IMEX_ARK324", 20.0, 2, 3), ("IMEX_ARK232", 15.0, 3, 2)])
+def test_sphere_steps(tinteg, dt, Ne, NeZ):
+    """GLOBALNONHYDRO3D_HEVI on the whole sphere (config 4 in small): six panels advanced together on one GPU."""
+    case = GlobalSphereCase(p=7, Ne=Ne, NeZ=NeZ, dt=dt, tinteg=tinteg)
+    s = case.make_oracle()
+    g = case.make_driver()
+    s.update(5); g.Update(5)
+    tot_o = tot_g = 0.0
+    for P, (d, o, m) in enumerate(zip(g.panels, s.panels, case.cs.panels)):
+        got = d.get_prog()
+        n = m.Ne * case.elem.Np
+        for nm in PROG:
+            assert rel_l2(got[nm][:n], o.arr(nm)[:n]) <= TOL, (P, nm)
+        w = np.tile(case.elem.IntWeight_lgl, m.Ne) * m.J.reshape(-1) * m.Gsqrt.reshape(-1)[:n]
+        tot_o += np.sum(w * o.arr("DDENS")[:n]); tot_g += np.sum(w * got["DDENS"][:n])
+    # mass of the closed sphere: same as the oracle's and conserved over the steps
+    m0 = sum(np.sum(np.tile(case.elem.IntWeight_lgl, m.Ne) * m.J.reshape(-1) * m.Gsqrt.reshape(-1)[:m.Ne * case.elem.Np] * f["DDENS"][:m.Ne].reshape(-1))
+             for m, f in zip(case.cs.panels, case.fields))
+    vol = 4 * np.pi * C0["RPlanet"] ** 2 * case.ztop
+    assert abs(tot_g - tot_o) <= 1e-13 * vol
+    assert abs(tot_g - m0) <= 1e-12 * vol
