@@ -633,6 +633,7 @@ void fill_stage_params(fedg_ctx* c, StageParams& P, int in, int out, int q0) {
   for (int k = 0; k < 6; ++k) P.phyt[k] = c->phyt[k].p;
   P.has_phyt = c->has_phyt;
   { static int fp = -1; if (fp < 0) { const char* e = getenv("FEDG_FAST_POW"); fp = (e && e[0] == '1') ? 1 : 0; } P.fast_pow = fp; }
+  { static int pf = -1; if (pf < 0) { const char* e = getenv("FEDG_P7_PREFETCH"); pf = e ? atoi(e) : 0; } P.prefetch_dist = pf; }   // experiment knob, off: see DESIGN.md 4.1
 }
 
 // DPRES of prog[buf] (interior): produced by the stage kernel that wrote prog[buf]; computed here only after the

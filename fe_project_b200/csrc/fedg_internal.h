@@ -72,6 +72,7 @@ struct StageParams {
   // physics tendencies DENS_tp, MOMX_tp, MOMY_tp, MOMZ_tp, RHOT_tp, RHOH_p (add_phy_tend, driver_nonhydro3d.F90:1098-1178)
   const double* phyt[6];
   int has_phyt;
+  int prefetch_dist;     // stage_p7: elements ahead whose inputs are pulled into L2 (0 = off)
 };
 
 struct HaloParams {

@@ -25,6 +25,10 @@ __device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t
                "l"(src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
+// L2 prefetch of a contiguous global range (no destination, no completion tracking)
+__device__ __forceinline__ void tma_prefetch_l2(const void* src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t done;
   asm volatile(
