@@ -23,8 +23,16 @@ import sys
 import tempfile
 import time
 
-# NCCL writes its banner / debug lines to stdout by default: the contract is ONE JSON line on stdout
-os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+# The contract is ONE JSON line on stdout, but NCCL / torch write banners ("NCCL version ...") to file descriptor 1 from
+# native code: everything goes to stderr until the result line is printed through the saved descriptor.
+_STDOUT_FD = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(line: dict):
+    sys.stdout.flush()
+    os.write(_STDOUT_FD, (json.dumps(line) + "\n").encode())
+
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 for _p in (ROOT, os.path.join(ROOT, "tests")):
@@ -132,7 +140,7 @@ def run_reference(args, rank, world):
                 e2e=dict(value=best["value"], unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0),
                 note="CPU oracle = reference-equivalent C++ restatement (g++ -O3 -fopenmp); the Fortran reference "
                      "needs gfortran+MPI+SCALE 5.5.5, none of which exist in this image")
-    print(json.dumps(line))
+    emit(line)
 
 
 def run_advect3d(args):
@@ -179,7 +187,7 @@ def run_advect3d(args):
     peak, peak_src = read_peaks()
     alg = 8 * 8.0 * dof
     ms_stage = tm["ms_total"] / (K * 4)
-    print(json.dumps(dict(
+    emit(dict(
         metric=METRIC.replace("nonhydro3d p=7", "advect3d p=3"), value=value, unit=UNIT, n_gpus=1, steps=K, warmup=W,
         ms_per_step=tm["ms_total"] / K, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64", data="synthetic",
         config=dict(workload="sample/advect3d 8x8x8 elements p=3, ERK_4s4o, dt=0.008, gaussian hill, u=v=w=0.5, triply periodic",
@@ -190,7 +198,7 @@ def run_advect3d(args):
                       traffic=None, kernel="advect_stage_kernel (halo kernel + stage kernel per RK stage, graph replay)", ms_per_launch=ms_stage,
                       algorithmic_bytes_per_launch=alg, peak_source=peak_src,
                       note="512 elements = 128 blocks < 148 SMs: the case cannot fill the device; the number documents launch latency"),
-        cpu_baseline=cpu, finite=bool(np.isfinite(q2).all()))))
+        cpu_baseline=cpu, finite=bool(np.isfinite(q2).all())))
 
 
 def run_sphere(args):
@@ -229,7 +237,7 @@ def run_sphere(args):
     nstage = 4
     # vertical-implicit column solve dominates: same accounting as the regional HEVI line (15.1 kflop per column-element)
     ms_vi = None
-    print(json.dumps(dict(
+    emit(dict(
         metric=METRIC, value=value, unit=UNIT, n_gpus=1, steps=K, warmup=W, ms_per_step=tm["ms_total"] / K, higher_is_better=True,
         scaling="weak", vs_baseline=None, dtype="f64", data="synthetic",
         config=dict(workload=f"atm_nonhydro3d global cubed sphere 6x{ne}x{ne}x{nez} elements p=7, GLOBALNONHYDRO3D_HEVI, IMEX_ARK324, "
@@ -239,7 +247,7 @@ def run_sphere(args):
         gpu_launches=tm["launches"],
         roofline=dict(bound="fp64", achieved=None, peak=34.07, unit="TFLOP/s", frac=None, traffic=None,
                       kernel="vi_column_kernel (see the global_panel line for its per-launch figures)", ms_per_launch=ms_vi),
-        cpu_baseline=None, finite=bool(finite))))
+        cpu_baseline=None, finite=bool(finite)))
 
 
 def main():
@@ -406,7 +414,7 @@ def main():
                            algorithmic_flops_per_launch=15.1e3 * Ne * 64, reduced_flops_per_launch=11.0e3 * Ne * 64,
                            peak_source="measured DFMA peak, profiles/r01_fp64_peak.txt")),
             cpu_baseline=cpu, finite=bool(finite))
-        print(json.dumps(line))
+        emit(line)
     if dist:
         dist.destroy_process_group()
 
