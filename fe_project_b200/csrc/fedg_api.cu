@@ -101,6 +101,9 @@ struct fedg_ctx {
   int* d_elem_inner = nullptr; int* d_elem_bnd = nullptr; int n_inner = 0, n_bnd = 0;
   int cur = 0;
   AdvectState adv;
+  // numerical diffusion (fedg_numdiff_init): PARAM_ATMOS_DYN_NUMDIFF, thermal BC ids, work fields
+  struct { bool on = false, in_update = false; int lap_num = 1; double coef_h = 0, coef_v = 0; int therm_bc[6] = {0, 0, 0, 0, 0, 0}; } nd;
+  DevBuf nd_g[3], nd_lap[2];
   // halo faces filled from another local mesh on the same device (cubed-sphere panel edges): fedg_link_halo
   struct HaloLink { fedg_ctx* src = nullptr; int* d_src = nullptr; double* d_rot = nullptr; int off = 0, cnt = 0; } link[6];
   int xbuf = 0;                    // buffer that holds the state other local meshes gather from (stage input of the explicit part)
@@ -122,6 +125,8 @@ struct fedg_ctx {
     for (auto& l : link) { if (l.d_src) cudaFree(l.d_src); if (l.d_rot) cudaFree(l.d_rot); }
     adv.release();
     for (auto& b : phyt) b.release();
+    for (auto& b : nd_g) b.release();
+    for (auto& b : nd_lap) b.release();
     for (auto& b : dp) b.release();
     for (auto& s : prog) for (auto& b : s) b.release();
     for (auto& b : vt) b.release();
@@ -646,6 +651,7 @@ void ensure_dp(fedg_ctx* c, int buf) {
 }
 
 int exchange_and_stage(fedg_ctx* c, StageParams& P, int buf, bool hevi, cudaEvent_t e0 = nullptr, cudaEvent_t e1 = nullptr);
+int run_numdiff(fedg_ctx* c, int buf);
 
 void fill_vi_params(fedg_ctx* c, VIParams& V, int in, int out, int i0, int stage, double impl_fac) {
   for (int v = 0; v < NVAR; ++v) {
@@ -719,6 +725,7 @@ int run_steps_hevi(fedg_ctx* c, int nsteps, size_t& iev, long& launches) {
       launches += 4;
     }
     hevi_end_step(c);
+    if (c->nd.on && c->nd.in_update) { int rc = run_numdiff(c, c->cur); if (rc) return rc; }
   }
   return FEDG_OK;
 }
@@ -749,6 +756,75 @@ int exchange_and_stage(fedg_ctx* c, StageParams& P, int buf, bool hevi, cudaEven
     launch_stage(P, c->np, c->terrain, c->moist, hevi, c->stream);
   }
   P.elem_list = nullptr; P.nelem = 0;
+  return FEDG_OK;
+}
+
+// halo of auxiliary work fields: same-tile faces by gather, remote faces through the six-slot NCCL exchange
+int exchange_work_fields(fedg_ctx* c, double* const f[], int nf) {
+  for (int k = 0; k < nf; ++k)
+    if (c->Nhalo > 0) aux_halo_kernel<<<(c->Nhalo + 255) / 256, 256, 0, c->stream>>>(f[k], c->d_halo_src, int(c->nint), c->Nhalo);
+  if (c->comm.active && c->comm.nremote > 0) {
+    double* q[NVAR];
+    for (int v = 0; v < NVAR; ++v) q[v] = f[v % nf];
+    std::string err;
+    int rc = comm_exchange_start(c->comm, q, f[(nf - 1)], c->d_vmapB, c->nint, c->stream, err);
+    if (rc) return fail(rc, err);
+    comm_exchange_wait(c->comm, c->stream);
+  }
+  return FEDG_OK;
+}
+
+// AtmDyn_Nonhydro3D_Numdiff%Apply on prog[buf] (numdiff.F90:214-376)
+int run_numdiff(fedg_ctx* c, int buf) {
+  for (auto& b : c->nd_g) if (b.n < c->nall) CUDA_TRY(b.alloc(c->nall));
+  if (c->nd.lap_num > 1) for (auto& b : c->nd_lap) if (b.n < c->nall) CUDA_TRY(b.alloc(c->nall));
+  ensure_tables(c);
+  // PROG_VARS%MeshFieldComm_Exchange (no boundary condition: the numdiff rules are applied at the face nodes)
+  ensure_dp(c, buf);
+  fill_halo(c, buf, false);
+  if (c->comm.active && c->comm.nremote > 0) {
+    double* q[NVAR];
+    for (int v = 0; v < NVAR; ++v) q[v] = c->prog[buf][v].p;
+    std::string err;
+    int rc = comm_exchange_start(c->comm, q, c->dp[buf].p, c->d_vmapB, c->nint, c->stream, err);
+    if (rc) return fail(rc, err);
+    comm_exchange_wait(c->comm, c->stream);
+  }
+  NumdiffParams P{};
+  P.ddens = c->prog[buf][V_DDENS].p; P.dens_hyd = c->dens_hyd.p; P.tab = c->d_tab;
+  P.escale = c->escale.p; P.fscale = c->fscale.p; P.vmapP = c->d_vmapP;
+  for (int f = 0; f < 6; ++f) {
+    const bool phys = c->nbr_rank[f] == c->my_rank && c->nbr_face[f] == f;
+    P.vel_bc[f] = phys ? c->vel_bc[f] : 0; P.therm_bc[f] = phys ? c->nd.therm_bc[f] : 0;
+  }
+  for (int f = 0; f < 7; ++f) P.face_off[f] = c->face_off[f];
+  P.Np = c->Np; P.Nfp = c->Nfp; P.NfpTot = c->NfpTot; P.np = c->np; P.Ne = c->Ne; P.nint = c->nint; P.dt = c->dt;
+  const double nd_sign = ((c->nd.lap_num + 1) % 2 == 0) ? 1.0 : -1.0;
+  const int order[NVAR] = {V_DRHOT, V_MOMZ, V_MOMX, V_MOMY, V_DDENS};
+  double* g[3] = {c->nd_g[0].p, c->nd_g[1].p, c->nd_g[2].p};
+  for (int iv = 0; iv < NVAR; ++iv) {
+    const int v = order[iv];
+    const bool dens_weight = v != V_DDENS;
+    double* var = c->prog[buf][v].p;
+    P.varid = v;
+    P.in0 = var; P.in1 = var; P.in2 = nullptr; P.out0 = g[0]; P.out1 = g[1]; P.out2 = g[2];
+    P.dens_flag = dens_weight; P.bc_on_v = 1;
+    launch_numdiff(0, P, c->stream);
+    { int rc = exchange_work_fields(c, g, 3); if (rc) return rc; }
+    for (int it = 1; it <= c->nd.lap_num - 1; ++it) {
+      double* lp[2] = {c->nd_lap[0].p, c->nd_lap[1].p};
+      P.in0 = g[0]; P.in1 = g[1]; P.in2 = g[2]; P.out0 = lp[0]; P.out1 = lp[1]; P.out2 = nullptr; P.dens_flag = 0;
+      launch_numdiff(1, P, c->stream);
+      { int rc = exchange_work_fields(c, lp, 2); if (rc) return rc; }
+      P.in0 = lp[0]; P.in1 = lp[1]; P.in2 = nullptr; P.out0 = g[0]; P.out1 = g[1]; P.out2 = g[2]; P.dens_flag = 0; P.bc_on_v = 0;
+      launch_numdiff(0, P, c->stream);
+      { int rc = exchange_work_fields(c, g, 3); if (rc) return rc; }
+    }
+    P.in0 = g[0]; P.in1 = g[1]; P.in2 = g[2]; P.var = var; P.dens_flag = dens_weight;
+    P.coef_h = nd_sign * c->nd.coef_h; P.coef_v = nd_sign * c->nd.coef_v;
+    launch_numdiff(2, P, c->stream);
+  }
+  c->dp_valid[buf] = false;
   return FEDG_OK;
 }
 
@@ -787,6 +863,7 @@ int run_steps(fedg_ctx* c, int nsteps) {
       in = out;
     }
     c->cur = in;
+    if (c->nd.on && c->nd.in_update) { int rc = run_numdiff(c, c->cur); if (rc) return rc; }
   }
   CUDA_TRY(cudaEventRecord(c->ev[1], c->stream));
   CUDA_TRY(cudaStreamSynchronize(c->stream));
@@ -1220,6 +1297,35 @@ int fedg_group_update(fedg_ctx** ctxs, int n, int nsteps) {
   float ms = 0;
   CUDA_TRY(cudaEventElapsedTime(&ms, lead->ev[0], lead->ev[1]));
   lead->last_ms_total = ms; lead->last_ms_stage = 0; lead->last_launches = launches;
+  return FEDG_OK;
+}
+
+}  // extern "C"
+
+// ---- numerical diffusion (row f1) ---------------------------------------------------------------------------
+extern "C" {
+
+int fedg_numdiff_init(fedg_ctx* c, int nd_laplacian_num, double nd_coef_h, double nd_coef_v, const int* therm_bc, int apply_in_update) {
+  if (!c) return fail(FEDG_ERR_ARG, "null argument");
+  if (!c->dyn_ready) return fail(FEDG_ERR_STATE, "fedg_dyn_init must be called first (the diffusion step uses TIME_DT)");
+  if (nd_laplacian_num < 1) return fail(FEDG_ERR_ARG, "ND_LAPLACIAN_NUM must be >= 1");
+  if (c->terrain || c->global) return fail(FEDG_ERR_UNSUPPORTED, "numerical diffusion is available on the flat regional mesh only");
+  for (int f = 0; f < 6; ++f) if (c->link[f].src) return fail(FEDG_ERR_UNSUPPORTED, "numerical diffusion with linked local meshes is not available");
+  c->nd.lap_num = nd_laplacian_num; c->nd.coef_h = nd_coef_h; c->nd.coef_v = nd_coef_v;
+  for (int f = 0; f < 6; ++f) c->nd.therm_bc[f] = therm_bc ? therm_bc[f] : 0;
+  c->nd.in_update = apply_in_update != 0;
+  c->nd.on = true;
+  return FEDG_OK;
+}
+
+int fedg_numdiff_apply(fedg_ctx* c) {
+  if (!c) return fail(FEDG_ERR_ARG, "null argument");
+  if (!c->nd.on) return fail(FEDG_ERR_STATE, "fedg_numdiff_init must be called first");
+  if (!c->aux_ready) return fail(FEDG_ERR_STATE, "fedg_set_aux must be called first");
+  int rc = run_numdiff(c, c->cur);
+  if (rc) return rc;
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  CUDA_TRY(cudaGetLastError());
   return FEDG_OK;
 }
 

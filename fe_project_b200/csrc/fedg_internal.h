@@ -134,6 +134,24 @@ void launch_advect_halo(double* q, double* u, double* v, double* w, const int* s
 cudaError_t launch_ell_spmv(int M, int N, int col_size, const double* val, const int* col, const double* b, double* c, int nvec,
                             cudaStream_t s);
 
+// numerical diffusion (numdiff.cu): one half-step of the local-DG Laplacian per launch
+struct NumdiffParams {
+  const double *in0, *in1, *in2;   // FLX: Varh, Varv (fields incl. halo);  LAP / TEND: Gx, Gy, Gz
+  double *out0, *out1, *out2;      // FLX: Gx, Gy, Gz;  LAP: lapla_h, lapla_v
+  double* var;                     // TEND: var += dt * tend
+  const double *ddens, *dens_hyd;
+  const ElemTables* tab;
+  const double *escale, *fscale;
+  const int* vmapP;
+  int vel_bc[6], therm_bc[6];      // per tile face, 0 where the face is not a physical boundary
+  int face_off[7];
+  int varid, dens_flag, bc_on_v;
+  double coef_h, coef_v, dt;
+  int Np, Nfp, NfpTot, np, Ne;
+  size_t nint;
+};
+void launch_numdiff(int mode, const NumdiffParams& P, cudaStream_t s);
+
 void launch_vi(const VIParams& p, bool moist, cudaStream_t s);
 void launch_lincomb(const LinCombParams& L, cudaStream_t s);
 void launch_lincomb_filter(const LinCombParams& L, const ElemTables* tab, const double* gsqrt, bool weighted, int Ne, int np,

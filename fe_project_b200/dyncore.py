@@ -148,6 +148,18 @@ class AtmDynDGMDriver_nonhydro3d:
         a = [None if x is None else self._chk_field(x) for x in (DENS_tp, MOMX_tp, MOMY_tp, MOMZ_tp, RHOT_tp, RHOH_p)]
         _lib.check(self.L.fedg_set_phy_tend(self.h, *[_ptr(x) for x in a]))
 
+    def numdiff_init(self, ND_LAPLACIAN_NUM=1, ND_COEF_h=0.0, ND_COEF_v=0.0, therm_bc: dict | None = None, apply_in_update=True):
+        """PARAM_ATMOS_DYN_NUMDIFF (scale_atm_dyn_dgm_nonhydro3d_numdiff.F90:119-212).  therm_bc: {'south',...,'top'} -> 'ADIABAT'."""
+        tb = np.zeros(6, dtype=np.int32)
+        names = ("south", "east", "north", "west", "btm", "top")
+        for k, v in (therm_bc or {}).items():
+            tb[names.index(k)] = 1 if str(v).upper() == "ADIABAT" else 0
+        self._nd_tb = tb
+        _lib.check(self.L.fedg_numdiff_init(self.h, int(ND_LAPLACIAN_NUM), float(ND_COEF_h), float(ND_COEF_v), _ptr(tb), int(apply_in_update)))
+
+    def numdiff_apply(self):
+        _lib.check(self.L.fedg_numdiff_apply(self.h))
+
     def set_coriolis(self, cor):
         a = None if cor is None else _f64(cor).reshape(-1)
         _lib.check(self.L.fedg_set_coriolis(self.h, _ptr(a)))

@@ -187,6 +187,16 @@ int fedg_last_timing(fedg_ctx* ctx, double* ms_total, double* ms_stage_kernels, 
 int fedg_comm_unique_id(void* id128);
 int fedg_comm_init(fedg_ctx* ctx, const void* id128, int rank, int nranks);
 
+/* ---- numerical diffusion (AtmDyn_Nonhydro3D_Numdiff, fluid_dyn_solver/scale_atm_dyn_dgm_nonhydro3d_numdiff.F90:119-376) --------
+ * fedg_numdiff_init: PARAM_ATMOS_DYN_NUMDIFF (ND_LAPLACIAN_NUM, ND_COEF_h, ND_COEF_v); the step is TIME_DT of fedg_dyn_init, the
+ * velocity BC ids are those of fedg_mesh_desc, therm_bc[6] gives the thermal BC id per tile face (1 = ADIABAT,
+ * mesh/scale_mesh_bndinfo.F90; NULL = none).  apply_in_update != 0: applied after every step inside fedg_dyn_update, where
+ * the model calls it (model/atm_nonhydro3d/src/atmos/mod_atmos_dyn.F90:343-349).
+ * fedg_numdiff_apply: %Apply on the state on the device (THERM, MOMZ, MOMX, MOMY, DENS in this order). */
+int fedg_numdiff_init(fedg_ctx* ctx, int nd_laplacian_num, double nd_coef_h, double nd_coef_v, const int* therm_bc,
+                      int apply_in_update);
+int fedg_numdiff_apply(fedg_ctx* ctx);
+
 /* ---- several local meshes on one device (LOCAL_MESH_NUM > 1; cubed-sphere panels) ------------------------------
  * fedg_link_halo: the halo of tile face `face` (1..6) of `ctx` is filled from the interior of `src`, another local mesh on
  * the same device -- the same-rank path of MeshFieldCommBase_exchange_core (data/scale_meshfieldcomm_base.F90:870-895).

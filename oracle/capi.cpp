@@ -143,6 +143,19 @@ int feo_prepare(void* hv) {
   });
 }
 
+// numerical diffusion after every step: PARAM_ATMOS_DYN_NUMDIFF (ND_LAPLACIAN_NUM, ND_COEF_h, ND_COEF_v), therm_bc: 1 = ADIABAT
+void feo_set_numdiff(void* hv, int on, int laplacian_num, double coef_h, double coef_v, const int* therm_bc) {
+  auto& d = static_cast<Handle*>(hv)->d;
+  d.numdiff = on != 0;
+  d.nd.laplacian_num = laplacian_num; d.nd.coef_h = coef_h; d.nd.coef_v = coef_v; d.nd.dt = d.tint.dt;
+  for (int f = 0; f < 6; ++f) { d.nd.vel_bc[f] = d.bnd.vel_bc[f]; d.nd.therm_bc[f] = therm_bc ? therm_bc[f] : 0; }
+}
+// one application on the current state (no dynamics step)
+int feo_numdiff_apply(void* hv) {
+  auto* h = static_cast<Handle*>(hv);
+  return guard([&] { numdiff_apply(h->d.elem, h->d.mesh, h->d.nd, h->d.st); });
+}
+
 // physics tendencies on / off (the arrays are DENS_tp ... RHOH_p of feo_array)
 void feo_set_phytend(void* hv, int on) { static_cast<Handle*>(hv)->d.phytend = on != 0; }
 

@@ -33,6 +33,8 @@ void Driver::update() {
   }
   if (modalfilter) modalfilter_apply(elem, mesh, st);                                  // :940-951
   drhot2pres(elem, mesh, cst, st);                                                     // :954
+  // numerical diffusion follows the dynamics step (model mod_atmos_dyn.F90:343-349)
+  if (numdiff) { numdiff_apply(elem, mesh, nd, st); drhot2pres(elem, mesh, cst, st); }
 }
 
 // file/scale_file_monitor_meshfield.F90:176-213 (cal_total_lc) over the fields of

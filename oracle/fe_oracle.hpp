@@ -174,6 +174,15 @@ void hevi_cal_tend(const Element& e, const Mesh& m, const Consts& c, const DynSt
 void hevi_cal_vi(const Element& e, const Mesh& m, const Consts& c, const DynState& s, const double* var0[5],
                  double impl_fac, double dt, double* dt5[5]);
 
+// numerical diffusion (numdiff.cpp): PARAM_ATMOS_DYN_NUMDIFF + the boundary ids it reads
+struct NumdiffCfg {
+  int laplacian_num = 1;
+  double coef_h = 0.0, coef_v = 0.0, dt = 0.0;
+  int vel_bc[6] = {0, 0, 0, 0, 0, 0};     // 0 nospec, 2 slip, 3 noslip
+  int therm_bc[6] = {0, 0, 0, 0, 0, 0};   // 1 adiabat
+};
+void numdiff_apply(const Element& e, const Mesh& m, const NumdiffCfg& cfg, DynState& s);
+
 // global (cubed-sphere) HEVI: explicit part (dyn_global.cpp); the column solve is hevi_cal_vi
 void global_hevi_numflux_generalhvc(const Element& e, const Mesh& m, const Consts& c, const DynState& s, vec& del_flux);
 void global_hevi_cal_tend(const Element& e, const Mesh& m, const Consts& c, const DynState& s, double* dt5[5]);
@@ -185,7 +194,8 @@ struct Driver {
   BndCfg bnd;
   DynState st;
   TimeIntRK tint;
-  bool hevi = false, modalfilter = false, global = false, phytend = false, entot_conserve = false;
+  bool hevi = false, modalfilter = false, global = false, phytend = false, entot_conserve = false, numdiff = false;
+  NumdiffCfg nd;
   void update();  // fluid_dyn_solver/scale_atm_dyn_dgm_driver_nonhydro3d.F90:614-963
 };
 

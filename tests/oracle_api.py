@@ -39,6 +39,8 @@ def lib():
         L.feo_prepare.argtypes = [C.c_void_p]
         L.feo_update.argtypes = [C.c_void_p, C.c_int]
         L.feo_set_phytend.argtypes = [C.c_void_p, C.c_int]
+        L.feo_set_numdiff.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_void_p]
+        L.feo_numdiff_apply.argtypes = [C.c_void_p]
         L.feo_sphere_exchange.argtypes = [C.c_void_p, C.c_int]
         L.feo_sphere_exchange_aux.argtypes = [C.c_void_p]
         L.feo_sphere_update.argtypes = [C.c_void_p, C.c_int]
@@ -128,6 +130,14 @@ class Oracle:
         mf = np.asarray(mf, dtype=np.float64)
         bc = np.asarray(vel_bc, dtype=np.int32)
         self._chk(lib().feo_setup_dyn(self.h, eqs.encode(), tinteg.encode(), dt, int(modalfilter), _p(mf), _p(bc)))
+
+    def set_numdiff(self, on=True, laplacian_num=1, coef_h=0.0, coef_v=0.0, therm_bc=(0,) * 6):
+        """PARAM_ATMOS_DYN_NUMDIFF; call after setup_dyn (takes dt and the velocity BCs from it)."""
+        tb = np.asarray(therm_bc, dtype=np.int32)
+        lib().feo_set_numdiff(self.h, int(on), int(laplacian_num), float(coef_h), float(coef_v), _p(tb))
+
+    def numdiff_apply(self):
+        self._chk(lib().feo_numdiff_apply(self.h))
 
     def set_phytend(self, on=True):
         lib().feo_set_phytend(self.h, int(on))

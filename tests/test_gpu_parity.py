@@ -445,3 +445,38 @@ def test_sphere_steps(tinteg, dt, Ne, NeZ):
     vol = 4 * np.pi * C0["RPlanet"] ** 2 * case.ztop
     assert abs(tot_g - tot_o) <= 1e-13 * vol
     assert abs(tot_g - m0) <= 1e-12 * vol
+
+
+# ------------------------------------------------------------------------------ numerical diffusion (row f1)
+ADIA = dict(south="ADIABAT", east="ADIABAT", north="ADIABAT", west="ADIABAT", btm="ADIABAT", top="ADIABAT")
+
+
+@pytest.mark.parametrize("p,lap,periodic", [(7, 1, (False, True, False)), (7, 2, (True, True, False)), (3, 1, (False, False, False)), (3, 3, (True, True, True))])
+def test_numdiff_apply(p, lap, periodic):
+    """AtmDyn_Nonhydro3D_Numdiff%Apply on a perturbed state: slip + adiabatic walls, periodic directions, hyper-diffusion."""
+    case = DensityCurrentCase(p=p, NeX=3, NeY=2, NeZ=3, perturb=2.0, periodic=periodic, modalfilter=False, dt=0.08, intrp_order=min(11, p + 4))
+    o = case.make_oracle()
+    d = case.make_driver(o)
+    coef = 75.0 if lap == 1 else 75.0 * (300.0 ** (2 * (lap - 1)))
+    o.set_numdiff(True, lap, coef, 0.5 * coef, therm_bc=(1,) * 6)
+    d.numdiff_init(lap, coef, 0.5 * coef, therm_bc=ADIA, apply_in_update=False)
+    o.numdiff_apply(); d.numdiff_apply()
+    g = d.get_prog()
+    n = case.mesh.Ne * case.elem.Np
+    for nm in PROG:
+        assert rel_l2(g[nm][:n], o.arr(nm)[:n]) <= 1e-12, nm
+
+
+@pytest.mark.parametrize("eqs,tinteg,dt", [("NONHYDRO3D_HEVE", "ERK_SSP_4s3o", 0.08), ("NONHYDRO3D_HEVI", "IMEX_ARK232", 0.25)])
+def test_steps_with_numdiff_shipped_density_current_setting(eqs, tinteg, dt):
+    """The shipped density-current run.conf: ND_LAPLACIAN_NUM = 1, ND_COEF = 75, applied after every dynamics step."""
+    case = DensityCurrentCase(p=7, NeX=4, NeY=2, NeZ=3, perturb=2.0, eqs=eqs, tinteg=tinteg, dt=dt)
+    o = case.make_oracle()
+    d = case.make_driver(o)
+    o.set_numdiff(True, 1, 75.0, 75.0, therm_bc=(1,) * 6)
+    d.numdiff_init(1, 75.0, 75.0, therm_bc=ADIA, apply_in_update=True)
+    o.update(8); d.Update(8)
+    g = d.get_prog()
+    n = case.mesh.Ne * case.elem.Np
+    for nm in PROG:
+        assert rel_l2(g[nm][:n], o.arr(nm)[:n]) <= TOL, nm
