@@ -104,6 +104,7 @@ struct fedg_ctx {
   // numerical diffusion (fedg_numdiff_init): PARAM_ATMOS_DYN_NUMDIFF, thermal BC ids, work fields
   struct { bool on = false, in_update = false; int lap_num = 1; double coef_h = 0, coef_v = 0; int therm_bc[6] = {0, 0, 0, 0, 0, 0}; } nd;
   DevBuf nd_g[3], nd_lap[2];
+  DevBuf sponge; double sponge_h = 0.0; bool has_sponge = false;
   // halo faces filled from another local mesh on the same device (cubed-sphere panel edges): fedg_link_halo
   struct HaloLink { fedg_ctx* src = nullptr; int* d_src = nullptr; double* d_rot = nullptr; int off = 0, cnt = 0; } link[6];
   int xbuf = 0;                    // buffer that holds the state other local meshes gather from (stage input of the explicit part)
@@ -127,6 +128,7 @@ struct fedg_ctx {
     for (auto& b : phyt) b.release();
     for (auto& b : nd_g) b.release();
     for (auto& b : nd_lap) b.release();
+    sponge.release();
     for (auto& b : dp) b.release();
     for (auto& s : prog) for (auto& b : s) b.release();
     for (auto& b : vt) b.release();
@@ -637,6 +639,7 @@ void fill_stage_params(fedg_ctx* c, StageParams& P, int in, int out, int q0) {
   P.g2d = c->g2d.p; P.OHM = c->OHM; P.is_global = c->global; P.panel = c->panel;
   for (int k = 0; k < 6; ++k) P.phyt[k] = c->phyt[k].p;
   P.has_phyt = c->has_phyt;
+  P.sponge = c->has_sponge ? c->sponge.p : nullptr; P.sponge_h = c->sponge_h;
   { static int fp = -1; if (fp < 0) { const char* e = getenv("FEDG_FAST_POW"); fp = (e && e[0] == '1') ? 1 : 0; } P.fast_pow = fp; }
   { static int pf = -1; if (pf < 0) { const char* e = getenv("FEDG_P7_PREFETCH"); pf = e ? atoi(e) : 0; } P.prefetch_dist = pf; }   // experiment knob, off: see DESIGN.md 4.1
 }
@@ -1330,3 +1333,38 @@ int fedg_numdiff_apply(fedg_ctx* c) {
 }
 
 }  // extern "C"
+
+// ---- sponge layer (row f3, flat part) ------------------------------------------------------------------------
+namespace {
+// calc_wdampcoef (spongelayer.F90:189-218) for every node from zlev
+__global__ void sponge_coef_kernel(const double* __restrict__ zlev, double* __restrict__ coef, double r_tau, double height, int Np, int Nfp,
+                                   int np, int Ne, int Ne2D, int NeZ) {
+  const size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= size_t(Np) * Ne) return;
+  const int ke = int(i / Np), p = int(i - size_t(ke) * Np);
+  const int keTop = (ke % Ne2D) + (NeZ - 1) * Ne2D;
+  const double z = zlev[i], zTop = zlev[size_t(keTop) * Np + (p % Nfp) + (np - 1) * Nfp];
+  coef[i] = 0.25 * r_tau * (1.0 + (z - height >= 0.0 ? 1.0 : -1.0)) * (1.0 - cos(3.14159265358979323846 * (z - height) / (zTop - height)));
+}
+}  // namespace
+
+extern "C" int fedg_sponge_init(fedg_ctx* c, double sl_wdamp_tau, double sl_wdamp_height, int sl_wdamp_layer, int sl_horiveldamp_flag) {
+  if (!c) return fail(FEDG_ERR_ARG, "null argument");
+  if (!c->dyn_ready) return fail(FEDG_ERR_STATE, "fedg_dyn_init must be called first (the default SL_WDAMP_TAU is 10 TIME_DT)");
+  if (c->terrain || c->global) return fail(FEDG_ERR_UNSUPPORTED, "the sponge layer is available on the flat regional mesh only");
+  if (sl_wdamp_layer > c->NeZ) return fail(FEDG_ERR_ARG, "SL_wdamp_layer should be less than total of vertical elements (NeGZ)");
+  double tau = sl_wdamp_tau, height = sl_wdamp_height;
+  if (sl_wdamp_layer > 0) {   // height of the first node of that layer (spongelayer.F90:104-106)
+    CUDA_TRY(cudaMemcpy(&height, c->zlev.p + size_t(sl_wdamp_layer - 1) * c->Ne2D * c->Np, sizeof(double), cudaMemcpyDeviceToHost));
+  }
+  if (tau < 0.0) tau = c->dt * 10.0;
+  else if (tau < c->dt) return fail(FEDG_ERR_ARG, "SL_wdamp_tau should be larger than TIME_DT (ATMOS_DYN)");
+  if (c->sponge.n < c->nint) CUDA_TRY(c->sponge.alloc(c->nint));
+  sponge_coef_kernel<<<unsigned((c->nint + 255) / 256), 256, 0, c->stream>>>(c->zlev.p, c->sponge.p, 1.0 / tau, height, c->Np, c->Nfp, c->np, c->Ne,
+                                                                          c->Ne2D, c->NeZ);
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  CUDA_TRY(cudaGetLastError());
+  c->sponge_h = sl_horiveldamp_flag ? 1.0 : 0.0;
+  c->has_sponge = true;
+  return FEDG_OK;
+}

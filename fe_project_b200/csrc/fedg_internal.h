@@ -72,6 +72,9 @@ struct StageParams {
   // physics tendencies DENS_tp, MOMX_tp, MOMY_tp, MOMZ_tp, RHOT_tp, RHOH_p (add_phy_tend, driver_nonhydro3d.F90:1098-1178)
   const double* phyt[6];
   int has_phyt;
+  // sponge layer: Rayleigh damping coefficient per node (Np,Ne), NULL = off; sponge_h = 1 damps MOMX / MOMY too
+  const double* sponge;
+  double sponge_h;
   int prefetch_dist;     // stage_p7: elements ahead whose inputs are pulled into L2 (0 = off)
 };
 

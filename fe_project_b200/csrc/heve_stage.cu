@@ -231,6 +231,8 @@ __global__ void __launch_bounds__(512, MINB) stage_kernel(const __grid_constant_
     else if (v == V_MOMX) tend = ((P.has_phyd ? -P.dphydx[gn] : 0.0) + cor * my) - div;
     else if (v == V_MOMY) tend = ((P.has_phyd ? -P.dphydy[gn] : 0.0) - cor * mx) - div;
     else tend = -div;
+    if (P.sponge && live && (v == V_MOMX || v == V_MOMY || v == V_MOMZ))   // AtmDynSpongeLayer%AddTend (spongelayer.F90:129-185)
+      tend -= ((v == V_MOMZ) ? 1.0 : P.sponge_h) * P.sponge[gn] * q;
     if (P.has_phyt && live) {   // add_phy_tend (driver_nonhydro3d.F90:1098-1178), non-conservative form
       const int pv = (v == V_DDENS) ? 0 : (v == V_MOMX) ? 1 : (v == V_MOMY) ? 2 : (v == V_MOMZ) ? 3 : 4;
       tend += P.phyt[pv][gn];

@@ -364,6 +364,11 @@ __global__ void __launch_bounds__(256, 3) stage_p7_kernel(const __grid_constant_
       tend = make_double2((-ph.x - cor.x * mx.x) - div.x, (-ph.y - cor.y * mx.y) - div.y);
     } else tend = make_double2(-div.x, -div.y);
 
+    if (P.sponge && (v == V_MOMX || v == V_MOMY || v == V_MOMZ)) {   // AtmDynSpongeLayer%AddTend (spongelayer.F90:129-185)
+      const double2 wc = *reinterpret_cast<const double2*>(P.sponge + gn);
+      const double sf = (v == V_MOMZ) ? 1.0 : P.sponge_h;
+      tend.x -= sf * wc.x * q.x; tend.y -= sf * wc.y * q.y;
+    }
     if (P.has_phyt) {   // add_phy_tend (driver_nonhydro3d.F90:1098-1178), non-conservative form: RHOT_tp + RHOH_p / (CP * EXNER)
       const int pv = (v == V_DDENS) ? 0 : (v == V_MOMX) ? 1 : (v == V_MOMY) ? 2 : (v == V_MOMZ) ? 3 : 4;
       const double2 tp = *reinterpret_cast<const double2*>(P.phyt[pv] + gn);

@@ -157,6 +157,10 @@ class AtmDynDGMDriver_nonhydro3d:
         self._nd_tb = tb
         _lib.check(self.L.fedg_numdiff_init(self.h, int(ND_LAPLACIAN_NUM), float(ND_COEF_h), float(ND_COEF_v), _ptr(tb), int(apply_in_update)))
 
+    def sponge_init(self, SL_WDAMP_TAU=-1.0, SL_WDAMP_HEIGHT=-1.0, SL_WDAMP_LAYER=-1, SL_HORIVELDAMP_FLAG=False):
+        """PARAM_ATMOS_DYN_SPONGELAYER (scale_atm_dyn_dgm_spongelayer.F90:55-118)."""
+        _lib.check(self.L.fedg_sponge_init(self.h, float(SL_WDAMP_TAU), float(SL_WDAMP_HEIGHT), int(SL_WDAMP_LAYER), int(SL_HORIVELDAMP_FLAG)))
+
     def numdiff_apply(self):
         _lib.check(self.L.fedg_numdiff_apply(self.h))
 

@@ -197,6 +197,12 @@ int fedg_numdiff_init(fedg_ctx* ctx, int nd_laplacian_num, double nd_coef_h, dou
                       int apply_in_update);
 int fedg_numdiff_apply(fedg_ctx* ctx);
 
+/* ---- sponge layer (AtmDynSpongeLayer, fluid_dyn_solver/scale_atm_dyn_dgm_spongelayer.F90:55-220) -------------------------
+ * PARAM_ATMOS_DYN_SPONGELAYER: SL_WDAMP_TAU (< 0: 10 TIME_DT), SL_WDAMP_HEIGHT, SL_WDAMP_LAYER (> 0 overrides the height by
+ * the first node of that element layer), SL_HORIVELDAMP_FLAG.  The Rayleigh damping enters the explicit tendency of every
+ * stage inside the stage kernel (driver_nonhydro3d.F90:830-841). */
+int fedg_sponge_init(fedg_ctx* ctx, double sl_wdamp_tau, double sl_wdamp_height, int sl_wdamp_layer, int sl_horiveldamp_flag);
+
 /* ---- several local meshes on one device (LOCAL_MESH_NUM > 1; cubed-sphere panels) ------------------------------
  * fedg_link_halo: the halo of tile face `face` (1..6) of `ctx` is filled from the interior of `src`, another local mesh on
  * the same device -- the same-rank path of MeshFieldCommBase_exchange_core (data/scale_meshfieldcomm_base.F90:870-895).

@@ -156,6 +156,14 @@ int feo_numdiff_apply(void* hv) {
   return guard([&] { numdiff_apply(h->d.elem, h->d.mesh, h->d.nd, h->d.st); });
 }
 
+// PARAM_ATMOS_DYN_SPONGELAYER (spongelayer.F90:55-118); call after setup_dyn
+void feo_set_sponge(void* hv, int on, double tau, double height, int layer, int hveldamp) {
+  auto& d = static_cast<Handle*>(hv)->d;
+  d.sponge.on = on != 0; d.sponge.tau = tau; d.sponge.height = height; d.sponge.layer = layer; d.sponge.hveldamp = hveldamp != 0;
+  if (layer > 0) d.sponge.height = d.mesh.pos[2][size_t((layer - 1) * d.mesh.NeX * d.mesh.NeY) * d.elem.Np];
+  if (d.sponge.tau < 0.0) d.sponge.tau = d.tint.dt * 10.0;
+}
+
 // physics tendencies on / off (the arrays are DENS_tp ... RHOH_p of feo_array)
 void feo_set_phytend(void* hv, int on) { static_cast<Handle*>(hv)->d.phytend = on != 0; }
 
@@ -229,6 +237,7 @@ int feo_stage_piece(void* hv, const char* what) {
       double* out[5]; for (int v = 0; v < 5; ++v) out[v] = d.tint.tend_ex_buf(v, 0);
       if (d.global) global_hevi_cal_tend(d.elem, d.mesh, d.cst, d.st, out);
       else if (d.hevi) hevi_cal_tend(d.elem, d.mesh, d.cst, d.st, out); else heve_cal_tend(d.elem, d.mesh, d.cst, d.st, out);
+      if (d.sponge.on) sponge_add_tend(d.elem, d.mesh, d.sponge, d.st, out);
       if (d.phytend) add_phy_tend(d.elem, d.mesh, d.cst, d.st, d.entot_conserve, out);
     }
     else if (w == "modalfilter") modalfilter_apply(d.elem, d.mesh, d.st);

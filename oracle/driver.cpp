@@ -28,6 +28,7 @@ void Driver::update() {
     if (global) global_hevi_cal_tend(elem, mesh, cst, st, out);
     else if (hevi) hevi_cal_tend(elem, mesh, cst, st, out);
     else heve_cal_tend(elem, mesh, cst, st, out);                                       // :815
+    if (sponge.on) sponge_add_tend(elem, mesh, sponge, st, out);                        // :830-841
     if (phytend) add_phy_tend(elem, mesh, cst, st, entot_conserve, out);                // :843-857
     for (int v : rkvar) tint.advance(stage, st.prog(v), v, 0, nint);                   // :920
   }

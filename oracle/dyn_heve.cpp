@@ -13,6 +13,25 @@ void DynState::alloc(size_t n, size_t n2d) {
   CORIOLIS.assign(n2d, 0.0);
 }
 
+// fluid_dyn_solver/scale_atm_dyn_dgm_spongelayer.F90:129-220 (add_tend, calc_wdampcoef); cfg.tau / cfg.height already resolved
+// as Init does (:97-118: SL_WDAMP_LAYER -> height of the first node of that layer, tau < 0 -> 10 dt)
+void sponge_add_tend(const Element& e, const Mesh& m, const SpongeCfg& cfg, const DynState& s, double* dt5[5]) {
+  const double PI = 3.14159265358979323846;
+  const int Np = e.Np, Nfp = e.Nfp, np = e.np;
+  const double sflag = cfg.hveldamp ? 1.0 : 0.0, r_tau = 1.0 / cfg.tau;
+  for (int ke = 0; ke < m.Ne; ++ke) {
+    const int keZtop = (ke % (m.NeX * m.NeY)) + (m.NeZ - 1) * m.NeX * m.NeY;
+    for (int p = 0; p < Np; ++p) {
+      const size_t i = size_t(ke) * Np + p;
+      const double z = m.pos[2][i], zTop = m.pos[2][size_t(keZtop) * Np + (p % Nfp) + (np - 1) * Nfp];
+      const double coef = 0.25 * r_tau * (1.0 + (z - cfg.height >= 0.0 ? 1.0 : -1.0)) * (1.0 - std::cos(PI * (z - cfg.height) / (zTop - cfg.height)));
+      dt5[MOMX_VID][i] = dt5[MOMX_VID][i] - sflag * coef * s.MOMX[i];
+      dt5[MOMY_VID][i] = dt5[MOMY_VID][i] - sflag * coef * s.MOMY[i];
+      dt5[MOMZ_VID][i] = dt5[MOMZ_VID][i] - coef * s.MOMZ[i];
+    }
+  }
+}
+
 // fluid_dyn_solver/scale_atm_dyn_dgm_driver_nonhydro3d.F90:1098-1178 (add_phy_tend, CPU branch)
 void add_phy_tend(const Element& e, const Mesh& m, const Consts& c, const DynState& s, bool entot_conserve, double* dt5[5]) {
   const double rP0 = 1.0 / c.PRES00;

@@ -167,6 +167,9 @@ void heve_numflux_generalvc(const Element& e, const Mesh& m, const Consts& c, co
 void heve_cal_tend(const Element& e, const Mesh& m, const Consts& c, const DynState& s, double* dt5[5]);
 void modalfilter_apply(const Element& e, const Mesh& m, DynState& s);
 void add_phy_tend(const Element& e, const Mesh& m, const Consts& c, const DynState& s, bool entot_conserve, double* dt5[5]);
+// sponge layer (fluid_dyn_solver/scale_atm_dyn_dgm_spongelayer.F90:55-220)
+struct SpongeCfg { bool on = false; double tau = -1.0, height = -1.0; int layer = -1; bool hveldamp = false; };
+void sponge_add_tend(const Element& e, const Mesh& m, const SpongeCfg& cfg, const DynState& s, double* dt5[5]);
 
 // HEVI (a6, a8-a12)
 void hevi_numflux_generalvc(const Element& e, const Mesh& m, const Consts& c, const DynState& s, vec& del_flux);
@@ -196,6 +199,7 @@ struct Driver {
   TimeIntRK tint;
   bool hevi = false, modalfilter = false, global = false, phytend = false, entot_conserve = false, numdiff = false;
   NumdiffCfg nd;
+  SpongeCfg sponge;
   void update();  // fluid_dyn_solver/scale_atm_dyn_dgm_driver_nonhydro3d.F90:614-963
 };
 

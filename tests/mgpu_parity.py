@@ -1,6 +1,6 @@
 """Multi-GPU parity (run under torchrun, one rank per GPU): NprcX x NprcY tiles with NCCL halo exchange against the
 single-domain CPU oracle on the same global mesh.  Rank 0 prints one line per variable and exits non-zero on failure.
-  torchrun --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 tests/mgpu_parity.py [hevi]"""
+  torchrun --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 tests/mgpu_parity.py [hevi] [numdiff]"""
 import os
 import sys
 
@@ -17,7 +17,8 @@ def main():
     rank, world, lrank = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(lrank)
     dist.init_process_group("nccl", device_id=torch.device("cuda", lrank))
-    hevi = len(sys.argv) > 1 and sys.argv[1] == "hevi"
+    hevi = "hevi" in sys.argv[1:]
+    numdiff = "numdiff" in sys.argv[1:]      # shipped density-current setting: ND_LAPLACIAN_NUM = 1, ND_COEF = 75, after every step
     NX, NY = {1: (1, 1), 2: (2, 1), 4: (2, 2), 8: (4, 2)}[world]
     pi, pj = rank % NX, rank // NX
     # HEVI: dt keeps the horizontally explicit part stable (acoustic CFL ~0.4) while the vertical CFL is ~1.5
@@ -34,6 +35,9 @@ def main():
         dist.broadcast_object_list(obj, src=0)
         return obj[0]
     d.init_comm(rank, world, bcast)
+    if numdiff:
+        d.numdiff_init(2, 75.0 * 300.0 ** 2, 75.0 * 300.0 ** 2, therm_bc={k: "ADIABAT" for k in ("south", "east", "north", "west", "btm", "top")},
+                       apply_in_update=True)
     nsteps = 10
     d.Update(nsteps)
     g = d.get_prog()
@@ -45,6 +49,8 @@ def main():
     # reference: the whole domain on the CPU oracle (every rank computes it: small)
     glob = DensityCurrentCase(NeX=nex * NX, NeY=ney * NY, NeZ=nez, **kw)
     o = glob.make_oracle()
+    if numdiff:
+        o.set_numdiff(True, 2, 75.0 * 300.0 ** 2, 75.0 * 300.0 ** 2, therm_bc=(1,) * 6)
     o.update(nsteps)
     Np = tile.elem.Np
     # global element index of each tile element
@@ -60,7 +66,7 @@ def main():
     mo = o.monitor()
     ok = errs.item() <= 1e-10 and abs(mon_g[1] - mo[1]) <= 1e-12 * abs(mo[1])
     if rank == 0:
-        print(f"mgpu_parity world={world} tiles={NX}x{NY} hevi={hevi}: worst rel L2 = {errs.item():.3e}; "
+        print(f"mgpu_parity world={world} tiles={NX}x{NY} hevi={hevi} numdiff={numdiff}: worst rel L2 = {errs.item():.3e}; "
               f"ENGT tiles {mon_g[1]:.15e} oracle {mo[1]:.15e} -> {'OK' if ok else 'FAIL'}")
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)

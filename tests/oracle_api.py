@@ -39,6 +39,7 @@ def lib():
         L.feo_prepare.argtypes = [C.c_void_p]
         L.feo_update.argtypes = [C.c_void_p, C.c_int]
         L.feo_set_phytend.argtypes = [C.c_void_p, C.c_int]
+        L.feo_set_sponge.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_int, C.c_int]
         L.feo_set_numdiff.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_void_p]
         L.feo_numdiff_apply.argtypes = [C.c_void_p]
         L.feo_sphere_exchange.argtypes = [C.c_void_p, C.c_int]
@@ -138,6 +139,9 @@ class Oracle:
 
     def numdiff_apply(self):
         self._chk(lib().feo_numdiff_apply(self.h))
+
+    def set_sponge(self, on=True, SL_WDAMP_TAU=-1.0, SL_WDAMP_HEIGHT=-1.0, SL_WDAMP_LAYER=-1, SL_HORIVELDAMP_FLAG=False):
+        lib().feo_set_sponge(self.h, int(on), float(SL_WDAMP_TAU), float(SL_WDAMP_HEIGHT), int(SL_WDAMP_LAYER), int(SL_HORIVELDAMP_FLAG))
 
     def set_phytend(self, on=True):
         lib().feo_set_phytend(self.h, int(on))

@@ -480,3 +480,22 @@ def test_steps_with_numdiff_shipped_density_current_setting(eqs, tinteg, dt):
     n = case.mesh.Ne * case.elem.Np
     for nm in PROG:
         assert rel_l2(g[nm][:n], o.arr(nm)[:n]) <= TOL, nm
+
+
+@pytest.mark.parametrize("p,eqs,tinteg,dt,kw", [(7, "NONHYDRO3D_HEVE", "ERK_SSP_4s3o", 0.08, dict(SL_WDAMP_TAU=1.0, SL_WDAMP_HEIGHT=4.0e3, SL_HORIVELDAMP_FLAG=True)),
+                                                (7, "NONHYDRO3D_HEVI", "IMEX_ARK232", 0.25, dict(SL_WDAMP_LAYER=3)),
+                                                (3, "NONHYDRO3D_HEVE", "ERK_SSP_3s3o", 0.2, dict(SL_WDAMP_TAU=5.0, SL_WDAMP_LAYER=2))])
+def test_sponge_layer_row_f3(p, eqs, tinteg, dt, kw):
+    """AtmDynSpongeLayer: Rayleigh damping of MOMZ (and of MOMX / MOMY with SL_HORIVELDAMP_FLAG) above SL_WDAMP_HEIGHT."""
+    case = DensityCurrentCase(p=p, NeX=3, NeY=2, NeZ=4, perturb=2.0, eqs=eqs, tinteg=tinteg, dt=dt, intrp_order=min(11, p + 4))
+    o = case.make_oracle()
+    d = case.make_driver(o)
+    o.set_sponge(True, **kw)
+    d.sponge_init(**kw)
+    o.update(6); d.Update(6)
+    g = d.get_prog()
+    n = case.mesh.Ne * case.elem.Np
+    for nm in PROG:
+        assert rel_l2(g[nm][:n], o.arr(nm)[:n]) <= TOL, nm
+    d2 = case.make_driver(o); d2.Update(6)
+    assert rel_l2(d2.get_prog()["MOMZ"][:n], g["MOMZ"][:n]) > 1e-6      # the damping matters
