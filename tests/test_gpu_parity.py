@@ -499,3 +499,67 @@ def test_sponge_layer_row_f3(p, eqs, tinteg, dt, kw):
         assert rel_l2(g[nm][:n], o.arr(nm)[:n]) <= TOL, nm
     d2 = case.make_driver(o); d2.Update(6)
     assert rel_l2(d2.get_prog()["MOMZ"][:n], g["MOMZ"][:n]) > 1e-6      # the damping matters
+
+
+# ------------------------------------------------------------------------------ terrain-following metric (row f3, metric part)
+def _terrain_case(p, dims, **kw):
+    """Bell mountain h(x) = h0 / (1 + ((x - xc)/a)^2 + ((y - yc)/b)^2) with the linear terrain-following map
+    z = zeta + h (1 - zeta / zTop): GsqrtV = 1 - h / zTop, G13 = -(1 - zeta/zTop) h_x / GsqrtV, G23 likewise (the
+    quantities MeshTopography%SetVCoordinate hands to Set_geometric_with_vcoord, mesh/scale_mesh_topography.F90:101-264,
+    evaluated analytically here: the test is about the metric terms of the tendency, not about the mesh generator)."""
+    case = DensityCurrentCase(p=p, NeX=dims[0], NeY=dims[1], NeZ=dims[2], perturb=2.0, intrp_order=min(11, p + 4), **kw)
+    m = case.mesh
+    x, y, zeta = m.pos_en[0], m.pos_en[1], m.pos_en[2]
+    zT, h0, a, b, xc, yc = m.zmax, 600.0, 5.0e3, 4.0e3, 12.0e3, 3.0e3
+    den = 1.0 + ((x - xc) / a) ** 2 + ((y - yc) / b) ** 2
+    h = h0 / den
+    hx = -h0 / den ** 2 * 2.0 * (x - xc) / a ** 2
+    hy = -h0 / den ** 2 * 2.0 * (y - yc) / b ** 2
+    gv = 1.0 - h / zT
+    Ne = m.Ne
+    m.Gsqrt[:Ne] = gv
+    m.GI3[0, :Ne] = -(1.0 - zeta / zT) * hx / gv
+    m.GI3[1, :Ne] = -(1.0 - zeta / zT) * hy / gv
+    for arr in (m.Gsqrt, m.GI3[0], m.GI3[1]):
+        m.exchange_halo_numpy(arr.reshape(-1))
+    return case      # zlev (used by the potential-energy monitor only) stays the computational height on both sides
+
+
+def _terrain_oracle(case):
+    o = case.make_oracle()
+    m = case.mesh
+    o.arr("Gsqrt")[:] = m.Gsqrt.reshape(-1)
+    o.arr("G13")[:] = m.GI3[0].reshape(-1)
+    o.arr("G23")[:] = m.GI3[1].reshape(-1)
+    o.prepare()
+    return o
+
+
+@pytest.mark.parametrize("p,dims", [(7, (4, 2, 3)), (3, (5, 3, 4))])
+def test_terrain_following_tendency(p, dims):
+    case = _terrain_case(p, dims)
+    o = _terrain_oracle(case)
+    d = case.make_driver(o)
+    for w in ("exchange", "pressure", "bc", "tend_ex"):
+        o.piece(w)
+    t = d.cal_tend_ex()
+    n = case.mesh.Ne * case.elem.Np
+    te = o.arr("tend_ex").reshape(5, -1)[:, :n]
+    for nm, iv in TEND:
+        assert rel_l2(t[nm], te[iv]) <= 5e-11, nm
+
+
+@pytest.mark.parametrize("p,dims,dt", [(7, (4, 2, 3), 0.05), (3, (5, 3, 4), 0.2)])
+def test_terrain_following_steps(p, dims, dt):
+    """HEVE over a mountain: slip walls use the contravariant vertical momentum, the modal filter and the monitors the
+    Gsqrt weight."""
+    case = _terrain_case(p, dims, dt=dt)
+    o = _terrain_oracle(case)
+    d = case.make_driver(o)
+    o.update(10); d.Update(10)
+    g = d.get_prog()
+    n = case.mesh.Ne * case.elem.Np
+    for nm in PROG:
+        assert rel_l2(g[nm][:n], o.arr(nm)[:n]) <= TOL, nm
+    mo, mg = o.monitor(), d.monitor()
+    assert abs(mo[1] - mg[1]) <= 1e-12 * abs(mo[1])
