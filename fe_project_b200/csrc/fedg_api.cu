@@ -422,12 +422,12 @@ int fedg_dyn_init(fedg_ctx* c, const char* eqs_type, const char* tinteg_type, do
   std::string eqs(eqs_type);
   if (eqs == "NONHYDRO3D_HEVE") c->hevi = false;
   else if (eqs == "NONHYDRO3D_HEVI") c->hevi = true;
-  else if (eqs == "GLOBALNONHYDRO3D_HEVI") {
-    if (!c->global) return fail(FEDG_ERR_ARG, "GLOBALNONHYDRO3D_HEVI needs a cubed-sphere panel mesh (fedg_mesh_desc.panelID)");
-    c->hevi = true;
+  else if (eqs == "GLOBALNONHYDRO3D_HEVI" || eqs == "GLOBALNONHYDRO3D_HEVE") {
+    if (!c->global) return fail(FEDG_ERR_ARG, eqs + " needs a cubed-sphere panel mesh (fedg_mesh_desc.panelID)");
+    c->hevi = (eqs == "GLOBALNONHYDRO3D_HEVI");
   }
-  else return fail(FEDG_ERR_UNSUPPORTED, "EQS_TYPE " + eqs + " is not available in this build (NONHYDRO3D_HEVE, NONHYDRO3D_HEVI, GLOBALNONHYDRO3D_HEVI)");
-  if (c->global && eqs != "GLOBALNONHYDRO3D_HEVI") return fail(FEDG_ERR_ARG, "a cubed-sphere panel mesh runs GLOBALNONHYDRO3D_HEVI only");
+  else return fail(FEDG_ERR_UNSUPPORTED, "EQS_TYPE " + eqs + " is not available in this build (NONHYDRO3D_HEVE, NONHYDRO3D_HEVI, GLOBALNONHYDRO3D_HEVE, GLOBALNONHYDRO3D_HEVI)");
+  if (c->global && eqs.rfind("GLOBAL", 0) != 0) return fail(FEDG_ERR_ARG, "a cubed-sphere panel mesh runs the GLOBALNONHYDRO3D equation sets only");
   if (!c->rk.init(tinteg_type)) return fail(FEDG_ERR_ARG, std::string("unsupported TINTEG_TYPE ") + tinteg_type);
   if (!(dt > 0.0)) return fail(FEDG_ERR_ARG, "dt must be positive");
   c->dt = dt;
@@ -715,6 +715,29 @@ void hevi_stage_combine(fedg_ctx* c, int s) {
 }
 void hevi_end_step(fedg_ctx* c) { c->cur = c->hs.in; c->xbuf = c->cur; }
 
+// explicit (HEVE) stage pieces: buffer choice + pressure of the stage input, then exchange + fused stage kernel
+void heve_stage_prepare(fedg_ctx* c, int s) {
+  const int ns = c->rk.nstage, i0 = c->hs.i0, in = c->hs.in;
+  int out;
+  if (s == ns - 1) out = (ns == 1) ? (i0 + 1) % 3 : i0;
+  else { out = (in + 1) % 3; if (out == i0) out = (out + 1) % 3; }
+  c->hs.nxt = out;
+  ensure_dp(c, in);
+  c->xbuf = in;
+}
+int heve_stage(fedg_ctx* c, int s, cudaEvent_t e0, cudaEvent_t e1) {
+  const int ns = c->rk.nstage, in = c->hs.in, out = c->hs.nxt;
+  StageParams P{};
+  fill_stage_params(c, P, in, out, c->hs.i0);
+  P.rk = c->stages[s];
+  if (s == ns - 1) { P.do_filter = c->modalfilter; P.write_pres = 1; }
+  int rc = exchange_and_stage(c, P, in, false, e0, e1);
+  if (rc) return rc;
+  c->dp_valid[out] = true;
+  c->hs.in = out;
+  return FEDG_OK;
+}
+
 int run_steps_hevi(fedg_ctx* c, int nsteps, size_t& iev, long& launches) {
   const int ns = c->rk.nstage;
   for (int step = 0; step < nsteps; ++step) {
@@ -847,25 +870,15 @@ int run_steps(fedg_ctx* c, int nsteps) {
     nsteps = 0;
   }
   for (int step = 0; step < nsteps; ++step) {
-    const int i0 = c->cur;
-    int in = i0;
+    hevi_begin_step(c);
     for (int s = 0; s < ns; ++s) {
-      int out;
-      if (s == ns - 1) out = (ns == 1) ? (i0 + 1) % 3 : i0;
-      else { out = (in + 1) % 3; if (out == i0) out = (out + 1) % 3; }
-      ensure_dp(c, in);
-      StageParams P{};
-      fill_stage_params(c, P, in, out, i0);
-      P.rk = c->stages[s];
-      if (s == ns - 1) { P.do_filter = c->modalfilter; P.write_pres = 1; }
       cudaEvent_t e0 = nullptr, e1 = nullptr;
       if (c->profile) { e0 = c->ev[iev++]; e1 = c->ev[iev++]; }
-      { int rc = exchange_and_stage(c, P, in, false, e0, e1); if (rc) return rc; }
-      c->dp_valid[out] = true;
+      heve_stage_prepare(c, s);
+      { int rc = heve_stage(c, s, e0, e1); if (rc) return rc; }
       launches += 2;
-      in = out;
     }
-    c->cur = in;
+    hevi_end_step(c);
     if (c->nd.on && c->nd.in_update) { int rc = run_numdiff(c, c->cur); if (rc) return rc; }
   }
   CUDA_TRY(cudaEventRecord(c->ev[1], c->stream));
@@ -1270,7 +1283,7 @@ int fedg_group_update(fedg_ctx** ctxs, int n, int nsteps) {
     fedg_ctx* c = ctxs[i];
     if (!c) return fail(FEDG_ERR_ARG, "null context");
     if (!c->dyn_ready || !c->aux_ready) return fail(FEDG_ERR_STATE, "fedg_dyn_init and fedg_set_aux must be called on every mesh of the group");
-    if (!c->hevi) return fail(FEDG_ERR_UNSUPPORTED, "group stepping is implemented for the HEVI equation sets");
+    if (c->hevi != ctxs[0]->hevi) return fail(FEDG_ERR_ARG, "the meshes of a group share the equation set");
     if (c->comm.active && c->comm.nremote > 0) return fail(FEDG_ERR_UNSUPPORTED, "group stepping and NCCL tiles cannot be combined yet");
     if (c->rk.nstage != ctxs[0]->rk.nstage || c->dt != ctxs[0]->dt) return fail(FEDG_ERR_ARG, "the meshes of a group share scheme and step");
   }
@@ -1287,10 +1300,16 @@ int fedg_group_update(fedg_ctx** ctxs, int n, int nsteps) {
   for (int step = 0; step < nsteps; ++step) {
     for (int i = 0; i < n; ++i) hevi_begin_step(ctxs[i]);
     for (int s = 0; s < ns; ++s) {
-      for (int i = 0; i < n; ++i) { int rc = hevi_stage_vi(ctxs[i], s, nullptr, nullptr); if (rc) return rc; }     // cal_vi + StoreImplicit
-      for (int i = 0; i < n; ++i) { int rc = hevi_stage_ex(ctxs[i], s); if (rc) return rc; }                        // exchange + cal_tend_ex
-      for (int i = 0; i < n; ++i) hevi_stage_combine(ctxs[i], s);                                                  // Advance
-      launches += 4L * n;
+      if (lead->hevi) {
+        for (int i = 0; i < n; ++i) { int rc = hevi_stage_vi(ctxs[i], s, nullptr, nullptr); if (rc) return rc; }     // cal_vi + StoreImplicit
+        for (int i = 0; i < n; ++i) { int rc = hevi_stage_ex(ctxs[i], s); if (rc) return rc; }                        // exchange + cal_tend_ex
+        for (int i = 0; i < n; ++i) hevi_stage_combine(ctxs[i], s);                                                  // Advance
+        launches += 4L * n;
+      } else {
+        for (int i = 0; i < n; ++i) heve_stage_prepare(ctxs[i], s);                                                  // pressure of every stage input
+        for (int i = 0; i < n; ++i) { int rc = heve_stage(ctxs[i], s, nullptr, nullptr); if (rc) return rc; }        // exchange + tendency + Advance
+        launches += 2L * n;
+      }
     }
     for (int i = 0; i < n; ++i) hevi_end_step(ctxs[i]);
   }

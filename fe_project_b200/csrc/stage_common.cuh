@@ -122,27 +122,32 @@ __device__ __forceinline__ void rusanov(FaceSide& M, FaceSide& Q, double sgn, do
   out5[V_MOMY] = hf * (Q.gMY * Q.Vel - M.gMY * M.Vel + py - alpha * (Q.gMY - M.gMY));
 }
 
-// Global (cubed-sphere) HEVI flux jump, rhot_hevi_numflux.F90:606-834 (numflux_get_generalhvc), specialised to the
-// shallow atmosphere without topography (gam = 1, GsqrtV = 1, G13 = G23 = 0; checked at fedg_create): Gs is GsqrtH on
-// both sides, G11/G12/G22 are the contravariant metric of the own face node (the reference uses the own element's
-// values for both sides, :739-752).
-template <int AX>
+// Global (cubed-sphere) flux jump, specialised to the shallow atmosphere without topography (gam = 1, GsqrtV = 1,
+// G13 = G23 = 0; checked at fedg_create): Gs is GsqrtH on both sides, G11/G12/G22 are the contravariant metric of the own
+// face node (the reference uses the own element's values for both sides).
+//   HEVI: rhot_hevi_numflux.F90:606-834 (numflux_get_generalhvc): alpha *= 1 - nz^2, mass / theta advect with the horizontal
+//         velocity, no vertical pressure term.   HEVE: rhot_heve_numflux.F90:1543-1772.
+template <int AX, bool HEVI>
 __device__ __forceinline__ void rusanov_global(FaceSide& M, FaceSide& Q, double sgn, double gamm, double hf, double G11, double G12,
                                                double G22, double* out5) {
   face_velocity<AX, false>(M, sgn);
   face_velocity<AX, false>(Q, sgn);
   double alpha = 0.0, G1n = 0.0, G2n = 0.0;
-  if (AX != 2) {
-    const double Gnn = (AX == 0) ? fabs(G11 * sgn) : fabs(G22 * sgn);
+  if (AX != 2 || !HEVI) {
+    const double Gnn = (AX == 0) ? fabs(G11 * sgn) : (AX == 1) ? fabs(G22 * sgn) : 1.0;
     alpha = fmax(sqrt(Gnn * gamm * (M.Phyd + M.dp) * M.Gs * M.rgDens) + fabs(M.Vel),
                  sqrt(Gnn * gamm * (Q.Phyd + Q.dp) * Q.Gs * Q.rgDens) + fabs(Q.Vel));
+  }
+  if (AX != 2) {
     G1n = (AX == 0) ? G11 * sgn : G12 * sgn;
     G2n = (AX == 0) ? G12 * sgn : G22 * sgn;
   }
-  out5[V_DDENS] = hf * (Q.gDens * Q.Velh - M.gDens * M.Velh - alpha * (Q.gDD - M.gDD));
-  out5[V_DRHOT] = hf * (Q.gRhot * Q.Velh - M.gRhot * M.Velh - alpha * (Q.gDR - M.gDR));
+  const double vM = HEVI ? M.Velh : M.Vel, vQ = HEVI ? Q.Velh : Q.Vel;
+  out5[V_DDENS] = hf * (Q.gDens * vQ - M.gDens * vM - alpha * (Q.gDD - M.gDD));
+  out5[V_DRHOT] = hf * (Q.gRhot * vQ - M.gRhot * vM - alpha * (Q.gDR - M.gDR));
   const double t3 = Q.Gs * Q.dp, t4 = M.Gs * M.dp;
-  out5[V_MOMZ] = hf * (Q.gMZ * Q.Vel - M.gMZ * M.Vel - alpha * (Q.gMZ - M.gMZ));
+  const double pz = (AX == 2 && !HEVI) ? (t3 - t4) * sgn : 0.0;
+  out5[V_MOMZ] = hf * (Q.gMZ * Q.Vel - M.gMZ * M.Vel + pz - alpha * (Q.gMZ - M.gMZ));
   out5[V_MOMX] = hf * (Q.gMX * Q.Vel - M.gMX * M.Vel + (G1n * t3 - G1n * t4) - alpha * (Q.gMX - M.gMX));
   out5[V_MOMY] = hf * (Q.gMY * Q.Vel - M.gMY * M.Vel + (G2n * t3 - G2n * t4) - alpha * (Q.gMY - M.gMY));
 }

@@ -200,12 +200,12 @@ __global__ void __launch_bounds__(256, 3) stage_p7_kernel(const __grid_constant_
       double o5[NVAR];
       if (GLOBAL) {
         switch (f) {
-          case 0: rusanov_global<1>(M, Q, -1.0, gamm, hf, fG11, fG12, fG22, o5); break;
-          case 1: rusanov_global<0>(M, Q, 1.0, gamm, hf, fG11, fG12, fG22, o5); break;
-          case 2: rusanov_global<1>(M, Q, 1.0, gamm, hf, fG11, fG12, fG22, o5); break;
-          case 3: rusanov_global<0>(M, Q, -1.0, gamm, hf, fG11, fG12, fG22, o5); break;
-          case 4: rusanov_global<2>(M, Q, -1.0, gamm, hf, fG11, fG12, fG22, o5); break;
-          default: rusanov_global<2>(M, Q, 1.0, gamm, hf, fG11, fG12, fG22, o5); break;
+          case 0: rusanov_global<1, HEVI>(M, Q, -1.0, gamm, hf, fG11, fG12, fG22, o5); break;
+          case 1: rusanov_global<0, HEVI>(M, Q, 1.0, gamm, hf, fG11, fG12, fG22, o5); break;
+          case 2: rusanov_global<1, HEVI>(M, Q, 1.0, gamm, hf, fG11, fG12, fG22, o5); break;
+          case 3: rusanov_global<0, HEVI>(M, Q, -1.0, gamm, hf, fG11, fG12, fG22, o5); break;
+          case 4: rusanov_global<2, HEVI>(M, Q, -1.0, gamm, hf, fG11, fG12, fG22, o5); break;
+          default: rusanov_global<2, HEVI>(M, Q, 1.0, gamm, hf, fG11, fG12, fG22, o5); break;
         }
       } else
       switch (f) {
@@ -473,8 +473,9 @@ void launch_stage_p7(const StageParams& p, bool terrain, bool moist, bool hevi, 
     }                                                                                                            \
     stage_p7_kernel<T, M, H, G><<<grid, block, shmem, s>>>(p);                                                   \
   } while (0)
-  if (p.is_global) {   // GLOBALNONHYDRO3D_HEVI (flat, shallow atmosphere: enforced at fedg_create / fedg_dyn_init)
-    if (moist) FEDG_LAUNCH(false, true, true, true); else FEDG_LAUNCH(false, false, true, true);
+  if (p.is_global) {   // GLOBALNONHYDRO3D_HEVI / _HEVE (flat, shallow atmosphere: enforced at fedg_create / fedg_dyn_init)
+    if (hevi) { if (moist) FEDG_LAUNCH(false, true, true, true); else FEDG_LAUNCH(false, false, true, true); }
+    else { if (moist) FEDG_LAUNCH(false, true, false, true); else FEDG_LAUNCH(false, false, false, true); }
   } else if (hevi) {
     if (terrain) { if (moist) FEDG_LAUNCH(true, true, true, false); else FEDG_LAUNCH(true, false, true, false); }
     else { if (moist) FEDG_LAUNCH(false, true, true, false); else FEDG_LAUNCH(false, false, true, false); }

@@ -98,8 +98,9 @@ int fedg_create(const fedg_mesh_desc* desc, fedg_ctx** out);
 void fedg_destroy(fedg_ctx* ctx);
 
 /* AtmDynDGMDriver_nonhydro3d%Init: fluid_dyn_solver/scale_atm_dyn_dgm_driver_nonhydro3d.F90:355-594
- * eqs_type: "NONHYDRO3D_HEVE" | "NONHYDRO3D_HEVI" (p = 7, flat mesh) | "GLOBALNONHYDRO3D_HEVI" (p = 7, cubed-sphere
- * panel tile: fluid_dyn_solver/scale_atm_dyn_dgm_globalnonhydro3d_rhot_hevi.F90:337-583, 873-1066, flux
+ * eqs_type: "NONHYDRO3D_HEVE" | "NONHYDRO3D_HEVI" (p = 7, flat mesh) | "GLOBALNONHYDRO3D_HEVE" | "GLOBALNONHYDRO3D_HEVI"
+ * (p = 7, cubed-sphere panel tile: fluid_dyn_solver/scale_atm_dyn_dgm_globalnonhydro3d_rhot_heve.F90:338-600,
+ * scale_atm_dyn_dgm_globalnonhydro3d_rhot_hevi.F90:337-583, 873-1066, fluxes scale_atm_dyn_dgm_nonhydro3d_rhot_heve_numflux.F90:1543-1772,
  * scale_atm_dyn_dgm_nonhydro3d_rhot_hevi_numflux.F90:606-834); tinteg_type: a timeint_rk scheme name
  * (common/scale_timeint_rk_butcher_tab.F90:27-67).  filter_h1D / filter_v1D are the (np,np) matrices
  * MFilter_h1D and MFilter_v1D of Setup_ModalFilter (tensorprod3D.F90.erb:160-181, 460-505); pass

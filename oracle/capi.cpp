@@ -119,8 +119,12 @@ int feo_setup_dyn(void* hv, const char* eqs, const char* tinteg, double dt, int 
       if (!d.mesh.is_global) throw std::runtime_error("GLOBALNONHYDRO3D_HEVI needs a cubed-sphere panel mesh");
       d.hevi = true; d.global = true;
     }
+    else if (e == "GLOBALNONHYDRO3D_HEVE") {
+      if (!d.mesh.is_global) throw std::runtime_error("GLOBALNONHYDRO3D_HEVE needs a cubed-sphere panel mesh");
+      d.hevi = false; d.global = true;
+    }
     else throw std::runtime_error("unsupported EQS_TYPE " + e);
-    if (d.mesh.is_global && !d.global) throw std::runtime_error("a cubed-sphere panel mesh needs GLOBALNONHYDRO3D_HEVI");
+    if (d.mesh.is_global && !d.global) throw std::runtime_error("a cubed-sphere panel mesh needs a GLOBALNONHYDRO3D equation set");
     d.tint.init(tinteg, dt, 5, size_t(d.elem.Np) * d.mesh.NeA);
     if (d.hevi != d.tint.sc.imex) throw std::runtime_error("HEVI needs an IMEX scheme and HEVE an explicit one");
     d.modalfilter = modalfilter != 0;
@@ -235,7 +239,7 @@ int feo_stage_piece(void* hv, const char* what) {
     else if (w == "bc") apply_bc_progvars(d.elem, d.mesh, d.bnd, d.st);
     else if (w == "tend_ex") {
       double* out[5]; for (int v = 0; v < 5; ++v) out[v] = d.tint.tend_ex_buf(v, 0);
-      if (d.global) global_hevi_cal_tend(d.elem, d.mesh, d.cst, d.st, out);
+      if (d.global) global_cal_tend(d.elem, d.mesh, d.cst, d.st, d.hevi, out);
       else if (d.hevi) hevi_cal_tend(d.elem, d.mesh, d.cst, d.st, out); else heve_cal_tend(d.elem, d.mesh, d.cst, d.st, out);
       if (d.sponge.on) sponge_add_tend(d.elem, d.mesh, d.sponge, d.st, out);
       if (d.phytend) add_phy_tend(d.elem, d.mesh, d.cst, d.st, d.entot_conserve, out);

@@ -25,7 +25,7 @@ void Driver::update() {
     apply_bc_progvars(elem, mesh, bnd, st);                                            // :797
     double* out[5];
     for (int v = 0; v < 5; ++v) out[v] = tint.tend_ex_buf(v, ind);
-    if (global) global_hevi_cal_tend(elem, mesh, cst, st, out);
+    if (global) global_cal_tend(elem, mesh, cst, st, hevi, out);
     else if (hevi) hevi_cal_tend(elem, mesh, cst, st, out);
     else heve_cal_tend(elem, mesh, cst, st, out);                                       // :815
     if (sponge.on) sponge_add_tend(elem, mesh, sponge, st, out);                        // :830-841

@@ -55,7 +55,9 @@ void Mesh::init_cubedsphere_panel(const Element& e, int panel, int nex, int ney,
 }
 
 // hevi_numflux.F90:606-834
-void global_hevi_numflux_generalhvc(const Element& e, const Mesh& m, const Consts& c, const DynState& s, vec& del_flux) {
+// hevi = true: rhot_hevi_numflux.F90:606-834;  hevi = false: rhot_heve_numflux.F90:1543-1772 (full dissipation, full normal
+// velocity in the mass / theta fluxes, vertical pressure term in MOMZ)
+void global_numflux_generalhvc(const Element& e, const Mesh& m, const Consts& c, const DynState& s, bool hevi, vec& del_flux) {
   const int NfpTot = e.NfpTot, Nfp = e.Nfp, np = e.np;
   const double gamm = c.CPdry / c.CVdry;
   del_flux.resize(size_t(NfpTot) * PRGVAR_NUM * m.Ne);
@@ -95,14 +97,16 @@ void global_hevi_numflux_generalhvc(const Element& e, const Mesh& m, const Const
       const double tmp1 = std::fabs(G11 * nx) + std::fabs(G22 * ny);
       for (int t = 0; t < 2; ++t)
         Gnn[t] = rgam2[t] * tmp1 + (1.0 * (RGv[t] * RGv[t]) + G13[t] * Gxz[t] + G23[t] * Gyz[t]) * std::fabs(nz);
-      const double swV = 1.0 - nz * nz;
+      const double swV = hevi ? 1.0 - nz * nz : 1.0;
       const double alpha = swV * std::max(std::sqrt(Gnn[0] * gamm * (Phyd[0] + dp[0]) * Gs[0] / gDens[0]) + std::fabs(Vel[0]),
                                           std::sqrt(Gnn[1] * gamm * (Phyd[1] + dp[1]) * Gs[1] / gDens[1]) + std::fabs(Vel[1]));
       const double hf = m.Fscale[f] * 0.5;
-      df[fp + DENS_VID * NfpTot] = hf * (gDens[1] * Velh[1] - gDens[0] * Velh[0] + (-alpha * (gDD[1] - gDD[0])));
-      df[fp + RHOT_VID * NfpTot] = hf * (gRhot[1] * Velh[1] - gRhot[0] * Velh[0] + (-alpha * (gDR[1] - gDR[0])));
-      df[fp + MOMZ_VID * NfpTot] = hf * (gMZ[1] * Vel[1] - gMZ[0] * Vel[0] + (-alpha * (gMZ[1] - gMZ[0])));
+      const double* Vm = hevi ? Velh : Vel;
+      df[fp + DENS_VID * NfpTot] = hf * (gDens[1] * Vm[1] - gDens[0] * Vm[0] + (-alpha * (gDD[1] - gDD[0])));
+      df[fp + RHOT_VID * NfpTot] = hf * (gRhot[1] * Vm[1] - gRhot[0] * Vm[0] + (-alpha * (gDR[1] - gDR[0])));
       const double t3 = Gs[1] * dp[1], t4 = Gs[0] * dp[0];
+      const double mz = hevi ? 0.0 : (t3 * RGv[1] - t4 * RGv[0]) * nz;
+      df[fp + MOMZ_VID * NfpTot] = hf * (gMZ[1] * Vel[1] - gMZ[0] * Vel[0] + mz + (-alpha * (gMZ[1] - gMZ[0])));
       const double mx = (G1n[1] + Gxz[1] * nz) * t3 - (G1n[0] + Gxz[0] * nz) * t4;
       const double my = (G2n[1] + Gyz[1] * nz) * t3 - (G2n[0] + Gyz[0] * nz) * t4;
       df[fp + MOMX_VID * NfpTot] = hf * (gMX[1] * Vel[1] - gMX[0] * Vel[0] + mx + (-alpha * (gMX[1] - gMX[0])));
@@ -112,10 +116,11 @@ void global_hevi_numflux_generalhvc(const Element& e, const Mesh& m, const Const
 }
 
 // globalnonhydro3d_rhot_hevi.F90:337-583
-void global_hevi_cal_tend(const Element& e, const Mesh& m, const Consts& c, const DynState& s, double* dt5[5]) {
+// hevi = true: globalnonhydro3d_rhot_hevi.F90:337-583;  hevi = false: globalnonhydro3d_rhot_heve.F90:338-600 (cal_tend_shallow_atm)
+void global_cal_tend(const Element& e, const Mesh& m, const Consts& c, const DynState& s, bool hevi, double* dt5[5]) {
   const int Np = e.Np, NfpTot = e.NfpTot, Nfp = e.Nfp;
   vec del_flux;
-  global_hevi_numflux_generalhvc(e, m, c, s, del_flux);
+  global_numflux_generalhvc(e, m, c, s, hevi, del_flux);
   double sgn = 1.0;
   bool is_panel1to4 = true;
   if (m.panelID == 5) is_panel1to4 = false;
@@ -123,7 +128,7 @@ void global_hevi_cal_tend(const Element& e, const Mesh& m, const Consts& c, cons
   const double OHM = c.OHM;
 #pragma omp parallel
   {
-    vec Flux(size_t(Np) * 3 * 5, 0.0), DFlux(size_t(Np) * 4 * 5), RGsqrtV(Np), RGsqrt(Np), RDENS(Np), G11(Np), G12(Np), G22(Np);
+    vec Flux(size_t(Np) * 3 * 5, 0.0), DFlux(size_t(Np) * 4 * 5), RGsqrtV(Np), RGsqrt(Np), RDENS(Np), G11(Np), G12(Np), G22(Np), drho(Np, 0.0);
 #pragma omp for
     for (int ke = 0; ke < m.Ne; ++ke) {
       const int ke2d = m.emap2d[ke];
@@ -149,11 +154,11 @@ void global_hevi_cal_tend(const Element& e, const Mesh& m, const Consts& c, cons
         const double pt = (s.THERM_hyd[o + p] + s.DRHOT[o + p]) * RDENS[p];
         F(p, 0, RHOT_VID) = F(p, 0, DENS_VID) * pt;
         F(p, 1, RHOT_VID) = F(p, 1, DENS_VID) * pt;
-        F(p, 2, RHOT_VID) = 0.0;   // not set in the reference (:474) and its derivative is not used
+        F(p, 2, RHOT_VID) = hevi ? 0.0 : F(p, 2, DENS_VID) * pt;   // HEVI: not set in the reference (:474), derivative unused
         const double w = s.MOMZ[o + p] * RDENS[p];
         F(p, 0, MOMZ_VID) = F(p, 0, DENS_VID) * w;
         F(p, 1, MOMZ_VID) = F(p, 1, DENS_VID) * w;
-        F(p, 2, MOMZ_VID) = F(p, 2, DENS_VID) * w;
+        F(p, 2, MOMZ_VID) = F(p, 2, DENS_VID) * w + (hevi ? 0.0 : m.Gsqrt[o + p] * RGsqrtV[p] * s.DPRES[o + p]);
       }
       for (int p = 0; p < Np; ++p) {
         const double GP = m.Gsqrt[o + p] * s.DPRES[o + p];
@@ -167,12 +172,20 @@ void global_hevi_cal_tend(const Element& e, const Mesh& m, const Consts& c, cons
       }
       for (int v = 0; v < 5; ++v)
         op_div(e, &Flux[size_t(Np) * 3 * v], &del_flux[(size_t(ke) * PRGVAR_NUM + v) * NfpTot], &DFlux[size_t(Np) * 4 * v]);
+      if (!hevi) op_matz(e, e.VPOrdM1.data(), &s.DDENS[o], drho.data());     // VFilterPM1 (rhot_heve.F90:507-508)
       for (int p = 0; p < Np; ++p) {
         const double E11 = m.E11[o + p], E22 = m.E22[o + p], E33 = m.E33[o + p];
-        dt5[DENS_VID][o + p] = -(E11 * DF(p, 0, DENS_VID) + E22 * DF(p, 1, DENS_VID) + DF(p, 3, DENS_VID)) * RGsqrt[p];
-        dt5[RHOT_VID][o + p] = -(E11 * DF(p, 0, RHOT_VID) + E22 * DF(p, 1, RHOT_VID) + DF(p, 3, RHOT_VID)) * RGsqrt[p];
-        dt5[MOMZ_VID][o + p] =
-            -(E11 * DF(p, 0, MOMZ_VID) + E22 * DF(p, 1, MOMZ_VID) + E33 * DF(p, 2, MOMZ_VID) + DF(p, 3, MOMZ_VID)) * RGsqrt[p];
+        if (hevi) {
+          dt5[DENS_VID][o + p] = -(E11 * DF(p, 0, DENS_VID) + E22 * DF(p, 1, DENS_VID) + DF(p, 3, DENS_VID)) * RGsqrt[p];
+          dt5[RHOT_VID][o + p] = -(E11 * DF(p, 0, RHOT_VID) + E22 * DF(p, 1, RHOT_VID) + DF(p, 3, RHOT_VID)) * RGsqrt[p];
+          dt5[MOMZ_VID][o + p] =
+              -(E11 * DF(p, 0, MOMZ_VID) + E22 * DF(p, 1, MOMZ_VID) + E33 * DF(p, 2, MOMZ_VID) + DF(p, 3, MOMZ_VID)) * RGsqrt[p];
+        } else {
+          dt5[DENS_VID][o + p] = -(E11 * DF(p, 0, DENS_VID) + E22 * DF(p, 1, DENS_VID) + E33 * DF(p, 2, DENS_VID) + DF(p, 3, DENS_VID)) * RGsqrt[p];
+          dt5[RHOT_VID][o + p] = -(E11 * DF(p, 0, RHOT_VID) + E22 * DF(p, 1, RHOT_VID) + E33 * DF(p, 2, RHOT_VID) + DF(p, 3, RHOT_VID)) * RGsqrt[p];
+          dt5[MOMZ_VID][o + p] =
+              -(E11 * DF(p, 0, MOMZ_VID) + E22 * DF(p, 1, MOMZ_VID) + E33 * DF(p, 2, MOMZ_VID) + DF(p, 3, MOMZ_VID)) * RGsqrt[p] - c.GRAV * drho[p];
+        }
         const size_t i2 = size_t(p % Nfp) + size_t(ke2d) * Nfp;
         const double X = std::tan(m.alpha2D[i2]), Y = std::tan(m.beta2D[i2]);
         const double twoOVdel2 = 2.0 / (1.0 + X * X + Y * Y);
@@ -192,4 +205,11 @@ void global_hevi_cal_tend(const Element& e, const Mesh& m, const Consts& c, cons
   }
 }
 
+}  // namespace feo
+
+namespace feo {
+void global_hevi_numflux_generalhvc(const Element& e, const Mesh& m, const Consts& c, const DynState& s, vec& del_flux) {
+  global_numflux_generalhvc(e, m, c, s, true, del_flux);
+}
+void global_hevi_cal_tend(const Element& e, const Mesh& m, const Consts& c, const DynState& s, double* dt5[5]) { global_cal_tend(e, m, c, s, true, dt5); }
 }  // namespace feo

@@ -189,6 +189,8 @@ void numdiff_apply(const Element& e, const Mesh& m, const NumdiffCfg& cfg, DynSt
 // global (cubed-sphere) HEVI: explicit part (dyn_global.cpp); the column solve is hevi_cal_vi
 void global_hevi_numflux_generalhvc(const Element& e, const Mesh& m, const Consts& c, const DynState& s, vec& del_flux);
 void global_hevi_cal_tend(const Element& e, const Mesh& m, const Consts& c, const DynState& s, double* dt5[5]);
+void global_numflux_generalhvc(const Element& e, const Mesh& m, const Consts& c, const DynState& s, bool hevi, vec& del_flux);
+void global_cal_tend(const Element& e, const Mesh& m, const Consts& c, const DynState& s, bool hevi, double* dt5[5]);
 
 struct Driver {
   Element elem;

@@ -118,12 +118,15 @@ void sphere_update(Driver* d[6]) {
     sphere_exchange(e, mesh, sc, u1, u2);
   };
   const int ns = d[0]->tint.sc.nstage;
-  for (int p = 0; p < 6; ++p) {
-    const size_t nint = size_t(e.Np) * d[p]->mesh.Ne;
-    for (int v : rkvar) d[p]->tint.store_var0(d[p]->st.prog(v), v, 0, nint);
-  }
+  const bool hevi = d[0]->hevi;
+  if (hevi)
+    for (int p = 0; p < 6; ++p) {
+      const size_t nint = size_t(e.Np) * d[p]->mesh.Ne;
+      for (int v : rkvar) d[p]->tint.store_var0(d[p]->st.prog(v), v, 0, nint);
+    }
   for (int stage = 0; stage < ns; ++stage) {
     for (int p = 0; p < 6; ++p) {
+      if (!hevi) { drhot2pres(d[p]->elem, d[p]->mesh, d[p]->cst, d[p]->st); continue; }
       Driver& D = *d[p];
       const size_t nint = size_t(e.Np) * D.mesh.Ne;
       const int ind = D.tint.sc.indmap[stage];
@@ -141,7 +144,7 @@ void sphere_update(Driver* d[6]) {
       apply_bc_progvars(D.elem, D.mesh, D.bnd, D.st);
       double* out[5];
       for (int v = 0; v < 5; ++v) out[v] = D.tint.tend_ex_buf(v, ind);
-      global_hevi_cal_tend(D.elem, D.mesh, D.cst, D.st, out);
+      global_cal_tend(D.elem, D.mesh, D.cst, D.st, hevi, out);
       if (D.phytend) add_phy_tend(D.elem, D.mesh, D.cst, D.st, D.entot_conserve, out);
       for (int v : rkvar) D.tint.advance(stage, D.st.prog(v), v, 0, nint);
     }

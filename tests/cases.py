@@ -93,9 +93,9 @@ class GlobalPanelCase(DensityCurrentCase):
     lateral halo of the tile holds its own face values (no panel-edge exchange in this scope)."""
 
     def __init__(self, p=7, panelID=1, NeX=2, NeY=2, NeZ=3, ztop=30.0e3, dt=20.0, tinteg="IMEX_ARK324", modalfilter=True,
-                 u0=30.0, T0=300.0, perturb=1.0, OHM=None, balanced=True):
+                 u0=30.0, T0=300.0, perturb=1.0, OHM=None, balanced=True, eqs="GLOBALNONHYDRO3D_HEVI"):
         self.p, self.dt, self.tinteg, self.modalfilter = p, dt, tinteg, modalfilter
-        self.eqs = "GLOBALNONHYDRO3D_HEVI"
+        self.eqs = eqs
         self.periodic = (False, False, False)
         self.NprcX = self.NprcY = 1
         self.pi = self.pj = 0
@@ -155,10 +155,11 @@ class GlobalSphereCase:
     solid-body rotation (gradient-wind balance) plus, when perturb != 0, a second solid-body rotation about a tilted axis
     (smooth across every panel edge and both poles), a vertical-velocity pattern and a warm blob."""
 
-    def __init__(self, p=7, Ne=2, NeZ=2, ztop=30.0e3, dt=20.0, tinteg="IMEX_ARK324", modalfilter=True, u0=30.0, T0=300.0, perturb=1.0):
+    def __init__(self, p=7, Ne=2, NeZ=2, ztop=30.0e3, dt=20.0, tinteg="IMEX_ARK324", modalfilter=True, u0=30.0, T0=300.0, perturb=1.0,
+                 eqs="GLOBALNONHYDRO3D_HEVI"):
         from fe_project_b200.cubedsphere import CubedSphere, cs2cart, cs2lonlat, lonlat2cs_vec
         self.p, self.dt, self.tinteg, self.modalfilter, self.ztop = p, dt, tinteg, modalfilter, ztop
-        self.eqs = "GLOBALNONHYDRO3D_HEVI"
+        self.eqs = eqs
         self.elem = HexElement(p)
         self.consts = c = dict(C0)
         self.cs = CubedSphere(self.elem, Ne, NeZ, ztop, c["RPlanet"])

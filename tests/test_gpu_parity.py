@@ -563,3 +563,36 @@ def test_terrain_following_steps(p, dims, dt):
         assert rel_l2(g[nm][:n], o.arr(nm)[:n]) <= TOL, nm
     mo, mg = o.monitor(), d.monitor()
     assert abs(mo[1] - mg[1]) <= 1e-12 * abs(mo[1])
+
+
+# ------------------------------------------------------------------------------ GLOBALNONHYDRO3D_HEVE (shallow atmosphere)
+@pytest.mark.parametrize("panelID", [2, 5, 6])
+def test_global_heve_panel_tendency(panelID):
+    """heve_numflux_get_generalhvc + globalnonhydro3d_rhot_heve cal_tend_shallow_atm on one panel."""
+    case = GlobalPanelCase(p=7, panelID=1, NeX=2, NeY=2, NeZ=3, eqs="GLOBALNONHYDRO3D_HEVE", tinteg="ERK_SSP_4s3o", dt=0.5)
+    case.panelID = panelID
+    case.mesh.panelID = panelID
+    o = case.make_oracle()
+    d = case.make_driver(o)
+    for w in ("exchange", "pressure", "bc", "tend_ex"):
+        o.piece(w)
+    t = d.cal_tend_ex()
+    n = case.mesh.Ne * case.elem.Np
+    N = case.mesh.NeA * case.elem.Np
+    te = o.arr("tend_ex")[:5 * N].reshape(5, -1)[:, :n]
+    for nm, iv in TEND:
+        assert rel_l2(t[nm], te[iv]) <= 5e-11, nm
+
+
+@pytest.mark.parametrize("tinteg,mf", [("ERK_SSP_4s3o", True), ("ERK_SSP_3s3o", False)])
+def test_global_heve_sphere_steps(tinteg, mf):
+    """Six linked panels advanced with the explicit scheme (fedg_group_update, HEVE pieces); vertical acoustic CFL < 1."""
+    case = GlobalSphereCase(p=7, Ne=2, NeZ=2, dt=0.5, tinteg=tinteg, modalfilter=mf, eqs="GLOBALNONHYDRO3D_HEVE")
+    s = case.make_oracle()
+    g = case.make_driver()
+    s.update(6); g.Update(6)
+    for P, (d, o, m) in enumerate(zip(g.panels, s.panels, case.cs.panels)):
+        got = d.get_prog()
+        n = m.Ne * case.elem.Np
+        for nm in PROG:
+            assert rel_l2(got[nm][:n], o.arr(nm)[:n]) <= TOL, (P, nm)

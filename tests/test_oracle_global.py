@@ -70,3 +70,26 @@ def test_steps_stay_finite_and_vi_is_the_regional_solver():
     for k in ("DDENS", "MOMX", "MOMY", "MOMZ", "DRHOT"):
         assert np.isfinite(o.arr(k)[:n]).all()
     assert np.abs(o.arr("MOMZ")[:n]).max() < 1.0
+
+
+def test_global_heve_steady_state_and_hydrostatic_residual():
+    """GLOBALNONHYDRO3D_HEVE (rhot_heve_numflux.F90:1543-1772, globalnonhydro3d_rhot_heve.F90:338-600) on the whole sphere: the
+    balanced rotation is steady; the MOMZ residual is the discretisation error of the hydrostatic balance and converges too."""
+    from cases import GlobalSphereCase
+    cor = 2 * 7.292e-5 * 30.0 / 6.37122e6
+    hm, wz = [], []
+    for p in (3, 5, 7):
+        case = GlobalSphereCase(p=p, Ne=2, NeZ=2, perturb=0.0, tinteg="ERK_SSP_3s3o", dt=1.0, eqs="GLOBALNONHYDRO3D_HEVE")
+        s = case.make_oracle()
+        for o in s.panels:
+            o.piece("pressure")
+        s.exchange(with_dpres=True)
+        a = b = 0.0
+        for o, m in zip(s.panels, case.cs.panels):
+            o.piece("bc"); o.piece("tend_ex")
+            n, N = m.Ne * case.elem.Np, m.NeA * case.elem.Np
+            te = o.arr("tend_ex")[:5 * N].reshape(5, -1)[:, :n]
+            a = max(a, np.abs(te[3]).max(), np.abs(te[4]).max()); b = max(b, np.abs(te[2]).max())
+        hm.append(a); wz.append(b)
+    assert hm[0] < 0.2 * cor and hm[1] < 0.1 * hm[0] and hm[2] < 0.1 * hm[1], hm
+    assert wz[1] < 0.05 * wz[0] and wz[2] < 0.05 * wz[1] and wz[2] < 1e-6, wz
