@@ -545,7 +545,6 @@ int fedg_set_phy_tend(fedg_ctx* c, const double* DENS_tp, const double* MOMX_tp,
   for (int k = 0; k < 6 && !nz; ++k)
     for (size_t n = 0; n < c->nint && !nz; ++n) if (h[k][n] != 0.0) nz = true;
   if (!nz) return FEDG_OK;
-  if (c->global) return fail(FEDG_ERR_UNSUPPORTED, "physics tendencies are not wired into the global equation set yet");
   for (int k = 0; k < 6; ++k) { int rc = upload(c, c->phyt[k], h[k], c->nint); if (rc) return rc; }
   CUDA_TRY(cudaStreamSynchronize(c->stream));
   c->has_phyt = true;

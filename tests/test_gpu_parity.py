@@ -596,3 +596,26 @@ def test_global_heve_sphere_steps(tinteg, mf):
         n = m.Ne * case.elem.Np
         for nm in PROG:
             assert rel_l2(got[nm][:n], o.arr(nm)[:n]) <= TOL, (P, nm)
+
+
+def test_global_panel_with_physics_tendencies():
+    """add_phy_tend is the same code for the global sets (driver_nonhydro3d.F90:843-857)."""
+    case = GlobalPanelCase(p=7, NeX=2, NeY=2, NeZ=3, dt=20.0)
+    o = case.make_oracle()
+    d = case.make_driver(o)
+    m, e = case.mesh, case.elem
+    n, N = m.Ne * e.Np, m.NeA * e.Np
+    a, z = m.pos_en[0].reshape(-1), m.pos_en[2].reshape(-1)
+    tp = {"DENS_tp": 1e-7 * np.sin(3 * a), "MOMX_tp": 1e-9 * np.cos(z / 5e3), "MOMY_tp": -5e-10 * np.sin(z / 7e3),
+          "MOMZ_tp": 1e-4 * np.sin(2 * a) * np.sin(z / 6e3), "RHOT_tp": 1e-4 * np.cos(2 * a), "RHOH_p": 0.5 * np.exp(-((z - 1e4) / 4e3) ** 2)}
+    full = {}
+    for k, v in tp.items():
+        arr = np.zeros(N); arr[:n] = v
+        o.arr(k)[:] = arr
+        full[k] = arr
+    o.set_phytend(True)
+    d.set_phy_tend(*(full[k] for k in ("DENS_tp", "MOMX_tp", "MOMY_tp", "MOMZ_tp", "RHOT_tp", "RHOH_p")))
+    o.update(4); d.Update(4)
+    g = d.get_prog()
+    for nm in PROG:
+        assert rel_l2(g[nm][:n], o.arr(nm)[:n]) <= TOL, nm
