@@ -38,6 +38,9 @@ struct DevBuf {
     n = n_;
     cudaError_t e = cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(double));
     if (e == cudaSuccess) e = cudaMemset(p, 0, std::max<size_t>(n, 1) * sizeof(double));
+    // the memset runs on the legacy stream, the context's streams are non-blocking: without this wait an upload that
+    // follows on the context stream could be overtaken by the zero fill (seen as a test-order dependent parity failure)
+    if (e == cudaSuccess) e = cudaStreamSynchronize(0);
     return e;
   }
   void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
@@ -71,6 +74,7 @@ struct fedg_ctx {
   int Ne = 0, NeA = 0, NeX = 0, NeY = 0, NeZ = 0, Ne2D = 0, Nhalo = 0;
   size_t nint = 0, nall = 0;  // Np*Ne, Np*Ne + Nhalo
   bool terrain = false, moist = false, has_cor = false, has_phyd = false;
+  bool zface_contig = false;
   bool global = false; int panel = 0;   // cubed-sphere panel tile (GLOBALNONHYDRO3D_HEVI)
   bool dyn_ready = false, aux_ready = false;
   PhysConst c{};
@@ -320,6 +324,15 @@ int fedg_create(const fedg_mesh_desc* d, fedg_ctx** out) {
       vP[q] = int(vp);
     }
   }
+  // z faces whose exterior nodes are Nfp consecutive, 16-byte aligned values (the element above / below, or a halo face):
+  // stage_p7 fetches them with one bulk copy per field instead of per-node gathers
+  c->zface_contig = true;
+  for (int ke = 0; ke < Ne && c->zface_contig; ++ke)
+    for (int f = 4; f < 6 && c->zface_contig; ++f) {
+      const int* row = &vP[size_t(ke) * NfpTot + f * Nfp];
+      if (row[0] % 2 != 0) c->zface_contig = false;
+      for (int p = 1; p < Nfp; ++p) if (row[p] != row[0] + p) { c->zface_contig = false; break; }
+    }
   for (int h = 0; h < c->Nhalo; ++h) {
     vB[h] = d->VMapB[h] - 1;
     if (vB[h] < 0 || size_t(vB[h]) >= c->nint) return fail(FEDG_ERR_ARG, "VMapB out of range");
@@ -336,6 +349,27 @@ int fedg_create(const fedg_mesh_desc* d, fedg_ctx** out) {
   CUDA_TRY(cudaMalloc(&c->d_vmapB, vB.size() * sizeof(int)));
   CUDA_TRY(cudaMalloc(&c->d_halo_src, src.size() * sizeof(int)));
   CUDA_TRY(cudaMemcpy(c->d_vmapP, vP.data(), vP.size() * sizeof(int), cudaMemcpyHostToDevice));
+  {
+    // VMapP is read once per stage by every element and sits at the head of a dependent load chain (index, then the gather):
+    // keep it in the persisting part of L2 so that the 1.3 GB streamed per stage does not evict it (FEDG_L2_PERSIST=0: off)
+    const char* e = getenv("FEDG_L2_PERSIST");
+    int dev = 0, max_persist = 0, max_window = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev);
+    cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, dev);
+    const size_t bytes = vP.size() * sizeof(int);
+    if (!(e && e[0] == '0') && max_persist > 0 && max_window > 0) {
+      const size_t set_aside = std::min<size_t>(size_t(max_persist), std::max<size_t>(bytes, size_t(1) << 20));
+      cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, set_aside);
+      cudaStreamAttrValue av{};
+      av.accessPolicyWindow.base_ptr = c->d_vmapP;
+      av.accessPolicyWindow.num_bytes = std::min<size_t>(bytes, size_t(max_window));
+      av.accessPolicyWindow.hitRatio = float(std::min(1.0, double(set_aside) / double(av.accessPolicyWindow.num_bytes)));
+      av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+      av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+      if (cudaStreamSetAttribute(c->stream, cudaStreamAttributeAccessPolicyWindow, &av) != cudaSuccess) cudaGetLastError();
+    }
+  }
   CUDA_TRY(cudaMemcpy(c->d_emap2d, e2.data(), e2.size() * sizeof(int), cudaMemcpyHostToDevice));
   CUDA_TRY(cudaMemcpy(c->d_vmapB, vB.data(), vB.size() * sizeof(int), cudaMemcpyHostToDevice));
   CUDA_TRY(cudaMemcpy(c->d_halo_src, src.data(), src.size() * sizeof(int), cudaMemcpyHostToDevice));
@@ -639,8 +673,9 @@ void fill_stage_params(fedg_ctx* c, StageParams& P, int in, int out, int q0) {
   for (int k = 0; k < 6; ++k) P.phyt[k] = c->phyt[k].p;
   P.has_phyt = c->has_phyt;
   P.sponge = c->has_sponge ? c->sponge.p : nullptr; P.sponge_h = c->sponge_h;
-  { static int fp = -1; if (fp < 0) { const char* e = getenv("FEDG_FAST_POW"); fp = (e && e[0] == '1') ? 1 : 0; } P.fast_pow = fp; }
-  { static int pf = -1; if (pf < 0) { const char* e = getenv("FEDG_P7_PREFETCH"); pf = e ? atoi(e) : 0; } P.prefetch_dist = pf; }   // experiment knob, off: see DESIGN.md 4.1
+  { const char* e = getenv("FEDG_EXACT_POW"); P.exact_pow = (e && e[0] == '1') ? 1 : 0; }   // stage_p7: pow() instead of exp(e log x)
+  { const char* e = getenv("FEDG_P7_VARIANT"); P.variant = e ? atoi(e) : 0; }
+  { const char* e = getenv("FEDG_P7_ZEXT"); P.zface_contig = (!(e && e[0] == '0') && c->zface_contig) ? 1 : 0; }   // A/B knob
 }
 
 // DPRES of prog[buf] (interior): produced by the stage kernel that wrote prog[buf]; computed here only after the

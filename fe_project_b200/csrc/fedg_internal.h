@@ -63,7 +63,7 @@ struct StageParams {
   int Ne, Ne2D;
   const int* elem_list;  // when non-null: process elements elem_list[0..nelem) (interior / tile-boundary split)
   int nelem;
-  int has_cor, has_phyd, do_filter, write_pres, fast_pow;
+  int has_cor, has_phyd, do_filter, write_pres, exact_pow;
   // global (cubed-sphere panel) equation set: 2D metric tables [6][Ne2D*Nfp] = GsqrtH, G11, G12, G22, X = tan(alpha),
   // Y = tan(beta); planetary rotation rate; panel id 1..6
   const double* g2d;
@@ -75,7 +75,8 @@ struct StageParams {
   // sponge layer: Rayleigh damping coefficient per node (Np,Ne), NULL = off; sponge_h = 1 damps MOMX / MOMY too
   const double* sponge;
   double sponge_h;
-  int prefetch_dist;     // stage_p7: elements ahead whose inputs are pulled into L2 (0 = off)
+  int variant;           // stage_p7 tuning bits (A/B measurements)
+  int zface_contig;      // stage_p7: exterior z-face values are 64 consecutive nodes per face (bulk copies instead of gathers)
 };
 
 struct HaloParams {

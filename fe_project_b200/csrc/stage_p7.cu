@@ -29,7 +29,7 @@ constexpr int NP = 8, N2 = 64, N3 = 512, NFT = 384;
 constexpr int KS_FZ = 68;   // k-stride of the z-staging layout  [k][j][i]: conflict-free B-fragment reads
 constexpr int KS_Z = 72;    // k-stride of the z-result layout   [k][j][i]: conflict-free 128-bit writes and reads
 constexpr int PLS = 12;     // row stride of the per-warp plane  [j][i]
-constexpr int TAB = 4 * 64 + 16;                       // D, Fh, Fv, VP, Lw
+constexpr int TAB = 4 * 64 + 16;                       // D, Lw, VP, Fh, Fv: the leading 272 doubles of ElemTables
 constexpr int STASH = 9 * N3;
 constexpr int ZREG = NVAR * NP * KS_FZ + NVAR * NP * KS_Z;   // sFz + sZ alias the stash
 constexpr int REGA = STASH > ZREG ? STASH : ZREG;
@@ -42,6 +42,21 @@ __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b)
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
+// the nine fields staged per element, in stash order
+__device__ __forceinline__ const double* stage_field(const StageParams& P, int l) {
+  switch (l) {
+    case 0: return P.qin[V_DDENS];
+    case 1: return P.qin[V_MOMX];
+    case 2: return P.qin[V_MOMY];
+    case 3: return P.qin[V_MOMZ];
+    case 4: return P.qin[V_DRHOT];
+    case 5: return P.dens_hyd;
+    case 6: return P.pres_hyd;
+    case 7: return P.therm_hyd;
+    default: return P.dpin;
+  }
+}
+
 template <bool TERRAIN, bool MOIST, bool HEVI, bool GLOBAL>
 __global__ void __launch_bounds__(256, 3) stage_p7_kernel(const __grid_constant__ StageParams P) {
   using namespace p7;
@@ -52,55 +67,42 @@ __global__ void __launch_bounds__(256, 3) stage_p7_kernel(const __grid_constant_
   const size_t gn = eb + n0;
 
   extern __shared__ __align__(16) double smem[];
+  // tables arrive as one bulk copy of the device ElemTables struct: D, Lw, VP, Fh, Fv (fedg_internal.h)
   double* sTabD = smem;
-  double* sTabFh = smem + 64;
-  double* sTabFv = smem + 128;
-  double* sTabVP = smem + 192;
-  double* sTabLw = smem + 256;
+  double* sTabLw = smem + 64;
+  double* sTabVP = smem + 80;
+  double* sTabFh = smem + 144;
+  double* sTabFv = smem + 208;
   double* sStash = smem + TAB;               // [9][512], dead after the face phase
   double* sFz = smem + TAB;                  // [5][8*KS_FZ]   aliases the stash
   double* sZ = sFz + NVAR * NP * KS_FZ;      // [5][8*KS_Z]
   double* sDel = smem + TAB + REGA;          // [5][384]
+  double* sExt = sDel + NVAR * NFT;          // [2][9][64] exterior side of the z faces; aliases the planes (first written in phase 5)
   double* sPx = sDel + NVAR * NFT + size_t(w) * 2 * NP * PLS;   // this warp's planes [j][i], row stride PLS
   double* sPy = sPx + NP * PLS;
   uint64_t* sBar = reinterpret_cast<uint64_t*>(smem + SM_DOUBLES);
+  const size_t fb = size_t(ke) * NFT;
+  // exterior z-face values by bulk copy when every z face of the mesh maps to 64 consecutive nodes (the element above / below
+  // or a halo face: checked at fedg_create); the terrain instantiation keeps the gathers (it needs three metric fields more)
+  const bool zext = !TERRAIN && P.zface_contig;
 
-  // ---- phase 0: TMA bulk loads of the element's nine input fields
+  // ---- phase 0: TMA bulk loads issued by the lanes of warp 0: nine input fields of the element, 2 x 9 exterior z-face
+  //      rows of 512 B, the operator tables
   if (tid == 0) {
+    constexpr uint32_t BYTES = N3 * sizeof(double), FBYTES = N2 * sizeof(double), TBYTES = TAB * sizeof(double);
     mbar_init(sBar, 1);
-    constexpr uint32_t BYTES = N3 * sizeof(double);
-    mbar_expect_tx(sBar, 9 * BYTES);
-    tma_load_1d(sStash + 0 * N3, P.qin[V_DDENS] + eb, BYTES, sBar);
-    tma_load_1d(sStash + 1 * N3, P.qin[V_MOMX] + eb, BYTES, sBar);
-    tma_load_1d(sStash + 2 * N3, P.qin[V_MOMY] + eb, BYTES, sBar);
-    tma_load_1d(sStash + 3 * N3, P.qin[V_MOMZ] + eb, BYTES, sBar);
-    tma_load_1d(sStash + 4 * N3, P.qin[V_DRHOT] + eb, BYTES, sBar);
-    tma_load_1d(sStash + 5 * N3, P.dens_hyd + eb, BYTES, sBar);
-    tma_load_1d(sStash + 6 * N3, P.pres_hyd + eb, BYTES, sBar);
-    tma_load_1d(sStash + 7 * N3, P.therm_hyd + eb, BYTES, sBar);
-    tma_load_1d(sStash + 8 * N3, P.dpin + eb, BYTES, sBar);
-    // experiment (FEDG_P7_PREFETCH=<elements ahead>, default off): pull the inputs of a later element into L2.  Measured
-    // 0.5825 ms per launch without, 0.5823 / 0.5865 / 0.5935 ms at 222 / 444 / 888 elements ahead: the mbarrier wait is not
-    // DRAM latency that a prefetch could hide
-    if (P.prefetch_dist > 0) {
-      const int bn = int(blockIdx.x) + P.prefetch_dist;
-      const int nb = P.elem_list ? P.nelem : P.Ne;
-      if (bn < nb) {
-        const size_t en = size_t(P.elem_list ? P.elem_list[bn] : bn) * N3;
-        tma_prefetch_l2(P.qin[V_DDENS] + en, BYTES); tma_prefetch_l2(P.qin[V_MOMX] + en, BYTES); tma_prefetch_l2(P.qin[V_MOMY] + en, BYTES);
-        tma_prefetch_l2(P.qin[V_MOMZ] + en, BYTES); tma_prefetch_l2(P.qin[V_DRHOT] + en, BYTES); tma_prefetch_l2(P.dens_hyd + en, BYTES);
-        tma_prefetch_l2(P.pres_hyd + en, BYTES); tma_prefetch_l2(P.therm_hyd + en, BYTES); tma_prefetch_l2(P.dpin + en, BYTES);
+    mbar_expect_tx(sBar, 9 * BYTES + TBYTES + (zext ? 18 * FBYTES : 0u));
+#pragma unroll
+    for (int l = 0; l < 9; ++l) tma_load_1d(sStash + l * N3, stage_field(P, l) + eb, BYTES, sBar);
+    tma_load_1d(smem, P.tab, TBYTES, sBar);
+    if (zext) {
+      const size_t ib4 = size_t(P.vmapP[fb + 4 * N2]), ib5 = size_t(P.vmapP[fb + 5 * N2]);
+#pragma unroll
+      for (int l = 0; l < 9; ++l) {
+        tma_load_1d(sExt + l * N2, stage_field(P, l) + ib4, FBYTES, sBar);
+        tma_load_1d(sExt + (9 + l) * N2, stage_field(P, l) + ib5, FBYTES, sBar);
       }
     }
-  }
-  for (int m = tid; m < TAB; m += 256) {
-    double v;
-    if (m < 64) v = P.tab->D[m];
-    else if (m < 128) v = P.tab->Fh[m - 64];
-    else if (m < 192) v = P.tab->Fv[m - 128];
-    else if (m < 256) v = P.tab->VP[m - 192];
-    else v = P.tab->Lw[m - 256];
-    smem[m] = v;
   }
   const double E11 = P.escale[ke], E22 = P.escale[P.Ne + ke], E33 = P.escale[2 * size_t(P.Ne) + ke];
   const int ke2d = P.emap2d[ke];
@@ -128,37 +130,10 @@ __global__ void __launch_bounds__(256, 3) stage_p7_kernel(const __grid_constant_
     Yn = *reinterpret_cast<const double2*>(P.g2d + 5 * n2d + h);
   }
   // exterior-side gather of this thread's first face node, issued while the bulk copies are in flight
-  const size_t fb = size_t(ke) * NFT;
   RawSide<TERRAIN> pre;
   pre.load(P, size_t(P.vmapP[fb + tid]));
-  __syncthreads();   // barrier init + tables visible
+  __syncthreads();   // barrier initialised before anybody polls it
   mbar_wait(sBar, 0);
-
-  // ---- phase 1: own-node values (two adjacent nodes per lane: 128-bit shared loads)
-  const double2 dd = *reinterpret_cast<const double2*>(sStash + 0 * N3 + n0);
-  const double2 mx = *reinterpret_cast<const double2*>(sStash + 1 * N3 + n0);
-  const double2 my = *reinterpret_cast<const double2*>(sStash + 2 * N3 + n0);
-  const double2 mz = *reinterpret_cast<const double2*>(sStash + 3 * N3 + n0);
-  const double2 dr = *reinterpret_cast<const double2*>(sStash + 4 * N3 + n0);
-  const double2 dp = *reinterpret_cast<const double2*>(sStash + 8 * N3 + n0);
-  double2 rdens, pt;
-  {
-    const double2 dh = *reinterpret_cast<const double2*>(sStash + 5 * N3 + n0);
-    const double2 th = *reinterpret_cast<const double2*>(sStash + 7 * N3 + n0);
-    rdens.x = 1.0 / (dd.x + dh.x); rdens.y = 1.0 / (dd.y + dh.y);
-    pt.x = (th.x + dr.x) * rdens.x; pt.y = (th.y + dr.y) * rdens.y;
-  }
-  double2 drho = make_double2(0.0, 0.0);
-  if (!HEVI) {  // VFilterPM1 of DDENS along the column (rhot_heve.F90:442-443), l ascending
-    const double* col = sStash + (n0 - 64 * w);
-#pragma unroll
-    for (int l = 0; l < NP; ++l) {
-      const double2 c = *reinterpret_cast<const double2*>(col + 64 * l);
-      const double vp = sTabVP[w * NP + l];
-      if (l == 0) { drho.x = c.x * vp; drho.y = c.y * vp; }
-      else { drho.x += c.x * vp; drho.y += c.y * vp; }
-    }
-  }
 
   // ---- phase 2: face flux jumps (384 face nodes over 256 threads: one pass for all, a second one for warps 0-3)
   {
@@ -178,7 +153,13 @@ __global__ void __launch_bounds__(256, 3) stage_p7_kernel(const __grid_constant_
         default: nloc = fp + (NP - 1) * N2; break;
       }
       RawSide<TERRAIN> ex;
-      if (pass == 0) ex = pre; else ex.load(P, size_t(P.vmapP[fb + m]));
+      if (pass == 0) ex = pre;
+      else if (zext) {
+        const double* se = sExt + (f - 4) * 9 * N2 + fp;
+        ex.dd = se[0]; ex.mx = se[N2]; ex.my = se[2 * N2]; ex.mz = se[3 * N2]; ex.dr = se[4 * N2];
+        ex.dh = se[5 * N2]; ex.ph = se[6 * N2]; ex.th = se[7 * N2]; ex.dp = se[8 * N2];
+        ex.Gs = 1.0; ex.G13 = 0.0; ex.G23 = 0.0;
+      } else ex.load(P, size_t(P.vmapP[fb + m]));
       double GsM = 1.0, G13M = 0.0, G23M = 0.0;
       if (TERRAIN) { GsM = P.gsqrt[eb + nloc]; G13M = P.g13[eb + nloc]; G23M = P.g23[eb + nloc]; }
       double fG11 = 1.0, fG12 = 0.0, fG22 = 1.0;
@@ -218,6 +199,33 @@ __global__ void __launch_bounds__(256, 3) stage_p7_kernel(const __grid_constant_
       }
 #pragma unroll
       for (int v = 0; v < NVAR; ++v) sDel[v * NFT + m] = o5[v];
+    }
+  }
+
+  // ---- own-node values (two adjacent nodes per lane: 128-bit shared loads).  Read after the face phase, right before the
+  //      stash dies: held across the face phase they were spilled to local memory and reloaded
+  const double2 dd = *reinterpret_cast<const double2*>(sStash + 0 * N3 + n0);
+  const double2 mx = *reinterpret_cast<const double2*>(sStash + 1 * N3 + n0);
+  const double2 my = *reinterpret_cast<const double2*>(sStash + 2 * N3 + n0);
+  const double2 mz = *reinterpret_cast<const double2*>(sStash + 3 * N3 + n0);
+  const double2 dr = *reinterpret_cast<const double2*>(sStash + 4 * N3 + n0);
+  const double2 dp = *reinterpret_cast<const double2*>(sStash + 8 * N3 + n0);
+  double2 rdens, pt;
+  {
+    const double2 dh = *reinterpret_cast<const double2*>(sStash + 5 * N3 + n0);
+    const double2 th = *reinterpret_cast<const double2*>(sStash + 7 * N3 + n0);
+    rdens.x = 1.0 / (dd.x + dh.x); rdens.y = 1.0 / (dd.y + dh.y);
+    pt.x = (th.x + dr.x) * rdens.x; pt.y = (th.y + dr.y) * rdens.y;
+  }
+  double2 drho = make_double2(0.0, 0.0);
+  if (!HEVI) {  // VFilterPM1 of DDENS along the column (rhot_heve.F90:442-443), l ascending
+    const double* col = sStash + (n0 - 64 * w);
+#pragma unroll
+    for (int l = 0; l < NP; ++l) {
+      const double2 c = *reinterpret_cast<const double2*>(col + 64 * l);
+      const double vp = sTabVP[w * NP + l];
+      if (l == 0) { drho.x = c.x * vp; drho.y = c.y * vp; }
+      else { drho.x += c.x * vp; drho.y += c.y * vp; }
     }
   }
 
@@ -280,7 +288,10 @@ __global__ void __launch_bounds__(256, 3) stage_p7_kernel(const __grid_constant_
   const bool tend_mode = P.tend_out[0] != nullptr;
   const double bx0 = E11 * Dg0, bx1 = E11 * Dg1, ay0 = E22 * Dg0, ay1 = E22 * Dg1;
   const int ownP = PLS * g + 2 * t, ownZ = 2 * t + 8 * g + KS_Z * w;
-  double2 qnew[NVAR];
+  double2 drn = make_double2(0.0, 0.0);   // DRHOT of the new state, for its pressure
+  // background of the own nodes for the pressure of the new state: issued here, consumed after the loop
+  double2 ph_pre = make_double2(0.0, 0.0), th_pre = make_double2(0.0, 0.0);
+  if (!tend_mode) { ph_pre = *reinterpret_cast<const double2*>(P.pres_hyd + gn); th_pre = *reinterpret_cast<const double2*>(P.therm_hyd + gn); }
 #pragma unroll
   for (int iv = 0; iv < NVAR; ++iv) {
     const int v = order[iv];
@@ -413,7 +424,10 @@ __global__ void __launch_bounds__(256, 3) stage_p7_kernel(const __grid_constant_
       // stage for the z pass (sFz[v] is free: phase 4 has completed for every warp)
       *reinterpret_cast<double2*>(sFz + v * NP * KS_FZ + ownFz) = make_double2(h0, h1);
     }
-    qnew[iv] = r;
+    else {   // no filter: the stage output is final, store it now instead of carrying five results to the end of the loop
+      *reinterpret_cast<double2*>(P.qout[v] + gn) = r;
+      if (v == V_DRHOT) drn = r;
+    }
   }
 
   if (tend_mode) return;
@@ -430,32 +444,26 @@ __global__ void __launch_bounds__(256, 3) stage_p7_kernel(const __grid_constant_
       *reinterpret_cast<double2*>(sZ + v * NP * KS_Z + 2 * t + 8 * w + KS_Z * g) = make_double2(c0, c1);
     }
     __syncthreads();
+    const double2 rG = make_double2(1.0 / Gn.x, 1.0 / Gn.y);
 #pragma unroll
-    for (int iv = 0; iv < NVAR; ++iv) {
-      const double2 z = *reinterpret_cast<const double2*>(sZ + order[iv] * NP * KS_Z + ownZ);
-      qnew[iv] = make_double2(z.x * (1.0 / Gn.x), z.y * (1.0 / Gn.y));
+    for (int v = 0; v < NVAR; ++v) {
+      const double2 z = *reinterpret_cast<const double2*>(sZ + v * NP * KS_Z + ownZ);
+      const double2 r = make_double2(z.x * rG.x, z.y * rG.y);
+      *reinterpret_cast<double2*>(P.qout[v] + gn) = r;
+      if (v == V_DRHOT) drn = r;
     }
   }
-#pragma unroll
-  for (int iv = 0; iv < NVAR; ++iv) *reinterpret_cast<double2*>(P.qout[order[iv]] + gn) = qnew[iv];
 
   {  // pressure of the new state: next stage's DPRES; PRES diagnostic at the end of Update (driver:954-959)
-    const double2 ph = *reinterpret_cast<const double2*>(P.pres_hyd + gn), th = *reinterpret_cast<const double2*>(P.therm_hyd + gn);
+    const double2 ph = ph_pre, th = th_pre;
     double2 R = make_double2(P.c.Rdry, P.c.Rdry), e = make_double2(P.c.CPovCV, P.c.CPovCV);
     if (MOIST) {
       R = *reinterpret_cast<const double2*>(P.rtot + gn);
       const double2 cp = *reinterpret_cast<const double2*>(P.cptot + gn), cv = *reinterpret_cast<const double2*>(P.cvtot + gn);
       e = make_double2(cp.x / cv.x, cp.y / cv.y);
     }
-    const double2 drn = qnew[1];   // order[1] == V_DRHOT
-    double p0, p1;
-    if (P.fast_pow) {  // tuning experiment (FEDG_FAST_POW=1): exp(e log x) instead of pow(x, e)
-      p0 = P.c.PRES00 * exp(e.x * log(R.x * P.c.rP0 * (th.x + drn.x)));
-      p1 = P.c.PRES00 * exp(e.y * log(R.y * P.c.rP0 * (th.y + drn.y)));
-    } else {
-      p0 = eos_pres(R.x, P.c.rP0, th.x + drn.x, e.x, P.c.PRES00);
-      p1 = eos_pres(R.y, P.c.rP0, th.y + drn.y, e.y, P.c.PRES00);
-    }
+    const double p0 = eos_pres_fast(R.x, P.c.rP0, th.x + drn.x, e.x, P.c.PRES00, P.exact_pow);
+    const double p1 = eos_pres_fast(R.y, P.c.rP0, th.y + drn.y, e.y, P.c.PRES00, P.exact_pow);
     *reinterpret_cast<double2*>(P.dpout + gn) = make_double2(p0 - ph.x, p1 - ph.y);
     if (P.write_pres) *reinterpret_cast<double2*>(P.pres_out + gn) = make_double2(p0, p1);
   }

@@ -44,15 +44,21 @@ def cosine_bell_projected(mesh: LocalMeshCube, qmax, rx, ry, rz, xc, yc, zc, int
     vy = (mesh.ymax - mesh.ymin) * np.arange(NeY + 1) / NeY + mesh.ymin
     vz = mesh.FZ
     out = np.empty((mesh.Ne, e.Np))
-    for ke in range(mesh.Ne):
-        ex, ey, ez = mesh.ex[ke], mesh.ey[ke], mesh.ez[ke]
-        x = vx[ex] + 0.5 * (xq + 1.0) * (vx[ex + 1] - vx[ex])
-        y = vy[ey] + 0.5 * (xq + 1.0) * (vy[ey + 1] - vy[ey])
-        z = vz[ez] + 0.5 * (xq + 1.0) * (vz[ez + 1] - vz[ez])
-        r = np.sqrt(((x[None, None, :] - xc) / rx) ** 2 + ((y[None, :, None] - yc) / ry) ** 2
-                    + ((z[:, None, None] - zc) / rz) ** 2)
-        q = np.where(r <= 1.0, qmax * (0.5 * (1.0 + np.cos(np.pi * r))), 0.0)      # [kq, jq, iq]
-        out[ke] = np.einsum("kc,jb,ia,cba->kji", T1, T1, T1, q).reshape(-1)
+    h = 0.5 * (xq + 1.0)
+    CH = 512                                        # elements per batch: three batched 1D contractions instead of one einsum per element
+    for k0 in range(0, mesh.Ne, CH):
+        sl = slice(k0, min(k0 + CH, mesh.Ne))
+        ex, ey, ez = mesh.ex[sl], mesh.ey[sl], mesh.ez[sl]
+        x = vx[ex][:, None] + h[None, :] * (vx[ex + 1] - vx[ex])[:, None]        # (B, nq)
+        y = vy[ey][:, None] + h[None, :] * (vy[ey + 1] - vy[ey])[:, None]
+        z = vz[ez][:, None] + h[None, :] * (vz[ez + 1] - vz[ez])[:, None]
+        r = np.sqrt(((x[:, None, None, :] - xc) / rx) ** 2 + ((y[:, None, :, None] - yc) / ry) ** 2
+                    + ((z[:, :, None, None] - zc) / rz) ** 2)
+        q = np.where(r <= 1.0, qmax * (0.5 * (1.0 + np.cos(np.pi * r))), 0.0)      # [B, kq, jq, iq]
+        q = q @ T1.T                                                               # [B, kq, jq, i]
+        q = np.einsum("jb,Bcbi->Bcji", T1, q, optimize=True)
+        q = np.einsum("kc,Bcji->Bkji", T1, q, optimize=True)
+        out[sl] = q.reshape(q.shape[0], -1)
     return out
 
 
