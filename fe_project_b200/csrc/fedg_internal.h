@@ -75,7 +75,6 @@ struct StageParams {
   // sponge layer: Rayleigh damping coefficient per node (Np,Ne), NULL = off; sponge_h = 1 damps MOMX / MOMY too
   const double* sponge;
   double sponge_h;
-  int variant;           // stage_p7 tuning bits (A/B measurements)
   int zface_contig;      // stage_p7: exterior z-face values are 64 consecutive nodes per face (bulk copies instead of gathers)
 };
 

@@ -26,9 +26,9 @@ namespace fedg {
 
 namespace p7 {
 constexpr int NP = 8, N2 = 64, N3 = 512, NFT = 384;
-constexpr int KS_FZ = 68;   // k-stride of the z-staging layout  [k][j][i]: conflict-free B-fragment reads
+constexpr int KS_FZ = 70;   // k-stride of the z-staging layout  [k][j][i]: conflict-free B-fragment reads at k = 2t, 2t+1
 constexpr int KS_Z = 72;    // k-stride of the z-result layout   [k][j][i]: conflict-free 128-bit writes and reads
-constexpr int PLS = 12;     // row stride of the per-warp plane  [j][i]
+constexpr int PLS = 10;     // row stride of the per-warp plane  [j][i]: conflict-free B-fragment reads at j = 2t, 2t+1
 constexpr int TAB = 4 * 64 + 16;                       // D, Lw, VP, Fh, Fv: the leading 272 doubles of ElemTables
 constexpr int STASH = 9 * N3;
 constexpr int ZREG = NVAR * NP * KS_FZ + NVAR * NP * KS_Z;   // sFz + sZ alias the stash
@@ -78,8 +78,7 @@ __global__ void __launch_bounds__(256, 3) stage_p7_kernel(const __grid_constant_
   double* sZ = sFz + NVAR * NP * KS_FZ;      // [5][8*KS_Z]
   double* sDel = smem + TAB + REGA;          // [5][384]
   double* sExt = sDel + NVAR * NFT;          // [2][9][64] exterior side of the z faces; aliases the planes (first written in phase 5)
-  double* sPx = sDel + NVAR * NFT + size_t(w) * 2 * NP * PLS;   // this warp's planes [j][i], row stride PLS
-  double* sPy = sPx + NP * PLS;
+  double* sPl = sDel + NVAR * NFT + size_t(w) * 2 * NP * PLS;   // this warp's two planes [j][i], row stride PLS, used alternately
   uint64_t* sBar = reinterpret_cast<uint64_t*>(smem + SM_DOUBLES);
   const size_t fb = size_t(ke) * NFT;
   // exterior z-face values by bulk copy when every z face of the mesh maps to 64 consecutive nodes (the element above / below
@@ -88,9 +87,12 @@ __global__ void __launch_bounds__(256, 3) stage_p7_kernel(const __grid_constant_
 
   // ---- phase 0: TMA bulk loads issued by the lanes of warp 0: nine input fields of the element, 2 x 9 exterior z-face
   //      rows of 512 B, the operator tables
+  if (tid == 0) mbar_init(sBar, 1);
+  __syncthreads();   // barrier initialised before anybody polls it.  Placed here, ahead of every global load: the warps run
+                     // independently from now to the end of the face phase (behind the gathers it made every warp wait for
+                     // the slowest VMapP fetch of the block: 10 % of the stall samples)
   if (tid == 0) {
     constexpr uint32_t BYTES = N3 * sizeof(double), FBYTES = N2 * sizeof(double), TBYTES = TAB * sizeof(double);
-    mbar_init(sBar, 1);
     mbar_expect_tx(sBar, 9 * BYTES + TBYTES + (zext ? 18 * FBYTES : 0u));
 #pragma unroll
     for (int l = 0; l < 9; ++l) tma_load_1d(sStash + l * N3, stage_field(P, l) + eb, BYTES, sBar);
@@ -130,9 +132,11 @@ __global__ void __launch_bounds__(256, 3) stage_p7_kernel(const __grid_constant_
     Yn = *reinterpret_cast<const double2*>(P.g2d + 5 * n2d + h);
   }
   // exterior-side gather of this thread's first face node, issued while the bulk copies are in flight
+  // (computing the index of in-tile lateral neighbours arithmetically on structured meshes instead of fetching VMapP was
+  //  measured slower: 0.4748 vs 0.4633 ms per launch, the integer divisions cost more than the L2 hit)
   RawSide<TERRAIN> pre;
-  pre.load(P, size_t(P.vmapP[fb + tid]));
-  __syncthreads();   // barrier initialised before anybody polls it
+  const size_t iP0 = size_t(P.vmapP[fb + tid]);
+  pre.load(P, iP0);
   mbar_wait(sBar, 0);
 
   // ---- phase 2: face flux jumps (384 face nodes over 256 threads: one pass for all, a second one for warps 0-3)
@@ -168,7 +172,7 @@ __global__ void __launch_bounds__(256, 3) stage_p7_kernel(const __grid_constant_
         // (fill_halo_metric, mesh_cubedspheredom3d.F90:657-678)
         const size_t h = size_t(ke2d) * N2 + (nloc & 63);
         GsM = P.g2d[h]; fG11 = P.g2d[n2d + h]; fG12 = P.g2d[2 * n2d + h]; fG22 = P.g2d[3 * n2d + h];
-        const size_t iP = size_t(P.vmapP[fb + m]);
+        const size_t iP = (pass == 0) ? iP0 : size_t(P.vmapP[fb + m]);
         ex.Gs = GsM;
         if (iP < size_t(P.Ne) * N3) ex.Gs = P.g2d[size_t(P.emap2d[iP >> 9]) * N2 + (iP & 63)];
       }
@@ -261,7 +265,10 @@ __global__ void __launch_bounds__(256, 3) stage_p7_kernel(const __grid_constant_
     *reinterpret_cast<double2*>(sFz + v * NP * KS_FZ + ownFz) = Fz;
   }
   // constant fragments: D[g][t], D[g][t+4] scaled by the element metric, lift weights Lw[g][s=t] (t < 2)
-  const double Dg0 = sTabD[g * NP + t], Dg1 = sTabD[g * NP + t + 4];
+  // The contraction index of every 8-term product is split over the two k = 4 steps as l = 2t (first) and l = 2t + 1 (second):
+  // with this order the A fragment of the x-derivative is the lane's own node pair, no exchange through shared memory.
+  const double2 Dg = *reinterpret_cast<const double2*>(sTabD + g * NP + 2 * t);
+  const double Dg0 = Dg.x, Dg1 = Dg.y;
   const double lwA = (t < 2) ? sTabLw[g * 2 + t] : 0.0;
   __syncthreads();
 
@@ -273,7 +280,7 @@ __global__ void __launch_bounds__(256, 3) stage_p7_kernel(const __grid_constant_
       const int v = order[iv];
       if (HEVI && (v == V_DDENS || v == V_DRHOT)) continue;
       const double* src = sFz + v * NP * KS_FZ + g + 8 * w;
-      const double b0 = src[KS_FZ * t], b1 = src[KS_FZ * (t + 4)];
+      const double b0 = src[KS_FZ * 2 * t], b1 = src[KS_FZ * (2 * t + 1)];
       const double bl = (t < 2) ? sDel[v * NFT + (4 + t) * N2 + g + 8 * w] : 0.0;
       double c0 = 0.0, c1 = 0.0;
       dmma(c0, c1, a0, b0);
@@ -315,8 +322,8 @@ __global__ void __launch_bounds__(256, 3) stage_p7_kernel(const __grid_constant_
       if (P.rk.use_q0) q0v = *reinterpret_cast<const double2*>(P.q0[v] + gn);
       if (P.rk.add_vt || (P.rk.vt_update && !P.rk.vt_init)) vtv = *reinterpret_cast<const double2*>(P.vt[v] + gn);
     }
-    __syncwarp();   // previous variable's fragment reads of the planes are done
-    *reinterpret_cast<double2*>(sPx + ownP) = Fx;
+    double* sPy = sPl + (iv & 1) * NP * PLS;   // alternate planes: the reads of variable iv - 2 finished before the __syncwarp of iv - 1
+    if (P.do_filter) __syncwarp();              // ... but the filter of the previous variable read the other plane
     *reinterpret_cast<double2*>(sPy + ownP) = Fy;
     double c0 = 0.0, c1 = 0.0;
     if (!(HEVI && (v == V_DDENS || v == V_DRHOT))) {
@@ -325,12 +332,11 @@ __global__ void __launch_bounds__(256, 3) stage_p7_kernel(const __grid_constant_
     }
     __syncwarp();
     {
-      // x: out^T[j][i] += Fx^T[j][l] * (E11 D)[i][l]      A = Fx(i = t | t+4, j = g),  B = const
-      const double ax0 = sPx[PLS * g + t], ax1 = sPx[PLS * g + t + 4];
-      dmma(c0, c1, ax0, bx0);
-      dmma(c0, c1, ax1, bx1);
-      // y: out^T[j][i] += (E22 D)[j][l] * Fy^T[l][i]      A = const,  B = Fy(i = g, j = t | t+4)
-      const double by0 = sPy[PLS * t + g], by1 = sPy[PLS * (t + 4) + g];
+      // x: out^T[j][i] += Fx^T[j][l] * (E11 D)[i][l]      A = Fx(j = g, l = 2t | 2t+1) = the own pair,  B = const
+      dmma(c0, c1, Fx.x, bx0);
+      dmma(c0, c1, Fx.y, bx1);
+      // y: out^T[j][i] += (E22 D)[j][l] * Fy^T[l][i]      A = const,  B = Fy(i = g, j = 2t | 2t+1)
+      const double by0 = sPy[PLS * 2 * t + g], by1 = sPy[PLS * (2 * t + 1) + g];
       dmma(c0, c1, ay0, by0);
       dmma(c0, c1, ay1, by1);
       // lift, x faces (3: x-, 1: x+): A = jump(j = g, k = w) for s = t < 2, B = Lw[i = g][s]
@@ -410,17 +416,16 @@ __global__ void __launch_bounds__(256, 3) stage_p7_kernel(const __grid_constant_
     }
     if (P.do_filter) {
       // modal filter of the Gsqrt-weighted variable (dyn_dgm_modalfilter.F90:49-130): x and y passes on the own plane
-      __syncwarp();
-      *reinterpret_cast<double2*>(sPx + ownP) = make_double2(Gn.x * r.x, Gn.y * r.y);
-      __syncwarp();
+      const double2 Fh2 = *reinterpret_cast<const double2*>(sTabFh + g * NP + 2 * t);
       double f0 = 0.0, f1 = 0.0;
-      dmma(f0, f1, sPx[PLS * g + t], sTabFh[g * NP + t]);            // out^T[j][i] = g^T[j][l] Fh[i][l]
-      dmma(f0, f1, sPx[PLS * g + t + 4], sTabFh[g * NP + t + 4]);
-      *reinterpret_cast<double2*>(sPy + ownP) = make_double2(f0, f1);
+      dmma(f0, f1, Gn.x * r.x, Fh2.x);                               // out^T[j][i] = g^T[j][l] Fh[i][l], A = the own pair
+      dmma(f0, f1, Gn.y * r.y, Fh2.y);
+      double* sPf = sPl + ((iv & 1) ^ 1) * NP * PLS;                 // the plane not holding this variable's Fy
+      *reinterpret_cast<double2*>(sPf + ownP) = make_double2(f0, f1);
       __syncwarp();
       double h0 = 0.0, h1 = 0.0;
-      dmma(h0, h1, sTabFh[g * NP + t], sPy[PLS * t + g]);            // out^T[j][i] = Fh[j][l] r1^T[l][i]
-      dmma(h0, h1, sTabFh[g * NP + t + 4], sPy[PLS * (t + 4) + g]);
+      dmma(h0, h1, Fh2.x, sPf[PLS * 2 * t + g]);                     // out^T[j][i] = Fh[j][l] r1^T[l][i]
+      dmma(h0, h1, Fh2.y, sPf[PLS * (2 * t + 1) + g]);
       // stage for the z pass (sFz[v] is free: phase 4 has completed for every warp)
       *reinterpret_cast<double2*>(sFz + v * NP * KS_FZ + ownFz) = make_double2(h0, h1);
     }
@@ -434,13 +439,13 @@ __global__ void __launch_bounds__(256, 3) stage_p7_kernel(const __grid_constant_
 
   if (P.do_filter) {
     __syncthreads();   // all planes staged; every warp has finished reading sZ
-    const double a0 = sTabFv[g * NP + t], a1 = sTabFv[g * NP + t + 4];
+    const double a0 = sTabFv[g * NP + 2 * t], a1 = sTabFv[g * NP + 2 * t + 1];
 #pragma unroll
     for (int v = 0; v < NVAR; ++v) {
       const double* src = sFz + v * NP * KS_FZ + g + 8 * w;
       double c0 = 0.0, c1 = 0.0;
-      dmma(c0, c1, a0, src[KS_FZ * t]);                              // out_j[k][i] = Fv[k][l] r2_j[l][i]
-      dmma(c0, c1, a1, src[KS_FZ * (t + 4)]);
+      dmma(c0, c1, a0, src[KS_FZ * 2 * t]);                          // out_j[k][i] = Fv[k][l] r2_j[l][i]
+      dmma(c0, c1, a1, src[KS_FZ * (2 * t + 1)]);
       *reinterpret_cast<double2*>(sZ + v * NP * KS_Z + 2 * t + 8 * w + KS_Z * g) = make_double2(c0, c1);
     }
     __syncthreads();

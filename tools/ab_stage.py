@@ -4,6 +4,9 @@ import os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import torch
+import fe_project_b200._lib as _L
+if os.environ.get("AB_LIB"):
+    _L.LIB_PATH = os.path.join(ROOT, "fe_project_b200", os.environ["AB_LIB"])
 import bench
 from cases import DensityCurrentCase
 from fe_project_b200.dyncore import rk_tables
