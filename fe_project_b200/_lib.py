@@ -18,7 +18,7 @@ ABI_SYMBOLS = (
     "fedg_dyn_update", "fedg_dyn_update_host", "fedg_cal_tend_ex", "fedg_cal_vi", "fedg_get_pres",
     "fedg_exchange_halo", "fedg_monitor", "fedg_rk_info", "fedg_rk_coef", "fedg_elem_op",
     "fedg_last_timing", "fedg_comm_unique_id", "fedg_comm_init",
-    "fedg_set_phy_tend", "fedg_numdiff_init", "fedg_numdiff_apply", "fedg_sponge_init", "fedg_link_halo", "fedg_group_update", "fedg_sparsemat_matmul", "fedg_advect3d_init", "fedg_advect3d_set", "fedg_advect3d_get",
+    "fedg_set_phy_tend", "fedg_numdiff_init", "fedg_numdiff_apply", "fedg_sponge_init", "fedg_link_halo", "fedg_link_halo_recv", "fedg_link_halo_send", "fedg_group_exchange_halo", "fedg_group_update", "fedg_sparsemat_matmul", "fedg_advect3d_init", "fedg_advect3d_set", "fedg_advect3d_get",
     "fedg_advect3d_cal_tend", "fedg_advect3d_update",
 )
 
@@ -70,6 +70,9 @@ def load() -> C.CDLL:
     L.fedg_sponge_init.argtypes = [vp, cd, cd, ci, ci]
     L.fedg_link_halo.argtypes = [vp, ci, vp, vp, vp]
     L.fedg_group_update.argtypes = [vp, ci, ci]
+    L.fedg_link_halo_recv.argtypes = [vp, ci, ci, ci, vp]
+    L.fedg_link_halo_send.argtypes = [vp, ci, ci, vp, ci]
+    L.fedg_group_exchange_halo.argtypes = [vp, ci, ci]
     L.fedg_dyn_update.argtypes = [vp, ci]
     L.fedg_dyn_update_host.argtypes = [vp] * 6 + [ci]
     L.fedg_cal_tend_ex.argtypes = [vp] * 6

@@ -110,7 +110,13 @@ struct fedg_ctx {
   DevBuf nd_g[3], nd_lap[2];
   DevBuf sponge; double sponge_h = 0.0; bool has_sponge = false;
   // halo faces filled from another local mesh on the same device (cubed-sphere panel edges): fedg_link_halo
-  struct HaloLink { fedg_ctx* src = nullptr; int* d_src = nullptr; double* d_rot = nullptr; int off = 0, cnt = 0; } link[6];
+  //   src != nullptr: gathered from that mesh;  recvbuf != nullptr: the data of a mesh on another rank, shipped by NCCL into
+  //   recvbuf[6][cnt] (fedg_link_halo_recv) and scattered with the same rotation
+  struct HaloLink { fedg_ctx* src = nullptr; int* d_src = nullptr; double* d_rot = nullptr; int off = 0, cnt = 0;
+                    double* recvbuf = nullptr; int peer = -1, msg_id = 0; } link[6];
+  // interior nodes of this mesh that feed a halo face of a mesh on another rank (fedg_link_halo_send)
+  struct OutMsg { int peer = -1, msg_id = 0, cnt = 0; int* d_idx = nullptr; double* sendbuf = nullptr; };
+  std::vector<OutMsg> outmsg;
   int xbuf = 0;                    // buffer that holds the state other local meshes gather from (stage input of the explicit part)
   struct { int i0, in, mid, nxt; } hs{0, 0, 0, 0};   // buffer cursor of the HEVI stage pieces
   // timing
@@ -119,6 +125,8 @@ struct fedg_ctx {
   double last_ms_total = 0, last_ms_stage = 0; long last_launches = 0;
   ~fedg_ctx() {
     for (auto& e : ev) cudaEventDestroy(e);
+    for (auto& l : link) { if (l.d_src) cudaFree(l.d_src); if (l.d_rot) cudaFree(l.d_rot); if (l.recvbuf) cudaFree(l.recvbuf); }
+    for (auto& m : outmsg) { if (m.d_idx) cudaFree(m.d_idx); if (m.sendbuf) cudaFree(m.sendbuf); }
     if (d_vmapP) cudaFree(d_vmapP);
     if (d_emap2d) cudaFree(d_emap2d);
     if (d_vmapB) cudaFree(d_vmapB);
@@ -127,7 +135,6 @@ struct fedg_ctx {
     if (d_elem_inner) cudaFree(d_elem_inner);
     if (d_elem_bnd) cudaFree(d_elem_bnd);
     comm_destroy(comm);
-    for (auto& l : link) { if (l.d_src) cudaFree(l.d_src); if (l.d_rot) cudaFree(l.d_rot); }
     adv.release();
     for (auto& b : phyt) b.release();
     for (auto& b : nd_g) b.release();
@@ -616,7 +623,7 @@ struct LinkFields { const double* s[6]; double* d[6]; };
 __global__ void halo_link_kernel(LinkFields F, const int* __restrict__ src, const double* __restrict__ rot, size_t dst0, int cnt) {
   const int m = blockIdx.x * blockDim.x + threadIdx.x;
   if (m >= cnt) return;
-  const int i = src[m];
+  const int i = src ? src[m] : m;
   const size_t o = dst0 + m;
   F.d[V_DDENS][o] = F.s[V_DDENS][i]; F.d[V_MOMZ][o] = F.s[V_MOMZ][i]; F.d[V_DRHOT][o] = F.s[V_DRHOT][i]; F.d[5][o] = F.s[5][i];
   const double sx = F.s[V_MOMX][i], sy = F.s[V_MOMY][i];
@@ -630,12 +637,18 @@ void fill_halo(fedg_ctx* c, int buf, bool apply_bc);
 void fill_halo_links(fedg_ctx* c, int buf) {
   for (int f = 0; f < 6; ++f) {
     const auto& l = c->link[f];
-    if (!l.src) continue;
+    if (!l.src && !l.recvbuf) continue;
     LinkFields F{};
-    const int sb = l.src->xbuf;
-    for (int v = 0; v < NVAR; ++v) { F.s[v] = l.src->prog[sb][v].p; F.d[v] = c->prog[buf][v].p; }
-    F.s[5] = l.src->dp[sb].p; F.d[5] = c->dp[buf].p;
-    halo_link_kernel<<<(l.cnt + 255) / 256, 256, 0, c->stream>>>(F, l.d_src, l.d_rot, c->nint + size_t(l.off), l.cnt);
+    for (int v = 0; v < NVAR; ++v) F.d[v] = c->prog[buf][v].p;
+    F.d[5] = c->dp[buf].p;
+    if (l.src) {
+      const int sb = l.src->xbuf;
+      for (int v = 0; v < NVAR; ++v) F.s[v] = l.src->prog[sb][v].p;
+      F.s[5] = l.src->dp[sb].p;
+    } else {   // received by group_exchange_remote, fields in the internal variable order + DPRES
+      for (int v = 0; v < 6; ++v) F.s[v] = l.recvbuf + size_t(v) * l.cnt;
+    }
+    halo_link_kernel<<<(l.cnt + 255) / 256, 256, 0, c->stream>>>(F, l.src ? l.d_src : nullptr, l.d_rot, c->nint + size_t(l.off), l.cnt);
   }
 }
 
@@ -1283,6 +1296,42 @@ int fedg_advect3d_update(fedg_ctx* c, int nsteps) {
 }  // extern "C"
 
 // ---- several local meshes on one device (the reference's LOCAL_MESH_NUM > 1; cubed-sphere panels) ----------------
+namespace {
+// sendbuf[v][m] = field_v[idx[m]] for the six travelling fields (extract_bounddata for a panel edge owned by another rank)
+__global__ void pack_link_kernel(LinkFields F, const int* __restrict__ idx, double* __restrict__ buf, int cnt) {
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= cnt) return;
+  const int i = idx[m];
+#pragma unroll
+  for (int v = 0; v < 6; ++v) buf[size_t(v) * cnt + m] = F.s[v][i];
+}
+
+// Panel-edge data between the local meshes of different ranks: every mesh packs what its remote neighbours gather from its
+// stage-input state (prog[xbuf], dp[xbuf]), one NCCL group ships all messages of the rank; the receive buffers are scattered
+// (with the basis change) by fill_halo_links of the receiving mesh.  Runs on the group's single stream.
+int group_exchange_remote(fedg_ctx** ctxs, int n) {
+  std::vector<P2PMsg> sends, recvs;
+  fedg_ctx* lead = ctxs[0];
+  for (int i = 0; i < n; ++i) {
+    fedg_ctx* c = ctxs[i];
+    for (auto& m : c->outmsg) {
+      LinkFields F{};
+      for (int v = 0; v < NVAR; ++v) F.s[v] = c->prog[c->xbuf][v].p;
+      F.s[5] = c->dp[c->xbuf].p;
+      pack_link_kernel<<<(m.cnt + 255) / 256, 256, 0, lead->stream>>>(F, m.d_idx, m.sendbuf, m.cnt);
+      sends.push_back(P2PMsg{m.peer, m.msg_id, m.sendbuf, size_t(6) * m.cnt});
+    }
+    for (auto& l : c->link) if (l.recvbuf) recvs.push_back(P2PMsg{l.peer, l.msg_id, l.recvbuf, size_t(6) * l.cnt});
+  }
+  if (sends.empty() && recvs.empty()) return FEDG_OK;
+  std::string err;
+  int rc = comm_p2p_group(lead->comm, sends, recvs, lead->stream, err);
+  if (rc) return fail(rc, err);
+  return FEDG_OK;
+}
+}  // namespace
+
+
 extern "C" {
 
 int fedg_link_halo(fedg_ctx* c, int face, fedg_ctx* src, const int* src_index, const double* rot) {
@@ -1307,6 +1356,56 @@ int fedg_link_halo(fedg_ctx* c, int face, fedg_ctx* src, const int* src_index, c
     CUDA_TRY(cudaMemcpy(l.d_rot, rot, size_t(cnt) * 4 * sizeof(double), cudaMemcpyHostToDevice));
   }
   l.src = src; l.off = c->face_off[f]; l.cnt = cnt;
+  return FEDG_OK;
+}
+
+int fedg_link_halo_recv(fedg_ctx* c, int face, int peer_rank, int msg_id, const double* rot) {
+  if (!c || face < 1 || face > 6 || peer_rank < 0) return fail(FEDG_ERR_ARG, "bad argument");
+  if (peer_rank == c->my_rank) return fail(FEDG_ERR_ARG, "the source mesh is on this rank: use fedg_link_halo");
+  const int f = face - 1, cnt = c->face_off[f + 1] - c->face_off[f];
+  auto& l = c->link[f];
+  if (l.d_src) cudaFree(l.d_src);
+  if (l.d_rot) cudaFree(l.d_rot);
+  if (l.recvbuf) cudaFree(l.recvbuf);
+  l = fedg_ctx::HaloLink{};
+  CUDA_TRY(cudaMalloc(&l.recvbuf, size_t(std::max(cnt, 1)) * 6 * sizeof(double)));
+  if (rot) {
+    CUDA_TRY(cudaMalloc(&l.d_rot, size_t(std::max(cnt, 1)) * 4 * sizeof(double)));
+    CUDA_TRY(cudaMemcpy(l.d_rot, rot, size_t(cnt) * 4 * sizeof(double), cudaMemcpyHostToDevice));
+  }
+  l.off = c->face_off[f]; l.cnt = cnt; l.peer = peer_rank; l.msg_id = msg_id;
+  return FEDG_OK;
+}
+
+int fedg_link_halo_send(fedg_ctx* c, int peer_rank, int msg_id, const int* src_index, int n) {
+  if (!c || !src_index || n < 1 || peer_rank < 0) return fail(FEDG_ERR_ARG, "bad argument");
+  if (peer_rank == c->my_rank) return fail(FEDG_ERR_ARG, "the receiving mesh is on this rank: use fedg_link_halo");
+  std::vector<int> idx(n);
+  for (int m = 0; m < n; ++m) {
+    idx[m] = src_index[m] - 1;
+    if (idx[m] < 0 || size_t(idx[m]) >= c->nint) return fail(FEDG_ERR_ARG, "src_index out of range (1-based interior index of this mesh)");
+  }
+  fedg_ctx::OutMsg m{};
+  m.peer = peer_rank; m.msg_id = msg_id; m.cnt = n;
+  CUDA_TRY(cudaMalloc(&m.d_idx, size_t(n) * sizeof(int)));
+  CUDA_TRY(cudaMemcpy(m.d_idx, idx.data(), size_t(n) * sizeof(int), cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMalloc(&m.sendbuf, size_t(n) * 6 * sizeof(double)));
+  c->outmsg.push_back(m);
+  return FEDG_OK;
+}
+
+int fedg_group_exchange_halo(fedg_ctx** ctxs, int n, int apply_bc) {
+  if (!ctxs || n < 1) return fail(FEDG_ERR_ARG, "bad argument");
+  for (int i = 0; i < n; ++i) if (!ctxs[i] || !ctxs[i]->aux_ready) return fail(FEDG_ERR_STATE, "fedg_set_aux must be called on every mesh of the group");
+  fedg_ctx* lead = ctxs[0];
+  std::vector<cudaStream_t> saved(n);
+  for (int i = 0; i < n; ++i) { CUDA_TRY(cudaStreamSynchronize(ctxs[i]->stream)); saved[i] = ctxs[i]->stream; ctxs[i]->stream = lead->stream; }
+  struct Restore { fedg_ctx** c; std::vector<cudaStream_t>& s; int n; ~Restore() { for (int i = 0; i < n; ++i) c[i]->stream = s[i]; } } restore{ctxs, saved, n};
+  for (int i = 0; i < n; ++i) { ensure_dp(ctxs[i], ctxs[i]->cur); ctxs[i]->xbuf = ctxs[i]->cur; }
+  { int rc = group_exchange_remote(ctxs, n); if (rc) return rc; }
+  for (int i = 0; i < n; ++i) fill_halo(ctxs[i], ctxs[i]->cur, apply_bc != 0);
+  CUDA_TRY(cudaStreamSynchronize(lead->stream));
+  CUDA_TRY(cudaGetLastError());
   return FEDG_OK;
 }
 
@@ -1335,11 +1434,13 @@ int fedg_group_update(fedg_ctx** ctxs, int n, int nsteps) {
     for (int s = 0; s < ns; ++s) {
       if (lead->hevi) {
         for (int i = 0; i < n; ++i) { int rc = hevi_stage_vi(ctxs[i], s, nullptr, nullptr); if (rc) return rc; }     // cal_vi + StoreImplicit
+        { int rc = group_exchange_remote(ctxs, n); if (rc) return rc; }                                              // panel edges owned by other ranks
         for (int i = 0; i < n; ++i) { int rc = hevi_stage_ex(ctxs[i], s); if (rc) return rc; }                        // exchange + cal_tend_ex
         for (int i = 0; i < n; ++i) hevi_stage_combine(ctxs[i], s);                                                  // Advance
         launches += 4L * n;
       } else {
         for (int i = 0; i < n; ++i) heve_stage_prepare(ctxs[i], s);                                                  // pressure of every stage input
+        { int rc = group_exchange_remote(ctxs, n); if (rc) return rc; }
         for (int i = 0; i < n; ++i) { int rc = heve_stage(ctxs[i], s, nullptr, nullptr); if (rc) return rc; }        // exchange + tendency + Advance
         launches += 2L * n;
       }

@@ -183,6 +183,8 @@ void comm_destroy(CommState& cs);
 int comm_exchange_start(CommState& cs, double* const q[NVAR], double* dp, const int* d_vmapB, size_t nint, cudaStream_t compute,
                         std::string& err);
 void comm_exchange_wait(CommState& cs, cudaStream_t compute);
+struct P2PMsg { int peer; int msg_id; double* buf; size_t count; };
+int comm_p2p_group(CommState& cs, std::vector<P2PMsg>& sends, std::vector<P2PMsg>& recvs, cudaStream_t s, std::string& err);
 int comm_allreduce_sum(CommState& cs, double* d_inout, int n, cudaStream_t s, std::string& err);
 
 void upload_tables(const ElemTables& t, cudaStream_t s);

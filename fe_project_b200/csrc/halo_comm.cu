@@ -23,6 +23,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <vector>
 
 #include "fedg_internal.h"
 
@@ -183,6 +184,24 @@ int comm_exchange_start(CommState& cs, double* const q[NVAR], double* dp, const 
 void comm_exchange_wait(CommState& cs, cudaStream_t compute) {
   if (!cs.active || cs.nremote == 0) return;
   cudaStreamWaitEvent(compute, cs.ev_done, 0);
+}
+
+// Messages between local meshes on different ranks (cubed-sphere panel edges, fedg_link_halo_send / _recv): one NCCL group
+// on stream s.  Point-to-point operations carry no tags, so both sides post the messages of a rank pair in ascending msg_id
+// (the id of the receiving (panel, face), the same number on both ranks).
+int comm_p2p_group(CommState& cs, std::vector<P2PMsg>& sends, std::vector<P2PMsg>& recvs, cudaStream_t s, std::string& err) {
+  if (!cs.active) { err = "no communicator: call fedg_comm_init on the first mesh of the group"; return FEDG_ERR_STATE; }
+  auto by_id = [](const P2PMsg& a, const P2PMsg& b) { return a.peer != b.peer ? a.peer < b.peer : a.msg_id < b.msg_id; };
+  std::sort(sends.begin(), sends.end(), by_id);
+  std::sort(recvs.begin(), recvs.end(), by_id);
+  ncclComm_t comm = static_cast<ncclComm_t>(cs.comm);
+  ncclResult_t r = g_nccl.GroupStart();
+  for (size_t i = 0; i < sends.size() && r == ncclSuccess; ++i) r = g_nccl.Send(sends[i].buf, sends[i].count, ncclDouble, sends[i].peer, comm, s);
+  for (size_t i = 0; i < recvs.size() && r == ncclSuccess; ++i) r = g_nccl.Recv(recvs[i].buf, recvs[i].count, ncclDouble, recvs[i].peer, comm, s);
+  ncclResult_t r2 = g_nccl.GroupEnd();
+  if (r == ncclSuccess) r = r2;
+  if (r != ncclSuccess) { err = std::string("NCCL panel-edge exchange: ") + g_nccl.GetErrorString(r); return FEDG_ERR_COMM; }
+  return FEDG_OK;
 }
 
 // global sums for the monitors (MPI_Allreduce in file/scale_file_monitor_meshfield.F90:203-211)

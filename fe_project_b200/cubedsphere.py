@@ -162,25 +162,75 @@ class CubedSphere:
                         fields[U][ny_][sl] = rot[:, 1, 0] * sx + rot[:, 1, 1] * sy
 
 
+def panel_owner(nranks: int):
+    """Rank owning each of the six panels: contiguous blocks, as the reference distributes whole panels over 1, 2, 3 or 6
+    processes (`MeshCubedSphereDom2D_check_division_params`, FElib/src/mesh/scale_mesh_cubedspheredom2d.F90:193-247)."""
+    if nranks not in (1, 2, 3, 6):
+        raise ValueError("whole panels are distributed over 1, 2, 3 or 6 ranks (the reference's rule)")
+    per = 6 // nranks
+    return [P // per for P in range(6)]
+
+
+def exchange_plan(links, owner, rank):
+    """Panel-edge messages of `rank`: (local, recvs, sends).
+    local: (U, g, T) both on this rank -> fedg_link_halo;  recvs: (U, g, peer, msg_id) halo face g of own panel U filled by
+    rank peer -> fedg_link_halo_recv;  sends: (T, peer, msg_id, U, g) own panel T feeds (U, g) on rank peer ->
+    fedg_link_halo_send.  msg_id = 6 U + g identifies the linked face on both sides; NCCL matches the messages of a rank pair in
+    ascending msg_id (tests/test_multi_tile.py runs the plan over gloo)."""
+    local, recvs, sends = [], [], []
+    for U in range(6):
+        for g, (T, _src, _rot) in links[U].items():
+            mid = 6 * U + g
+            if owner[U] == rank and owner[T] == rank:
+                local.append((U, g, T))
+            elif owner[U] == rank:
+                recvs.append((U, g, owner[T], mid))
+            elif owner[T] == rank:
+                sends.append((T, owner[U], mid, U, g))
+    recvs.sort(key=lambda r: (r[2], r[3]))
+    sends.sort(key=lambda r: (r[1], r[2]))
+    return local, recvs, sends
+
+
 class GlobalSphereDriver:
     """The six local meshes of the global model on one GPU: one `AtmDynDGMDriver_nonhydro3d` per panel, linked halos,
     stage-synchronous stepping (`fedg_group_update`), i.e. what `AtmDynDGMDriver_nonhydro3d%Update` does with
     `LOCAL_MESH_NUM = 6` (fluid_dyn_solver/scale_atm_dyn_dgm_driver_nonhydro3d.F90:703-921)."""
 
-    def __init__(self, cs: CubedSphere, consts: dict, vel_bc=None):
+    def __init__(self, cs: CubedSphere, consts: dict, vel_bc=None, rank: int = 0, nranks: int = 1, bcast=None):
+        """rank / nranks: the panels are spread over the ranks (`panel_owner`), one GPU per rank; bcast broadcasts the NCCL
+        unique id (see AtmDynDGMDriver_nonhydro3d.init_comm).  `panels` holds the drivers of the OWN panels, `panel_ids` their
+        0-based panel numbers."""
         import ctypes as C
         from . import _lib
         from .dyncore import AtmDynDGMDriver_nonhydro3d
         self.cs, self.L = cs, _lib.load()
-        self.panels = [AtmDynDGMDriver_nonhydro3d(cs.elem, m, consts, vel_bc=vel_bc or dict(btm="SLIP", top="SLIP")) for m in cs.panels]
+        self.rank, self.nranks = rank, nranks
+        self.owner = panel_owner(nranks)
+        self.panel_ids = [P for P in range(6) if self.owner[P] == rank]
+        bc = vel_bc or dict(btm="SLIP", top="SLIP")
+        self.panels = [AtmDynDGMDriver_nonhydro3d(cs.elem, cs.panels[P], consts, vel_bc=bc, my_rank=rank) for P in self.panel_ids]
+        drv = dict(zip(self.panel_ids, self.panels))
         self._keep = []
-        for U, d in enumerate(self.panels):
-            for g, (T, src, rot) in cs.links[U].items():
-                idx = np.ascontiguousarray(src + 1, dtype=np.int32)
-                r = np.ascontiguousarray(rot.reshape(-1, 4), dtype=np.float64)        # [r00, r01, r10, r11] per node
-                self._keep += [idx, r]
-                _lib.check(self.L.fedg_link_halo(d.h, g + 1, self.panels[T].h, idx.ctypes.data_as(C.c_void_p), r.ctypes.data_as(C.c_void_p)))
-        self._h = (C.c_void_p * 6)(*[d.h for d in self.panels])
+        local, recvs, sends = exchange_plan(cs.links, self.owner, rank)
+        vp = C.c_void_p
+        for U, g, T in local:
+            _, src, rot = cs.links[U][g]
+            idx = np.ascontiguousarray(src + 1, dtype=np.int32)
+            r = np.ascontiguousarray(rot.reshape(-1, 4), dtype=np.float64)        # [r00, r01, r10, r11] per node
+            self._keep += [idx, r]
+            _lib.check(self.L.fedg_link_halo(drv[U].h, g + 1, drv[T].h, idx.ctypes.data_as(vp), r.ctypes.data_as(vp)))
+        for U, g, peer, mid in recvs:
+            r = np.ascontiguousarray(cs.links[U][g][2].reshape(-1, 4), dtype=np.float64)
+            self._keep.append(r)
+            _lib.check(self.L.fedg_link_halo_recv(drv[U].h, g + 1, peer, mid, r.ctypes.data_as(vp)))
+        for T, peer, mid, U, g in sends:
+            idx = np.ascontiguousarray(cs.links[U][g][1] + 1, dtype=np.int32)
+            self._keep.append(idx)
+            _lib.check(self.L.fedg_link_halo_send(drv[T].h, peer, mid, idx.ctypes.data_as(vp), idx.size))
+        if nranks > 1:
+            self.panels[0].init_comm(rank, nranks, bcast)      # the group's communicator lives on its first mesh
+        self._h = (C.c_void_p * len(self.panels))(*[d.h for d in self.panels])
 
     def Init(self, *a, **kw):
         for d in self.panels:
@@ -188,7 +238,12 @@ class GlobalSphereDriver:
 
     def Update(self, nsteps=1):
         from . import _lib
-        _lib.check(self.L.fedg_group_update(self._h, 6, int(nsteps)))
+        _lib.check(self.L.fedg_group_update(self._h, len(self.panels), int(nsteps)))
+
+    def exchange_halo(self, apply_bc=False):
+        """MeshFieldComm_Exchange of the prognostic variables of every own panel (remote panel edges included)."""
+        from . import _lib
+        _lib.check(self.L.fedg_group_exchange_halo(self._h, len(self.panels), int(bool(apply_bc))))
 
     def last_timing(self):
         return self.panels[0].last_timing()

@@ -214,6 +214,18 @@ int fedg_sponge_init(fedg_ctx* ctx, double sl_wdamp_tau, double sl_wdamp_height,
  * LonLat2CSVec(own panel, own face node) o CS2LonLatVec(source panel, source node)
  * (MeshFieldCommCubedSphereDom3D_exchange :226-420, common/scale_cubedsphere_coord_cnv.F90:150-236, 314-401). */
 int fedg_link_halo(fedg_ctx* ctx, int face, fedg_ctx* src, const int* src_index, const double* rot);
+/* The same link when the source mesh lives on ANOTHER rank (the reference ships panel edges between ranks with MPI_Isend / Irecv
+ * tagged 10*tileID+faceID, data/scale_meshfieldcomm_base.F90:870-884; here one NCCL send/recv pair per linked face inside one
+ * group per exchange).  The receiving rank calls fedg_link_halo_recv(ctx, face, peer_rank, msg_id, rot); the rank that owns
+ * the source mesh calls fedg_link_halo_send(src_ctx, peer_rank, msg_id, src_index, n) with the same src_index the local form
+ * takes.  msg_id is any number both sides agree on and that is unique per linked face (e.g. 6*panel + face of the receiver):
+ * NCCL matches the messages of a rank pair in ascending msg_id.  The communicator is the one of the FIRST mesh passed to
+ * fedg_group_update / fedg_group_exchange_halo (fedg_comm_init on it). */
+int fedg_link_halo_recv(fedg_ctx* ctx, int face, int peer_rank, int msg_id, const double* rot);
+int fedg_link_halo_send(fedg_ctx* src_ctx, int peer_rank, int msg_id, const int* src_index, int n);
+/* MeshFieldComm_Exchange of the prognostic variables (+ DPRES) over the local meshes of a rank: remote panel edges, then
+ * fedg_exchange_halo of every mesh. */
+int fedg_group_exchange_halo(fedg_ctx** ctxs, int n, int apply_bc);
 /* AtmDynDGMDriver_nonhydro3d%Update over the local meshes of a rank (the `do n = 1, LOCAL_MESH_NUM` loops of
  * driver_nonhydro3d.F90:703-921): every stage piece runs on all meshes before the next one starts, so that linked halos
  * see the neighbours' stage state.  HEVI equation sets. */

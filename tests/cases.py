@@ -213,11 +213,12 @@ class GlobalSphereCase:
         s.exchange_aux()
         return s
 
-    def make_driver(self):
+    def make_driver(self, rank=0, nranks=1, bcast=None):
+        """rank / nranks > 1: only the panels this rank owns get a device context (`g.panel_ids`)."""
         from fe_project_b200.cubedsphere import GlobalSphereDriver
-        g = GlobalSphereDriver(self.cs, self.consts, vel_bc=self.vel_bc)
+        g = GlobalSphereDriver(self.cs, self.consts, vel_bc=self.vel_bc, rank=rank, nranks=nranks, bcast=bcast)
         g.Init(self.eqs, self.tinteg, self.dt, MODALFILTER_FLAG=self.modalfilter, **MF)
-        for d, f in zip(g.panels, self.fields):
+        for d, f in zip(g.panels, [self.fields[P] for P in g.panel_ids]):
             d.set_aux(f["DENS_hyd"], f["PRES_hyd"])
             d.set_prog(*(f[k] for k in ("DDENS", "MOMX", "MOMY", "MOMZ", "DRHOT")))
         return g

@@ -106,3 +106,106 @@ def test_two_gpu_nccl_parity(mode):
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     assert "OK" in out.stdout
+
+
+# ------------------------------------------------------------------------------ cubed sphere: panels spread over ranks
+def _sphere_worker(rank, world, port, outq):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch
+    import torch.distributed as dist
+    from fe_project_b200.element import HexElement
+    from fe_project_b200.cubedsphere import CubedSphere, exchange_plan, panel_owner
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        e = HexElement(2)
+        cs = CubedSphere(e, 2, 2, 1.0e4, 6.37122e6)
+        owner = panel_owner(world)
+        names = ("DDENS", "MOMX", "MOMY")
+        rng = np.random.default_rng(7)                        # the same on every rank: the whole sphere, for the expectation
+        full = [{n: rng.standard_normal(m.NeA * e.Np) for n in names} for m in cs.panels]
+        mine = {P: {n: full[P][n].copy() for n in names} for P in range(6) if owner[P] == rank}
+        for P in mine:                                         # nothing of another rank's panels may be used below
+            for n in names:
+                mine[P][n][cs.panels[P].Ne * e.Np:] = np.nan
+        local, recvs, sends = exchange_plan(cs.links, owner, rank)
+
+        def put(U, g, vals, rot):
+            m = cs.panels[U]
+            nint, o = m.Ne * e.Np, m.halo_face_off[g]
+            sl = slice(nint + o, nint + o + vals["DDENS"].size)
+            mine[U]["DDENS"][sl] = vals["DDENS"]
+            mine[U]["MOMX"][sl] = rot[:, 0, 0] * vals["MOMX"] + rot[:, 0, 1] * vals["MOMY"]
+            mine[U]["MOMY"][sl] = rot[:, 1, 0] * vals["MOMX"] + rot[:, 1, 1] * vals["MOMY"]
+
+        for U, g, T in local:
+            _, src, rot = cs.links[U][g]
+            put(U, g, {n: mine[T][n][src] for n in names}, rot)
+        # tag-free matching as NCCL does it: per peer, messages in posting order; both sides post in ascending msg_id
+        reqs, keep, rb = [], [], []
+        for T, peer, mid, U, g in sends:
+            src = cs.links[U][g][1]
+            t = torch.from_numpy(np.concatenate([mine[T][n][src] for n in names]))
+            keep.append(t)
+            reqs.append(dist.isend(t, peer))
+        for U, g, peer, mid in recvs:
+            t = torch.empty(3 * cs.links[U][g][1].size, dtype=torch.float64)
+            rb.append((U, g, t))
+            reqs.append(dist.irecv(t, peer))
+        for r in reqs:
+            r.wait()
+        for U, g, t in rb:
+            a = t.numpy().reshape(3, -1)
+            put(U, g, dict(zip(names, a)), cs.links[U][g][2])
+        cs.exchange_numpy(full)
+        ok = True
+        for P in mine:
+            m = cs.panels[P]
+            lat = slice(m.Ne * e.Np, m.Ne * e.Np + m.halo_face_off[4])       # the four lateral halo faces
+            for n in names:
+                ok = ok and np.array_equal(mine[P][n][lat], full[P][n][lat])
+        # every linked face is covered exactly once
+        ok = ok and len(local) + len(recvs) == 4 * len(mine)
+        res = bool(ok)
+    except Exception as exc:  # noqa: BLE001
+        res = repr(exc)
+    outq.put((rank, res))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sphere_panel_exchange_plan_gloo(world):
+    """Panels spread over 2 / 3 ranks: local links + the send / receive plan (ascending msg_id per peer, no tags) reproduce the
+    single-process panel-edge exchange bit for bit."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31000 + (os.getpid() + 7 * world) % 2000
+    procs = [ctx.Process(target=_sphere_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=180) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    for rank, ok in res:
+        assert ok is True, (rank, ok)
+
+
+def test_panel_owner_follows_the_reference_rule():
+    from fe_project_b200.cubedsphere import panel_owner
+    assert panel_owner(1) == [0] * 6 and panel_owner(2) == [0, 0, 0, 1, 1, 1] and panel_owner(6) == list(range(6))
+    with pytest.raises(ValueError):
+        panel_owner(4)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["hevi", "heve"])
+def test_two_gpu_sphere_parity(mode):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs (run: gpurun --gpus 2 -- python -m pytest tests -m gpu -k sphere_parity)")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", str(29700 + os.getpid() % 300), os.path.join(ROOT, "tests", "mgpu_sphere_parity.py")] + (["heve"] if mode == "heve" else [])
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert "OK" in out.stdout
