@@ -201,32 +201,64 @@ def run_advect3d(args):
         cpu_baseline=cpu, finite=bool(np.isfinite(q2).all())))
 
 
-def run_sphere(args):
-    """configs[3]: global cubed sphere 6 x 32 x 32 x 12 elements p=7, GLOBALNONHYDRO3D_HEVI + IMEX_ARK324, the six panels as six
-    local meshes on one GPU (fedg_group_update); synthetic state: balanced solid-body rotation + perturbations."""
+def run_sphere(args, rank=0, world=1, local_rank=0):
+    """configs[3]: global cubed sphere 6 x 32 x 32 x 12 elements p=7, GLOBALNONHYDRO3D_HEVI + IMEX_ARK324, the six panels as local
+    meshes (fedg_group_update); synthetic state: balanced solid-body rotation + perturbations.  With --gpus 2 / 3 / 6 the panels
+    are spread over the ranks (whole panels, the reference's rule) and the panel edges between ranks travel over NCCL: the
+    sphere is fixed, so these lines are STRONG scaling."""
     import torch
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    bcast = None
+    if world > 1:
+        if world not in (2, 3, 6):
+            if rank == 0:
+                emit(dict(metric=METRIC, unavailable="whole panels spread over 1, 2, 3 or 6 ranks only (the reference rejects other counts, "
+                          "scale_mesh_cubedspheredom2d.F90:193-247); sub-panel tiles are not built yet", n_gpus=world))
+            return
+        import torch.distributed as dist_
+        dist = dist_
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+        def bcast(raw):
+            obj = [raw]
+            dist.broadcast_object_list(obj, src=0)
+            return obj[0]
     from cases import GlobalSphereCase
     from fe_project_b200.dyncore import PROG_NAMES
     ne, nez = (args.nex if args.nex != WORKLOAD["NeX"] else 32), (args.nez if args.nez != WORKLOAD["NeZ"] else 12)
     case = GlobalSphereCase(p=7, Ne=ne, NeZ=nez, dt=5.0 * 32 / ne, tinteg="IMEX_ARK324", modalfilter=True)
-    g = case.make_driver()
+    g = case.make_driver(rank=rank, nranks=world, bcast=bcast)
     W, K = max(3, args.warmup), args.steps
     g.Update(W)
-    sampler = ClockSampler(0); sampler.start(); time.sleep(0.12)
+    torch.cuda.synchronize()
+    if dist:
+        dist.barrier()
+    sampler = ClockSampler(local_rank); sampler.start(); time.sleep(0.12)
     g.Update(K)
+    torch.cuda.synchronize()
     tm = g.last_timing()
     clocks = sampler.stop()
+    ms_total = tm["ms_total"]
+    if dist:
+        dist.barrier()
+        t = torch.tensor([ms_total], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
     Np = case.elem.Np
     nel = sum(m.Ne for m in case.cs.panels)
     dof = 5 * Np * nel
-    value = dof * K / (tm["ms_total"] * 1e-3)
+    value = dof * K / (ms_total * 1e-3)
+    own = [case.cs.panels[P] for P in g.panel_ids]
     states = [d.get_prog() for d in g.panels]
-    finite = all(np.isfinite(st[k][:Np * m.Ne]).all() for st, m in zip(states, case.cs.panels) for k in PROG_NAMES)
-    # e2e: host state of the six panels in, one step, host state out
-    t0 = time.perf_counter()
+    finite = all(np.isfinite(st[k][:Np * m.Ne]).all() for st, m in zip(states, own) for k in PROG_NAMES)
+    # e2e: host state of the own panels in, one step, host state out
     ne2e = 3
+    if dist:
+        dist.barrier()
+    t0 = time.perf_counter()
     for _ in range(ne2e):
         for d, st in zip(g.panels, states):
             d.set_prog(*(st[k] for k in PROG_NAMES))
@@ -234,20 +266,26 @@ def run_sphere(args):
         states = [d.get_prog() for d in g.panels]
     t_e2e = (time.perf_counter() - t0) / ne2e
     nbytes = sum(5 * d.n_field * 8 for d in g.panels)
-    nstage = 4
-    # vertical-implicit column solve dominates: same accounting as the regional HEVI line (15.1 kflop per column-element)
-    ms_vi = None
-    emit(dict(
-        metric=METRIC, value=value, unit=UNIT, n_gpus=1, steps=K, warmup=W, ms_per_step=tm["ms_total"] / K, higher_is_better=True,
-        scaling="weak", vs_baseline=None, dtype="f64", data="synthetic",
-        config=dict(workload=f"atm_nonhydro3d global cubed sphere 6x{ne}x{ne}x{nez} elements p=7, GLOBALNONHYDRO3D_HEVI, IMEX_ARK324, "
-                             f"dt={case.dt}, modal filter on, six local meshes on one GPU with linked panel-edge halos",
-                    dof=dof, l2_policy="inputs larger than L2 (50 MB per field and panel)"),
-        clocks=clocks, e2e=dict(value=dof / t_e2e, unit=UNIT, h2d_bytes_per_step=nbytes, d2h_bytes_per_step=nbytes, steps_per_call=1),
-        gpu_launches=tm["launches"],
-        roofline=dict(bound="fp64", achieved=None, peak=34.07, unit="TFLOP/s", frac=None, traffic=None,
-                      kernel="vi_column_kernel (see the global_panel line for its per-launch figures)", ms_per_launch=ms_vi),
-        cpu_baseline=None, finite=bool(finite)))
+    if dist:
+        t = torch.tensor([t_e2e, float(nbytes), 0.0 if finite else 1.0], device="cuda", dtype=torch.float64)
+        tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        t_e2e, nbytes, finite = float(tmax[0].item()), int(tsum[1].item()), tmax[2].item() == 0.0
+    if rank == 0:
+        emit(dict(
+            metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=K, warmup=W, ms_per_step=ms_total / K, higher_is_better=True,
+            scaling=("weak" if world == 1 else "strong"), vs_baseline=None, dtype="f64", data="synthetic",
+            config=dict(workload=f"atm_nonhydro3d global cubed sphere 6x{ne}x{ne}x{nez} elements p=7, GLOBALNONHYDRO3D_HEVI, IMEX_ARK324, "
+                                 f"dt={case.dt}, modal filter on, {6 // world} panel(s) per GPU as local meshes with linked panel-edge halos"
+                                 + (", panel edges between ranks over NCCL" if world > 1 else ""),
+                        dof=dof, l2_policy="inputs larger than L2 (50 MB per field and panel)"),
+            clocks=clocks, e2e=dict(value=dof / t_e2e, unit=UNIT, h2d_bytes_per_step=nbytes, d2h_bytes_per_step=nbytes, steps_per_call=1),
+            gpu_launches=tm["launches"],
+            roofline=dict(bound="fp64", achieved=None, peak=34.07, unit="TFLOP/s", frac=None, traffic=None,
+                          kernel="vi_column_kernel (see the global_panel line for its per-launch figures)", ms_per_launch=None),
+            cpu_baseline=None, finite=bool(finite)))
+    if dist:
+        dist.destroy_process_group()
 
 
 def main():
@@ -275,7 +313,7 @@ def main():
         run_advect3d(args)
         return
     if args.workload == "global_sphere":
-        run_sphere(args)
+        run_sphere(args, rank, world, local_rank)
         return
 
     import torch
@@ -401,7 +439,7 @@ def main():
                                        "roofline uses the unspecialised 232 B/node/stage"),
             clocks=clocks, e2e=e2e, gpu_launches=tm["launches"],
             roofline=(dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak, traffic=traffic,
-                           kernel="stage_p7_kernel<flat,dry,HEVE> (DMMA contractions, TMA-staged inputs)", ms_per_launch=ms_stage,
+                           kernel="stage_p7_kernel<flat,dry,HEVE> (DMMA contractions, TMA-staged inputs and z-face neighbours)", ms_per_launch=ms_stage,
                            algorithmic_bytes_per_launch=alg_bytes, peak_source=peak_src) if not hevi else
                       # vertical-implicit column solve: FP64 bound.  Algorithmic flops of the reference algorithm per
                       # column-element: 24x24 LU 9.2 kflop + 4 RHS substitutions 4.6 kflop + coupling

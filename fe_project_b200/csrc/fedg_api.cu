@@ -712,6 +712,7 @@ void fill_vi_params(fedg_ctx* c, VIParams& V, int in, int out, int i0, int stage
   V.rtot = c->rtot.p; V.cvtot = c->cvtot.p; V.cptot = c->cptot.p;
   V.escale = c->escale.p; V.fscale = c->fscale.p; V.tab = c->d_tab; V.scratch = c->vi_scratch.p;
   V.c = c->c; V.impl_fac = impl_fac; V.Ne = c->Ne; V.Ne2D = c->Ne2D; V.NeZ = c->NeZ;
+  { const char* e = getenv("FEDG_EXACT_POW"); V.exact_pow = (e && e[0] == '1') ? 1 : 0; }
 }
 
 // HEVI / IMEX step (driver_nonhydro3d.F90:703-763 + 769-921): per stage  cal_vi -> StoreImplicit -> halo + BC ->

@@ -104,6 +104,7 @@ struct VIParams {
   PhysConst c;
   double impl_fac;
   int Ne, Ne2D, NeZ;
+  int exact_pow;              // pow() instead of exp(e log x) for the equation of state
 };
 constexpr int MAXTERM = 20;   // 2 * stages of the largest IMEX scheme supported
 struct LinCombParams {

@@ -296,6 +296,8 @@ __global__ void __launch_bounds__(256, 3) stage_p7_kernel(const __grid_constant_
   const double bx0 = E11 * Dg0, bx1 = E11 * Dg1, ay0 = E22 * Dg0, ay1 = E22 * Dg1;
   const int ownP = PLS * g + 2 * t, ownZ = 2 * t + 8 * g + KS_Z * w;
   double2 drn = make_double2(0.0, 0.0);   // DRHOT of the new state, for its pressure
+  // horizontal gradient of the background pressure: fetched one variable ahead of its use (MOMX, MOMY come last in `order`)
+  double2 phx_c = make_double2(0.0, 0.0), phy_c = make_double2(0.0, 0.0);
   // background of the own nodes for the pressure of the new state: issued here, consumed after the loop
   double2 ph_pre = make_double2(0.0, 0.0), th_pre = make_double2(0.0, 0.0);
   if (!tend_mode) { ph_pre = *reinterpret_cast<const double2*>(P.pres_hyd + gn); th_pre = *reinterpret_cast<const double2*>(P.therm_hyd + gn); }
@@ -315,12 +317,15 @@ __global__ void __launch_bounds__(256, 3) stage_p7_kernel(const __grid_constant_
       else { Fx = make_double2(fx0.x * vv.x, fx0.y * vv.y); Fy = make_double2(fy0.x * vv.x + GP.x, fy0.y * vv.y + GP.y); }
       q = my;
     }
-    // RK operands of this variable: issued here so that their latency is covered by the contractions below (they used to be
-    // loaded right before use: 12 % of the stall samples were long-scoreboard waits at the update)
     double2 q0v = make_double2(0.0, 0.0), vtv = make_double2(0.0, 0.0);
     if (!tend_mode) {
       if (P.rk.use_q0) q0v = *reinterpret_cast<const double2*>(P.q0[v] + gn);
       if (P.rk.add_vt || (P.rk.vt_update && !P.rk.vt_init)) vtv = *reinterpret_cast<const double2*>(P.vt[v] + gn);
+    }
+    if (P.has_phyd) {
+      if (GLOBAL) { if (iv == 2) { phx_c = *reinterpret_cast<const double2*>(P.dphydx + gn); phy_c = *reinterpret_cast<const double2*>(P.dphydy + gn); } }
+      else if (iv == 2) phx_c = *reinterpret_cast<const double2*>(P.dphydx + gn);
+      else if (iv == 3) phy_c = *reinterpret_cast<const double2*>(P.dphydy + gn);
     }
     double* sPy = sPl + (iv & 1) * NP * PLS;   // alternate planes: the reads of variable iv - 2 finished before the __syncwarp of iv - 1
     if (P.do_filter) __syncwarp();              // ... but the filter of the previous variable read the other plane
@@ -352,7 +357,7 @@ __global__ void __launch_bounds__(256, 3) stage_p7_kernel(const __grid_constant_
     else if (GLOBAL && (v == V_MOMX || v == V_MOMY)) {
       // pressure-gradient of the background, metric (Christoffel) and Coriolis terms, globalnonhydro3d_rhot_hevi.F90:535-566
       double2 phx = make_double2(0.0, 0.0), phy = make_double2(0.0, 0.0);
-      if (P.has_phyd) { phx = *reinterpret_cast<const double2*>(P.dphydx + gn); phy = *reinterpret_cast<const double2*>(P.dphydy + gn); }
+      phx = phx_c; phy = phy_c;
       const double sg = (P.panel == 6) ? -1.0 : 1.0;
       const bool p14 = P.panel <= 4;
       double r[2];
@@ -373,11 +378,11 @@ __global__ void __launch_bounds__(256, 3) stage_p7_kernel(const __grid_constant_
       tend = make_double2(r[0] - div.x, r[1] - div.y);
     } else if (v == V_MOMX) {
       double2 ph = make_double2(0.0, 0.0);
-      if (P.has_phyd) ph = *reinterpret_cast<const double2*>(P.dphydx + gn);
+      ph = phx_c;
       tend = make_double2((-ph.x + cor.x * my.x) - div.x, (-ph.y + cor.y * my.y) - div.y);
     } else if (v == V_MOMY) {
       double2 ph = make_double2(0.0, 0.0);
-      if (P.has_phyd) ph = *reinterpret_cast<const double2*>(P.dphydy + gn);
+      ph = phy_c;
       tend = make_double2((-ph.x - cor.x * mx.x) - div.x, (-ph.y - cor.y * mx.y) - div.y);
     } else tend = make_double2(-div.x, -div.y);
 

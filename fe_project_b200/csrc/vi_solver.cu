@@ -47,6 +47,13 @@ __device__ __forceinline__ RawQ raw_load(const VIParams& P, size_t n) {
   if (MOIST) { r.R = P.rtot[n]; r.cp = P.cptot[n]; r.cv = P.cvtot[n]; }
   return r;
 }
+// x^e as exp(e log x) for x = Rtot RHOT / P00 in [0.25, 2] (see eos_pres_fast in stage_common.cuh: <= 3.5e-16 relative, 64 % of
+// the instructions of pow()); pow() outside the range or with FEDG_EXACT_POW=1
+__device__ __forceinline__ double vi_pow(double x, double e, int exact) {
+  if (!exact && x > 0.25 && x < 2.0) return exp(e * log(x));
+  return pow(x, e);
+}
+
 template <bool MOIST>
 __device__ __forceinline__ NodeQ node_q(const VIParams& P, const RawQ& r) {
   NodeQ q;
@@ -56,13 +63,13 @@ __device__ __forceinline__ NodeQ node_q(const VIParams& P, const RawQ& r) {
   q.dens = r.dh + q.rho0;
   q.rhot = r.rh + q.th0;
   q.pot = q.rhot / q.dens;
-  const double ptot = P.c.PRES00 * pow(R * P.c.rP0 * q.rhot, gm);
+  const double ptot = P.c.PRES00 * vi_pow(R * P.c.rP0 * q.rhot, gm, P.exact_pow);
   q.dpres_vol = ptot - r.ph;
   q.wt = q.w0 / q.dens;
   q.dpd = gm * ptot / q.rhot;
   const double rdens0 = 1.0 / q.dens;
   q.a = fabs(q.w0 * rdens0) + sqrt(P.c.gamm * ptot * rdens0);
-  q.dpf = P.c.PRES00 * pow(R * P.c.rP0 * q.dens * q.pot, gm) - r.ph;
+  q.dpf = P.c.PRES00 * vi_pow(R * P.c.rP0 * q.dens * q.pot, gm, P.exact_pow) - r.ph;
   return q;
 }
 
@@ -571,7 +578,7 @@ __global__ void __launch_bounds__(VI_THREADS, MINB) vi_column_kernel(const __gri
     }
     P.qout[V_DDENS][n] = qr; P.qout[V_MOMZ][n] = qw; P.qout[V_DRHOT][n] = qt; P.qout[V_MOMX][n] = qu; P.qout[V_MOMY][n] = qv;
     // DPRES of the updated state for the explicit part of this stage (DRHOT2PRES, nonhydro3d_common.F90:467-474)
-    P.dpout[n] = P.c.PRES00 * pow(in.R * P.c.rP0 * (in.th + qt), in.gm) - in.ph;
+    P.dpout[n] = P.c.PRES00 * vi_pow(in.R * P.c.rP0 * (in.th + qt), in.gm, P.exact_pow) - in.ph;
   }
 }
 

@@ -17,6 +17,9 @@ case = DensityCurrentCase(p=7, NeX=32, NeY=32, NeZ=16, dom=W["dom"], dt=(2 * W["
                           tinteg=("IMEX_ARK324" if hevi else W["tinteg"]), modalfilter=True,
                           eqs=("NONHYDRO3D_HEVI" if hevi else "NONHYDRO3D_HEVE"))
 d = case.make_driver(None)
+if os.environ.get("AB_PHYD", "1") == "1":   # as bench.py does on one tile: DPhydDx / DPhydDy registered (two more fields per stage)
+    from fe_project_b200.setup_aux import calc_phyd_hgrad
+    d.set_phyd_hgrad(*calc_phyd_hgrad(case.elem, case.mesh, case.fields["PRES_hyd"]))
 nstage = rk_tables(case.tinteg)["nstage"]
 K = int(os.environ.get("AB_STEPS", "40"))
 variants = []
