@@ -687,6 +687,7 @@ void fill_stage_params(fedg_ctx* c, StageParams& P, int in, int out, int q0) {
   P.has_phyt = c->has_phyt;
   P.sponge = c->has_sponge ? c->sponge.p : nullptr; P.sponge_h = c->sponge_h;
   { const char* e = getenv("FEDG_EXACT_POW"); P.exact_pow = (e && e[0] == '1') ? 1 : 0; }   // stage_p7: pow() instead of exp(e log x)
+  { const char* e = getenv("FEDG_P7_L2PF"); P.l2_prefetch = (e && e[0] == '0') ? 0 : 1; }
   { const char* e = getenv("FEDG_P7_ZEXT"); P.zface_contig = (!(e && e[0] == '0') && c->zface_contig) ? 1 : 0; }   // A/B knob
 }
 

@@ -75,6 +75,7 @@ struct StageParams {
   // sponge layer: Rayleigh damping coefficient per node (Np,Ne), NULL = off; sponge_h = 1 damps MOMX / MOMY too
   const double* sponge;
   double sponge_h;
+  int l2_prefetch;       // stage_p7: L2 prefetch of the late-use fields at block start (A/B knob FEDG_P7_L2PF)
   int zface_contig;      // stage_p7: exterior z-face values are 64 consecutive nodes per face (bulk copies instead of gathers)
 };
 

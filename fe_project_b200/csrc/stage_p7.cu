@@ -57,7 +57,9 @@ __device__ __forceinline__ const double* stage_field(const StageParams& P, int l
   }
 }
 
-template <bool TERRAIN, bool MOIST, bool HEVI, bool GLOBAL>
+// PLAIN: no sponge layer, no physics tendencies, and the output the step of the equation set takes (HEVE: the new state,
+// HEVI: the tendency) -- the dynamics-only step; the other branches and their code (a pow() per node among it) are compiled out.
+template <bool TERRAIN, bool MOIST, bool HEVI, bool GLOBAL, bool PLAIN>
 __global__ void __launch_bounds__(256, 3) stage_p7_kernel(const __grid_constant__ StageParams P) {
   using namespace p7;
   const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
@@ -103,6 +105,21 @@ __global__ void __launch_bounds__(256, 3) stage_p7_kernel(const __grid_constant_
       for (int l = 0; l < 9; ++l) {
         tma_load_1d(sExt + l * N2, stage_field(P, l) + ib4, FBYTES, sBar);
         tma_load_1d(sExt + (9 + l) * N2, stage_field(P, l) + ib5, FBYTES, sBar);
+      }
+    }
+    // fields read per node late in the kernel (background pressure gradient, RK operands): pull the element's 4 KB of each
+    // into L2 now, so that the loads in phase 5 find them there instead of paying a DRAM round trip per variable
+    if (P.l2_prefetch) {
+      if (P.has_phyd) { tma_prefetch_l2(P.dphydx + eb, BYTES); tma_prefetch_l2(P.dphydy + eb, BYTES); }
+      if (PLAIN ? !HEVI : (P.tend_out[0] == nullptr)) {
+        if (P.rk.use_q0) {
+#pragma unroll
+          for (int v = 0; v < NVAR; ++v) tma_prefetch_l2(P.q0[v] + eb, BYTES);
+        }
+        if (P.rk.add_vt || (P.rk.vt_update && !P.rk.vt_init)) {
+#pragma unroll
+          for (int v = 0; v < NVAR; ++v) tma_prefetch_l2(P.vt[v] + eb, BYTES);
+        }
       }
     }
   }
@@ -292,7 +309,7 @@ __global__ void __launch_bounds__(256, 3) stage_p7_kernel(const __grid_constant_
   __syncthreads();
 
   // ---- phase 5: per variable x/y-derivative + lateral lift on the own plane, tendency, RK update, filter passes x/y
-  const bool tend_mode = P.tend_out[0] != nullptr;
+  const bool tend_mode = PLAIN ? HEVI : (P.tend_out[0] != nullptr);   // PLAIN: HEVI steps take the tendency, HEVE steps the new state
   const double bx0 = E11 * Dg0, bx1 = E11 * Dg1, ay0 = E22 * Dg0, ay1 = E22 * Dg1;
   const int ownP = PLS * g + 2 * t, ownZ = 2 * t + 8 * g + KS_Z * w;
   double2 drn = make_double2(0.0, 0.0);   // DRHOT of the new state, for its pressure
@@ -386,12 +403,12 @@ __global__ void __launch_bounds__(256, 3) stage_p7_kernel(const __grid_constant_
       tend = make_double2((-ph.x - cor.x * mx.x) - div.x, (-ph.y - cor.y * mx.y) - div.y);
     } else tend = make_double2(-div.x, -div.y);
 
-    if (P.sponge && (v == V_MOMX || v == V_MOMY || v == V_MOMZ)) {   // AtmDynSpongeLayer%AddTend (spongelayer.F90:129-185)
+    if (!PLAIN && P.sponge && (v == V_MOMX || v == V_MOMY || v == V_MOMZ)) {   // AtmDynSpongeLayer%AddTend (spongelayer.F90:129-185)
       const double2 wc = *reinterpret_cast<const double2*>(P.sponge + gn);
       const double sf = (v == V_MOMZ) ? 1.0 : P.sponge_h;
       tend.x -= sf * wc.x * q.x; tend.y -= sf * wc.y * q.y;
     }
-    if (P.has_phyt) {   // add_phy_tend (driver_nonhydro3d.F90:1098-1178), non-conservative form: RHOT_tp + RHOH_p / (CP * EXNER)
+    if (!PLAIN && P.has_phyt) {   // add_phy_tend (driver_nonhydro3d.F90:1098-1178), non-conservative form: RHOT_tp + RHOH_p / (CP * EXNER)
       const int pv = (v == V_DDENS) ? 0 : (v == V_MOMX) ? 1 : (v == V_MOMY) ? 2 : (v == V_MOMZ) ? 3 : 4;
       const double2 tp = *reinterpret_cast<const double2*>(P.phyt[pv] + gn);
       tend.x += tp.x; tend.y += tp.y;
@@ -482,14 +499,19 @@ __global__ void __launch_bounds__(256, 3) stage_p7_kernel(const __grid_constant_
 void launch_stage_p7(const StageParams& p, bool terrain, bool moist, bool hevi, cudaStream_t s) {
   const size_t shmem = p7::SMEM_BYTES;
   dim3 grid(p.elem_list ? p.nelem : p.Ne), block(256);
-#define FEDG_LAUNCH(T, M, H, G)                                                                                  \
-  do {                                                                                                           \
-    static bool attr_set = false;                                                                                \
-    if (!attr_set) {                                                                                             \
-      cudaFuncSetAttribute(stage_p7_kernel<T, M, H, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem); \
-      attr_set = true;                                                                                           \
-    }                                                                                                            \
-    stage_p7_kernel<T, M, H, G><<<grid, block, shmem, s>>>(p);                                                   \
+  const bool plain = !p.sponge && !p.has_phyt && ((p.tend_out[0] != nullptr) == hevi);
+#define FEDG_LAUNCH2(T, M, H, G, PL)                                                                                  \
+  do {                                                                                                                \
+    static bool attr_set = false;                                                                                     \
+    if (!attr_set) {                                                                                                  \
+      cudaFuncSetAttribute(stage_p7_kernel<T, M, H, G, PL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem); \
+      attr_set = true;                                                                                                \
+    }                                                                                                                 \
+    stage_p7_kernel<T, M, H, G, PL><<<grid, block, shmem, s>>>(p);                                                    \
+  } while (0)
+#define FEDG_LAUNCH(T, M, H, G)                                                \
+  do {                                                                         \
+    if (plain) FEDG_LAUNCH2(T, M, H, G, true); else FEDG_LAUNCH2(T, M, H, G, false); \
   } while (0)
   if (p.is_global) {   // GLOBALNONHYDRO3D_HEVI / _HEVE (flat, shallow atmosphere: enforced at fedg_create / fedg_dyn_init)
     if (hevi) { if (moist) FEDG_LAUNCH(false, true, true, true); else FEDG_LAUNCH(false, false, true, true); }
@@ -502,6 +524,7 @@ void launch_stage_p7(const StageParams& p, bool terrain, bool moist, bool hevi, 
     else { if (moist) FEDG_LAUNCH(false, true, false, false); else FEDG_LAUNCH(false, false, false, false); }
   }
 #undef FEDG_LAUNCH
+#undef FEDG_LAUNCH2
 }
 
 }  // namespace fedg
