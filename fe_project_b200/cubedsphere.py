@@ -100,53 +100,85 @@ def revert_hori(idx, np1, nv, nex, nez):
 
 
 class CubedSphere:
-    """Six panel tiles + the halo links between them."""
+    """The panel tiles + the halo links between them.  ntile = k: every panel is cut into k x k tiles (24 local meshes for
+    k = 2, the layout that spreads over 4 or 8 GPUs); `panels` lists the tiles panel by panel, tile (ti, tj) of panel P at
+    index P k^2 + tj k + ti, and `links[U][g] = (T, src, rot)` says that the halo of face g of tile U is node-wise the interior
+    nodes `src` of tile T, with (MOMX, MOMY) multiplied by `rot` (None inside a panel: same basis)."""
 
-    def __init__(self, elem, Ne, NeZ, ztop, RPlanet, FZ=None):
-        self.elem, self.Ne_h, self.NeZ, self.R = elem, Ne, NeZ, RPlanet
-        self.panels = [LocalMeshCubedSpherePanel(elem, pid, Ne, Ne, NeZ, ztop, RPlanet, FZ=FZ) for pid in range(1, 7)]
+    def __init__(self, elem, Ne, NeZ, ztop, RPlanet, FZ=None, ntile=1):
+        """Ne: elements per tile edge (the panel has ntile * Ne)."""
+        self.elem, self.Ne_h, self.NeZ, self.R, self.ntile = elem, Ne, NeZ, RPlanet, int(ntile)
+        k = self.ntile
+        self.panels = [LocalMeshCubedSpherePanel(elem, pid, Ne, Ne, NeZ, ztop, RPlanet, FZ=FZ, sub=(k, ti, tj))
+                       for pid in range(1, 7) for tj in range(k) for ti in range(k)]
+        self.panel_of = [P for P in range(6) for _ in range(k * k)]
         self.links = self._build_links()
+
+    def tile_index(self, P, ti, tj):
+        return P * self.ntile ** 2 + tj * self.ntile + ti
 
     def _face_nodes(self, mesh, f):
         """0-based flat interior indices of the boundary nodes of tile face f (0-based) in halo order."""
         o, n = mesh.halo_face_off[f], mesh.halo_face_size[f]
         return mesh.VMapB[o:o + n]
 
+    @staticmethod
+    def _edge_tile(k, f, e):
+        """(ti, tj) of the e-th tile along panel face f (faces: 0 south, 1 east, 2 north, 3 west)."""
+        return ((e, 0), (k - 1, e), (e, k - 1), (0, e))[f]
+
     def _build_links(self):
-        """links[U][g] = (T, src_index (0-based into T's fields), rot (n,2,2)) for the four lateral faces g of panel U."""
+        """Panel edges follow `panel_connectivity`; a reverted edge (negative face id) reverts the order of the tiles along the
+        edge as well as the nodes inside each tile (`revert_hori`).  Inside a panel the neighbour tile's opposite face feeds
+        the halo in the same order (the tile graph of MeshCubeDom3D)."""
         pc, fc = panel_connectivity()
         e = self.elem
         npts, nv = e.np1, e.np1
-        links = [dict() for _ in range(6)]
-        for T in range(6):
-            mT = self.panels[T]
+        k = self.ntile
+        links = [dict() for _ in self.panels]
+        # tile faces inside a panel: (dx, dy) of the neighbour and its opposite face
+        inner = ((0, -1, 2), (1, 0, 3), (0, 1, 0), (-1, 0, 1))
+        for P in range(6):
+            for tj in range(k):
+                for ti in range(k):
+                    U = self.tile_index(P, ti, tj)
+                    for g, (dx, dy, fo) in enumerate(inner):
+                        qi, qj = ti + dx, tj + dy
+                        if 0 <= qi < k and 0 <= qj < k:
+                            T = self.tile_index(P, qi, qj)
+                            links[U][g] = (T, self._face_nodes(self.panels[T], fo).copy(), None)
+        for Tp in range(6):
             for f in range(4):
-                U = pc[f, T] - 1
-                g = abs(fc[f, T]) - 1
-                src = self._face_nodes(mT, f)
-                if fc[f, T] < 0:
-                    src = revert_hori(src, npts, nv, self.Ne_h, self.NeZ)
-                mU = self.panels[U]
-                own = self._face_nodes(mU, g)
-                assert own.size == src.size
-                # positions: horizontal coordinates of the 3D nodes
-                aT, bT = mT.pos_en[0].reshape(-1)[src], mT.pos_en[1].reshape(-1)[src]
-                aU, bU = mU.pos_en[0].reshape(-1)[own], mU.pos_en[1].reshape(-1)[own]
-                rot = np.empty((own.size, 2, 2))
-                for c, (va, vb) in enumerate(((1.0, 0.0), (0.0, 1.0))):
-                    vl, vt = cs2lonlat_vec(T + 1, aT, bT, np.full(own.size, va), np.full(own.size, vb), self.R)
-                    ua, ub = lonlat2cs_vec(U + 1, aU, bU, vl, vt, self.R)
-                    rot[:, 0, c], rot[:, 1, c] = ua, ub
-                assert g not in links[U], "two faces feed the same halo face"
-                links[U][g] = (T, src.copy(), rot)
-        for U in range(6):
+                Up = pc[f, Tp] - 1
+                g = abs(fc[f, Tp]) - 1
+                rev = fc[f, Tp] < 0
+                for et in range(k):
+                    T = self.tile_index(Tp, *self._edge_tile(k, f, et))
+                    U = self.tile_index(Up, *self._edge_tile(k, g, k - 1 - et if rev else et))
+                    mT, mU = self.panels[T], self.panels[U]
+                    src = self._face_nodes(mT, f)
+                    if rev:
+                        src = revert_hori(src, npts, nv, self.Ne_h, self.NeZ)
+                    own = self._face_nodes(mU, g)
+                    assert own.size == src.size
+                    # positions: horizontal coordinates of the 3D nodes
+                    aT, bT = mT.pos_en[0].reshape(-1)[src], mT.pos_en[1].reshape(-1)[src]
+                    aU, bU = mU.pos_en[0].reshape(-1)[own], mU.pos_en[1].reshape(-1)[own]
+                    rot = np.empty((own.size, 2, 2))
+                    for c, (va, vb) in enumerate(((1.0, 0.0), (0.0, 1.0))):
+                        vl, vt = cs2lonlat_vec(Tp + 1, aT, bT, np.full(own.size, va), np.full(own.size, vb), self.R)
+                        ua, ub = lonlat2cs_vec(Up + 1, aU, bU, vl, vt, self.R)
+                        rot[:, 0, c], rot[:, 1, c] = ua, ub
+                    assert g not in links[U], "two faces feed the same halo face"
+                    links[U][g] = (T, src.copy(), rot)
+        for U in range(len(self.panels)):
             assert sorted(links[U]) == [0, 1, 2, 3]
         return links
 
     def exchange_numpy(self, fields, vector_pairs=(("MOMX", "MOMY"),)):
         """fields: list of 6 dicts name -> (NeA*Np,) arrays.  Fills the lateral halos (reference semantics) in place."""
         vec = {n for pr in vector_pairs for n in pr}
-        for U in range(6):
+        for U in range(len(self.panels)):
             mU = self.panels[U]
             nint = mU.Ne * self.elem.Np
             for g, (T, src, rot) in self.links[U].items():
@@ -158,17 +190,25 @@ class CubedSphere:
                 for nx_, ny_ in vector_pairs:
                     if nx_ in fields[U]:
                         sx, sy = fields[T][nx_][src], fields[T][ny_][src]
-                        fields[U][nx_][sl] = rot[:, 0, 0] * sx + rot[:, 0, 1] * sy
-                        fields[U][ny_][sl] = rot[:, 1, 0] * sx + rot[:, 1, 1] * sy
+                        if rot is None:
+                            fields[U][nx_][sl], fields[U][ny_][sl] = sx, sy
+                        else:
+                            fields[U][nx_][sl] = rot[:, 0, 0] * sx + rot[:, 0, 1] * sy
+                            fields[U][ny_][sl] = rot[:, 1, 0] * sx + rot[:, 1, 1] * sy
 
 
-def panel_owner(nranks: int):
-    """Rank owning each of the six panels: contiguous blocks, as the reference distributes whole panels over 1, 2, 3 or 6
-    processes (`MeshCubedSphereDom2D_check_division_params`, FElib/src/mesh/scale_mesh_cubedspheredom2d.F90:193-247)."""
-    if nranks not in (1, 2, 3, 6):
-        raise ValueError("whole panels are distributed over 1, 2, 3 or 6 ranks (the reference's rule)")
-    per = 6 // nranks
-    return [P // per for P in range(6)]
+def panel_owner(nranks: int, ntile: int = 1):
+    """Rank owning each local mesh (tile), contiguous blocks in tile order.  ntile = 1: whole panels over 1, 2, 3 or 6 ranks,
+    as the reference distributes them (`MeshCubedSphereDom2D_check_division_params`,
+    FElib/src/mesh/scale_mesh_cubedspheredom2d.F90:193-247).  ntile = k > 1: the reference's 6 k^2-tile graph with several
+    local meshes per rank (its `NLocalMeshPerPrc`), any rank count that divides 6 k^2 (4 and 8 GPUs at k = 2)."""
+    n = 6 * ntile * ntile
+    if ntile == 1 and nranks not in (1, 2, 3, 6):
+        raise ValueError("whole panels are distributed over 1, 2, 3 or 6 ranks (the reference's rule); use ntile = 2 for 4 or 8")
+    if n % nranks:
+        raise ValueError(f"{nranks} ranks do not divide the {n} tiles")
+    per = n // nranks
+    return [t // per for t in range(n)]
 
 
 def exchange_plan(links, owner, rank):
@@ -178,7 +218,7 @@ def exchange_plan(links, owner, rank):
     fedg_link_halo_send.  msg_id = 6 U + g identifies the linked face on both sides; NCCL matches the messages of a rank pair in
     ascending msg_id (tests/test_multi_tile.py runs the plan over gloo)."""
     local, recvs, sends = [], [], []
-    for U in range(6):
+    for U in range(len(links)):
         for g, (T, _src, _rot) in links[U].items():
             mid = 6 * U + g
             if owner[U] == rank and owner[T] == rank:
@@ -206,8 +246,8 @@ class GlobalSphereDriver:
         from .dyncore import AtmDynDGMDriver_nonhydro3d
         self.cs, self.L = cs, _lib.load()
         self.rank, self.nranks = rank, nranks
-        self.owner = panel_owner(nranks)
-        self.panel_ids = [P for P in range(6) if self.owner[P] == rank]
+        self.owner = panel_owner(nranks, cs.ntile)
+        self.panel_ids = [P for P in range(len(cs.panels)) if self.owner[P] == rank]      # local meshes (tiles) of this rank
         bc = vel_bc or dict(btm="SLIP", top="SLIP")
         self.panels = [AtmDynDGMDriver_nonhydro3d(cs.elem, cs.panels[P], consts, vel_bc=bc, my_rank=rank) for P in self.panel_ids]
         drv = dict(zip(self.panel_ids, self.panels))
@@ -217,13 +257,14 @@ class GlobalSphereDriver:
         for U, g, T in local:
             _, src, rot = cs.links[U][g]
             idx = np.ascontiguousarray(src + 1, dtype=np.int32)
-            r = np.ascontiguousarray(rot.reshape(-1, 4), dtype=np.float64)        # [r00, r01, r10, r11] per node
+            r = None if rot is None else np.ascontiguousarray(rot.reshape(-1, 4), dtype=np.float64)   # [r00, r01, r10, r11] per node
             self._keep += [idx, r]
-            _lib.check(self.L.fedg_link_halo(drv[U].h, g + 1, drv[T].h, idx.ctypes.data_as(vp), r.ctypes.data_as(vp)))
+            _lib.check(self.L.fedg_link_halo(drv[U].h, g + 1, drv[T].h, idx.ctypes.data_as(vp), None if r is None else r.ctypes.data_as(vp)))
         for U, g, peer, mid in recvs:
-            r = np.ascontiguousarray(cs.links[U][g][2].reshape(-1, 4), dtype=np.float64)
+            rot = cs.links[U][g][2]
+            r = None if rot is None else np.ascontiguousarray(rot.reshape(-1, 4), dtype=np.float64)
             self._keep.append(r)
-            _lib.check(self.L.fedg_link_halo_recv(drv[U].h, g + 1, peer, mid, r.ctypes.data_as(vp)))
+            _lib.check(self.L.fedg_link_halo_recv(drv[U].h, g + 1, peer, mid, None if r is None else r.ctypes.data_as(vp)))
         for T, peer, mid, U, g in sends:
             idx = np.ascontiguousarray(cs.links[U][g][1] + 1, dtype=np.int32)
             self._keep.append(idx)

@@ -223,9 +223,18 @@ class LocalMeshCubedSpherePanel(LocalMeshCube):
     The lateral halo of the tile holds its own face values: the panel-edge exchange is not part of this class."""
 
     def __init__(self, elem: HexElement, panelID: int, NeX: int, NeY: int, NeZ: int, ztop: float, RPlanet: float,
-                 FZ: np.ndarray | None = None):
+                 FZ: np.ndarray | None = None, sub=(1, 0, 0)):
+        """sub = (k, ti, tj): the tile (ti, tj) of a k x k decomposition of the panel (NeX, NeY are per tile), the layout the
+        reference uses beyond six processes (`MeshCubedSphereDom2D` with NprcX = NprcY = k tiles per panel,
+        scale_mesh_cubedspheredom2d.F90:193-247).  The tile is its own local mesh: all four lateral faces are filled by links
+        (fe_project_b200/cubedsphere.py), none by the tile graph of `LocalMeshCube`."""
         q = 0.25 * np.pi
-        super().__init__(elem, NeX, NeY, NeZ, -q, q, -q, q, 0.0, ztop, FZ=FZ, periodic=(False, False, False))
+        k, ti, tj = sub
+        assert 0 <= ti < k and 0 <= tj < k
+        w = 2.0 * q / k
+        super().__init__(elem, NeX, NeY, NeZ, -q + ti * w, -q + (ti + 1) * w if ti + 1 < k else q,
+                         -q + tj * w, -q + (tj + 1) * w if tj + 1 < k else q, 0.0, ztop, FZ=FZ, periodic=(False, False, False))
+        self.sub = (int(k), int(ti), int(tj))
         assert 1 <= panelID <= 6
         self.panelID, self.RPlanet = int(panelID), float(RPlanet)
         Np, Nfp, Ne = elem.Np, elem.Nfp, self.Ne

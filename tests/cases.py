@@ -156,19 +156,22 @@ class GlobalSphereCase:
     (smooth across every panel edge and both poles), a vertical-velocity pattern and a warm blob."""
 
     def __init__(self, p=7, Ne=2, NeZ=2, ztop=30.0e3, dt=20.0, tinteg="IMEX_ARK324", modalfilter=True, u0=30.0, T0=300.0, perturb=1.0,
-                 eqs="GLOBALNONHYDRO3D_HEVI"):
+                 eqs="GLOBALNONHYDRO3D_HEVI", ntile=1):
+        """ntile = k: k x k tiles per panel, Ne elements per TILE edge (24 local meshes for k = 2); the oracle takes whole panels
+        (make_oracle needs ntile = 1: build a second case with Ne * k for it)."""
         from fe_project_b200.cubedsphere import CubedSphere, cs2cart, cs2lonlat, lonlat2cs_vec
         self.p, self.dt, self.tinteg, self.modalfilter, self.ztop = p, dt, tinteg, modalfilter, ztop
         self.eqs = eqs
         self.elem = HexElement(p)
         self.consts = c = dict(C0)
-        self.cs = CubedSphere(self.elem, Ne, NeZ, ztop, c["RPlanet"])
+        self.cs = CubedSphere(self.elem, Ne, NeZ, ztop, c["RPlanet"], ntile=ntile)
         self.vel_bc = dict(btm="SLIP", top="SLIP")
         H = c["Rdry"] * T0 / c["GRAV"]
         amp = (u0 ** 2 + 2.0 * c["RPlanet"] * c["OHM"] * u0) / (2.0 * c["Rdry"] * T0)
         w2 = perturb * 8.0 / c["RPlanet"] * np.array([0.6, -0.3, 0.74])          # tilted rotation vector [1/s]
         self.fields = []
-        for P, m in enumerate(self.cs.panels):
+        for m in self.cs.panels:
+            P = m.panelID - 1
             Np, NeA, Nel = self.elem.Np, m.NeA, m.Ne
             a, b, z = m.pos_en[0], m.pos_en[1], m.pos_en[2]
             lon, lat = cs2lonlat(P + 1, a, b)
@@ -198,6 +201,7 @@ class GlobalSphereCase:
 
     def make_oracle(self):
         from oracle_api import Oracle, OracleSphere
+        assert self.cs.ntile == 1, "the oracle steps whole panels"
         c = self.consts
         panels = []
         for P, m in enumerate(self.cs.panels):

@@ -1,7 +1,9 @@
-"""Whole cubed sphere over several GPUs (run under torchrun, 2 / 3 / 6 ranks, one per GPU): every rank owns a block of panels,
-panel edges between ranks travel over NCCL (fedg_link_halo_send / _recv).  Checked against the single-process CPU oracle of the
-whole sphere: halo contents after one exchange, then N steps.  Rank 0 prints one line and exits non-zero on failure.
-  torchrun --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29534 tests/mgpu_sphere_parity.py [heve]"""
+"""Whole cubed sphere over several GPUs (run under torchrun, one rank per GPU): every rank owns a block of local meshes, the
+edges between meshes of different ranks travel over NCCL (fedg_link_halo_send / _recv).  Whole panels: 2 / 3 / 6 ranks;
+with `tiles` every panel is cut into 2 x 2 tiles (24 local meshes): 1 / 2 / 4 / 8 ranks.  Checked against the single-process CPU
+oracle of the whole sphere (whole panels): halo contents after one exchange (whole panels only), then N steps.  Rank 0 prints one
+line and exits non-zero on failure.
+  torchrun --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29534 tests/mgpu_sphere_parity.py [heve] [tiles]"""
 import os
 import sys
 
@@ -12,15 +14,59 @@ sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 PROG = ("DDENS", "MOMX", "MOMY", "MOMZ", "DRHOT")
 
 
+def run_tiles(kw, rank, world, dist, torch):
+    """2 x 2 tiles per panel on the device(s) against the whole-panel oracle."""
+    from cases import GlobalSphereCase, rel_l2
+    case = GlobalSphereCase(p=7, Ne=2, NeZ=2, ntile=2, **kw)          # 24 tiles of 2 x 2 x 2 elements
+    ref = GlobalSphereCase(p=7, Ne=4, NeZ=2, ntile=1, **kw)           # the same sphere as six whole panels
+
+    def bcast(raw):
+        obj = [raw]
+        dist.broadcast_object_list(obj, src=0)
+        return obj[0]
+    g = case.make_driver(rank=rank, nranks=world, bcast=bcast if world > 1 else None)
+    s = ref.make_oracle()
+    nsteps = 5
+    g.Update(nsteps)
+    s.update(nsteps)
+    Np = case.elem.Np
+    worst = 0.0
+    for d, t in zip(g.panels, g.panel_ids):
+        m = case.cs.panels[t]
+        k, ti, tj = m.sub
+        nxp = k * m.NeX
+        kep = (m.ex + ti * m.NeX) + (m.ey + tj * m.NeY) * nxp + m.ez * nxp * (k * m.NeY)
+        o = s.panels[case.cs.panel_of[t]]
+        got = d.get_prog()
+        for nm in PROG:
+            exp = o.arr(nm)[: ref.cs.panels[0].Ne * Np].reshape(-1, Np)[kep].reshape(-1)
+            worst = max(worst, rel_l2(got[nm][: m.Ne * Np], exp))
+    if world > 1:
+        t = torch.tensor([worst], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        worst = t.item()
+    ok = worst <= 1e-10
+    if rank == 0:
+        print(f"mgpu_sphere_parity tiles=2x2 per panel ({24 // world} local meshes per rank) world={world} eqs={case.eqs} {case.tinteg}: "
+              f"worst rel L2 after {nsteps} steps = {worst:.3e} -> {'OK' if ok else 'FAIL'}")
+    if world > 1:
+        dist.destroy_process_group()
+    sys.exit(0 if ok else 1)
+
+
 def main():
     import torch
     import torch.distributed as dist
     from cases import GlobalSphereCase, rel_l2
-    rank, world, lrank = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ.get("LOCAL_RANK", "0"))
+    rank, world, lrank = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(lrank)
-    dist.init_process_group("nccl", device_id=torch.device("cuda", lrank))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", lrank))
     heve = "heve" in sys.argv[1:]
+    tiles = "tiles" in sys.argv[1:]
     kw = dict(eqs="GLOBALNONHYDRO3D_HEVE", tinteg="ERK_SSP_4s3o", dt=2.0) if heve else dict(tinteg="IMEX_ARK324", dt=20.0)
+    if tiles:
+        return run_tiles(kw, rank, world, dist, torch)
     case = GlobalSphereCase(p=7, Ne=2, NeZ=3, **kw)
 
     def bcast(raw):

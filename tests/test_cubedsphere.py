@@ -93,3 +93,72 @@ def test_six_panel_steps_stay_finite():
         for k in ("DDENS", "MOMX", "MOMY", "MOMZ", "DRHOT"):
             assert np.isfinite(o.arr(k)[:n]).all()
         assert np.abs(o.arr("MOMZ")[:n]).max() < 2.0
+
+
+def tile_to_panel_elements(cs_tiles, t):
+    """Element index inside the whole panel (k Ne x k Ne x NeZ elements) of every element of tile t."""
+    m = cs_tiles.panels[t]
+    k, ti, tj = m.sub
+    nxp = k * m.NeX
+    return (m.ex + ti * m.NeX) + (m.ey + tj * m.NeY) * nxp + m.ez * nxp * (k * m.NeY)
+
+
+def test_sub_panel_tiles_reproduce_the_whole_panel_exchange():
+    """2 x 2 tiles per panel (24 local meshes: the layout for 4 and 8 GPUs): after the tile exchange every face node sees
+    through VMapP exactly what it sees on the whole-panel mesh -- neighbour tiles inside a panel, reverted and non-reverted panel
+    edges, the basis change of (MOMX, MOMY)."""
+    e = HexElement(2)
+    whole = CubedSphere(e, 4, 2, 30.0e3, 6.37122e6)
+    tiles = CubedSphere(e, 2, 2, 30.0e3, 6.37122e6, ntile=2)
+    assert len(tiles.panels) == 24
+    Np = e.Np
+    rng = np.random.default_rng(3)
+    names = ("DDENS", "MOMX", "MOMY")
+    fw = [{n: np.zeros(m.NeA * Np) for n in names} for m in whole.panels]
+    for P, m in enumerate(whole.panels):
+        for n in names:
+            fw[P][n][: m.Ne * Np] = rng.standard_normal(m.Ne * Np)
+    ft = []
+    for t, m in enumerate(tiles.panels):
+        P, kep = tiles.panel_of[t], tile_to_panel_elements(tiles, t)
+        d = {}
+        for n in names:
+            a = np.full(m.NeA * Np, np.nan)
+            a[: m.Ne * Np] = fw[P][n][: whole.panels[P].Ne * Np].reshape(-1, Np)[kep].reshape(-1)
+            d[n] = a
+        ft.append(d)
+        # the tile covers the same nodes as its part of the panel
+        assert np.abs(m.pos_en[0] - whole.panels[P].pos_en[0][kep]).max() <= 1e-15
+        assert np.abs(m.pos_en[1] - whole.panels[P].pos_en[1][kep]).max() <= 1e-15
+    whole.exchange_numpy(fw)
+    tiles.exchange_numpy(ft)
+    for t, m in enumerate(tiles.panels):
+        P, kep = tiles.panel_of[t], tile_to_panel_elements(tiles, t)
+        mp = whole.panels[P]
+        lat = slice(0, 4 * e.Nfp)                              # the four lateral faces
+        for n in names:
+            got = ft[t][n][m.VMapP][:, lat]
+            exp = fw[P][n][mp.VMapP][kep][:, lat]
+            assert np.isfinite(got).all(), (t, n)
+            if n == "DDENS":
+                assert np.array_equal(got, exp), (t, n)
+            else:                                              # rot from tile node positions: equal to round-off
+                assert np.abs(got - exp).max() <= 1e-13 * np.abs(exp).max(), (t, n)
+
+
+@pytest.mark.parametrize("nranks", [4, 8])
+def test_tile_owner_and_plan_cover_every_face(nranks):
+    from fe_project_b200.cubedsphere import exchange_plan, panel_owner
+    tiles = CubedSphere(HexElement(1), 1, 1, 1.0e4, 6.37122e6, ntile=2)
+    owner = panel_owner(nranks, 2)
+    assert [owner.count(r) for r in range(nranks)] == [24 // nranks] * nranks
+    seen_send, seen_recv = set(), set()
+    for r in range(nranks):
+        local, recvs, sends = exchange_plan(tiles.links, owner, r)
+        mine = [t for t in range(24) if owner[t] == r]
+        assert len(local) + len(recvs) == 4 * len(mine)
+        seen_recv |= {(peer, r, mid) for _, _, peer, mid in recvs}
+        seen_send |= {(r, peer, mid) for _, peer, mid, _, _ in sends}
+    assert seen_send == seen_recv                      # every message has exactly one sender and one receiver
+    with pytest.raises(ValueError):
+        panel_owner(4, 1)

@@ -209,3 +209,26 @@ def test_two_gpu_sphere_parity(mode):
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     assert "OK" in out.stdout
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["hevi", "heve"])
+def test_sphere_sub_panel_tiles_one_gpu(mode):
+    """24 local meshes (2 x 2 tiles per panel) advanced together on one GPU == the whole-panel oracle."""
+    cmd = [sys.executable, os.path.join(ROOT, "tests", "mgpu_sphere_parity.py"), "tiles"] + (["heve"] if mode == "heve" else [])
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")}
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=env)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert "OK" in out.stdout
+
+
+@pytest.mark.gpu
+def test_two_gpu_sphere_tiles_parity():
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", str(29800 + os.getpid() % 150), os.path.join(ROOT, "tests", "mgpu_sphere_parity.py"), "tiles"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert "OK" in out.stdout
