@@ -213,10 +213,10 @@ def run_sphere(args, rank=0, world=1, local_rank=0):
     dist = None
     bcast = None
     if world > 1:
-        if world not in (2, 3, 6):
+        if world not in (2, 3, 4, 6, 8):
             if rank == 0:
-                emit(dict(metric=METRIC, unavailable="whole panels spread over 1, 2, 3 or 6 ranks only (the reference rejects other counts, "
-                          "scale_mesh_cubedspheredom2d.F90:193-247); sub-panel tiles are not built yet", n_gpus=world))
+                emit(dict(metric=METRIC, unavailable="the sphere is spread as whole panels (2, 3, 6 ranks) or as 2 x 2 tiles per panel "
+                          "(4, 8 ranks)", n_gpus=world))
             return
         import torch.distributed as dist_
         dist = dist_
@@ -229,7 +229,11 @@ def run_sphere(args, rank=0, world=1, local_rank=0):
     from cases import GlobalSphereCase
     from fe_project_b200.dyncore import PROG_NAMES
     ne, nez = (args.nex if args.nex != WORKLOAD["NeX"] else 32), (args.nez if args.nez != WORKLOAD["NeZ"] else 12)
-    case = GlobalSphereCase(p=7, Ne=ne, NeZ=nez, dt=5.0 * 32 / ne, tinteg="IMEX_ARK324", modalfilter=True)
+    from fe_project_b200.cubedsphere import panel_owner
+    ntile = 2 if world in (4, 8) else 1          # 4 / 8 GPUs: 2 x 2 tiles per panel (24 local meshes), the same sphere
+    own_ids = [t for t, r in enumerate(panel_owner(world, ntile)) if r == rank]
+    case = GlobalSphereCase(p=7, Ne=ne // ntile, NeZ=nez, dt=5.0 * 32 / ne, tinteg="IMEX_ARK324", modalfilter=True, ntile=ntile,
+                            fields_for=own_ids)
     g = case.make_driver(rank=rank, nranks=world, bcast=bcast)
     W, K = max(3, args.warmup), args.steps
     g.Update(W)
@@ -276,7 +280,7 @@ def run_sphere(args, rank=0, world=1, local_rank=0):
             metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=K, warmup=W, ms_per_step=ms_total / K, higher_is_better=True,
             scaling=("weak" if world == 1 else "strong"), vs_baseline=None, dtype="f64", data="synthetic",
             config=dict(workload=f"atm_nonhydro3d global cubed sphere 6x{ne}x{ne}x{nez} elements p=7, GLOBALNONHYDRO3D_HEVI, IMEX_ARK324, "
-                                 f"dt={case.dt}, modal filter on, {6 // world} panel(s) per GPU as local meshes with linked panel-edge halos"
+                                 f"dt={case.dt}, modal filter on, {len(own_ids)} {'panel' if ntile == 1 else 'tile (2x2 per panel)'}(s) per GPU as local meshes with linked halos"
                                  + (", panel edges between ranks over NCCL" if world > 1 else ""),
                         dof=dof, l2_policy="inputs larger than L2 (50 MB per field and panel)"),
             clocks=clocks, e2e=dict(value=dof / t_e2e, unit=UNIT, h2d_bytes_per_step=nbytes, d2h_bytes_per_step=nbytes, steps_per_call=1),

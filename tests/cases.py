@@ -156,9 +156,10 @@ class GlobalSphereCase:
     (smooth across every panel edge and both poles), a vertical-velocity pattern and a warm blob."""
 
     def __init__(self, p=7, Ne=2, NeZ=2, ztop=30.0e3, dt=20.0, tinteg="IMEX_ARK324", modalfilter=True, u0=30.0, T0=300.0, perturb=1.0,
-                 eqs="GLOBALNONHYDRO3D_HEVI", ntile=1):
+                 eqs="GLOBALNONHYDRO3D_HEVI", ntile=1, fields_for=None):
         """ntile = k: k x k tiles per panel, Ne elements per TILE edge (24 local meshes for k = 2); the oracle takes whole panels
-        (make_oracle needs ntile = 1: build a second case with Ne * k for it)."""
+        (make_oracle needs ntile = 1: build a second case with Ne * k for it).  fields_for: the local meshes whose initial state is
+        evaluated (default all; a rank of a multi-GPU run passes the ones it owns)."""
         from fe_project_b200.cubedsphere import CubedSphere, cs2cart, cs2lonlat, lonlat2cs_vec
         self.p, self.dt, self.tinteg, self.modalfilter, self.ztop = p, dt, tinteg, modalfilter, ztop
         self.eqs = eqs
@@ -170,7 +171,10 @@ class GlobalSphereCase:
         amp = (u0 ** 2 + 2.0 * c["RPlanet"] * c["OHM"] * u0) / (2.0 * c["Rdry"] * T0)
         w2 = perturb * 8.0 / c["RPlanet"] * np.array([0.6, -0.3, 0.74])          # tilted rotation vector [1/s]
         self.fields = []
-        for m in self.cs.panels:
+        for t, m in enumerate(self.cs.panels):
+            if fields_for is not None and t not in fields_for:
+                self.fields.append(None)
+                continue
             P = m.panelID - 1
             Np, NeA, Nel = self.elem.Np, m.NeA, m.Ne
             a, b, z = m.pos_en[0], m.pos_en[1], m.pos_en[2]
