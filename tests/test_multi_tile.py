@@ -109,7 +109,7 @@ def test_two_gpu_nccl_parity(mode):
 
 
 # ------------------------------------------------------------------------------ cubed sphere: panels spread over ranks
-def _sphere_worker(rank, world, port, outq):
+def _sphere_worker(rank, world, port, outq, ntile=1):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
     import torch
@@ -119,12 +119,13 @@ def _sphere_worker(rank, world, port, outq):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         e = HexElement(2)
-        cs = CubedSphere(e, 2, 2, 1.0e4, 6.37122e6)
-        owner = panel_owner(world)
+        cs = CubedSphere(e, 2, 2, 1.0e4, 6.37122e6, ntile=ntile)
+        owner = panel_owner(world, ntile)
+        nmesh = len(cs.panels)
         names = ("DDENS", "MOMX", "MOMY")
         rng = np.random.default_rng(7)                        # the same on every rank: the whole sphere, for the expectation
         full = [{n: rng.standard_normal(m.NeA * e.Np) for n in names} for m in cs.panels]
-        mine = {P: {n: full[P][n].copy() for n in names} for P in range(6) if owner[P] == rank}
+        mine = {P: {n: full[P][n].copy() for n in names} for P in range(nmesh) if owner[P] == rank}
         for P in mine:                                         # nothing of another rank's panels may be used below
             for n in names:
                 mine[P][n][cs.panels[P].Ne * e.Np:] = np.nan
@@ -135,8 +136,11 @@ def _sphere_worker(rank, world, port, outq):
             nint, o = m.Ne * e.Np, m.halo_face_off[g]
             sl = slice(nint + o, nint + o + vals["DDENS"].size)
             mine[U]["DDENS"][sl] = vals["DDENS"]
-            mine[U]["MOMX"][sl] = rot[:, 0, 0] * vals["MOMX"] + rot[:, 0, 1] * vals["MOMY"]
-            mine[U]["MOMY"][sl] = rot[:, 1, 0] * vals["MOMX"] + rot[:, 1, 1] * vals["MOMY"]
+            if rot is None:                                   # neighbour tile inside a panel: same basis
+                mine[U]["MOMX"][sl], mine[U]["MOMY"][sl] = vals["MOMX"], vals["MOMY"]
+            else:
+                mine[U]["MOMX"][sl] = rot[:, 0, 0] * vals["MOMX"] + rot[:, 0, 1] * vals["MOMY"]
+                mine[U]["MOMY"][sl] = rot[:, 1, 0] * vals["MOMX"] + rot[:, 1, 1] * vals["MOMY"]
 
         for U, g, T in local:
             _, src, rot = cs.links[U][g]
@@ -173,15 +177,15 @@ def _sphere_worker(rank, world, port, outq):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world", [2, 3])
-def test_sphere_panel_exchange_plan_gloo(world):
-    """Panels spread over 2 / 3 ranks: local links + the send / receive plan (ascending msg_id per peer, no tags) reproduce the
-    single-process panel-edge exchange bit for bit."""
+@pytest.mark.parametrize("world,ntile", [(2, 1), (3, 1), (4, 2)])
+def test_sphere_panel_exchange_plan_gloo(world, ntile):
+    """Panels spread over 2 / 3 ranks, 2 x 2 tiles per panel over 4 ranks: local links + the send / receive plan (ascending
+    msg_id per peer, no tags) reproduce the single-process exchange bit for bit."""
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = 31000 + (os.getpid() + 7 * world) % 2000
-    procs = [ctx.Process(target=_sphere_worker, args=(r, world, port, q)) for r in range(world)]
+    procs = [ctx.Process(target=_sphere_worker, args=(r, world, port, q, ntile)) for r in range(world)]
     for p in procs:
         p.start()
     res = [q.get(timeout=180) for _ in procs]
