@@ -51,7 +51,8 @@ def _jacobi_gauss_pts(alpha: int, beta: int, N: int) -> np.ndarray:
         return np.array([-(alpha - beta) / (alpha + beta + 2.0)])
     i = np.arange(N + 1, dtype=np.float64)
     h1 = 2.0 * i + alpha + beta
-    d = -(alpha ** 2 - beta ** 2) / (h1 * (h1 + 2.0))
+    with np.errstate(invalid="ignore", divide="ignore"):      # alpha = beta = 0: 0 / 0 in the first entry, set below
+        d = -(alpha ** 2 - beta ** 2) / (h1 * (h1 + 2.0))
     k = np.arange(1, N + 1, dtype=np.float64)
     e = 2.0 / (h1[:-1] + 2.0) * np.sqrt(
         k * (k + alpha + beta) * (k + alpha) * (k + beta) / ((h1[:-1] + 1.0) * (h1[:-1] + 3.0)))

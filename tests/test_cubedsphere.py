@@ -162,3 +162,68 @@ def test_tile_owner_and_plan_cover_every_face(nranks):
     assert seen_send == seen_recv                      # every message has exactly one sender and one receiver
     with pytest.raises(ValueError):
         panel_owner(4, 1)
+
+
+def _ref_get_index(s_face, Ne1D, n1, i1D, k, fph, fpv):
+    """get_index of the reference's own halo test (FElib/test/FE/field_cubedspheredom3d/test_field_cubedspheredom3d.f90:367-407):
+    source element and face-node number (1-based) behind halo slot (fph, fpv) of the i1D-th element along the edge in layer k,
+    for the signed source face id of tileFaceID_globalMap."""
+    a = abs(s_face)
+    rev = s_face < 0
+    ii = Ne1D - i1D + 1 if rev else i1D
+    base = (k - 1) * Ne1D ** 2
+    if a == 1:
+        ke = ii + base
+    elif a == 2:
+        ke = Ne1D + (ii - 1) * Ne1D + base
+    elif a == 3:
+        ke = ii + (Ne1D - 1) * Ne1D + base
+    else:
+        ke = 1 + (ii - 1) * Ne1D + base
+    fp = (n1 - fph + 1 if rev else fph) + (fpv - 1) * n1
+    return ke, fp
+
+
+def test_halo_sources_match_the_reference_field_test():
+    """Known-answer pin from the reference: test_field_cubedspheredom3d.f90:243-350 fills q with a value that encodes (tile,
+    element, node) and asserts the lateral halo of every tile face against get_index (3 x 3 x 2 elements per panel, six local
+    meshes).  Restated here on the link tables: the source tile and the source node of every halo slot are the ones that test
+    expects, for all 24 panel faces (reverted and not)."""
+    e = HexElement(2)
+    Ne, NeZ = 3, 2
+    cs = CubedSphere(e, Ne, NeZ, 30.0e3, 6.37122e6)
+    pc, fc = panel_connectivity()                       # tileID_globalMap / tileFaceID_globalMap for one tile per panel
+    n1, Np = e.np1, e.Np
+    for U in range(6):
+        for g in range(4):
+            s_face, T_ref = int(fc[g, U]), int(pc[g, U]) - 1
+            T, src, _ = cs.links[U][g]
+            assert T == T_ref, (U, g)
+            exp = []
+            for k in range(1, NeZ + 1):
+                for i in range(1, Ne + 1):
+                    for fpv in range(1, n1 + 1):
+                        for fph in range(1, n1 + 1):
+                            ke, fp = _ref_get_index(s_face, Ne, n1, i, k, fph, fpv)
+                            exp.append((ke - 1) * Np + e.Fmask[abs(s_face) - 1][fp - 1])     # Fmask_h(fp, |s_face|)
+            assert np.array_equal(src, np.asarray(exp)), (U, g, s_face)
+    # and the exchange moves exactly those values: q = 1e6 tile + 1e3 element + node, as get_field_val builds it
+    fields = []
+    for P, m in enumerate(cs.panels):
+        q = np.zeros(m.NeA * Np)
+        q[: m.Ne * Np] = (1e6 * (P + 1) + 1e3 * (np.arange(m.Ne)[:, None] + 1) + (np.arange(Np)[None, :] + 1)).reshape(-1)
+        fields.append({"q": q})
+    cs.exchange_numpy(fields, vector_pairs=())
+    for U, m in enumerate(cs.panels):
+        nint = m.Ne * Np
+        for g in range(4):
+            s_face, T_ref = int(fc[g, U]), int(pc[g, U])
+            o = m.halo_face_off[g]
+            got = fields[U]["q"][nint + o: nint + o + m.halo_face_size[g]].reshape(NeZ, Ne, n1, n1)
+            for k in range(1, NeZ + 1):
+                for i in range(1, Ne + 1):
+                    for fpv in range(1, n1 + 1):
+                        for fph in range(1, n1 + 1):
+                            ke, fp = _ref_get_index(s_face, Ne, n1, i, k, fph, fpv)
+                            ans = 1e6 * T_ref + 1e3 * ke + (e.Fmask[abs(s_face) - 1][fp - 1] + 1)
+                            assert got[k - 1, i - 1, fpv - 1, fph - 1] == ans, (U, g, k, i, fpv, fph)
