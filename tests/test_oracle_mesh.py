@@ -97,3 +97,84 @@ def test_multi_tile_graph():
     assert t.tile_neighbors[3] == ((0, 0), 3)   # west: domain boundary -> itself, same face
     assert t.tile_neighbors[4] == ((0, 0), 4) and t.tile_neighbors[5] == ((0, 0), 5)
     assert np.isclose(tiles[(1, 1)].xmin, 2.0) and np.isclose(tiles[(1, 1)].ymax, 4.0)
+
+
+def reference_vmaps(n1, NeX, NeY, NeZ):
+    """VMapM_h/v_ans, VMapP_h/v_ans of check_connectivity (test_mesh_cubedom3d_hexahedral.f90:120-190, identical in
+    test_mesh_cubedsphere3d.f90:110-180), 1-based, faces in the order south, east, north, west, bottom, top."""
+    Np, Nfp, Ne = n1 ** 3, n1 ** 2, NeX * NeY * NeZ
+
+    def elem_id(i, j, k):
+        return i + (j - 1) * NeX + (k - 1) * NeX * NeY
+
+    def node_id(i, j, k):
+        return i + (j - 1) * n1 + (k - 1) * n1 ** 2
+
+    vM = np.zeros((Ne, 6 * Nfp), dtype=np.int64)
+    vP = np.zeros((Ne, 6 * Nfp), dtype=np.int64)
+    for k in range(1, NeZ + 1):
+        for j in range(1, NeY + 1):
+            for i in range(1, NeX + 1):
+                ke = elem_id(i, j, k)
+                etoe = [elem_id(i, j - 1, k), elem_id(i + 1, j, k), elem_id(i, j + 1, k), elem_id(i - 1, j, k),
+                        elem_id(i, j, k - 1), elem_id(i, j, k + 1)]
+                for q in range(1, n1 + 1):
+                    for p in range(1, n1 + 1):
+                        n = p + (q - 1) * n1
+                        own_h = [node_id(p, 1, q), node_id(n1, p, q), node_id(p, n1, q), node_id(1, p, q)]
+                        nbr_h = [node_id(p, n1, q), node_id(1, p, q), node_id(p, 1, q), node_id(n1, p, q)]
+                        own_v = [node_id(p, q, 1), node_id(p, q, n1)]
+                        nbr_v = [node_id(p, q, n1), node_id(p, q, 1)]
+                        for f in range(4):
+                            vM[ke - 1, f * Nfp + n - 1] = (ke - 1) * Np + own_h[f]
+                            vP[ke - 1, f * Nfp + n - 1] = (etoe[f] - 1) * Np + nbr_h[f]
+                        for f in range(2):
+                            vM[ke - 1, (4 + f) * Nfp + n - 1] = (ke - 1) * Np + own_v[f]
+                            vP[ke - 1, (4 + f) * Nfp + n - 1] = (etoe[4 + f] - 1) * Np + nbr_v[f]
+                pp = np.arange(1, Nfp + 1)
+                if j == 1:
+                    vP[ke - 1, 0 * Nfp:1 * Nfp] = Ne * Np + (pp + ((i - 1) + (k - 1) * NeX) * Nfp)
+                if i == NeX:
+                    vP[ke - 1, 1 * Nfp:2 * Nfp] = Ne * Np + Nfp * NeX * NeZ + (pp + ((j - 1) + (k - 1) * NeY) * Nfp)
+                if j == NeY:
+                    vP[ke - 1, 2 * Nfp:3 * Nfp] = Ne * Np + Nfp * (NeX + NeY) * NeZ + (pp + ((i - 1) + (k - 1) * NeX) * Nfp)
+                if i == 1:
+                    vP[ke - 1, 3 * Nfp:4 * Nfp] = Ne * Np + Nfp * (2 * NeX + NeY) * NeZ + (pp + ((j - 1) + (k - 1) * NeY) * Nfp)
+                if k == 1:
+                    vP[ke - 1, 4 * Nfp:5 * Nfp] = Ne * Np + 2 * Nfp * (NeX + NeY) * NeZ + (pp + ((i - 1) + (j - 1) * NeX) * Nfp)
+                if k == NeZ:
+                    vP[ke - 1, 5 * Nfp:6 * Nfp] = Ne * Np + 2 * Nfp * (NeX + NeY) * NeZ + NeX * NeY * Nfp + (pp + ((i - 1) + (j - 1) * NeX) * Nfp)
+    return vM, vP
+
+
+@pytest.mark.parametrize("dims", [(3, 3, 3), (4, 2, 3)])
+def test_reference_connectivity_answers(dims):
+    """Known-answer pin from the reference: check_connectivity of FElib/test/FE/mesh_cubedom3d_hexahedral/
+    test_mesh_cubedom3d_hexahedral.f90:84-222 (3 x 3 x 3 elements, p = 2, one tile, periodic in all directions) writes VMapM
+    and VMapP of every element in closed form -- interior faces pair with the opposite face of the neighbour, faces on the
+    tile boundary point into the halo in the order south, east, north, west, bottom, top.  Restated 1-based as there and held
+    against both mesh restatements."""
+    e = HexElement(2)
+    NeX, NeY, NeZ = dims
+    m = LocalMeshCube(e, NeX, NeY, NeZ, 0.0, 1.0, 0.0, 1.0, 0.0, 1.0, periodic=(True, True, True))
+    o = Oracle(2, NeX, NeY, NeZ, (0, 1, 0, 1, 0, 1), periodic=(True, True, True))
+    vM, vP = reference_vmaps(e.np1, NeX, NeY, NeZ)
+    Ne = m.Ne
+    assert np.array_equal(m.abi_vmapM().reshape(Ne, -1), vM)
+    assert np.array_equal(m.abi_vmapP().reshape(Ne, -1), vP)
+    assert np.array_equal(o.iarr("vmapM").reshape(Ne, -1) + 1, vM)
+    assert np.array_equal(o.iarr("vmapP").reshape(Ne, -1) + 1, vP)
+
+
+def test_reference_connectivity_answers_cubed_sphere_local_meshes():
+    """The same answers for the six local meshes of MeshCubedSphereDom3D (FElib/test/FE/mesh_cubedsphere3d/
+    test_mesh_cubedsphere3d.f90:74-215: 3 x 3 x 2 elements per panel, p = 2): every lateral panel face is a tile boundary."""
+    from fe_project_b200.mesh import LocalMeshCubedSpherePanel
+    e = HexElement(2)
+    vM, vP = reference_vmaps(e.np1, 3, 3, 2)
+    for pid in range(1, 7):
+        m = LocalMeshCubedSpherePanel(e, pid, 3, 3, 2, 10.0e3, 6.37122e6)
+        assert np.array_equal(m.abi_vmapM().reshape(m.Ne, -1), vM), pid
+        assert np.array_equal(m.abi_vmapP().reshape(m.Ne, -1), vP), pid
+        o = Oracle(2, 3, 3, 2, panel=dict(panelID=pid, ztop=10.0e3, RPlanet=6.37122e6))
+        assert np.array_equal(o.iarr("vmapP").reshape(m.Ne, -1) + 1, vP), pid
