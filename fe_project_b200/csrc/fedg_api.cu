@@ -1506,7 +1506,9 @@ __global__ void sponge_coef_kernel(const double* __restrict__ zlev, double* __re
 extern "C" int fedg_sponge_init(fedg_ctx* c, double sl_wdamp_tau, double sl_wdamp_height, int sl_wdamp_layer, int sl_horiveldamp_flag) {
   if (!c) return fail(FEDG_ERR_ARG, "null argument");
   if (!c->dyn_ready) return fail(FEDG_ERR_STATE, "fedg_dyn_init must be called first (the default SL_WDAMP_TAU is 10 TIME_DT)");
-  if (c->terrain || c->global) return fail(FEDG_ERR_UNSUPPORTED, "the sponge layer is available on the flat regional mesh only");
+  // the reference damps in the computational height pos_en(:,:,3) (spongelayer.F90:168-172); the descriptor carries zlev, which
+  // equals it on meshes without topography (regional flat, cubed sphere) only
+  if (c->terrain) return fail(FEDG_ERR_UNSUPPORTED, "the sponge layer needs a mesh without topography (zlev = computational height)");
   if (sl_wdamp_layer > c->NeZ) return fail(FEDG_ERR_ARG, "SL_wdamp_layer should be less than total of vertical elements (NeGZ)");
   double tau = sl_wdamp_tau, height = sl_wdamp_height;
   if (sl_wdamp_layer > 0) {   // height of the first node of that layer (spongelayer.F90:104-106)

@@ -145,6 +145,7 @@ void sphere_update(Driver* d[6]) {
       double* out[5];
       for (int v = 0; v < 5; ++v) out[v] = D.tint.tend_ex_buf(v, ind);
       global_cal_tend(D.elem, D.mesh, D.cst, D.st, hevi, out);
+      if (D.sponge.on) sponge_add_tend(D.elem, D.mesh, D.sponge, D.st, out);               // driver_nonhydro3d.F90:830-841
       if (D.phytend) add_phy_tend(D.elem, D.mesh, D.cst, D.st, D.entot_conserve, out);
       for (int v : rkvar) D.tint.advance(stage, D.st.prog(v), v, 0, nint);
     }

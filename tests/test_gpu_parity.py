@@ -619,3 +619,35 @@ def test_global_panel_with_physics_tendencies():
     g = d.get_prog()
     for nm in PROG:
         assert rel_l2(g[nm][:n], o.arr(nm)[:n]) <= TOL, nm
+
+
+@pytest.mark.parametrize("eqs,tinteg,dt", [("GLOBALNONHYDRO3D_HEVI", "IMEX_ARK324", 20.0), ("GLOBALNONHYDRO3D_HEVE", "ERK_SSP_4s3o", 2.0)])
+def test_sponge_layer_on_the_sphere(eqs, tinteg, dt):
+    """AtmDynSpongeLayer with the global equation sets (the shipped baroclinic_wave_global/run.conf carries
+    PARAM_ATMOS_DYN_SPONGELAYER: SL_WDAMP_HEIGHT = 20 km): one panel against the oracle, then the six panels together; a short
+    relaxation time so that the damping is well above round-off in a few steps."""
+    kw = dict(SL_WDAMP_TAU=200.0, SL_WDAMP_HEIGHT=12.0e3, SL_HORIVELDAMP_FLAG=True)
+    case = GlobalPanelCase(p=7, NeX=2, NeY=2, NeZ=3, dt=dt, eqs=eqs, tinteg=tinteg)
+    o = case.make_oracle()
+    d = case.make_driver(o)
+    o.set_sponge(True, **kw); d.sponge_init(**kw)
+    o.update(4); d.Update(4)
+    g = d.get_prog()
+    n = case.mesh.Ne * case.elem.Np
+    for nm in PROG:
+        assert rel_l2(g[nm][:n], o.arr(nm)[:n]) <= TOL, nm
+    d2 = case.make_driver(o); d2.Update(4)
+    assert rel_l2(d2.get_prog()["MOMZ"][:n], g["MOMZ"][:n]) > 1e-6      # the damping matters
+    sph = GlobalSphereCase(p=7, Ne=2, NeZ=3, dt=dt, tinteg=tinteg, eqs=eqs)
+    s = sph.make_oracle()
+    gs = sph.make_driver()
+    for op in s.panels:
+        op.set_sponge(True, **kw)
+    for dp in gs.panels:
+        dp.sponge_init(**kw)
+    s.update(3); gs.Update(3)
+    for P, (dp, op, m) in enumerate(zip(gs.panels, s.panels, sph.cs.panels)):
+        got = dp.get_prog()
+        n = m.Ne * sph.elem.Np
+        for nm in PROG:
+            assert rel_l2(got[nm][:n], op.arr(nm)[:n]) <= TOL, (P, nm)
