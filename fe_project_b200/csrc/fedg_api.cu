@@ -968,10 +968,22 @@ int fedg_dyn_update(fedg_ctx* c, int nsteps) {
 }
 
 int fedg_dyn_update_host(fedg_ctx* c, double* DDENS, double* MOMX, double* MOMY, double* MOMZ, double* DRHOT, int nsteps) {
+  if (!c || !DDENS || !MOMX || !MOMY || !MOMZ || !DRHOT) return fail(FEDG_ERR_ARG, "null argument");
+  // Only the (Np, Ne) interior part travels: the halo slots [Ne+1:NeA] are rebuilt on the device by the exchange of every
+  // stage before anything reads them, and what the reference leaves there after Update is the exchange of the LAST STAGE INPUT,
+  // not a state the caller uses.  20 % fewer PCIe bytes at 32x32x16; the copies are queued on the compute stream, no host
+  // synchronisation between upload, steps and download.
+  double* h[NVAR] = {DDENS, MOMX, MOMY, MOMZ, DRHOT};
+  for (int v = 0; v < NVAR; ++v)
+    CUDA_TRY(cudaMemcpyAsync(c->prog[c->cur][v].p, h[v], c->nint * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  c->dp_valid[c->cur] = false;
+  c->xbuf = c->cur;
   int rc;
-  if ((rc = fedg_set_prog(c, DDENS, MOMX, MOMY, MOMZ, DRHOT))) return rc;
   if ((rc = run_steps(c, nsteps))) return rc;
-  return fedg_get_prog(c, DDENS, MOMX, MOMY, MOMZ, DRHOT);
+  for (int v = 0; v < NVAR; ++v)
+    CUDA_TRY(cudaMemcpyAsync(h[v], c->prog[c->cur][v].p, c->nint * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  return FEDG_OK;
 }
 
 int fedg_exchange_halo(fedg_ctx* c, int apply_bc) {

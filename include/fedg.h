@@ -132,8 +132,9 @@ int fedg_set_coriolis(fedg_ctx* ctx, const double* coriolis);
 /* AtmDynDGMDriver_nonhydro3d%Update (driver_nonhydro3d.F90:614-963), nsteps times, state resident
  * on the device. */
 int fedg_dyn_update(fedg_ctx* ctx, int nsteps);
-/* Same, called the way the reference driver calls Update: prognostic fields live in host arrays;
- * they are copied to the device, advanced nsteps and copied back. */
+/* Same, called the way the reference driver calls Update: prognostic fields live in host arrays (Np, NeA);
+ * their (Np, Ne) interior is copied to the device, advanced nsteps and copied back.  The halo part [Ne+1:NeA] of the host
+ * arrays is neither read nor written: the exchange of every stage rebuilds it on the device. */
 int fedg_dyn_update_host(fedg_ctx* ctx, double* DDENS, double* MOMX, double* MOMY, double* MOMZ,
                          double* DRHOT, int nsteps);
 
