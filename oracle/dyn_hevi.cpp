@@ -14,6 +14,7 @@
 //       and top of the column vmapP == vmapM)
 // The reference vectorises over `im` horizontal nodes (first array index); the arithmetic per column
 // is what is restated here, one column (ke2D, ij) at a time.
+#include <cstdlib>
 #include "fe_oracle.hpp"
 
 #include <algorithm>
@@ -168,6 +169,37 @@ void lu_solve(const double* A, int n, const int* ipiv, double* rhs, int nrhs) {
       for (int j = i + 1; j < n; ++j) t = t - A[i * n + j] * rhs[j * nrhs + r];
       rhs[i * nrhs + r] = t * A[i * n + i];
     }
+}
+
+// Experiment switch (tests only, FEO_VI_STATIC_PIVOT=1): eliminate in the fixed order DDENS_0..n, MOMZ_0..n, DRHOT_0..n
+// without any pivot search, to measure how far a search-free device solver may deviate from the reference's partial pivoting.
+bool vi_static_pivot() {
+  static int v = -1;
+  if (v < 0) { const char* e = std::getenv("FEO_VI_STATIC_PIVOT"); v = (e && e[0] == '1') ? 1 : 0; }
+  return v == 1;
+}
+// symmetric permutation to block order, LU without pivoting, solve, permute back.  A: n x n row-major (destroyed); rhs n x nrhs.
+void solve_static_order(double* A, int n, double* rhs, int nrhs) {
+  const int np = n / 3;
+  std::vector<int> ord(n);
+  for (int v = 0; v < 3; ++v) for (int pv = 0; pv < np; ++pv) ord[v * np + pv] = 3 * pv + v;
+  std::vector<double> B(size_t(n) * n), r(size_t(n) * nrhs);
+  for (int i = 0; i < n; ++i) {
+    for (int j = 0; j < n; ++j) B[size_t(i) * n + j] = A[size_t(ord[i]) * n + ord[j]];
+    for (int q = 0; q < nrhs; ++q) r[size_t(i) * nrhs + q] = rhs[size_t(ord[i]) * nrhs + q];
+  }
+  for (int k = 0; k < n; ++k) {                      // Gauss-Jordan, pivot (k, k)
+    const double inv = 1.0 / B[size_t(k) * n + k];
+    for (int i = 0; i < n; ++i) {
+      if (i == k) continue;
+      const double m = B[size_t(i) * n + k] * inv;
+      for (int j = k + 1; j < n; ++j) B[size_t(i) * n + j] -= m * B[size_t(k) * n + j];
+      for (int q = 0; q < nrhs; ++q) r[size_t(i) * nrhs + q] -= m * r[size_t(k) * nrhs + q];
+    }
+    for (int q = 0; q < nrhs; ++q) r[size_t(k) * nrhs + q] *= inv;
+    for (int j = k + 1; j < n; ++j) B[size_t(k) * n + j] *= inv;
+  }
+  for (int i = 0; i < n; ++i) for (int q = 0; q < nrhs; ++q) rhs[size_t(ord[i]) * nrhs + q] = r[size_t(i) * nrhs + q];
 }
 
 struct VIWork {
@@ -473,13 +505,16 @@ void solve_var3(const Element& e, const Mesh& m, const Consts& c, const DynState
               b[size_t(kz) * nb + r] = b[size_t(kz) * nb + r] - a0 * bp[p1] - a1 * bp[p1 + 1] - a2 * bp[p1 + 2];
             }
           }
-          lu_factor(D.data(), nb, ipiv.data());
           const int nr = (kz == NeZ - 1) ? 1 : 4;
           for (int r = 0; r < nb; ++r) {
             rhs[r * nr] = b[size_t(kz) * nb + r];
             if (nr == 4) for (int cc = 0; cc < 3; ++cc) rhs[r * nr + 1 + cc] = G[size_t(kz) * nb * 3 + r * 3 + cc];
           }
-          lu_solve(D.data(), nb, ipiv.data(), rhs.data(), nr);
+          if (vi_static_pivot()) solve_static_order(D.data(), nb, rhs.data(), nr);
+          else {
+            lu_factor(D.data(), nb, ipiv.data());
+            lu_solve(D.data(), nb, ipiv.data(), rhs.data(), nr);
+          }
           for (int r = 0; r < nb; ++r) {
             b[size_t(kz) * nb + r] = rhs[r * nr];
             if (nr == 4) for (int cc = 0; cc < 3; ++cc) G[size_t(kz) * nb * 3 + r * 3 + cc] = rhs[r * nr + 1 + cc];
