@@ -205,6 +205,25 @@ struct Driver {
   void update();  // fluid_dyn_solver/scale_atm_dyn_dgm_driver_nonhydro3d.F90:614-963
 };
 
+// tracer advection (tracer.cpp; row f4, restatement only: no device kernel yet)
+void trc_face_int_weight(const Element& e, vec& W);
+void trc_cal_alphdens_advtest(const Element& e, const Mesh& m, const double* DDENS, const double* MOMX, const double* MOMY,
+                              const double* MOMZ, const double* DENS_hyd, vec& alphM, vec& alphP);
+void trc_net_outward_flux(const Element& e, const Mesh& m, const vec& W, const double* Q, const double* MX, const double* MY,
+                          const double* MZ, const vec& alphM, const vec& alphP, vec& net);
+void trc_calc_fct_coef(const Element& e, const Mesh& m, const vec& W, const double* Q, const double* MX, const double* MY,
+                       const double* MZ, const double* RHOQ_tp, const vec& alphM, const vec& alphP, const double* DENS_hyd,
+                       const double* DDENS, const double* DDENS0, double rk_c_ssm1, double dt, bool disable_limiter, double* fct);
+void trc_cal_tend(const Element& e, const Mesh& m, const vec& W, const double* Q, const double* MX, const double* MY, const double* MZ,
+                  const vec& alphM, const vec& alphP, const double* fct, const double* RHOQ_tp, double* Q_dt);
+void trc_tmar(const Element& e, const Mesh& m, const double* DENS_hyd, const double* DDENS, double* Q);
+void trc_modalfilter(const Element& ef, const Mesh& m, const double* DENS_hyd, const double* DDENS, double* Q);
+void rk_advance_trcvar_low_storage(const RKScheme& sc, double dt, int stage, size_t n, double* q, const double* DDENS,
+                                   const double* DDENS0, const double* DENS_hyd, double* var0, double* varTmp, const double* tend);
+struct Driver;
+void trcadv_update_advtest(Driver& d, const Element& elem_trcfilter, const RKScheme& sc, double dt, bool modalfilter,
+                           bool disable_limiter, double* QTRC, const double* RHOQ_tp);
+
 // whole cubed sphere (sphere.cpp): panel-edge exchange and the six-panel step
 void sphere_exchange(const Element& e, Mesh* const mesh[6], const std::vector<double*> scal[6], double* const u1[6], double* const u2[6]);
 void sphere_update(Driver* d[6]);
