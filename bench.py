@@ -72,6 +72,19 @@ class ClockSampler:
         except OSError:
             self.p = None
 
+    def wait_started(self, timeout=3.0):
+        """nvidia-smi needs a few hundred ms before its first line: wait for it, so that the samples fall INTO the timed region."""
+        t0 = time.perf_counter()
+        while self.p is not None and time.perf_counter() - t0 < timeout:
+            if self.p.poll() is not None:          # nvidia-smi exited (no device / no permission): nothing to wait for
+                return
+            try:
+                if os.path.getsize(self.f.name) > 0:
+                    return
+            except OSError:
+                return
+            time.sleep(0.02)
+
     def stop(self):
         out = dict(sm_mhz=None, sm_max_mhz=None, reasons=[], samples=0)
         if self.p is None:
@@ -160,7 +173,7 @@ def run_advect3d(args):
     g.set(q, u, u, u)
     W, K = max(3, args.warmup), args.steps
     g.update(W)
-    sampler = ClockSampler(0); sampler.start(); time.sleep(0.12)
+    sampler = ClockSampler(0); sampler.start(); sampler.wait_started()
     g.update(K)
     tm = g.last_timing()
     clocks = sampler.stop()
@@ -240,7 +253,7 @@ def run_sphere(args, rank=0, world=1, local_rank=0):
     torch.cuda.synchronize()
     if dist:
         dist.barrier()
-    sampler = ClockSampler(local_rank); sampler.start(); time.sleep(0.12)
+    sampler = ClockSampler(local_rank); sampler.start(); sampler.wait_started()
     g.Update(K)
     torch.cuda.synchronize()
     tm = g.last_timing()
@@ -380,7 +393,7 @@ def main():
         dist.barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
-    time.sleep(0.12)
+    sampler.wait_started()
     d.Update(K)
     torch.cuda.synchronize()
     tm = d.last_timing()
