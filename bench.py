@@ -72,7 +72,7 @@ class ClockSampler:
         except OSError:
             self.p = None
 
-    def wait_started(self, timeout=3.0):
+    def wait_started(self, timeout=1.0):
         """nvidia-smi needs a few hundred ms before its first line: wait for it, so that the samples fall INTO the timed region."""
         t0 = time.perf_counter()
         while self.p is not None and time.perf_counter() - t0 < timeout:
