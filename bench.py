@@ -381,8 +381,19 @@ def main():
             dist.broadcast_object_list(obj, src=0)
             return obj[0]
         d.init_comm(rank, world, bcast)
-    if world == 1 and args.workload == "density_current":   # horizontally uniform background: DPhydDx/y vanish to round-off; single tile keeps the set-up path exercised
-        gx, gy = calc_phyd_hgrad(case.elem, case.mesh, case.fields["PRES_hyd"])
+    if args.workload == "density_current":
+        # DPhydDx / DPhydDy are registered on every rank count, so that the per-GPU work (two more fields per stage) is the same
+        # at N = 1 and N > 1.  The background is horizontally uniform: the gradients vanish to round-off and do not depend on
+        # the neighbours, so a tile evaluates them on a stand-alone copy of its own mesh (its lateral halo = own face values)
+        # instead of exchanging PRES_hyd with the other ranks.
+        if world == 1:
+            gmesh = case.mesh
+        else:
+            from fe_project_b200.mesh import LocalMeshCube
+            cm = case.mesh
+            gmesh = LocalMeshCube(case.elem, cm.NeX, cm.NeY, cm.NeZ, cm.xmin, cm.xmax, cm.ymin, cm.ymax, cm.zmin, cm.zmax, FZ=cm.FZ,
+                                  periodic=(False, False, False))
+        gx, gy = calc_phyd_hgrad(case.elem, gmesh, case.fields["PRES_hyd"])
         d.set_phyd_hgrad(gx, gy)
     Np, Ne = case.elem.Np, case.mesh.Ne
     dof = 5 * Np * Ne * world
