@@ -136,6 +136,22 @@ int feo_setup_dyn(void* hv, const char* eqs, const char* tinteg, double dt, int 
 // Tracer advection with a prescribed mass flux (ONLY_TRACERADV_FLAG, driver_trcadv3d.F90:312-559): advances QTRC (Np*NeA, in/out)
 // by nsteps of `tinteg` with the momentum / density of the handle's state; mf[6] = tracer modal filter (etac_h, alpha_h, ord_h,
 // etac_v, alpha_v, ord_v) when modalfilter != 0; RHOQ_tp may be NULL (zero).
+void feo_set_tracer_coupling(void* hv, int on) { static_cast<Handle*>(hv)->d.tracer = on != 0; }
+// one tracer step with the mass fluxes the last dynamics step accumulated (feo_set_tracer_coupling(1) before feo_update)
+int feo_trcadv_update_coupled(void* hv, const char* tinteg, double dt, int modalfilter, const double* mf, int disable_limiter,
+                              double* QTRC, const double* RHOQ_tp) {
+  auto* h = static_cast<Handle*>(hv);
+  return guard([&] {
+    auto& d = h->d;
+    RKScheme sc;
+    if (!sc.init(tinteg)) throw std::runtime_error(std::string("unsupported RK scheme ") + tinteg);
+    Element ef = d.elem;
+    if (modalfilter) ef.setup_filter(mf[0], mf[1], int(mf[2]), mf[3], mf[4], int(mf[5]));
+    vec zero;
+    if (!RHOQ_tp) { zero.assign(size_t(d.elem.Np) * d.mesh.NeA, 0.0); RHOQ_tp = zero.data(); }
+    trcadv_update_coupled(d, ef, sc, dt, modalfilter != 0, disable_limiter != 0, QTRC, RHOQ_tp);
+  });
+}
 int feo_trcadv_update(void* hv, const char* tinteg, double dt, int nsteps, int modalfilter, const double* mf, int disable_limiter,
                       double* QTRC, const double* RHOQ_tp) {
   auto* h = static_cast<Handle*>(hv);

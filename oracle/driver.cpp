@@ -10,6 +10,7 @@ void Driver::update() {
   const int rkvar[5] = {DENS_VID, THERM_VID, MOMZ_VID, MOMX_VID, MOMY_VID};
   if (hevi)
     for (int v : rkvar) tint.store_var0(st.prog(v), v, 0, nint);                       // :703-713
+  if (tracer) DENS0_TRC = st.DDENS;                                                    // = tint%var0_2D(:,:,DENS_VID), :926-937
   for (int stage = 0; stage < tint.sc.nstage; ++stage) {
     const int ind = tint.sc.indmap[stage];
     if (hevi) {                                                                        // :730-766
@@ -30,8 +31,10 @@ void Driver::update() {
     else heve_cal_tend(elem, mesh, cst, st, out);                                       // :815
     if (sponge.on) sponge_add_tend(elem, mesh, sponge, st, out);                        // :830-841
     if (phytend) add_phy_tend(elem, mesh, cst, st, entot_conserve, out);                // :843-857
+    if (tracer) trc_save_massflux(*this, stage);                                       // :900-917
     for (int v : rkvar) tint.advance(stage, st.prog(v), v, 0, nint);                   // :920
   }
+  if (tracer) DENS_TRC = st.DDENS;                                                     // before the modal filter, :926-937
   if (modalfilter) modalfilter_apply(elem, mesh, st);                                  // :940-951
   drhot2pres(elem, mesh, cst, st);                                                     // :954
   // numerical diffusion follows the dynamics step (model mod_atmos_dyn.F90:343-349)

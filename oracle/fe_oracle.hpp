@@ -202,6 +202,10 @@ struct Driver {
   bool hevi = false, modalfilter = false, global = false, phytend = false, entot_conserve = false, numdiff = false;
   NumdiffCfg nd;
   SpongeCfg sponge;
+  // tracer coupling (QA > 0): stage-averaged mass fluxes and dissipation coefficients saved by the dynamics stages
+  // (driver_nonhydro3d.F90:900-917, 926-937) for AtmDynDGMDriver_trcadv3d_update
+  bool tracer = false;
+  vec MFLX_x, MFLX_y, MFLX_z, alphM_tavg, alphP_tavg, DENS_TRC, DENS0_TRC;
   void update();  // fluid_dyn_solver/scale_atm_dyn_dgm_driver_nonhydro3d.F90:614-963
 };
 
@@ -221,6 +225,9 @@ void trc_modalfilter(const Element& ef, const Mesh& m, const double* DENS_hyd, c
 void rk_advance_trcvar_low_storage(const RKScheme& sc, double dt, int stage, size_t n, double* q, const double* DDENS,
                                    const double* DDENS0, const double* DENS_hyd, double* var0, double* varTmp, const double* tend);
 struct Driver;
+void trc_save_massflux(Driver& d, int stage);
+void trcadv_update_coupled(Driver& d, const Element& elem_trcfilter, const RKScheme& sc, double dt, bool modalfilter,
+                           bool disable_limiter, double* QTRC, const double* RHOQ_tp);
 void trcadv_update_advtest(Driver& d, const Element& elem_trcfilter, const RKScheme& sc, double dt, bool modalfilter,
                            bool disable_limiter, double* QTRC, const double* RHOQ_tp);
 

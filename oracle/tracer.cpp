@@ -214,44 +214,120 @@ void rk_advance_trcvar_low_storage(const RKScheme& sc, double dt, int stage /*0-
   }
 }
 
-// AtmDynDGMDriver_trcadv3d_update (driver_trcadv3d.F90:312-559), ONLY_TRACERADV_FLAG = .true.: the mass flux is the momentum of
-// the (frozen) dynamical state, DDENS_TRC = DDENS0_TRC = DDENS; one tracer QTRC (Np,NeA) advanced by one step.
-void trcadv_update_advtest(Driver& d, const Element& elem_trcfilter, const RKScheme& sc, double dt, bool modalfilter,
-                           bool disable_limiter, double* QTRC, const double* RHOQ_tp) {
+// atm_dyn_dgm_trcadvect3d_heve_cal_alphdens_dyn (:460-551): dissipation coefficient x density of the dynamics' Rusanov flux at
+// the stage state, accumulated with the Butcher weights (horizontal faces: b_ex, vertical faces: b_im for HEVI)
+void trc_cal_alphdens_dyn(const Element& e, const Mesh& m, const Consts& c, const DynState& s, double w_h, double w_v, bool is_hevi,
+                          vec& alphM, vec& alphP) {
+  const int np = e.np, Nfp = e.Nfp, NfpTot = e.NfpTot;
+  const double gamm = c.CPdry / c.CVdry;
+  for (int ke = 0; ke < m.Ne; ++ke)
+    for (int fp = 0; fp < NfpTot; ++fp) {
+      const size_t f = size_t(fp) + size_t(ke) * NfpTot;
+      const int iM = m.vmapM[f], iP = m.vmapP[f];
+      const int fl = fp % Nfp, fc = fp / Nfp;
+      const int h2d = fc < 4 ? (fc == 0 ? fl % np : fc == 1 ? (np - 1) + (fl % np) * np : fc == 2 ? fl % np + (np - 1) * np : (fl % np) * np) : fl;
+      const size_t h = h2d + size_t(m.emap2d[ke]) * Nfp;
+      const double G11 = m.is_global ? m.GIJ11[h] : 1.0, G22 = m.is_global ? m.GIJ22[h] : 1.0;
+      const double anx = std::fabs(m.nx[f]), any = std::fabs(m.ny[f]), anz = std::fabs(m.nz[f]);
+      const double Gnn = is_hevi ? G11 * anx + G22 * any : G11 * anx + G22 * any + anz;
+      const double densM = s.DDENS[iM] + s.DENS_hyd[iM], densP = s.DDENS[iP] + s.DENS_hyd[iP];
+      const double VelM = (s.MOMX[iM] * m.nx[f] + s.MOMY[iM] * m.ny[f] + s.MOMZ[iM] * m.nz[f]) / densM;
+      const double VelP = (s.MOMX[iP] * m.nx[f] + s.MOMY[iP] * m.ny[f] + s.MOMZ[iP] * m.nz[f]) / densP;
+      const double alpha = std::max(std::sqrt(Gnn * gamm * (s.PRES_hyd[iM] + s.DPRES[iM]) / densM) + std::fabs(VelM),
+                                    std::sqrt(Gnn * gamm * (s.PRES_hyd[iP] + s.DPRES[iP]) / densP) + std::fabs(VelP));
+      const double w = w_h * (anx + any) + w_v * anz;
+      alphM[f] = alphM[f] + w * alpha * densM * m.Gsqrt[iM];
+      alphP[f] = alphP[f] + w * alpha * densP * m.Gsqrt[iP];
+    }
+}
+
+// atm_dyn_dgm_trcadvect3d_save_massflux (:343-401), called by the dynamics driver in every RK stage before Advance
+// (driver_nonhydro3d.F90:900-917) with tavg_weight_h = b_ex(stage), tavg_weight_v = b_im(stage) (IMEX) or b_ex(stage)
+void trc_save_massflux(Driver& d, int stage) {
+  const Element& e = d.elem; const Mesh& m = d.mesh; const DynState& s = d.st;
+  const size_t nint = size_t(e.Np) * m.Ne, nall = size_t(e.Np) * m.NeA, nf = size_t(e.NfpTot) * m.Ne;
+  const double w_h = d.tint.sc.b_ex[stage], w_v = d.tint.sc.imex ? d.tint.sc.b_im[stage] : d.tint.sc.b_ex[stage];
+  if (stage == 0) {
+    d.MFLX_x.assign(nall, 0.0); d.MFLX_y.assign(nall, 0.0); d.MFLX_z.assign(nall, 0.0);
+    d.alphM_tavg.assign(nf, 0.0); d.alphP_tavg.assign(nf, 0.0);
+    for (size_t i = 0; i < nint; ++i) { d.MFLX_x[i] = w_h * s.MOMX[i]; d.MFLX_y[i] = w_h * s.MOMY[i]; d.MFLX_z[i] = w_v * s.MOMZ[i]; }
+  } else {
+    for (size_t i = 0; i < nint; ++i) {
+      d.MFLX_x[i] = d.MFLX_x[i] + w_h * s.MOMX[i]; d.MFLX_y[i] = d.MFLX_y[i] + w_h * s.MOMY[i]; d.MFLX_z[i] = d.MFLX_z[i] + w_v * s.MOMZ[i];
+    }
+  }
+  trc_cal_alphdens_dyn(e, m, d.cst, s, w_h, w_v, d.hevi, d.alphM_tavg, d.alphP_tavg);
+}
+
+namespace {
+struct TrcInputs { vec MFx, MFy, MFz, DD, DD0, alphM, alphP; };
+// the per-tracer part of AtmDynDGMDriver_trcadv3d_update (driver_trcadv3d.F90:426-539)
+void trc_core(Driver& d, const Element& elem_trcfilter, const RKScheme& sc, double dt, bool modalfilter, bool disable_limiter,
+              bool apply_tmar, TrcInputs& in, double* QTRC, const double* RHOQ_tp) {
   const Element& e = d.elem;
   const Mesh& m = d.mesh;
   DynState& s = d.st;
   const size_t nint = size_t(e.Np) * m.Ne, nall = size_t(e.Np) * m.NeA;
-  vec W, alphM, alphP;
+  vec W;
   trc_face_int_weight(e, W);
-  // mass flux = momentum, density of the tracer step = DDENS (:376-399).  The reference evaluates alphDens on the halo of the
-  // dynamical state as the caller left it; here that halo is made valid first (exchange + boundary condition), so that the
-  // function is defined by its interior inputs alone.
-  vec MFx(s.MOMX), MFy(s.MOMY), MFz(s.MOMZ), DD(s.DDENS), DH(s.DENS_hyd);
-  for (vec* f : {&MFx, &MFy, &MFz, &DD, &DH}) m.exchange_halo(e, f->data());
-  {
-    DynState t = s;
-    t.MOMX = MFx; t.MOMY = MFy; t.MOMZ = MFz; t.DDENS = DD;
-    apply_bc_progvars(e, m, d.bnd, t);                                           // ApplyBC_PROGVARS_lc on the mass fluxes (:408-420)
-    MFx = t.MOMX; MFy = t.MOMY; MFz = t.MOMZ;
-  }
-  trc_cal_alphdens_advtest(e, m, DD.data(), MFx.data(), MFy.data(), MFz.data(), DH.data(), alphM, alphP);
   vec Qtmp(QTRC, QTRC + nall), fct(nall, 1.0), var0(nint), varTmp(nint), tend(nint);
   const int ns = sc.nstage;
   for (int st = 0; st < ns; ++st) {
     m.exchange_halo(e, Qtmp.data());                                             // TRCVAR3D_manager%MeshFieldComm_Exchange
     const double dttmp = dt * sc.GAM(st + 1, st) / sc.SIG(st + 1, st);
-    trc_calc_fct_coef(e, m, W, Qtmp.data(), MFx.data(), MFy.data(), MFz.data(), RHOQ_tp, alphM, alphP, s.DENS_hyd.data(), DD.data(),
-                      DD.data(), sc.c_ex[st], dttmp, disable_limiter, fct.data());
+    trc_calc_fct_coef(e, m, W, Qtmp.data(), in.MFx.data(), in.MFy.data(), in.MFz.data(), RHOQ_tp, in.alphM, in.alphP, s.DENS_hyd.data(),
+                      in.DD.data(), in.DD0.data(), sc.c_ex[st], dttmp, disable_limiter, fct.data());
     m.exchange_halo(e, fct.data());                                              // AUXTRCVAR3D_manager%MeshFieldComm_Exchange
-    trc_cal_tend(e, m, W, Qtmp.data(), MFx.data(), MFy.data(), MFz.data(), alphM, alphP, fct.data(), RHOQ_tp, tend.data());
-    rk_advance_trcvar_low_storage(sc, dt, st, nint, Qtmp.data(), DD.data(), DD.data(), s.DENS_hyd.data(), var0.data(), varTmp.data(),
-                                  tend.data());
-    if (st == ns - 1 && modalfilter) trc_modalfilter(elem_trcfilter, m, s.DENS_hyd.data(), DD.data(), Qtmp.data());
-    if (st == ns - 1 && !disable_limiter) trc_tmar(e, m, s.DENS_hyd.data(), DD.data(), Qtmp.data());
+    trc_cal_tend(e, m, W, Qtmp.data(), in.MFx.data(), in.MFy.data(), in.MFz.data(), in.alphM, in.alphP, fct.data(), RHOQ_tp, tend.data());
+    rk_advance_trcvar_low_storage(sc, dt, st, nint, Qtmp.data(), in.DD.data(), in.DD0.data(), s.DENS_hyd.data(), var0.data(),
+                                  varTmp.data(), tend.data());
+    if (st == ns - 1 && modalfilter) trc_modalfilter(elem_trcfilter, m, s.DENS_hyd.data(), in.DD.data(), Qtmp.data());
+    if (st == ns - 1 && apply_tmar) trc_tmar(e, m, s.DENS_hyd.data(), in.DD.data(), Qtmp.data());   // ONLY_TRACERADV_FLAG and limiter on
   }
-  // QTRC = (DENS_hyd + DDENS_TRC) / (DENS_hyd + DDENS) * QTRC_tmp (:530-537); the two densities coincide in this mode
-  for (size_t i = 0; i < nint; ++i) QTRC[i] = (s.DENS_hyd[i] + DD[i]) / (s.DENS_hyd[i] + s.DDENS[i]) * Qtmp[i];
+  // QTRC = (DENS_hyd + DDENS_TRC) / (DENS_hyd + DDENS) * QTRC_tmp (:530-537): DDENS may have been filtered after DDENS_TRC was taken
+  for (size_t i = 0; i < nint; ++i) QTRC[i] = (s.DENS_hyd[i] + in.DD[i]) / (s.DENS_hyd[i] + s.DDENS[i]) * Qtmp[i];
+}
+// exchange of the mass fluxes + ApplyBC_PROGVARS_lc on them (:404-420)
+void trc_massflux_halo(Driver& d, TrcInputs& in) {
+  const Element& e = d.elem; const Mesh& m = d.mesh;
+  for (vec* f : {&in.MFx, &in.MFy, &in.MFz}) m.exchange_halo(e, f->data());
+  DynState t = d.st;
+  t.MOMX = in.MFx; t.MOMY = in.MFy; t.MOMZ = in.MFz; t.DDENS = in.DD;
+  apply_bc_progvars(e, m, d.bnd, t);
+  in.MFx = t.MOMX; in.MFy = t.MOMY; in.MFz = t.MOMZ;
+}
+}  // namespace
+
+// AtmDynDGMDriver_trcadv3d_update (driver_trcadv3d.F90:312-559) after a dynamics step that accumulated the mass fluxes
+// (Driver::tracer = true): DDENS0_TRC = density at the start of the step, DDENS_TRC = density after the RK loop
+// (driver_nonhydro3d.F90:926-937).  Without the negative fixer and the pressure / specific-heat update that follow in the model.
+void trcadv_update_coupled(Driver& d, const Element& elem_trcfilter, const RKScheme& sc, double dt, bool modalfilter,
+                           bool disable_limiter, double* QTRC, const double* RHOQ_tp) {
+  if (!d.tracer || d.MFLX_x.empty()) throw std::runtime_error("no accumulated mass flux: enable the tracer coupling and run a dynamics step first");
+  TrcInputs in;
+  in.MFx = d.MFLX_x; in.MFy = d.MFLX_y; in.MFz = d.MFLX_z; in.DD = d.DENS_TRC; in.DD0 = d.DENS0_TRC;
+  in.alphM = d.alphM_tavg; in.alphP = d.alphP_tavg;
+  trc_massflux_halo(d, in);
+  trc_core(d, elem_trcfilter, sc, dt, modalfilter, disable_limiter, false, in, QTRC, RHOQ_tp);
+}
+
+// The same with ONLY_TRACERADV_FLAG = .true. (:376-399): the mass flux is the momentum of the (frozen) dynamical state,
+// DDENS_TRC = DDENS0_TRC = DDENS; one tracer QTRC (Np,NeA) advanced by one step.
+void trcadv_update_advtest(Driver& d, const Element& elem_trcfilter, const RKScheme& sc, double dt, bool modalfilter,
+                           bool disable_limiter, double* QTRC, const double* RHOQ_tp) {
+  const Element& e = d.elem;
+  const Mesh& m = d.mesh;
+  DynState& s = d.st;
+  // The reference evaluates alphDens on the halo of the dynamical state as the caller left it; here that halo is made valid first
+  // (exchange + boundary condition), so that the function is defined by its interior inputs alone.
+  TrcInputs in;
+  in.MFx = s.MOMX; in.MFy = s.MOMY; in.MFz = s.MOMZ; in.DD = s.DDENS;
+  vec DH(s.DENS_hyd);
+  m.exchange_halo(e, in.DD.data()); m.exchange_halo(e, DH.data());
+  trc_massflux_halo(d, in);
+  in.DD0 = in.DD;
+  trc_cal_alphdens_advtest(e, m, in.DD.data(), in.MFx.data(), in.MFy.data(), in.MFz.data(), DH.data(), in.alphM, in.alphP);
+  trc_core(d, elem_trcfilter, sc, dt, modalfilter, disable_limiter, !disable_limiter, in, QTRC, RHOQ_tp);
 }
 
 }  // namespace feo

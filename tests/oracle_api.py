@@ -46,6 +46,8 @@ def lib():
         L.feo_sphere_exchange_aux.argtypes = [C.c_void_p]
         L.feo_sphere_update.argtypes = [C.c_void_p, C.c_int]
         L.feo_monitor.argtypes = [C.c_void_p, C.c_void_p]
+        L.feo_set_tracer_coupling.argtypes = [C.c_void_p, C.c_int]
+        L.feo_trcadv_update_coupled.argtypes = [C.c_void_p, C.c_char_p, C.c_double, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.feo_trcadv_update.argtypes = [C.c_void_p, C.c_char_p, C.c_double, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.feo_cal_vi.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_void_p, C.c_void_p]
         L.feo_stage_piece.argtypes = [C.c_void_p, C.c_char_p]
@@ -154,6 +156,17 @@ class Oracle:
         tp = None if rhoq_tp is None else np.ascontiguousarray(rhoq_tp, dtype=np.float64)
         self._chk(lib().feo_trcadv_update(self.h, tinteg.encode(), float(dt), int(nsteps), int(modalfilter is not None), _p(mf),
                                           int(disable_limiter), _p(q), None if tp is None else _p(tp)))
+
+    def set_tracer_coupling(self, on=True):
+        lib().feo_set_tracer_coupling(self.h, int(on))
+
+    def trcadv_update_coupled(self, q, tinteg, dt, modalfilter=None, disable_limiter=False, rhoq_tp=None):
+        """One tracer step with the stage-averaged mass flux of the LAST dynamics step (set_tracer_coupling before update)."""
+        assert q.dtype == np.float64 and q.flags.c_contiguous
+        mf = np.asarray(modalfilter if modalfilter else (0, 0, 0, 0, 0, 0), dtype=np.float64)
+        tp = None if rhoq_tp is None else np.ascontiguousarray(rhoq_tp, dtype=np.float64)
+        self._chk(lib().feo_trcadv_update_coupled(self.h, tinteg.encode(), float(dt), int(modalfilter is not None), _p(mf),
+                                                  int(disable_limiter), _p(q), None if tp is None else _p(tp)))
 
     def prepare(self):
         self._chk(lib().feo_prepare(self.h))
