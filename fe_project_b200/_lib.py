@@ -19,7 +19,7 @@ ABI_SYMBOLS = (
     "fedg_exchange_halo", "fedg_monitor", "fedg_rk_info", "fedg_rk_coef", "fedg_elem_op",
     "fedg_last_timing", "fedg_comm_unique_id", "fedg_comm_init",
     "fedg_set_phy_tend", "fedg_numdiff_init", "fedg_numdiff_apply", "fedg_sponge_init", "fedg_link_halo", "fedg_link_halo_recv", "fedg_link_halo_send", "fedg_group_exchange_halo", "fedg_group_update", "fedg_sparsemat_matmul", "fedg_advect3d_init", "fedg_advect3d_set", "fedg_advect3d_get",
-    "fedg_advect3d_cal_tend", "fedg_advect3d_update",
+    "fedg_advect3d_cal_tend", "fedg_advect3d_update", "fedg_trcadv_init", "fedg_trcadv_update",
 )
 
 
@@ -93,6 +93,8 @@ def load() -> C.CDLL:
     L.fedg_advect3d_get.argtypes = [vp, vp]
     L.fedg_advect3d_cal_tend.argtypes = [vp, vp]
     L.fedg_advect3d_update.argtypes = [vp, ci]
+    L.fedg_trcadv_init.argtypes = [vp, C.c_char_p, cd, ci, vp, vp, ci]
+    L.fedg_trcadv_update.argtypes = [vp, vp, vp, ci]
     _lib = L
     return L
 

@@ -69,6 +69,20 @@ struct AdvectState {
   }
 };
 
+// tracer advection with a prescribed mass flux (fedg_trcadv_*)
+struct TracerState {
+  bool ready = false;
+  RKTable rk;
+  double dt = 0;
+  bool disable_limiter = false, do_filter = false;
+  DevBuf q[2], fct, var0, vartmp, alphM, alphP, rhoq, filt;
+  double w1d[MAXNP] = {0};
+  void release() {
+    for (DevBuf* b : {&q[0], &q[1], &fct, &var0, &vartmp, &alphM, &alphP, &rhoq, &filt}) b->release();
+    ready = false;
+  }
+};
+
 struct fedg_ctx {
   int np = 0, Np = 0, Nfp = 0, NfpTot = 0;
   int Ne = 0, NeA = 0, NeX = 0, NeY = 0, NeZ = 0, Ne2D = 0, Nhalo = 0;
@@ -117,6 +131,7 @@ struct fedg_ctx {
   // interior nodes of this mesh that feed a halo face of a mesh on another rank (fedg_link_halo_send)
   struct OutMsg { int peer = -1, msg_id = 0, cnt = 0; int* d_idx = nullptr; double* sendbuf = nullptr; };
   std::vector<OutMsg> outmsg;
+  TracerState trc;
   int xbuf = 0;                    // buffer that holds the state other local meshes gather from (stage input of the explicit part)
   struct { int i0, in, mid, nxt; } hs{0, 0, 0, 0};   // buffer cursor of the HEVI stage pieces
   // timing
@@ -125,6 +140,7 @@ struct fedg_ctx {
   double last_ms_total = 0, last_ms_stage = 0; long last_launches = 0;
   ~fedg_ctx() {
     for (auto& e : ev) cudaEventDestroy(e);
+    trc.release();
     for (auto& l : link) { if (l.d_src) cudaFree(l.d_src); if (l.d_rot) cudaFree(l.d_rot); if (l.recvbuf) cudaFree(l.recvbuf); }
     for (auto& m : outmsg) { if (m.d_idx) cudaFree(m.d_idx); if (m.sendbuf) cudaFree(m.sendbuf); }
     if (d_vmapP) cudaFree(d_vmapP);
@@ -1535,5 +1551,97 @@ extern "C" int fedg_sponge_init(fedg_ctx* c, double sl_wdamp_tau, double sl_wdam
   CUDA_TRY(cudaGetLastError());
   c->sponge_h = sl_horiveldamp_flag ? 1.0 : 0.0;
   c->has_sponge = true;
+  return FEDG_OK;
+}
+
+// ---- tracer advection with a prescribed mass flux (row f4; NOT yet validated on hardware, see tracer.cu) ------------------
+extern "C" int fedg_trcadv_init(fedg_ctx* c, const char* tinteg_type, double dt, int modalfilter_flag, const double* filter_h1D,
+                                const double* filter_v1D, int disable_limiter) {
+  if (!c || !tinteg_type) return fail(FEDG_ERR_ARG, "null argument");
+  TracerState& t = c->trc;
+  t.release();
+  if (!t.rk.init(tinteg_type)) return fail(FEDG_ERR_ARG, std::string("unsupported TINTEG_TYPE ") + tinteg_type);
+  if (t.rk.imex || !t.rk.low_storage) return fail(FEDG_ERR_UNSUPPORTED, "the tracer integrator takes the low-storage explicit schemes (Advance_trcvar)");
+  if (!(dt > 0.0)) return fail(FEDG_ERR_ARG, "dt must be positive");
+  if (c->terrain || c->global) return fail(FEDG_ERR_UNSUPPORTED, "tracer advection is available on the flat regional mesh only");
+  if (c->comm.active && c->comm.nremote > 0) return fail(FEDG_ERR_UNSUPPORTED, "tracer advection runs on a single tile");
+  if (c->np != 4 && c->np != 8) return fail(FEDG_ERR_UNSUPPORTED, "tracer advection: p = 3 or p = 7");
+  if (!c->aux_ready) return fail(FEDG_ERR_STATE, "fedg_set_aux must be called first (DENS_hyd)");
+  t.dt = dt; t.disable_limiter = disable_limiter != 0; t.do_filter = modalfilter_flag != 0;
+  const int np = c->np;
+  std::vector<double> f(size_t(2) * np * np, 0.0);
+  for (int i = 0; i < np; ++i) f[i * np + i] = f[np * np + i * np + i] = 1.0;
+  if (t.do_filter) {
+    if (!filter_h1D || !filter_v1D) return fail(FEDG_ERR_ARG, "modal filter matrices missing");
+    for (int i = 0; i < np; ++i)
+      for (int l = 0; l < np; ++l) { f[i * np + l] = filter_h1D[i + l * np]; f[np * np + i * np + l] = filter_v1D[i + l * np]; }   // column-major in
+  }
+  CUDA_TRY(t.filt.alloc(f.size()));
+  CUDA_TRY(cudaMemcpy(t.filt.p, f.data(), f.size() * sizeof(double), cudaMemcpyHostToDevice));
+  // 1D LGL weights from IntWeight_lgl(i,1,1) = w(i) w(1)^2 and sum_i w(i) = 2
+  std::vector<double> w3(np);
+  CUDA_TRY(cudaMemcpy(w3.data(), c->w3.p, np * sizeof(double), cudaMemcpyDeviceToHost));
+  double sum = 0.0;
+  for (int i = 0; i < np; ++i) sum += w3[i];
+  for (int i = 0; i < np; ++i) t.w1d[i] = w3[i] * 2.0 / sum;
+  for (auto& b : t.q) CUDA_TRY(b.alloc(c->nall));
+  CUDA_TRY(t.fct.alloc(c->nall));
+  CUDA_TRY(t.rhoq.alloc(c->nall));
+  CUDA_TRY(t.var0.alloc(c->nint));
+  CUDA_TRY(t.vartmp.alloc(c->nint));
+  CUDA_TRY(t.alphM.alloc(size_t(c->NfpTot) * c->Ne));
+  CUDA_TRY(t.alphP.alloc(size_t(c->NfpTot) * c->Ne));
+  t.ready = true;
+  return FEDG_OK;
+}
+
+extern "C" int fedg_trcadv_update(fedg_ctx* c, double* QTRC, const double* RHOQ_tp, int nsteps) {
+  if (!c || !QTRC || nsteps < 0) return fail(FEDG_ERR_ARG, "bad argument");
+  TracerState& t = c->trc;
+  if (!t.ready) return fail(FEDG_ERR_STATE, "fedg_trcadv_init must be called first");
+  ensure_tables(c);
+  const int cur = c->cur;
+  ensure_dp(c, cur);
+  fill_halo(c, cur, true);           // halo + boundary condition of the state whose momentum is the mass flux (driver_trcadv3d.F90:404-420)
+  CUDA_TRY(cudaMemcpyAsync(t.q[0].p, QTRC, c->nint * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  if (RHOQ_tp) CUDA_TRY(cudaMemcpyAsync(t.rhoq.p, RHOQ_tp, c->nint * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  TracerParams P{};
+  P.mfx = c->prog[cur][V_MOMX].p; P.mfy = c->prog[cur][V_MOMY].p; P.mfz = c->prog[cur][V_MOMZ].p;
+  P.ddens = c->prog[cur][V_DDENS].p; P.ddens0 = c->prog[cur][V_DDENS].p; P.dens_hyd = c->dens_hyd.p;
+  P.alphM = t.alphM.p; P.alphP = t.alphP.p; P.fct = t.fct.p; P.rhoq_tp = RHOQ_tp ? t.rhoq.p : nullptr;
+  P.var0 = t.var0.p; P.vartmp = t.vartmp.p;
+  P.escale = c->escale.p; P.fscale = c->fscale.p; P.jac = c->Jac.p; P.w3 = c->w3.p; P.vmapP = c->d_vmapP; P.tab = c->d_tab; P.filt = t.filt.p;
+  for (int i = 0; i < MAXNP; ++i) P.w1d[i] = t.w1d[i];
+  P.Np = c->Np; P.Nfp = c->Nfp; P.NfpTot = c->NfpTot; P.np = c->np; P.Ne = c->Ne;
+  P.disable_limiter = t.disable_limiter;
+  const RKTable& rk = t.rk;
+  const int ns = rk.nstage;
+  const double EPS = 2.220446e-16;
+  P.q = t.q[0].p;
+  { cudaError_t e = launch_trc_alphdens(P, c->stream); if (e != cudaSuccess) return fail(FEDG_ERR_CUDA, cudaGetErrorString(e)); }
+  int in = 0;
+  for (int step = 0; step < nsteps; ++step)
+    for (int st = 0; st < ns; ++st) {
+      P.q = t.q[in].p; P.qout = t.q[in ^ 1].p;
+      P.stage = st; P.nstage = ns;
+      P.sig_ss = rk.sg(st + 1, st); P.gam_ss = t.dt * rk.gm(st + 1, st);
+      P.sig_Ns = rk.sg(ns, st); P.gam_Ns = t.dt * rk.gm(ns, st);
+      P.upd_vartmp = (std::fabs(P.sig_Ns) > EPS || std::fabs(rk.gm(ns, st)) > EPS) ? 1 : 0;
+      double c0 = 0.0, c1 = 0.0;
+      for (int j = 0; j < ns; ++j) { c0 += rk.aex(st, j); if (st + 1 < ns) c1 += rk.aex(st + 1, j); }
+      P.c_ssm1 = c0; P.c_ss = c1;
+      P.dttmp = t.dt * rk.gm(st + 1, st) / rk.sg(st + 1, st);
+      P.do_filter = (st == ns - 1 && t.do_filter) ? 1 : 0;
+      P.do_tmar = (st == ns - 1 && !t.disable_limiter) ? 1 : 0;
+      if (c->Nhalo > 0) aux_halo_kernel<<<(c->Nhalo + 255) / 256, 256, 0, c->stream>>>(t.q[in].p, c->d_halo_src, int(c->nint), c->Nhalo);
+      { cudaError_t e = launch_trc_fct(P, c->stream); if (e != cudaSuccess) return fail(FEDG_ERR_CUDA, cudaGetErrorString(e)); }
+      if (c->Nhalo > 0) aux_halo_kernel<<<(c->Nhalo + 255) / 256, 256, 0, c->stream>>>(t.fct.p, c->d_halo_src, int(c->nint), c->Nhalo);
+      { cudaError_t e = launch_trc_stage(P, c->stream); if (e != cudaSuccess) return fail(FEDG_ERR_CUDA, cudaGetErrorString(e)); }
+      in ^= 1;
+    }
+  CUDA_TRY(cudaMemcpyAsync(QTRC, t.q[in].p, c->nint * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  CUDA_TRY(cudaGetLastError());
+  if (in != 0) std::swap(t.q[0], t.q[1]);
   return FEDG_OK;
 }

@@ -116,6 +116,30 @@ struct LinCombParams {
   int nterm;
   size_t n;
 };
+// tracer advection with a prescribed mass flux (tracer.cu; row f4)
+struct TracerParams {
+  const double* q;             // stage input (Np*Ne + halo), halo filled
+  double* qout;
+  const double *mfx, *mfy, *mfz;          // mass flux = momentum of the dynamical state (halo + boundary condition applied)
+  const double *ddens, *ddens0, *dens_hyd;
+  double *alphM, *alphP;       // (NfpTot, Ne)
+  double* fct;                 // FCT coefficient (Np*Ne + halo)
+  const double* rhoq_tp;       // physics tendency of rho*q, may be NULL
+  double *var0, *vartmp;       // work arrays of the tracer integrator (Np*Ne)
+  const double *escale, *fscale, *jac, *w3;
+  const int* vmapP;
+  const ElemTables* tab;
+  const double* filt;          // tracer modal filter [2][np*np] row-major: horizontal, vertical
+  double w1d[MAXNP];           // 1D LGL weights (surface quadrature of FaceIntMat)
+  double sig_ss, gam_ss, sig_Ns, gam_Ns, c_ssm1, c_ss, dttmp;
+  int stage, nstage, upd_vartmp;
+  int disable_limiter, do_filter, do_tmar;
+  int Np, Nfp, NfpTot, np, Ne;
+};
+cudaError_t launch_trc_alphdens(const TracerParams& P, cudaStream_t s);
+cudaError_t launch_trc_fct(const TracerParams& P, cudaStream_t s);
+cudaError_t launch_trc_stage(const TracerParams& P, cudaStream_t s);
+
 // sample/advect3d stage (advect3d.cu)
 struct AdvectParams {
   const double *q, *u, *v, *w;   // stage input (Np*Ne + Nhalo), halo filled

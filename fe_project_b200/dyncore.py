@@ -157,6 +157,24 @@ class AtmDynDGMDriver_nonhydro3d:
         self._nd_tb = tb
         _lib.check(self.L.fedg_numdiff_init(self.h, int(ND_LAPLACIAN_NUM), float(ND_COEF_h), float(ND_COEF_v), _ptr(tb), int(apply_in_update)))
 
+    # ---- tracer advection with a prescribed mass flux (row f4; see csrc/tracer.cu for its validation status) ----
+    def trcadv_init(self, TINTEG_TYPE: str, TIME_DT: float, MODALFILTER_FLAG: bool = False, MF_ETAC_h=0.0, MF_ALPHA_h=1.0, MF_ORDER_h=16,
+                    MF_ETAC_v=0.0, MF_ALPHA_v=1.0, MF_ORDER_v=16, disable_limiter: bool = False):
+        """AtmDynDGMDriver_trcadv3d with ONLY_TRACERADV_FLAG: the mass flux is the momentum of the registered state."""
+        fh = fv = None
+        if MODALFILTER_FLAG:
+            fh = _f64(self.elem.filter1d(MF_ETAC_h, MF_ALPHA_h, MF_ORDER_h).T)
+            fv = _f64(self.elem.filter1d(MF_ETAC_v, MF_ALPHA_v, MF_ORDER_v).T)
+        _lib.check(self.L.fedg_trcadv_init(self.h, TINTEG_TYPE.encode(), float(TIME_DT), int(bool(MODALFILTER_FLAG)), _ptr(fh), _ptr(fv),
+                                           int(bool(disable_limiter))))
+
+    def trcadv_update(self, q, nsteps: int = 1, rhoq_tp=None):
+        """q: (Np*NeA,) host array, interior advanced in place."""
+        q = self._chk_field(q)
+        tp = None if rhoq_tp is None else self._chk_field(rhoq_tp)
+        _lib.check(self.L.fedg_trcadv_update(self.h, _ptr(q), _ptr(tp), int(nsteps)))
+        return q
+
     def sponge_init(self, SL_WDAMP_TAU=-1.0, SL_WDAMP_HEIGHT=-1.0, SL_WDAMP_LAYER=-1, SL_HORIVELDAMP_FLAG=False):
         """PARAM_ATMOS_DYN_SPONGELAYER (scale_atm_dyn_dgm_spongelayer.F90:55-118)."""
         _lib.check(self.L.fedg_sponge_init(self.h, float(SL_WDAMP_TAU), float(SL_WDAMP_HEIGHT), int(SL_WDAMP_LAYER), int(SL_HORIVELDAMP_FLAG)))

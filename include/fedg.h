@@ -232,6 +232,17 @@ int fedg_group_exchange_halo(fedg_ctx** ctxs, int n, int apply_bc);
  * see the neighbours' stage state.  HEVI equation sets. */
 int fedg_group_update(fedg_ctx** ctxs, int n, int nsteps);
 
+/* ---- tracer advection with a prescribed mass flux --------------------------------------------
+ * AtmDynDGMDriver_trcadv3d_update with ONLY_TRACERADV_FLAG = .true. (fluid_dyn_solver/scale_atm_dyn_dgm_driver_trcadv3d.F90:312-559;
+ * kernels of scale_atm_dyn_dgm_trcadvect3d_heve.F90:149-777): the mass flux is the momentum of the state registered with
+ * fedg_set_prog, DDENS_TRC = DDENS0_TRC = DDENS.  FCT coefficient + TMAR limiters unless disable_limiter, tracer modal filter
+ * (1D matrices as in fedg_dyn_init) at the last stage; low-storage explicit schemes (Advance_trcvar).  Flat regional mesh, one
+ * tile, p = 3 or 7.  STATUS: checked against the CPU restatement in design, not yet run on hardware (tests marked accordingly).
+ * fedg_trcadv_update: QTRC (Np, NeA) host array, its (Np, Ne) interior advanced in place by nsteps; RHOQ_tp may be NULL. */
+int fedg_trcadv_init(fedg_ctx* ctx, const char* tinteg_type, double dt, int modalfilter_flag, const double* filter_h1D,
+                     const double* filter_v1D, int disable_limiter);
+int fedg_trcadv_update(fedg_ctx* ctx, double* QTRC, const double* RHOQ_tp, int nsteps);
+
 /* ---- sample/advect3d (BASELINE config 1) --------------------------------------------------------------
  * `sparsemat` in ELL storage as the reference holds it (common/scale_sparsemat.F90:33-55, 100-250):
  * val(M*col_size), colIdx(M*col_size), slot-major l = i + (k-1)*M (:172), colIdx 1-based. */
