@@ -35,9 +35,8 @@ def emit(line: dict):
 
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
-for _p in (ROOT, os.path.join(ROOT, "tests")):
-    if _p not in sys.path:
-        sys.path.insert(0, _p)
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
 
 import numpy as np  # noqa: E402
 
@@ -117,42 +116,64 @@ class ClockSampler:
         return out
 
 
-def oracle_sample(threads=None, target_s=12.0):
-    """Times the CPU oracle on a bounded sample: same equations/scheme/filter, 16x8x8 p=7 elements."""
-    from cases import DensityCurrentCase
-    if threads:
-        os.environ["OMP_NUM_THREADS"] = str(threads)
-    case = DensityCurrentCase(p=7, NeX=16, NeY=8, NeZ=8, dom=(0.0, 12.8e3, 0.0, 6.4e3, 0.0, 3.2e3), dt=WORKLOAD["dt"],
-                              tinteg=WORKLOAD["tinteg"], modalfilter=True)
-    o = case.make_oracle()
-    o.update(1)
-    t0 = time.perf_counter(); o.update(2); t1 = (time.perf_counter() - t0) / 2
-    nsteps = int(max(3, min(200, target_s / max(t1, 1e-6))))
-    t0 = time.perf_counter(); o.update(nsteps); dt = time.perf_counter() - t0
+def _oracle_modules():
+    """The CPU oracle (oracle/, test infrastructure) is imported by the two CPU timing legs only (cpu_baseline, --impl reference),
+    in its timing build (-O3, FMA contraction on; oracle/Makefile)."""
+    os.environ["FEO_VARIANT"] = "perf"
+    od = os.path.join(ROOT, "oracle")
+    if od not in sys.path:
+        sys.path.insert(0, od)
+    import oracle_api
+    import oracle_cases
+    return oracle_api, oracle_cases
+
+
+def workload_case(args, hevi=False, tiles=(1, 1), tile=(0, 0)):
+    from fe_project_b200.cases import DensityCurrentCase
+    NX, NY = tiles
+    x0, x1, y0, y1, z0, z1 = WORKLOAD["dom"]
+    dom = (x0, x0 + (x1 - x0) * NX, y0, y0 + (y1 - y0) * NY, z0, z1)
+    return DensityCurrentCase(p=WORKLOAD["p"], NeX=args.nex, NeY=args.ney, NeZ=args.nez, dom=dom,
+                              dt=(2.0 * WORKLOAD["dt"] if hevi else WORKLOAD["dt"]), tinteg=("IMEX_ARK324" if hevi else WORKLOAD["tinteg"]),
+                              modalfilter=True, NprcX=NX, NprcY=NY, pi=tile[0], pj=tile[1],
+                              eqs=("NONHYDRO3D_HEVI" if hevi else "NONHYDRO3D_HEVE"))
+
+
+def oracle_timed(case, warmup=1, steps=None, target_s=12.0, threads=None):
+    """Times the CPU oracle on the SAME configuration as the GPU arm (one tile of it), all host threads: `steps` steps, or as many
+    as fit into about target_s seconds (at least 3)."""
+    oracle_api, oracle_cases = _oracle_modules()
+    cores = threads or os.cpu_count() or 1
+    used = oracle_api.lib().feo_set_num_threads(cores)      # explicit: torchrun exports OMP_NUM_THREADS=1
+    o = oracle_cases.make_oracle_regional(case)
+    t0 = time.perf_counter(); o.update(max(1, warmup)); t1 = (time.perf_counter() - t0) / max(1, warmup)
+    n = steps if steps else int(max(3, min(200, target_s / max(t1, 1e-6))))
+    t0 = time.perf_counter(); o.update(n); dt = time.perf_counter() - t0
     dof = 5 * case.elem.Np * case.mesh.Ne
-    return dict(value=dof * nsteps / dt, steps=nsteps, seconds=dt,
-                sample=f"density current 16x8x8 elements p=7 ({dof} DOF), {nsteps} steps of ERK_SSP_4s3o + modal filter")
+    m = case.mesh
+    return dict(value=dof * n / dt, steps=n, seconds=dt, cores=used, lib=oracle_api._variant_so(),
+                sample=f"the bench configuration itself, one tile: density current {m.NeX}x{m.NeY}x{m.NeZ} elements p={case.p} ({dof} DOF), "
+                       f"{n} steps of {case.tinteg} ({case.eqs}) + modal filter, {used} OpenMP threads, {oracle_api._variant_so()}")
 
 
 def run_reference(args, rank, world):
+    """CPU arm: the reference-equivalent C++ restatement (the Fortran reference needs gfortran + MPI + SCALE 5.5.5, none of which exist
+    in this image) on the bench configuration, all host threads, timing build."""
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
-    vals = []
-    for _ in range(max(1, args.warmup and 1)):
-        pass
-    K = max(1, min(args.steps, 3))
-    for _ in range(K):
-        vals.append(oracle_sample(threads=cores, target_s=8.0))
-    best = max(vals, key=lambda r: r["value"])
-    line = dict(metric=METRIC, value=best["value"], unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
-                ms_per_step=1e3 * best["seconds"] / best["steps"], higher_is_better=True, scaling="weak", vs_baseline=None,
+    hevi = args.eqs == "hevi"
+    case = workload_case(args, hevi=hevi)
+    W, K = max(1, min(args.warmup, 3)), max(3, min(args.steps, 40 if not hevi else 10))
+    r = oracle_timed(case, warmup=W, steps=K)
+    line = dict(metric=METRIC, value=r["value"], unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
+                ms_per_step=1e3 * r["seconds"] / r["steps"], higher_is_better=True, scaling="weak", vs_baseline=None,
                 dtype="f64", data="synthetic", impl="reference",
-                config=dict(workload=f"{WORKLOAD['name']} (bounded sample of 32x32x16 p=7, HEVE, ERK_SSP_4s3o)"),
-                cpu_baseline=dict(value=best["value"], unit=UNIT, cores=cores, kind="port", sample=best["sample"]),
-                e2e=dict(value=best["value"], unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0),
-                note="CPU oracle = reference-equivalent C++ restatement (g++ -O3 -fopenmp); the Fortran reference "
-                     "needs gfortran+MPI+SCALE 5.5.5, none of which exist in this image")
+                config=dict(workload=f"{WORKLOAD['name']}, {args.nex}x{args.ney}x{args.nez} elements p=7, {case.eqs}, {case.tinteg}, "
+                                     f"dt={case.dt}, modal filter on (the GPU arm's configuration; {r['steps']} timed steps)"),
+                cpu_baseline=dict(value=r["value"], unit=UNIT, cores=r["cores"], kind="port", sample=r["sample"]),
+                e2e=dict(value=r["value"], unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+                note="CPU oracle = reference-equivalent C++ restatement, timing build (g++ -O3 -ffp-contract=fast -fopenmp, "
+                     f"{r['lib']}); the Fortran reference needs gfortran+MPI+SCALE 5.5.5, none of which exist in this image")
     emit(line)
 
 
@@ -187,7 +208,8 @@ def run_advect3d(args):
     nbytes = 4 * q.size * 8
     cpu = None
     if not args.no_cpu_baseline:
-        from oracle_api import Oracle, OracleAdvect3D
+        oracle_api, _ = _oracle_modules()
+        Oracle, OracleAdvect3D = oracle_api.Oracle, oracle_api.OracleAdvect3D
         o = Oracle(3, *ne, (0, 1, 0, 1, 0, 1), periodic=(True, True, True))
         a = OracleAdvect3D(o, "ERK_4s4o", 0.008)
         a.arr("q")[:] = q.reshape(-1)
@@ -239,7 +261,7 @@ def run_sphere(args, rank=0, world=1, local_rank=0):
             obj = [raw]
             dist.broadcast_object_list(obj, src=0)
             return obj[0]
-    from cases import GlobalSphereCase
+    from fe_project_b200.cases import GlobalSphereCase
     from fe_project_b200.dyncore import PROG_NAMES
     ne, nez = (args.nex if args.nex != WORKLOAD["NeX"] else 32), (args.nez if args.nez != WORKLOAD["NeZ"] else 12)
     from fe_project_b200.cubedsphere import panel_owner
@@ -343,9 +365,8 @@ def main():
         dist = dist_
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    from cases import DensityCurrentCase
     from fe_project_b200.setup_aux import calc_phyd_hgrad
-    from fe_project_b200.dyncore import PROG_NAMES
+    from fe_project_b200.dyncore import PROG_NAMES, rk_tables
 
     W = max(3, args.warmup)
     K = args.steps
@@ -353,19 +374,14 @@ def main():
     # mod_atmos_mesh_rm.F90:104-106); the domain grows with the tile count
     NX, NY = {1: (1, 1), 2: (2, 1), 4: (2, 2), 8: (4, 2)}.get(world, (world, 1))
     pi, pj = rank % NX, rank // NX
-    x0, x1, y0, y1, z0, z1 = WORKLOAD["dom"]
-    dom = (x0, x0 + (x1 - x0) * NX, y0, y0 + (y1 - y0) * NY, z0, z1)
     hevi = args.eqs == "hevi" or args.workload != "density_current"
     wl_name = WORKLOAD["name"]
     if args.workload == "density_current":
-        case = DensityCurrentCase(p=WORKLOAD["p"], NeX=args.nex, NeY=args.ney, NeZ=args.nez, dom=dom,
-                                  dt=(2.0 * WORKLOAD["dt"] if hevi else WORKLOAD["dt"]), tinteg=("IMEX_ARK324" if hevi else WORKLOAD["tinteg"]),
-                                  modalfilter=True, NprcX=NX, NprcY=NY, pi=pi, pj=pj,
-                                  eqs=("NONHYDRO3D_HEVI" if hevi else "NONHYDRO3D_HEVE"))
+        case = workload_case(args, hevi=hevi, tiles=(NX, NY), tile=(pi, pj))
     else:
         if world > 1:
             raise SystemExit("the extra workloads are single-GPU measurement lines")
-        from cases import SoundWaveCase, GlobalPanelCase
+        from fe_project_b200.cases import SoundWaveCase, GlobalPanelCase
         if args.workload == "sound_wave":     # configs[1]: sample/euler3d_hevi, rate variant 16x16x16
             args.nex = args.ney = args.nez = 16
             case = SoundWaveCase(p=7, NeX=16, NeY=16, NeZ=16, dt=0.015, tinteg="IMEX_ARK232", amplitude=1.0e-3)
@@ -397,66 +413,105 @@ def main():
         d.set_phyd_hgrad(gx, gy)
     Np, Ne = case.elem.Np, case.mesh.Ne
     dof = 5 * Np * Ne * world
+    nstage = rk_tables(case.tinteg)["nstage"]
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist:
+            dist.barrier()
+
+    def max_over_ranks(x):
+        if not dist:
+            return x
+        t = torch.tensor([x], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
 
     d.Update(W)
-    torch.cuda.synchronize()
-    if dist:
-        dist.barrier()
+    barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
     sampler.wait_started()
-    d.Update(K)
-    torch.cuda.synchronize()
-    tm = d.last_timing()
+    # The timed region is EXACTLY K steps between two barriers, CUDA events on the launching stream, max over ranks.  It is repeated
+    # (R regions, every one timed the same way) until about a second of GPU time has passed, so that the clock sampler sees the
+    # load; the reported region is the MEDIAN one.
+    regions = []
+    t_wall0 = time.perf_counter()
+    while True:
+        barrier()
+        d.Update(K)
+        torch.cuda.synchronize()
+        tm = d.last_timing()
+        regions.append((max_over_ranks(tm["ms_total"]), tm["ms_stage_kernels"], tm["launches"]))
+        stop = (time.perf_counter() - t_wall0 >= 1.0 and len(regions) >= 3) or len(regions) >= 200
+        if dist:       # every rank takes the same decision
+            t = torch.tensor([1.0 if stop else 0.0], device="cuda"); dist.broadcast(t, src=0); stop = bool(t.item() > 0.5)
+        if stop:
+            break
     clocks = sampler.stop()
-    if dist:
-        dist.barrier()
-    ms_total = tm["ms_total"]
-    if dist:
-        t = torch.tensor([ms_total], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total = float(t.item())
+    barrier()
+    order = sorted(range(len(regions)), key=lambda i: regions[i][0])
+    ms_total, ms_stage_sum, launches = regions[order[len(order) // 2]]
     value = dof * K / (ms_total * 1e-3)
-    from fe_project_b200.dyncore import rk_tables
-    nstage = rk_tables(case.tinteg)["nstage"]
     n_regions = K * nstage                      # one event-bracketed region per stage: the dominant kernel
-    ms_stage = tm["ms_stage_kernels"] / max(1, n_regions)
+    ms_stage = ms_stage_sum / max(1, n_regions)
     peak, peak_src = read_peaks()
     alg_bytes = ALG_BYTES_PER_NODE_STAGE * Np * Ne
     achieved = alg_bytes / (ms_stage * 1e-3) / 1e9
-    traffic = None
+    traffic, traffic_src = None, None
     tpath = os.path.join(ROOT, "profiles", "heve_stage_traffic.json")
-    if os.path.exists(tpath):
+    if os.path.exists(tpath) and not hevi and args.workload == "density_current" and (args.nex, args.ney, args.nez) == (32, 32, 16):
         with open(tpath) as f:
             traffic = json.load(f).get("dram_bytes_per_launch")
+        traffic_src = "ncu --set full capture of this kernel at this size, profiles/heve_stage_traffic.json (not measured in this run)"
     state = d.get_prog()
     finite = all(np.isfinite(state[k][:Np * Ne]).all() for k in PROG_NAMES)
 
-    # ---- e2e: host buffers in, host buffers out, one step per call
+    # ---- e2e: the reference-facing entry point with HOST buffers.  One dynamics step per call; pinned host arrays; the upload of the
+    # step's five input fields and the download of its five output fields are inside the timed region.  The caller double-buffers
+    # (two sets of host arrays = two tiles / ensemble members / the physics side working on the other set): call n + 1 is issued before
+    # call n is waited for, so PCIe runs in both directions at once (fedg_dyn_update_host_async / _wait).  The blocking single call
+    # (fedg_dyn_update_host) is reported next to it.
     nall = d.n_field
-    pinned = {k: torch.empty(nall, dtype=torch.float64).pin_memory() for k in PROG_NAMES}
-    host = {k: pinned[k].numpy() for k in PROG_NAMES}
-    for k in PROG_NAMES:
-        host[k][:] = case.fields[k].reshape(-1)
-    d.Update_host(host, 1)
-    ne2e = 5
+    sets = []
+    for _ in range(2):
+        pin = {k: torch.empty(nall, dtype=torch.float64).pin_memory() for k in PROG_NAMES}
+        pout = {k: torch.empty(nall, dtype=torch.float64).pin_memory() for k in PROG_NAMES}
+        hin, hout = {k: pin[k].numpy() for k in PROG_NAMES}, {k: pout[k].numpy() for k in PROG_NAMES}
+        for k in PROG_NAMES:
+            hin[k][:] = case.fields[k].reshape(-1)
+        sets.append((pin, pout, hin, hout))
+    d.Update_host(sets[0][2], 1)
+    ncall = 12
+    barrier()
     t0 = time.perf_counter()
-    for _ in range(ne2e):
-        d.Update_host(host, 1)
+    for i in range(ncall):
+        s_ = i % 2
+        if i >= 2:
+            d.Update_host_wait(s_)
+        d.Update_host_async(sets[s_][2], sets[s_][3], 1, slot=s_)
+    d.Update_host_wait(0); d.Update_host_wait(1)
     torch.cuda.synchronize()
-    t_e2e = (time.perf_counter() - t0) / ne2e
-    if dist:
-        t = torch.tensor([t_e2e], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        t_e2e = float(t.item())
-    nbytes = 5 * Np * Ne * 8          # fedg_dyn_update_host moves the (Np, Ne) interior of the five variables each way
-    e2e = dict(value=dof / t_e2e, unit=UNIT, h2d_bytes_per_step=nbytes, d2h_bytes_per_step=nbytes, steps_per_call=1)
+    t_pipe = max_over_ranks((time.perf_counter() - t0) / ncall)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(4):
+        d.Update_host(sets[0][2], 1)
+    torch.cuda.synchronize()
+    t_block = max_over_ranks((time.perf_counter() - t0) / 4)
+    e2e_finite = all(np.isfinite(sets[s_][3][k][:Np * Ne]).all() for s_ in range(2) for k in PROG_NAMES)
+    nbytes = 5 * Np * Ne * 8          # the (Np, Ne) interior of the five variables travels each way
+    e2e = dict(value=dof / t_pipe, unit=UNIT, h2d_bytes_per_step=nbytes, d2h_bytes_per_step=nbytes, steps_per_call=1,
+               mode="fedg_dyn_update_host_async/_wait, two host buffer sets in flight (upload, step and download of consecutive calls overlap)",
+               blocking_call_value=dof / t_block, ms_per_call=t_pipe * 1e3, ms_per_blocking_call=t_block * 1e3, finite=bool(e2e_finite))
 
     if rank == 0:
         cpu = None
         if not args.no_cpu_baseline:
-            r = oracle_sample(threads=os.cpu_count(), target_s=12.0)
-            cpu = dict(value=r["value"], unit=UNIT, cores=os.cpu_count(), kind="port", sample=r["sample"])
+            ccase = case if world == 1 and args.workload == "density_current" else workload_case(args, hevi=hevi)
+            r = oracle_timed(ccase, warmup=1, target_s=12.0)
+            cpu = dict(value=r["value"], unit=UNIT, cores=r["cores"], kind="port", sample=r["sample"])
+        vi_flops_ref, vi_flops_exec = 15.1e3 * Ne * 64, 11.0e3 * Ne * 64
         line = dict(
             metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=K, warmup=W, ms_per_step=ms_total / K,
             higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64", data="synthetic",
@@ -464,20 +519,23 @@ def main():
                                  f"{case.tinteg}, dt={case.dt}, modal filter {'on' if case.modalfilter else 'off'}, tiles {NX}x{NY}",
                         dof=dof, l2_policy="inputs larger than L2 (67 MB per field, >1 GB touched per stage)",
                         specialisation="flat mesh (Gsqrt=1, GI3=0) and dry thermodynamics detected at registration; "
-                                       "roofline uses the unspecialised 232 B/node/stage"),
-            clocks=clocks, e2e=e2e, gpu_launches=tm["launches"],
-            roofline=(dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak, traffic=traffic,
+                                       "roofline uses the unspecialised 232 B/node/stage",
+                        timed_regions=len(regions), region_ms=[round(regions[i][0], 4) for i in order[:1] + order[len(order) // 2:len(order) // 2 + 1] + order[-1:]],
+                        halo=("direct peer memory (pack kernel stores into the neighbour's halo staging area over NVLink, flag per face)"
+                              if world > 1 and os.environ.get("FEDG_HALO", "") != "nccl" else ("NCCL send/recv" if world > 1 else "none"))),
+            clocks=clocks, e2e=e2e, gpu_launches=launches,
+            roofline=(dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak, traffic=traffic, traffic_source=traffic_src,
                            kernel="stage_p7_kernel<flat,dry,HEVE> (DMMA contractions, TMA-staged inputs and z-face neighbours)", ms_per_launch=ms_stage,
                            algorithmic_bytes_per_launch=alg_bytes, peak_source=peak_src) if not hevi else
-                      # vertical-implicit column solve: FP64 bound.  Algorithmic flops of the reference algorithm per
-                      # column-element: 24x24 LU 9.2 kflop + 4 RHS substitutions 4.6 kflop + coupling
-                      # elimination 0.6 kflop + the 8x8 (u,v) system 0.7 kflop = 15.1 kflop.  The kernel eliminates DDENS
-                      # first and pivots on the 16x16 remainder: 11.0 kflop per column-element (reduced_flops_per_launch);
-                      # ms_per_launch averages the implicit stages and the explicit-evaluation stage of the scheme
-                      dict(bound="fp64", achieved=15.1e3 * Ne * 64 / (ms_stage * 1e-3) / 1e12, peak=34.07, unit="TFLOP/s",
-                           frac=15.1e3 * Ne * 64 / (ms_stage * 1e-3) / 1e12 / 34.07, traffic=None,
-                           kernel="vi_column_kernel (DDENS eliminated, 16x16 partial-pivot Gauss-Jordan, block-Thomas)", ms_per_launch=ms_stage,
-                           algorithmic_flops_per_launch=15.1e3 * Ne * 64, reduced_flops_per_launch=11.0e3 * Ne * 64,
+                      # vertical-implicit column solve: FP64 bound.  achieved / frac use the flops the kernel EXECUTES per column-element
+                      # (DDENS eliminated first, 16x16 partial-pivot Gauss-Jordan with four right-hand sides: 11.0 kflop); the reference
+                      # algorithm's count (24x24 LU 9.2 k + substitutions 4.6 k + coupling 0.6 k + (u,v) 0.7 k = 15.1 kflop) is
+                      # reported next to it.  ms_per_launch averages the implicit stages and the explicit-evaluation stage of the scheme
+                      dict(bound="fp64", achieved=vi_flops_exec / (ms_stage * 1e-3) / 1e12, peak=34.07, unit="TFLOP/s",
+                           frac=vi_flops_exec / (ms_stage * 1e-3) / 1e12 / 34.07, traffic=None,
+                           kernel="vi_column_kernel (block-Thomas over the column, DDENS eliminated, partial-pivot Gauss-Jordan per element)", ms_per_launch=ms_stage,
+                           executed_flops_per_launch=vi_flops_exec, reference_algorithm_flops_per_launch=vi_flops_ref,
+                           frac_on_reference_algorithm_flops=vi_flops_ref / (ms_stage * 1e-3) / 1e12 / 34.07,
                            peak_source="measured DFMA peak, profiles/r01_fp64_peak.txt")),
             cpu_baseline=cpu, finite=bool(finite))
         emit(line)

@@ -20,6 +20,9 @@ ABI_SYMBOLS = (
     "fedg_last_timing", "fedg_comm_unique_id", "fedg_comm_init",
     "fedg_set_phy_tend", "fedg_numdiff_init", "fedg_numdiff_apply", "fedg_sponge_init", "fedg_link_halo", "fedg_link_halo_recv", "fedg_link_halo_send", "fedg_group_exchange_halo", "fedg_group_update", "fedg_sparsemat_matmul", "fedg_advect3d_init", "fedg_advect3d_set", "fedg_advect3d_get",
     "fedg_advect3d_cal_tend", "fedg_advect3d_update", "fedg_trcadv_init", "fedg_trcadv_update",
+    "fedg_dyn_update_host_async", "fedg_dyn_update_host_wait", "fedg_rk_store_var0", "fedg_rk_store_implicit", "fedg_rk_advance",
+    "fedg_cal_tend_ex_dev", "fedg_cal_vi_dev", "fedg_halo_start", "fedg_halo_wait", "fedg_modalfilter_apply", "fedg_rk_get_tend",
+    "fedg_elem_div", "fedg_group_exchange_aux",
 )
 
 
@@ -73,6 +76,7 @@ def load() -> C.CDLL:
     L.fedg_link_halo_recv.argtypes = [vp, ci, ci, ci, vp]
     L.fedg_link_halo_send.argtypes = [vp, ci, ci, vp, ci]
     L.fedg_group_exchange_halo.argtypes = [vp, ci, ci]
+    L.fedg_group_exchange_aux.argtypes = [vp, ci]
     L.fedg_dyn_update.argtypes = [vp, ci]
     L.fedg_dyn_update_host.argtypes = [vp] * 6 + [ci]
     L.fedg_cal_tend_ex.argtypes = [vp] * 6
@@ -95,6 +99,14 @@ def load() -> C.CDLL:
     L.fedg_advect3d_update.argtypes = [vp, ci]
     L.fedg_trcadv_init.argtypes = [vp, C.c_char_p, cd, ci, vp, vp, ci]
     L.fedg_trcadv_update.argtypes = [vp, vp, vp, ci]
+    L.fedg_dyn_update_host_async.argtypes = [vp] * 11 + [ci, ci]
+    L.fedg_dyn_update_host_wait.argtypes = [vp, ci]
+    for name in ("fedg_rk_store_var0", "fedg_halo_start", "fedg_halo_wait", "fedg_modalfilter_apply"):
+        getattr(L, name).argtypes = [vp]
+    for name in ("fedg_rk_store_implicit", "fedg_rk_advance", "fedg_cal_tend_ex_dev", "fedg_cal_vi_dev"):
+        getattr(L, name).argtypes = [vp, ci]
+    L.fedg_rk_get_tend.argtypes = [vp, ci, ci] + [vp] * 5
+    L.fedg_elem_div.argtypes = [vp, vp, vp, vp, ci]
     _lib = L
     return L
 

@@ -193,6 +193,23 @@ struct RemoteFace {
   double* sendbuf = nullptr;                               // [6][cnt]
   double* recvbuf = nullptr;                               // [6][cnt]
 };
+// Direct peer-memory exchange (default when the ranks can map each other's memory; FEDG_HALO=nccl keeps NCCL send/recv): every
+// rank owns one receive area [flags | parity 0: faces | parity 1: faces]; a face is six fields of cnt nodes.  The neighbour's pack
+// kernel stores the face values straight into that area over NVLink and then raises the face's flag to the exchange number; the
+// receiver's unpack kernel spins on its own flag.  Two parities: a sender may run one exchange ahead of the receiver, never two
+// (it needs the receiver's data of exchange n before it can pack n + 1, and the receiver packs n only after unpacking n - 1).
+struct PeerHalo {
+  bool on = false;
+  unsigned char* area = nullptr;                 // own receive area (cudaMalloc, exported with cudaIpcGetMemHandle)
+  size_t face_off[2][6] = {{0}};                 // byte offset of (parity, own face id) inside the area
+  void* peer_base[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // mapped area of the peer of remote face i (shared between faces of one peer)
+  bool peer_owner[6] = {false, false, false, false, false, false};               // this entry opened the handle (closes it)
+  double* dst[2][6] = {{nullptr}};               // where the data of own remote face i lands on the peer
+  unsigned long long* dst_flag[2][6] = {{nullptr}};
+  unsigned long long seq = 0;                    // exchanges started so far
+  double* cur_q[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};     // fields of the exchange in flight (start -> wait)
+  size_t cur_nint = 0;
+};
 struct CommState {
   bool active = false;
   void* comm = nullptr;          // ncclComm_t
@@ -201,6 +218,7 @@ struct CommState {
   int recv_order[6] = {0, 1, 2, 3, 4, 5};
   cudaStream_t stream = nullptr;
   cudaEvent_t ev_packed = nullptr, ev_done = nullptr;
+  PeerHalo p2p;
 };
 int comm_unique_id(void* id128, std::string& err);
 int comm_init(CommState& cs, const void* id128, int rank, int nranks, const int nbr_rank[6], const int nbr_face[6], const int face_off[7],
@@ -209,6 +227,7 @@ void comm_destroy(CommState& cs);
 int comm_exchange_start(CommState& cs, double* const q[NVAR], double* dp, const int* d_vmapB, size_t nint, cudaStream_t compute,
                         std::string& err);
 void comm_exchange_wait(CommState& cs, cudaStream_t compute);
+int comm_allreduce_max(CommState& cs, double* d_inout, int n, cudaStream_t s, std::string& err);
 struct P2PMsg { int peer; int msg_id; double* buf; size_t count; };
 int comm_p2p_group(CommState& cs, std::vector<P2PMsg>& sends, std::vector<P2PMsg>& recvs, cudaStream_t s, std::string& err);
 int comm_allreduce_sum(CommState& cs, double* d_inout, int n, cudaStream_t s, std::string& err);

@@ -281,6 +281,11 @@ class GlobalSphereDriver:
         from . import _lib
         _lib.check(self.L.fedg_group_update(self._h, len(self.panels), int(nsteps)))
 
+    def exchange_aux(self):
+        """AUX_VARS exchange over the linked faces (DENS_hyd, PRES_hyd, THERM_hyd); after set_aux on every own panel."""
+        from . import _lib
+        _lib.check(self.L.fedg_group_exchange_aux(self._h, len(self.panels)))
+
     def exchange_halo(self, apply_bc=False):
         """MeshFieldComm_Exchange of the prognostic variables of every own panel (remote panel edges included)."""
         from . import _lib

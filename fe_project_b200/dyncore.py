@@ -198,6 +198,51 @@ class AtmDynDGMDriver_nonhydro3d:
             assert a.dtype == np.float64 and a.flags.c_contiguous and a.size == self.n_field
         _lib.check(self.L.fedg_dyn_update_host(self.h, *[_ptr(a) for a in arrs], int(nsteps)))
 
+    def Update_host_async(self, fields_in: dict, fields_out: dict, nsteps: int = 1, slot: int = 0):
+        """Pipelined Update_host: returns once the work is queued; `Update_host_wait(slot)` completes it.  Two slots."""
+        a = [fields_in[k] for k in PROG_NAMES] + [fields_out[k] for k in PROG_NAMES]
+        for x in a:
+            assert x.dtype == np.float64 and x.flags.c_contiguous and x.size == self.n_field
+        _lib.check(self.L.fedg_dyn_update_host_async(self.h, *[_ptr(x) for x in a], int(nsteps), int(slot)))
+
+    def Update_host_wait(self, slot: int = 0):
+        _lib.check(self.L.fedg_dyn_update_host_wait(self.h, int(slot)))
+
+    # ---- stage-level seams (timeint_rk%StoreVar0 / StoreImplicit / Advance, cal_tend_ex, cal_vi, MeshFieldComm_Exchange / _Get) ----
+    def rk_store_var0(self): _lib.check(self.L.fedg_rk_store_var0(self.h))
+    def rk_store_implicit(self, stage): _lib.check(self.L.fedg_rk_store_implicit(self.h, int(stage)))
+    def rk_advance(self, stage): _lib.check(self.L.fedg_rk_advance(self.h, int(stage)))
+    def cal_tend_ex_dev(self, stage): _lib.check(self.L.fedg_cal_tend_ex_dev(self.h, int(stage)))
+    def cal_vi_dev(self, stage): _lib.check(self.L.fedg_cal_vi_dev(self.h, int(stage)))
+    def halo_start(self): _lib.check(self.L.fedg_halo_start(self.h))
+    def halo_wait(self): _lib.check(self.L.fedg_halo_wait(self.h))
+    def modalfilter_apply(self): _lib.check(self.L.fedg_modalfilter_apply(self.h))
+
+    def rk_get_tend(self, stage, implicit=False):
+        out = [np.zeros(self.n_int) for _ in range(5)]
+        _lib.check(self.L.fedg_rk_get_tend(self.h, int(bool(implicit)), int(stage), *[_ptr(a) for a in out]))
+        return dict(zip(("DENS_dt", "MOMX_dt", "MOMY_dt", "MOMZ_dt", "RHOT_dt"), out))
+
+    def Update_by_stages(self, nstage: int, hevi: bool, overlap_halo: bool = False):
+        """One step through the stage-level seams, in the order of the reference's driver loop (driver_nonhydro3d.F90:703-951)."""
+        self.rk_store_var0()
+        for s in range(1, nstage + 1):
+            if hevi:
+                self.cal_vi_dev(s); self.rk_store_implicit(s)
+            self.halo_start()
+            if not overlap_halo:
+                self.halo_wait()
+            self.cal_tend_ex_dev(s)
+            self.rk_advance(s)
+        self.modalfilter_apply()
+
+    def elem_div(self, vec_in: np.ndarray, vec_in_lift: np.ndarray, nelem: int):
+        """ElementOperationBase3D%Div: vec_in (nelem,3,Np), vec_in_lift (nelem,NfpTot) -> (nelem,4,Np)."""
+        a, b = _f64(vec_in).reshape(-1), _f64(vec_in_lift).reshape(-1)
+        out = np.zeros(nelem * 4 * self.elem.Np)
+        _lib.check(self.L.fedg_elem_div(self.h, _ptr(a), _ptr(b), _ptr(out), int(nelem)))
+        return out.reshape(nelem, 4, self.elem.Np)
+
     def cal_tend_ex(self):
         out = [np.zeros(self.n_int) for _ in range(5)]
         _lib.check(self.L.fedg_cal_tend_ex(self.h, *[_ptr(a) for a in out]))

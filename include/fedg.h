@@ -138,6 +138,48 @@ int fedg_dyn_update(fedg_ctx* ctx, int nsteps);
 int fedg_dyn_update_host(fedg_ctx* ctx, double* DDENS, double* MOMX, double* MOMY, double* MOMZ,
                          double* DRHOT, int nsteps);
 
+/* Pipelined form of fedg_dyn_update_host for a caller that keeps two sets of host arrays (slot 0 / 1): the call returns once the
+ * work is queued -- upload on a copy stream, nsteps on the compute stream, download on a second copy stream -- and
+ * fedg_dyn_update_host_wait(slot) blocks until the outputs of that slot are complete.  While one slot downloads, the other uploads
+ * and computes: PCIe runs in both directions at once.  Inputs are read and outputs written between the call and its wait; pinned
+ * (page-locked) host memory is needed for the copies to be asynchronous.  In / out arrays may be the same. */
+int fedg_dyn_update_host_async(fedg_ctx* ctx, const double* DDENS, const double* MOMX, const double* MOMY, const double* MOMZ,
+                               const double* DRHOT, double* DDENS_out, double* MOMX_out, double* MOMY_out, double* MOMZ_out,
+                               double* DRHOT_out, int nsteps, int slot);
+int fedg_dyn_update_host_wait(fedg_ctx* ctx, int slot);
+
+/* ---- stage-level seams: a driver that keeps the reference's own stage loop (driver_nonhydro3d.F90:703-921) over DEVICE-RESIDENT
+ * buffers, no host copy per stage.  One step is
+ *     fedg_rk_store_var0
+ *     do stage = 1, nstage                                   (1-based, as tint%Advance takes it)
+ *        [HEVI] fedg_cal_vi_dev(stage); fedg_rk_store_implicit(stage)
+ *        fedg_halo_start; fedg_halo_wait                      (optional: fedg_cal_tend_ex_dev does the exchange when it was not done)
+ *        fedg_cal_tend_ex_dev(stage)
+ *        fedg_rk_advance(stage)
+ *     fedg_modalfilter_apply
+ * and gives the state fedg_dyn_update(ctx, 1) gives (the fused path applies the same operations inside fewer kernels).
+ *   fedg_rk_store_var0      timeint_rk%StoreVar0            common/scale_timeint_rk.F90:624
+ *   fedg_rk_store_implicit  timeint_rk%StoreImplicit        common/scale_timeint_rk.F90:2510 (rk_storeimpl_general2D): q += impl_fac * k_im;
+ *                           the column kernel of fedg_cal_vi_dev has produced that state together with k_im, this call makes it current
+ *   fedg_rk_advance         timeint_rk%Advance_varlist      common/scale_timeint_rk.F90:536 -> :1182 (low storage), :2201 (general / IMEX)
+ *   fedg_cal_tend_ex_dev    cal_tend_ex into tint%tend_buf2D_ex(:,:,:,tintbuf_ind)   driver_nonhydro3d.F90:815-828
+ *   fedg_cal_vi_dev         cal_vi into tint%tend_buf2D_im, impl_fac = tint%Get_implicit_diagfac(stage)   driver_nonhydro3d.F90:738-753
+ *   fedg_halo_start / _wait MeshFieldComm_Exchange(do_wait=.false.) / MeshFieldComm_Get + ApplyBC_PROGVARS_lc
+ *                           model_framework/scale_model_var_manager.F90:458-487, driver_nonhydro3d.F90:770-808; a tendency call between
+ *                           start and wait processes the interior elements first (HIDE_MPI_COMM_FLAG, driver_nonhydro3d.F90:859-895)
+ *   fedg_modalfilter_apply  atm_dyn_dgm_modalfilter_apply   driver_nonhydro3d.F90:940-951
+ *   fedg_rk_get_tend        reads tint%tend_buf2D_ex / _im of a stage back to host arrays (Np,Ne) (diagnostics, tests) */
+int fedg_rk_store_var0(fedg_ctx* ctx);
+int fedg_rk_store_implicit(fedg_ctx* ctx, int stage);
+int fedg_rk_advance(fedg_ctx* ctx, int stage);
+int fedg_cal_tend_ex_dev(fedg_ctx* ctx, int stage);
+int fedg_cal_vi_dev(fedg_ctx* ctx, int stage);
+int fedg_halo_start(fedg_ctx* ctx);
+int fedg_halo_wait(fedg_ctx* ctx);
+int fedg_modalfilter_apply(fedg_ctx* ctx);
+int fedg_rk_get_tend(fedg_ctx* ctx, int implicit, int stage, double* DENS_dt, double* MOMX_dt, double* MOMY_dt, double* MOMZ_dt,
+                     double* RHOT_dt);
+
 /* atm_dyn_nonhydro3d_cal_tend_ex seam (driver_nonhydro3d.F90:152-199, 815-828): explicit tendency of
  * the state currently on the device, after halo exchange, pressure and boundary conditions, i.e.
  * what the driver stores in tint%tend_buf2D_ex at one stage.  Outputs are host arrays (Np,Ne). */
@@ -178,6 +220,12 @@ int fedg_rk_coef(const char* scheme, double* a_ex, double* b_ex, double* a_im, d
  * in: (Np,nelem) or (NfpTot,nelem) for Lift; out: (Np,nelem). */
 int fedg_elem_op(fedg_ctx* ctx, const char* name, const double* in, double* out, int nelem);
 
+/* ElementOperationBase3D%Div (element/scale_element_operation_base.F90:106-118, scale_element_operation_tensorprod3D.F90.erb:299-329):
+ * vec_out(:,1:3) = Dx vec_in(:,1), Dy vec_in(:,2), Dz vec_in(:,3); vec_out(:,4) = Lift vec_in_lift.  Host arrays vec_in (Np,3,nelem),
+ * vec_in_lift (NfpTot,nelem), vec_out (Np,4,nelem); the caller combines them with Escale / Gsqrt as the tendency routines do
+ * (FElib/test/FE/element_operation_hexahedral/test_element_operation_hexahedral.f90:131-139). */
+int fedg_elem_div(fedg_ctx* ctx, const double* vec_in, const double* vec_in_lift, double* vec_out, int nelem);
+
 /* Timing of the last fedg_dyn_update call measured with CUDA events on the context's stream:
  * ms_total, and the summed duration of the stage kernels only. */
 int fedg_last_timing(fedg_ctx* ctx, double* ms_total, double* ms_stage_kernels, long* n_launches);
@@ -194,7 +242,9 @@ int fedg_comm_init(fedg_ctx* ctx, const void* id128, int rank, int nranks);
  * velocity BC ids are those of fedg_mesh_desc, therm_bc[6] gives the thermal BC id per tile face (1 = ADIABAT,
  * mesh/scale_mesh_bndinfo.F90; NULL = none).  apply_in_update != 0: applied after every step inside fedg_dyn_update, where
  * the model calls it (model/atm_nonhydro3d/src/atmos/mod_atmos_dyn.F90:343-349).
- * fedg_numdiff_apply: %Apply on the state on the device (THERM, MOMZ, MOMX, MOMY, DENS in this order). */
+ * fedg_numdiff_apply: %Apply on the state on the device (THERM, MOMZ, MOMX, MOMY, DENS in this order).
+ * With apply_in_update the diffusion runs inside fedg_dyn_update only: fedg_group_update (several local meshes) returns
+ * FEDG_ERR_UNSUPPORTED for a mesh configured that way instead of silently stepping without it. */
 int fedg_numdiff_init(fedg_ctx* ctx, int nd_laplacian_num, double nd_coef_h, double nd_coef_v, const int* therm_bc,
                       int apply_in_update);
 int fedg_numdiff_apply(fedg_ctx* ctx);
@@ -227,6 +277,10 @@ int fedg_link_halo_send(fedg_ctx* src_ctx, int peer_rank, int msg_id, const int*
 /* MeshFieldComm_Exchange of the prognostic variables (+ DPRES) over the local meshes of a rank: remote panel edges, then
  * fedg_exchange_halo of every mesh. */
 int fedg_group_exchange_halo(fedg_ctx** ctxs, int n, int apply_bc);
+/* The same exchange for the background fields DENS_hyd, PRES_hyd, THERM_hyd of the linked faces (the AUX_VARS exchange the model does
+ * after the restart file is read, model mod_atmos_vars.F90:553-636); call once after fedg_set_aux on every mesh of the group.  Without
+ * it a linked face keeps the own-face values fedg_set_aux leaves in the halo. */
+int fedg_group_exchange_aux(fedg_ctx** ctxs, int n);
 /* AtmDynDGMDriver_nonhydro3d%Update over the local meshes of a rank (the `do n = 1, LOCAL_MESH_NUM` loops of
  * driver_nonhydro3d.F90:703-921): every stage piece runs on all meshes before the next one starts, so that linked halos
  * see the neighbours' stage state.  HEVI equation sets. */
@@ -237,7 +291,7 @@ int fedg_group_update(fedg_ctx** ctxs, int n, int nsteps);
  * kernels of scale_atm_dyn_dgm_trcadvect3d_heve.F90:149-777): the mass flux is the momentum of the state registered with
  * fedg_set_prog, DDENS_TRC = DDENS0_TRC = DDENS.  FCT coefficient + TMAR limiters unless disable_limiter, tracer modal filter
  * (1D matrices as in fedg_dyn_init) at the last stage; low-storage explicit schemes (Advance_trcvar).  Flat regional mesh, one
- * tile, p = 3 or 7.  STATUS: checked against the CPU restatement in design, not yet run on hardware (tests marked accordingly).
+ * tile, p = 3 or 7.  Parity with the CPU restatement: tests/test_gpu_tracer.py (first run on hardware: round-1 driver suite).
  * fedg_trcadv_update: QTRC (Np, NeA) host array, its (Np, Ne) interior advanced in place by nsteps; RHOQ_tp may be NULL. */
 int fedg_trcadv_init(fedg_ctx* ctx, const char* tinteg_type, double dt, int modalfilter_flag, const double* filter_h1D,
                      const double* filter_v1D, int disable_limiter);

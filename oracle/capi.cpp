@@ -3,6 +3,8 @@
 #include <stdexcept>
 #include <cstdio>
 
+#include <omp.h>
+
 #include "fe_oracle.hpp"
 
 using namespace feo;
@@ -21,6 +23,9 @@ template <class F> int guard(F&& f) {
 extern "C" {
 
 const char* feo_last_error() { return g_err.c_str(); }
+// OpenMP team size of the restatement's element loops (torchrun exports OMP_NUM_THREADS=1 before libgomp is initialised, so
+// the timing legs of bench.py set the thread count explicitly); returns the value in effect
+int feo_set_num_threads(int n) { if (n > 0) omp_set_num_threads(n); return omp_get_max_threads(); }
 
 void* feo_create(int p, int lumped, int NeX, int NeY, int NeZ, const double* dom, const double* FZ, const int* periodic) {
   Handle* h = nullptr;

@@ -202,6 +202,49 @@ void solve_static_order(double* A, int n, double* rhs, int nrhs) {
   for (int i = 0; i < n; ++i) for (int q = 0; q < nrhs; ++q) rhs[size_t(ord[i]) * nrhs + q] = r[size_t(i) * nrhs + q];
 }
 
+// Experiment switch (tests only, FEO_VI_BLOCK=1): the elimination order a thread-per-column device solver would use -- DDENS
+// eliminated with static pivots, then the DRHOT block (8 x 8, partial pivoting inside), then the Schur complement in MOMZ
+// (8 x 8, partial pivoting) -- to measure its deviation from the reference's partial pivoting over the whole block.
+bool vi_block_order() {
+  static int v = -1;
+  if (v < 0) { const char* e = std::getenv("FEO_VI_BLOCK"); v = (e && e[0] == '1') ? 1 : 0; }
+  return v == 1;
+}
+void solve_block_order(double* A, int n, double* rhs, int nrhs) {
+  const int np = n / 3;
+  std::vector<int> ord(n);
+  for (int v = 0; v < 3; ++v) for (int pv = 0; pv < np; ++pv) ord[v * np + pv] = 3 * pv + v;      // [rho | w | theta]
+  std::vector<double> B(size_t(n) * n), r(size_t(n) * nrhs);
+  for (int i = 0; i < n; ++i) {
+    for (int j = 0; j < n; ++j) B[size_t(i) * n + j] = A[size_t(ord[i]) * n + ord[j]];
+    for (int q = 0; q < nrhs; ++q) r[size_t(i) * nrhs + q] = rhs[size_t(ord[i]) * nrhs + q];
+  }
+  auto elim = [&](int k, int p) {     // Gauss-Jordan step: pivot row p for column k (all rows of the whole system are updated)
+    const double inv = 1.0 / B[size_t(p) * n + k];
+    for (int i = 0; i < n; ++i) {
+      if (i == p) continue;
+      const double m = B[size_t(i) * n + k] * inv;
+      if (m == 0.0) continue;
+      for (int j = 0; j < n; ++j) if (j != k) B[size_t(i) * n + j] -= m * B[size_t(p) * n + j];
+      B[size_t(i) * n + k] = 0.0;
+      for (int q = 0; q < nrhs; ++q) r[size_t(i) * nrhs + q] -= m * r[size_t(p) * nrhs + q];
+    }
+    for (int q = 0; q < nrhs; ++q) r[size_t(p) * nrhs + q] *= inv;
+    for (int j = 0; j < n; ++j) if (j != k) B[size_t(p) * n + j] *= inv;
+    B[size_t(p) * n + k] = 1.0;
+  };
+  std::vector<int> rowof(n, -1);
+  std::vector<char> used(n, 0);
+  for (int k = 0; k < np; ++k) { elim(k, k); used[k] = 1; rowof[k] = k; }            // rho: static pivots
+  for (int blk : {2, 1})                                                            // theta block, then w: partial pivoting inside the block rows
+    for (int k = blk * np; k < (blk + 1) * np; ++k) {
+      int p = -1; double best = -1.0;
+      for (int i = blk * np; i < (blk + 1) * np; ++i) if (!used[i] && std::fabs(B[size_t(i) * n + k]) > best) { best = std::fabs(B[size_t(i) * n + k]); p = i; }
+      elim(k, p); used[p] = 1; rowof[k] = p;
+    }
+  for (int k = 0; k < n; ++k) for (int q = 0; q < nrhs; ++q) rhs[size_t(ord[k]) * nrhs + q] = r[size_t(rowof[k]) * nrhs + q];
+}
+
 struct VIWork {
   // PROG_VARS (the Newton iterate), indexed like the fields: [VID][Np*Ne]
   vec pv[5];
@@ -511,6 +554,7 @@ void solve_var3(const Element& e, const Mesh& m, const Consts& c, const DynState
             if (nr == 4) for (int cc = 0; cc < 3; ++cc) rhs[r * nr + 1 + cc] = G[size_t(kz) * nb * 3 + r * 3 + cc];
           }
           if (vi_static_pivot()) solve_static_order(D.data(), nb, rhs.data(), nr);
+          else if (vi_block_order()) solve_block_order(D.data(), nb, rhs.data(), nr);
           else {
             lu_factor(D.data(), nb, ipiv.data());
             lu_solve(D.data(), nb, ipiv.data(), rhs.data(), nr);

@@ -7,13 +7,24 @@ import subprocess
 
 import numpy as np
 
-_HERE = os.path.dirname(os.path.abspath(__file__))
-_ORACLE_DIR = os.path.join(os.path.dirname(_HERE), "oracle")
+_ORACLE_DIR = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
 
 
+def _variant_so():
+    """FEO_VARIANT=perf (set by the timing legs of bench.py before the first call): the -O3 / FMA build for the widest vector
+    ISA of this host; default: the parity build (-ffp-contract=off), the one every test compares against."""
+    if os.environ.get("FEO_VARIANT", "") == "perf":
+        try:
+            flags = open("/proc/cpuinfo").read()
+        except OSError:
+            flags = ""
+        return "libfeoracle_perf_v4.so" if ("avx512f" in flags and "avx512vl" in flags and "avx512dq" in flags) else "libfeoracle_perf_v3.so"
+    return "libfeoracle.so"
+
+
 def build_oracle():
-    so = os.path.join(_ORACLE_DIR, "libfeoracle.so")
+    so = os.path.join(_ORACLE_DIR, _variant_so())
     srcs = [os.path.join(_ORACLE_DIR, f) for f in os.listdir(_ORACLE_DIR) if f.endswith((".cpp", ".hpp"))]
     if (not os.path.exists(so)) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         subprocess.check_call(["make", "-s", "-j8", "-C", _ORACLE_DIR])
@@ -67,6 +78,7 @@ def lib():
         L.feo_rk_store_implicit.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
         L.feo_rk_advance.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
         L.feo_last_error.restype = C.c_char_p
+        L.feo_set_num_threads.argtypes = [C.c_int]
         L.feo_advect3d_create.restype = C.c_void_p
         L.feo_advect3d_create.argtypes = [C.c_void_p, C.c_char_p, C.c_double, C.c_int]
         L.feo_advect3d_destroy.argtypes = [C.c_void_p]

@@ -1,7 +1,6 @@
 """Row f4 on the device: tracer advection with a prescribed mass flux against the oracle (tests/gpu_tracer_parity.py).
-The kernels were written after the round's GPU budget was spent, so they had never run on hardware when committed: the test runs
-them in a subprocess (a device fault stays contained) and is xfail(strict=False) -- XPASS in the driver's round-end log means the
-kernels are right as written, XFAIL means they still need their first debugging session."""
+First run on hardware: the driver's round-1 GPU suite (GPUTEST_r01.json: XPASS on all four cases), so the test is a plain
+parity test now; it still runs in a subprocess so that a device fault stays contained."""
 import os
 import subprocess
 import sys
@@ -12,7 +11,6 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 @pytest.mark.gpu
-@pytest.mark.xfail(strict=False, reason="fe_project_b200/csrc/tracer.cu has not been validated on hardware yet")
 def test_tracer_advection_prescribed_mass_flux():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "gpu_tracer_parity.py")], capture_output=True, text=True, timeout=600)
     print(out.stdout[-3000:]); print(out.stderr[-2000:])

@@ -2,7 +2,7 @@
 usage: python tools/ab_stage.py "name:ENV=val,ENV2=val" ...   (knobs are re-read by the library at every launch)"""
 import os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests")); sys.path.insert(0, os.path.join(ROOT, "oracle"))
 import torch
 import fe_project_b200._lib as _L
 if os.environ.get("AB_LIB"):

@@ -1,5 +1,5 @@
 import sys, time, numpy as np
-sys.path.insert(0, '/root/repo'); sys.path.insert(0, '/root/repo/tests')
+sys.path.insert(0, '/root/repo'); sys.path.insert(0, '/root/repo/tests'); sys.path.insert(0, '/root/repo/oracle')
 from cases import DensityCurrentCase, rel_l2
 case = DensityCurrentCase(p=7, NeX=4, NeY=2, NeZ=3, perturb=2.0)
 o = case.make_oracle()

@@ -1,7 +1,7 @@
 """Prints the relative L2 error of every prognostic variable vs the CPU oracle after N steps (GPU box)."""
 import sys, os
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests")); sys.path.insert(0, os.path.join(ROOT, "oracle"))
 from cases import DensityCurrentCase, rel_l2
 
 for (p, dims, nstep) in ((7, (4, 2, 3), 20), (7, (6, 2, 4), 100), (3, (6, 4, 4), 50)):

@@ -6,7 +6,7 @@ sound wave dt=10 s: 1.4e-1, global panel dt=20 s: 4.8e-13, dt=75 s: 1.3e-11 -> a
 import os, sys, subprocess, json
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, os.path.join(ROOT, "tests")); sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests")); sys.path.insert(0, os.path.join(ROOT, "oracle")); sys.path.insert(0, ROOT)
 mode=sys.argv[1]
 from cases import DensityCurrentCase, SoundWaveCase, GlobalPanelCase
 out={}
