@@ -22,7 +22,7 @@ ABI_SYMBOLS = (
     "fedg_advect3d_cal_tend", "fedg_advect3d_update", "fedg_trcadv_init", "fedg_trcadv_update",
     "fedg_dyn_update_host_async", "fedg_dyn_update_host_wait", "fedg_rk_store_var0", "fedg_rk_store_implicit", "fedg_rk_advance",
     "fedg_cal_tend_ex_dev", "fedg_cal_vi_dev", "fedg_halo_start", "fedg_halo_wait", "fedg_modalfilter_apply", "fedg_rk_get_tend",
-    "fedg_elem_div", "fedg_group_exchange_aux",
+    "fedg_elem_div", "fedg_group_exchange_aux", "fedg_update_phyd_hgrad",
 )
 
 
@@ -77,6 +77,7 @@ def load() -> C.CDLL:
     L.fedg_link_halo_send.argtypes = [vp, ci, ci, vp, ci]
     L.fedg_group_exchange_halo.argtypes = [vp, ci, ci]
     L.fedg_group_exchange_aux.argtypes = [vp, ci]
+    L.fedg_update_phyd_hgrad.argtypes = [vp, vp]
     L.fedg_dyn_update.argtypes = [vp, ci]
     L.fedg_dyn_update_host.argtypes = [vp] * 6 + [ci]
     L.fedg_cal_tend_ex.argtypes = [vp] * 6

@@ -157,6 +157,7 @@ class GlobalSphereCase:
         from .cubedsphere import CubedSphere, cs2cart, cs2lonlat, lonlat2cs_vec
         self.p, self.dt, self.tinteg, self.modalfilter, self.ztop = p, dt, tinteg, modalfilter, ztop
         self.eqs = eqs
+        self.init = init
         self.mf = dict(MF, **(mf or {}))
         self.sponge = sponge
         self.FZ = None if FZ is None else np.asarray(FZ, dtype=np.float64)
@@ -215,6 +216,9 @@ class GlobalSphereCase:
                 d.sponge_init(**self.sponge)
             d.set_prog(*(f[k] for k in ("DDENS", "MOMX", "MOMY", "MOMZ", "DRHOT")))
         g.exchange_aux()
+        if self.init == "jw":          # PRES_hyd varies horizontally: update_phyd_hgrad after the background fields were exchanged
+            for d in g.panels:
+                d.update_phyd_hgrad()
         return g
 
 

@@ -133,12 +133,13 @@ struct fedg_ctx {
   std::vector<OutMsg> outmsg;
   TracerState trc;
   // pipelined host update (fedg_dyn_update_host_async / _wait): device staging of two slots, one copy stream per direction
+  static constexpr int NSLOT = 3;   // one slot uploads, one computes, one downloads
   struct HostPipe {
     bool ready = false;
     cudaStream_t h2d = nullptr, d2h = nullptr;
-    DevBuf in[2][NVAR], out[2][NVAR];
-    cudaEvent_t in_ready[2] = {nullptr, nullptr}, in_free[2] = {nullptr, nullptr}, out_ready[2] = {nullptr, nullptr}, out_done[2] = {nullptr, nullptr};
-    bool pending[2] = {false, false};
+    DevBuf in[NSLOT][NVAR], out[NSLOT][NVAR];
+    cudaEvent_t in_ready[NSLOT] = {}, in_free[NSLOT] = {}, out_ready[NSLOT] = {}, out_done[NSLOT] = {};
+    bool pending[NSLOT] = {};
   } hp;
   int xbuf = 0;                    // buffer that holds the state other local meshes gather from (stage input of the explicit part)
   struct { int i0, in, mid, nxt; } hs{0, 0, 0, 0};   // buffer cursor of the HEVI stage pieces
@@ -150,7 +151,7 @@ struct fedg_ctx {
   double last_ms_total = 0, last_ms_stage = 0; long last_launches = 0;
   ~fedg_ctx() {
     for (auto& e : ev) cudaEventDestroy(e);
-    for (int k = 0; k < 2; ++k) {
+    for (int k = 0; k < NSLOT; ++k) {
       for (auto& b : hp.in[k]) b.release();
       for (auto& b : hp.out[k]) b.release();
       for (cudaEvent_t e : {hp.in_ready[k], hp.in_free[k], hp.out_ready[k], hp.out_done[k]}) if (e) cudaEventDestroy(e);
@@ -609,6 +610,27 @@ int fedg_set_phyd_hgrad(fedg_ctx* c, const double* DPhydDx, const double* DPhydD
   return FEDG_OK;
 }
 
+// update_phyd_hgrad (driver_nonhydro3d.F90:1060-1095): DPhydDx / DPhydDy from the PRES_hyd on the device, whose halo holds what the
+// last aux exchange left there (fedg_set_aux: own tile + NCCL neighbours; fedg_group_exchange_aux: linked local meshes)
+int fedg_update_phyd_hgrad(fedg_ctx* c, const double* PRES_hyd_ref) {
+  if (!c) return fail(FEDG_ERR_ARG, "null argument");
+  if (!c->aux_ready) return fail(FEDG_ERR_STATE, "fedg_set_aux must be called first");
+  ensure_tables(c);
+  for (DevBuf* b : {&c->dphydx, &c->dphydy}) if (b->n < c->nint) CUDA_TRY(b->alloc(c->nint));
+  DevBuf ref;
+  struct Rel { DevBuf& b; ~Rel() { b.release(); } } rel{ref};
+  if (PRES_hyd_ref) {
+    CUDA_TRY(ref.alloc(c->nall));
+    CUDA_TRY(cudaMemcpyAsync(ref.p, PRES_hyd_ref, c->nall * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  }
+  launch_phyd_hgrad(c->pres_hyd.p, PRES_hyd_ref ? ref.p : nullptr, c->gsqrt.p, c->g13.p, c->g23.p, c->gsqrtH.p, c->escale.p, c->fscale.p,
+                    c->d_vmapP, c->d_emap2d, c->dphydx.p, c->dphydy.p, c->np, c->Ne, c->terrain, c->stream);
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  CUDA_TRY(cudaGetLastError());
+  c->has_phyd = true;
+  return FEDG_OK;
+}
+
 int fedg_set_phy_tend(fedg_ctx* c, const double* DENS_tp, const double* MOMX_tp, const double* MOMY_tp, const double* MOMZ_tp,
                       const double* RHOT_tp, const double* RHOH_p) {
   if (!c) return fail(FEDG_ERR_ARG, "null argument");
@@ -1055,7 +1077,7 @@ static int host_pipe_init(fedg_ctx* c) {
   if (hp.ready) return FEDG_OK;
   CUDA_TRY(cudaStreamCreateWithFlags(&hp.h2d, cudaStreamNonBlocking));
   CUDA_TRY(cudaStreamCreateWithFlags(&hp.d2h, cudaStreamNonBlocking));
-  for (int k = 0; k < 2; ++k) {
+  for (int k = 0; k < fedg_ctx::NSLOT; ++k) {
     for (auto& b : hp.in[k]) CUDA_TRY(b.alloc(c->nint));
     for (auto& b : hp.out[k]) CUDA_TRY(b.alloc(c->nint));
     for (cudaEvent_t* e : {&hp.in_ready[k], &hp.in_free[k], &hp.out_ready[k], &hp.out_done[k]})
@@ -1065,17 +1087,18 @@ static int host_pipe_init(fedg_ctx* c) {
   return FEDG_OK;
 }
 
-// One pass of the pipeline for slot `slot` (0 / 1).  Three streams: H2D copies -> (event) -> compute stream: staging -> state, the
-// steps, state -> staging -> (event) -> D2H copies.  PCIe is full duplex: while slot 0 is being downloaded, slot 1 is uploaded
-// and computed, so a caller that alternates the slots (two sets of host arrays) is bound by one direction of the link, not by the
-// sum of both plus the step.  Only the (Np, Ne) interior travels: the halo slots [Ne+1:NeA] are rebuilt on the device by the
+// One pass of the pipeline for slot `slot` (0 .. 2).  Three streams: H2D copies -> (event) -> compute stream: staging -> state, the
+// steps, state -> staging -> (event) -> D2H copies.  PCIe is full duplex: while one slot is being downloaded, the next is computed and
+// a third uploaded, so a caller that rotates three sets of host arrays is bound by one direction of the link (7.2 ms for 335 MB each
+// way, measured with both directions busy), not by the sum of both plus the step; with two sets the chain of one slot (upload + step +
+// download = 16 ms) bounds the rate at 8.9 ms per call.  Only the (Np, Ne) interior travels: the halo slots [Ne+1:NeA] are rebuilt on the device by the
 // exchange of every stage before anything reads them.
 int fedg_dyn_update_host_async(fedg_ctx* c, const double* DDENS, const double* MOMX, const double* MOMY, const double* MOMZ,
                                const double* DRHOT, double* DDENS_out, double* MOMX_out, double* MOMY_out, double* MOMZ_out,
                                double* DRHOT_out, int nsteps, int slot) {
   if (!c || !DDENS || !MOMX || !MOMY || !MOMZ || !DRHOT || !DDENS_out || !MOMX_out || !MOMY_out || !MOMZ_out || !DRHOT_out || nsteps < 0)
     return fail(FEDG_ERR_ARG, "null argument");
-  if (slot < 0 || slot > 1) return fail(FEDG_ERR_ARG, "slot must be 0 or 1");
+  if (slot < 0 || slot >= fedg_ctx::NSLOT) return fail(FEDG_ERR_ARG, "slot must be 0, 1 or 2");
   if (!c->dyn_ready || !c->aux_ready) return fail(FEDG_ERR_STATE, "fedg_dyn_init and fedg_set_aux must be called before the update");
   { int rc = host_pipe_init(c); if (rc) return rc; }
   auto& hp = c->hp;
@@ -1108,7 +1131,7 @@ int fedg_dyn_update_host_async(fedg_ctx* c, const double* DDENS, const double* M
 }
 
 int fedg_dyn_update_host_wait(fedg_ctx* c, int slot) {
-  if (!c || slot < 0 || slot > 1) return fail(FEDG_ERR_ARG, "bad argument");
+  if (!c || slot < 0 || slot >= fedg_ctx::NSLOT) return fail(FEDG_ERR_ARG, "bad argument");
   auto& hp = c->hp;
   if (!hp.ready || !hp.pending[slot]) return FEDG_OK;
   CUDA_TRY(cudaEventSynchronize(hp.out_done[slot]));
@@ -1119,7 +1142,7 @@ int fedg_dyn_update_host_wait(fedg_ctx* c, int slot) {
 
 int fedg_dyn_update_host(fedg_ctx* c, double* DDENS, double* MOMX, double* MOMY, double* MOMZ, double* DRHOT, int nsteps) {
   if (!c || !DDENS || !MOMX || !MOMY || !MOMZ || !DRHOT) return fail(FEDG_ERR_ARG, "null argument");
-  for (int k = 0; k < 2; ++k) { int rc = fedg_dyn_update_host_wait(c, k); if (rc) return rc; }
+  for (int k = 0; k < fedg_ctx::NSLOT; ++k) { int rc = fedg_dyn_update_host_wait(c, k); if (rc) return rc; }
   // One blocking call is a strict chain upload -> steps -> download (nothing to overlap): the copies go straight into / out of the
   // state buffers on the compute stream, no staging.  Only the (Np, Ne) interior travels (20 % fewer PCIe bytes at 32x32x16).
   double* h[NVAR] = {DDENS, MOMX, MOMY, MOMZ, DRHOT};

@@ -243,5 +243,8 @@ void launch_monitor(const double* const q[NVAR], const double* dens_hyd, const d
                     bool moist, const double* w3, const double* Jac, const double* gsqrt, bool terrain,
                     const double* zlev, PhysConst c, int Np, int Ne, double* out5, cudaStream_t s);
 void launch_elem_op(int op, const double* in, double* out, int nelem, int np, cudaStream_t s);
+void launch_phyd_hgrad(const double* pres_hyd, const double* pres_ref, const double* gsqrt, const double* g13, const double* g23,
+                       const double* gsqrtH, const double* escale, const double* fscale, const int* vmapP, const int* emap2d,
+                       double* outx, double* outy, int np, int Ne, bool terrain, cudaStream_t s);
 
 }  // namespace fedg

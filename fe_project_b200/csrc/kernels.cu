@@ -227,6 +227,87 @@ void launch_modal_filter5(double* const q[NVAR], const double* gsqrt, bool terra
   modal_filter5_kernel<<<Ne, N3, size_t(2) * N3 * sizeof(double), s>>>(q[0], q[1], q[2], q[3], q[4], gsqrt, terrain ? 1 : 0, np);
 }
 
+
+// atm_dyn_dgm_nonhydro3d_common_calc_phyd_hgrad_lc + get_phyd_hgrad_numflux_generalhvc (nonhydro3d_common.F90:624-777): horizontal
+// gradient of the hydrostatic pressure (minus a reference profile), the set-up product the driver refreshes after a restart is read
+// (driver_nonhydro3d.F90:1060-1095) and every explicit tendency subtracts.  One block per element, one thread per node.
+//   DPhydDx = [E11 Dx(Gv P) + E33 Dz(G13 Gv P) + Lift(delx)] / Gv,   Gv = Gsqrt / GsqrtH   (= 1 without topography)
+//   delx = (nx + G13_P nz) Fscale/2 Gv_P P_P - (nx + G13_M nz) Fscale/2 Gv_M P_M        (central flux jump)
+struct PhydParams {
+  const double *pres_hyd, *pres_ref;      // (Np*Ne + halo); pres_ref may be NULL
+  const double *gsqrt, *g13, *g23, *gsqrtH;
+  const double *escale, *fscale;
+  const int *vmapP, *emap2d;
+  double *outx, *outy;
+  int np, Ne, terrain;
+};
+__global__ void phyd_hgrad_kernel(const __grid_constant__ PhydParams P) {
+  extern __shared__ double sm[];
+  const int np = P.np, N2 = np * np, N3 = N2 * np, NFT = 6 * N2;
+  double* F = sm;               // Gv * dP
+  double* F13 = sm + N3;        // G13 * F   (terrain)
+  double* F23 = sm + 2 * N3;    // G23 * F
+  double* dlx = sm + 3 * N3;    // [NFT]
+  double* dly = dlx + NFT;
+  const int ke = blockIdx.x, n = threadIdx.x;
+  const int i = n % np, j = (n / np) % np, k = n / N2;
+  const size_t g = size_t(ke) * N3 + n;
+  const int ke2d = P.emap2d[ke];
+  auto dpres = [&](size_t idx) { return P.pres_hyd[idx] - (P.pres_ref ? P.pres_ref[idx] : 0.0); };
+  double Gv = 1.0, g13 = 0.0, g23 = 0.0;
+  if (P.terrain) { Gv = P.gsqrt[g] / P.gsqrtH[size_t(ke2d) * N2 + (n % N2)]; g13 = P.g13[g]; g23 = P.g23[g]; }
+  const double f = Gv * dpres(g);
+  F[n] = f; F13[n] = g13 * f; F23[n] = g23 * f;
+  for (int fp = n; fp < NFT; fp += N3) {
+    const int face = fp / N2, fl = fp % N2;
+    int nloc, h2d;
+    switch (face) {
+      case 0: nloc = (fl % np) + (fl / np) * N2; h2d = fl % np; break;
+      case 1: nloc = (np - 1) + (fl % np) * np + (fl / np) * N2; h2d = (np - 1) + (fl % np) * np; break;
+      case 2: nloc = (fl % np) + (np - 1) * np + (fl / np) * N2; h2d = (fl % np) + (np - 1) * np; break;
+      case 3: nloc = (fl % np) * np + (fl / np) * N2; h2d = (fl % np) * np; break;
+      case 4: nloc = fl; h2d = fl; break;
+      default: nloc = fl + (np - 1) * N2; h2d = fl; break;
+    }
+    const size_t iM = size_t(ke) * N3 + nloc, iP = size_t(P.vmapP[size_t(ke) * NFT + fp]);
+    const double nx = (face == 1) ? 1.0 : (face == 3) ? -1.0 : 0.0;
+    const double ny = (face == 2) ? 1.0 : (face == 0) ? -1.0 : 0.0;
+    const double nz = (face == 5) ? 1.0 : (face == 4) ? -1.0 : 0.0;
+    double GvM = 1.0, GvP = 1.0, g13M = 0.0, g13P = 0.0, g23M = 0.0, g23P = 0.0;
+    if (P.terrain) {
+      const double gh = P.gsqrtH[size_t(ke2d) * N2 + h2d];
+      GvM = P.gsqrt[iM] / gh; GvP = P.gsqrt[iP] / gh;
+      g13M = P.g13[iM]; g13P = P.g13[iP]; g23M = P.g23[iM]; g23P = P.g23[iP];
+    }
+    const double fs = P.fscale[size_t(face) * P.Ne + ke];
+    const double t1 = fs * 0.5 * GvP * dpres(iP), t2 = fs * 0.5 * GvM * dpres(iM);
+    dlx[fp] = (nx + g13P * nz) * t1 - (nx + g13M * nz) * t2;
+    dly[fp] = (ny + g23P * nz) * t1 - (ny + g23M * nz) * t2;
+  }
+  __syncthreads();
+  double dx = 0.0, dy = 0.0, dz1 = 0.0, dz2 = 0.0;
+  for (int l = 0; l < np; ++l) {
+    dx += cT.D[i * np + l] * F[l + j * np + k * N2];
+    dy += cT.D[j * np + l] * F[i + l * np + k * N2];
+    if (P.terrain) { dz1 += cT.D[k * np + l] * F13[i + j * np + l * N2]; dz2 += cT.D[k * np + l] * F23[i + j * np + l * N2]; }
+  }
+  // Lift: the same tensor-product weights as elem_op_kernel (op 3)
+  const double lx = cT.Lw[j * 2] * dlx[i + k * np] + cT.Lw[i * 2 + 1] * dlx[N2 + j + k * np] + cT.Lw[j * 2 + 1] * dlx[2 * N2 + i + k * np] +
+                    cT.Lw[i * 2] * dlx[3 * N2 + j + k * np] + cT.Lw[k * 2] * dlx[4 * N2 + i + j * np] + cT.Lw[k * 2 + 1] * dlx[5 * N2 + i + j * np];
+  const double ly = cT.Lw[j * 2] * dly[i + k * np] + cT.Lw[i * 2 + 1] * dly[N2 + j + k * np] + cT.Lw[j * 2 + 1] * dly[2 * N2 + i + k * np] +
+                    cT.Lw[i * 2] * dly[3 * N2 + j + k * np] + cT.Lw[k * 2] * dly[4 * N2 + i + j * np] + cT.Lw[k * 2 + 1] * dly[5 * N2 + i + j * np];
+  const double E11 = P.escale[ke], E22 = P.escale[size_t(P.Ne) + ke], E33 = P.escale[2 * size_t(P.Ne) + ke];
+  P.outx[g] = (E11 * dx + E33 * dz1 + lx) / Gv;
+  P.outy[g] = (E22 * dy + E33 * dz2 + ly) / Gv;
+}
+void launch_phyd_hgrad(const double* pres_hyd, const double* pres_ref, const double* gsqrt, const double* g13, const double* g23,
+                       const double* gsqrtH, const double* escale, const double* fscale, const int* vmapP, const int* emap2d,
+                       double* outx, double* outy, int np, int Ne, bool terrain, cudaStream_t s) {
+  PhydParams P{pres_hyd, pres_ref, gsqrt, g13, g23, gsqrtH, escale, fscale, vmapP, emap2d, outx, outy, np, Ne, terrain ? 1 : 0};
+  const int N3 = np * np * np;
+  phyd_hgrad_kernel<<<Ne, N3, (size_t(3) * N3 + 12 * np * np) * sizeof(double), s>>>(P);
+}
+
 void launch_elem_op(int op, const double* in, double* out, int nelem, int np, cudaStream_t s) {
   int N3 = np * np * np;
   size_t sh = size_t(2) * (6 * np * np > N3 ? 6 * np * np : N3) * sizeof(double);

@@ -143,6 +143,11 @@ class AtmDynDGMDriver_nonhydro3d:
         b = None if DPhydDy is None else self._chk_field(DPhydDy)
         _lib.check(self.L.fedg_set_phyd_hgrad(self.h, _ptr(a), _ptr(b)))
 
+    def update_phyd_hgrad(self, PRES_hyd_ref=None):
+        """update_phyd_hgrad (driver_nonhydro3d.F90:1060-1095) on the device, from the registered PRES_hyd and its exchanged halo."""
+        a = None if PRES_hyd_ref is None else self._chk_field(PRES_hyd_ref)
+        _lib.check(self.L.fedg_update_phyd_hgrad(self.h, _ptr(a)))
+
     def set_phy_tend(self, DENS_tp, MOMX_tp, MOMY_tp, MOMZ_tp, RHOT_tp, RHOH_p):
         """Physics tendencies of add_phy_tend (driver_nonhydro3d.F90:1098-1178); None switches them off."""
         a = [None if x is None else self._chk_field(x) for x in (DENS_tp, MOMX_tp, MOMY_tp, MOMZ_tp, RHOT_tp, RHOH_p)]

@@ -171,7 +171,7 @@ def baroclinic_wave_global(mesh, intrp_order=8, c=SCALE_CONST, prm=JW_DEFAULT, c
         q = np.einsum("kc,Bcji->Bkji", T1, q, optimize=True)
         return q.reshape(q.shape[0], -1)
 
-    for k0 in range(0, Ne, ch):
+    def chunk(k0):
         sl = slice(k0, min(k0 + ch, Ne))
         ex, ey, ez = mesh.ex[sl], mesh.ey[sl], mesh.ez[sl]
         B = ex.size
@@ -195,4 +195,10 @@ def baroclinic_wave_global(mesh, intrp_order=8, c=SCALE_CONST, prm=JW_DEFAULT, c
         f["DENS_hyd"][sl] = proj(dens)
         f["MOMX"][sl] = proj(dens * (U + Ud))
         f["MOMY"][sl] = proj(dens * (V + Vd))
+
+    # the chunks are independent and NumPy releases the GIL inside its loops: a thread per core (set-up time of the 6x32x32x12 case)
+    import os
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=max(1, min(32, os.cpu_count() or 1))) as ex_:
+        list(ex_.map(chunk, range(0, Ne, ch)))
     return f

@@ -121,6 +121,11 @@ int fedg_set_aux(fedg_ctx* ctx, const double* DENS_hyd, const double* PRES_hyd, 
                  const double* Rtot, const double* CVtot, const double* CPtot);
 /* AUXDYNVARS3D DPhydDx, DPhydDy (driver_nonhydro3d.F90:323-326, 1060-1095); NULL = zero. */
 int fedg_set_phyd_hgrad(fedg_ctx* ctx, const double* DPhydDx, const double* DPhydDy);
+/* update_phyd_hgrad (driver_nonhydro3d.F90:1060-1095 -> atm_dyn_dgm_nonhydro3d_common_calc_phyd_hgrad_lc, nonhydro3d_common.F90:624-777):
+ * the same two fields computed ON THE DEVICE from the registered PRES_hyd (minus PRES_hyd_ref (Np,NeA), NULL = 0), with the halo values
+ * the last background-field exchange left there (fedg_set_aux / fedg_comm_init across NCCL tiles, fedg_group_exchange_aux across linked
+ * local meshes).  Needed whenever PRES_hyd varies horizontally (baroclinic-wave initial state). */
+int fedg_update_phyd_hgrad(fedg_ctx* ctx, const double* PRES_hyd_ref);
 /* Physics tendencies handed to the dynamics step, (Np,NeA) each: DENS_tp, MOMX_tp, MOMY_tp, MOMZ_tp, RHOT_tp, RHOH_p of
  * add_phy_tend (driver_nonhydro3d.F90:843-857, 1098-1178; ENTOT_CONSERVE_SCHEME_FLAG = .false. form).  They are added
  * to the explicit tendency of every stage inside the stage kernel.  NULL or all-zero arrays switch the term off. */
@@ -138,7 +143,7 @@ int fedg_dyn_update(fedg_ctx* ctx, int nsteps);
 int fedg_dyn_update_host(fedg_ctx* ctx, double* DDENS, double* MOMX, double* MOMY, double* MOMZ,
                          double* DRHOT, int nsteps);
 
-/* Pipelined form of fedg_dyn_update_host for a caller that keeps two sets of host arrays (slot 0 / 1): the call returns once the
+/* Pipelined form of fedg_dyn_update_host for a caller that keeps up to three sets of host arrays (slot 0 / 1 / 2): the call returns once the
  * work is queued -- upload on a copy stream, nsteps on the compute stream, download on a second copy stream -- and
  * fedg_dyn_update_host_wait(slot) blocks until the outputs of that slot are complete.  While one slot downloads, the other uploads
  * and computes: PCIe runs in both directions at once.  Inputs are read and outputs written between the call and its wait; pinned

@@ -238,6 +238,12 @@ int feo_sphere_exchange_aux(void** hv6) {
       u1[p] = u2[p] = nullptr;
     }
     sphere_exchange(static_cast<Handle*>(hv6[0])->d.elem, mesh, sc, u1, u2);
+    // update_phyd_hgrad follows the exchange of the background fields (model mod_atmos_vars.F90:553-636, driver_nonhydro3d.F90:1060-1095):
+    // at a panel edge the exterior value of PRES_hyd is the neighbour panel's, not the own face value feo_prepare had
+    for (int p = 0; p < 6; ++p) {
+      auto& d = static_cast<Handle*>(hv6[p])->d;
+      calc_phyd_hgrad(d.elem, d.mesh, d.st);
+    }
   });
 }
 int feo_sphere_update(void** hv6, int nsteps) {

@@ -22,42 +22,93 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 
 # ------------------------------------------------------------------------------------------------ config 3 at 32x32x16
 @pytest.mark.parametrize("eqs,tinteg,dt,nsteps", [("NONHYDRO3D_HEVE", "ERK_SSP_4s3o", 0.04, 10), ("NONHYDRO3D_HEVI", "IMEX_ARK324", 0.08, 5)])
-def test_config3_full_size_against_oracle(eqs, tinteg, dt, nsteps):
-    """BASELINE configs[2]: regional density current, 32 x 32 x 16 elements, p = 7, modal filter on -- the bench workload itself."""
+@pytest.mark.parametrize("perturb", [0.0, 2.0])
+def test_config3_full_size_against_oracle(eqs, tinteg, dt, nsteps, perturb):
+    """BASELINE configs[2]: regional density current, 32 x 32 x 16 elements, p = 7, modal filter on -- the bench workload itself.
+    perturb = 0: the case as shipped.  The fluid starts at rest, so after 10 steps MOMX is a 1e-3 residual of the cancelling
+    hydrostatic forces and MOMY is round-off: those two are judged against the momentum scale of the run (max |MOMZ|), the other
+    three against their own norm.  perturb = 2: the same state with a smooth O(1) momentum field on top, every variable judged
+    against its own norm."""
     import oracle_api
     oracle_api.lib().feo_set_num_threads(os.cpu_count())
     case = DensityCurrentCase(p=7, NeX=32, NeY=32, NeZ=16, dom=(0.0, 25.6e3, 0.0, 25.6e3, 0.0, 6.4e3), dt=dt, eqs=eqs, tinteg=tinteg,
-                              modalfilter=True)
+                              modalfilter=True, perturb=perturb)
     o = case.make_oracle()
     d = case.make_driver(o)
     d.Update(nsteps)
     o.update(nsteps)
     g = d.get_prog()
     n = case.mesh.Ne * case.elem.Np
-    assert np.abs(o.arr("MOMX")[:n]).max() > 1e-4          # the current has started to move
-    for nm in ("DDENS", "MOMX", "MOMZ", "DRHOT"):
-        assert rel_l2(g[nm][:n], o.arr(nm)[:n]) <= TOL, (eqs, nm)
-    # MOMY is round-off noise around zero (the case is y-independent): judged against the scale of the horizontal momentum
-    assert np.abs(g["MOMY"][:n] - o.arr("MOMY")[:n]).max() <= TOL * np.abs(o.arr("MOMX")[:n]).max()
+    err = {nm: rel_l2(g[nm][:n], o.arr(nm)[:n]) for nm in PROG}
+    mscale = np.abs(o.arr("MOMZ")[:n]).max()
+    aerr = {nm: np.abs(g[nm][:n] - o.arr(nm)[:n]).max() / mscale for nm in ("MOMX", "MOMY")}
+    print("config3", eqs, "perturb", perturb, {k: f"{v:.2e}" for k, v in err.items()}, {k: f"{v:.2e}" for k, v in aerr.items()})
+    assert mscale > 1e-2                                    # the cold bubble has started to sink
+    for nm in (PROG if perturb else ("DDENS", "MOMZ", "DRHOT")):
+        assert err[nm] <= TOL, (eqs, nm, err)
+    for nm in ("MOMX", "MOMY"):
+        assert aerr[nm] <= TOL, (eqs, nm, aerr)
     mo, mg = o.monitor(), d.monitor()
-    assert abs(mo[1] - mg[1]) <= 1e-12 * abs(mo[1])        # total energy
+    assert abs(mo[1] - mg[1]) <= 1e-11 * abs(mo[1])        # total energy (8.4e6-term sums in different orders: 1.1e-12 measured)
+
+
+def test_update_phyd_hgrad_on_the_device():
+    """fedg_update_phyd_hgrad == the oracle's calc_phyd_hgrad, seen through the explicit tendency of a state whose hydrostatic pressure
+    varies horizontally (as the baroclinic-wave background does)."""
+    case = DensityCurrentCase(p=7, NeX=3, NeY=2, NeZ=2, perturb=1.0, periodic=(True, True, False))
+    m = case.mesh
+    x, y = m.pos_en[0], m.pos_en[1]
+    case.fields["PRES_hyd"][:m.Ne] *= 1.0 + 1e-3 * np.sin(2 * np.pi * x / 25.6e3) * np.cos(2 * np.pi * y / 6.4e3)
+    o = case.make_oracle()
+    assert np.abs(o.arr("DPhydDx")[:m.Ne * case.elem.Np]).max() > 1e-4
+    d = case.make_driver(None)
+    d.update_phyd_hgrad()
+    for w in ("exchange", "pressure", "bc", "tend_ex"):
+        o.piece(w)
+    t = d.cal_tend_ex()
+    n = m.Ne * case.elem.Np
+    N = m.NeA * case.elem.Np
+    te = o.arr("tend_ex")[:5 * N].reshape(5, -1)[:, :n]
+    for nm, iv in (("DENS_dt", 0), ("RHOT_dt", 1), ("MOMZ_dt", 2), ("MOMX_dt", 3), ("MOMY_dt", 4)):
+        assert rel_l2(t[nm], te[iv]) <= 5e-11, nm
+    d0 = case.make_driver(None)                            # and it matters
+    assert rel_l2(d0.cal_tend_ex()["MOMX_dt"], te[3]) > 1e-6
 
 
 # ------------------------------------------------------------------------------------------------ config 4 (JW baroclinic wave)
-def _check_sphere(case, g, ref_of, tol=TOL):
+def _sphere_err(name, got, ref, scale, n):
+    """Relative L2 error of one variable on one panel.  A field that is round-off noise on a panel (away from the perturbation) is
+    judged against 1e-3 of the field's global scale."""
+    return np.linalg.norm(got - ref) / max(np.linalg.norm(ref), 1e-3 * scale * np.sqrt(n))
+
+
+def _judge_sphere(errs, mom_errs):
+    """errs[(P, name)]: relative L2 errors against the variable's own norm; mom_errs[P]: error of MOMZ against the momentum scale.
+    In the balanced Jablonowski-Williamson state MOMZ (~1e-3 kg m-2 s-1) is the residual of the cancelling vertical pressure-gradient
+    and buoyancy forces, each ~1e4 times larger: one ulp of the pressure (1.5e-11 Pa; the device evaluates x^gamma as exp(gamma log x),
+    1.6 ulp, the oracle calls glibc's pow) moves it by ~1e-10 of itself.  MOMZ is therefore judged (i) at 1e-10 against the momentum
+    scale of the run, max |MOMX| R (~30 kg m-2 s-1), and (ii) at 1e-9 against its own norm (measured: 1.9e-10 .. 2.9e-10); every other
+    variable at 1e-10 against its own norm."""
+    print("config4 worst:", {nm: f"{max(v for (P, n_), v in errs.items() if n_ == nm):.2e}" for nm in PROG}, "MOMZ vs momentum scale:", f"{max(mom_errs.values()):.2e}")
+    for (P, nm), e in errs.items():
+        assert e <= (1e-9 if nm == "MOMZ" else TOL), (P, nm, e)
+    for P, e in mom_errs.items():
+        assert e <= TOL, (P, "MOMZ / momentum scale", e)
+
+
+def _check_sphere(case, g, ref_of):
     """ref_of(P, name) -> reference interior array of panel P."""
-    worst = 0.0
+    from fe_project_b200.initcond import SCALE_CONST
     scale = {nm: max(np.abs(ref_of(P, nm)).max() for P in range(6)) for nm in PROG}
+    mom = scale["MOMX"] * SCALE_CONST["RPlanet"]
+    errs, mom_errs = {}, {}
     for P, (d, m) in enumerate(zip(g.panels, case.cs.panels)):
         got = d.get_prog()
         n = m.Ne * case.elem.Np
         for nm in PROG:
-            ref = ref_of(P, nm)
-            # a field that is round-off noise on one panel (MOMZ away from the perturbation) is judged against the field's global scale
-            err = np.linalg.norm(got[nm][:n] - ref) / max(np.linalg.norm(ref), 1e-3 * scale[nm] * np.sqrt(n))
-            worst = max(worst, err)
-            assert err <= tol, (P, nm, err)
-    return worst
+            errs[(P, nm)] = _sphere_err(nm, got[nm][:n], ref_of(P, nm), scale[nm], n)
+        mom_errs[P] = np.linalg.norm(got["MOMZ"][:n] - ref_of(P, "MOMZ")) / (mom * np.sqrt(n))
+    _judge_sphere(errs, mom_errs)
 
 
 def test_config4_jw_shipped_size_against_oracle():
@@ -87,16 +138,20 @@ def test_config4_jw_full_size_against_oracle_fixture():
         s = case.make_oracle(); s.update(nsteps)
         _check_sphere(case, g, lambda P, nm: s.panels[P].arr(nm)[:s.panels[P].Ne * s.panels[P].Np])
         return
+    from fe_project_b200.initcond import SCALE_CONST
     scale = {nm: max(np.abs(fx[f"s_{P}_{nm}"]).max() for P in range(6)) for nm in PROG}
+    mom = scale["MOMX"] * SCALE_CONST["RPlanet"]
+    errs, mom_errs = {}, {}
     for P, (d, m) in enumerate(zip(g.panels, case.cs.panels)):
         got = d.get_prog()
         n = m.Ne * case.elem.Np
         for nm in PROG:
             ref, a = fx[f"s_{P}_{nm}"], got[nm][:n]
-            err = np.linalg.norm(a[::stride] - ref) / max(np.linalg.norm(ref), 1e-3 * scale[nm] * np.sqrt(ref.size))
-            assert err <= TOL, (P, nm, err)
+            errs[(P, nm)] = _sphere_err(nm, a[::stride], ref, scale[nm], ref.size)
             nrm = float(fx[f"n_{P}_{nm}"])
-            assert abs(np.linalg.norm(a) - nrm) <= TOL * max(nrm, 1e-3 * scale[nm] * np.sqrt(n)), (P, nm)
+            assert abs(np.linalg.norm(a) - nrm) <= (1e-9 if nm == "MOMZ" else TOL) * max(nrm, 1e-3 * scale[nm] * np.sqrt(n)), (P, nm)
+        mom_errs[P] = np.linalg.norm(got["MOMZ"][:n][::stride] - fx[f"s_{P}_MOMZ"]) / (mom * np.sqrt(fx[f"s_{P}_MOMZ"].size))
+    _judge_sphere(errs, mom_errs)
 
 
 # ------------------------------------------------------------------------------------------------ tiles on one device
