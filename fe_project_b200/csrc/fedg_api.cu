@@ -775,7 +775,7 @@ void fill_vi_params(fedg_ctx* c, VIParams& V, int in, int out, int i0, int stage
   V.dpout = c->dp[out].p;
   V.dens_hyd = c->dens_hyd.p; V.pres_hyd = c->pres_hyd.p; V.therm_hyd = c->therm_hyd.p; V.rhot_hyd_vi = c->rhot_hyd_vi.p;
   V.rtot = c->rtot.p; V.cvtot = c->cvtot.p; V.cptot = c->cptot.p;
-  V.escale = c->escale.p; V.fscale = c->fscale.p; V.tab = c->d_tab; V.scratch = c->vi_scratch.p;
+  V.escale = c->escale.p; V.fscale = c->fscale.p; V.tab = c->d_tab; V.htab = &c->tab; V.scratch = c->vi_scratch.p;
   V.c = c->c; V.impl_fac = impl_fac; V.Ne = c->Ne; V.Ne2D = c->Ne2D; V.NeZ = c->NeZ;
   { const char* e = getenv("FEDG_EXACT_POW"); V.exact_pow = (e && e[0] == '1') ? 1 : 0; }
 }

@@ -106,6 +106,7 @@ struct VIParams {
   double impl_fac;
   int Ne, Ne2D, NeZ;
   int exact_pow;              // pow() instead of exp(e log x) for the equation of state
+  const ElemTables* htab;     // HOST copy of the operator tables (the second kernel derives its constant-memory tables from it)
 };
 constexpr int MAXTERM = 20;   // 2 * stages of the largest IMEX scheme supported
 struct LinCombParams {
@@ -182,6 +183,7 @@ struct NumdiffParams {
 void launch_numdiff(int mode, const NumdiffParams& P, cudaStream_t s);
 
 void launch_vi(const VIParams& p, bool moist, cudaStream_t s);
+bool launch_vi2(const VIParams& p, const ElemTables& tab, bool moist, cudaStream_t s);
 void launch_lincomb(const LinCombParams& L, cudaStream_t s);
 void launch_lincomb_filter(const LinCombParams& L, const ElemTables* tab, const double* gsqrt, bool weighted, int Ne, int np,
                            cudaStream_t s);

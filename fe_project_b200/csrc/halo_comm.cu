@@ -116,8 +116,11 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
   asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
 }
-// gather the face nodes of six fields and store them into the neighbour's receive area (remote stores over NVLink)
-__global__ void pack_peer_kernel(SixFields q, const int* __restrict__ vmapB, PeerFaceSet fs) {
+// Gather the face nodes of six fields and store them into the neighbour's receive area (remote stores over NVLink); the last block to
+// finish raises the flags.  Ordering: every block synchronises, then ONE thread per block issues the system-scope fence (cumulative
+// over the block's stores through the barrier) before it counts the block as done; the last block fences again and publishes the
+// exchange number with release stores.
+__global__ void pack_peer_kernel(SixFields q, const int* __restrict__ vmapB, PeerFaceSet fs, unsigned long long seq, unsigned int* done_ctr) {
   const int g = blockIdx.x * blockDim.x + threadIdx.x;
   if (g < fs.start[fs.n]) {
     int i = 0;
@@ -128,14 +131,18 @@ __global__ void pack_peer_kernel(SixFields q, const int* __restrict__ vmapB, Pee
 #pragma unroll
     for (int v = 0; v < 6; ++v) buf[size_t(v) * cnt + m] = q.f[v][src];
   }
-  __threadfence_system();              // the stores of this thread are performed at system scope before the kernel ends
-}
-// after the pack kernel (stream order): publish the exchange number to every neighbour
-__global__ void signal_peer_kernel(PeerFaceSet fs, unsigned long long seq) {
-  const int i = threadIdx.x;
-  if (i >= fs.n) return;
-  __threadfence_system();
-  st_release_sys(fs.flag[i], seq);
+  __shared__ int last;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    last = (atomicAdd(done_ctr, 1u) == gridDim.x - 1) ? 1 : 0;
+  }
+  __syncthreads();
+  if (last && threadIdx.x < fs.n) {
+    __threadfence_system();
+    if (threadIdx.x == 0) *done_ctr = 0u;          // next exchange (stream-ordered after this kernel)
+    st_release_sys(fs.flag[threadIdx.x], seq);
+  }
 }
 // wait until the neighbour's data of exchange `seq` has landed, then scatter it into the halo slots of the six fields
 __global__ void wait_unpack_peer_kernel(SixFields q, size_t nint, PeerFaceSet fs, unsigned long long seq, long long timeout_clk) {
@@ -179,7 +186,7 @@ void peer_halo_init(CommState& cs, int device) {
   ph = PeerHalo{};
   { const char* e = getenv("FEDG_HALO"); if (e && std::strcmp(e, "nccl") == 0) return; }
   ncclComm_t comm = static_cast<ncclComm_t>(cs.comm);
-  // own area: 256 B of flags, then two parities of the remote faces
+  // own area: 256 B header (12 flags of 8 B; the pack kernel's block counter at byte 192), then two parities of the remote faces
   PeerTable mine{};
   size_t bytes = 256;
   for (int par = 0; par < 2; ++par)
@@ -320,8 +327,7 @@ int comm_exchange_start(CommState& cs, double* const q[NVAR], double* dp, const 
     for (int v = 0; v < NVAR; ++v) { six.f[v] = q[v]; ph.cur_q[v] = q[v]; }
     six.f[5] = dp; ph.cur_q[5] = dp; ph.cur_nint = nint;
     const int ntot = fs.start[cs.nremote];
-    pack_peer_kernel<<<(ntot + 255) / 256, 256, 0, compute>>>(six, d_vmapB, fs);
-    signal_peer_kernel<<<1, 32, 0, compute>>>(fs, seq);
+    pack_peer_kernel<<<(ntot + 255) / 256, 256, 0, compute>>>(six, d_vmapB, fs, seq, reinterpret_cast<unsigned int*>(ph.area + 192));
     return FEDG_OK;
   }
   FaceSet snd{}, rcv{};

@@ -131,29 +131,32 @@ VI_HD void rho_pivots(Coef& C, const Tables& T) {
   C.kap7b = C.k10 * T.lw0[0] + C.k11 * T.lw0[7]; C.kap7t = C.k10 * T.lw1[0] + C.k11 * T.lw1[7];
 }
 
-// The four linear forms the eliminated density leaves behind, over the columns (w_0..7, theta_0, rhs 0..3):
+// The four linear forms the eliminated density leaves behind, over the columns c = (w_0..7, theta_0, rhs 0..3):
 //   rho_0, rho_7 and phi0 = B0[0].zb, phi7 = B7[0].zt  with  rho_l = Rrho_l - dfac (D w)_l - lw0_l phi0 - lw1_l phi7.
-// Rrho0[r], Rrho7[r]: right-hand sides of the density rows of node 0 / 7.  LF[4][NLF] in the order rho0, rho7, phi0, phi7; the rhs
-// entries are the VALUES of the forms for unit right-hand side r (they move to the other side with a minus sign in the rows).
-VI_HD void rho_forms(const Coef& C, const Tables& T, const double* Rrho0, const double* Rrho7, double (*LF)[NLF]) {
-  for (int j = 0; j < N; ++j) {
-    const double x0 = -C.dfac * T.D[0 * N + j] - (j == 0 ? T.lw0[0] * C.B0[0][1] : 0.0) - (j == 7 ? T.lw1[0] * C.B7[0][1] : 0.0);
-    const double x7 = -C.dfac * T.D[7 * N + j] - (j == 0 ? T.lw0[7] * C.B0[0][1] : 0.0) - (j == 7 ? T.lw1[7] * C.B7[0][1] : 0.0);
-    LF[0][j] = C.k00 * x0 + C.k01 * x7;
-    LF[1][j] = C.k10 * x0 + C.k11 * x7;
+// The density rows have the right-hand sides Rrho_l[0] = Rrho0[l] (rhs 0) and Rrho_l[1+b] = lw1_l U[0][b].  out[4] = column c of
+// (rho0, rho7, phi0, phi7); the rhs entries are the VALUES of the forms for unit right-hand side r (they move to the other side with a
+// minus sign in the rows).
+VI_HD double rrho(const Coef& C, const Tables& T, int l, int r, double Rrho0_l) { return r == 0 ? Rrho0_l : T.lw1[l] * C.U[0][r - 1]; }
+VI_HD void rho_form_col(const Coef& C, const Tables& T, int c, double Rrho0_0, double Rrho0_7, double* out /* [4] */) {
+  double x0, x7;
+  if (c < N) {
+    x0 = -C.dfac * T.D[0 * N + c] - (c == 0 ? T.lw0[0] * C.B0[0][1] : 0.0) - (c == 7 ? T.lw1[0] * C.B7[0][1] : 0.0);
+    x7 = -C.dfac * T.D[7 * N + c] - (c == 0 ? T.lw0[7] * C.B0[0][1] : 0.0) - (c == 7 ? T.lw1[7] * C.B7[0][1] : 0.0);
+  } else if (c == 8) {
+    x0 = -T.lw0[0] * C.B0[0][2]; x7 = -T.lw0[7] * C.B0[0][2];
+  } else {
+    x0 = rrho(C, T, 0, c - 9, Rrho0_0); x7 = rrho(C, T, 7, c - 9, Rrho0_7);
   }
-  {
-    const double x0 = -T.lw0[0] * C.B0[0][2], x7 = -T.lw0[7] * C.B0[0][2];
-    LF[0][8] = C.k00 * x0 + C.k01 * x7;
-    LF[1][8] = C.k10 * x0 + C.k11 * x7;
-  }
-  for (int r = 0; r < NR; ++r) {
-    LF[0][9 + r] = C.k00 * Rrho0[r] + C.k01 * Rrho7[r];
-    LF[1][9 + r] = C.k10 * Rrho0[r] + C.k11 * Rrho7[r];
-  }
+  out[0] = C.k00 * x0 + C.k01 * x7;
+  out[1] = C.k10 * x0 + C.k11 * x7;
+  out[2] = C.B0[0][0] * out[0] + (c == 0 ? C.B0[0][1] : 0.0) + (c == 8 ? C.B0[0][2] : 0.0);
+  out[3] = C.B7[0][0] * out[1] + (c == 7 ? C.B7[0][1] : 0.0);
+}
+VI_HD void rho_forms(const Coef& C, const Tables& T, double Rrho0_0, double Rrho0_7, double (*LF)[NLF]) {
   for (int c = 0; c < NLF; ++c) {
-    LF[2][c] = C.B0[0][0] * LF[0][c] + (c == 0 ? C.B0[0][1] : 0.0) + (c == 8 ? C.B0[0][2] : 0.0);
-    LF[3][c] = C.B7[0][0] * LF[1][c] + (c == 7 ? C.B7[0][1] : 0.0);
+    double o[4];
+    rho_form_col(C, T, c, Rrho0_0, Rrho0_7, o);
+    for (int f = 0; f < 4; ++f) LF[f][c] = o[f];
   }
 }
 
@@ -166,9 +169,9 @@ VI_HD void row_rhs(const Coef& C, const Tables& T, int l, const double base[3], 
 }
 
 // Row l of [S_thth | S_thw | RHS_th] after the density has been eliminated (20 entries).
-//   pot, wt, s: node vectors; Rrho[m][r]: right-hand sides of the density rows; Rth[r]: of the own theta row; LF: rho_forms
+//   pot, wt, s: node vectors; Rrho0[m]: rhs 0 of the density rows; Rth[r]: right-hand sides of the own theta row; LF: rho_forms
 VI_HD void theta_row(const Coef& C, const Tables& T, int l, const double* pot, const double* wt, const double* s,
-                     const double (*Rrho)[NR], const double* Rth, const double (*LF)[NLF], double* A /* [20] */) {
+                     const double* Rrho0, const double* Rth, const double (*LF)[NLF], double* A /* [20] */) {
   const double* Dl = T.D + l * N;
   double a0 = 0.0, a7 = 0.0;                    // dfac (D (s o lw0))_l, dfac (D (s o lw1))_l
   for (int m = 0; m < N; ++m) { a0 += Dl[m] * (s[m] * T.lw0[m]); a7 += Dl[m] * (s[m] * T.lw1[m]); }
@@ -191,16 +194,17 @@ VI_HD void theta_row(const Coef& C, const Tables& T, int l, const double* pot, c
   }
   A[8 + 0] += T.lw0[l] * C.B0[2][1];
   A[8 + 7] += T.lw1[l] * C.B7[2][1];
-  // right-hand sides: Rth + dfac (D (s o Rrho))_l - lf[9 + r]
-  for (int r = 0; r < NR; ++r) {
+  // right-hand sides: Rth + dfac (D (s o Rrho))_l - lf[9 + r];  Rrho[:, 1+b] = lw1 U[0][b]  ->  dfac (D (s o lw1))_l U[0][b] = a7 U[0][b]
+  {
     double acc = 0.0;
-    for (int m = 0; m < N; ++m) acc += t[m] * Rrho[m][r];
-    A[16 + r] = Rth[r] + acc - lf[9 + r];
+    for (int m = 0; m < N; ++m) acc += t[m] * Rrho0[m];
+    A[16] = Rth[0] + acc - lf[9];
   }
+  for (int b = 0; b < 3; ++b) A[17 + b] = Rth[1 + b] + a7 * C.U[0][b] - lf[10 + b];
 }
 
 // Row l of the Schur complement [H | rhs_H] = [S_ww | RHS_w] - S_wth X, X = S_thth^-1 [S_thw | RHS_th] (8 x 12, row = theta unknown).
-VI_HD void schur_row(const Coef& C, const Tables& T, int l, const double* dpd, const double (*Rrho)[NR], const double* Rw,
+VI_HD void schur_row(const Coef& C, const Tables& T, int l, const double* dpd, const double* Rrho0, const double* Rw,
                      const double (*LF)[NLF], const double (*X)[12], double* H /* [12] */) {
   const double* Dl = T.D + l * N;
   const double a0 = -C.gfac * T.VPlw0[l], a7 = -C.gfac * T.VPlw1[l];
@@ -222,7 +226,8 @@ VI_HD void schur_row(const Coef& C, const Tables& T, int l, const double* dpd, c
   }
   for (int r = 0; r < NR; ++r) {
     double vp = 0.0;
-    for (int m = 0; m < N; ++m) vp += T.VP[l * N + m] * Rrho[m][r];
+    if (r == 0) { for (int m = 0; m < N; ++m) vp += T.VP[l * N + m] * Rrho0[m]; }
+    else vp = T.VPlw1[l] * C.U[0][r - 1];
     double h = Rw[r] - C.gfac * vp - lf[9 + r];
     for (int m = 0; m < N; ++m) h -= sw[m] * X[m][8 + r];
     H[8 + r] = h;
@@ -239,12 +244,12 @@ VI_HD void theta_solve(int k, const double (*X)[12], const double (*w)[NR], doub
 }
 
 // rho_l[r] = Rrho_l[r] - dfac (D w[:, r])_l - lw0_l phi0[r] - lw1_l phi7[r];  phi[r] = sum_j phi_w[j] w_j[r] + phi_t theta_0[r] + phi_r[r]
-VI_HD void rho_solve(const Coef& C, const Tables& T, int l, const double* Rrho_l, const double (*LF)[NLF], const double (*w)[NR],
+VI_HD void rho_solve(const Coef& C, const Tables& T, int l, double Rrho0_l, const double (*LF)[NLF], const double (*w)[NR],
                      const double* th0 /* [NR] */, double* rho /* [NR] */) {
   for (int r = 0; r < NR; ++r) {
     double dw = 0.0, p0 = LF[2][8] * th0[r] + LF[2][9 + r], p7 = LF[3][8] * th0[r] + LF[3][9 + r];
     for (int j = 0; j < N; ++j) { dw += T.D[l * N + j] * w[j][r]; p0 += LF[2][j] * w[j][r]; p7 += LF[3][j] * w[j][r]; }
-    rho[r] = Rrho_l[r] - C.dfac * dw - T.lw0[l] * p0 - T.lw1[l] * p7;
+    rho[r] = rrho(C, T, l, r, Rrho0_l) - C.dfac * dw - T.lw0[l] * p0 - T.lw1[l] * p7;
   }
 }
 

@@ -1,0 +1,85 @@
+"""Algebra of the block-eliminated vertical-implicit solve (fe_project_b200/csrc/vi_block.cuh, the row functions vi_column2_kernel is
+built from) on the CPU: tests/vi_block_host.cpp loops over the rows where the kernel splits them over two lanes, and must reproduce
+the oracle's cal_vi (dense 24 x 24 blocks, partial-pivot LU, block Thomas) on regional HEVI cases -- lumped and consistent mass
+matrix, several impl_fac, slip walls at both column ends, one and many elements per column."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from cases import DensityCurrentCase, SoundWaveCase, rel_l2
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+ORD = ("DDENS", "DRHOT", "MOMZ", "MOMX", "MOMY")            # oracle variable order
+DEV = ("DDENS", "MOMX", "MOMY", "MOMZ", "DRHOT")            # device variable order
+
+
+@pytest.fixture(scope="module")
+def vib():
+    so = os.path.join(HERE, "_vi_block_host.so")
+    src = os.path.join(HERE, "vi_block_host.cpp")
+    hdr = os.path.join(ROOT, "fe_project_b200", "csrc", "vi_block.cuh")
+    if not os.path.exists(so) or max(os.path.getmtime(src), os.path.getmtime(hdr)) > os.path.getmtime(so):
+        subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-fopenmp", "-shared", "-fPIC", "-x", "c++", "-I", os.path.dirname(hdr), src, "-o", so])
+    L = C.CDLL(so)
+    L.vib_cal_vi.argtypes = [C.c_int, C.c_int] + [C.c_void_p] * 10 + [C.c_void_p, C.c_double, C.c_void_p]
+    return L
+
+
+def _run(L, case, o, var0, impl_fac):
+    m, e = case.mesh, case.elem
+    n = m.Ne * e.Np
+    f64 = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+    q0 = [f64(var0[ORD.index(k)][:n]) for k in DEV]
+    qc = [f64(o.arr(k)[:n]) for k in DEV]
+    out = [np.zeros(n) for _ in DEV]
+    ptrs = lambda arrs: (C.c_void_p * 5)(*[a.ctypes.data for a in arrs])
+    dh, ph = f64(o.arr("DENS_hyd")[:n]), f64(o.arr("PRES_hyd")[:n])
+    E33 = f64(m.Escale[2, 2][:, 0])
+    Fb, Ft = f64(m.Fscale[:, 4 * e.Nfp]), f64(m.Fscale[:, 5 * e.Nfp])
+    D, VP, Lw = f64(e.D1D), f64(e.VPOrdM1), f64(e.lift1d)
+    c = case.consts
+    cst = f64([c["GRAV"], c["Rdry"], c["CPdry"], c["CVdry"], c["PRES00"]])
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    rc = L.vib_cal_vi(m.Ne2D, m.NeZ, ptrs(q0), ptrs(qc), p(dh), p(ph), p(E33), p(Fb), p(Ft), p(D), p(VP), p(Lw), p(cst), float(impl_fac), ptrs(out))
+    assert rc == 0
+    return dict(zip(DEV, out))
+
+
+CASES = {
+    "dc": lambda: DensityCurrentCase(p=7, NeX=2, NeY=2, NeZ=4, perturb=1.0, eqs="NONHYDRO3D_HEVI", tinteg="IMEX_ARK232", dt=0.5),
+    "dc_one_element": lambda: DensityCurrentCase(p=7, NeX=1, NeY=1, NeZ=1, perturb=1.0, eqs="NONHYDRO3D_HEVI", tinteg="IMEX_ARK232", dt=0.5),
+    "dc_thin": lambda: DensityCurrentCase(p=7, NeX=2, NeY=1, NeZ=6, perturb=2.0, eqs="NONHYDRO3D_HEVI", tinteg="IMEX_ARK232", dt=0.6,
+                                         dom=(0.0, 25.6e3, 0.0, 12.8e3, 0.0, 640.0)),
+    "sound_wave": lambda: SoundWaveCase(p=7, NeX=1, NeY=1, NeZ=20, dt=0.25, amplitude=1.0),
+}
+
+
+@pytest.mark.parametrize("name,impl_fac", [("dc", 0.0), ("dc", 0.05), ("dc", 2.0), ("dc", 20.0), ("dc_one_element", 0.5), ("dc_thin", 0.3),
+                                           ("dc_thin", 3.0), ("sound_wave", 0.1), ("sound_wave", 3.0)])
+def test_block_elimination_reproduces_cal_vi(vib, name, impl_fac):
+    case = CASES[name]()
+    o = case.make_oracle()
+    n = case.mesh.Ne * case.elem.Np
+    rng = np.random.default_rng(11)
+    var0 = np.stack([o.arr(k).copy() for k in ORD])
+    if impl_fac != 0.0:
+        var0[:, :n] += 1e-3 * rng.standard_normal((5, n)) * np.maximum(np.abs(var0[:, :n]).max(axis=1, keepdims=True), 1e-6)
+    ref = o.cal_vi(impl_fac, case.dt, var0)[:, :n]
+    got = _run(vib, case, o, var0, impl_fac)
+    for i, k in enumerate(ORD):
+        if impl_fac == 0.0:
+            assert rel_l2(got[k], ref[i]) <= 1e-12, (k, impl_fac)
+            continue
+        # the Newton iterate q* = q + impl_fac * tend is what the step uses; the tendency itself cancels to round-off where the
+        # vertical operator is inactive
+        qcur = o.arr(k)[:n]
+        qs_ref, qs_got = qcur + impl_fac * ref[i], qcur + impl_fac * got[k]
+        # a momentum component that is identically zero in the case (MOMX / MOMY of the 1D sound wave) is judged against rho * c_s
+        floor = 1e-6 * np.sqrt(n) if k in ("MOMX", "MOMY") else 0.0
+        err = np.linalg.norm(qs_got - qs_ref) / max(np.linalg.norm(qs_ref), floor)
+        tol = 1e-11 if not (name == "dc_thin" and impl_fac >= 3.0) else 2e-10     # vertical acoustic CFL ~150: conditioning of the block
+        assert err <= tol, (name, k, impl_fac, err)
