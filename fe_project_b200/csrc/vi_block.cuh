@@ -22,8 +22,10 @@
 
 #ifdef __CUDACC__
 #define VI_HD __host__ __device__ __forceinline__
+#define VI_UNROLL _Pragma("unroll")
 #else
 #define VI_HD inline
+#define VI_UNROLL
 #endif
 
 namespace fedg {
@@ -82,11 +84,11 @@ VI_HD void face_coef(Coef& C, bool bot, bool top, double hb2, double ht2, double
                      double dpd0, double pot7, double wt7, double dpd7, const FaceNbr& F) {
   const double s0 = pot0 * wt0, s7 = pot7 * wt7;
   double Lam[3][NR];
-  for (int a = 0; a < 3; ++a) for (int c = 0; c < NR; ++c) Lam[a][c] = 0.0;
+  VI_UNROLL for (int a = 0; a < 3; ++a) VI_UNROLL for (int c = 0; c < NR; ++c) Lam[a][c] = 0.0;
   if (!bot) {
     const double sn = F.potn_b * F.wtn_b;
     // L = lw0_l hb2 lam, lam = [[-alph_b, -1, 0], [0, -alph_b, -dpdn], [sn, -potn, -alph_b - wtn]];  Lam[a][c] = - sum_b lam[a][b] g[b][c]
-    for (int c = 0; c < NR; ++c) {
+    VI_UNROLL for (int c = 0; c < NR; ++c) {
       Lam[0][c] = alph_b * F.g[0][c] + F.g[1][c];
       Lam[1][c] = alph_b * F.g[1][c] + F.dpdn_b * F.g[2][c];
       Lam[2][c] = -sn * F.g[0][c] + F.potn_b * F.g[1][c] + (alph_b + F.wtn_b) * F.g[2][c];
@@ -102,7 +104,7 @@ VI_HD void face_coef(Coef& C, bool bot, bool top, double hb2, double ht2, double
   C.B0[2][0] = (bot ? -2.0 * hb2 * s0 : -hb2 * s0) + hb2 * Lam[2][1];
   C.B0[2][1] = (bot ? 2.0 * hb2 * pot0 : hb2 * pot0) + hb2 * Lam[2][2];
   C.B0[2][2] = (bot ? 2.0 * hb2 * wt0 : hb2 * (alph_b + wt0)) + hb2 * Lam[2][3];
-  for (int a = 0; a < 3; ++a) C.rb[a] = hb2 * Lam[a][0];
+  VI_UNROLL for (int a = 0; a < 3; ++a) C.rb[a] = hb2 * Lam[a][0];
   C.B7[0][0] = top ? 0.0 : ht2 * alph_t;
   C.B7[0][1] = top ? -2.0 * ht2 : -ht2;
   C.B7[0][2] = 0.0;
@@ -112,7 +114,7 @@ VI_HD void face_coef(Coef& C, bool bot, bool top, double hb2, double ht2, double
   C.B7[2][0] = (top ? 2.0 : 1.0) * ht2 * s7;
   C.B7[2][1] = top ? -2.0 * ht2 * pot7 : -ht2 * pot7;
   C.B7[2][2] = top ? -2.0 * ht2 * wt7 : ht2 * (alph_t - wt7);
-  for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) C.U[a][b] = 0.0;
+  VI_UNROLL for (int a = 0; a < 3; ++a) VI_UNROLL for (int b = 0; b < 3; ++b) C.U[a][b] = 0.0;
   if (!top) {
     const double sn = F.potn_t * F.wtn_t;
     C.U[0][0] = -ht2 * alph_t; C.U[0][1] = ht2;             C.U[0][2] = 0.0;
@@ -153,18 +155,18 @@ VI_HD void rho_form_col(const Coef& C, const Tables& T, int c, double Rrho0_0, d
   out[3] = C.B7[0][0] * out[1] + (c == 7 ? C.B7[0][1] : 0.0);
 }
 VI_HD void rho_forms(const Coef& C, const Tables& T, double Rrho0_0, double Rrho0_7, double (*LF)[NLF]) {
-  for (int c = 0; c < NLF; ++c) {
+  VI_UNROLL for (int c = 0; c < NLF; ++c) {
     double o[4];
     rho_form_col(C, T, c, Rrho0_0, Rrho0_7, o);
-    for (int f = 0; f < 4; ++f) LF[f][c] = o[f];
+    VI_UNROLL for (int f = 0; f < 4; ++f) LF[f][c] = o[f];
   }
 }
 
 // right-hand sides of the three rows of node l: base[a] = impl_fac * A_v - var0 + q (eval_Ax :306-317) for rhs 0
 VI_HD void row_rhs(const Coef& C, const Tables& T, int l, const double base[3], double R[3][NR]) {
-  for (int a = 0; a < 3; ++a) {
+  VI_UNROLL for (int a = 0; a < 3; ++a) {
     R[a][0] = base[a] + T.lw0[l] * C.rb[a];
-    for (int b = 0; b < 3; ++b) R[a][1 + b] = T.lw1[l] * C.U[a][b];
+    VI_UNROLL for (int b = 0; b < 3; ++b) R[a][1 + b] = T.lw1[l] * C.U[a][b];
   }
 }
 
@@ -174,22 +176,22 @@ VI_HD void theta_row(const Coef& C, const Tables& T, int l, const double* pot, c
                      const double* Rrho0, const double* Rth, const double (*LF)[NLF], double* A /* [20] */) {
   const double* Dl = T.D + l * N;
   double a0 = 0.0, a7 = 0.0;                    // dfac (D (s o lw0))_l, dfac (D (s o lw1))_l
-  for (int m = 0; m < N; ++m) { a0 += Dl[m] * (s[m] * T.lw0[m]); a7 += Dl[m] * (s[m] * T.lw1[m]); }
+  VI_UNROLL for (int m = 0; m < N; ++m) { a0 += Dl[m] * (s[m] * T.lw0[m]); a7 += Dl[m] * (s[m] * T.lw1[m]); }
   a0 *= C.dfac; a7 *= C.dfac;
   const double c0 = T.lw0[l] * C.B0[2][0], c7 = T.lw1[l] * C.B7[2][0];      // face terms on rho_0 / rho_7
   // lf[c] = a0 phi0[c] + a7 phi7[c] + c0 rho0[c] + c7 rho7[c]
   double lf[NLF];
-  for (int c = 0; c < NLF; ++c) lf[c] = a0 * LF[2][c] + a7 * LF[3][c] + c0 * LF[0][c] + c7 * LF[1][c];
+  VI_UNROLL for (int c = 0; c < NLF; ++c) lf[c] = a0 * LF[2][c] + a7 * LF[3][c] + c0 * LF[0][c] + c7 * LF[1][c];
   // theta columns
-  for (int j = 0; j < N; ++j) A[j] = (j == l ? 1.0 : 0.0) + C.dfac * Dl[j] * wt[j];
+  VI_UNROLL for (int j = 0; j < N; ++j) A[j] = (j == l ? 1.0 : 0.0) + C.dfac * Dl[j] * wt[j];
   A[0] += T.lw0[l] * C.B0[2][2] + lf[8];
   A[7] += T.lw1[l] * C.B7[2][2];
   // w columns: dfac D_lj pot_j + dfac^2 sum_m D_lm s_m D_mj + lf[j] + face
   double t[N];
-  for (int m = 0; m < N; ++m) t[m] = C.dfac * Dl[m] * s[m];
-  for (int j = 0; j < N; ++j) {
+  VI_UNROLL for (int m = 0; m < N; ++m) t[m] = C.dfac * Dl[m] * s[m];
+  VI_UNROLL for (int j = 0; j < N; ++j) {
     double acc = Dl[j] * pot[j];
-    for (int m = 0; m < N; ++m) acc += t[m] * T.D[m * N + j];
+    VI_UNROLL for (int m = 0; m < N; ++m) acc += t[m] * T.D[m * N + j];
     A[8 + j] = C.dfac * acc + lf[j];
   }
   A[8 + 0] += T.lw0[l] * C.B0[2][1];
@@ -197,10 +199,10 @@ VI_HD void theta_row(const Coef& C, const Tables& T, int l, const double* pot, c
   // right-hand sides: Rth + dfac (D (s o Rrho))_l - lf[9 + r];  Rrho[:, 1+b] = lw1 U[0][b]  ->  dfac (D (s o lw1))_l U[0][b] = a7 U[0][b]
   {
     double acc = 0.0;
-    for (int m = 0; m < N; ++m) acc += t[m] * Rrho0[m];
+    VI_UNROLL for (int m = 0; m < N; ++m) acc += t[m] * Rrho0[m];
     A[16] = Rth[0] + acc - lf[9];
   }
-  for (int b = 0; b < 3; ++b) A[17 + b] = Rth[1 + b] + a7 * C.U[0][b] - lf[10 + b];
+  VI_UNROLL for (int b = 0; b < 3; ++b) A[17 + b] = Rth[1 + b] + a7 * C.U[0][b] - lf[10 + b];
 }
 
 // Row l of the Schur complement [H | rhs_H] = [S_ww | RHS_w] - S_wth X, X = S_thth^-1 [S_thw | RHS_th] (8 x 12, row = theta unknown).
@@ -210,35 +212,35 @@ VI_HD void schur_row(const Coef& C, const Tables& T, int l, const double* dpd, c
   const double a0 = -C.gfac * T.VPlw0[l], a7 = -C.gfac * T.VPlw1[l];
   const double c0 = T.lw0[l] * C.B0[1][0];
   double lf[NLF];
-  for (int c = 0; c < NLF; ++c) lf[c] = a0 * LF[2][c] + a7 * LF[3][c] + c0 * LF[0][c];
+  VI_UNROLL for (int c = 0; c < NLF; ++c) lf[c] = a0 * LF[2][c] + a7 * LF[3][c] + c0 * LF[0][c];
   // S_wth row: dfac D_lj dpd_j + face (theta_0, theta_7) + lf[8] on theta_0
   double sw[N];
-  for (int j = 0; j < N; ++j) sw[j] = C.dfac * Dl[j] * dpd[j];
+  VI_UNROLL for (int j = 0; j < N; ++j) sw[j] = C.dfac * Dl[j] * dpd[j];
   sw[0] += T.lw0[l] * C.B0[1][2] + lf[8];
   sw[7] += T.lw1[l] * C.B7[1][2];
   const double gd = C.gfac * C.dfac;
-  for (int j = 0; j < N; ++j) {
+  VI_UNROLL for (int j = 0; j < N; ++j) {
     double h = (j == l ? 1.0 : 0.0) - gd * T.VPD[l * N + j] + lf[j];
     if (j == 0) h += T.lw0[l] * C.B0[1][1];
     if (j == 7) h += T.lw1[l] * C.B7[1][1];
-    for (int m = 0; m < N; ++m) h -= sw[m] * X[m][j];
+    VI_UNROLL for (int m = 0; m < N; ++m) h -= sw[m] * X[m][j];
     H[j] = h;
   }
-  for (int r = 0; r < NR; ++r) {
+  VI_UNROLL for (int r = 0; r < NR; ++r) {
     double vp = 0.0;
-    if (r == 0) { for (int m = 0; m < N; ++m) vp += T.VP[l * N + m] * Rrho0[m]; }
+    if (r == 0) { VI_UNROLL for (int m = 0; m < N; ++m) vp += T.VP[l * N + m] * Rrho0[m]; }
     else vp = T.VPlw1[l] * C.U[0][r - 1];
     double h = Rw[r] - C.gfac * vp - lf[9 + r];
-    for (int m = 0; m < N; ++m) h -= sw[m] * X[m][8 + r];
+    VI_UNROLL for (int m = 0; m < N; ++m) h -= sw[m] * X[m][8 + r];
     H[8 + r] = h;
   }
 }
 
 // theta_k[r] = X[k][8 + r] - sum_j X[k][j] w_j[r]
 VI_HD void theta_solve(int k, const double (*X)[12], const double (*w)[NR], double* th /* [NR] */) {
-  for (int r = 0; r < NR; ++r) {
+  VI_UNROLL for (int r = 0; r < NR; ++r) {
     double a = X[k][8 + r];
-    for (int j = 0; j < N; ++j) a -= X[k][j] * w[j][r];
+    VI_UNROLL for (int j = 0; j < N; ++j) a -= X[k][j] * w[j][r];
     th[r] = a;
   }
 }
@@ -246,9 +248,9 @@ VI_HD void theta_solve(int k, const double (*X)[12], const double (*w)[NR], doub
 // rho_l[r] = Rrho_l[r] - dfac (D w[:, r])_l - lw0_l phi0[r] - lw1_l phi7[r];  phi[r] = sum_j phi_w[j] w_j[r] + phi_t theta_0[r] + phi_r[r]
 VI_HD void rho_solve(const Coef& C, const Tables& T, int l, double Rrho0_l, const double (*LF)[NLF], const double (*w)[NR],
                      const double* th0 /* [NR] */, double* rho /* [NR] */) {
-  for (int r = 0; r < NR; ++r) {
+  VI_UNROLL for (int r = 0; r < NR; ++r) {
     double dw = 0.0, p0 = LF[2][8] * th0[r] + LF[2][9 + r], p7 = LF[3][8] * th0[r] + LF[3][9 + r];
-    for (int j = 0; j < N; ++j) { dw += T.D[l * N + j] * w[j][r]; p0 += LF[2][j] * w[j][r]; p7 += LF[3][j] * w[j][r]; }
+    VI_UNROLL for (int j = 0; j < N; ++j) { dw += T.D[l * N + j] * w[j][r]; p0 += LF[2][j] * w[j][r]; p7 += LF[3][j] * w[j][r]; }
     rho[r] = rrho(C, T, l, r, Rrho0_l) - C.dfac * dw - T.lw0[l] * p0 - T.lw1[l] * p7;
   }
 }

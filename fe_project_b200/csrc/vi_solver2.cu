@@ -122,14 +122,13 @@ __device__ __forceinline__ void gauss_jordan_pair(double (&A)[4][W], int h, int 
     }
     const double ob = __shfl_xor_sync(FULL, best, 1);
     const bool mine = (best > ob) || (best == ob && h == 0);
-    double p[W];
-#pragma unroll
-    for (int j = k; j < W; ++j) {
-      const double c = sel4(cs, A[0][j], A[1][j], A[2][j], A[3][j]);
+    double pk;
+    {
+      const double c = sel4(cs, A[0][k], A[1][k], A[2][k], A[3][k]);
       const double o = __shfl_xor_sync(FULL, c, 1);
-      p[j] = mine ? c : o;
+      pk = mine ? c : o;
     }
-    const double rp = 1.0 / p[k];
+    const double rp = 1.0 / pk;
     double m[4];
 #pragma unroll
     for (int s = 0; s < 4; ++s) {
@@ -138,9 +137,13 @@ __device__ __forceinline__ void gauss_jordan_pair(double (&A)[4][W], int h, int 
       if (is_piv) { used |= 1u << s; kk[s] = k; rpiv[s] = rp; }
     }
 #pragma unroll
-    for (int j = k + 1; j < W; ++j)
+    for (int j = k + 1; j < W; ++j) {
+      const double c = sel4(cs, A[0][j], A[1][j], A[2][j], A[3][j]);
+      const double o = __shfl_xor_sync(FULL, c, 1);
+      const double pj = mine ? c : o;
 #pragma unroll
-      for (int s = 0; s < 4; ++s) A[s][j] -= m[s] * p[j];
+      for (int s = 0; s < 4; ++s) A[s][j] -= m[s] * pj;
+    }
   }
 }
 
@@ -258,38 +261,18 @@ __global__ void __launch_bounds__(V2_THREADS, IMPLICIT ? 3 : 6) vi_column2_kerne
       sm.C = C;
     }
     // state entering the stage at the own rows, right-hand sides of rhs 0 (eval_Ax :306-317: impl_fac A_t - PROG_VARS + q00)
-    double base[4][3], bu[4], bv[4];
+    double Rrho_own[4], Rw0[4], Rth0[4], bu[4], bv[4];
 #pragma unroll
     for (int a = 0; a < 4; ++a) {
       const size_t n = node(kz, 4 * h + a);
-      base[a][0] = ifac * t_r[a] - base_in[a][0] + P.qcur[V_DDENS][n];
-      base[a][1] = ifac * t_w[a] - base_in[a][1] + P.qcur[V_MOMZ][n];
-      base[a][2] = ifac * t_t[a] - base_in[a][2] + P.qcur[V_DRHOT][n];
+      Rrho_own[a] = ifac * t_r[a] - base_in[a][0] + P.qcur[V_DDENS][n];
+      Rw0[a] = ifac * t_w[a] - base_in[a][1] + P.qcur[V_MOMZ][n];
+      Rth0[a] = ifac * t_t[a] - base_in[a][2] + P.qcur[V_DRHOT][n];
       bu[a] = ifac * t_u[a] - base_in[a][3] + P.qcur[V_MOMX][n];
       bv[a] = ifac * t_v[a] - base_in[a][4] + P.qcur[V_MOMY][n];
     }
-    pair_sync();
-    const Coef& C = sm.C;
-#pragma unroll
-    for (int a = 0; a < 4; ++a) { const int l = 4 * h + a; sm.Rrho0[l] = base[a][0] + T.lw0[l] * C.rb[0]; }
-    pair_sync();
-    // ---- linear forms of the eliminated density: the 13 columns are split over the two lanes
-    {
-      const double r00 = sm.Rrho0[0], r07 = sm.Rrho0[7];
-#pragma unroll
-      for (int cc = 0; cc < 7; ++cc) {
-        const int c = 2 * cc + h;
-        if (c < NLF) {
-          double o[4];
-          rho_form_col(C, T, c, r00, r07, o);
-          sm.LF[0][c] = o[0]; sm.LF[1][c] = o[1]; sm.LF[2][c] = o[2]; sm.LF[3][c] = o[3];
-        }
-      }
-    }
-    pair_sync();
-
-    // ---- (MOMX, MOMY): (I + ua0 e0^T + ua7 e7^T) x = [bu | bv | bg]  (construct_matbnd_uv :960-1003, solve_uv :640-674)
-    double su[4], sv[4], sg[4];
+    // ---- (MOMX, MOMY): (I + ua0 e0^T + ua7 e7^T) x = [bu | bv | bg]  (construct_matbnd_uv :960-1003, solve_uv :640-674); the
+    // solution goes to the scratch arrays at once
     {
       double ua0[4], ua7[4], bg[4];
 #pragma unroll
@@ -314,11 +297,40 @@ __global__ void __launch_bounds__(V2_THREADS, IMPLICIT ? 3 : 6) vi_column2_kerne
 #pragma unroll
       for (int a = 0; a < 4; ++a) {
         const int l = 4 * h + a;
-        su[a] = (l == 0) ? xu0 : (l == 7) ? xu7 : bu[a] - ua0[a] * xu0 - ua7[a] * xu7;
-        sv[a] = (l == 0) ? xv0 : (l == 7) ? xv7 : bv[a] - ua0[a] * xv0 - ua7[a] * xv7;
-        sg[a] = (l == 0) ? xg0 : (l == 7) ? xg7 : bg[a] - ua0[a] * xg0 - ua7[a] * xg7;
+        const double xu = (l == 0) ? xu0 : (l == 7) ? xu7 : bu[a] - ua0[a] * xu0 - ua7[a] * xu7;
+        const double xv = (l == 0) ? xv0 : (l == 7) ? xv7 : bv[a] - ua0[a] * xv0 - ua7[a] * xv7;
+        const double xg = (l == 0) ? xg0 : (l == 7) ? xg7 : bg[a] - ua0[a] * xg0 - ua7[a] * xg7;
+        scr[scr_uv + ((size_t(kz) * 3 + 0) * 8 + l) * ncol + col] = xu;
+        scr[scr_uv + ((size_t(kz) * 3 + 1) * 8 + l) * ncol + col] = xv;
+        scr[scr_uv + ((size_t(kz) * 3 + 2) * 8 + l) * ncol + col] = xg;
+      }
+      // every read of the old hand-over values precedes the shuffles above: the top node's solution can take their place
+      if (h == 1) { sm.uvp[0] = xu7; sm.uvp[1] = xv7; sm.uvp[2] = xg7; }
+    }
+    pair_sync();
+    if (h == 1) put_node(sm.prev, M7);       // every read of the old hand-over node is done (face states, face_coef)
+    const Coef& C = sm.C;
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      const int l = 4 * h + a;
+      sm.Rrho0[l] = Rrho_own[a] + T.lw0[l] * C.rb[0];
+      Rw0[a] += T.lw0[l] * C.rb[1]; Rth0[a] += T.lw0[l] * C.rb[2];
+    }
+    pair_sync();
+    // ---- linear forms of the eliminated density: the 13 columns are split over the two lanes
+    {
+      const double r00 = sm.Rrho0[0], r07 = sm.Rrho0[7];
+#pragma unroll
+      for (int cc = 0; cc < 7; ++cc) {
+        const int c = 2 * cc + h;
+        if (c < NLF) {
+          double o[4];
+          rho_form_col(C, T, c, r00, r07, o);
+          sm.LF[0][c] = o[0]; sm.LF[1][c] = o[1]; sm.LF[2][c] = o[2]; sm.LF[3][c] = o[3];
+        }
       }
     }
+    pair_sync();
 
     // ---- theta block: [S_thth | S_thw | RHS_th] rows of the own nodes, Gauss-Jordan, X to shared memory
     {
@@ -327,10 +339,11 @@ __global__ void __launch_bounds__(V2_THREADS, IMPLICIT ? 3 : 6) vi_column2_kerne
       for (int a = 0; a < 4; ++a) {
         const int l = 4 * h + a;
         double Rth[NR];
-        Rth[0] = base[a][2] + T.lw0[l] * C.rb[2];
+        Rth[0] = Rth0[a];
 #pragma unroll
         for (int b = 0; b < 3; ++b) Rth[1 + b] = T.lw1[l] * C.U[2][b];
         theta_row(C, T, l, vpot, vwt, vs, sm.Rrho0, Rth, sm.LF, A[a]);
+        asm volatile("" ::: "memory");      // keep the loads of the next row behind this one (register pressure)
       }
       pair_sync();                            // the operator-evaluation vectors (union with X) are dead on both lanes
       int kk[4];
@@ -349,10 +362,11 @@ __global__ void __launch_bounds__(V2_THREADS, IMPLICIT ? 3 : 6) vi_column2_kerne
       for (int a = 0; a < 4; ++a) {
         const int l = 4 * h + a;
         double Rw[NR];
-        Rw[0] = base[a][1] + T.lw0[l] * C.rb[1];
+        Rw[0] = Rw0[a];
 #pragma unroll
         for (int b = 0; b < 3; ++b) Rw[1 + b] = T.lw1[l] * C.U[1][b];
         schur_row(C, T, l, vdpd, sm.Rrho0, Rw, sm.LF, sm.u.X, Hm[a]);
+        asm volatile("" ::: "memory");
       }
       int kw[4];
       double rpiv[4];
@@ -392,16 +406,11 @@ __global__ void __launch_bounds__(V2_THREADS, IMPLICIT ? 3 : 6) vi_column2_kerne
         scr[((size_t(kz) * 12 + 1 * 4 + r) * 8 + l) * ncol + col] = wl[a][r];
         scr[((size_t(kz) * 12 + 2 * 4 + r) * 8 + l) * ncol + col] = th[a][r];
       }
-      scr[scr_uv + ((size_t(kz) * 3 + 0) * 8 + l) * ncol + col] = su[a];
-      scr[scr_uv + ((size_t(kz) * 3 + 1) * 8 + l) * ncol + col] = sv[a];
-      scr[scr_uv + ((size_t(kz) * 3 + 2) * 8 + l) * ncol + col] = sg[a];
     }
     pair_sync();
     if (h == 1) {
-      put_node(sm.prev, M7);
 #pragma unroll
       for (int r = 0; r < NR; ++r) { sm.g[0][r] = rho[3][r]; sm.g[1][r] = wl[3][r]; sm.g[2][r] = th[3][r]; }
-      sm.uvp[0] = su[3]; sm.uvp[1] = sv[3]; sm.uvp[2] = sg[3];
     }
     pair_sync();
   }

@@ -1,0 +1,28 @@
+"""two independent restatements of the dynamics rows agree.  oracle/numpy_dyn.py (NumPy, written from the Fortran)
+against oracle/dyn_heve.cpp (C++) for pressure, numerical flux + explicit HEVE tendency on flat and terrain-following meshes; the
+vertical-implicit Newton step has its own second restatement in tests/test_vi_block_host.py (different elimination, different code)."""
+import numpy as np
+import pytest
+
+from cases import DensityCurrentCase, rel_l2
+import numpy_dyn
+
+
+@pytest.mark.parametrize("p,dims,periodic", [(7, (3, 2, 2), (False, True, False)), (3, (4, 3, 3), (True, True, False)), (5, (2, 2, 2), (False, False, False))])
+def test_numpy_restatement_of_flux_and_tendency_equals_the_cpp_oracle(p, dims, periodic):
+    case = DensityCurrentCase(p=p, NeX=dims[0], NeY=dims[1], NeZ=dims[2], perturb=2.0, periodic=periodic, intrp_order=min(11, p + 4))
+    o = case.make_oracle()
+    for w in ("exchange", "pressure", "bc", "tend_ex"):
+        o.piece(w)
+    e, m, c = case.elem, case.mesh, case.consts
+    n, N = m.Ne * e.Np, m.NeA * e.Np
+    q = {k: o.arr(k).copy() for k in ("DDENS", "MOMX", "MOMY", "MOMZ", "DRHOT")}            # halo + boundary condition applied by the oracle
+    aux = {k: o.arr(k).copy() for k in ("DENS_hyd", "PRES_hyd", "THERM_hyd")}
+    R, cv, cp = o.arr("Rtot"), o.arr("CVtot"), o.arr("CPtot")
+    pres, dpres = numpy_dyn.drhot2pres(c, q["DRHOT"], aux["PRES_hyd"], aux["THERM_hyd"], R, cv, cp)
+    assert rel_l2(pres[:n], o.arr("PRES")[:n]) <= 1e-15
+    # the halo of DPRES is exchanged like a field: take the oracle's, whose interior we have just reproduced
+    t = numpy_dyn.cal_tend_heve(e, m, c, q, aux, o.arr("DPRES"), o.arr("DPhydDx"), o.arr("DPhydDy"))
+    te = o.arr("tend_ex")[:5 * N].reshape(5, -1)[:, :n]
+    for nm, iv in (("DENS_dt", 0), ("RHOT_dt", 1), ("MOMZ_dt", 2), ("MOMX_dt", 3), ("MOMY_dt", 4)):
+        assert rel_l2(t[nm].reshape(-1), te[iv]) <= 1e-13, nm
