@@ -17,19 +17,29 @@ ORD = ("DDENS", "DRHOT", "MOMZ", "MOMX", "MOMY")            # oracle variable or
 DEV = ("DDENS", "MOMX", "MOMY", "MOMZ", "DRHOT")            # device variable order
 
 
+def _build(so, src, extra=()):
+    hdr = os.path.join(ROOT, "fe_project_b200", "csrc", "vi_block.cuh")
+    deps = [src, hdr, os.path.join(HERE, "vi_block_host.cpp")]
+    if not os.path.exists(so) or max(os.path.getmtime(d) for d in deps) > os.path.getmtime(so):
+        subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-fopenmp", "-shared", "-fPIC", "-x", "c++", "-I", os.path.dirname(hdr), "-I", HERE, src, "-o", so])
+    return C.CDLL(so)
+
+
+@pytest.fixture(scope="module")
+def vib_ld():
+    L = _build(os.path.join(HERE, "_vi_block_host_ld.so"), os.path.join(HERE, "vi_block_host_ld.cpp"))
+    L.vib_cal_vi_ld.argtypes = [C.c_int, C.c_int] + [C.c_void_p] * 10 + [C.c_void_p, C.c_double, C.c_void_p]
+    return L
+
+
 @pytest.fixture(scope="module")
 def vib():
-    so = os.path.join(HERE, "_vi_block_host.so")
-    src = os.path.join(HERE, "vi_block_host.cpp")
-    hdr = os.path.join(ROOT, "fe_project_b200", "csrc", "vi_block.cuh")
-    if not os.path.exists(so) or max(os.path.getmtime(src), os.path.getmtime(hdr)) > os.path.getmtime(so):
-        subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-fopenmp", "-shared", "-fPIC", "-x", "c++", "-I", os.path.dirname(hdr), src, "-o", so])
-    L = C.CDLL(so)
+    L = _build(os.path.join(HERE, "_vi_block_host.so"), os.path.join(HERE, "vi_block_host.cpp"))
     L.vib_cal_vi.argtypes = [C.c_int, C.c_int] + [C.c_void_p] * 10 + [C.c_void_p, C.c_double, C.c_void_p]
     return L
 
 
-def _run(L, case, o, var0, impl_fac):
+def _run(L, case, o, var0, impl_fac, fn="vib_cal_vi"):
     m, e = case.mesh, case.elem
     n = m.Ne * e.Np
     f64 = lambda a: np.ascontiguousarray(a, dtype=np.float64)
@@ -44,7 +54,7 @@ def _run(L, case, o, var0, impl_fac):
     c = case.consts
     cst = f64([c["GRAV"], c["Rdry"], c["CPdry"], c["CVdry"], c["PRES00"]])
     p = lambda a: a.ctypes.data_as(C.c_void_p)
-    rc = L.vib_cal_vi(m.Ne2D, m.NeZ, ptrs(q0), ptrs(qc), p(dh), p(ph), p(E33), p(Fb), p(Ft), p(D), p(VP), p(Lw), p(cst), float(impl_fac), ptrs(out))
+    rc = getattr(L, fn)(m.Ne2D, m.NeZ, ptrs(q0), ptrs(qc), p(dh), p(ph), p(E33), p(Fb), p(Ft), p(D), p(VP), p(Lw), p(cst), float(impl_fac), ptrs(out))
     assert rc == 0
     return dict(zip(DEV, out))
 
@@ -83,3 +93,33 @@ def test_block_elimination_reproduces_cal_vi(vib, name, impl_fac):
         err = np.linalg.norm(qs_got - qs_ref) / max(np.linalg.norm(qs_ref), floor)
         tol = 1e-11 if not (name == "dc_thin" and impl_fac >= 3.0) else 2e-10     # vertical acoustic CFL ~150: conditioning of the block
         assert err <= tol, (name, k, impl_fac, err)
+
+
+@pytest.mark.parametrize("nez,impl_fac", [(4, 33.0), (12, 8.2)])
+def test_block_elimination_is_as_accurate_as_the_reference_lu(vib, vib_ld, nez, impl_fac):
+    """Columns of BASELINE config 4 (30 km deep, dt = 75 s at 4 levels / 18.75 s at 12 levels: vertical acoustic CFL ~ 100) with a
+    near-rest state whose perturbations are 1e-5 of the background, as in the balanced baroclinic-wave state.  Against a 19-digit
+    solution of the same systems (the harness in long double) the oracle's partial-pivot LU and the block elimination are EQUALLY
+    far off -- ~1e-11 of the perturbation fields per solve: the conditioning of the problem, not of either algorithm.  This is why
+    the config-4 parity tests judge DDENS / DRHOT / MOMZ at 1e-10 against the full-field scales and only at 2e-9 against their own
+    norms (tests/test_gpu_config_sizes.py)."""
+    case = DensityCurrentCase(p=7, NeX=1, NeY=1, NeZ=nez, dom=(0, 100e3, 0, 100e3, 0, 30e3), dt=75.0, eqs="NONHYDRO3D_HEVI", tinteg="IMEX_ARK324")
+    o = case.make_oracle()
+    n = case.mesh.Ne * case.elem.Np
+    rng = np.random.default_rng(3)
+    var0 = np.stack([o.arr(k).copy() for k in ORD])
+    pert = 1e-5
+    var0[0, :n] = pert * rng.standard_normal(n); var0[1, :n] = pert * 300 * rng.standard_normal(n); var0[2, :n] = pert * 10 * rng.standard_normal(n)
+    for i, k in enumerate(ORD):
+        o.arr(k)[:n] = var0[i, :n] * (1 + 0.1 * rng.standard_normal(n))
+    ref = _run(vib_ld, case, o, var0, impl_fac, fn="vib_cal_vi_ld")
+    blk = _run(vib, case, o, var0, impl_fac)
+    orc = o.cal_vi(impl_fac, case.dt, var0)[:, :n]
+    for i, k in enumerate(ORD[:3]):
+        qc = o.arr(k)[:n]
+        qr = qc + impl_fac * ref[k]
+        e_blk = np.linalg.norm(qc + impl_fac * blk[k] - qr) / np.linalg.norm(qr)
+        e_orc = np.linalg.norm(qc + impl_fac * orc[i] - qr) / np.linalg.norm(qr)
+        print(f"{k}: block {e_blk:.2e}  oracle LU {e_orc:.2e}  (relative to the perturbation field, vs long double)")
+        assert e_blk <= 3.0 * e_orc + 1e-13, (k, e_blk, e_orc)
+        assert e_orc >= 1e-13, "the column systems of config 4 are not solvable to 1e-13 of the perturbation in double precision"

@@ -8,12 +8,12 @@ import fe_project_b200._lib as _L
 if os.environ.get("AB_LIB"):
     _L.LIB_PATH = os.path.join(ROOT, "fe_project_b200", os.environ["AB_LIB"])
 import bench
-from cases import DensityCurrentCase
+from fe_project_b200.cases import DensityCurrentCase
 from fe_project_b200.dyncore import rk_tables
 
 W = bench.WORKLOAD
 hevi = os.environ.get("AB_EQS", "heve") == "hevi"
-case = DensityCurrentCase(p=7, NeX=32, NeY=32, NeZ=16, dom=W["dom"], dt=(2 * W["dt"] if hevi else W["dt"]),
+case = DensityCurrentCase(p=7, NeX=32, NeY=32, NeZ=16, dom=W["dom"], dt=(1.5 * W["dt"] if hevi else W["dt"]),
                           tinteg=("IMEX_ARK324" if hevi else W["tinteg"]), modalfilter=True,
                           eqs=("NONHYDRO3D_HEVI" if hevi else "NONHYDRO3D_HEVE"))
 d = case.make_driver(None)
