@@ -263,12 +263,14 @@ def run_sphere(args, rank=0, world=1, local_rank=0):
             return obj[0]
     from fe_project_b200.cases import GlobalSphereCase
     from fe_project_b200.dyncore import PROG_NAMES
-    ne, nez = (args.nex if args.nex != WORKLOAD["NeX"] else 32), (args.nez if args.nez != WORKLOAD["NeZ"] else 12)
+    # configs[3]: NeGX = NeGY = 32, NeZ = 12; configs[4] (--sphere-ne N): the same run with N elements per panel edge, sized by the caller
+    # so that the state fills the HBM of the GPUs it runs on
+    ne, nez = (args.sphere_ne or 32), (args.nez if args.nez != WORKLOAD["NeZ"] else 12)
     from fe_project_b200.cubedsphere import panel_owner
     ntile = 2 if world in (4, 8) else 1          # 4 / 8 GPUs: 2 x 2 tiles per panel (24 local meshes), the same sphere
     own_ids = [t for t, r in enumerate(panel_owner(world, ntile)) if r == rank]
-    case = GlobalSphereCase(p=7, Ne=ne // ntile, NeZ=nez, dt=5.0 * 32 / ne, tinteg="IMEX_ARK324", modalfilter=True, ntile=ntile,
-                            fields_for=own_ids)
+    # run.conf of test/case/baroclinic_wave_global: Jablonowski-Williamson state, lumped mass matrix, stretched FZ, eta_c = 0, sponge
+    case = GlobalSphereCase.config4(Ne=ne // ntile, NeZ=nez, ntile=ntile, fields_for=own_ids)
     g = case.make_driver(rank=rank, nranks=world, bcast=bcast)
     W, K = max(3, args.warmup), args.steps
     g.Update(W)
@@ -293,8 +295,10 @@ def run_sphere(args, rank=0, world=1, local_rank=0):
     own = [case.cs.panels[P] for P in g.panel_ids]
     states = [d.get_prog() for d in g.panels]
     finite = all(np.isfinite(st[k][:Np * m.Ne]).all() for st, m in zip(states, own) for k in PROG_NAMES)
+    free_b, total_b = torch.cuda.mem_get_info()
+    hbm_used_gb = (total_b - free_b) / 1e9
     # e2e: host state of the own panels in, one step, host state out
-    ne2e = 3
+    ne2e = 1 if args.sphere_ne and args.sphere_ne > 48 else 3
     if dist:
         dist.barrier()
     t0 = time.perf_counter()
@@ -314,10 +318,11 @@ def run_sphere(args, rank=0, world=1, local_rank=0):
         emit(dict(
             metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=K, warmup=W, ms_per_step=ms_total / K, higher_is_better=True,
             scaling=("weak" if world == 1 else "strong"), vs_baseline=None, dtype="f64", data="synthetic",
-            config=dict(workload=f"atm_nonhydro3d global cubed sphere 6x{ne}x{ne}x{nez} elements p=7, GLOBALNONHYDRO3D_HEVI, IMEX_ARK324, "
-                                 f"dt={case.dt}, modal filter on, {len(own_ids)} {'panel' if ntile == 1 else 'tile (2x2 per panel)'}(s) per GPU as local meshes with linked halos"
+            config=dict(workload=f"atm_nonhydro3d global baroclinic wave (Jablonowski-Williamson) on the cubed sphere 6x{ne}x{ne}x{nez} elements p=7, "
+                                 f"GLOBALNONHYDRO3D_HEVI, IMEX_ARK324, dt={case.dt}, lumped mass matrix, stretched FZ, modal filter eta_c=0, sponge layer, {len(own_ids)} {'panel' if ntile == 1 else 'tile (2x2 per panel)'}(s) per GPU as local meshes with linked halos"
                                  + (", panel edges between ranks over NCCL" if world > 1 else ""),
-                        dof=dof, l2_policy="inputs larger than L2 (50 MB per field and panel)"),
+                        dof=dof, l2_policy="inputs larger than L2 (50 MB per field and panel)", hbm_used_gb_rank0=round(hbm_used_gb, 1),
+                        vi_kernel=os.environ.get("FEDG_VI_KERNEL", "2")),
             clocks=clocks, e2e=dict(value=dof / t_e2e, unit=UNIT, h2d_bytes_per_step=nbytes, d2h_bytes_per_step=nbytes, steps_per_call=1),
             gpu_launches=tm["launches"],
             roofline=dict(bound="fp64", achieved=None, peak=34.07, unit="TFLOP/s", frac=None, traffic=None,
@@ -337,6 +342,7 @@ def main():
     ap.add_argument("--ney", type=int, default=WORKLOAD["NeY"])
     ap.add_argument("--nez", type=int, default=WORKLOAD["NeZ"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--sphere-ne", type=int, default=0, help="global_sphere: elements per panel edge (default 32 = configs[3]; configs[4] sizes it to the HBM)")
     ap.add_argument("--eqs", default="heve", choices=["heve", "hevi"], help="hevi: NONHYDRO3D_HEVI + IMEX_ARK324 (extra, not the headline)")
     ap.add_argument("--workload", default="density_current", choices=["density_current", "sound_wave", "global_panel", "global_sphere", "advect3d"],
                     help="density_current = BASELINE configs[2] (headline); the others are extra measurement lines: sound_wave = "

@@ -584,8 +584,8 @@ __global__ void __launch_bounds__(VI_THREADS, MINB) vi_column_kernel(const __gri
 
 void launch_vi(const VIParams& p, bool moist, cudaStream_t s) {
   // default: the two-lane block-elimination kernel (vi_solver2.cu); FEDG_VI_KERNEL=1 keeps this file's eight-lane kernel (A/B runs)
-  static int which = -1;
-  if (which < 0) { const char* e = getenv("FEDG_VI_KERNEL"); which = (e && e[0] == '1') ? 1 : 2; }
+  int which;
+  { const char* e = getenv("FEDG_VI_KERNEL"); which = (e && e[0] == '1') ? 1 : 2; }   // read at every launch: in-process A/B runs
   if (which == 2 && p.htab && launch_vi2(p, *p.htab, moist, s)) return;
   const int ncol = p.Ne2D * 64;
   const int groups = VI_THREADS / 8;

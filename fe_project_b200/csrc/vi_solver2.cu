@@ -39,12 +39,17 @@ struct NodeQ {            // quantities of one node evaluated on var0 (the Newto
 };
 constexpr int NQ = 13;
 
+__device__ __noinline__ double vi_pow_slow(double x, double e) { return pow(x, e); }
 __device__ __forceinline__ double vi_pow(double x, double e, int exact) {
   if (!exact && x > 0.25 && x < 2.0) return exp(e * log(x));
-  return pow(x, e);
+  return vi_pow_slow(x, e);
+}
+// DPRES of a state value (DRHOT2PRES, nonhydro3d_common.F90:467-474), out of line: used once per node in the backward sweep
+__device__ __noinline__ double dpres_of(double R, double rP0, double rhot, double gm, double P00, double ph, int exact) {
+  return P00 * vi_pow(R * rP0 * rhot, gm, exact) - ph;
 }
 template <bool MOIST>
-__device__ __forceinline__ NodeQ load_node(const VIParams& P, size_t n) {
+__device__ __noinline__ NodeQ load_node(const VIParams& P, size_t n) {
   NodeQ q;
   q.rho0 = P.q0[V_DDENS][n]; q.w0 = P.q0[V_MOMZ][n]; q.th0 = P.q0[V_DRHOT][n]; q.u0 = P.q0[V_MOMX][n]; q.v0 = P.q0[V_MOMY][n];
   const double dh = P.dens_hyd[n], rh = P.rhot_hyd_vi[n], ph = P.pres_hyd[n];
@@ -93,9 +98,39 @@ struct ColSm {
 static_assert(sizeof(ColSm) % 8 == 0, "doubles");
 static_assert((sizeof(ColSm) / 4) % 32 == 4, "bank layout: column stride = 4 words mod 32");
 
+__device__ __forceinline__ void pf_l2(const double* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void pair_sync() {
   __syncwarp();
   asm volatile("" ::: "memory");
+}
+// One row of the theta block / of the Schur complement, assembled OUT OF LINE into the lane's staging slot: one copy of the row code
+// instead of four, and the row's temporaries cannot be interleaved with the rows the caller already holds in registers (inlined four
+// times the kernel spilled 1.2 KB per thread).
+__device__ __noinline__ void theta_row_staged(ColSm& sm, int h, int l, double Rth0) {
+  const Tables& T = cVT;
+  const Coef& C = sm.C;
+  double Rth[NR], A[20];
+  Rth[0] = Rth0;
+#pragma unroll
+  for (int b = 0; b < 3; ++b) Rth[1 + b] = T.lw1[l] * C.U[2][b];
+  theta_row(C, T, l, sm.vec, sm.vec + 8, sm.vec + 16, sm.Rrho0, Rth, sm.LF, A);
+#pragma unroll
+  double* st = &sm.u.X[4][0] + 20 * h;      // staging: the upper half of the X area (free until the theta block is solved)
+#pragma unroll
+  for (int j = 0; j < 20; ++j) st[j] = A[j];
+}
+__device__ __noinline__ void schur_row_staged(ColSm& sm, int h, int l, double Rw0) {
+  const Tables& T = cVT;
+  const Coef& C = sm.C;
+  double Rw[NR], H[12];
+  Rw[0] = Rw0;
+#pragma unroll
+  for (int b = 0; b < 3; ++b) Rw[1 + b] = T.lw1[l] * C.U[1][b];
+  schur_row(C, T, l, sm.vec + 24, sm.Rrho0, Rw, sm.LF, sm.u.X, H);
+#pragma unroll
+  double* st = sm.vec + 12 * h;             // staging: pot / wt / s are dead once the theta rows exist (dpd, vec[24..31], is not)
+#pragma unroll
+  for (int j = 0; j < 12; ++j) st[j] = H[j];
 }
 __device__ __forceinline__ double sel4(int c, double a0, double a1, double a2, double a3) {
   const double lo = (c & 1) ? a1 : a0, hi = (c & 1) ? a3 : a2;
@@ -105,26 +140,29 @@ __device__ __forceinline__ double sel4(int c, double a0, double a1, double a2, d
 // Partial-pivot Gauss-Jordan on the leading 8 x 8 block of a system whose rows 4h .. 4h+3 sit on lane h of the pair (W columns).
 // Pivot of column k = the largest magnitude among the rows not used yet, the lowest row index winning ties (the host harness and the
 // reference's rule).  The pivot row is taken out of the owner's registers by selects and handed to the partner by one shuffle per
-// entry.  On return row s of this lane solves unknown kk[s]: x = A[s][8 ..] * rpiv[s].
+// entry.  The matrix is SHIFTED one column to the left with every step (the update writes A[s][j-1]), so that the pivot column is
+// always column 0 and the eight steps are one rolled loop body: an eighth of the code of the unrolled form (the unrolled kernel spent
+// 2.5 cycles per issued instruction waiting for the instruction cache).  On return row s of this lane solves unknown kk[s]:
+// x_r = A[s][r] * rpiv[s], r = 0 .. W-9.
 template <int W>
 __device__ __forceinline__ void gauss_jordan_pair(double (&A)[4][W], int h, int (&kk)[4], double (&rpiv)[4]) {
   unsigned used = 0;
 #pragma unroll
   for (int s = 0; s < 4; ++s) { kk[s] = 0; rpiv[s] = 1.0; }
-#pragma unroll
+#pragma unroll 1
   for (int k = 0; k < 8; ++k) {
     double best = -1.0;
     int cs = 0;
 #pragma unroll
     for (int s = 0; s < 4; ++s) {
-      const double v = fabs(A[s][k]);
+      const double v = fabs(A[s][0]);
       if (!((used >> s) & 1u) && v > best) { best = v; cs = s; }
     }
     const double ob = __shfl_xor_sync(FULL, best, 1);
     const bool mine = (best > ob) || (best == ob && h == 0);
     double pk;
     {
-      const double c = sel4(cs, A[0][k], A[1][k], A[2][k], A[3][k]);
+      const double c = sel4(cs, A[0][0], A[1][0], A[2][0], A[3][0]);
       const double o = __shfl_xor_sync(FULL, c, 1);
       pk = mine ? c : o;
     }
@@ -133,16 +171,16 @@ __device__ __forceinline__ void gauss_jordan_pair(double (&A)[4][W], int h, int 
 #pragma unroll
     for (int s = 0; s < 4; ++s) {
       const bool is_piv = mine && (cs == s);
-      m[s] = is_piv ? 0.0 : A[s][k] * rp;
+      m[s] = is_piv ? 0.0 : A[s][0] * rp;
       if (is_piv) { used |= 1u << s; kk[s] = k; rpiv[s] = rp; }
     }
 #pragma unroll
-    for (int j = k + 1; j < W; ++j) {
+    for (int j = 1; j < W; ++j) {
       const double c = sel4(cs, A[0][j], A[1][j], A[2][j], A[3][j]);
       const double o = __shfl_xor_sync(FULL, c, 1);
       const double pj = mine ? c : o;
 #pragma unroll
-      for (int s = 0; s < 4; ++s) A[s][j] -= m[s] * pj;
+      for (int s = 0; s < 4; ++s) A[s][j - 1] = A[s][j] - m[s] * pj;
     }
   }
 }
@@ -174,6 +212,17 @@ __global__ void __launch_bounds__(V2_THREADS, IMPLICIT ? 3 : 6) vi_column2_kerne
     const double* nq0 = sm.nq0[kz & 1];
     double* nq0n = sm.nq0[(kz + 1) & 1];
     // ---- node quantities: lane 0 evaluates nodes 1, 2, 3 and node 0 of the element above, lane 1 nodes 4 .. 7 (four each)
+    // L2 prefetch of the inputs of the element above (one lane per 128-byte line: 16 columns share it)
+    if (kz + 1 < NeZ && ((threadIdx.x >> 1) & 15) == 0) {
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        const size_t n = node(kz + 1, 4 * h + a);
+        pf_l2(P.q0[V_DDENS] + n); pf_l2(P.q0[V_MOMZ] + n); pf_l2(P.q0[V_DRHOT] + n); pf_l2(P.q0[V_MOMX] + n); pf_l2(P.q0[V_MOMY] + n);
+        pf_l2(P.dens_hyd + n); pf_l2(P.rhot_hyd_vi + n); pf_l2(P.pres_hyd + n);
+        if (MOIST) { pf_l2(P.rtot + n); pf_l2(P.cptot + n); pf_l2(P.cvtot + n); }
+        if (IMPLICIT) { pf_l2(P.qcur[V_DDENS] + n); pf_l2(P.qcur[V_MOMZ] + n); pf_l2(P.qcur[V_DRHOT] + n); pf_l2(P.qcur[V_MOMX] + n); pf_l2(P.qcur[V_MOMY] + n); }
+      }
+    }
     double base_in[4][5];                    // var0 of the own rows (rho0, w0, th0, u0, v0)
 #pragma unroll
     for (int a = 0; a < 4; ++a) {
@@ -236,7 +285,7 @@ __global__ void __launch_bounds__(V2_THREADS, IMPLICIT ? 3 : 6) vi_column2_kerne
         P.qout[V_DDENS][n] = qr; P.qout[V_MOMZ][n] = qw; P.qout[V_DRHOT][n] = qt; P.qout[V_MOMX][n] = qu; P.qout[V_MOMY][n] = qv;
         const double R = MOIST ? P.rtot[n] : P.c.Rdry;
         const double gm = MOIST ? P.cptot[n] / P.cvtot[n] : P.c.CPovCV;
-        P.dpout[n] = P.c.PRES00 * vi_pow(R * P.c.rP0 * (P.therm_hyd[n] + qt), gm, P.exact_pow) - P.pres_hyd[n];
+        P.dpout[n] = dpres_of(R, P.c.rP0, P.therm_hyd[n] + qt, gm, P.c.PRES00, P.pres_hyd[n], P.exact_pow);
       }
       pair_sync();
       if (h == 1) put_node(sm.prev, M7);
@@ -337,13 +386,9 @@ __global__ void __launch_bounds__(V2_THREADS, IMPLICIT ? 3 : 6) vi_column2_kerne
       double A[4][20];
 #pragma unroll
       for (int a = 0; a < 4; ++a) {
-        const int l = 4 * h + a;
-        double Rth[NR];
-        Rth[0] = Rth0[a];
+        theta_row_staged(sm, h, 4 * h + a, Rth0[a]);
 #pragma unroll
-        for (int b = 0; b < 3; ++b) Rth[1 + b] = T.lw1[l] * C.U[2][b];
-        theta_row(C, T, l, vpot, vwt, vs, sm.Rrho0, Rth, sm.LF, A[a]);
-        asm volatile("" ::: "memory");      // keep the loads of the next row behind this one (register pressure)
+        for (int j = 0; j < 20; ++j) A[a][j] = (&sm.u.X[4][0] + 20 * h)[j];
       }
       pair_sync();                            // the operator-evaluation vectors (union with X) are dead on both lanes
       int kk[4];
@@ -352,7 +397,7 @@ __global__ void __launch_bounds__(V2_THREADS, IMPLICIT ? 3 : 6) vi_column2_kerne
 #pragma unroll
       for (int s = 0; s < 4; ++s)
 #pragma unroll
-        for (int c = 0; c < 12; ++c) sm.u.X[kk[s]][c] = A[s][8 + c] * rpiv[s];
+        for (int c = 0; c < 12; ++c) sm.u.X[kk[s]][c] = A[s][c] * rpiv[s];
     }
     pair_sync();
     // ---- Schur complement in w: rows of the own nodes, Gauss-Jordan, solution to shared memory
@@ -360,13 +405,9 @@ __global__ void __launch_bounds__(V2_THREADS, IMPLICIT ? 3 : 6) vi_column2_kerne
       double Hm[4][12];
 #pragma unroll
       for (int a = 0; a < 4; ++a) {
-        const int l = 4 * h + a;
-        double Rw[NR];
-        Rw[0] = Rw0[a];
+        schur_row_staged(sm, h, 4 * h + a, Rw0[a]);
 #pragma unroll
-        for (int b = 0; b < 3; ++b) Rw[1 + b] = T.lw1[l] * C.U[1][b];
-        schur_row(C, T, l, vdpd, sm.Rrho0, Rw, sm.LF, sm.u.X, Hm[a]);
-        asm volatile("" ::: "memory");
+        for (int j = 0; j < 12; ++j) Hm[a][j] = (sm.vec + 12 * h)[j];
       }
       int kw[4];
       double rpiv[4];
@@ -376,7 +417,7 @@ __global__ void __launch_bounds__(V2_THREADS, IMPLICIT ? 3 : 6) vi_column2_kerne
 #pragma unroll
       for (int s = 0; s < 4; ++s)
 #pragma unroll
-        for (int r = 0; r < NR; ++r) wsol[kw[s]][r] = Hm[s][8 + r] * rpiv[s];
+        for (int r = 0; r < NR; ++r) wsol[kw[s]][r] = Hm[s][r] * rpiv[s];
     }
     pair_sync();
     const double (*wsol)[NR] = reinterpret_cast<const double (*)[NR]>(sm.vec);
@@ -459,7 +500,7 @@ __global__ void __launch_bounds__(V2_THREADS, IMPLICIT ? 3 : 6) vi_column2_kerne
       // DPRES of the updated state for the explicit part of this stage (DRHOT2PRES, nonhydro3d_common.F90:467-474)
       const double R = MOIST ? P.rtot[n] : P.c.Rdry;
       const double gm = MOIST ? P.cptot[n] / P.cvtot[n] : P.c.CPovCV;
-      P.dpout[n] = P.c.PRES00 * vi_pow(R * P.c.rP0 * (P.therm_hyd[n] + qt), gm, P.exact_pow) - P.pres_hyd[n];
+      P.dpout[n] = dpres_of(R, P.c.rP0, P.therm_hyd[n] + qt, gm, P.c.PRES00, P.pres_hyd[n], P.exact_pow);
     }
   }
 }
