@@ -583,9 +583,12 @@ __global__ void __launch_bounds__(VI_THREADS, MINB) vi_column_kernel(const __gri
 }
 
 void launch_vi(const VIParams& p, bool moist, cudaStream_t s) {
-  // default: the two-lane block-elimination kernel (vi_solver2.cu); FEDG_VI_KERNEL=1 keeps this file's eight-lane kernel (A/B runs)
+  // FEDG_VI_KERNEL=2 selects the two-lane block-elimination kernel (vi_solver2.cu); default: this file's eight-lane kernel with
+  // partial pivoting over the whole block.  Measured (profiles/r02_*): kernel 2 is 3-6 % faster (2.21 vs 2.40 ms per launch at
+  // 32x32x16) but, at config 4's vertical acoustic CFL of ~100, 30 times further from the oracle in the near-zero perturbation
+  // fields (3.6e-9 vs 1e-10 of their own norm; both 1e-16 of the full fields), so the parity-first default stays.
   int which;
-  { const char* e = getenv("FEDG_VI_KERNEL"); which = (e && e[0] == '1') ? 1 : 2; }   // read at every launch: in-process A/B runs
+  { const char* e = getenv("FEDG_VI_KERNEL"); which = (e && e[0] == '2') ? 2 : 1; }   // read at every launch: in-process A/B runs
   if (which == 2 && p.htab && launch_vi2(p, *p.htab, moist, s)) return;
   const int ncol = p.Ne2D * 64;
   const int groups = VI_THREADS / 8;

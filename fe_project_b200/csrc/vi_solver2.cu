@@ -48,24 +48,36 @@ __device__ __forceinline__ double vi_pow(double x, double e, int exact) {
 __device__ __noinline__ double dpres_of(double R, double rP0, double rhot, double gm, double P00, double ph, int exact) {
   return P00 * vi_pow(R * rP0 * rhot, gm, exact) - ph;
 }
+// raw inputs of one node: var0 (5), DENS_hyd, RHOT_hyd (dry, as the solver recomputes it), PRES_hyd, and for moist runs Rtot, CPtot / CVtot
+struct RawQ { double rho0, w0, th0, u0, v0, dh, rh, ph, R, gm; };
 template <bool MOIST>
-__device__ __noinline__ NodeQ load_node(const VIParams& P, size_t n) {
+__device__ __forceinline__ RawQ load_raw(const VIParams& P, size_t n) {
+  RawQ r;
+  r.rho0 = P.q0[V_DDENS][n]; r.w0 = P.q0[V_MOMZ][n]; r.th0 = P.q0[V_DRHOT][n]; r.u0 = P.q0[V_MOMX][n]; r.v0 = P.q0[V_MOMY][n];
+  r.dh = P.dens_hyd[n]; r.rh = P.rhot_hyd_vi[n]; r.ph = P.pres_hyd[n];
+  r.R = MOIST ? P.rtot[n] : P.c.Rdry;
+  r.gm = MOIST ? P.cptot[n] / P.cvtot[n] : P.c.CPovCV;
+  return r;
+}
+// out of line: one copy of the pow / exp / log / sqrt / division sequences
+__device__ __noinline__ NodeQ node_q(const RawQ r, double P00, double rP0, double gamm, int exact) {
   NodeQ q;
-  q.rho0 = P.q0[V_DDENS][n]; q.w0 = P.q0[V_MOMZ][n]; q.th0 = P.q0[V_DRHOT][n]; q.u0 = P.q0[V_MOMX][n]; q.v0 = P.q0[V_MOMY][n];
-  const double dh = P.dens_hyd[n], rh = P.rhot_hyd_vi[n], ph = P.pres_hyd[n];
-  const double R = MOIST ? P.rtot[n] : P.c.Rdry;
-  const double gm = MOIST ? P.cptot[n] / P.cvtot[n] : P.c.CPovCV;
-  q.dens = dh + q.rho0;
-  q.rhot = rh + q.th0;
+  q.rho0 = r.rho0; q.w0 = r.w0; q.th0 = r.th0; q.u0 = r.u0; q.v0 = r.v0;
+  q.dens = r.dh + q.rho0;
+  q.rhot = r.rh + q.th0;
   q.pot = q.rhot / q.dens;
-  const double ptot = P.c.PRES00 * vi_pow(R * P.c.rP0 * q.rhot, gm, P.exact_pow);
-  q.dpres_vol = ptot - ph;
+  const double ptot = P00 * vi_pow(r.R * rP0 * q.rhot, r.gm, exact);
+  q.dpres_vol = ptot - r.ph;
   q.wt = q.w0 / q.dens;
-  q.dpd = gm * ptot / q.rhot;
+  q.dpd = r.gm * ptot / q.rhot;
   const double rdens0 = 1.0 / q.dens;
-  q.a = fabs(q.w0 * rdens0) + sqrt(P.c.gamm * ptot * rdens0);
-  q.dpf = P.c.PRES00 * vi_pow(R * P.c.rP0 * q.dens * q.pot, gm, P.exact_pow) - ph;
+  q.a = fabs(q.w0 * rdens0) + sqrt(gamm * ptot * rdens0);
+  q.dpf = P00 * vi_pow(r.R * rP0 * q.dens * q.pot, r.gm, exact) - r.ph;
   return q;
+}
+template <bool MOIST>
+__device__ __forceinline__ NodeQ load_node(const VIParams& P, size_t n) {
+  return node_q(load_raw<MOIST>(P, n), P.c.PRES00, P.c.rP0, P.c.gamm, P.exact_pow);
 }
 __device__ __forceinline__ void put_node(double* s, const NodeQ& q) {
   s[0] = q.rho0; s[1] = q.w0; s[2] = q.th0; s[3] = q.u0; s[4] = q.v0; s[5] = q.dens; s[6] = q.rhot; s[7] = q.pot; s[8] = q.wt; s[9] = q.dpd;
@@ -224,12 +236,26 @@ __global__ void __launch_bounds__(V2_THREADS, IMPLICIT ? 3 : 6) vi_column2_kerne
       }
     }
     double base_in[4][5];                    // var0 of the own rows (rho0, w0, th0, u0, v0)
+    RawQ raw[4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {            // all loads of the element first (the four L2 latencies overlap), then the arithmetic
+      const bool nxt = (h == 0 && a == 0);
+      raw[a] = load_raw<MOIST>(P, node(nxt ? min(kz + 1, NeZ - 1) : kz, 4 * h + a));
+    }
+    double qc[4][5];                         // state entering the stage at the own rows
+    if (IMPLICIT) {
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        const size_t n = node(kz, 4 * h + a);
+        qc[a][0] = P.qcur[V_DDENS][n]; qc[a][1] = P.qcur[V_MOMZ][n]; qc[a][2] = P.qcur[V_DRHOT][n]; qc[a][3] = P.qcur[V_MOMX][n]; qc[a][4] = P.qcur[V_MOMY][n];
+      }
+    }
 #pragma unroll
     for (int a = 0; a < 4; ++a) {
       // slot 0 of lane 0: the evaluation goes to the hand-over slot of the element above, row 0 itself comes from this element's slot
       const bool nxt = (h == 0 && a == 0);
       const int l = 4 * h + a;
-      NodeQ q = load_node<MOIST>(P, node(nxt ? min(kz + 1, NeZ - 1) : kz, l));
+      NodeQ q = node_q(raw[a], P.c.PRES00, P.c.rP0, P.c.gamm, P.exact_pow);
       if (nxt) { put_node(nq0n, q); q = get_node(nq0); }
       vpot[l] = q.pot; vwt[l] = q.wt; vs[l] = q.pot * q.wt; vdpd[l] = q.dpd;
       sm.u.a.w0[l] = q.w0; sm.u.a.pw[l] = q.pot * q.w0; sm.u.a.dpv[l] = q.dpres_vol; sm.u.a.rho0[l] = q.rho0;
@@ -313,12 +339,11 @@ __global__ void __launch_bounds__(V2_THREADS, IMPLICIT ? 3 : 6) vi_column2_kerne
     double Rrho_own[4], Rw0[4], Rth0[4], bu[4], bv[4];
 #pragma unroll
     for (int a = 0; a < 4; ++a) {
-      const size_t n = node(kz, 4 * h + a);
-      Rrho_own[a] = ifac * t_r[a] - base_in[a][0] + P.qcur[V_DDENS][n];
-      Rw0[a] = ifac * t_w[a] - base_in[a][1] + P.qcur[V_MOMZ][n];
-      Rth0[a] = ifac * t_t[a] - base_in[a][2] + P.qcur[V_DRHOT][n];
-      bu[a] = ifac * t_u[a] - base_in[a][3] + P.qcur[V_MOMX][n];
-      bv[a] = ifac * t_v[a] - base_in[a][4] + P.qcur[V_MOMY][n];
+      Rrho_own[a] = ifac * t_r[a] - base_in[a][0] + qc[a][0];
+      Rw0[a] = ifac * t_w[a] - base_in[a][1] + qc[a][1];
+      Rth0[a] = ifac * t_t[a] - base_in[a][2] + qc[a][2];
+      bu[a] = ifac * t_u[a] - base_in[a][3] + qc[a][3];
+      bv[a] = ifac * t_v[a] - base_in[a][4] + qc[a][4];
     }
     // ---- (MOMX, MOMY): (I + ua0 e0^T + ua7 e7^T) x = [bu | bv | bg]  (construct_matbnd_uv :960-1003, solve_uv :640-674); the
     // solution goes to the scratch arrays at once

@@ -82,6 +82,13 @@ def _sphere_err(name, got, ref, scale, n):
     return np.linalg.norm(got - ref) / max(np.linalg.norm(ref), 1e-3 * scale * np.sqrt(n))
 
 
+def _own_tol():
+    """Own-norm tolerances of the three near-zero perturbation fields, by vertical-implicit kernel (FEDG_VI_KERNEL)."""
+    if os.environ.get("FEDG_VI_KERNEL", "1") == "2":
+        return {"DDENS": 1e-8, "DRHOT": 1e-8, "MOMZ": 1e-7, "MOMX": TOL, "MOMY": TOL}
+    return {"DDENS": TOL, "DRHOT": TOL, "MOMZ": 1e-9, "MOMX": TOL, "MOMY": TOL}
+
+
 def _judge_sphere(errs, full_errs):
     """errs[(P, name)]: relative L2 errors against the variable's own norm; full_errs[(P, name)]: the same errors against the scale
     of the FULL field the variable perturbs (DENS_hyd for DDENS, RHOT_hyd for DRHOT, the momentum max |MOMX| R for MOMZ).
@@ -90,11 +97,13 @@ def _judge_sphere(errs, full_errs):
     to better than ~1e-11 of those perturbations per solve in double precision BY ANY ALGORITHM: against a 19-digit solution the
     oracle's partial-pivot LU is as far off as the device's block elimination (tests/test_vi_block_host.py::
     test_block_elimination_is_as_accurate_as_the_reference_lu); one ulp of the pressure moves MOMZ by ~1e-10 of itself.  So these three
-    are judged at 1e-10 against the full-field scale and at 2e-9 (MOMZ: 5e-8) against their own norm; MOMX and MOMY at 1e-10 against
-    their own norm.  Measured: DDENS / DRHOT 3.6e-10, MOMZ 1.2e-8 own-norm (two-lane kernel), 1e-10 / 2e-10 (eight-lane kernel)."""
+    are judged at 1e-10 against the full-field scale AND against their own norm at: DDENS / DRHOT 1e-10, MOMZ 1e-9 with the default
+    eight-lane kernel (partial pivoting over the whole block; measured <= 1e-10 / 2.9e-10), and 1e-8 / 1e-7 with the two-lane
+    block-elimination kernel FEDG_VI_KERNEL=2 (measured 3.6e-9 / 1.9e-8 at 6x32x32x12, 3.6e-10 / 1.2e-8 at 6x8x8x4: the theta
+    unknowns come out of a difference of terms ~CFL times larger).  MOMX and MOMY: 1e-10 against their own norm."""
     print("config4 worst (own norm):", {nm: f"{max(v for (P, n_), v in errs.items() if n_ == nm):.2e}" for nm in PROG},
           "(full-field scale):", {nm: f"{max(v for (P, n_), v in full_errs.items() if n_ == nm):.2e}" for nm in ("DDENS", "DRHOT", "MOMZ")})
-    own_tol = {"DDENS": 2e-9, "DRHOT": 2e-9, "MOMZ": 5e-8, "MOMX": TOL, "MOMY": TOL}
+    own_tol = _own_tol()
     for (P, nm), e in errs.items():
         assert e <= own_tol[nm], (P, nm, e)
     for (P, nm), e in full_errs.items():
@@ -125,7 +134,19 @@ def _check_sphere(case, g, ref_of):
     _judge_sphere(errs, full_errs)
 
 
-def test_config4_jw_shipped_size_against_oracle():
+@pytest.fixture(params=["1", "2"], ids=["vi_eight_lane", "vi_two_lane"])
+def vi_kernel(request):
+    """Both vertical-implicit kernels (the library reads FEDG_VI_KERNEL at every launch)."""
+    old = os.environ.get("FEDG_VI_KERNEL")
+    os.environ["FEDG_VI_KERNEL"] = request.param
+    yield request.param
+    if old is None:
+        os.environ.pop("FEDG_VI_KERNEL", None)
+    else:
+        os.environ["FEDG_VI_KERNEL"] = old
+
+
+def test_config4_jw_shipped_size_against_oracle(vi_kernel):
     """BASELINE configs[3] as shipped (run.conf: NeGX = NeGY = 8, NeZ = 4, FZ = 0/3/8/15/30 km, LumpedMassMatFlag, MF_ETAC = 0,
     sponge above 20 km, IMEX_ARK324, dt = 75 s), Jablonowski-Williamson initial state, 5 steps."""
     case = GlobalSphereCase.config4(Ne=8, NeZ=4)
@@ -138,7 +159,7 @@ def test_config4_jw_shipped_size_against_oracle():
     assert max(np.abs(p.arr("DDENS")[:p.Ne * p.Np]).max() for p in s.panels) > 1e-6
 
 
-def test_config4_jw_full_size_against_oracle_fixture():
+def test_config4_jw_full_size_against_oracle_fixture(vi_kernel):
     """The same configuration at BASELINE's 6 x 32 x 32 x 12 elements (dt = 18.75 s, FZ cut to 12 levels), 2 steps, against the oracle's
     state sampled at every 4099th node + the L2 norms of the full fields (tests/golden/config4_jw_6x32x32x12.npz; FEDG_LIVE_ORACLE=1
     runs the oracle itself instead: ~45 GB of host memory, about a minute per step)."""
@@ -162,8 +183,7 @@ def test_config4_jw_full_size_against_oracle_fixture():
             ref, a = fx[f"s_{P}_{nm}"], got[nm][:n]
             errs[(P, nm)] = _sphere_err(nm, a[::stride], ref, scale[nm], ref.size)
             nrm = float(fx[f"n_{P}_{nm}"])
-            own_tol = {"DDENS": 2e-9, "DRHOT": 2e-9, "MOMZ": 5e-8}.get(nm, TOL)
-            assert abs(np.linalg.norm(a) - nrm) <= own_tol * max(nrm, 1e-3 * scale[nm] * np.sqrt(n)), (P, nm)
+            assert abs(np.linalg.norm(a) - nrm) <= _own_tol()[nm] * max(nrm, 1e-3 * scale[nm] * np.sqrt(n)), (P, nm)
         for nm in full:
             ref = fx[f"s_{P}_{nm}"]
             full_errs[(P, nm)] = np.linalg.norm(got[nm][:n][::stride] - ref) / (full[nm] * np.sqrt(ref.size))

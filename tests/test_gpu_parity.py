@@ -221,7 +221,7 @@ def test_hevi_explicit_tendency():
 
 
 @pytest.mark.parametrize("impl_fac", [0.0, 0.05, 2.0])
-def test_hevi_cal_vi(impl_fac):
+def test_hevi_cal_vi(impl_fac, vi_kernel):
     """cal_vi seam: one Newton iteration of the vertical-implicit system about var0 != current state."""
     case = _hevi_case()
     o = case.make_oracle()
@@ -246,8 +246,21 @@ def test_hevi_cal_vi(impl_fac):
             assert np.abs(got[OUT[k]] - ref[i]).max() <= 1e-10 * max(np.abs(var0[i]).max(), np.abs(ref[i]).max()) / impl_fac, (k, impl_fac)
 
 
+@pytest.fixture(params=["1", "2"], ids=["vi_eight_lane", "vi_two_lane"])
+def vi_kernel(request):
+    """Both vertical-implicit kernels: the default eight-lane one and the two-lane block elimination (FEDG_VI_KERNEL, read per launch)."""
+    import os
+    old = os.environ.get("FEDG_VI_KERNEL")
+    os.environ["FEDG_VI_KERNEL"] = request.param
+    yield request.param
+    if old is None:
+        os.environ.pop("FEDG_VI_KERNEL", None)
+    else:
+        os.environ["FEDG_VI_KERNEL"] = old
+
+
 @pytest.mark.parametrize("tinteg,dt,dims", [("IMEX_ARK232", 0.5, (2, 2, 4)), ("IMEX_ARK324", 1.0, (3, 1, 6)), ("IMEX_ARK324", 0.1, (1, 1, 1))])
-def test_hevi_steps(tinteg, dt, dims):
+def test_hevi_steps(tinteg, dt, dims, vi_kernel):
     """Full HEVI step: vertical acoustic CFL well above 1 (dt = 1 s, dz_node ~ 10 m), modal filter on."""
     case = _hevi_case(tinteg=tinteg, dt=dt, NeX=dims[0], NeY=dims[1], NeZ=dims[2], dom=(0.0, 25.6e3, 0.0, 25.6e3, 0.0, 6.4e3))
     o = case.make_oracle()
