@@ -587,8 +587,11 @@ void launch_vi(const VIParams& p, bool moist, cudaStream_t s) {
   // partial pivoting over the whole block.  Measured (profiles/r02_*): kernel 2 is 3-6 % faster (2.21 vs 2.40 ms per launch at
   // 32x32x16) but, at config 4's vertical acoustic CFL of ~100, 30 times further from the oracle in the near-zero perturbation
   // fields (3.6e-9 vs 1e-10 of their own norm; both 1e-16 of the full fields), so the parity-first default stays.
-  int which;
-  { const char* e = getenv("FEDG_VI_KERNEL"); which = (e && e[0] == '2') ? 2 : 1; }   // read at every launch: in-process A/B runs
+  // The explicit evaluation (impl_fac = 0, first stage of the ARK schemes) has no linear solve: the two-lane kernel does it in 0.55 ms
+  // against 0.92 ms here, so it takes those launches by default.  FEDG_VI_KERNEL=1 / 2 forces one kernel for every launch.
+  int which = 0;
+  { const char* e = getenv("FEDG_VI_KERNEL"); if (e && (e[0] == '1' || e[0] == '2')) which = e[0] - '0'; }   // read at every launch: in-process A/B runs
+  if (which == 0) which = (p.impl_fac == 0.0) ? 2 : 1;
   if (which == 2 && p.htab && launch_vi2(p, *p.htab, moist, s)) return;
   const int ncol = p.Ne2D * 64;
   const int groups = VI_THREADS / 8;
