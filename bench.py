@@ -267,7 +267,7 @@ def run_sphere(args, rank=0, world=1, local_rank=0):
     # so that the state fills the HBM of the GPUs it runs on
     ne, nez = (args.sphere_ne or 32), (args.nez if args.nez != WORKLOAD["NeZ"] else 12)
     from fe_project_b200.cubedsphere import panel_owner
-    ntile = 2 if world in (4, 8) else 1          # 4 / 8 GPUs: 2 x 2 tiles per panel (24 local meshes), the same sphere
+    ntile = args.sphere_ntile or (2 if world in (4, 8) else 1)          # 4 / 8 GPUs: 2 x 2 tiles per panel (24 local meshes), the same sphere
     own_ids = [t for t, r in enumerate(panel_owner(world, ntile)) if r == rank]
     # run.conf of test/case/baroclinic_wave_global: Jablonowski-Williamson state, lumped mass matrix, stretched FZ, eta_c = 0, sponge
     case = GlobalSphereCase.config4(Ne=ne // ntile, NeZ=nez, ntile=ntile, fields_for=own_ids)
@@ -342,6 +342,7 @@ def main():
     ap.add_argument("--ney", type=int, default=WORKLOAD["NeY"])
     ap.add_argument("--nez", type=int, default=WORKLOAD["NeZ"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--sphere-ntile", type=int, default=0, help="global_sphere: k x k tiles per panel (default: 1, or 2 on 4 / 8 GPUs)")
     ap.add_argument("--sphere-ne", type=int, default=0, help="global_sphere: elements per panel edge (default 32 = configs[3]; configs[4] sizes it to the HBM)")
     ap.add_argument("--eqs", default="heve", choices=["heve", "hevi"], help="hevi: NONHYDRO3D_HEVI + IMEX_ARK324 (extra, not the headline)")
     ap.add_argument("--workload", default="density_current", choices=["density_current", "sound_wave", "global_panel", "global_sphere", "advect3d"],
