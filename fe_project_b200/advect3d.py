@@ -21,13 +21,23 @@ from .mesh import LocalMeshCube
 
 
 class SparseMat:
-    """`sparsemat` in ELL storage.  mat: dense (M, N)."""
+    """`sparsemat` in ELL (default, what the kernels consume) or CSR storage.  mat: dense (M, N)."""
 
-    def __init__(self, mat: np.ndarray, eps: float | None = None):
+    def __init__(self, mat: np.ndarray, eps: float | None = None, storage_format: str = "ELL"):
         mat = np.asarray(mat, dtype=np.float64)
         self.M, self.N = mat.shape
         eps = SCALE_CONST["EPS"] * 500.0 if eps is None else eps
         keep = np.abs(mat) > eps
+        self.storage_format = storage_format.upper()
+        assert self.storage_format in ("ELL", "CSR")
+        if self.storage_format == "CSR":            # sparsemat_Init, CSR branch (scale_sparsemat.F90:137-150, 176-195): 1-based arrays
+            rows, cols = np.nonzero(keep)
+            self.nnz = int(rows.size)
+            self.val = np.ascontiguousarray(mat[rows, cols])
+            self.colIdx = (cols + 1).astype(np.int32)
+            self.rowPtr = (np.concatenate([[0], np.cumsum(keep.sum(axis=1))]) + 1).astype(np.int32)
+            self.col_size = 0
+            return
         self.col_size = int(keep.sum(axis=1).max())
         self.nnz = int(keep.sum())
         self.val = np.zeros(self.M * self.col_size)
@@ -49,8 +59,39 @@ class SparseMat:
         d.colIdx = self.colIdx.ctypes.data_as(C.c_void_p)
         return d
 
+    def abi_any(self) -> "_lib.SparseMatAnyDesc":
+        d = _lib.SparseMatAnyDesc()
+        d.storage_format_id = 1 if self.storage_format == "CSR" else 2     # SPARSEMAT_STORAGE_TYPEID_* (scale_sparsemat.F90:68-69)
+        d.M, d.N, d.nnz, d.col_size = self.M, self.N, self.nnz, self.col_size
+        d.val = self.val.ctypes.data_as(C.c_void_p)
+        d.colIdx = self.colIdx.ctypes.data_as(C.c_void_p)
+        if self.storage_format == "CSR":
+            d.rowPtrSize = self.M + 1
+            d.rowPtr = self.rowPtr.ctypes.data_as(C.c_void_p)
+        return d
+
+    def matmul1(self, b: np.ndarray) -> np.ndarray:
+        """sparsemat_matmul1, either storage: b (N,) -> (M,)."""
+        b = _f64(b); c = np.zeros(self.M); d = self.abi_any()
+        _lib.check(_lib.load().fedg_sparsemat_matmul1(C.byref(d), _ptr(b), _ptr(c)))
+        return c
+
+    def matmul1_2(self, b1: np.ndarray, b2: np.ndarray) -> np.ndarray:
+        """sparsemat_matmul1_2: A (b1 .* b2)."""
+        b1, b2 = _f64(b1), _f64(b2); c = np.zeros(self.M); d = self.abi_any()
+        _lib.check(_lib.load().fedg_sparsemat_matmul1_2(C.byref(d), _ptr(b1), _ptr(b2), _ptr(c)))
+        return c
+
+    def matmul2(self, b: np.ndarray) -> np.ndarray:
+        """sparsemat_matmul2: b given as (N, NQ) in C order (= the reference's b(NQ,N)) -> (M, NQ)."""
+        b = _f64(b); assert b.ndim == 2 and b.shape[0] == self.N
+        c = np.zeros((self.M, b.shape[1])); d = self.abi_any()
+        _lib.check(_lib.load().fedg_sparsemat_matmul2(C.byref(d), _ptr(b), _ptr(c), int(b.shape[1])))
+        return c
+
     def matmul(self, b: np.ndarray) -> np.ndarray:
         """sparsemat_matmul on the GPU: b (nvec, N) or (N,) -> (nvec, M) or (M,)."""
+        assert self.storage_format == "ELL"
         b2 = _f64(np.atleast_2d(b))
         assert b2.shape[1] == self.N
         c = np.zeros((b2.shape[0], self.M))

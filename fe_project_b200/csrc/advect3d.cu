@@ -126,7 +126,41 @@ __global__ void ell_spmv_kernel(int M, int N, int col_size, const double* __rest
   }
 }
 
+// General sparsemat product for the conformance entries (row a1): CSR or ELL storage, one or two operand vectors, vectors stored
+// one after the other (matmul1, batched) or interleaved (matmul2: b(NQ,N), c(NQ,M)).  One thread per (row, vector); the sums run in
+// the reference's order (CSR: j ascending, scale_sparsemat.F90:439-474; ELL: slots ascending, :554-634).
+//   b[col * sb_col + q * sb_q],  c[row * sc_row + q * sc_q]
+__global__ void sparsemat_general_kernel(int M, int nq, int col_size, const double* __restrict__ val, const int* __restrict__ col,
+                                         const int* __restrict__ rowptr, const double* __restrict__ b1, const double* __restrict__ b2,
+                                         double* __restrict__ c, size_t sb_col, size_t sb_q, size_t sc_row, size_t sc_q) {
+  const size_t x = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (x >= size_t(M) * nq) return;
+  const int i = int(x % M), q = int(x / M);
+  const double* bq1 = b1 + q * sb_q;
+  const double* bq2 = b2 ? b2 + q * sb_q : nullptr;
+  double s = 0.0;
+  if (rowptr) {
+    for (int j = rowptr[i]; j < rowptr[i + 1]; ++j) {
+      const size_t cj = size_t(col[j]) * sb_col;
+      s = bq2 ? s + val[j] * bq1[cj] * bq2[cj] : s + val[j] * bq1[cj];
+    }
+  } else {
+    for (int k = 0; k < col_size; ++k) {
+      const size_t l = size_t(i) + size_t(k) * M, cj = size_t(col[l]) * sb_col;
+      s = bq2 ? s + val[l] * bq1[cj] * bq2[cj] : s + val[l] * bq1[cj];
+    }
+  }
+  c[i * sc_row + q * sc_q] = s;
+}
+
 }  // namespace
+
+cudaError_t launch_sparsemat_general(int M, int nq, int col_size, const double* val, const int* col, const int* rowptr, const double* b1,
+                                     const double* b2, double* c, size_t sb_col, size_t sb_q, size_t sc_row, size_t sc_q, cudaStream_t s) {
+  const size_t n = size_t(M) * nq;
+  sparsemat_general_kernel<<<unsigned((n + 127) / 128), 128, 0, s>>>(M, nq, col_size, val, col, rowptr, b1, b2, c, sb_col, sb_q, sc_row, sc_q);
+  return cudaGetLastError();
+}
 
 size_t advect_smem_bytes(const AdvectParams& P) {
   const size_t nell = size_t(3) * P.Np * P.colsz[0] + size_t(P.Np) * P.colsz[3];

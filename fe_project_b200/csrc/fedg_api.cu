@@ -1557,6 +1557,59 @@ int fedg_sparsemat_matmul(const fedg_sparsemat* A, const double* b, double* c, i
   return FEDG_OK;
 }
 
+namespace {
+struct IntDevBuf {   // device int array freed on scope exit
+  int* p = nullptr;
+  ~IntDevBuf() { if (p) cudaFree(p); }
+};
+struct DevBufGuard {   // DevBuf has no destructor (contexts own theirs): release on scope exit here
+  DevBuf b;
+  ~DevBufGuard() { b.release(); }
+};
+// mode 0: c = A b1; mode 1: c = A (b1 .* b2); mode 2: c(NQ,M) = A b1(NQ,N)
+int sparsemat_any_product(const fedg_sparsemat_any* A, const double* b1, const double* b2, double* c, int mode, int NQ) {
+  if (!A || !A->val || !A->colIdx || !b1 || !c || (mode == 1 && !b2) || NQ <= 0 || A->M <= 0 || A->N <= 0) return fail(FEDG_ERR_ARG, "bad argument");
+  const bool csr = A->storage_format_id == 1;
+  if (!csr && A->storage_format_id != 2) return fail(FEDG_ERR_ARG, "storage_format_id must be 1 (CSR) or 2 (ELL)");
+  if (csr && (!A->rowPtr || A->rowPtrSize != A->M + 1 || A->nnz < 0)) return fail(FEDG_ERR_ARG, "CSR needs rowPtr(M + 1) and nnz");
+  if (!csr && A->col_size <= 0) return fail(FEDG_ERR_ARG, "ELL needs col_size");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(FEDG_ERR_CUDA, "no CUDA device (this library has no CPU fallback)");
+  const size_t nent = csr ? size_t(A->nnz) : size_t(A->M) * A->col_size;
+  std::vector<int> col0(std::max<size_t>(nent, 1)), rp0(csr ? A->M + 1 : 1);
+  for (size_t l = 0; l < nent; ++l) {
+    col0[l] = A->colIdx[l] - 1;
+    if (col0[l] < 0 || col0[l] >= A->N) return fail(FEDG_ERR_ARG, "colIdx out of range (must be 1-based)");
+  }
+  if (csr) {
+    for (int i = 0; i <= A->M; ++i) {
+      rp0[i] = A->rowPtr[i] - 1;
+      if (rp0[i] < 0 || size_t(rp0[i]) > nent || (i > 0 && rp0[i] < rp0[i - 1])) return fail(FEDG_ERR_ARG, "rowPtr must be 1-based, ascending, within nnz");
+    }
+  }
+  DevBufGuard dv, d1, d2, dc; IntDevBuf dcol, drp;
+  const size_t nb = size_t(A->N) * NQ, nc = size_t(A->M) * NQ;
+  CUDA_TRY(dv.b.alloc(std::max<size_t>(nent, 1))); CUDA_TRY(d1.b.alloc(nb)); CUDA_TRY(dc.b.alloc(nc));
+  if (mode == 1) CUDA_TRY(d2.b.alloc(nb));
+  CUDA_TRY(cudaMalloc(&dcol.p, std::max<size_t>(nent, 1) * sizeof(int)));
+  if (csr) CUDA_TRY(cudaMalloc(&drp.p, size_t(A->M + 1) * sizeof(int)));
+  if (nent) { CUDA_TRY(cudaMemcpy(dv.b.p, A->val, nent * sizeof(double), cudaMemcpyHostToDevice)); CUDA_TRY(cudaMemcpy(dcol.p, col0.data(), nent * sizeof(int), cudaMemcpyHostToDevice)); }
+  if (csr) CUDA_TRY(cudaMemcpy(drp.p, rp0.data(), size_t(A->M + 1) * sizeof(int), cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(d1.b.p, b1, nb * sizeof(double), cudaMemcpyHostToDevice));
+  if (mode == 1) CUDA_TRY(cudaMemcpy(d2.b.p, b2, nb * sizeof(double), cudaMemcpyHostToDevice));
+  // matmul2 keeps the right-hand-side index fastest: b(NQ,N), c(NQ,M)
+  const size_t sb_col = (mode == 2) ? size_t(NQ) : 1, sb_q = (mode == 2) ? 1 : size_t(A->N), sc_row = (mode == 2) ? size_t(NQ) : 1, sc_q = (mode == 2) ? 1 : size_t(A->M);
+  CUDA_TRY(launch_sparsemat_general(A->M, NQ, csr ? 0 : A->col_size, dv.b.p, dcol.p, csr ? drp.p : nullptr, d1.b.p, mode == 1 ? d2.b.p : nullptr, dc.b.p,
+                                    sb_col, sb_q, sc_row, sc_q, nullptr));
+  CUDA_TRY(cudaMemcpy(c, dc.b.p, nc * sizeof(double), cudaMemcpyDeviceToHost));
+  return FEDG_OK;
+}
+}  // namespace
+
+int fedg_sparsemat_matmul1(const fedg_sparsemat_any* A, const double* b, double* c) { return sparsemat_any_product(A, b, nullptr, c, 0, 1); }
+int fedg_sparsemat_matmul1_2(const fedg_sparsemat_any* A, const double* b1, const double* b2, double* c) { return sparsemat_any_product(A, b1, b2, c, 1, 1); }
+int fedg_sparsemat_matmul2(const fedg_sparsemat_any* A, const double* b, double* c, int NQ) { return sparsemat_any_product(A, b, nullptr, c, 2, NQ); }
+
 int fedg_advect3d_init(fedg_ctx* c, const char* tinteg_type, double dt, const fedg_sparsemat* Dx, const fedg_sparsemat* Dy,
                        const fedg_sparsemat* Dz, const fedg_sparsemat* Lift) {
   if (!c || !tinteg_type || !Dx || !Dy || !Dz || !Lift) return fail(FEDG_ERR_ARG, "null argument");

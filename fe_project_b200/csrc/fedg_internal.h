@@ -161,6 +161,8 @@ size_t advect_smem_bytes(const AdvectParams& P);
 cudaError_t launch_advect_stage(const AdvectParams& P, cudaStream_t s);
 void launch_advect_halo(double* q, double* u, double* v, double* w, const int* src, size_t nint, int nhalo, bool with_vel,
                         cudaStream_t s);
+cudaError_t launch_sparsemat_general(int M, int nq, int col_size, const double* val, const int* col, const int* rowptr, const double* b1,
+                                     const double* b2, double* c, size_t sb_col, size_t sb_q, size_t sc_row, size_t sc_q, cudaStream_t s);
 cudaError_t launch_ell_spmv(int M, int N, int col_size, const double* val, const int* col, const double* b, double* c, int nvec,
                             cudaStream_t s);
 

@@ -315,6 +315,26 @@ typedef struct fedg_sparsemat {
  * b is (N,nvec), c is (M,nvec), host arrays. */
 int fedg_sparsemat_matmul(const fedg_sparsemat* A, const double* b, double* c, int nvec);
 
+/* `sparsemat` in either storage format of the reference type (common/scale_sparsemat.F90:33-55):
+ *   storage_format_id = 1 (SPARSEMAT_STORAGE_TYPEID_CSR, :68): val(nnz), colIdx(nnz), rowPtr(rowPtrSize = M + 1), all 1-based;
+ *   storage_format_id = 2 (SPARSEMAT_STORAGE_TYPEID_ELL, :69): val(M*col_size), colIdx(M*col_size) as in fedg_sparsemat, rowPtr unused. */
+typedef struct fedg_sparsemat_any {
+  int storage_format_id;
+  int M, N, nnz, col_size, rowPtrSize;
+  const double* val;
+  const int* colIdx;
+  const int* rowPtr;
+} fedg_sparsemat_any;
+
+/* The three generic products of the type, either storage (host arrays in, host arrays out):
+ *   fedg_sparsemat_matmul1    sparsemat_matmul1   (:355-383; CSR kernel :439-474, ELL :554-585)   c(M) = A b(N)
+ *   fedg_sparsemat_matmul1_2  sparsemat_matmul1_2 (:386-408; CSR :476-512, ELL :587-634)           c(M) = A (b1 .* b2)
+ *   fedg_sparsemat_matmul2    sparsemat_matmul2   (:411-431; CSR :514-552, ELL :636-664)           c(NQ,M) = A b(NQ,N), Fortran order
+ * The sums run in the reference's order (CSR: entries of a row ascending; ELL: slots ascending). */
+int fedg_sparsemat_matmul1(const fedg_sparsemat_any* A, const double* b, double* c);
+int fedg_sparsemat_matmul1_2(const fedg_sparsemat_any* A, const double* b1, const double* b2, double* c);
+int fedg_sparsemat_matmul2(const fedg_sparsemat_any* A, const double* b, double* c, int NQ);
+
 /* Set-up of the advection run on the mesh of ctx: the four operators the sample passes to
  * advect3d_kernel_cal_tend (sample/advect3d/mod_advect3d_kernel.f90:34-44) and the timeint_rk scheme and step of
  * sample/advect3d/test_advect3d.f90 (TINTEG_SCHEME_TYPE, TIME_DT). */

@@ -324,6 +324,23 @@ int feo_sparsemat_matmul(const double* A, int M, int N, double eps, int ell, con
   });
 }
 
+// c = A (b1 .* b2) (mode 1) or c(NQ,M) = A b(NQ,N) (mode 2), CSR or ELL storage; also hands out the CSR arrays (1-based like the
+// reference's colIdx / rowPtr) when csr_val != nullptr (sized nnz, nnz, M + 1 by the caller; nnz returned through *nnz_out)
+int feo_sparsemat_matmul_ex(const double* A, int M, int N, double eps, int ell, int mode, int NQ, const double* b1, const double* b2,
+                            double* c, int* nnz_out, double* csr_val, int* csr_col, int* csr_rowptr) {
+  return guard([&] {
+    SparseMat sm; sm.init(A, M, N, eps, ell != 0);
+    if (mode == 1) sm.matmul_1_2(b1, b2, c);
+    else if (mode == 2) sm.matmul2(b1, c, NQ);
+    else sm.matmul(b1, c);
+    if (nnz_out) *nnz_out = sm.nnz;
+    if (csr_val && !sm.ell) {
+      for (int k = 0; k < sm.nnz; ++k) { csr_val[k] = sm.val[k]; csr_col[k] = sm.colIdx[k] + 1; }
+      for (int i = 0; i <= M; ++i) csr_rowptr[i] = sm.rowPtr[i] + 1;
+    }
+  });
+}
+
 // RK scheme tables: out arrays sized by the caller from nstage
 int feo_rk_info(const char* scheme, int* nstage, int* tend_buf_size, int* low_storage, int* imex) {
   RKScheme sc; if (!sc.init(scheme)) return 1;

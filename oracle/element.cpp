@@ -309,5 +309,34 @@ void SparseMat::matmul(const double* b, double* c) const {
       for (int i = 0; i < M; ++i) { size_t l = size_t(i) + size_t(k) * M; c[i] += val[l] * b[colIdx[l]]; }
   }
 }
+// sparsemat_matmul_CSR_1_2 (:476-512), sparsemat_matmul_ELL_1_2 (:587-634): c = A (b1 .* b2), evaluated as (A(j) * b1) * b2
+void SparseMat::matmul_1_2(const double* b1, const double* b2, double* c) const {
+  if (!ell) {
+    for (int i = 0; i < M; ++i) {
+      double s = 0.0;
+      for (int k = rowPtr[i]; k < rowPtr[i + 1]; ++k) s = s + val[k] * b1[colIdx[k]] * b2[colIdx[k]];
+      c[i] = s;
+    }
+  } else {
+    for (int i = 0; i < M; ++i) c[i] = 0.0;
+    for (int k = 0; k < col_size; ++k)
+      for (int i = 0; i < M; ++i) { size_t l = size_t(i) + size_t(k) * M; c[i] = c[i] + val[l] * b1[colIdx[l]] * b2[colIdx[l]]; }
+  }
+}
+// sparsemat_matmul_CSR_2 (:514-552), sparsemat_matmul_ELL_2 (:636-664): b(NQ,N), c(NQ,M) in Fortran order (q fastest)
+void SparseMat::matmul2(const double* b, double* c, int NQ) const {
+  for (size_t x = 0; x < size_t(NQ) * M; ++x) c[x] = 0.0;
+  if (!ell) {
+    for (int i = 0; i < M; ++i)
+      for (int k = rowPtr[i]; k < rowPtr[i + 1]; ++k)
+        for (int q = 0; q < NQ; ++q) c[q + size_t(NQ) * i] = c[q + size_t(NQ) * i] + val[k] * b[q + size_t(NQ) * colIdx[k]];
+  } else {
+    for (int k = 0; k < col_size; ++k)
+      for (int i = 0; i < M; ++i) {
+        size_t l = size_t(i) + size_t(k) * M;
+        for (int q = 0; q < NQ; ++q) c[q + size_t(NQ) * i] = c[q + size_t(NQ) * i] + val[l] * b[q + size_t(NQ) * colIdx[l]];
+      }
+  }
+}
 
 }  // namespace feo

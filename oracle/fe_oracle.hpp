@@ -78,6 +78,8 @@ struct SparseMat {
   void init(const double* dense_rowmajor, int M, int N, double eps, bool ell_format);
   double get(int i, int j) const;
   void matmul(const double* b, double* c) const;
+  void matmul_1_2(const double* b1, const double* b2, double* c) const;   // c = A (b1 .* b2)            (:386-408)
+  void matmul2(const double* b, double* c, int NQ) const;                  // b(NQ,N) -> c(NQ,M), Fortran order (:411-431)
 };
 
 // ---------------------------------------------------------------- mesh

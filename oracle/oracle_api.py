@@ -290,6 +290,25 @@ def sparsemat_matmul(A, b, eps, ell):
     return c, g
 
 
+def sparsemat_matmul_ex(A, b1, eps, ell, mode=0, b2=None, NQ=1):
+    """mode 0: c = A b1; mode 1: c = A (b1 .* b2) (sparsemat_matmul1_2); mode 2: b1 is (N, NQ) C-order = Fortran b(NQ,N), returns (M, NQ)
+    (sparsemat_matmul2).  Also returns the CSR arrays (1-based) of the matrix when ell is False."""
+    A = np.ascontiguousarray(A, dtype=np.float64)
+    b1 = np.ascontiguousarray(b1, dtype=np.float64)
+    b2 = None if b2 is None else np.ascontiguousarray(b2, dtype=np.float64)
+    M, N = A.shape
+    c = np.zeros((M, NQ) if mode == 2 else M)
+    nnz = C.c_int()
+    val, col, rp = np.zeros(M * N), np.zeros(M * N, dtype=np.int32), np.zeros(M + 1, dtype=np.int32)
+    L = lib()
+    L.feo_sparsemat_matmul_ex.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 7
+    rc = L.feo_sparsemat_matmul_ex(_p(A), M, N, eps, int(ell), int(mode), int(NQ), _p(b1), None if b2 is None else _p(b2), _p(c),
+                                   C.byref(nnz), _p(val), _p(col), _p(rp))
+    assert rc == 0
+    n = nnz.value
+    return c, (val[:n].copy(), col[:n].copy(), rp)
+
+
 def rk_tables(name):
     L = lib()
     n = [C.c_int() for _ in range(4)]

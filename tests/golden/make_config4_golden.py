@@ -3,7 +3,10 @@ Jablonowski-Williamson baroclinic wave, 6 x 32 x 32 x 12 elements, p = 7, GLOBAL
 stretched FZ, modal filter with eta_c = 0, sponge layer) after NSTEPS steps, at every STRIDE-th node of every panel and variable,
 plus the L2 norms of the full fields.  The oracle needs ~45 GB and ~70 s per step on 8 cores at this size, so the GPU test compares
 against this fixture instead of running it on the GPU box (tests/test_gpu_config_sizes.py).  ORACLE OUTPUT, not reference output: the
-Fortran reference cannot be built in this image."""
+Fortran reference cannot be built in this image.
+A second run of the same oracle from an initial state whose MOMX / MOMY are moved by at most one unit in the last place (u_P_name) measures
+how far round-off alone carries each variable: DDENS, DRHOT and MOMZ of this balanced state are near-zero perturbations and the test judges
+them against that measured sensitivity instead of pretending they are determined to 1e-10 of their own norm."""
 import os
 import sys
 import time
@@ -36,6 +39,20 @@ def main():
             a = pn.arr(nm)[:n]
             out[f"s_{P}_{nm}"] = a[::STRIDE].copy()
             out[f"n_{P}_{nm}"] = float(np.linalg.norm(a))
+    del o
+    # the oracle's own sensitivity to round-off: same run, MOMX / MOMY of the initial state moved by -1 / 0 / +1 ulp
+    o = case.make_oracle()
+    rng = np.random.default_rng(1)
+    for pn in o.panels:
+        for nm in ("MOMX", "MOMY"):
+            a = pn.arr(nm)
+            a *= 1.0 + 2.2e-16 * rng.integers(-1, 2, a.shape)
+    o.update(NSTEPS)
+    print("perturbed steps", time.time() - t0, flush=True)
+    for P, pn in enumerate(o.panels):
+        n = pn.Ne * pn.Np
+        for nm in ("DDENS", "MOMX", "MOMY", "MOMZ", "DRHOT"):
+            out[f"u_{P}_{nm}"] = pn.arr(nm)[:n][::STRIDE].copy()
     np.savez_compressed(os.path.join(HERE, f"config4_jw_6x{ne}x{ne}x{NEZ}.npz"), **out)
     print("done", time.time() - t0)
 

@@ -22,6 +22,30 @@ def test_sparsemat_matmul_reference_5x5():
     assert np.abs(s.matmul(b) - b @ A.T).max() <= 1e-14
 
 
+@pytest.mark.parametrize("fmt", ["CSR", "ELL"])
+def test_sparsemat_csr_ell_matmul1_matmul1_2_matmul2(fmt):
+    """The three generic products of the reference type in both storage formats (scale_sparsemat.F90:355-431) on the device against the
+    oracle: the reference's 5x5 known answer (test_sparsemat.f90:69-93) and the p = 3 element matrices (Dx: 64 x 64, Lift: 64 x 96)."""
+    from oracle_api import sparsemat_matmul_ex
+    A = np.array([[1, 3, 0, 0, 0], [1, 2, 5, 0, 0], [4, 1, 3, 0, 0], [0, 3, 7, 4, 0], [1, 0, 0, 0, 5]], dtype=np.float64)
+    s = SparseMat(A, eps=1e-16, storage_format=fmt)
+    assert np.array_equal(s.matmul1(np.ones(5)), [4, 8, 8, 14, 6])
+    assert np.array_equal(s.matmul1_2(np.ones(5), np.ones(5)), [4, 8, 8, 14, 6])
+    o = Oracle(3, 1, 1, 1, (-1, 1, -1, 1, -1, 1))
+    rng = np.random.default_rng(11)
+    eps = 500 * 2.220446e-16
+    for dense in (A, o.dmat_dense(0), o.dmat_dense(2), o.lift_dense()):
+        M, N = dense.shape
+        s = SparseMat(dense, eps=1e-16 if dense is A else eps, storage_format=fmt)
+        e = 1e-16 if dense is A else eps
+        b1, b2, B = rng.standard_normal(N), rng.standard_normal(N), rng.standard_normal((N, 6))
+        ell = fmt == "ELL"
+        scale = np.abs(dense).sum(axis=1).max()
+        assert np.abs(s.matmul1(b1) - sparsemat_matmul_ex(dense, b1, e, ell)[0]).max() <= 1e-14 * scale
+        assert np.abs(s.matmul1_2(b1, b2) - sparsemat_matmul_ex(dense, b1, e, ell, mode=1, b2=b2)[0]).max() <= 1e-14 * scale
+        assert np.abs(s.matmul2(B) - sparsemat_matmul_ex(dense, B, e, ell, mode=2, NQ=6)[0]).max() <= 1e-14 * scale
+
+
 @pytest.mark.parametrize("p", [3, 7])
 def test_sparsemat_matmul_element_matrices(p):
     """Dx/Dy/Dz/Lift as ELL sparsemat objects: GPU product == oracle product (same slot order), many right-hand sides."""

@@ -82,32 +82,50 @@ def _sphere_err(name, got, ref, scale, n):
     return np.linalg.norm(got - ref) / max(np.linalg.norm(ref), 1e-3 * scale * np.sqrt(n))
 
 
-def _own_tol():
-    """Own-norm tolerances of the three near-zero perturbation fields, by vertical-implicit kernel (FEDG_VI_KERNEL)."""
-    if os.environ.get("FEDG_VI_KERNEL", "1") == "2":
-        return {"DDENS": 1e-8, "DRHOT": 1e-8, "MOMZ": 1e-7, "MOMX": TOL, "MOMY": TOL}
-    return {"DDENS": TOL, "DRHOT": TOL, "MOMZ": 1e-9, "MOMX": TOL, "MOMY": TOL}
+SENS_FACTOR = 10.0
 
 
-def _judge_sphere(errs, full_errs):
+def _own_tol(sens):
+    """Own-norm tolerance per variable: 1e-10, or SENS_FACTOR x the oracle's own sensitivity to round-off where that is larger.
+    sens[name] = worst relative L2 distance (same denominator as the errors) between two runs of the ORACLE whose initial MOMX / MOMY
+    differ by at most one unit in the last place."""
+    return {nm: max(TOL, SENS_FACTOR * sens.get(nm, 0.0)) for nm in PROG}
+
+
+def _judge_sphere(errs, full_errs, sens):
     """errs[(P, name)]: relative L2 errors against the variable's own norm; full_errs[(P, name)]: the same errors against the scale
     of the FULL field the variable perturbs (DENS_hyd for DDENS, RHOT_hyd for DRHOT, the momentum max |MOMX| R for MOMZ).
     The Jablonowski-Williamson state is balanced: DDENS, DRHOT (1e-5 of the background) and MOMZ (the residual of vertical forces
-    1e4 times larger) are near-zero perturbations, and at config 4's vertical acoustic CFL (~100) the column systems are not solvable
-    to better than ~1e-11 of those perturbations per solve in double precision BY ANY ALGORITHM: against a 19-digit solution the
-    oracle's partial-pivot LU is as far off as the device's block elimination (tests/test_vi_block_host.py::
-    test_block_elimination_is_as_accurate_as_the_reference_lu); one ulp of the pressure moves MOMZ by ~1e-10 of itself.  So these three
-    are judged at 1e-10 against the full-field scale AND against their own norm at: DDENS / DRHOT 1e-10, MOMZ 1e-9 with the default
-    eight-lane kernel (partial pivoting over the whole block; measured <= 1e-10 / 2.9e-10), and 1e-8 / 1e-7 with the two-lane
-    block-elimination kernel FEDG_VI_KERNEL=2 (measured 3.6e-9 / 1.9e-8 at 6x32x32x12, 3.6e-10 / 1.2e-8 at 6x8x8x4: the theta
-    unknowns come out of a difference of terms ~CFL times larger).  MOMX and MOMY: 1e-10 against their own norm."""
+    1e4 times larger) are near-zero perturbations and the column systems at config 4's vertical acoustic CFL (~100 at dt = 18.75 s,
+    ~400 at the shipped 75 s) amplify round-off: the ORACLE ITSELF moves by 2.6e-10 (DDENS, DRHOT) and 6.6e-9 (MOMZ) of those
+    variables' own norm after 5 shipped-size steps when MOMX / MOMY of its initial state are changed by one unit in the last place
+    (tests/test_oracle_global.py::test_config4_round_off_sensitivity_of_the_oracle).  The device result sits at the same distance
+    (3.6e-10 / 1.2e-8) whichever vertical-implicit kernel and whichever pow() it uses (tools/cfg4_diag.py).  A bar of 1e-10 of the own
+    norm is therefore not a property any implementation -- the reference's included -- can have for these three; they are judged
+    at 1e-10 against the full-field scale AND at SENS_FACTOR x the measured sensitivity of the oracle against their own norm (the
+    single-ulp perturbation of two fields at t = 0 is a LOWER bound of the round-off an implementation commits at every operation of
+    every step, hence the factor; measured with either vertical-implicit kernel: 1.4x / 1.8x (DDENS / MOMZ) at the shipped size after 5 steps,
+    6.4x / 6.8x at 6x32x32x12 after 2 steps, where the sensitivity is 5.6e-10 / 2.8e-9 -- FMA contraction and one reciprocal instead
+    of three divisions per face node move every operation of the device step by an ulp, not two fields once).
+    MOMX and MOMY (and every variable whose sensitivity is below 2.5e-11): 1e-10 against their own norm."""
     print("config4 worst (own norm):", {nm: f"{max(v for (P, n_), v in errs.items() if n_ == nm):.2e}" for nm in PROG},
+          "oracle's round-off sensitivity:", {nm: f"{v:.2e}" for nm, v in sens.items()},
           "(full-field scale):", {nm: f"{max(v for (P, n_), v in full_errs.items() if n_ == nm):.2e}" for nm in ("DDENS", "DRHOT", "MOMZ")})
-    own_tol = _own_tol()
+    own_tol = _own_tol(sens)
+    assert own_tol["MOMX"] == TOL and own_tol["MOMY"] == TOL, sens
     for (P, nm), e in errs.items():
-        assert e <= own_tol[nm], (P, nm, e)
+        assert e <= own_tol[nm], (P, nm, e, own_tol[nm])
     for (P, nm), e in full_errs.items():
         assert e <= TOL, (P, nm, "against the full-field scale", e)
+
+
+def _ulp_perturb(oracle_sphere, seed=1):
+    """MOMX / MOMY of every panel of an oracle sphere times (1 + k * 2.2e-16), k in {-1, 0, 1}: at most one unit in the last place."""
+    rng = np.random.default_rng(seed)
+    for pn in oracle_sphere.panels:
+        for nm in ("MOMX", "MOMY"):
+            a = pn.arr(nm)
+            a *= 1.0 + 2.2e-16 * rng.integers(-1, 2, a.shape)
 
 
 def _full_scales(case, scale):
@@ -119,8 +137,9 @@ def _full_scales(case, scale):
     return {"DDENS": dens, "DRHOT": dens * theta, "MOMZ": scale["MOMX"] * c["RPlanet"]}
 
 
-def _check_sphere(case, g, ref_of):
-    """ref_of(P, name) -> reference interior array of panel P."""
+def _check_sphere(case, g, ref_of, pert_of):
+    """ref_of(P, name) -> reference interior array of panel P; pert_of(P, name) -> the same from the oracle run whose initial state
+    was moved by one unit in the last place."""
     scale = {nm: max(np.abs(ref_of(P, nm)).max() for P in range(6)) for nm in PROG}
     full = _full_scales(case, scale)
     errs, full_errs = {}, {}
@@ -131,7 +150,8 @@ def _check_sphere(case, g, ref_of):
             errs[(P, nm)] = _sphere_err(nm, got[nm][:n], ref_of(P, nm), scale[nm], n)
         for nm in full:
             full_errs[(P, nm)] = np.linalg.norm(got[nm][:n] - ref_of(P, nm)) / (full[nm] * np.sqrt(n))
-    _judge_sphere(errs, full_errs)
+    sens = {nm: max(_sphere_err(nm, pert_of(P, nm), ref_of(P, nm), scale[nm], ref_of(P, nm).size) for P in range(6)) for nm in PROG}
+    _judge_sphere(errs, full_errs, sens)
 
 
 @pytest.fixture(params=["1", "2"], ids=["vi_eight_lane", "vi_two_lane"])
@@ -152,9 +172,12 @@ def test_config4_jw_shipped_size_against_oracle(vi_kernel):
     case = GlobalSphereCase.config4(Ne=8, NeZ=4)
     assert case.elem.lumped and case.dt == 75.0
     s = case.make_oracle()
+    s2 = case.make_oracle()
+    _ulp_perturb(s2)
     g = case.make_driver()
-    s.update(5); g.Update(5)
-    _check_sphere(case, g, lambda P, nm: s.panels[P].arr(nm)[:s.panels[P].Ne * s.panels[P].Np])
+    s.update(5); s2.update(5); g.Update(5)
+    _check_sphere(case, g, lambda P, nm: s.panels[P].arr(nm)[:s.panels[P].Ne * s.panels[P].Np],
+                  lambda P, nm: s2.panels[P].arr(nm)[:s2.panels[P].Ne * s2.panels[P].Np])
     # the wave perturbation has propagated: DDENS differs from zero on the perturbed panel
     assert max(np.abs(p.arr("DDENS")[:p.Ne * p.Np]).max() for p in s.panels) > 1e-6
 
@@ -171,11 +194,16 @@ def test_config4_jw_full_size_against_oracle_fixture(vi_kernel):
     g.Update(nsteps)
     if os.environ.get("FEDG_LIVE_ORACLE") == "1":
         s = case.make_oracle(); s.update(nsteps)
-        _check_sphere(case, g, lambda P, nm: s.panels[P].arr(nm)[:s.panels[P].Ne * s.panels[P].Np])
+        ref = {(P, nm): s.panels[P].arr(nm)[:s.panels[P].Ne * s.panels[P].Np].copy() for P in range(6) for nm in PROG}
+        del s
+        s2 = case.make_oracle(); _ulp_perturb(s2); s2.update(nsteps)
+        _check_sphere(case, g, lambda P, nm: ref[(P, nm)], lambda P, nm: s2.panels[P].arr(nm)[:s2.panels[P].Ne * s2.panels[P].Np])
         return
     scale = {nm: max(np.abs(fx[f"s_{P}_{nm}"]).max() for P in range(6)) for nm in PROG}
     full = _full_scales(case, scale)
     errs, full_errs = {}, {}
+    sens = {nm: max(_sphere_err(nm, fx[f"u_{P}_{nm}"], fx[f"s_{P}_{nm}"], scale[nm], fx[f"s_{P}_{nm}"].size) for P in range(6)) for nm in PROG}
+    own_tol = _own_tol(sens)
     for P, (d, m) in enumerate(zip(g.panels, case.cs.panels)):
         got = d.get_prog()
         n = m.Ne * case.elem.Np
@@ -183,11 +211,11 @@ def test_config4_jw_full_size_against_oracle_fixture(vi_kernel):
             ref, a = fx[f"s_{P}_{nm}"], got[nm][:n]
             errs[(P, nm)] = _sphere_err(nm, a[::stride], ref, scale[nm], ref.size)
             nrm = float(fx[f"n_{P}_{nm}"])
-            assert abs(np.linalg.norm(a) - nrm) <= _own_tol()[nm] * max(nrm, 1e-3 * scale[nm] * np.sqrt(n)), (P, nm)
+            assert abs(np.linalg.norm(a) - nrm) <= own_tol[nm] * max(nrm, 1e-3 * scale[nm] * np.sqrt(n)), (P, nm)
         for nm in full:
             ref = fx[f"s_{P}_{nm}"]
             full_errs[(P, nm)] = np.linalg.norm(got[nm][:n][::stride] - ref) / (full[nm] * np.sqrt(ref.size))
-    _judge_sphere(errs, full_errs)
+    _judge_sphere(errs, full_errs, sens)
 
 
 # ------------------------------------------------------------------------------------------------ tiles on one device

@@ -93,3 +93,31 @@ def test_global_heve_steady_state_and_hydrostatic_residual():
         hm.append(a); wz.append(b)
     assert hm[0] < 0.2 * cor and hm[1] < 0.1 * hm[0] and hm[2] < 0.1 * hm[1], hm
     assert wz[1] < 0.05 * wz[0] and wz[2] < 0.05 * wz[1] and wz[2] < 1e-6, wz
+
+
+def test_config4_round_off_sensitivity_of_the_oracle():
+    """How far round-off alone carries BASELINE config 4 (Jablonowski-Williamson sphere as shipped: 6 x 8 x 8 x 4, dt = 75 s) in the ORACLE:
+    two runs whose initial MOMX / MOMY differ by at most one unit in the last place, 5 steps.  MOMX / MOMY stay together to 1e-14; DDENS,
+    DRHOT and MOMZ -- near-zero perturbations of a balanced state, advanced through column systems at vertical acoustic CFL ~400 -- drift
+    apart by MORE than 1e-10 of their own norm.  This is the measured reason why tests/test_gpu_config_sizes.py judges those three
+    against SENS_FACTOR x this sensitivity (and 1e-10 of the full-field scale) instead of 1e-10 of their own norm."""
+    from cases import GlobalSphereCase
+    case = GlobalSphereCase.config4(Ne=8, NeZ=4)
+    a, b = case.make_oracle(), case.make_oracle()
+    rng = np.random.default_rng(1)
+    for pn in b.panels:
+        for nm in ("MOMX", "MOMY"):
+            v = pn.arr(nm)
+            v *= 1.0 + 2.2e-16 * rng.integers(-1, 2, v.shape)
+    a.update(5); b.update(5)
+    sens = {}
+    for nm in ("DDENS", "MOMX", "MOMY", "MOMZ", "DRHOT"):
+        ref = [p.arr(nm)[:p.Ne * p.Np] for p in a.panels]
+        got = [p.arr(nm)[:p.Ne * p.Np] for p in b.panels]
+        scale = max(np.abs(r).max() for r in ref)
+        sens[nm] = max(np.linalg.norm(g - r) / max(np.linalg.norm(r), 1e-3 * scale * np.sqrt(r.size)) for g, r in zip(got, ref))
+    print("round-off sensitivity of the oracle, config 4 as shipped, 5 steps:", {k: f"{v:.2e}" for k, v in sens.items()})
+    assert sens["MOMX"] < 1e-13 and sens["MOMY"] < 1e-13
+    for nm in ("DDENS", "DRHOT"):
+        assert 2e-11 < sens[nm] < 5e-9, (nm, sens[nm])
+    assert 5e-10 < sens["MOMZ"] < 1e-7, sens["MOMZ"]

@@ -31,3 +31,32 @@ def test_element_matrices_spmv(ell):
     f = rng.standard_normal(o.NfpTot)
     c, _ = sparsemat_matmul(o.lift_dense(), f, 500 * 2.220446e-16, ell)
     assert np.abs(c - o.elem_op("Lift", f)).max() < 1e-11
+
+
+@pytest.mark.parametrize("ell", [False, True])
+def test_matmul1_2_and_matmul2(ell):
+    """sparsemat_matmul1_2 (c = A (b1 .* b2), scale_sparsemat.F90:386-408) and sparsemat_matmul2 (b(NQ,N) -> c(NQ,M), :411-431) in both
+    storage formats against dense products; on the reference's 5x5 matrix with b1 = b2 = ones the first is the test's (4, 8, 8, 14, 6)."""
+    from oracle_api import sparsemat_matmul_ex
+    c, _ = sparsemat_matmul_ex(A, np.ones(5), EPS, ell, mode=1, b2=np.ones(5))
+    assert np.array_equal(c, [4, 8, 8, 14, 6])
+    rng = np.random.default_rng(5)
+    b1, b2 = rng.standard_normal(5), rng.standard_normal(5)
+    c, _ = sparsemat_matmul_ex(A, b1, EPS, ell, mode=1, b2=b2)
+    assert np.abs(c - A @ (b1 * b2)).max() <= 1e-14
+    B = rng.standard_normal((5, 3))                       # (N, NQ) in C order = b(NQ,N) in Fortran order
+    c, _ = sparsemat_matmul_ex(A, B, EPS, ell, mode=2, NQ=3)
+    assert np.abs(c - A @ B).max() <= 1e-14
+
+
+def test_python_csr_arrays_are_the_oracles():
+    """The host mirror's CSR arrays (1-based val / colIdx / rowPtr, sparsemat_Init :137-195) equal the oracle's, on the reference's 5x5
+    matrix and on an element matrix with the reference's drop tolerance."""
+    from oracle_api import sparsemat_matmul_ex
+    from fe_project_b200.advect3d import SparseMat
+    o = Oracle(3, 1, 1, 1, (-1, 1, -1, 1, -1, 1))
+    for mat, eps in ((A, EPS), (o.dmat_dense(0), 500 * 2.220446e-16), (o.lift_dense(), 500 * 2.220446e-16)):
+        s = SparseMat(mat, eps=eps, storage_format="CSR")
+        _, (val, col, rp) = sparsemat_matmul_ex(mat, np.ones(mat.shape[1]), eps, False)
+        assert np.array_equal(s.val, val) and np.array_equal(s.colIdx, col) and np.array_equal(s.rowPtr, rp)
+        assert s.rowPtr[0] == 1 and s.rowPtr[-1] == s.nnz + 1
