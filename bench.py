@@ -270,8 +270,10 @@ def run_sphere(args, rank=0, world=1, local_rank=0):
     ntile = args.sphere_ntile or (2 if world in (4, 8) else 1)          # 4 / 8 GPUs: 2 x 2 tiles per panel (24 local meshes), the same sphere
     own_ids = [t for t, r in enumerate(panel_owner(world, ntile)) if r == rank]
     # run.conf of test/case/baroclinic_wave_global: Jablonowski-Williamson state, lumped mass matrix, stretched FZ, eta_c = 0, sponge
-    case = GlobalSphereCase.config4(Ne=ne // ntile, NeZ=nez, ntile=ntile, fields_for=own_ids)
+    t_setup = time.perf_counter()
+    case = GlobalSphereCase.config4(Ne=ne // ntile, NeZ=nez, ntile=ntile, fields_for=own_ids, init=args.sphere_init)
     g = case.make_driver(rank=rank, nranks=world, bcast=bcast)
+    t_setup = time.perf_counter() - t_setup
     W, K = max(3, args.warmup), args.steps
     g.Update(W)
     torch.cuda.synchronize()
@@ -317,11 +319,14 @@ def run_sphere(args, rank=0, world=1, local_rank=0):
     if rank == 0:
         emit(dict(
             metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=K, warmup=W, ms_per_step=ms_total / K, higher_is_better=True,
-            scaling=("weak" if world == 1 else "strong"), vs_baseline=None, dtype="f64", data="synthetic",
-            config=dict(workload=f"atm_nonhydro3d global baroclinic wave (Jablonowski-Williamson) on the cubed sphere 6x{ne}x{ne}x{nez} elements p=7, "
+            scaling=("weak" if (world == 1 or args.sphere_ne) else "strong"), vs_baseline=None, dtype="f64", data="synthetic",
+            config=dict(workload=("atm_nonhydro3d global baroclinic wave (Jablonowski-Williamson)" if args.sphere_init == "jw" else
+                                  "atm_nonhydro3d global model, balanced solid-body rotation + perturbations (run.conf of baroclinic_wave_global)")
+                                 + f" on the cubed sphere 6x{ne}x{ne}x{nez} elements p=7, "
                                  f"GLOBALNONHYDRO3D_HEVI, IMEX_ARK324, dt={case.dt}, lumped mass matrix, stretched FZ, modal filter eta_c=0, sponge layer, {len(own_ids)} {'panel' if ntile == 1 else 'tile (2x2 per panel)'}(s) per GPU as local meshes with linked halos"
                                  + (", panel edges between ranks over NCCL" if world > 1 else ""),
-                        dof=dof, l2_policy="inputs larger than L2 (50 MB per field and panel)", hbm_used_gb_rank0=round(hbm_used_gb, 1),
+                        dof=dof, dof_per_gpu=dof // world, l2_policy="inputs larger than L2 (>= 50 MB per field and panel)", hbm_used_gb_rank0=round(hbm_used_gb, 1),
+                        host_setup_s_rank0=round(t_setup, 1),
                         vi_kernel=os.environ.get("FEDG_VI_KERNEL", "2")),
             clocks=clocks, e2e=dict(value=dof / t_e2e, unit=UNIT, h2d_bytes_per_step=nbytes, d2h_bytes_per_step=nbytes, steps_per_call=1),
             gpu_launches=tm["launches"],
@@ -343,6 +348,7 @@ def main():
     ap.add_argument("--nez", type=int, default=WORKLOAD["NeZ"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--sphere-ntile", type=int, default=0, help="global_sphere: k x k tiles per panel (default: 1, or 2 on 4 / 8 GPUs)")
+    ap.add_argument("--sphere-init", default="jw", choices=["jw", "solid_body"], help="global_sphere: initial state (configs[3] = jw; the configs[4] sizes use the cheap analytic one)")
     ap.add_argument("--sphere-ne", type=int, default=0, help="global_sphere: elements per panel edge (default 32 = configs[3]; configs[4] sizes it to the HBM)")
     ap.add_argument("--eqs", default="heve", choices=["heve", "hevi"], help="hevi: NONHYDRO3D_HEVI + IMEX_ARK324 (extra, not the headline)")
     ap.add_argument("--workload", default="density_current", choices=["density_current", "sound_wave", "global_panel", "global_sphere", "advect3d"],

@@ -138,14 +138,16 @@ class GlobalSphereCase:
     FZ_SHIPPED = (0.0, 3000.0, 8000.0, 15000.0, 30000.0)      # run.conf:41 (NeZ = 4)
 
     @classmethod
-    def config4(cls, Ne=8, NeZ=4, ntile=1, fields_for=None, p=7):
-        """BASELINE configs[3] at NeGX = NeGY = Ne * ntile, NeZ levels: every shipped layer is cut into NeZ / 4 equal parts."""
+    def config4(cls, Ne=8, NeZ=4, ntile=1, fields_for=None, p=7, init="jw"):
+        """BASELINE configs[3] at NeGX = NeGY = Ne * ntile, NeZ levels: every shipped layer is cut into NeZ / 4 equal parts.
+        init = "solid_body": the same run.conf on the cheap analytic state (configs[4] sizes: the Jablonowski-Williamson set-up costs a
+        Newton iteration per quadrature point, minutes of host time at 2e8 nodes)."""
         assert NeZ % 4 == 0
         sub = NeZ // 4
         fz0 = np.array(cls.FZ_SHIPPED)
         FZ = np.concatenate([fz0[:1]] + [fz0[i] + (fz0[i + 1] - fz0[i]) * np.arange(1, sub + 1) / sub for i in range(4)])
         return cls(p=p, Ne=Ne, NeZ=NeZ, ztop=30.0e3, dt=75.0 * 8.0 / (Ne * ntile), tinteg="IMEX_ARK324", modalfilter=True, ntile=ntile,
-                   fields_for=fields_for, init="jw", lumped=True, FZ=FZ,
+                   fields_for=fields_for, init=init, lumped=True, FZ=FZ,
                    mf=dict(MF_ETAC_h=0.0, MF_ALPHA_h=1.0, MF_ORDER_h=16, MF_ETAC_v=0.0, MF_ALPHA_v=1.0, MF_ORDER_v=16),
                    sponge=dict(SL_WDAMP_TAU=86400.0, SL_WDAMP_HEIGHT=20.0e3))
 
@@ -163,7 +165,7 @@ class GlobalSphereCase:
         self.FZ = None if FZ is None else np.asarray(FZ, dtype=np.float64)
         self.elem = HexElement(p, lumped=lumped)
         self.consts = c = dict(C0)
-        self.cs = CubedSphere(self.elem, Ne, NeZ, ztop, c["RPlanet"], FZ=self.FZ, ntile=ntile)
+        self.cs = CubedSphere(self.elem, Ne, NeZ, ztop, c["RPlanet"], FZ=self.FZ, ntile=ntile, build=fields_for)
         self.vel_bc = dict(btm="SLIP", top="SLIP")
         if init == "jw":
             self.fields = [initcond.baroclinic_wave_global(m, c=c) if (fields_for is None or t in fields_for) else None
@@ -172,11 +174,10 @@ class GlobalSphereCase:
         H = c["Rdry"] * T0 / c["GRAV"]
         amp = (u0 ** 2 + 2.0 * c["RPlanet"] * c["OHM"] * u0) / (2.0 * c["Rdry"] * T0)
         w2 = perturb * 8.0 / c["RPlanet"] * np.array([0.6, -0.3, 0.74])          # tilted rotation vector [1/s]
-        self.fields = []
-        for t, m in enumerate(self.cs.panels):
+        def one_tile(tm):
+            t, m = tm
             if fields_for is not None and t not in fields_for:
-                self.fields.append(None)
-                continue
+                return None
             P = m.panelID - 1
             Np, NeA, Nel = self.elem.Np, m.NeA, m.Ne
             a, b, z = m.pos_en[0], m.pos_en[1], m.pos_en[2]
@@ -203,7 +204,13 @@ class GlobalSphereCase:
             f["DRHOT"][:Nel] = dens * theta - rhot_hyd
             f["MOMX"][:Nel] = dens * ua; f["MOMY"][:Nel] = dens * ub
             f["MOMZ"][:Nel] = perturb * dens * 0.05 * x[0] * x[1] * np.sin(np.pi * z / ztop)
-            self.fields.append(f)
+            return f
+
+        # the tiles are independent and NumPy releases the GIL in its loops: one thread per own tile
+        from concurrent.futures import ThreadPoolExecutor
+        import os
+        with ThreadPoolExecutor(max_workers=max(1, int(os.environ.get("FEDG_INIT_THREADS", "4")))) as ex_:   # ~250 B per node of temporaries per tile in flight
+            self.fields = list(ex_.map(one_tile, enumerate(self.cs.panels)))
 
     def make_driver(self, rank=0, nranks=1, bcast=None):
         """rank / nranks > 1: only the panels this rank owns get a device context (`g.panel_ids`)."""

@@ -105,11 +105,15 @@ class CubedSphere:
     index P k^2 + tj k + ti, and `links[U][g] = (T, src, rot)` says that the halo of face g of tile U is node-wise the interior
     nodes `src` of tile T, with (MOMX, MOMY) multiplied by `rot` (None inside a panel: same basis)."""
 
-    def __init__(self, elem, Ne, NeZ, ztop, RPlanet, FZ=None, ntile=1):
-        """Ne: elements per tile edge (the panel has ntile * Ne)."""
+    def __init__(self, elem, Ne, NeZ, ztop, RPlanet, FZ=None, ntile=1, build=None):
+        """Ne: elements per tile edge (the panel has ntile * Ne).  build: the tiles whose full geometry is needed (default all; a rank
+        of a multi-GPU run passes the ones it owns): the others are skeletons (sizes, send-buffer maps and face coordinates, enough
+        to link halos to them), and only the links with an end in `build` are worked out."""
         self.elem, self.Ne_h, self.NeZ, self.R, self.ntile = elem, Ne, NeZ, RPlanet, int(ntile)
         k = self.ntile
-        self.panels = [LocalMeshCubedSpherePanel(elem, pid, Ne, Ne, NeZ, ztop, RPlanet, FZ=FZ, sub=(k, ti, tj))
+        self.build = None if build is None else set(int(t) for t in build)
+        self.panels = [LocalMeshCubedSpherePanel(elem, pid, Ne, Ne, NeZ, ztop, RPlanet, FZ=FZ, sub=(k, ti, tj),
+                                                 skeleton=(self.build is not None and (pid - 1) * k * k + tj * k + ti not in self.build))
                        for pid in range(1, 7) for tj in range(k) for ti in range(k)]
         self.panel_of = [P for P in range(6) for _ in range(k * k)]
         self.links = self._build_links()
@@ -146,6 +150,8 @@ class CubedSphere:
                         qi, qj = ti + dx, tj + dy
                         if 0 <= qi < k and 0 <= qj < k:
                             T = self.tile_index(P, qi, qj)
+                            if self.build is not None and U not in self.build and T not in self.build:
+                                continue
                             links[U][g] = (T, self._face_nodes(self.panels[T], fo).copy(), None)
         for Tp in range(6):
             for f in range(4):
@@ -155,24 +161,29 @@ class CubedSphere:
                 for et in range(k):
                     T = self.tile_index(Tp, *self._edge_tile(k, f, et))
                     U = self.tile_index(Up, *self._edge_tile(k, g, k - 1 - et if rev else et))
+                    if self.build is not None and U not in self.build and T not in self.build:
+                        continue
                     mT, mU = self.panels[T], self.panels[U]
                     src = self._face_nodes(mT, f)
                     if rev:
                         src = revert_hori(src, npts, nv, self.Ne_h, self.NeZ)
                     own = self._face_nodes(mU, g)
                     assert own.size == src.size
-                    # positions: horizontal coordinates of the 3D nodes
-                    aT, bT = mT.pos_en[0].reshape(-1)[src], mT.pos_en[1].reshape(-1)[src]
-                    aU, bU = mU.pos_en[0].reshape(-1)[own], mU.pos_en[1].reshape(-1)[own]
-                    rot = np.empty((own.size, 2, 2))
-                    for c, (va, vb) in enumerate(((1.0, 0.0), (0.0, 1.0))):
-                        vl, vt = cs2lonlat_vec(Tp + 1, aT, bT, np.full(own.size, va), np.full(own.size, vb), self.R)
-                        ua, ub = lonlat2cs_vec(Up + 1, aU, bU, vl, vt, self.R)
-                        rot[:, 0, c], rot[:, 1, c] = ua, ub
+                    rot = None
+                    if self.build is None or U in self.build:     # the basis change is applied by the receiving tile
+                        # positions: horizontal coordinates of the 3D nodes
+                        aT, bT = mT.hpos(src)
+                        aU, bU = mU.hpos(own)
+                        rot = np.empty((own.size, 2, 2))
+                        for c, (va, vb) in enumerate(((1.0, 0.0), (0.0, 1.0))):
+                            vl, vt = cs2lonlat_vec(Tp + 1, aT, bT, np.full(own.size, va), np.full(own.size, vb), self.R)
+                            ua, ub = lonlat2cs_vec(Up + 1, aU, bU, vl, vt, self.R)
+                            rot[:, 0, c], rot[:, 1, c] = ua, ub
                     assert g not in links[U], "two faces feed the same halo face"
                     links[U][g] = (T, src.copy(), rot)
         for U in range(len(self.panels)):
-            assert sorted(links[U]) == [0, 1, 2, 3]
+            if self.build is None or U in self.build:
+                assert sorted(links[U]) == [0, 1, 2, 3]
         return links
 
     def exchange_numpy(self, fields, vector_pairs=(("MOMX", "MOMY"),)):

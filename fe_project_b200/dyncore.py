@@ -78,6 +78,7 @@ class AtmDynDGMDriver_nonhydro3d:
         self.consts = dict(consts)
         h = C.c_void_p()
         _lib.check(self.L.fedg_create(C.byref(d), C.byref(h)))
+        keep.clear()          # fedg_create copied what it needs to the device: the expanded Fortran-shaped arrays are not kept on the host
         self.h = h
         self.n_field = mesh.NeA * elem.Np
         self.n_int = mesh.Ne * elem.Np

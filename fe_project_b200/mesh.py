@@ -35,8 +35,11 @@ class LocalMeshCube:
                  xmin: float, xmax: float, ymin: float, ymax: float,
                  zmin: float, zmax: float, FZ: np.ndarray | None = None,
                  periodic=(False, False, False),
-                 NprcX: int = 1, NprcY: int = 1, pi: int = 0, pj: int = 0):
-        """One tile (pi, pj) of an NprcX x NprcY horizontal decomposition; NeX/NeY/NeZ are per tile."""
+                 NprcX: int = 1, NprcY: int = 1, pi: int = 0, pj: int = 0, skeleton: bool = False):
+        """One tile (pi, pj) of an NprcX x NprcY horizontal decomposition; NeX/NeY/NeZ are per tile.
+        skeleton = True: only what OTHER tiles need from this one to link their halos (sizes, vertex coordinates, `VMapB`, `hpos`):
+        no per-node geometry, no VMapM / VMapP -- a rank of a multi-GPU run builds the tiles of the other ranks this way."""
+        self.skeleton = bool(skeleton)
         self.elem = elem
         self.NeX, self.NeY, self.NeZ = NeX, NeY, NeZ
         self.NprcX, self.NprcY, self.pi, self.pj = NprcX, NprcY, pi, pj
@@ -67,6 +70,12 @@ class LocalMeshCube:
         self.ex, self.ey, self.ez = ex, ey, ez
         self.EMap3Dto2D = ex + ey * NeX
 
+        self._vx, self._vy = vx, vy
+        if skeleton:
+            self._build_vmapB()
+            self._build_tile_graph()
+            return
+
         x0, x1 = vx[ex], vx[ex + 1]
         y0, y1 = vy[ey], vy[ey + 1]
         z0, z1 = vz[ez], vz[ez + 1]
@@ -77,12 +86,16 @@ class LocalMeshCube:
 
         xX, yY, zZ = 0.5 * (x1 - x0), 0.5 * (y1 - y0), 0.5 * (z1 - z0)
         J = xX * yY * zZ
-        self.J = np.repeat(J[:, None], Np, axis=1)
+        # J and Escale are constant inside an element of this mapping: kept per element and handed out as read-only broadcast views
+        # of the reference's shapes (the ABI copy in dyncore.py expands them for the call and drops them afterwards) -- 80 B per node
+        # less host memory, which is what lets a 180 GB tile (2.4e8 nodes) be set up from Python
+        self.J = np.broadcast_to(J[:, None], (Ne, Np))
         # Escale(:,ke,d,d): only the diagonal is non-zero for this mapping
-        self.Escale = np.zeros((3, 3, Ne, Np))
-        self.Escale[0, 0] = ((yY * zZ) / J)[:, None]
-        self.Escale[1, 1] = ((xX * zZ) / J)[:, None]
-        self.Escale[2, 2] = ((xX * yY) / J)[:, None]
+        esc = np.zeros((3, 3, Ne, 1))
+        esc[0, 0, :, 0] = (yY * zZ) / J
+        esc[1, 1, :, 0] = (xX * zZ) / J
+        esc[2, 2, :, 0] = (xX * yY) / J
+        self.Escale = np.broadcast_to(esc, (3, 3, Ne, Np))
 
         # normals / Fscale (MeshCubeDom3D_calc_normal + setGeometricInfo)
         self.normal_fn = np.zeros((3, Ne, elem.NfpTot))
@@ -109,6 +122,39 @@ class LocalMeshCube:
         self._build_tile_graph()
 
     # ------------------------------------------------------------------
+    def hpos(self, idx):
+        """Horizontal coordinates (x, y) of the interior nodes with flat 0-based indices idx, from the vertex coordinates (the same
+        expression as pos_en, so the values are bit-identical); available on skeleton tiles too."""
+        idx = np.asarray(idx)
+        ke, p = idx // self.elem.Np, idx % self.elem.Np
+        ex, ey = self.ex[ke], self.ey[ke]
+        x0, x1 = self._vx[ex], self._vx[ex + 1]
+        y0, y1 = self._vy[ey], self._vy[ey + 1]
+        return x0 + 0.5 * (self.elem.x1[p] + 1.0) * (x1 - x0), y0 + 0.5 * (self.elem.x2[p] + 1.0) * (y1 - y0)
+
+    def _boundary_faces(self):
+        """Per tile face: (elements on it in ascending order, their rank along the face), genPatchBoundaryMap ordering."""
+        NeX, NeY, NeZ = self.NeX, self.NeY, self.NeZ
+        ex, ey, ez = self.ex, self.ey, self.ez
+        on = (ey == 0, ex == NeX - 1, ey == NeY - 1, ex == 0, ez == 0, ez == NeZ - 1)
+        rank = (ex + ez * NeX, ey + ez * NeY, ex + ez * NeX, ey + ez * NeY, ex + ey * NeX, ex + ey * NeX)
+        return [(np.nonzero(on[f])[0], rank[f]) for f in range(6)]
+
+    def _build_vmapB(self):
+        """Halo layout (sizes, offsets) and VMapB: the interior node feeding each slot of the send buffer / owning each halo slot."""
+        e = self.elem
+        NeX, NeY, NeZ = self.NeX, self.NeY, self.NeZ
+        Np, Nfp = e.Np, e.Nfp
+        sizes = np.array([NeX * NeZ, NeY * NeZ, NeX * NeZ, NeY * NeZ, NeX * NeY, NeX * NeY]) * Nfp
+        self.halo_face_size = sizes
+        self.halo_face_off = np.concatenate([[0], np.cumsum(sizes)[:-1]])
+        self.Nhalo = int(sizes.sum())
+        vmapB = np.empty(self.Nhalo, dtype=np.int64)
+        for f, (sel, rank) in enumerate(self._boundary_faces()):
+            base = self.halo_face_off[f] + rank[sel] * Nfp
+            vmapB[(base[:, None] + np.arange(Nfp)[None, :]).reshape(-1)] = (sel[:, None] * Np + e.Fmask[f][None, :]).reshape(-1)
+        self.VMapB = vmapB
+
     def _build_maps(self):
         e = self.elem
         NeX, NeY, NeZ, Ne = self.NeX, self.NeY, self.NeZ, self.Ne
@@ -223,7 +269,7 @@ class LocalMeshCubedSpherePanel(LocalMeshCube):
     The lateral halo of the tile holds its own face values: the panel-edge exchange is not part of this class."""
 
     def __init__(self, elem: HexElement, panelID: int, NeX: int, NeY: int, NeZ: int, ztop: float, RPlanet: float,
-                 FZ: np.ndarray | None = None, sub=(1, 0, 0)):
+                 FZ: np.ndarray | None = None, sub=(1, 0, 0), skeleton: bool = False):
         """sub = (k, ti, tj): the tile (ti, tj) of a k x k decomposition of the panel (NeX, NeY are per tile), the layout the
         reference uses beyond six processes (`MeshCubedSphereDom2D` with NprcX = NprcY = k tiles per panel,
         scale_mesh_cubedspheredom2d.F90:193-247).  The tile is its own local mesh: all four lateral faces are filled by links
@@ -233,10 +279,13 @@ class LocalMeshCubedSpherePanel(LocalMeshCube):
         assert 0 <= ti < k and 0 <= tj < k
         w = 2.0 * q / k
         super().__init__(elem, NeX, NeY, NeZ, -q + ti * w, -q + (ti + 1) * w if ti + 1 < k else q,
-                         -q + tj * w, -q + (tj + 1) * w if tj + 1 < k else q, 0.0, ztop, FZ=FZ, periodic=(False, False, False))
+                         -q + tj * w, -q + (tj + 1) * w if tj + 1 < k else q, 0.0, ztop, FZ=FZ, periodic=(False, False, False),
+                         skeleton=skeleton)
         self.sub = (int(k), int(ti), int(tj))
         assert 1 <= panelID <= 6
         self.panelID, self.RPlanet = int(panelID), float(RPlanet)
+        if skeleton:
+            return
         Np, Nfp, Ne = elem.Np, elem.Nfp, self.Ne
         # 2D nodes = bottom-layer elements, k = 0 plane
         a = self.pos_en[0][: self.Ne2D, :Nfp]

@@ -227,3 +227,35 @@ def test_halo_sources_match_the_reference_field_test():
                             ke, fp = _ref_get_index(s_face, Ne, n1, i, k, fph, fpv)
                             ans = 1e6 * T_ref + 1e3 * ke + (e.Fmask[abs(s_face) - 1][fp - 1] + 1)
                             assert got[k - 1, i - 1, fpv - 1, fph - 1] == ans, (U, g, k, i, fpv, fph)
+
+
+@pytest.mark.parametrize("ntile,own", [(1, [2, 3]), (2, [9, 10, 11])])
+def test_skeleton_tiles_give_the_same_links(ntile, own):
+    """A rank of a multi-GPU run builds only its own tiles in full; the others are skeletons (sizes, VMapB, face coordinates).  The
+    links with an end on an own tile -- source indices and the (MOMX, MOMY) basis change -- must be bit-identical to the ones of the
+    fully built sphere, hpos() must reproduce pos_en, and the exchange plan of the rank must not change."""
+    from fe_project_b200.cubedsphere import CubedSphere, exchange_plan, panel_owner
+    from fe_project_b200.element import HexElement
+    e = HexElement(3)
+    FZ = np.array([0.0, 1000.0, 3000.0])
+    full = CubedSphere(e, 2, 2, 3000.0, 6.37122e6, FZ=FZ, ntile=ntile)
+    part = CubedSphere(e, 2, 2, 3000.0, 6.37122e6, FZ=FZ, ntile=ntile, build=own)
+    for t, (a, b) in enumerate(zip(full.panels, part.panels)):
+        assert b.skeleton == (t not in own)
+        assert np.array_equal(a.VMapB, b.VMapB) and a.Nhalo == b.Nhalo and a.Ne == b.Ne
+        idx = np.arange(a.Ne * e.Np)
+        x, y = b.hpos(idx)
+        assert np.array_equal(x, a.pos_en[0].reshape(-1)) and np.array_equal(y, a.pos_en[1].reshape(-1))
+    for U in own:
+        assert sorted(part.links[U]) == [0, 1, 2, 3]
+        for g in range(4):
+            T, src, rot = full.links[U][g]
+            T2, src2, rot2 = part.links[U][g]
+            assert T == T2 and np.array_equal(src, src2)
+            assert (rot is None) == (rot2 is None) and (rot is None or np.array_equal(rot, rot2))
+    n = 6 * ntile * ntile
+    owner = [0 if t in own else 1 for t in range(n)]
+    pf, pp = exchange_plan(full.links, owner, 0), exchange_plan(part.links, owner, 0)
+    assert pf == pp
+    for T, peer, mid, U, g in pp[2]:                      # what this rank sends: source indices on its own tiles
+        assert np.array_equal(full.links[U][g][1], part.links[U][g][1])
