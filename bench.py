@@ -277,9 +277,12 @@ def run_sphere(args, rank=0, world=1, local_rank=0):
     W, K = max(3, args.warmup), args.steps
     g.Update(W)
     torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank); sampler.start(); sampler.wait_started()
+    # barrier RIGHT before the timed steps: starting the clock sampler takes a different time on every rank, and a rank that enters the
+    # region early spends the difference waiting in its first panel-edge exchange (measured: 20-40 ms on 8 GPUs, profiles/README.md)
+    torch.cuda.synchronize()
     if dist:
         dist.barrier()
-    sampler = ClockSampler(local_rank); sampler.start(); sampler.wait_started()
     g.Update(K)
     torch.cuda.synchronize()
     tm = g.last_timing()

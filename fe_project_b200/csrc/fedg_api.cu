@@ -1881,12 +1881,18 @@ int fedg_group_update(fedg_ctx** ctxs, int n, int nsteps) {
   CUDA_TRY(cudaEventRecord(lead->ev[0], lead->stream));
   const int ns = lead->rk.nstage;
   long launches = 0;
+  // FEDG_GROUP_TIMING=1 (diagnostic): events around every remote exchange, the sum is printed per rank on stderr
+  static const bool timing = [] { const char* e = getenv("FEDG_GROUP_TIMING"); return e && e[0] == '1'; }();
+  std::vector<cudaEvent_t> tev;
+  auto mark = [&]() { if (timing) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, lead->stream); tev.push_back(e); } };
   for (int step = 0; step < nsteps; ++step) {
     for (int i = 0; i < n; ++i) hevi_begin_step(ctxs[i]);
     for (int s = 0; s < ns; ++s) {
       if (lead->hevi) {
         for (int i = 0; i < n; ++i) { int rc = hevi_stage_vi(ctxs[i], s, nullptr, nullptr); if (rc) return rc; }     // cal_vi + StoreImplicit
+        mark();
         { int rc = group_exchange_remote(ctxs, n); if (rc) return rc; }                                              // panel edges owned by other ranks
+        mark();
         for (int i = 0; i < n; ++i) { int rc = hevi_stage_ex(ctxs[i], s); if (rc) return rc; }                        // exchange + cal_tend_ex
         for (int i = 0; i < n; ++i) hevi_stage_combine(ctxs[i], s);                                                  // Advance
         launches += 4L * n;
@@ -1905,6 +1911,13 @@ int fedg_group_update(fedg_ctx** ctxs, int n, int nsteps) {
   float ms = 0;
   CUDA_TRY(cudaEventElapsedTime(&ms, lead->ev[0], lead->ev[1]));
   lead->last_ms_total = ms; lead->last_ms_stage = 0; lead->last_launches = launches;
+  if (timing) {
+    float ex = 0, mx = 0;
+    for (size_t k = 0; k + 1 < tev.size(); k += 2) { float t = 0; cudaEventElapsedTime(&t, tev[k], tev[k + 1]); ex += t; mx = std::max(mx, t); }
+    for (cudaEvent_t e : tev) cudaEventDestroy(e);
+    fprintf(stderr, "[fedg group timing] rank %d: %d steps %.2f ms total, remote exchanges %.2f ms (%zu, longest %.3f ms)\n", lead->my_rank, nsteps, ms, ex,
+            tev.size() / 2, mx);
+  }
   return FEDG_OK;
 }
 

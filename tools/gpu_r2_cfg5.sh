@@ -5,13 +5,26 @@ N=${N:-1}; NE=${NE:-32}; INIT=${INIT:-solid_body}; STEPS=${STEPS:-3}; TMO=${TMO:
 mkdir -p gpurun_out
 free -g | head -2; nproc
 export FEDG_INIT_THREADS=${INIT_THREADS:-4}
-out=gpurun_out/r02_cfg5_${N}gpu_ne${NE}
+out=gpurun_out/r02_cfg5_${N}gpu_ne${NE}${TAG}
+if [ -n "$DIAG" ]; then export FEDG_GROUP_TIMING=1; nvidia-smi --query-gpu=index,clocks.sm,power.draw,clocks_throttle_reasons.active --format=csv,noheader -lms 250 > $out.smi 2>&1 & SMI=$!; fi
 if [ "$N" = "1" ]; then
   timeout $TMO python bench.py --workload global_sphere --sphere-ne $NE --sphere-init $INIT --steps $STEPS --warmup 3 > $out.json 2> $out.err
 else
   timeout $TMO python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29571 bench.py --gpus $N --workload global_sphere --sphere-ne $NE --sphere-init $INIT --steps $STEPS --warmup 3 > $out.json 2> $out.err
 fi
-echo "rc=$?"; tail -3 $out.err | cut -c1-300
+echo "rc=$?"; [ -n "$SMI" ] && kill $SMI; grep "fedg group timing" $out.err | tail -16; tail -3 $out.err | cut -c1-300
+if [ -n "$DIAG" ]; then python - <<PY2
+import collections
+mn=collections.defaultdict(lambda:1e9); pw=collections.defaultdict(float); rs=collections.defaultdict(set)
+for ln in open("$out.smi"):
+    p=[x.strip() for x in ln.split(",")]
+    if len(p)<4: continue
+    try: c=float(p[1].split()[0]); w=float(p[2].split()[0])
+    except Exception: continue
+    if w>300: mn[p[0]]=min(mn[p[0]],c); pw[p[0]]=max(pw[p[0]],w); rs[p[0]].add(p[3])
+for k in sorted(mn): print("gpu",k,"min sm MHz under load",mn[k],"max W",pw[k],"reasons",sorted(rs[k]))
+PY2
+fi
 python - <<PY
 import json
 try:
