@@ -111,7 +111,7 @@ struct fedg_ctx {
   bool has_phyt = false;
   // HEVI: stage tendencies k_ex / k_im [stage][var], var0-based IMEX combination, column-solver scratch
   std::vector<DevBuf> kex, kim;
-  DevBuf rhot_hyd_vi, vi_scratch;
+  DevBuf rhot_hyd_vi, vi_scratch, vi_pvu, vi_pvv;
   double last_ms_vi = 0;
   int* d_vmapP = nullptr; int* d_emap2d = nullptr; int* d_vmapB = nullptr; int* d_halo_src = nullptr;
   // multi-GPU: NCCL state and the interior / tile-boundary element lists used to overlap the exchange
@@ -180,7 +180,7 @@ struct fedg_ctx {
     for (auto& b : tendbuf) b.release();
     for (auto& b : kex) b.release();
     for (auto& b : kim) b.release();
-    rhot_hyd_vi.release(); vi_scratch.release();
+    rhot_hyd_vi.release(); vi_scratch.release(); vi_pvu.release(); vi_pvv.release();
     for (DevBuf* b : {&dens_hyd, &pres_hyd, &therm_hyd, &rtot, &cvtot, &cptot, &gsqrt, &g13, &g23, &gsqrtH, &dphydx, &dphydy,
                       &coriolis, &escale, &fscale, &pres, &w3, &Jac, &zlev, &mon, &g2d})
       b->release();
@@ -510,7 +510,8 @@ int fedg_dyn_init(fedg_ctx* c, const char* eqs_type, const char* tinteg_type, do
     // driver_nonhydro3d.F90:437-452: the HEVI equation sets run with an IMEX scheme
     if (!c->rk.imex) return fail(FEDG_ERR_ARG, "HEVI needs an IMEX scheme (IMEX_ARK232, IMEX_ARK324)");
     if (c->np != 8) return fail(FEDG_ERR_UNSUPPORTED, "the vertical-implicit column kernel is built for p = 7 only");
-    if (c->terrain) return fail(FEDG_ERR_UNSUPPORTED, "terrain-following HEVI is not available in this build");
+    // terrain-following HEVI (regional): the eight-lane column kernel with the metric terms, two passes per implicit stage
+    if (c->terrain) { if (c->vi_pvu.n < c->nint) CUDA_TRY(c->vi_pvu.alloc(c->nint)); if (c->vi_pvv.n < c->nint) CUDA_TRY(c->vi_pvv.alloc(c->nint)); }
     if (2 * c->rk.nstage > MAXTERM) return fail(FEDG_ERR_UNSUPPORTED, "too many IMEX stages");
     c->kex.resize(size_t(c->rk.nstage) * NVAR); c->kim.resize(size_t(c->rk.nstage) * NVAR);
     for (auto& b : c->kex) if (b.n < c->nint) CUDA_TRY(b.alloc(c->nint));
@@ -778,6 +779,10 @@ void fill_vi_params(fedg_ctx* c, VIParams& V, int in, int out, int i0, int stage
   V.escale = c->escale.p; V.fscale = c->fscale.p; V.tab = c->d_tab; V.htab = &c->tab; V.scratch = c->vi_scratch.p;
   V.c = c->c; V.impl_fac = impl_fac; V.Ne = c->Ne; V.Ne2D = c->Ne2D; V.NeZ = c->NeZ;
   { const char* e = getenv("FEDG_EXACT_POW"); V.exact_pow = (e && e[0] == '1') ? 1 : 0; }
+  if (c->terrain && !c->global) {
+    V.gsqrt = c->gsqrt.p; V.g13 = c->g13.p; V.g23 = c->g23.p; V.gsqrtH = c->gsqrtH.p;
+    V.pvu_out = c->vi_pvu.p; V.pvv_out = c->vi_pvv.p;
+  }
 }
 
 // HEVI / IMEX step (driver_nonhydro3d.F90:703-763 + 769-921): per stage  cal_vi -> StoreImplicit -> halo + BC ->

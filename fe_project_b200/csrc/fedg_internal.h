@@ -107,6 +107,12 @@ struct VIParams {
   int Ne, Ne2D, NeZ;
   int exact_pow;              // pow() instead of exp(e log x) for the equation of state
   const ElemTables* htab;     // HOST copy of the operator tables (the second kernel derives its constant-memory tables from it)
+  // terrain-following mesh (gsqrt != nullptr): Gsqrt, G13, G23 per node, GsqrtH per 2D node; MOMX', MOMY' after their implicit solve
+  // (written by pass 0 into pvu_out / pvv_out, read by pass 1 through pvu / pvv)
+  const double *gsqrt, *g13, *g23, *gsqrtH;
+  const double *pvu, *pvv;
+  double *pvu_out, *pvv_out;
+  int pass0;
 };
 constexpr int MAXTERM = 20;   // 2 * stages of the largest IMEX scheme supported
 struct LinCombParams {

@@ -16,8 +16,12 @@
 // rows busy at every step and needs no triangular solves.  The (MOMX, MOMY) system is an 8x8 block with a scalar
 // coupling and runs in the same sweep with one row per lane.
 //
-// Scope of this kernel: flat MeshCubeDom3D geometry (GsqrtV = 1, G13 = G23 = 0), the configuration the regional
-// HEVI cases run on; terrain-following HEVI is rejected at fedg_dyn_init.
+// TERRAIN = false: flat MeshCubeDom3D geometry (GsqrtV = 1, G13 = G23 = 0), the configuration the regional and global HEVI cases
+// run on.  TERRAIN = true (regional mesh with topography): GsqrtV = Gsqrt / GsqrtH scales every row of the vertical operator, the
+// vertical mass flux is MOMZ + GsqrtV (G13 MOMX + G23 MOMY) with the horizontal momenta AFTER their own implicit solve
+// (rhot_hevi.F90:895-925 calls solve_uv before eval_Ax), and the dissipation coefficient carries Gnn = 1/GsqrtV^2 + G13^2 + G23^2
+// (vi_cal_del_flux_dyn_uv :1100-1130).  Because the (MOMX, MOMY) solution of a node is only known after the backward sweep, the
+// terrain path runs the kernel twice: pass 0 solves the horizontal momenta alone and stores them, pass 1 is the full solve.
 #include <cstdint>
 #include <cstdlib>
 
@@ -31,20 +35,27 @@ struct NodeQ {            // quantities of one node evaluated on var0 (the Newto
   double rho0, w0, th0, u0, v0;   // DDENS, MOMZ, DRHOT, MOMX, MOMY of var0
   double dens, rhot, pot, wt, dpd, dpres_vol, a;
   double dpf;                     // face form of the pressure perturbation (vi_cal_del_flux_dyn :1262-1266: dens * pott instead of RHOT)
+  double rgv, mw;                 // TERRAIN: 1 / GsqrtV and the vertical mass flux MOMZ + GsqrtV (G13 MOMX' + G23 MOMY'); flat: 1 and MOMZ
 };
 
 // raw inputs of one node: var0 (5), DENS_hyd, RHOT_hyd (dry, as the solver recomputes it), PRES_hyd, and for moist runs
 // Rtot, CPtot, CVtot
 struct RawQ {
   double rho0, w0, th0, u0, v0, dh, rh, ph, R, cp, cv;
+  double gs, g13, g23, up, vp;    // TERRAIN: Gsqrt, G13, G23 and the horizontal momenta after their implicit solve (pass 1) / of var0
 };
-template <bool MOIST>
+template <bool MOIST, bool TERRAIN>
 __device__ __forceinline__ RawQ raw_load(const VIParams& P, size_t n) {
   RawQ r;
   r.rho0 = P.q0[V_DDENS][n]; r.w0 = P.q0[V_MOMZ][n]; r.th0 = P.q0[V_DRHOT][n]; r.u0 = P.q0[V_MOMX][n]; r.v0 = P.q0[V_MOMY][n];
   r.dh = P.dens_hyd[n]; r.rh = P.rhot_hyd_vi[n]; r.ph = P.pres_hyd[n];
   r.R = r.cp = r.cv = 0.0;
   if (MOIST) { r.R = P.rtot[n]; r.cp = P.cptot[n]; r.cv = P.cvtot[n]; }
+  r.gs = 1.0; r.g13 = r.g23 = 0.0; r.up = r.u0; r.vp = r.v0;
+  if (TERRAIN) {
+    r.gs = P.gsqrt[n]; r.g13 = P.g13[n]; r.g23 = P.g23[n];
+    if (P.pvu) { r.up = P.pvu[n]; r.vp = P.pvv[n]; }
+  }
   return r;
 }
 // x^e as exp(e log x) for x = Rtot RHOT / P00 in [0.25, 2] (see eos_pres_fast in stage_common.cuh: <= 3.5e-16 relative, 64 % of
@@ -54,8 +65,9 @@ __device__ __forceinline__ double vi_pow(double x, double e, int exact) {
   return pow(x, e);
 }
 
-template <bool MOIST>
-__device__ __forceinline__ NodeQ node_q(const VIParams& P, const RawQ& r) {
+// rgh = 1 / GsqrtH of the column (TERRAIN only)
+template <bool MOIST, bool TERRAIN>
+__device__ __forceinline__ NodeQ node_q(const VIParams& P, const RawQ& r, double rgh) {
   NodeQ q;
   q.rho0 = r.rho0; q.w0 = r.w0; q.th0 = r.th0; q.u0 = r.u0; q.v0 = r.v0;
   const double R = MOIST ? r.R : P.c.Rdry;
@@ -65,10 +77,21 @@ __device__ __forceinline__ NodeQ node_q(const VIParams& P, const RawQ& r) {
   q.pot = q.rhot / q.dens;
   const double ptot = P.c.PRES00 * vi_pow(R * P.c.rP0 * q.rhot, gm, P.exact_pow);
   q.dpres_vol = ptot - r.ph;
-  q.wt = q.w0 / q.dens;
   q.dpd = gm * ptot / q.rhot;
   const double rdens0 = 1.0 / q.dens;
-  q.a = fabs(q.w0 * rdens0) + sqrt(P.c.gamm * ptot * rdens0);
+  if (TERRAIN) {
+    const double gv = r.gs * rgh;      // GsqrtV = Gsqrt / GsqrtH (rhot_hevi.F90:864)
+    q.rgv = 1.0 / gv;
+    q.mw = q.w0 + gv * r.g13 * r.up + gv * r.g23 * r.vp;                 // eval_Ax :224-230, with the updated horizontal momenta
+    q.wt = q.mw / q.dens;
+    const double wt0 = (q.w0 * q.rgv + r.g13 * q.u0 + r.g23 * q.v0) * rdens0;     // vi_cal_del_flux_dyn_uv :1100-1130, on var0
+    const double Gnn = q.rgv * q.rgv + r.g13 * r.g13 + r.g23 * r.g23;
+    q.a = fabs(wt0) + sqrt(Gnn * P.c.gamm * ptot * rdens0);
+  } else {
+    q.rgv = 1.0; q.mw = q.w0;
+    q.wt = q.w0 / q.dens;
+    q.a = fabs(q.w0 * rdens0) + sqrt(P.c.gamm * ptot * rdens0);
+  }
   q.dpf = P.c.PRES00 * vi_pow(R * P.c.rP0 * q.dens * q.pot, gm, P.exact_pow) - r.ph;
   return q;
 }
@@ -181,19 +204,22 @@ constexpr int VI_YROW = 14;       // eliminated DDENS row of a node: [W_0..7 | T
 // warp on distinct banks for the broadcast 128-bit loads
 constexpr int VI_SOL = 96 + 24 + 2 * PROW + VI_PREV + 8 * VI_YROW;
 static_assert(VI_SOL == 292, "bank layout");
-constexpr int VI_NQ = 13;         // doubles of a NodeQ parked in shared memory across the elimination
+constexpr int VI_NQ = 13;         // doubles of a NodeQ parked in shared memory across the elimination (+ 2 with TERRAIN)
 constexpr int VI_PF = 16;         // prefetch slots per thread: raw inputs of the node two elements up (11) + qcur of the next element (5)
+constexpr int VI_NQ_T = 15, VI_PF_T = 21;   // TERRAIN: rgv, mw parked; Gsqrt, G13, G23, MOMX', MOMY' prefetched
 
 __device__ __forceinline__ void park(double* s, const NodeQ& q) {
   s[0 * VI_THREADS] = q.rho0; s[1 * VI_THREADS] = q.w0; s[2 * VI_THREADS] = q.th0; s[3 * VI_THREADS] = q.u0; s[4 * VI_THREADS] = q.v0;
   s[5 * VI_THREADS] = q.dens; s[6 * VI_THREADS] = q.rhot; s[7 * VI_THREADS] = q.pot; s[8 * VI_THREADS] = q.wt; s[9 * VI_THREADS] = q.dpd;
   s[10 * VI_THREADS] = q.dpres_vol; s[11 * VI_THREADS] = q.a; s[12 * VI_THREADS] = q.dpf;
 }
+__device__ __forceinline__ void park_t(double* s, const NodeQ& q) { s[13 * VI_THREADS] = q.rgv; s[14 * VI_THREADS] = q.mw; }
 __device__ __forceinline__ NodeQ unpark(const double* s) {
   NodeQ q;
   q.rho0 = s[0 * VI_THREADS]; q.w0 = s[1 * VI_THREADS]; q.th0 = s[2 * VI_THREADS]; q.u0 = s[3 * VI_THREADS]; q.v0 = s[4 * VI_THREADS];
   q.dens = s[5 * VI_THREADS]; q.rhot = s[6 * VI_THREADS]; q.pot = s[7 * VI_THREADS]; q.wt = s[8 * VI_THREADS]; q.dpd = s[9 * VI_THREADS];
   q.dpres_vol = s[10 * VI_THREADS]; q.a = s[11 * VI_THREADS]; q.dpf = s[12 * VI_THREADS];
+  q.rgv = 1.0; q.mw = q.w0;
   return q;
 }
 
@@ -207,7 +233,7 @@ __device__ __forceinline__ double group_matvec_s(const double* __restrict__ sMT,
 
 // IMPLICIT = false is the explicit evaluation k_im = -A_v(q) of a stage with a_im(s,s) = 0 (first stage of the ARK schemes): no
 // elimination code, a fraction of the registers, so it runs at the occupancy of a streaming kernel.
-template <bool MOIST, bool IMPLICIT, int MINB>
+template <bool MOIST, bool IMPLICIT, int MINB, bool TERRAIN>
 __global__ void __launch_bounds__(VI_THREADS, MINB) vi_column_kernel(const __grid_constant__ VIParams P) {
   const int tid = threadIdx.x, grp = tid >> 3, l8 = tid & 7;
   const int ncol = P.Ne2D * 64;
@@ -226,7 +252,9 @@ __global__ void __launch_bounds__(VI_THREADS, MINB) vi_column_kernel(const __gri
   double* sPrev = sRow + 2 * PROW;
   double* sY = sPrev + VI_PREV;
   double* sQ = smem + 144 + size_t(VI_THREADS / 8) * VI_SOL + tid;   // [VI_NQ][VI_THREADS]
-  double* sPF = sQ + size_t(VI_NQ) * VI_THREADS;                      // [VI_PF][VI_THREADS]
+  double* sPF = sQ + size_t(TERRAIN ? VI_NQ_T : VI_NQ) * VI_THREADS;   // [VI_PF][VI_THREADS]
+  const bool pass0 = TERRAIN && IMPLICIT && P.pass0;                  // terrain pass 0: only the (MOMX, MOMY) solve, stored in pvu_out / pvv_out
+  const double rgh = TERRAIN ? 1.0 / P.gsqrtH[size_t(ke2d) * 64 + ij] : 1.0;
   for (int m = tid; m < 144; m += VI_THREADS) {
     if (m < 128) { const int r = (m & 63) >> 3, c = m & 7; smem[(m & 64) + c * 8 + r] = m < 64 ? P.tab->D[m] : P.tab->VP[m - 64]; }
     else smem[m] = P.tab->Lw[m - 128];
@@ -247,6 +275,10 @@ __global__ void __launch_bounds__(VI_THREADS, MINB) vi_column_kernel(const __gri
       cp_async8(sPF + 4 * VI_THREADS, P.q0[V_MOMY] + m); cp_async8(sPF + 5 * VI_THREADS, P.dens_hyd + m);
       cp_async8(sPF + 6 * VI_THREADS, P.rhot_hyd_vi + m); cp_async8(sPF + 7 * VI_THREADS, P.pres_hyd + m);
       if (MOIST) { cp_async8(sPF + 8 * VI_THREADS, P.rtot + m); cp_async8(sPF + 9 * VI_THREADS, P.cptot + m); cp_async8(sPF + 10 * VI_THREADS, P.cvtot + m); }
+      if (TERRAIN) {
+        cp_async8(sPF + 16 * VI_THREADS, P.gsqrt + m); cp_async8(sPF + 17 * VI_THREADS, P.g13 + m); cp_async8(sPF + 18 * VI_THREADS, P.g23 + m);
+        cp_async8(sPF + 19 * VI_THREADS, (P.pvu ? P.pvu : P.q0[V_MOMX]) + m); cp_async8(sPF + 20 * VI_THREADS, (P.pvv ? P.pvv : P.q0[V_MOMY]) + m);
+      }
     }
     if (IMPLICIT && kc < NeZ) {
       const size_t m = node(kc);
@@ -257,7 +289,7 @@ __global__ void __launch_bounds__(VI_THREADS, MINB) vi_column_kernel(const __gri
     cp_async_commit();
   };
   prefetch(1, 0);
-  NodeQ q = node_q<MOIST>(P, raw_load<MOIST>(P, node(0)));
+  NodeQ q = node_q<MOIST, TERRAIN>(P, raw_load<MOIST, TERRAIN>(P, node(0)), rgh);
 
   // ---------------- forward sweep
   for (int kz = 0; kz < NeZ; ++kz) {
@@ -273,7 +305,9 @@ __global__ void __launch_bounds__(VI_THREADS, MINB) vi_column_kernel(const __gri
       r.v0 = sPF[4 * VI_THREADS]; r.dh = sPF[5 * VI_THREADS]; r.rh = sPF[6 * VI_THREADS]; r.ph = sPF[7 * VI_THREADS];
       r.R = r.cp = r.cv = 0.0;
       if (MOIST) { r.R = sPF[8 * VI_THREADS]; r.cp = sPF[9 * VI_THREADS]; r.cv = sPF[10 * VI_THREADS]; }
-      qn = node_q<MOIST>(P, r);
+      r.gs = 1.0; r.g13 = r.g23 = 0.0; r.up = r.u0; r.vp = r.v0;
+      if (TERRAIN) { r.gs = sPF[16 * VI_THREADS]; r.g13 = sPF[17 * VI_THREADS]; r.g23 = sPF[18 * VI_THREADS]; r.up = sPF[19 * VI_THREADS]; r.vp = sPF[20 * VI_THREADS]; }
+      qn = node_q<MOIST, TERRAIN>(P, r, rgh);
     }
     double cr = 0.0, cw_ = 0.0, ct = 0.0, cu = 0.0, cv = 0.0;   // state entering the stage at the own node
     if (IMPLICIT) { cr = sPF[11 * VI_THREADS]; cw_ = sPF[12 * VI_THREADS]; ct = sPF[13 * VI_THREADS]; cu = sPF[14 * VI_THREADS]; cv = sPF[15 * VI_THREADS]; }
@@ -297,45 +331,50 @@ __global__ void __launch_bounds__(VI_THREADS, MINB) vi_column_kernel(const __gri
     const double rM_t = __shfl_sync(FULL, q.rho0, 7, 8), wM_t = __shfl_sync(FULL, q.w0, 7, 8), tM_t = __shfl_sync(FULL, q.th0, 7, 8);
     const double pM_t = __shfl_sync(FULL, q.pot, 7, 8), dM_t = __shfl_sync(FULL, dpf_own, 7, 8);
     const double uM_t = __shfl_sync(FULL, q.u0, 7, 8), vM_t = __shfl_sync(FULL, q.v0, 7, 8);
+    // vertical mass flux of the own face nodes (TERRAIN: MOMZ + GsqrtV (G13 MOMX + G23 MOMY); flat: MOMZ itself)
+    const double mwM_b = TERRAIN ? __shfl_sync(FULL, q.mw, 0, 8) : wM_b, mwM_t = TERRAIN ? __shfl_sync(FULL, q.mw, 7, 8) : wM_t;
     double rP_b, wP_b, mwP_b, tP_b, pP_b, dP_b, uP_b, vP_b, rP_t, wP_t, mwP_t, tP_t, pP_t, dP_t, uP_t, vP_t;
     double potn_b = 0.0, wtn_b = 0.0, dpdn_b = 0.0;   // Jacobian factors of the node below the bottom face
-    if (bot_bc) { rP_b = rM_b; wP_b = -wM_b; mwP_b = -wM_b; tP_b = tM_b; pP_b = pM_b; dP_b = dM_b; uP_b = uM_b; vP_b = vM_b; }
+    // slip wall (vi_cal_del_flux_dyn :1268-1274): MOMZ_P = -MOMZ_M - 2 GsqrtV (G13 MOMX + G23 MOMY) = MOMZ_M - 2 MW_M, MW_P = -MW_M
+    if (bot_bc) { rP_b = rM_b; wP_b = TERRAIN ? wM_b - 2.0 * mwM_b : -wM_b; mwP_b = -mwM_b; tP_b = tM_b; pP_b = pM_b; dP_b = dM_b; uP_b = uM_b; vP_b = vM_b; }
     else {
-      rP_b = sPrev[0]; wP_b = sPrev[1]; mwP_b = wP_b; tP_b = sPrev[2]; pP_b = sPrev[3]; dP_b = sPrev[8];
+      rP_b = sPrev[0]; wP_b = sPrev[1]; mwP_b = TERRAIN ? sPrev[10] : wP_b; tP_b = sPrev[2]; pP_b = sPrev[3]; dP_b = sPrev[8];
       uP_b = sPrev[4]; vP_b = sPrev[5]; potn_b = sPrev[3]; wtn_b = sPrev[6]; dpdn_b = sPrev[7];
     }
-    if (top_bc) { rP_t = rM_t; wP_t = -wM_t; mwP_t = -wM_t; tP_t = tM_t; pP_t = pM_t; dP_t = dM_t; uP_t = uM_t; vP_t = vM_t; }
+    if (top_bc) { rP_t = rM_t; wP_t = TERRAIN ? wM_t - 2.0 * mwM_t : -wM_t; mwP_t = -mwM_t; tP_t = tM_t; pP_t = pM_t; dP_t = dM_t; uP_t = uM_t; vP_t = vM_t; }
     else {
-      rP_t = __shfl_sync(FULL, qn.rho0, 0, 8); wP_t = __shfl_sync(FULL, qn.w0, 0, 8); mwP_t = wP_t;
+      rP_t = __shfl_sync(FULL, qn.rho0, 0, 8); wP_t = __shfl_sync(FULL, qn.w0, 0, 8); mwP_t = TERRAIN ? __shfl_sync(FULL, qn.mw, 0, 8) : wP_t;
       tP_t = __shfl_sync(FULL, qn.th0, 0, 8); pP_t = __shfl_sync(FULL, qn.pot, 0, 8); dP_t = __shfl_sync(FULL, dpf_next, 0, 8);
       uP_t = __shfl_sync(FULL, qn.u0, 0, 8); vP_t = __shfl_sync(FULL, qn.v0, 0, 8);
     }
     // flux jumps (vi_cal_del_flux_dyn :1306-1322, _uv :1158-1161); nz = -1 at the bottom face, +1 at the top face
     const double hb = 0.5 * Fs_b, ht = 0.5 * Fs_t;
-    const double dl_r_b = hb * ((mwP_b - wM_b) * (-1.0) - alph_b * (rP_b - rM_b));
+    const double dl_r_b = hb * ((mwP_b - mwM_b) * (-1.0) - alph_b * (rP_b - rM_b));
     const double dl_w_b = hb * ((dP_b - dM_b) * (-1.0) - alph_b * (wP_b - wM_b));
-    const double dl_t_b = hb * ((pP_b * mwP_b - pM_b * wM_b) * (-1.0) - alph_b * (tP_b - tM_b));
-    const double dl_r_t = ht * ((mwP_t - wM_t) * (1.0) - alph_t * (rP_t - rM_t));
+    const double dl_t_b = hb * ((pP_b * mwP_b - pM_b * mwM_b) * (-1.0) - alph_b * (tP_b - tM_b));
+    const double dl_r_t = ht * ((mwP_t - mwM_t) * (1.0) - alph_t * (rP_t - rM_t));
     const double dl_w_t = ht * ((dP_t - dM_t) * (1.0) - alph_t * (wP_t - wM_t));
-    const double dl_t_t = ht * ((pP_t * mwP_t - pM_t * wM_t) * (1.0) - alph_t * (tP_t - tM_t));
+    const double dl_t_t = ht * ((pP_t * mwP_t - pM_t * mwM_t) * (1.0) - alph_t * (tP_t - tM_t));
     const double dl_u_b = (-0.5 * Fs_b * alph_b) * (uP_b - uM_b), dl_v_b = (-0.5 * Fs_b * alph_b) * (vP_b - vM_b);
     const double dl_u_t = (-0.5 * Fs_t * alph_t) * (uP_t - uM_t), dl_v_t = (-0.5 * Fs_t * alph_t) * (vP_t - vM_t);
 
     // ---- vertical operator at var0 (eval_Ax :224-262, eval_Ax_uv :546-553); GsqrtV = 1
-    const double dz_r = group_matvec_s(sDT, l8, q.w0);
-    const double dz_t = group_matvec_s(sDT, l8, q.pot * q.w0);
+    const double dz_r = group_matvec_s(sDT, l8, TERRAIN ? q.mw : q.w0);
+    const double dz_t = group_matvec_s(sDT, l8, q.pot * (TERRAIN ? q.mw : q.w0));
     const double dz_w = group_matvec_s(sDT, l8, q.dpres_vol);
     const double drho = group_matvec_s(sVPT, l8, q.rho0);
-    const double t_r = -(E33 * dz_r + (lw0 * dl_r_b + lw1 * dl_r_t));
-    const double t_t = -(E33 * dz_t + (lw0 * dl_t_b + lw1 * dl_t_t));
-    const double t_w = -(E33 * dz_w + (lw0 * dl_w_b + lw1 * dl_w_t)) - P.c.GRAV * drho;
-    const double t_u = -(lw0 * dl_u_b + lw1 * dl_u_t), t_v = -(lw0 * dl_v_b + lw1 * dl_v_t);
+    double t_r = -(E33 * dz_r + (lw0 * dl_r_b + lw1 * dl_r_t));
+    double t_t = -(E33 * dz_t + (lw0 * dl_t_b + lw1 * dl_t_t));
+    double t_w = -(E33 * dz_w + (lw0 * dl_w_b + lw1 * dl_w_t));
+    double t_u = -(lw0 * dl_u_b + lw1 * dl_u_t), t_v = -(lw0 * dl_v_b + lw1 * dl_v_t);
+    if (TERRAIN) { t_r *= q.rgv; t_t *= q.rgv; t_w *= q.rgv; t_u *= q.rgv; t_v *= q.rgv; }   // eval_Ax :246-262, eval_Ax_uv :546-553: / GsqrtV
+    t_w = t_w - P.c.GRAV * drho;
 
     if (!IMPLICIT) {   // explicit evaluation only (first IMEX stage): k_im = -A_v(q)
       P.kim[V_DDENS][n] = t_r; P.kim[V_MOMZ][n] = t_w; P.kim[V_DRHOT][n] = t_t; P.kim[V_MOMX][n] = t_u; P.kim[V_MOMY][n] = t_v;
       __syncwarp();
       if (l8 == 7) { sPrev[0] = q.rho0; sPrev[1] = q.w0; sPrev[2] = q.th0; sPrev[3] = q.pot; sPrev[4] = q.u0; sPrev[5] = q.v0;
-                     sPrev[6] = q.wt; sPrev[7] = q.dpd; sPrev[8] = dpf_own; sPrev[9] = q.a; }
+                     sPrev[6] = q.wt; sPrev[7] = q.dpd; sPrev[8] = dpf_own; sPrev[9] = q.a; if (TERRAIN) sPrev[10] = q.mw; }
       __syncwarp();
       q = qn;
     } else {
@@ -350,7 +389,8 @@ __global__ void __launch_bounds__(VI_THREADS, MINB) vi_column_kernel(const __gri
       double ra0 = 0.0, ra7 = 0.0, rT0 = 0.0, rW[8], rR[4], A2[2][20];
       double cw0 = 0.0, cth0 = 0.0, cth7 = 0.0;   // face / coupling corrections of the DDENS columns of node 0 and node 7
       const double potl = q.pot, wtl = q.wt, dpdl = q.dpd;
-      const double gfac = ifac * P.c.GRAV, dfac = E33 / 1.0 * ifac;
+      // TERRAIN: every row of the block is divided by GsqrtV of its node (construct_matbnd :750-772, :795)
+      const double gfac = ifac * P.c.GRAV, dfac = TERRAIN ? E33 * q.rgv * ifac : E33 / 1.0 * ifac;
 #pragma unroll
       for (int p2 = 0; p2 < 8; ++p2) {
         const double fdz = dfac * sDT[p2 * 8 + l8];
@@ -368,7 +408,8 @@ __global__ void __launch_bounds__(VI_THREADS, MINB) vi_column_kernel(const __gri
       // face couplings (construct_matbnd :774-871)
       const double pot0 = __shfl_sync(FULL, potl, 0, 8), wt0 = __shfl_sync(FULL, wtl, 0, 8), dpd0 = __shfl_sync(FULL, dpdl, 0, 8);
       const double pot7 = __shfl_sync(FULL, potl, 7, 8), wt7 = __shfl_sync(FULL, wtl, 7, 8), dpd7 = __shfl_sync(FULL, dpdl, 7, 8);
-      const double facb = 0.5 * ifac / 1.0 * lw0 * Fs_b, fact = 0.5 * ifac / 1.0 * lw1 * Fs_t;
+      const double facb = TERRAIN ? 0.5 * ifac * q.rgv * lw0 * Fs_b : 0.5 * ifac / 1.0 * lw0 * Fs_b;
+      const double fact = TERRAIN ? 0.5 * ifac * q.rgv * lw1 * Fs_t : 0.5 * ifac / 1.0 * lw1 * Fs_t;
       const double t1b = facb * fmax(alph_b, alph_b), t2b = facb * (-1.0);
       const double t1t = fact * fmax(alph_t, alph_t), t2t = fact * (1.0);
       if (bot_bc) {
@@ -427,9 +468,10 @@ __global__ void __launch_bounds__(VI_THREADS, MINB) vi_column_kernel(const __gri
       }
       // park what the next element needs: the lookahead node and the top node of this element
       park(sQ, qn);
+      if (TERRAIN) park_t(sQ, qn);
       __syncwarp();
       if (l8 == 7) { sPrev[0] = q.rho0; sPrev[1] = q.w0; sPrev[2] = q.th0; sPrev[3] = q.pot; sPrev[4] = q.u0; sPrev[5] = q.v0;
-                     sPrev[6] = q.wt; sPrev[7] = q.dpd; sPrev[8] = dpf_own; sPrev[9] = q.a; }
+                     sPrev[6] = q.wt; sPrev[7] = q.dpd; sPrev[8] = dpf_own; sPrev[9] = q.a; if (TERRAIN) sPrev[10] = q.mw; }
 
       // ---- (MOMX, MOMY): (I + ua0 e0^T + ua7 e7^T) x = [bu | bv | bg], two static pivots
       {
@@ -442,7 +484,8 @@ __global__ void __launch_bounds__(VI_THREADS, MINB) vi_column_kernel(const __gri
         const double mu = __shfl_sync(FULL, bu, 7, 8) * rp7, mv = __shfl_sync(FULL, bv, 7, 8) * rp7, mg = __shfl_sync(FULL, bg, 7, 8) * rp7;
         VI_ROWOP(bu, mu, ua7, is7); VI_ROWOP(bv, mv, ua7, is7); VI_ROWOP(bg, mg, ua7, is7);
       }
-      // ---- DDENS rows: pivot on (row 0, rho_0), then (row 7, rho_7)
+      // ---- DDENS rows: pivot on (row 0, rho_0), then (row 7, rho_7)   (terrain pass 0 skips the three-variable system)
+      if (!pass0) {
       {
         const bool is0 = (l8 == 0), is7 = (l8 == 7);
         const double rp0 = 1.0 / (1.0 + __shfl_sync(FULL, ra0, 0, 8));
@@ -506,9 +549,11 @@ __global__ void __launch_bounds__(VI_THREADS, MINB) vi_column_kernel(const __gri
         x0 -= t8.x * sa.x; x1 -= t8.x * sa.y; x2 -= t8.x * sb.x; x3 -= t8.x * sb.y;
         sts_pair(sSol + (3 * l8) * 4, x0, x1); sts_pair(sSol + (3 * l8) * 4 + 2, x2, x3);
       }
+      }   // !pass0
       sSolUV[l8 * 3 + 0] = bu; sSolUV[l8 * 3 + 1] = bv; sSolUV[l8 * 3 + 2] = bg;
       __syncwarp();
       // ---- keep b and G of this element for the backward sweep
+      if (!pass0)
 #pragma unroll
       for (int v = 0; v < 3; ++v) {
         const double2 sa = lds_pair(sSol + (3 * l8 + v) * 4), sb = lds_pair(sSol + (3 * l8 + v) * 4 + 2);
@@ -521,6 +566,7 @@ __global__ void __launch_bounds__(VI_THREADS, MINB) vi_column_kernel(const __gri
       scr[scr_uv + ((size_t(kz) * 3 + 1) * 8 + l8) * ncol + col] = bv;
       scr[scr_uv + ((size_t(kz) * 3 + 2) * 8 + l8) * ncol + col] = bg;
       q = unpark(sQ);
+      if (TERRAIN) { q.rgv = sQ[13 * VI_THREADS]; q.mw = sQ[14 * VI_THREADS]; }
     }
   }
 
@@ -572,6 +618,7 @@ __global__ void __launch_bounds__(VI_THREADS, MINB) vi_column_kernel(const __gri
       // PROG_VARS = var0 + delta;  tendency = (PROG_VARS - q) / impl_fac  (rhot_hevi.F90:931-940); StoreImplicit: q += impl_fac * k
       const double pr = in.q0[0] + d[0], pw = in.q0[1] + d[1], pth = in.q0[2] + d[2];
       const double pu = in.q0[3] + du, pvv = in.q0[4] + dv;
+      if (pass0) { P.pvu_out[n] = pu; P.pvv_out[n] = pvv; continue; }   // terrain pass 0: MOMX', MOMY' for the mass flux of pass 1
       const double kr = (pr - cr) / ifac, kw = (pw - cw) / ifac, kt = (pth - ct) / ifac, ku = (pu - cu) / ifac, kv = (pvv - cv) / ifac;
       P.kim[V_DDENS][n] = kr; P.kim[V_MOMZ][n] = kw; P.kim[V_DRHOT][n] = kt; P.kim[V_MOMX][n] = ku; P.kim[V_MOMY][n] = kv;
       qr = cr + ifac * kr; qw = cw + ifac * kw; qt = ct + ifac * kt; qu = cu + ifac * ku; qv = cv + ifac * kv;
@@ -583,6 +630,31 @@ __global__ void __launch_bounds__(VI_THREADS, MINB) vi_column_kernel(const __gri
 }
 
 void launch_vi(const VIParams& p, bool moist, cudaStream_t s) {
+  if (p.gsqrt) {   // terrain-following mesh: the eight-lane kernel with the metric terms; implicit launches run pass 0 + pass 1
+    const int ncol = p.Ne2D * 64, groups = VI_THREADS / 8;
+    dim3 grid(ncol / groups), block(VI_THREADS);
+    const size_t shmem = (144 + size_t(groups) * VI_SOL + size_t(VI_NQ_T + VI_PF_T) * VI_THREADS) * sizeof(double);
+#define FEDG_VIT_LAUNCH(M, I, Q)                                                                                    \
+  do {                                                                                                              \
+    static bool attr_set = false;                                                                                   \
+    if (!attr_set) {                                                                                                \
+      cudaFuncSetAttribute(vi_column_kernel<M, I, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(shmem)); \
+      attr_set = true;                                                                                              \
+    }                                                                                                               \
+    vi_column_kernel<M, I, 2, true><<<grid, block, shmem, s>>>(Q);                                                  \
+  } while (0)
+    if (p.impl_fac == 0.0) {
+      VIParams q = p; q.pvu = q.pvv = nullptr; q.pass0 = 0;
+      if (moist) FEDG_VIT_LAUNCH(true, false, q); else FEDG_VIT_LAUNCH(false, false, q);
+    } else {
+      VIParams q0 = p; q0.pvu = q0.pvv = nullptr; q0.pass0 = 1;
+      if (moist) FEDG_VIT_LAUNCH(true, true, q0); else FEDG_VIT_LAUNCH(false, true, q0);
+      VIParams q1 = p; q1.pvu = p.pvu_out; q1.pvv = p.pvv_out; q1.pass0 = 0;
+      if (moist) FEDG_VIT_LAUNCH(true, true, q1); else FEDG_VIT_LAUNCH(false, true, q1);
+    }
+#undef FEDG_VIT_LAUNCH
+    return;
+  }
   // FEDG_VI_KERNEL=2 selects the two-lane block-elimination kernel (vi_solver2.cu); default: this file's eight-lane kernel with
   // partial pivoting over the whole block.  Measured (profiles/r02_*): kernel 2 is 3-6 % faster (2.21 vs 2.40 ms per launch at
   // 32x32x16) but, at config 4's vertical acoustic CFL of ~100, 30 times further from the oracle in the near-zero perturbation
@@ -606,10 +678,10 @@ void launch_vi(const VIParams& p, bool moist, cudaStream_t s) {
   do {                                                                                                       \
     static bool attr_set = false;                                                                            \
     if (!attr_set) {                                                                                         \
-      cudaFuncSetAttribute(vi_column_kernel<M, I, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(shmem)); \
+      cudaFuncSetAttribute(vi_column_kernel<M, I, B, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(shmem)); \
       attr_set = true;                                                                                       \
     }                                                                                                        \
-    vi_column_kernel<M, I, B><<<grid, block, shmem, s>>>(p);                                                 \
+    vi_column_kernel<M, I, B, false><<<grid, block, shmem, s>>>(p);                                          \
   } while (0)
   const bool implicit = p.impl_fac != 0.0;
   if (!implicit) { if (moist) FEDG_VI_LAUNCH(true, false, 4); else FEDG_VI_LAUNCH(false, false, 4); }

@@ -515,37 +515,7 @@ def test_sponge_layer_row_f3(p, eqs, tinteg, dt, kw):
 
 
 # ------------------------------------------------------------------------------ terrain-following metric (row f3, metric part)
-def _terrain_case(p, dims, **kw):
-    """Bell mountain h(x) = h0 / (1 + ((x - xc)/a)^2 + ((y - yc)/b)^2) with the linear terrain-following map
-    z = zeta + h (1 - zeta / zTop): GsqrtV = 1 - h / zTop, G13 = -(1 - zeta/zTop) h_x / GsqrtV, G23 likewise (the
-    quantities MeshTopography%SetVCoordinate hands to Set_geometric_with_vcoord, mesh/scale_mesh_topography.F90:101-264,
-    evaluated analytically here: the test is about the metric terms of the tendency, not about the mesh generator)."""
-    case = DensityCurrentCase(p=p, NeX=dims[0], NeY=dims[1], NeZ=dims[2], perturb=2.0, intrp_order=min(11, p + 4), **kw)
-    m = case.mesh
-    x, y, zeta = m.pos_en[0], m.pos_en[1], m.pos_en[2]
-    zT, h0, a, b, xc, yc = m.zmax, 600.0, 5.0e3, 4.0e3, 12.0e3, 3.0e3
-    den = 1.0 + ((x - xc) / a) ** 2 + ((y - yc) / b) ** 2
-    h = h0 / den
-    hx = -h0 / den ** 2 * 2.0 * (x - xc) / a ** 2
-    hy = -h0 / den ** 2 * 2.0 * (y - yc) / b ** 2
-    gv = 1.0 - h / zT
-    Ne = m.Ne
-    m.Gsqrt[:Ne] = gv
-    m.GI3[0, :Ne] = -(1.0 - zeta / zT) * hx / gv
-    m.GI3[1, :Ne] = -(1.0 - zeta / zT) * hy / gv
-    for arr in (m.Gsqrt, m.GI3[0], m.GI3[1]):
-        m.exchange_halo_numpy(arr.reshape(-1))
-    return case      # zlev (used by the potential-energy monitor only) stays the computational height on both sides
-
-
-def _terrain_oracle(case):
-    o = case.make_oracle()
-    m = case.mesh
-    o.arr("Gsqrt")[:] = m.Gsqrt.reshape(-1)
-    o.arr("G13")[:] = m.GI3[0].reshape(-1)
-    o.arr("G23")[:] = m.GI3[1].reshape(-1)
-    o.prepare()
-    return o
+from cases import terrain_case as _terrain_case, terrain_oracle as _terrain_oracle  # noqa: E402
 
 
 @pytest.mark.parametrize("p,dims", [(7, (4, 2, 3)), (3, (5, 3, 4))])
@@ -574,6 +544,67 @@ def test_terrain_following_steps(p, dims, dt):
     n = case.mesh.Ne * case.elem.Np
     for nm in PROG:
         assert rel_l2(g[nm][:n], o.arr(nm)[:n]) <= TOL, nm
+    mo, mg = o.monitor(), d.monitor()
+    assert abs(mo[1] - mg[1]) <= 1e-12 * abs(mo[1])
+
+
+# ------------------------------------------------------------------------------ terrain-following HEVI (row f3 / a9-a12 with GsqrtV, G13, G23)
+def _terrain_hevi_case(**kw):
+    args = dict(eqs="NONHYDRO3D_HEVI", tinteg="IMEX_ARK324", dt=0.2)
+    args.update(kw)
+    return _terrain_case(7, (4, 2, 3), **args)
+
+
+def test_terrain_hevi_explicit_tendency():
+    """Horizontally explicit tendency over the bell mountain (rhot_hevi.F90:289-482 with the metric terms; numflux :232-416)."""
+    case = _terrain_hevi_case()
+    o = _terrain_oracle(case)
+    d = case.make_driver(o)
+    for w in ("exchange", "pressure", "bc", "tend_ex"):
+        o.piece(w)
+    t = d.cal_tend_ex()
+    n = case.mesh.Ne * case.elem.Np
+    N = case.mesh.NeA * case.elem.Np
+    te = o.arr("tend_ex")[:5 * N].reshape(5, -1)[:, :n]
+    for nm, iv in TEND:
+        assert rel_l2(t[nm], te[iv]) <= 5e-11, nm
+
+
+@pytest.mark.parametrize("impl_fac", [0.0, 0.05, 2.0])
+def test_terrain_hevi_cal_vi(impl_fac):
+    """cal_vi over the bell mountain: GsqrtV scales the rows, the mass flux carries GsqrtV (G13 MOMX' + G23 MOMY') with the horizontal
+    momenta after their own implicit solve, the dissipation coefficient carries Gnn (rhot_hevi.F90:772-965, hevi_common_2.F90:111-1328)."""
+    case = _terrain_hevi_case()
+    o = _terrain_oracle(case)
+    d = case.make_driver(o)
+    n = case.mesh.Ne * case.elem.Np
+    rng = np.random.default_rng(12)
+    var0 = np.stack([o.arr(k).copy() for k in ORD])
+    if impl_fac != 0.0:
+        var0[:, :n] += 1e-3 * rng.standard_normal((5, n)) * np.abs(var0[:, :n]).max(axis=1, keepdims=True)
+    ref = o.cal_vi(impl_fac, case.dt, var0)[:, :n]
+    got = d.cal_vi(impl_fac, {k: var0[i] for i, k in enumerate(ORD)})
+    for i, k in enumerate(ORD):
+        if impl_fac == 0.0:
+            assert rel_l2(got[OUT[k]], ref[i]) <= 1e-10, (k, impl_fac)
+        else:
+            qcur = o.arr(k)[:n]
+            qs_ref, qs_got = qcur + impl_fac * ref[i], qcur + impl_fac * got[OUT[k]]
+            assert rel_l2(qs_got, qs_ref) <= 1e-11, (k, impl_fac)
+            assert np.abs(got[OUT[k]] - ref[i]).max() <= 1e-10 * max(np.abs(var0[i]).max(), np.abs(ref[i]).max()) / impl_fac, (k, impl_fac)
+
+
+@pytest.mark.parametrize("tinteg,dt", [("IMEX_ARK324", 0.2), ("IMEX_ARK232", 0.1)])
+def test_terrain_hevi_steps(tinteg, dt):
+    """Ten HEVI steps over the bell mountain, modal filter on (Gsqrt-weighted), against the oracle; total energy to round-off."""
+    case = _terrain_hevi_case(tinteg=tinteg, dt=dt)
+    o = _terrain_oracle(case)
+    d = case.make_driver(o)
+    o.update(10); d.Update(10)
+    g = d.get_prog()
+    n = case.mesh.Ne * case.elem.Np
+    for nm in PROG:
+        assert rel_l2(g[nm][:n], o.arr(nm)[:n]) <= TOL, (tinteg, nm)
     mo, mg = o.monitor(), d.monitor()
     assert abs(mo[1] - mg[1]) <= 1e-12 * abs(mo[1])
 
