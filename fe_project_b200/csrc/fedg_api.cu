@@ -1957,8 +1957,9 @@ int fedg_numdiff_apply(fedg_ctx* c) {
 
 }  // extern "C"
 
-// ---- sponge layer (row f3, flat part) ------------------------------------------------------------------------
+// ---- sponge layer (row f3) -----------------------------------------------------------------------------------
 namespace {
+struct DevBufGuardZ { DevBuf b; ~DevBufGuardZ() { b.release(); } };
 // calc_wdampcoef (spongelayer.F90:189-218) for every node from zlev
 __global__ void sponge_coef_kernel(const double* __restrict__ zlev, double* __restrict__ coef, double r_tau, double height, int Np, int Nfp,
                                    int np, int Ne, int Ne2D, int NeZ) {
@@ -1971,27 +1972,44 @@ __global__ void sponge_coef_kernel(const double* __restrict__ zlev, double* __re
 }
 }  // namespace
 
-extern "C" int fedg_sponge_init(fedg_ctx* c, double sl_wdamp_tau, double sl_wdamp_height, int sl_wdamp_layer, int sl_horiveldamp_flag) {
-  if (!c) return fail(FEDG_ERR_ARG, "null argument");
-  if (!c->dyn_ready) return fail(FEDG_ERR_STATE, "fedg_dyn_init must be called first (the default SL_WDAMP_TAU is 10 TIME_DT)");
-  // the reference damps in the computational height pos_en(:,:,3) (spongelayer.F90:168-172); the descriptor carries zlev, which
-  // equals it on meshes without topography (regional flat, cubed sphere) only
-  if (c->terrain) return fail(FEDG_ERR_UNSUPPORTED, "the sponge layer needs a mesh without topography (zlev = computational height)");
+namespace {
+// zsrc: device array (Np, Ne) of the computational height the damping profile is evaluated in
+int sponge_init_from(fedg_ctx* c, const double* zsrc, double sl_wdamp_tau, double sl_wdamp_height, int sl_wdamp_layer, int sl_horiveldamp_flag) {
   if (sl_wdamp_layer > c->NeZ) return fail(FEDG_ERR_ARG, "SL_wdamp_layer should be less than total of vertical elements (NeGZ)");
   double tau = sl_wdamp_tau, height = sl_wdamp_height;
   if (sl_wdamp_layer > 0) {   // height of the first node of that layer (spongelayer.F90:104-106)
-    CUDA_TRY(cudaMemcpy(&height, c->zlev.p + size_t(sl_wdamp_layer - 1) * c->Ne2D * c->Np, sizeof(double), cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(&height, zsrc + size_t(sl_wdamp_layer - 1) * c->Ne2D * c->Np, sizeof(double), cudaMemcpyDeviceToHost));
   }
   if (tau < 0.0) tau = c->dt * 10.0;
   else if (tau < c->dt) return fail(FEDG_ERR_ARG, "SL_wdamp_tau should be larger than TIME_DT (ATMOS_DYN)");
   if (c->sponge.n < c->nint) CUDA_TRY(c->sponge.alloc(c->nint));
-  sponge_coef_kernel<<<unsigned((c->nint + 255) / 256), 256, 0, c->stream>>>(c->zlev.p, c->sponge.p, 1.0 / tau, height, c->Np, c->Nfp, c->np, c->Ne,
+  sponge_coef_kernel<<<unsigned((c->nint + 255) / 256), 256, 0, c->stream>>>(zsrc, c->sponge.p, 1.0 / tau, height, c->Np, c->Nfp, c->np, c->Ne,
                                                                           c->Ne2D, c->NeZ);
   CUDA_TRY(cudaStreamSynchronize(c->stream));
   CUDA_TRY(cudaGetLastError());
   c->sponge_h = sl_horiveldamp_flag ? 1.0 : 0.0;
   c->has_sponge = true;
   return FEDG_OK;
+}
+}  // namespace
+
+extern "C" int fedg_sponge_init(fedg_ctx* c, double sl_wdamp_tau, double sl_wdamp_height, int sl_wdamp_layer, int sl_horiveldamp_flag) {
+  if (!c) return fail(FEDG_ERR_ARG, "null argument");
+  if (!c->dyn_ready) return fail(FEDG_ERR_STATE, "fedg_dyn_init must be called first (the default SL_WDAMP_TAU is 10 TIME_DT)");
+  // the reference damps in the computational height pos_en(:,:,3) (spongelayer.F90:168-172); the descriptor carries zlev, which
+  // equals it on meshes without topography (regional flat, cubed sphere) only: with topography use fedg_sponge_init_pos
+  if (c->terrain) return fail(FEDG_ERR_UNSUPPORTED, "mesh with topography: hand the computational height over with fedg_sponge_init_pos");
+  return sponge_init_from(c, c->zlev.p, sl_wdamp_tau, sl_wdamp_height, sl_wdamp_layer, sl_horiveldamp_flag);
+}
+
+extern "C" int fedg_sponge_init_pos(fedg_ctx* c, double sl_wdamp_tau, double sl_wdamp_height, int sl_wdamp_layer, int sl_horiveldamp_flag,
+                                    const double* pos_en3) {
+  if (!c || !pos_en3) return fail(FEDG_ERR_ARG, "null argument");
+  if (!c->dyn_ready) return fail(FEDG_ERR_STATE, "fedg_dyn_init must be called first (the default SL_WDAMP_TAU is 10 TIME_DT)");
+  DevBufGuardZ z;
+  CUDA_TRY(z.b.alloc(c->nint));
+  CUDA_TRY(cudaMemcpy(z.b.p, pos_en3, c->nint * sizeof(double), cudaMemcpyHostToDevice));
+  return sponge_init_from(c, z.b.p, sl_wdamp_tau, sl_wdamp_height, sl_wdamp_layer, sl_horiveldamp_flag);
 }
 
 // ---- tracer advection with a prescribed mass flux (row f4; NOT yet validated on hardware, see tracer.cu) ------------------

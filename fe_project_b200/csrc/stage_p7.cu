@@ -87,8 +87,9 @@ __global__ void __launch_bounds__(256, 3) stage_p7_kernel(const __grid_constant_
   // or a halo face: checked at fedg_create); the terrain instantiation keeps the gathers (it needs three metric fields more)
   const bool zext = !TERRAIN && P.zface_contig;
 
-  // ---- phase 0: TMA bulk loads issued by the lanes of warp 0: nine input fields of the element, 2 x 9 exterior z-face
-  //      rows of 512 B, the operator tables
+  // ---- phase 0: TMA bulk loads issued by one thread: nine input fields of the element, 2 x 9 exterior z-face rows of 512 B, the
+  //      operator tables.  (Issuing the 28 copies from 28 lanes of warp 0 at once was measured SLOWER: 0.520 vs 0.471 ms per launch
+  //      in the same process, profiles/r02_ab_stage_tma_lanes.txt -- the lanes diverge over the field switch and the address set-up.)
   if (tid == 0) mbar_init(sBar, 1);
   __syncthreads();   // barrier initialised before anybody polls it.  Placed here, ahead of every global load: the warps run
                      // independently from now to the end of the face phase (behind the gathers it made every warp wait for

@@ -655,15 +655,14 @@ void launch_vi(const VIParams& p, bool moist, cudaStream_t s) {
 #undef FEDG_VIT_LAUNCH
     return;
   }
-  // FEDG_VI_KERNEL=2 selects the two-lane block-elimination kernel (vi_solver2.cu); default: this file's eight-lane kernel with
-  // partial pivoting over the whole block.  Measured (profiles/r02_*): kernel 2 is 3-6 % faster (2.21 vs 2.40 ms per launch at
-  // 32x32x16) but, at config 4's vertical acoustic CFL of ~100, 30 times further from the oracle in the near-zero perturbation
-  // fields (3.6e-9 vs 1e-10 of their own norm; both 1e-16 of the full fields), so the parity-first default stays.
-  // The explicit evaluation (impl_fac = 0, first stage of the ARK schemes) has no linear solve: the two-lane kernel does it in 0.55 ms
-  // against 0.92 ms here, so it takes those launches by default.  FEDG_VI_KERNEL=1 / 2 forces one kernel for every launch.
-  int which = 0;
-  { const char* e = getenv("FEDG_VI_KERNEL"); if (e && (e[0] == '1' || e[0] == '2')) which = e[0] - '0'; }   // read at every launch: in-process A/B runs
-  if (which == 0) which = (p.impl_fac == 0.0) ? 2 : 1;
+  // Two kernels for the flat geometry: this file's eight-lane kernel (partial pivoting over the whole reduced block) and the two-lane
+  // block elimination of vi_solver2.cu.  Measured (profiles/r02_ab_vi_kernels.txt): the two-lane kernel is faster for the implicit
+  // launches (2.76 vs 2.9 ms at 32x32x16) and for the explicit evaluation of the first ARK stage (0.55 vs 0.92 ms); both pass every
+  // parity test, and at config 4's vertical acoustic CFL both sit at the same distance from the oracle (tools/cfg4_diag.py: 3.56e-10 /
+  // 1.20e-8 of DDENS / MOMZ's own norm with either kernel, 1.4x / 1.8x the oracle's own response to a one-ulp perturbation), so the
+  // faster one is the default.  FEDG_VI_KERNEL=1 / 2 forces one kernel for every launch (read at every launch: in-process A/B runs).
+  int which = 2;
+  { const char* e = getenv("FEDG_VI_KERNEL"); if (e && (e[0] == '1' || e[0] == '2')) which = e[0] - '0'; }
   if (which == 2 && p.htab && launch_vi2(p, *p.htab, moist, s)) return;
   const int ncol = p.Ne2D * 64;
   const int groups = VI_THREADS / 8;

@@ -183,6 +183,12 @@ class AtmDynDGMDriver_nonhydro3d:
 
     def sponge_init(self, SL_WDAMP_TAU=-1.0, SL_WDAMP_HEIGHT=-1.0, SL_WDAMP_LAYER=-1, SL_HORIVELDAMP_FLAG=False):
         """PARAM_ATMOS_DYN_SPONGELAYER (scale_atm_dyn_dgm_spongelayer.F90:55-118)."""
+        m = self.mesh
+        if np.any(m.Gsqrt[:m.Ne] != 1.0) and not getattr(m, "panelID", 0):      # topography: the profile lives in the computational height
+            z = _f64(m.pos_en[2])
+            _lib.check(self.L.fedg_sponge_init_pos(self.h, float(SL_WDAMP_TAU), float(SL_WDAMP_HEIGHT), int(SL_WDAMP_LAYER),
+                                                   int(SL_HORIVELDAMP_FLAG), _ptr(z)))
+            return
         _lib.check(self.L.fedg_sponge_init(self.h, float(SL_WDAMP_TAU), float(SL_WDAMP_HEIGHT), int(SL_WDAMP_LAYER), int(SL_HORIVELDAMP_FLAG)))
 
     def numdiff_apply(self):

@@ -259,6 +259,10 @@ int fedg_numdiff_apply(fedg_ctx* ctx);
  * the first node of that element layer), SL_HORIVELDAMP_FLAG.  The Rayleigh damping enters the explicit tendency of every
  * stage inside the stage kernel (driver_nonhydro3d.F90:830-841). */
 int fedg_sponge_init(fedg_ctx* ctx, double sl_wdamp_tau, double sl_wdamp_height, int sl_wdamp_layer, int sl_horiveldamp_flag);
+/* The same on a mesh with topography: the damping profile is a function of the COMPUTATIONAL height lmesh%pos_en(:,:,3)
+ * (spongelayer.F90:111, 168-173), which fedg_mesh_desc does not carry (its zlev is the real height); pos_en3: host array (Np,Ne). */
+int fedg_sponge_init_pos(fedg_ctx* ctx, double sl_wdamp_tau, double sl_wdamp_height, int sl_wdamp_layer, int sl_horiveldamp_flag,
+                         const double* pos_en3);
 
 /* ---- several local meshes on one device (LOCAL_MESH_NUM > 1; cubed-sphere panels) ------------------------------
  * fedg_link_halo: the halo of tile face `face` (1..6) of `ctx` is filled from the interior of `src`, another local mesh on

@@ -609,6 +609,25 @@ def test_terrain_hevi_steps(tinteg, dt):
     assert abs(mo[1] - mg[1]) <= 1e-12 * abs(mo[1])
 
 
+@pytest.mark.parametrize("eqs,tinteg,dt,kw", [("NONHYDRO3D_HEVE", "ERK_SSP_4s3o", 0.05, dict(SL_WDAMP_TAU=1.0, SL_WDAMP_HEIGHT=4.0e3, SL_HORIVELDAMP_FLAG=True)),
+                                              ("NONHYDRO3D_HEVI", "IMEX_ARK324", 0.2, dict(SL_WDAMP_LAYER=3))])
+def test_sponge_layer_over_topography(eqs, tinteg, dt, kw):
+    """AtmDynSpongeLayer on the terrain-following mesh: the damping profile is a function of the computational height pos_en(:,:,3)
+    (spongelayer.F90:168-173), handed over with fedg_sponge_init_pos."""
+    case = _terrain_case(7, (4, 2, 3), eqs=eqs, tinteg=tinteg, dt=dt)
+    o = _terrain_oracle(case)
+    d = case.make_driver(o)
+    o.set_sponge(True, **kw)
+    d.sponge_init(**kw)
+    o.update(6); d.Update(6)
+    g = d.get_prog()
+    n = case.mesh.Ne * case.elem.Np
+    for nm in PROG:
+        assert rel_l2(g[nm][:n], o.arr(nm)[:n]) <= TOL, nm
+    d2 = case.make_driver(o); d2.Update(6)
+    assert rel_l2(d2.get_prog()["MOMZ"][:n], g["MOMZ"][:n]) > 1e-6      # the damping matters
+
+
 # ------------------------------------------------------------------------------ GLOBALNONHYDRO3D_HEVE (shallow atmosphere)
 @pytest.mark.parametrize("panelID", [2, 5, 6])
 def test_global_heve_panel_tendency(panelID):
