@@ -535,7 +535,11 @@ def main():
             ccase = case if world == 1 and args.workload == "density_current" else workload_case(args, hevi=hevi)
             r = oracle_timed(ccase, warmup=1, target_s=12.0)
             cpu = dict(value=r["value"], unit=UNIT, cores=r["cores"], kind="port", sample=r["sample"])
-        vi_flops_ref, vi_flops_exec = 15.1e3 * Ne * 64, 11.0e3 * Ne * 64
+        # flops a vertical-implicit launch EXECUTES per column-element: two-lane block elimination (default) 16.7 k (ncu thread-instruction
+        # counts of the implicit launch, gpurun_out/r02_vi2_raw.csv: 2 x DFMA + DADD + DMUL = 1.749e10 per launch at 32x32x16; it rebuilds
+        # the rows from constant tables instead of loading a stored block), eight-lane kernel (FEDG_VI_KERNEL=1) 11.0 k
+        vi_k2 = os.environ.get("FEDG_VI_KERNEL", "2") != "1"
+        vi_flops_ref, vi_flops_exec = 15.1e3 * Ne * 64, (16.7e3 if vi_k2 else 11.0e3) * Ne * 64
         line = dict(
             metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=K, warmup=W, ms_per_step=ms_total / K,
             higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64", data="synthetic",
@@ -552,12 +556,13 @@ def main():
                            kernel="stage_p7_kernel<flat,dry,HEVE> (DMMA contractions, TMA-staged inputs and z-face neighbours)", ms_per_launch=ms_stage,
                            algorithmic_bytes_per_launch=alg_bytes, peak_source=peak_src) if not hevi else
                       # vertical-implicit column solve: FP64 bound.  achieved / frac use the flops the kernel EXECUTES per column-element
-                      # (DDENS eliminated first, 16x16 partial-pivot Gauss-Jordan with four right-hand sides: 11.0 kflop); the reference
+                      # (see vi_flops_exec above); the reference
                       # algorithm's count (24x24 LU 9.2 k + substitutions 4.6 k + coupling 0.6 k + (u,v) 0.7 k = 15.1 kflop) is
                       # reported next to it.  ms_per_launch averages the implicit stages and the explicit-evaluation stage of the scheme
                       dict(bound="fp64", achieved=vi_flops_exec / (ms_stage * 1e-3) / 1e12, peak=34.07, unit="TFLOP/s",
                            frac=vi_flops_exec / (ms_stage * 1e-3) / 1e12 / 34.07, traffic=None,
-                           kernel="vi_column_kernel (block-Thomas over the column, DDENS eliminated, partial-pivot Gauss-Jordan per element)", ms_per_launch=ms_stage,
+                           kernel=("vi_column2_kernel (block-Thomas over the column; per element: density in closed form, theta block and Schur complement in w by partial-pivot Gauss-Jordan, two lanes per column)"
+                                   if vi_k2 else "vi_column_kernel (block-Thomas over the column, DDENS eliminated, partial-pivot Gauss-Jordan per element, eight lanes per column)"), ms_per_launch=ms_stage,
                            executed_flops_per_launch=vi_flops_exec, reference_algorithm_flops_per_launch=vi_flops_ref,
                            frac_on_reference_algorithm_flops=vi_flops_ref / (ms_stage * 1e-3) / 1e12 / 34.07,
                            peak_source="measured DFMA peak, profiles/r01_fp64_peak.txt")),
