@@ -98,7 +98,9 @@ int fedg_create(const fedg_mesh_desc* desc, fedg_ctx** out);
 void fedg_destroy(fedg_ctx* ctx);
 
 /* AtmDynDGMDriver_nonhydro3d%Init: fluid_dyn_solver/scale_atm_dyn_dgm_driver_nonhydro3d.F90:355-594
- * eqs_type: "NONHYDRO3D_HEVE" | "NONHYDRO3D_HEVI" (p = 7, flat mesh) | "GLOBALNONHYDRO3D_HEVE" | "GLOBALNONHYDRO3D_HEVI"
+ * eqs_type: "NONHYDRO3D_HEVE" | "NONHYDRO3D_HEVI" (p = 7; flat or terrain-following mesh: with Gsqrt / GI3 of the descriptor different
+ * from 1 / 0 the vertical-implicit solver carries GsqrtV, G13, G23, scale_atm_dyn_dgm_nonhydro3d_rhot_hevi_common_2.F90:111-1328)
+ * | "GLOBALNONHYDRO3D_HEVE" | "GLOBALNONHYDRO3D_HEVI"
  * (p = 7, cubed-sphere panel tile: fluid_dyn_solver/scale_atm_dyn_dgm_globalnonhydro3d_rhot_heve.F90:338-600,
  * scale_atm_dyn_dgm_globalnonhydro3d_rhot_hevi.F90:337-583, 873-1066, fluxes scale_atm_dyn_dgm_nonhydro3d_rhot_heve_numflux.F90:1543-1772,
  * scale_atm_dyn_dgm_nonhydro3d_rhot_hevi_numflux.F90:606-834); tinteg_type: a timeint_rk scheme name
