@@ -19,7 +19,7 @@ ABI_SYMBOLS = (
     "fedg_exchange_halo", "fedg_monitor", "fedg_rk_info", "fedg_rk_coef", "fedg_elem_op",
     "fedg_last_timing", "fedg_comm_unique_id", "fedg_comm_init",
     "fedg_set_phy_tend", "fedg_numdiff_init", "fedg_numdiff_apply", "fedg_sponge_init", "fedg_sponge_init_pos", "fedg_link_halo", "fedg_link_halo_recv", "fedg_link_halo_send", "fedg_group_exchange_halo", "fedg_group_update", "fedg_sparsemat_matmul", "fedg_sparsemat_matmul1", "fedg_sparsemat_matmul1_2", "fedg_sparsemat_matmul2", "fedg_advect3d_init", "fedg_advect3d_set", "fedg_advect3d_get",
-    "fedg_advect3d_cal_tend", "fedg_advect3d_update", "fedg_trcadv_init", "fedg_trcadv_update",
+    "fedg_advect3d_cal_tend", "fedg_advect3d_update", "fedg_trcadv_init", "fedg_trcadv_update", "fedg_trcadv_couple", "fedg_trcadv_update_coupled",
     "fedg_dyn_update_host_async", "fedg_dyn_update_host_wait", "fedg_rk_store_var0", "fedg_rk_store_implicit", "fedg_rk_advance",
     "fedg_cal_tend_ex_dev", "fedg_cal_vi_dev", "fedg_halo_start", "fedg_halo_wait", "fedg_modalfilter_apply", "fedg_rk_get_tend",
     "fedg_elem_div", "fedg_group_exchange_aux", "fedg_update_phyd_hgrad",
@@ -110,6 +110,8 @@ def load() -> C.CDLL:
     L.fedg_advect3d_update.argtypes = [vp, ci]
     L.fedg_trcadv_init.argtypes = [vp, C.c_char_p, cd, ci, vp, vp, ci]
     L.fedg_trcadv_update.argtypes = [vp, vp, vp, ci]
+    L.fedg_trcadv_couple.argtypes = [vp, ci]
+    L.fedg_trcadv_update_coupled.argtypes = [vp, vp, vp]
     L.fedg_dyn_update_host_async.argtypes = [vp] * 11 + [ci, ci]
     L.fedg_dyn_update_host_wait.argtypes = [vp, ci]
     for name in ("fedg_rk_store_var0", "fedg_halo_start", "fedg_halo_wait", "fedg_modalfilter_apply"):

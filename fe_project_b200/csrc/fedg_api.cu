@@ -77,9 +77,17 @@ struct TracerState {
   bool disable_limiter = false, do_filter = false;
   DevBuf q[2], fct, var0, vartmp, alphM, alphP, rhoq, filt;
   double w1d[MAXNP] = {0};
+  // coupling with the dynamics (fedg_trcadv_couple): stage-averaged mass flux and alphDens, density at the start of the step / after the RK loop
+  bool couple = false, have_flux = false;
+  int stage = 0;
+  DevBuf mflx[3], alphM_t, alphP_t, dens0, dens1;
   void release() {
     for (DevBuf* b : {&q[0], &q[1], &fct, &var0, &vartmp, &alphM, &alphP, &rhoq, &filt}) b->release();
     ready = false;
+  }
+  void release_coupling() {
+    for (DevBuf* b : {&mflx[0], &mflx[1], &mflx[2], &alphM_t, &alphP_t, &dens0, &dens1}) b->release();
+    couple = have_flux = false;
   }
 };
 
@@ -158,7 +166,7 @@ struct fedg_ctx {
     }
     if (hp.h2d) cudaStreamDestroy(hp.h2d);
     if (hp.d2h) cudaStreamDestroy(hp.d2h);
-    trc.release();
+    trc.release(); trc.release_coupling();
     for (auto& l : link) { if (l.d_src) cudaFree(l.d_src); if (l.d_rot) cudaFree(l.d_rot); if (l.recvbuf) cudaFree(l.recvbuf); }
     for (auto& m : outmsg) { if (m.d_idx) cudaFree(m.d_idx); if (m.sendbuf) cudaFree(m.sendbuf); }
     if (d_vmapP) cudaFree(d_vmapP);
@@ -789,7 +797,11 @@ void fill_vi_params(fedg_ctx* c, VIParams& V, int in, int out, int i0, int stage
 // explicit tendency -> Advance (general IMEX form, scale_timeint_rk.F90:2201-2355, accumulated from var0 in the
 // reference's term order); then the modal filter.
 // stage pieces (so that several local meshes on one device can be advanced stage by stage, fedg_group_update)
-void hevi_begin_step(fedg_ctx* c) { c->hs.i0 = c->cur; c->hs.in = c->cur; }
+void hevi_begin_step(fedg_ctx* c) {
+  c->hs.i0 = c->cur; c->hs.in = c->cur;
+  if (c->trc.couple)      // DDENS0_TRC = tint%var0 of DDENS (driver_nonhydro3d.F90:926-937): the last stage may overwrite this buffer
+    cudaMemcpyAsync(c->trc.dens0.p, c->prog[c->cur][V_DDENS].p, c->nint * sizeof(double), cudaMemcpyDeviceToDevice, c->stream);
+}
 int hevi_stage_vi(fedg_ctx* c, int s, cudaEvent_t e0, cudaEvent_t e1) {
   const int i0 = c->hs.i0, bA = (i0 + 1) % 3, bB = (i0 + 2) % 3, in = c->hs.in;
   const int mid = (in == i0) ? bA : in;            // the column solve may update in place except on var0
@@ -810,6 +822,7 @@ int hevi_stage_ex(fedg_ctx* c, int s) {
   StageParams P{};
   fill_stage_params(c, P, c->hs.mid, c->hs.mid, c->hs.i0);
   for (int v = 0; v < NVAR; ++v) P.tend_out[v] = c->kex[size_t(s) * NVAR + v].p;
+  c->trc.stage = s;
   return exchange_and_stage(c, P, c->hs.mid, true);
 }
 void hevi_stage_combine(fedg_ctx* c, int s, bool with_filter = true) {
@@ -826,13 +839,26 @@ void hevi_stage_combine(fedg_ctx* c, int s, bool with_filter = true) {
     L.coef[L.nterm] = ce; L.coef[L.nterm + 1] = ci;
     L.nterm += 2;
   }
-  // the last stage's combination carries the modal filter of the step (driver_nonhydro3d.F90:940-951)
-  if (s == ns - 1 && c->modalfilter && with_filter) launch_lincomb_filter(L, c->d_tab, c->gsqrt.p, c->terrain || c->global, c->Ne, c->np, c->stream);
+  // the last stage's combination carries the modal filter of the step (driver_nonhydro3d.F90:940-951); with the tracer coupling the
+  // unfiltered density is needed first (DDENS_TRC), so the filter runs on its own in hevi_end_step
+  if (s == ns - 1 && c->modalfilter && with_filter && !c->trc.couple) launch_lincomb_filter(L, c->d_tab, c->gsqrt.p, c->terrain || c->global, c->Ne, c->np, c->stream);
   else launch_lincomb(L, c->stream);
   c->dp_valid[nxt] = false;
   c->hs.in = nxt;
 }
-void hevi_end_step(fedg_ctx* c) { c->cur = c->hs.in; c->xbuf = c->cur; }
+void hevi_end_step(fedg_ctx* c) {
+  c->cur = c->hs.in; c->xbuf = c->cur;
+  if (c->trc.couple) {    // DDENS_TRC = DDENS after the RK loop, before the modal filter (driver_nonhydro3d.F90:926-951)
+    cudaMemcpyAsync(c->trc.dens1.p, c->prog[c->cur][V_DDENS].p, c->nint * sizeof(double), cudaMemcpyDeviceToDevice, c->stream);
+    if (c->modalfilter) {
+      double* q[NVAR];
+      for (int v = 0; v < NVAR; ++v) q[v] = c->prog[c->cur][v].p;
+      launch_modal_filter5(q, c->gsqrt.p, c->terrain || c->global, c->Ne, c->np, c->stream);
+      c->dp_valid[c->cur] = false;
+    }
+    c->trc.have_flux = true;
+  }
+}
 
 // explicit (HEVE) stage pieces: buffer choice + pressure of the stage input, then exchange + fused stage kernel
 void heve_stage_prepare(fedg_ctx* c, int s) {
@@ -849,7 +875,8 @@ int heve_stage(fedg_ctx* c, int s, cudaEvent_t e0, cudaEvent_t e1) {
   StageParams P{};
   fill_stage_params(c, P, in, out, c->hs.i0);
   P.rk = c->stages[s];
-  if (s == ns - 1) { P.do_filter = c->modalfilter; P.write_pres = 1; }
+  if (s == ns - 1) { P.do_filter = c->modalfilter && !c->trc.couple; P.write_pres = 1; }
+  c->trc.stage = s;
   int rc = exchange_and_stage(c, P, in, false, e0, e1);
   if (rc) return rc;
   c->dp_valid[out] = true;
@@ -880,6 +907,15 @@ int run_steps_hevi(fedg_ctx* c, int nsteps, size_t& iev, long& launches) {
 // has arrived (HIDE_MPI_COMM_FLAG path of the reference, driver_nonhydro3d.F90:859-895).
 int exchange_and_stage(fedg_ctx* c, StageParams& P, int buf, bool hevi, cudaEvent_t e0, cudaEvent_t e1) {
   fill_halo(c, buf, true);    // faces whose neighbour is on this rank + physical boundaries
+  if (c->trc.couple) {        // atm_dyn_dgm_trcadvect3d_save_massflux on the stage state (driver_nonhydro3d.F90:900-917)
+    const int st = c->trc.stage;
+    const double w_h = c->rk.b_ex[st], w_v = c->rk.imex ? c->rk.b_im[st] : c->rk.b_ex[st];
+    const double* q[NVAR];
+    for (int v = 0; v < NVAR; ++v) q[v] = c->prog[buf][v].p;
+    double* mf[3] = {c->trc.mflx[0].p, c->trc.mflx[1].p, c->trc.mflx[2].p};
+    CUDA_TRY(launch_trc_save_massflux(q, c->dens_hyd.p, c->pres_hyd.p, c->dp[buf].p, c->d_vmapP, mf, c->trc.alphM_t.p, c->trc.alphP_t.p, w_h, w_v,
+                                      c->c.gamm, hevi, st == 0, c->Np, c->Nfp, c->NfpTot, c->np, c->Ne, c->stream));
+  }
   if (e0) cudaEventRecord(e0, c->stream);   // the timed region brackets the stage kernel(s) (+ the exchange when there is one)
   struct Rec { cudaEvent_t e; cudaStream_t s; ~Rec() { if (e) cudaEventRecord(e, s); } } rec{e1, c->stream};
   if (!c->comm.active || c->comm.nremote == 0) {
@@ -2053,31 +2089,24 @@ extern "C" int fedg_trcadv_init(fedg_ctx* c, const char* tinteg_type, double dt,
   return FEDG_OK;
 }
 
-extern "C" int fedg_trcadv_update(fedg_ctx* c, double* QTRC, const double* RHOQ_tp, int nsteps) {
-  if (!c || !QTRC || nsteps < 0) return fail(FEDG_ERR_ARG, "bad argument");
+namespace {
+void trc_common_params(fedg_ctx* c, TracerParams& P, bool with_rhoq) {
   TracerState& t = c->trc;
-  if (!t.ready) return fail(FEDG_ERR_STATE, "fedg_trcadv_init must be called first");
-  ensure_tables(c);
-  const int cur = c->cur;
-  ensure_dp(c, cur);
-  fill_halo(c, cur, true);           // halo + boundary condition of the state whose momentum is the mass flux (driver_trcadv3d.F90:404-420)
-  CUDA_TRY(cudaMemcpyAsync(t.q[0].p, QTRC, c->nint * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-  if (RHOQ_tp) CUDA_TRY(cudaMemcpyAsync(t.rhoq.p, RHOQ_tp, c->nint * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-  TracerParams P{};
-  P.mfx = c->prog[cur][V_MOMX].p; P.mfy = c->prog[cur][V_MOMY].p; P.mfz = c->prog[cur][V_MOMZ].p;
-  P.ddens = c->prog[cur][V_DDENS].p; P.ddens0 = c->prog[cur][V_DDENS].p; P.dens_hyd = c->dens_hyd.p;
-  P.alphM = t.alphM.p; P.alphP = t.alphP.p; P.fct = t.fct.p; P.rhoq_tp = RHOQ_tp ? t.rhoq.p : nullptr;
+  P.dens_hyd = c->dens_hyd.p;
+  P.fct = t.fct.p; P.rhoq_tp = with_rhoq ? t.rhoq.p : nullptr;
   P.var0 = t.var0.p; P.vartmp = t.vartmp.p;
   P.escale = c->escale.p; P.fscale = c->fscale.p; P.jac = c->Jac.p; P.w3 = c->w3.p; P.vmapP = c->d_vmapP; P.tab = c->d_tab; P.filt = t.filt.p;
   for (int i = 0; i < MAXNP; ++i) P.w1d[i] = t.w1d[i];
   P.Np = c->Np; P.Nfp = c->Nfp; P.NfpTot = c->NfpTot; P.np = c->np; P.Ne = c->Ne;
   P.disable_limiter = t.disable_limiter;
+}
+// the stage loop of AtmDynDGMDriver_trcadv3d_update (driver_trcadv3d.F90:426-528) on t.q[0]; returns the buffer holding the result
+int trc_run_stages(fedg_ctx* c, TracerParams& P, int nsteps, bool tmar, int& in) {
+  TracerState& t = c->trc;
   const RKTable& rk = t.rk;
   const int ns = rk.nstage;
   const double EPS = 2.220446e-16;
-  P.q = t.q[0].p;
-  { cudaError_t e = launch_trc_alphdens(P, c->stream); if (e != cudaSuccess) return fail(FEDG_ERR_CUDA, cudaGetErrorString(e)); }
-  int in = 0;
+  in = 0;
   for (int step = 0; step < nsteps; ++step)
     for (int st = 0; st < ns; ++st) {
       P.q = t.q[in].p; P.qout = t.q[in ^ 1].p;
@@ -2090,13 +2119,84 @@ extern "C" int fedg_trcadv_update(fedg_ctx* c, double* QTRC, const double* RHOQ_
       P.c_ssm1 = c0; P.c_ss = c1;
       P.dttmp = t.dt * rk.gm(st + 1, st) / rk.sg(st + 1, st);
       P.do_filter = (st == ns - 1 && t.do_filter) ? 1 : 0;
-      P.do_tmar = (st == ns - 1 && !t.disable_limiter) ? 1 : 0;
+      P.do_tmar = (st == ns - 1 && tmar) ? 1 : 0;
       if (c->Nhalo > 0) aux_halo_kernel<<<(c->Nhalo + 255) / 256, 256, 0, c->stream>>>(t.q[in].p, c->d_halo_src, int(c->nint), c->Nhalo);
       { cudaError_t e = launch_trc_fct(P, c->stream); if (e != cudaSuccess) return fail(FEDG_ERR_CUDA, cudaGetErrorString(e)); }
       if (c->Nhalo > 0) aux_halo_kernel<<<(c->Nhalo + 255) / 256, 256, 0, c->stream>>>(t.fct.p, c->d_halo_src, int(c->nint), c->Nhalo);
       { cudaError_t e = launch_trc_stage(P, c->stream); if (e != cudaSuccess) return fail(FEDG_ERR_CUDA, cudaGetErrorString(e)); }
       in ^= 1;
     }
+  return FEDG_OK;
+}
+}  // namespace
+
+extern "C" int fedg_trcadv_update(fedg_ctx* c, double* QTRC, const double* RHOQ_tp, int nsteps) {
+  if (!c || !QTRC || nsteps < 0) return fail(FEDG_ERR_ARG, "bad argument");
+  TracerState& t = c->trc;
+  if (!t.ready) return fail(FEDG_ERR_STATE, "fedg_trcadv_init must be called first");
+  ensure_tables(c);
+  const int cur = c->cur;
+  ensure_dp(c, cur);
+  fill_halo(c, cur, true);           // halo + boundary condition of the state whose momentum is the mass flux (driver_trcadv3d.F90:404-420)
+  CUDA_TRY(cudaMemcpyAsync(t.q[0].p, QTRC, c->nint * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  if (RHOQ_tp) CUDA_TRY(cudaMemcpyAsync(t.rhoq.p, RHOQ_tp, c->nint * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  TracerParams P{};
+  trc_common_params(c, P, RHOQ_tp != nullptr);
+  P.mfx = c->prog[cur][V_MOMX].p; P.mfy = c->prog[cur][V_MOMY].p; P.mfz = c->prog[cur][V_MOMZ].p;
+  P.ddens = c->prog[cur][V_DDENS].p; P.ddens0 = c->prog[cur][V_DDENS].p;
+  P.alphM = t.alphM.p; P.alphP = t.alphP.p;
+  P.q = t.q[0].p;
+  { cudaError_t e = launch_trc_alphdens(P, c->stream); if (e != cudaSuccess) return fail(FEDG_ERR_CUDA, cudaGetErrorString(e)); }
+  int in = 0;
+  { int rc = trc_run_stages(c, P, nsteps, !t.disable_limiter, in); if (rc) return rc; }
+  CUDA_TRY(cudaMemcpyAsync(QTRC, t.q[in].p, c->nint * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  CUDA_TRY(cudaGetLastError());
+  if (in != 0) std::swap(t.q[0], t.q[1]);
+  return FEDG_OK;
+}
+
+extern "C" int fedg_trcadv_couple(fedg_ctx* c, int on) {
+  if (!c) return fail(FEDG_ERR_ARG, "null argument");
+  TracerState& t = c->trc;
+  if (!on) { t.release_coupling(); return FEDG_OK; }
+  if (c->terrain || c->global) return fail(FEDG_ERR_UNSUPPORTED, "tracer advection is available on the flat regional mesh only");
+  if (c->comm.active && c->comm.nremote > 0) return fail(FEDG_ERR_UNSUPPORTED, "tracer advection runs on a single tile");
+  for (int f = 0; f < 6; ++f) if (c->link[f].src || c->link[f].recvbuf) return fail(FEDG_ERR_UNSUPPORTED, "tracer advection runs on a single local mesh");
+  for (auto& b : t.mflx) CUDA_TRY(b.alloc(c->nall));
+  CUDA_TRY(t.alphM_t.alloc(size_t(c->NfpTot) * c->Ne)); CUDA_TRY(t.alphP_t.alloc(size_t(c->NfpTot) * c->Ne));
+  CUDA_TRY(t.dens0.alloc(c->nall)); CUDA_TRY(t.dens1.alloc(c->nall));
+  t.couple = true; t.have_flux = false;
+  return FEDG_OK;
+}
+
+extern "C" int fedg_trcadv_update_coupled(fedg_ctx* c, double* QTRC, const double* RHOQ_tp) {
+  if (!c || !QTRC) return fail(FEDG_ERR_ARG, "bad argument");
+  TracerState& t = c->trc;
+  if (!t.ready) return fail(FEDG_ERR_STATE, "fedg_trcadv_init must be called first");
+  if (!t.couple || !t.have_flux) return fail(FEDG_ERR_STATE, "no accumulated mass flux: call fedg_trcadv_couple and run a dynamics step first");
+  ensure_tables(c);
+  const int cur = c->cur, sp = (cur + 1) % 3;
+  // MeshFieldComm_Exchange of the averaged mass flux + ApplyBC_PROGVARS_lc on it (driver_trcadv3d.F90:404-420): staged through a spare
+  // state buffer so that the halo / boundary-condition kernel of the dynamics does it
+  const double* src[NVAR];
+  src[V_DDENS] = t.dens1.p; src[V_MOMX] = t.mflx[0].p; src[V_MOMY] = t.mflx[1].p; src[V_MOMZ] = t.mflx[2].p; src[V_DRHOT] = c->prog[cur][V_DRHOT].p;
+  for (int v = 0; v < NVAR; ++v)
+    CUDA_TRY(cudaMemcpyAsync(c->prog[sp][v].p, src[v], c->nint * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+  c->dp_valid[sp] = false;
+  ensure_dp(c, sp);
+  fill_halo(c, sp, true);
+  c->dp_valid[sp] = false;
+  CUDA_TRY(cudaMemcpyAsync(t.q[0].p, QTRC, c->nint * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  if (RHOQ_tp) CUDA_TRY(cudaMemcpyAsync(t.rhoq.p, RHOQ_tp, c->nint * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  TracerParams P{};
+  trc_common_params(c, P, RHOQ_tp != nullptr);
+  P.mfx = c->prog[sp][V_MOMX].p; P.mfy = c->prog[sp][V_MOMY].p; P.mfz = c->prog[sp][V_MOMZ].p;
+  P.ddens = t.dens1.p; P.ddens0 = t.dens0.p;
+  P.alphM = t.alphM_t.p; P.alphP = t.alphP_t.p;
+  int in = 0;
+  { int rc = trc_run_stages(c, P, 1, false, in); if (rc) return rc; }
+  CUDA_TRY(launch_trc_rescale(t.q[in].p, c->dens_hyd.p, t.dens1.p, c->prog[cur][V_DDENS].p, c->nint, c->stream));
   CUDA_TRY(cudaMemcpyAsync(QTRC, t.q[in].p, c->nint * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   CUDA_TRY(cudaStreamSynchronize(c->stream));
   CUDA_TRY(cudaGetLastError());

@@ -143,6 +143,10 @@ struct TracerParams {
   int disable_limiter, do_filter, do_tmar;
   int Np, Nfp, NfpTot, np, Ne;
 };
+cudaError_t launch_trc_save_massflux(const double* const prog[NVAR], const double* dens_hyd, const double* pres_hyd, const double* dpres,
+                                     const int* vmapP, double* const mflx[3], double* alphM, double* alphP, double w_h, double w_v, double gamm,
+                                     bool hevi, bool first, int Np, int Nfp, int NfpTot, int np, int Ne, cudaStream_t s);
+cudaError_t launch_trc_rescale(double* q, const double* dens_hyd, const double* dd_trc, const double* ddens, size_t n, cudaStream_t s);
 cudaError_t launch_trc_alphdens(const TracerParams& P, cudaStream_t s);
 cudaError_t launch_trc_fct(const TracerParams& P, cudaStream_t s);
 cudaError_t launch_trc_stage(const TracerParams& P, cudaStream_t s);

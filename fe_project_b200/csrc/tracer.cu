@@ -1,9 +1,11 @@
 // DG tracer advection with a prescribed mass flux on the GPU (the ONLY_TRACERADV_FLAG mode of
 // AtmDynDGMDriver_trcadv3d_update, fluid_dyn_solver/scale_atm_dyn_dgm_driver_trcadv3d.F90:312-559) for the flat regional mesh.
 //
-// STATUS: written against the CPU restatement of the test infrastructure but NOT yet validated on hardware -- the round's GPU budget was
-// spent when it was written.  tests/test_gpu_tracer.py runs it in a subprocess and is marked xfail(strict=False) until it has
-// been seen green on a B200; nothing else in the library depends on it.
+// Parity with the CPU restatement: tests/test_gpu_tracer.py (green on hardware since the round-1 driver run).  Round 2 adds the COUPLED
+// mode (driver_trcadv3d.F90:426-539 after a dynamics step): the mass flux and the dissipation coefficient are the stage averages the
+// dynamics saved (trc_massflux_accum_kernel / trc_alphdens_dyn_kernel = atm_dyn_dgm_trcadvect3d_save_massflux :343-401 and
+// ..._cal_alphdens_dyn :460-551, called from the stage loop at driver_nonhydro3d.F90:900-917), DDENS0_TRC / DDENS_TRC the density at the
+// start of the step and after the RK loop.
 //
 //   trc_alphdens_kernel   atm_dyn_dgm_trcadvect3d_heve_cal_alphdens_advtest   trcadvect3d_heve.F90:404-455
 //   trc_fct_kernel        ..._calc_fct_coef + get_netOutwardFlux_generalhvc   :234-306, :678-777
@@ -205,12 +207,68 @@ __global__ void trc_stage_kernel(const __grid_constant__ TracerParams P) {
   P.qout[gn] = qn;
 }
 
+// save_massflux: MFLX = (first ? 0 : MFLX) + w MOM at the interior nodes
+__global__ void trc_massflux_accum_kernel(const double* __restrict__ mx, const double* __restrict__ my, const double* __restrict__ mz,
+                                          double* __restrict__ fx, double* __restrict__ fy, double* __restrict__ fz, double w_h, double w_v,
+                                          int first, size_t n) {
+  const size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (first) { fx[i] = w_h * mx[i]; fy[i] = w_h * my[i]; fz[i] = w_v * mz[i]; }
+  else { fx[i] = fx[i] + w_h * mx[i]; fy[i] = fy[i] + w_h * my[i]; fz[i] = fz[i] + w_v * mz[i]; }
+}
+// cal_alphdens_dyn: the Rusanov coefficient of the dynamics at the stage state (halo filled, boundary condition applied, DPRES of
+// the state) times the density of each side, accumulated with the stage weight of the face's direction; flat mesh (Gsqrt = G11 = G22 = 1)
+__global__ void trc_alphdens_dyn_kernel(const double* __restrict__ ddens, const double* __restrict__ dens_hyd, const double* __restrict__ mx,
+                                        const double* __restrict__ my, const double* __restrict__ mz, const double* __restrict__ pres_hyd,
+                                        const double* __restrict__ dpres, const int* __restrict__ vmapP, double* __restrict__ alphM,
+                                        double* __restrict__ alphP, double w_h, double w_v, double gamm, int hevi, int first, int Np, int Nfp,
+                                        int NfpTot, int np, int Ne) {
+  const size_t g = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (g >= size_t(NfpTot) * Ne) return;
+  const int ke = int(g / NfpTot), m = int(g - size_t(ke) * NfpTot), f = m / Nfp, fp = m - f * Nfp;
+  const size_t iM = size_t(ke) * Np + trc_face_node(f, fp, np), iP = size_t(vmapP[g]);
+  double nx, ny, nz;
+  trc_normal(f, nx, ny, nz);
+  const double anx = fabs(nx), any = fabs(ny), anz = fabs(nz);
+  const double Gnn = hevi ? anx + any : anx + any + anz;
+  const double densM = ddens[iM] + dens_hyd[iM], densP = ddens[iP] + dens_hyd[iP];
+  const double VelM = (mx[iM] * nx + my[iM] * ny + mz[iM] * nz) / densM;
+  const double VelP = (mx[iP] * nx + my[iP] * ny + mz[iP] * nz) / densP;
+  const double alpha = fmax(sqrt(Gnn * gamm * (pres_hyd[iM] + dpres[iM]) / densM) + fabs(VelM),
+                            sqrt(Gnn * gamm * (pres_hyd[iP] + dpres[iP]) / densP) + fabs(VelP));
+  const double w = w_h * (anx + any) + w_v * anz;
+  const double aM = first ? 0.0 : alphM[g], aP = first ? 0.0 : alphP[g];
+  alphM[g] = aM + w * alpha * densM;
+  alphP[g] = aP + w * alpha * densP;
+}
+// QTRC = (DENS_hyd + DDENS_TRC) / (DENS_hyd + DDENS) * QTRC_tmp (driver_trcadv3d.F90:530-537)
+__global__ void trc_rescale_kernel(double* __restrict__ q, const double* __restrict__ dens_hyd, const double* __restrict__ dd_trc,
+                                   const double* __restrict__ ddens, size_t n) {
+  const size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  q[i] = (dens_hyd[i] + dd_trc[i]) / (dens_hyd[i] + ddens[i]) * q[i];
+}
+
 size_t trc_smem_bytes(const TracerParams& P) {
   return (size_t(3) * P.NfpTot + 8 + size_t(4) * P.Np + size_t(3) * P.np * P.np + 2 * P.np + 8) * sizeof(double);
 }
 
 }  // namespace
 
+cudaError_t launch_trc_save_massflux(const double* const prog[NVAR], const double* dens_hyd, const double* pres_hyd, const double* dpres,
+                                     const int* vmapP, double* const mflx[3], double* alphM, double* alphP, double w_h, double w_v, double gamm,
+                                     bool hevi, bool first, int Np, int Nfp, int NfpTot, int np, int Ne, cudaStream_t s) {
+  const size_t n = size_t(Np) * Ne, nf = size_t(NfpTot) * Ne;
+  trc_massflux_accum_kernel<<<unsigned((n + 255) / 256), 256, 0, s>>>(prog[V_MOMX], prog[V_MOMY], prog[V_MOMZ], mflx[0], mflx[1], mflx[2], w_h, w_v,
+                                                                      first ? 1 : 0, n);
+  trc_alphdens_dyn_kernel<<<unsigned((nf + 255) / 256), 256, 0, s>>>(prog[V_DDENS], dens_hyd, prog[V_MOMX], prog[V_MOMY], prog[V_MOMZ], pres_hyd, dpres,
+                                                                     vmapP, alphM, alphP, w_h, w_v, gamm, hevi ? 1 : 0, first ? 1 : 0, Np, Nfp, NfpTot, np, Ne);
+  return cudaGetLastError();
+}
+cudaError_t launch_trc_rescale(double* q, const double* dens_hyd, const double* dd_trc, const double* ddens, size_t n, cudaStream_t s) {
+  trc_rescale_kernel<<<unsigned((n + 255) / 256), 256, 0, s>>>(q, dens_hyd, dd_trc, ddens, n);
+  return cudaGetLastError();
+}
 cudaError_t launch_trc_alphdens(const TracerParams& P, cudaStream_t s) {
   const size_t n = size_t(P.NfpTot) * P.Ne;
   trc_alphdens_kernel<<<unsigned((n + 255) / 256), 256, 0, s>>>(P);

@@ -181,6 +181,17 @@ class AtmDynDGMDriver_nonhydro3d:
         _lib.check(self.L.fedg_trcadv_update(self.h, _ptr(q), _ptr(tp), int(nsteps)))
         return q
 
+    def trcadv_couple(self, on: bool = True):
+        """Tracer coupling: the dynamics stages save the averaged mass flux for fedg_trcadv_update_coupled."""
+        _lib.check(self.L.fedg_trcadv_couple(self.h, int(bool(on))))
+
+    def trcadv_update_coupled(self, q, rhoq_tp=None):
+        """One tracer step with the stage-averaged mass flux of the last dynamics step; q (Np*NeA,) advanced in place."""
+        q = self._chk_field(q)
+        tp = None if rhoq_tp is None else self._chk_field(rhoq_tp)
+        _lib.check(self.L.fedg_trcadv_update_coupled(self.h, _ptr(q), _ptr(tp)))
+        return q
+
     def sponge_init(self, SL_WDAMP_TAU=-1.0, SL_WDAMP_HEIGHT=-1.0, SL_WDAMP_LAYER=-1, SL_HORIVELDAMP_FLAG=False):
         """PARAM_ATMOS_DYN_SPONGELAYER (scale_atm_dyn_dgm_spongelayer.F90:55-118)."""
         m = self.mesh

@@ -302,11 +302,20 @@ int fedg_group_update(fedg_ctx** ctxs, int n, int nsteps);
  * kernels of scale_atm_dyn_dgm_trcadvect3d_heve.F90:149-777): the mass flux is the momentum of the state registered with
  * fedg_set_prog, DDENS_TRC = DDENS0_TRC = DDENS.  FCT coefficient + TMAR limiters unless disable_limiter, tracer modal filter
  * (1D matrices as in fedg_dyn_init) at the last stage; low-storage explicit schemes (Advance_trcvar).  Flat regional mesh, one
- * tile, p = 3 or 7.  Parity with the CPU restatement: tests/test_gpu_tracer.py (first run on hardware: round-1 driver suite).
+ * tile, p = 3 or 7.  Parity with the CPU restatement: tests/test_gpu_tracer.py.
  * fedg_trcadv_update: QTRC (Np, NeA) host array, its (Np, Ne) interior advanced in place by nsteps; RHOQ_tp may be NULL. */
 int fedg_trcadv_init(fedg_ctx* ctx, const char* tinteg_type, double dt, int modalfilter_flag, const double* filter_h1D,
                      const double* filter_v1D, int disable_limiter);
 int fedg_trcadv_update(fedg_ctx* ctx, double* QTRC, const double* RHOQ_tp, int nsteps);
+/* The coupled mode (ONLY_TRACERADV_FLAG = .false., driver_trcadv3d.F90:426-539).  fedg_trcadv_couple(ctx, 1): from now on every dynamics
+ * stage of fedg_dyn_update saves the mass flux and the Rusanov coefficient x density with the Butcher weights
+ * (atm_dyn_dgm_trcadvect3d_save_massflux / _cal_alphdens_dyn, trcadvect3d_heve.F90:343-401, 460-551, called at
+ * driver_nonhydro3d.F90:900-917), DDENS0_TRC / DDENS_TRC are the density at the start of the step and after the RK loop (:926-937; the
+ * modal filter of the step then runs after the density was taken, as in the reference).  fedg_trcadv_update_coupled advances one
+ * tracer by one step with the averages of the LAST dynamics step (scheme, step and limiter of fedg_trcadv_init; no TMAR in this mode) and
+ * rescales it to the filtered density (:530-537).  Flat regional mesh, one tile.  Not included: the negative fixer of the model. */
+int fedg_trcadv_couple(fedg_ctx* ctx, int on);
+int fedg_trcadv_update_coupled(fedg_ctx* ctx, double* QTRC, const double* RHOQ_tp);
 
 /* ---- sample/advect3d (BASELINE config 1) --------------------------------------------------------------
  * `sparsemat` in ELL storage as the reference holds it (common/scale_sparsemat.F90:33-55, 100-250):
