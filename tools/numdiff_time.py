@@ -22,4 +22,4 @@ N = 20
 for _ in range(N):
     d.numdiff_apply()
 torch.cuda.synchronize()
-print(f"numdiff_apply: {(time.perf_counter() - t0) / N * 1e3:.3f} ms per call (5 variables x {2 * int(os.environ.get('ND_LAP', '1'))} launches... wall clock around synchronous calls)")
+print(f"FEDG_ND_KERNEL={os.environ.get('FEDG_ND_KERNEL', 'default(p7 tensor-core)')} ND_LAP={os.environ.get('ND_LAP', '1')} numdiff_apply: {(time.perf_counter() - t0) / N * 1e3:.3f} ms per call (5 variables x {2 * int(os.environ.get('ND_LAP', '1'))} launches... wall clock around synchronous calls)")
