@@ -350,6 +350,8 @@ def main():
     ap.add_argument("--ney", type=int, default=WORKLOAD["NeY"])
     ap.add_argument("--nez", type=int, default=WORKLOAD["NeZ"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--numdiff", action="store_true", help="density_current as SHIPPED (run.conf: NUMDIFF_FLAG, ND_LAPLACIAN_NUM = 1, ND_COEF = 75): "
+                    "numerical diffusion after every step, inside the timed region (extra line, not the headline)")
     ap.add_argument("--sphere-ntile", type=int, default=0, help="global_sphere: k x k tiles per panel (default: 1, or 2 on 4 / 8 GPUs)")
     ap.add_argument("--sphere-init", default="jw", choices=["jw", "solid_body"], help="global_sphere: initial state (configs[3] = jw; the configs[4] sizes use the cheap analytic one)")
     ap.add_argument("--sphere-ne", type=int, default=0, help="global_sphere: elements per panel edge (default 32 = configs[3]; configs[4] sizes it to the HBM)")
@@ -407,6 +409,11 @@ def main():
             case = GlobalPanelCase(p=7, NeX=32, NeY=32, NeZ=12, dt=5.0, tinteg="IMEX_ARK324", modalfilter=True)
             wl_name = "atm_nonhydro3d global, one cubed-sphere panel (lateral halo = own face values)"
     d = case.make_driver(None)
+    if args.numdiff:
+        if args.workload != "density_current":
+            raise SystemExit("--numdiff belongs to the density_current workload")
+        d.numdiff_init(ND_LAPLACIAN_NUM=1, ND_COEF_h=75.0, ND_COEF_v=75.0, apply_in_update=True)
+        wl_name += " + numerical diffusion as shipped (ND_LAPLACIAN_NUM=1, ND_COEF=75)"
     if world > 1:
         def bcast(raw):
             obj = [raw]

@@ -129,7 +129,7 @@ struct fedg_ctx {
   AdvectState adv;
   // numerical diffusion (fedg_numdiff_init): PARAM_ATMOS_DYN_NUMDIFF, thermal BC ids, work fields
   struct { bool on = false, in_update = false; int lap_num = 1; double coef_h = 0, coef_v = 0; int therm_bc[6] = {0, 0, 0, 0, 0, 0}; } nd;
-  DevBuf nd_g[3], nd_lap[2];
+  DevBuf nd_g[3], nd_lap[2], nd_g5[15];
   DevBuf sponge; double sponge_h = 0.0; bool has_sponge = false;
   // halo faces filled from another local mesh on the same device (cubed-sphere panel edges): fedg_link_halo
   //   src != nullptr: gathered from that mesh;  recvbuf != nullptr: the data of a mesh on another rank, shipped by NCCL into
@@ -180,6 +180,7 @@ struct fedg_ctx {
     adv.release();
     for (auto& b : phyt) b.release();
     for (auto& b : nd_g) b.release();
+    for (auto& b : nd_g5) b.release();
     for (auto& b : nd_lap) b.release();
     sponge.release();
     for (auto& b : dp) b.release();
@@ -982,6 +983,43 @@ int run_numdiff(fedg_ctx* c, int buf) {
   P.Np = c->Np; P.Nfp = c->Nfp; P.NfpTot = c->NfpTot; P.np = c->np; P.Ne = c->Ne; P.nint = c->nint; P.dt = c->dt;
   const double nd_sign = ((c->nd.lap_num + 1) % 2 == 0) ? 1.0 : -1.0;
   const int order[NVAR] = {V_DRHOT, V_MOMZ, V_MOMX, V_MOMY, V_DDENS};
+  // p = 7 and one Laplacian (the shipped configuration): the five variables of a half-step go through ONE launch each -- gradients of
+  // all five, exchange of the fifteen gradient fields, then the divergence + update of the four density-weighted variables, and DDENS
+  // last in its own launch (the others read the neighbours' un-diffused DDENS for their weights, as in the reference's order).
+  // FEDG_ND_KERNEL=1 / 2 select the node-per-thread kernel / the tensor-core kernel one variable at a time (A/B runs).
+  {
+    const char* e = getenv("FEDG_ND_KERNEL");
+    if (c->np == 8 && c->nd.lap_num == 1 && !(e && (e[0] == '1' || e[0] == '2'))) {
+      for (auto& b : c->nd_g5) if (b.n < c->nall) CUDA_TRY(b.alloc(c->nall));
+      NumdiffMulti M{};
+      M.P = P; M.P.bc_on_v = 1; M.nvar = NVAR;
+      for (int iv = 0; iv < NVAR; ++iv) {
+        const int v = order[iv];
+        NdVar& V = M.v[iv];
+        V.in0 = V.in1 = c->prog[buf][v].p; V.in2 = nullptr;
+        V.out0 = c->nd_g5[3 * iv].p; V.out1 = c->nd_g5[3 * iv + 1].p; V.out2 = c->nd_g5[3 * iv + 2].p;
+        V.var = nullptr; V.varid = v; V.dens_flag = (v != V_DDENS) ? 1 : 0;
+      }
+      launch_numdiff_multi(0, M, c->stream);
+      for (int iv = 0; iv < NVAR; ++iv) {
+        double* g3[3] = {c->nd_g5[3 * iv].p, c->nd_g5[3 * iv + 1].p, c->nd_g5[3 * iv + 2].p};
+        int rc = exchange_work_fields(c, g3, 3);
+        if (rc) return rc;
+      }
+      M.P.coef_h = nd_sign * c->nd.coef_h; M.P.coef_v = nd_sign * c->nd.coef_v;
+      for (int iv = 0; iv < NVAR; ++iv) {
+        NdVar& V = M.v[iv];
+        V.in0 = c->nd_g5[3 * iv].p; V.in1 = c->nd_g5[3 * iv + 1].p; V.in2 = c->nd_g5[3 * iv + 2].p;
+        V.out0 = V.out1 = V.out2 = nullptr; V.var = c->prog[buf][order[iv]].p;
+      }
+      M.nvar = NVAR - 1;                        // DRHOT, MOMZ, MOMX, MOMY
+      launch_numdiff_multi(2, M, c->stream);
+      M.v[0] = M.v[NVAR - 1]; M.nvar = 1;       // DDENS
+      launch_numdiff_multi(2, M, c->stream);
+      c->dp_valid[buf] = false;
+      return FEDG_OK;
+    }
+  }
   double* g[3] = {c->nd_g[0].p, c->nd_g[1].p, c->nd_g[2].p};
   for (int iv = 0; iv < NVAR; ++iv) {
     const int v = order[iv];

@@ -192,7 +192,20 @@ struct NumdiffParams {
   int Np, Nfp, NfpTot, np, Ne;
   size_t nint;
 };
+// per-variable arguments of a half-step (the five prognostic variables go through the same kernel)
+struct NdVar {
+  const double *in0, *in1, *in2;
+  double *out0, *out1, *out2, *var;
+  int varid, dens_flag;
+};
+constexpr int ND_MAXVAR = 5;
+struct NumdiffMulti {
+  NumdiffParams P;           // everything the variables share (in0 .. var, varid, dens_flag of P are not used)
+  NdVar v[ND_MAXVAR];
+  int nvar;
+};
 void launch_numdiff(int mode, const NumdiffParams& P, cudaStream_t s);
+void launch_numdiff_multi(int mode, const NumdiffMulti& M, cudaStream_t s);
 
 void launch_vi(const VIParams& p, bool moist, cudaStream_t s);
 bool launch_vi2(const VIParams& p, const ElemTables& tab, bool moist, cudaStream_t s);

@@ -176,34 +176,22 @@ __device__ __forceinline__ double2 nd_ld2(const double* p) { return *reinterpret
 // (Gathering the exterior side of the face nodes with 8-byte cp.async copies issued at block start, to overlap them with the element's own
 // loads, was measured slower: 1.91 vs 1.43 ms per Apply -- 1920 eight-byte asynchronous copies per element cost more than the latency.)
 
+// one variable of one element; the caller has loaded the tables, the face-node indices and the density of the own node pair
 template <int MODE>
-__global__ void __launch_bounds__(256, 5) numdiff_p7_kernel(const __grid_constant__ NumdiffParams P) {
+__device__ __forceinline__ void nd_p7_body(const NumdiffParams& P, const NdVar& V, double* sm, size_t iPa, size_t iPb, double2 rho_own) {
   using namespace p7nd;
-  extern __shared__ __align__(16) double sm[];
   const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
   const int ke = blockIdx.x;
   const size_t eb = size_t(ke) * N3;
   const int n0 = 2 * t + 8 * g + 64 * w;
   const size_t gn = eb + n0;
-  double* sD = sm;                    // D1D[i][l]
-  double* sLw = sm + 64;              // lift1d[m][side]
-  double* sRaw = sm + 80;             // [4][512] fields of the element as loaded: FLX h, v, rho; LAP x, y, z; TEND x, y, z, rho
-  double* sDel = sRaw + 4 * N3;       // [384] Fscale * face jump (one array: the jump of a face enters the component(s) of its normal only)
-  double* sFz = sDel + NFT;           // [k][j][i], k-stride KS_FZ: z operand
-  double* sZ = sFz + NP * KS_FZ;      // [k][j][i], k-stride KS_Z: z result (TEND)
-  double* sPl = sZ + NP * KS_Z + w * NP * PLS;   // this warp's plane [j][i], row stride PLS: y operand
-  // index loads of the face phase first: their latency passes under the element's own loads
-  const size_t iPa = size_t(P.vmapP[size_t(ke) * NFT + tid]);
-  const size_t iPb = (tid < NFT - 256) ? size_t(P.vmapP[size_t(ke) * NFT + 256 + tid]) : 0;
-  if (tid < 64) sD[tid] = P.tab->D[tid];
-  if (tid < 16) sLw[tid] = P.tab->Lw[tid];
-  const bool dens = P.dens_flag != 0;
-  const double2 a0 = nd_ld2(P.in0 + gn), a1 = nd_ld2(P.in1 + gn);
+  double* sD = sm; double* sLw = sm + 64; double* sRaw = sm + 80; double* sDel = sRaw + 4 * N3; double* sFz = sDel + NFT;
+  double* sZ = sFz + NP * KS_FZ; double* sPl = sZ + NP * KS_Z + w * NP * PLS;
+  const bool dens = V.dens_flag != 0;
+  const double2 a0 = nd_ld2(V.in0 + gn), a1 = nd_ld2(V.in1 + gn);
   double2 a2 = make_double2(0.0, 0.0), rho = make_double2(1.0, 1.0);
-  if (MODE != MODE_FLX) a2 = nd_ld2(P.in2 + gn);
-  double2 dd = make_double2(0.0, 0.0), dh = make_double2(1.0, 1.0);
-  if (dens) { dd = nd_ld2(P.ddens + gn); dh = nd_ld2(P.dens_hyd + gn); }
-  if (dens) rho = make_double2(dd.x + dh.x, dd.y + dh.y);
+  if (MODE != MODE_FLX) a2 = nd_ld2(V.in2 + gn);
+  if (dens) rho = rho_own;
   *reinterpret_cast<double2*>(sRaw + n0) = a0;
   *reinterpret_cast<double2*>(sRaw + N3 + n0) = a1;
   *reinterpret_cast<double2*>(sRaw + 2 * N3 + n0) = (MODE == MODE_FLX) ? rho : a2;
@@ -245,10 +233,10 @@ __global__ void __launch_bounds__(256, 5) numdiff_p7_kernel(const __grid_constan
     if (MODE == MODE_FLX) {
       const bool is_bound = (vel == FEDG_BND_SLIP || vel == FEDG_BND_NOSLIP);
       const double hM = sRaw[nloc], vM = sRaw[N3 + nloc];
-      double hP = P.in0[iP], vP = P.in1[iP];
+      double hP = V.in0[iP], vP = V.in1[iP];
       if (is_bound) {
-        const bool mom = (P.varid == V_MOMX || P.varid == V_MOMY || P.varid == V_MOMZ);
-        const double nn = (P.varid == V_MOMX) ? nx : (P.varid == V_MOMY) ? ny : nz;
+        const bool mom = (V.varid == V_MOMX || V.varid == V_MOMY || V.varid == V_MOMZ);
+        const double nn = (V.varid == V_MOMX) ? nx : (V.varid == V_MOMY) ? ny : nz;
         double eh = hP, ev = vP;
         if (vel == FEDG_BND_SLIP && mom) { eh = hM - 2.0 * (hM * nn) * nn; ev = vM - 2.0 * (vM * nn) * nn; }
         else if (vel == FEDG_BND_NOSLIP && mom) { eh = -hM; ev = -vM; }
@@ -264,15 +252,15 @@ __global__ void __launch_bounds__(256, 5) numdiff_p7_kernel(const __grid_constan
     } else {
       const bool is_bound = (vel == FEDG_BND_SLIP) || (therm == 1);
       const double xM = sRaw[nloc], yM = sRaw[N3 + nloc], zM = sRaw[2 * N3 + nloc];
-      double xP = P.in0[iP], yP = P.in1[iP], zP = P.in2[iP];
+      double xP = V.in0[iP], yP = V.in1[iP], zP = V.in2[iP];
       if (is_bound) {
         const double gnrm = xM * nx + yM * ny + zM * nz;
         if (vel == FEDG_BND_SLIP) {
-          if (P.varid == V_MOMX) { yP = yM - 2.0 * gnrm * ny; zP = zM - 2.0 * gnrm * nz; }
-          else if (P.varid == V_MOMY) { xP = xM - 2.0 * gnrm * nx; zP = zM - 2.0 * gnrm * nz; }
-          else if (P.varid == V_MOMZ) { xP = xM - 2.0 * gnrm * nx; yP = yM - 2.0 * gnrm * ny; }
+          if (V.varid == V_MOMX) { yP = yM - 2.0 * gnrm * ny; zP = zM - 2.0 * gnrm * nz; }
+          else if (V.varid == V_MOMY) { xP = xM - 2.0 * gnrm * nx; zP = zM - 2.0 * gnrm * nz; }
+          else if (V.varid == V_MOMZ) { xP = xM - 2.0 * gnrm * nx; yP = yM - 2.0 * gnrm * ny; }
         }
-        if (therm == 1 && (P.varid == V_DDENS || P.varid == V_DRHOT)) {
+        if (therm == 1 && (V.varid == V_DDENS || V.varid == V_DRHOT)) {
           xP = xM - 2.0 * gnrm * nx; yP = yM - 2.0 * gnrm * ny; zP = zM - 2.0 * gnrm * nz;
         }
       }
@@ -304,8 +292,8 @@ __global__ void __launch_bounds__(256, 5) numdiff_p7_kernel(const __grid_constan
     nd_dmma(z0, z1, lwA, bl);
   }
   const size_t gz = eb + 2 * t + 8 * w + 64 * g;            // the nodes of the z tile's C fragment: (i = 2t, 2t+1; j = w; k = g)
-  if (MODE == MODE_FLX) *reinterpret_cast<double2*>(P.out2 + gz) = make_double2(z0, z1);
-  else if (MODE == MODE_LAP) *reinterpret_cast<double2*>(P.out1 + gz) = make_double2(z0, z1);
+  if (MODE == MODE_FLX) *reinterpret_cast<double2*>(V.out2 + gz) = make_double2(z0, z1);
+  else if (MODE == MODE_LAP) *reinterpret_cast<double2*>(V.out1 + gz) = make_double2(z0, z1);
   else {
     *reinterpret_cast<double2*>(sZ + 2 * t + 8 * w + KS_Z * g) = make_double2(z0, z1);
     __syncthreads();
@@ -318,24 +306,74 @@ __global__ void __launch_bounds__(256, 5) numdiff_p7_kernel(const __grid_constan
   if (MODE == MODE_FLX) {
     double c0 = 0.0, c1 = 0.0;
     nd_dmma(c0, c1, Fx.x, bx0); nd_dmma(c0, c1, Fx.y, bx1); nd_dmma(c0, c1, axl, lwA);
-    *reinterpret_cast<double2*>(P.out0 + gn) = make_double2(c0, c1);
+    *reinterpret_cast<double2*>(V.out0 + gn) = make_double2(c0, c1);
     double d0 = 0.0, d1 = 0.0;
     nd_dmma(d0, d1, ay0, by0); nd_dmma(d0, d1, ay1, by1); nd_dmma(d0, d1, lwA, byl);
-    *reinterpret_cast<double2*>(P.out1 + gn) = make_double2(d0, d1);
+    *reinterpret_cast<double2*>(V.out1 + gn) = make_double2(d0, d1);
   } else {
     double c0 = 0.0, c1 = 0.0;
     if (MODE == MODE_TEND) { const double2 z = nd_ld2(sZ + 2 * t + 8 * g + KS_Z * w); c0 = z.x; c1 = z.y; }
     nd_dmma(c0, c1, Fx.x, bx0); nd_dmma(c0, c1, Fx.y, bx1);
     nd_dmma(c0, c1, ay0, by0); nd_dmma(c0, c1, ay1, by1);
     nd_dmma(c0, c1, axl, lwA); nd_dmma(c0, c1, lwA, byl);
-    if (MODE == MODE_LAP) *reinterpret_cast<double2*>(P.out0 + gn) = make_double2(c0, c1);
+    if (MODE == MODE_LAP) *reinterpret_cast<double2*>(V.out0 + gn) = make_double2(c0, c1);
     else {
-      const double2 v = nd_ld2(P.var + gn);
-      *reinterpret_cast<double2*>(P.var + gn) = make_double2(v.x + P.dt * c0, v.y + P.dt * c1);
+      const double2 v = nd_ld2(V.var + gn);
+      *reinterpret_cast<double2*>(V.var + gn) = make_double2(v.x + P.dt * c0, v.y + P.dt * c1);
     }
   }
 }
+
+// the shared part of a block: tables, face-node indices (issued first: their latency passes under the element's own loads), density
+#define ND_P7_PROLOGUE                                                                                               \
+  using namespace p7nd;                                                                                              \
+  extern __shared__ __align__(16) double sm[];                                                                       \
+  const int tid = threadIdx.x;                                                                                       \
+  const int ke = blockIdx.x;                                                                                         \
+  const size_t gn0 = size_t(ke) * N3 + 2 * (tid & 3) + 8 * ((tid & 31) >> 2) + 64 * (tid >> 5);                      \
+  const size_t iPa = size_t(P.vmapP[size_t(ke) * NFT + tid]);                                                        \
+  const size_t iPb = (tid < NFT - 256) ? size_t(P.vmapP[size_t(ke) * NFT + 256 + tid]) : 0;                          \
+  if (tid < 64) sm[tid] = P.tab->D[tid];                                                                             \
+  if (tid < 16) sm[64 + tid] = P.tab->Lw[tid];                                                                       \
+  const double2 dd_ = nd_ld2(P.ddens + gn0), dh_ = nd_ld2(P.dens_hyd + gn0);                                         \
+  const double2 rho_own = make_double2(dd_.x + dh_.x, dd_.y + dh_.y);
+
+template <int MODE>
+__global__ void __launch_bounds__(256, 5) numdiff_p7_kernel(const __grid_constant__ NumdiffParams P) {
+  ND_P7_PROLOGUE
+  NdVar V;
+  V.in0 = P.in0; V.in1 = P.in1; V.in2 = P.in2; V.out0 = P.out0; V.out1 = P.out1; V.out2 = P.out2; V.var = P.var;
+  V.varid = P.varid; V.dens_flag = P.dens_flag;
+  nd_p7_body<MODE>(P, V, sm, iPa, iPb, rho_own);
+}
+
+// several variables of the same half-step in one launch: the density, the tables and the face indices are loaded once, and the
+// fields of the next variable are pulled into L2 while the current one is worked on (one variable per launch left the kernel waiting
+// for two dependent global latencies per element: profiles/r02_numdiff_p7_details.txt)
+template <int MODE>
+__global__ void __launch_bounds__(256, 5) numdiff_p7_multi_kernel(const __grid_constant__ NumdiffMulti M) {
+  const NumdiffParams& P = M.P;
+  ND_P7_PROLOGUE
+  for (int iv = 0; iv < M.nvar; ++iv) {
+    if (iv + 1 < M.nvar && tid < 3) {
+      const NdVar& N = M.v[iv + 1];
+      const double* f = (tid == 0) ? N.in0 : (tid == 1) ? N.in1 : N.in2;
+      if (f && (tid == 0 || f != N.in0))
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(f + size_t(ke) * N3), "r"(uint32_t(N3 * sizeof(double))) : "memory");
+    }
+    nd_p7_body<MODE>(P, M.v[iv], sm, iPa, iPb, rho_own);
+    __syncthreads();       // the staging areas are reused by the next variable
+  }
+}
 }  // namespace
+
+// several variables of one half-step (p = 7 only): FLX or TEND of M.nvar variables in one launch
+void launch_numdiff_multi(int mode, const NumdiffMulti& M, cudaStream_t s) {
+  const size_t shmem = size_t(p7nd::SM_DOUBLES) * sizeof(double);
+  if (mode == MODE_FLX) numdiff_p7_multi_kernel<MODE_FLX><<<M.P.Ne, 256, shmem, s>>>(M);
+  else if (mode == MODE_LAP) numdiff_p7_multi_kernel<MODE_LAP><<<M.P.Ne, 256, shmem, s>>>(M);
+  else numdiff_p7_multi_kernel<MODE_TEND><<<M.P.Ne, 256, shmem, s>>>(M);
+}
 
 void launch_numdiff(int mode, const NumdiffParams& P, cudaStream_t s) {
   // p = 7: tensor-core kernel (FEDG_ND_KERNEL=1 selects the node-per-thread kernel: A/B runs, read at every launch)
