@@ -7,10 +7,11 @@ timeout 600 python bench.py --steps 20 --warmup 3 > gpurun_out/r02_bench_heve.js
 for k in 2 1; do
   FEDG_VI_KERNEL=$k timeout 600 python bench.py --steps 10 --warmup 3 --eqs hevi --no-cpu-baseline > gpurun_out/r02_bench_hevi_k$k.json 2> gpurun_out/r02_bench_hevi_k$k.err; echo "bench hevi k$k rc=$?"
 done
+timeout 600 python bench.py --steps 20 --warmup 3 --numdiff --no-cpu-baseline > gpurun_out/r02_bench_heve_numdiff.json 2> gpurun_out/r02_bench_heve_numdiff.err; echo "bench heve+numdiff rc=$?"
 timeout 900 python bench.py --steps 5 --warmup 3 --workload global_sphere > gpurun_out/r02_bench_sphere_k2.json 2> gpurun_out/r02_bench_sphere_k2.err; echo "bench sphere rc=$?"; tail -2 gpurun_out/r02_bench_sphere_k2.err
 python - <<'PY'
 import json
-for f in ("heve","hevi_k2","hevi_k1","sphere_k2"):
+for f in ("heve","heve_numdiff","hevi_k2","hevi_k1","sphere_k2"):
     try:
         d=json.load(open(f"gpurun_out/r02_bench_{f}.json")); r=d["roofline"]
         print(f, "value %.4e ms/step %.3f kernel-ms %s frac %s e2e %.3e (%s) finite %s clocks %s"%(d["value"],d["ms_per_step"],r["ms_per_launch"],r["frac"],d["e2e"]["value"],d["e2e"].get("blocking_call_value"),d["finite"],d["clocks"]))
