@@ -231,7 +231,9 @@ int fedg_create(const fedg_mesh_desc* d, fedg_ctx** out) {
   if (ce != cudaSuccess || ndev == 0)
     return fail(FEDG_ERR_CUDA, std::string("no CUDA device: ") + cudaGetErrorString(ce) + " (this library has no CPU fallback)");
   const int np = d->polyorder + 1;
-  if (np != 8 && np != 4) return fail(FEDG_ERR_UNSUPPORTED, "polyorder must be 7 or 3 in this build");
+  // p = 7: tensor-core stage kernel; p = 1, 3, 5: the generic node-per-thread kernel (an even number of nodes per direction: its
+  // rows are read as 128-bit pairs and an element's 8 np^3 bytes must keep the 16-byte alignment of the bulk copies)
+  if (np != 8 && np != 6 && np != 4 && np != 2) return fail(FEDG_ERR_UNSUPPORTED, "polyorder must be 7, 5, 3 or 1 in this build");
   if (d->Ne != d->NeX * d->NeY * d->NeZ || d->Ne2D != d->NeX * d->NeY) return fail(FEDG_ERR_ARG, "Ne / NeX*NeY*NeZ mismatch");
   for (const void* p : {(const void*)d->D1D, (const void*)d->Lift, (const void*)d->VPOrdM1, (const void*)d->IntWeight_lgl,
                         (const void*)d->Escale, (const void*)d->Fscale, (const void*)d->normal_fn, (const void*)d->J,

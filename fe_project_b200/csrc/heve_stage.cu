@@ -290,7 +290,7 @@ static void launch_stage_np(const StageParams& p, bool terrain, bool moist, cuda
   using G = StageGeo<NP>;
   const size_t shmem = G::SMEM_BYTES;
   const int nel = p.elem_list ? p.nelem : p.Ne;
-  dim3 grid((nel + G::EPB - 1) / G::EPB), block(512);
+  dim3 grid((nel + G::EPB - 1) / G::EPB), block(G::EPB * G::N3);   // 512 threads for p = 7, 3, 1; 2 x 216 for p = 5
 #define FEDG_LAUNCH(T, M)                                                                                             \
   do {                                                                                                                \
     static bool attr_set = false;                                                                                     \
@@ -329,6 +329,10 @@ void launch_stage(const StageParams& p, int np, bool terrain, bool moist, bool h
     else { if (hevi) launch_stage_np<8, true, 2>(p, terrain, moist, s); else launch_stage_np<8, false, 2>(p, terrain, moist, s); }
   } else if (np == 4) {
     if (hevi) launch_stage_np<4, true, 2>(p, terrain, moist, s); else launch_stage_np<4, false, 2>(p, terrain, moist, s);
+  } else if (np == 6) {   // p = 5 (HEVE only: the vertical-implicit kernels are built for p = 7)
+    launch_stage_np<6, false, 2>(p, terrain, moist, s);
+  } else if (np == 2) {   // p = 1
+    launch_stage_np<2, false, 2>(p, terrain, moist, s);
   }
   // other orders are rejected at fedg_create
 }

@@ -45,7 +45,8 @@ enum { FEDG_BND_NOSPEC = 0, FEDG_BND_PERIODIC = 1, FEDG_BND_SLIP = 2, FEDG_BND_N
  *   element/scale_element_base.F90:111-145,
  *   element/scale_element_operation_tensorprod3D.F90.erb:66-80 (D1D, Lift_mat, IntrpMat_VPOrdM1). */
 typedef struct fedg_mesh_desc {
-  int polyorder;            /* PolyOrder_h == PolyOrder_v (TensorProd3D requirement, tensorprod3D.F90.erb:112) */
+  int polyorder;            /* PolyOrder_h == PolyOrder_v (TensorProd3D requirement, tensorprod3D.F90.erb:112); 7 (every equation set),
+                             * 5, 3, 1 (NONHYDRO3D_HEVE; the element-operation factory covers P1..P15, tensorprod3D.F90:578-632) */
   int Ne, NeA, NeX, NeY, NeZ, Ne2D;
   int Nhalo;                /* size(VMapB) */
   /* reference element */

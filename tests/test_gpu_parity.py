@@ -72,7 +72,7 @@ def test_halo_and_bc(small_case):
         assert np.array_equal(g[nm][:n], o.arr(nm)[:n]), nm
 
 
-@pytest.mark.parametrize("p,dims", [(7, (4, 2, 3)), (3, (5, 3, 4))])
+@pytest.mark.parametrize("p,dims", [(7, (4, 2, 3)), (3, (5, 3, 4)), (5, (3, 2, 3)), (1, (6, 4, 5))])
 def test_tendency(p, dims):
     """cal_tend_ex seam: halo + pressure + BC + Rusanov flux + Div_var5 + tendency assembly."""
     case = DensityCurrentCase(p=p, NeX=dims[0], NeY=dims[1], NeZ=dims[2], perturb=2.0, intrp_order=min(11, p + 4))
@@ -104,11 +104,13 @@ def test_steps_all_schemes(tinteg):
 @pytest.mark.parametrize("p,dims,mf,periodic", [(7, (4, 2, 3), True, (False, True, False)),
                                                 (7, (3, 3, 2), False, (False, False, False)),
                                                 (3, (6, 4, 4), True, (True, True, False)),
-                                                (7, (1, 1, 1), True, (False, True, False))])
+                                                (7, (1, 1, 1), True, (False, True, False)),
+                                                (5, (3, 2, 3), True, (False, True, False)),
+                                                (1, (6, 4, 5), True, (True, False, False))])
 def test_steps_density_current(p, dims, mf, periodic):
     """N = 20 steps of the full dynamics step (all stages, BC, modal filter, final pressure)."""
     case = DensityCurrentCase(p=p, NeX=dims[0], NeY=dims[1], NeZ=dims[2], perturb=2.0, modalfilter=mf,
-                              periodic=periodic, intrp_order=min(11, p + 4), dt=0.08 if p == 7 else 0.2)
+                              periodic=periodic, intrp_order=min(11, p + 4), dt={7: 0.08, 5: 0.1, 3: 0.2, 1: 0.5}[p])
     o = case.make_oracle()
     d = case.make_driver(o)
     o.update(20); d.Update(20)
