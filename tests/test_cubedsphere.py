@@ -259,3 +259,27 @@ def test_skeleton_tiles_give_the_same_links(ntile, own):
     assert pf == pp
     for T, peer, mid, U, g in pp[2]:                      # what this rank sends: source indices on its own tiles
         assert np.array_equal(full.links[U][g][1], part.links[U][g][1])
+
+
+@pytest.mark.parametrize("world,ntile", [(2, 1), (3, 1), (6, 1), (4, 2), (8, 2)])
+def test_every_rank_gets_its_exchange_plan_from_skeletons(world, ntile):
+    """What bench.py does on N GPUs: rank r builds its own tiles in full and the rest as skeletons.  Its exchange plan (local links,
+    receives, sends) must be the plan the fully built sphere gives, and the plans of all ranks must pair up: every send of rank a to
+    rank b with message id m is a receive of rank b from rank a with the same id and the same number of nodes."""
+    from fe_project_b200.cubedsphere import CubedSphere, exchange_plan, panel_owner
+    e = HexElement(3)
+    FZ = np.array([0.0, 1000.0, 3000.0])
+    full = CubedSphere(e, 2, 2, 3000.0, 6.37122e6, FZ=FZ, ntile=ntile)
+    owner = panel_owner(world, ntile)
+    sends, recvs = {}, {}
+    for r in range(world):
+        own = [t for t, o in enumerate(owner) if o == r]
+        part = CubedSphere(e, 2, 2, 3000.0, 6.37122e6, FZ=FZ, ntile=ntile, build=own)
+        plan = exchange_plan(part.links, owner, r)
+        assert plan == exchange_plan(full.links, owner, r)
+        for T, peer, mid, U, g in plan[2]:
+            sends[(r, peer, mid)] = part.links[U][g][1].size
+        for U, g, peer, mid in plan[1]:
+            recvs[(peer, r, mid)] = part.links[U][g][1].size
+            assert part.links[U][g][2] is None or part.links[U][g][2].shape == (part.links[U][g][1].size, 2, 2)
+    assert sends == recvs and len(sends) > 0
