@@ -5,6 +5,8 @@ the Fortran, not from oracle/dyn_heve.cpp, vectorised over elements with dense t
   cal_tend_heve  atm_dyn_dgm_nonhydro3d_rhot_heve_cal_tend                fluid_dyn_solver/scale_atm_dyn_dgm_nonhydro3d_rhot_heve.F90:292-489
   drhot2pres     atm_dyn_dgm_nonhydro3d_common_DRHOT2PRES                 fluid_dyn_solver/scale_atm_dyn_dgm_nonhydro3d_common.F90:428-479
   apply_bc       AtmDynBnd%ApplyBC_PROGVARS_lc (SLIP / NOSLIP, flat)      fluid_dyn_solver/scale_atm_dyn_dgm_bnd.F90:270-367
+  numflux_hevi   atm_dyn_dgm_nonhydro3d_rhot_hevi_numflux_get_generalvc   fluid_dyn_solver/scale_atm_dyn_dgm_nonhydro3d_rhot_hevi_numflux.F90:232-416
+  cal_tend_hevi  atm_dyn_dgm_nonhydro3d_rhot_hevi_cal_tend                fluid_dyn_solver/scale_atm_dyn_dgm_nonhydro3d_rhot_hevi.F90:289-482
 
 Inputs are the host-side mesh / element objects of fe_project_b200 (themselves an independent restatement of the set-up code) and flat
 (NeA * Np) field arrays with the halo part filled.  tests/test_oracle_numpy_dyn.py asserts agreement with the C++ oracle to 1e-13."""
@@ -103,6 +105,82 @@ def cal_tend_heve(elem, mesh, c, q, aux, DPRES, DPhydDx=None, DPhydDy=None, cori
     n = elem.np1
     drho = np.einsum("kl,elji->ekji", elem.VPOrdM1, dd.reshape(Ne, n, n, n)).reshape(Ne, Np)
     out["MOMZ_dt"] = out["MOMZ_dt"] - c["GRAV"] * drho
+    cor = 0.0 if coriolis is None else np.asarray(coriolis).reshape(mesh.Ne2D, -1)[mesh.EMap3Dto2D][:, elem.IndexH2Dto3D]
+    gx = 0.0 if DPhydDx is None else sh(DPhydDx)
+    gy = 0.0 if DPhydDy is None else sh(DPhydDy)
+    out["MOMX_dt"] = (-gx + cor * my) + out["MOMX_dt"]
+    out["MOMY_dt"] = (-gy - cor * mx) + out["MOMY_dt"]
+    return out
+
+
+def numflux_hevi(elem, mesh, c, q, aux, DPRES):
+    """Horizontally explicit Rusanov flux of the HEVI equation set (rhot_hevi_numflux.F90:304-414): the dissipation coefficient carries
+    swV = 1 - nz^2 (none on the vertical faces), mass and theta are advected with the HORIZONTAL velocity only, MOMZ has no vertical
+    pressure term, GsqrtV_ = Gsqrt_ inside the flux (:320).  Same argument conventions as numflux_heve."""
+    iM, iP = mesh.VMapM, mesh.VMapP
+    nx, ny, nz = mesh.normal_fn
+    G = mesh.Gsqrt.reshape(-1)
+    G13, G23 = mesh.GI3[0].reshape(-1), mesh.GI3[1].reshape(-1)
+    gamm = c["CPdry"] / c["CVdry"]
+    side = {}
+    for tag, idx in (("IN", iM), ("EX", iP)):
+        Gs = G[idx]
+        s = dict(Gs=Gs, RGv=1.0 / Gs, G13=G13[idx], G23=G23[idx])
+        for nm in ("DDENS", "MOMX", "MOMY", "MOMZ", "DRHOT"):
+            s[nm] = Gs * q[nm][idx]
+        s["Phyd"] = aux["PRES_hyd"][idx]
+        s["dp"] = DPRES[idx]
+        s["Dens"] = s["DDENS"] + Gs * aux["DENS_hyd"][idx]
+        s["Rhot"] = Gs * aux["THERM_hyd"][idx] + s["DRHOT"]
+        s["Velh"] = (s["MOMX"] * nx + s["MOMY"] * ny) / s["Dens"]
+        s["Vel"] = s["Velh"] + ((s["MOMZ"] * s["RGv"] + s["G13"] * s["MOMX"] + s["G23"] * s["MOMY"]) * nz) / s["Dens"]
+        side[tag] = s
+    I, E = side["IN"], side["EX"]
+    swV = 1.0 - nz ** 2
+    alpha = swV * np.maximum(np.sqrt(gamm * (I["Phyd"] + I["dp"]) * I["Gs"] / I["Dens"]) + np.abs(I["Vel"]),
+                             np.sqrt(gamm * (E["Phyd"] + E["dp"]) * E["Gs"] / E["Dens"]) + np.abs(E["Vel"]))
+    hf = mesh.Fscale * 0.5
+    out = {}
+    out["DENS"] = hf * (E["Dens"] * E["Velh"] - I["Dens"] * I["Velh"] + (-alpha * (E["DDENS"] - I["DDENS"])))
+    out["RHOT"] = hf * (E["Rhot"] * E["Velh"] - I["Rhot"] * I["Velh"] + (-alpha * (E["DRHOT"] - I["DRHOT"])))
+    out["MOMZ"] = hf * (E["MOMZ"] * E["Vel"] - I["MOMZ"] * I["Vel"] + (-alpha * (E["MOMZ"] - I["MOMZ"])))
+    t3, t4 = E["Gs"] * E["dp"], I["Gs"] * I["dp"]
+    mom1 = (nx + E["G13"] * nz) * t3 - (nx + I["G13"] * nz) * t4
+    mom2 = (ny + E["G23"] * nz) * t3 - (ny + I["G23"] * nz) * t4
+    out["MOMX"] = hf * (E["MOMX"] * E["Vel"] - I["MOMX"] * I["Vel"] + mom1 + (-alpha * (E["MOMX"] - I["MOMX"])))
+    out["MOMY"] = hf * (E["MOMY"] * E["Vel"] - I["MOMY"] * I["Vel"] + mom2 + (-alpha * (E["MOMY"] - I["MOMY"])))
+    return out
+
+
+def cal_tend_hevi(elem, mesh, c, q, aux, DPRES, DPhydDx=None, DPhydDy=None, coriolis=None):
+    """Horizontally explicit tendency of the HEVI equation set (rhot_hevi.F90:372-478): DENS and RHOT take the horizontal derivatives
+    and the lift only, MOMZ has no pressure term and no buoyancy here (both are in the vertical-implicit part), MOMX / MOMY as in HEVE."""
+    Ne, Np = mesh.Ne, elem.Np
+    ni = Ne * Np
+    dfl = numflux_hevi(elem, mesh, c, q, aux, DPRES)
+    sh = lambda a: np.asarray(a).reshape(-1)[:ni].reshape(Ne, Np)
+    G = sh(mesh.Gsqrt)
+    gH = mesh.GsqrtH[mesh.EMap3Dto2D][:, elem.IndexH2Dto3D]
+    RGv = 1.0 / (G / gH)
+    RG = 1.0 / G
+    GI1, GI2 = sh(mesh.GI3[0]), sh(mesh.GI3[1])
+    dd, mx, my, mz, dr = (sh(q[k]) for k in ("DDENS", "MOMX", "MOMY", "MOMZ", "DRHOT"))
+    RD = 1.0 / (dd + sh(aux["DENS_hyd"]))
+    gdp = G * sh(DPRES)
+    Fd = (G * mx, G * my, G * (mz * RGv + GI1 * mx + GI2 * my))
+    pt = (sh(aux["THERM_hyd"]) + dr) * RD
+    w, u, v = mz * RD, mx * RD, my * RD
+    zero = np.zeros_like(G)
+    F = {"DENS": (Fd[0], Fd[1], zero), "RHOT": (Fd[0] * pt, Fd[1] * pt, zero),
+         "MOMZ": (Fd[0] * w, Fd[1] * w, Fd[2] * w),
+         "MOMX": (Fd[0] * u + gdp, Fd[1] * u, Fd[2] * u + gdp * GI1),
+         "MOMY": (Fd[0] * v, Fd[1] * v + gdp, Fd[2] * v + gdp * GI2)}
+    E11, E22, E33 = mesh.Escale[0, 0], mesh.Escale[1, 1], mesh.Escale[2, 2]
+    out = {}
+    for nm in ("DENS", "RHOT", "MOMZ", "MOMX", "MOMY"):
+        dx, dy, dz, lift = _div_lift(elem, *F[nm], dfl[nm], Ne)
+        vert = 0.0 if nm in ("DENS", "RHOT") else E33 * dz      # the vertical mass / theta fluxes belong to the implicit part
+        out[nm + "_dt"] = -(E11 * dx + E22 * dy + vert + lift) * RG
     cor = 0.0 if coriolis is None else np.asarray(coriolis).reshape(mesh.Ne2D, -1)[mesh.EMap3Dto2D][:, elem.IndexH2Dto3D]
     gx = 0.0 if DPhydDx is None else sh(DPhydDx)
     gy = 0.0 if DPhydDy is None else sh(DPhydDy)

@@ -26,3 +26,30 @@ def test_numpy_restatement_of_flux_and_tendency_equals_the_cpp_oracle(p, dims, p
     te = o.arr("tend_ex")[:5 * N].reshape(5, -1)[:, :n]
     for nm, iv in (("DENS_dt", 0), ("RHOT_dt", 1), ("MOMZ_dt", 2), ("MOMX_dt", 3), ("MOMY_dt", 4)):
         assert rel_l2(t[nm].reshape(-1), te[iv]) <= 1e-13, nm
+
+
+@pytest.mark.parametrize("p,dims,terrain", [(7, (3, 2, 2), False), (3, (4, 3, 3), False), (7, (3, 2, 3), True)])
+def test_numpy_restatement_of_the_hevi_explicit_rows_equals_the_cpp_oracle(p, dims, terrain):
+    """The horizontally explicit part of the HEVI equation set (numflux_get_generalvc of rhot_hevi_numflux.F90, cal_tend of rhot_hevi.F90)
+    written a second time in NumPy from the Fortran, on the flat mesh and over the bell mountain, against oracle/dyn_hevi.cpp."""
+    from cases import terrain_case, terrain_oracle
+    kw = dict(eqs="NONHYDRO3D_HEVI", tinteg="IMEX_ARK232")
+    if terrain:
+        case = terrain_case(p, dims, **kw)
+        o = terrain_oracle(case)
+    else:
+        case = DensityCurrentCase(p=p, NeX=dims[0], NeY=dims[1], NeZ=dims[2], perturb=2.0, periodic=(False, True, False),
+                                  intrp_order=min(11, p + 4), **kw)
+        o = case.make_oracle()
+    for w in ("exchange", "pressure", "bc", "tend_ex"):
+        o.piece(w)
+    e, m, c = case.elem, case.mesh, case.consts
+    n, N = m.Ne * e.Np, m.NeA * e.Np
+    q = {k: o.arr(k).copy() for k in ("DDENS", "MOMX", "MOMY", "MOMZ", "DRHOT")}
+    aux = {k: o.arr(k).copy() for k in ("DENS_hyd", "PRES_hyd", "THERM_hyd")}
+    t = numpy_dyn.cal_tend_hevi(e, m, c, q, aux, o.arr("DPRES"), o.arr("DPhydDx"), o.arr("DPhydDy"))
+    te = o.arr("tend_ex")[:5 * N].reshape(5, -1)[:, :n]
+    for nm, iv in (("DENS_dt", 0), ("RHOT_dt", 1), ("MOMZ_dt", 2), ("MOMX_dt", 3), ("MOMY_dt", 4)):
+        assert rel_l2(t[nm].reshape(-1), te[iv]) <= 1e-13, nm
+    if terrain:
+        assert np.abs(m.GI3[0]).max() > 1e-3
