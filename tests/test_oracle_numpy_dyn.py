@@ -53,3 +53,26 @@ def test_numpy_restatement_of_the_hevi_explicit_rows_equals_the_cpp_oracle(p, di
         assert rel_l2(t[nm].reshape(-1), te[iv]) <= 1e-13, nm
     if terrain:
         assert np.abs(m.GI3[0]).max() > 1e-3
+
+
+@pytest.mark.parametrize("panelID", [1, 4, 5, 6])
+def test_numpy_restatement_of_the_global_hevi_explicit_rows_equals_the_cpp_oracle(panelID):
+    """numflux_get_generalhvc + the explicit tendency of GLOBALNONHYDRO3D_HEVI on one cubed-sphere panel (metric, Christoffel and Coriolis
+    terms; the Coriolis term changes form between the equatorial panels, panel 5 and panel 6), written a second time in NumPy from the
+    Fortran, against oracle/dyn_global.cpp."""
+    from cases import GlobalPanelCase
+    case = GlobalPanelCase(p=7, panelID=1, NeX=2, NeY=2, NeZ=3)
+    case.panelID = panelID
+    case.mesh.panelID = panelID        # the metric tables are functions of the panel coordinates only
+    o = case.make_oracle()
+    for w in ("exchange", "pressure", "bc", "tend_ex"):
+        o.piece(w)
+    e, m, c = case.elem, case.mesh, case.consts
+    n, N = m.Ne * e.Np, m.NeA * e.Np
+    q = {k: o.arr(k).copy() for k in ("DDENS", "MOMX", "MOMY", "MOMZ", "DRHOT")}
+    aux = {k: o.arr(k).copy() for k in ("DENS_hyd", "PRES_hyd", "THERM_hyd")}
+    t = numpy_dyn.cal_tend_hevi_global(e, m, c, q, aux, o.arr("DPRES"), o.arr("DPhydDx"), o.arr("DPhydDy"))
+    te = o.arr("tend_ex")[:5 * N].reshape(5, -1)[:, :n]
+    for nm, iv in (("DENS_dt", 0), ("RHOT_dt", 1), ("MOMZ_dt", 2), ("MOMX_dt", 3), ("MOMY_dt", 4)):
+        assert rel_l2(t[nm].reshape(-1), te[iv]) <= 1e-13, (panelID, nm)
+    assert np.abs(te[3]).max() > 0.0 and np.abs(te[4]).max() > 0.0      # contravariant momenta: tendencies of order u / R per second
