@@ -61,7 +61,8 @@ def test_numpy_restatement_of_the_global_hevi_explicit_rows_equals_the_cpp_oracl
     terms; the Coriolis term changes form between the equatorial panels, panel 5 and panel 6), written a second time in NumPy from the
     Fortran, against oracle/dyn_global.cpp."""
     from cases import GlobalPanelCase
-    case = GlobalPanelCase(p=7, panelID=1, NeX=2, NeY=2, NeZ=3)
+    # balanced = False: with the zonal flow in gradient-wind balance MOMY_dt is a 1e-12 residual of cancelling terms, nothing to compare
+    case = GlobalPanelCase(p=7, panelID=1, NeX=2, NeY=2, NeZ=3, balanced=False)
     case.panelID = panelID
     case.mesh.panelID = panelID        # the metric tables are functions of the panel coordinates only
     o = case.make_oracle()
