@@ -9,6 +9,10 @@ the Fortran, not from oracle/dyn_heve.cpp, vectorised over elements with dense t
   cal_tend_hevi  atm_dyn_dgm_nonhydro3d_rhot_hevi_cal_tend                fluid_dyn_solver/scale_atm_dyn_dgm_nonhydro3d_rhot_hevi.F90:289-482
   numflux_hevi_global    ..._rhot_hevi_numflux_get_generalhvc             fluid_dyn_solver/scale_atm_dyn_dgm_nonhydro3d_rhot_hevi_numflux.F90:606-834
   cal_tend_hevi_global   atm_dyn_dgm_globalnonhydro3d_rhot_hevi_cal_tend  fluid_dyn_solver/scale_atm_dyn_dgm_globalnonhydro3d_rhot_hevi.F90:337-583
+  cal_vi         atm_dyn_dgm_nonhydro3d_rhot_hevi_cal_vi (:772-965) with eval_Ax, eval_Ax_uv, vi_cal_del_flux_dyn(_uv), construct_matbnd(_uv)
+                 of scale_atm_dyn_dgm_nonhydro3d_rhot_hevi_common_2.F90:111-1328 -- the column systems assembled as ONE dense matrix per column
+                 and solved with numpy.linalg.solve (the reference and the C++ restatement run a block-Thomas sweep with a partial-pivot LU
+                 per element: a different algorithm for the same linear system), flat and terrain-following regional meshes
 
 Inputs are the host-side mesh / element objects of fe_project_b200 (themselves an independent restatement of the set-up code) and flat
 (NeA * Np) field arrays with the halo part filled.  tests/test_oracle_numpy_dyn.py asserts agreement with the C++ oracle to 1e-13."""
@@ -287,3 +291,152 @@ def cal_tend_hevi_global(elem, mesh, c, q, aux, DPRES, DPhydDx, DPhydDy):
     out["MOMX_dt"] = (-(G11 * gx + G12 * gy) - two * Y * (X * Y * u - (1.0 + Y ** 2) * v) * mx + cori1) + out["MOMX_dt"]
     out["MOMY_dt"] = (-(G12 * gx + G22 * gy) - two * X * (-(1.0 + X ** 2) * u + X * Y * v) * my + cori2) + out["MOMY_dt"]
     return out
+
+
+def cal_vi(elem, mesh, c, aux, cur, var0, impl_fac):
+    """One Newton iteration of the vertical-implicit step about var0 (regional mesh, dry).  cur / var0: dicts DDENS, MOMX, MOMY, MOMZ, DRHOT
+    of flat arrays (at least the Np * Ne interior values); aux: DENS_hyd, PRES_hyd.  Returns the implicit tendencies (dict, (Ne * Np,)):
+    (PROG_VARS - cur) / impl_fac, or the vertical operator itself for impl_fac = 0."""
+    n1, Nfp, Np, NeZ, Ne2D = elem.np1, elem.Nfp, elem.Np, mesh.NeZ, mesh.Ne2D
+    ni = mesh.Ne * Np
+    R4 = lambda a: np.array(np.asarray(a).reshape(-1)[:ni].reshape(NeZ, Ne2D, n1, Nfp), dtype=np.float64)    # [kz, ke2D, pv, ij]
+    names = ("DDENS", "MOMX", "MOMY", "MOMZ", "DRHOT")
+    q0 = {k: R4(var0[k]) for k in names}
+    qc = {k: R4(cur[k]) for k in names}
+    pv_ = {k: q0[k].copy() for k in names}                       # PROG_VARS, starts at var0
+    dh, ph = R4(aux["DENS_hyd"]), R4(aux["PRES_hyd"])
+    Gv = R4(mesh.Gsqrt) / mesh.GsqrtH[None, :, None, :]           # GsqrtV = Gsqrt / GsqrtH (rhot_hevi.F90:864)
+    G13, G23 = R4(mesh.GI3[0]), R4(mesh.GI3[1])
+    E33 = R4(mesh.Escale[2, 2])
+    Fs = np.asarray(mesh.Fscale).reshape(NeZ, Ne2D, 6, Nfp)[:, :, 4:6, :]     # vertical faces: [kz, ke2D, side, ij]
+    D, VP, lw = elem.D1D, elem.VPOrdM1, elem.lift1d             # lw[pv, side]
+    gamm, P00, Rd, grav = c["CPdry"] / c["CVdry"], c["PRES00"], c["Rdry"], c["GRAV"]
+    rgamm = c["CVdry"] / c["CPdry"]
+    rhot_hyd = P00 / Rd * (ph / P00) ** rgamm
+    pres_of = lambda rhot: P00 * (Rd / P00 * rhot) ** gamm
+
+    def faces(field):
+        """interior / exterior values at the bottom and top face of every element: [kz, ke2D, side, ij]; at the column ends exterior = interior."""
+        inn = np.stack([field[:, :, 0, :], field[:, :, n1 - 1, :]], axis=2)
+        ext = inn.copy()
+        ext[1:, :, 0, :] = field[:-1, :, n1 - 1, :]
+        ext[:-1, :, 1, :] = field[1:, :, 0, :]
+        return inn, ext
+    nz = np.array([-1.0, 1.0])[None, None, :, None]
+    wall = np.zeros((NeZ, 1, 2, 1), dtype=bool)
+    wall[0, 0, 0, 0] = True; wall[NeZ - 1, 0, 1, 0] = True
+    lift = lambda df: lw[None, None, :, 0, None] * df[:, :, None, 0, :] + lw[None, None, :, 1, None] * df[:, :, None, 1, :]
+    Dz = lambda f: np.einsum("pl,zelj->zepj", D, f)
+
+    # ---- dissipation coefficient of the vertical faces from var0 (vi_cal_del_flux_dyn_uv :1085-1150)
+    rdens0 = 1.0 / (dh + q0["DDENS"])
+    wt0 = (q0["MOMZ"] / Gv + G13 * q0["MOMX"] + G23 * q0["MOMY"]) * rdens0
+    a_node = np.abs(wt0) + np.sqrt((1.0 / Gv ** 2 + G13 * G13 + G23 * G23) * gamm * pres_of(rhot_hyd + q0["DRHOT"]) * rdens0)
+    aI, aE = faces(a_node)
+    alph = np.maximum(aI, aE)                                     # nz^2 = 1 on the vertical faces; the same value seen from both elements
+
+    # ---- (MOMX, MOMY): eval_Ax_uv (:546-553) and, when implicit, their own column systems (construct_matbnd_uv :940-1003)
+    t_uv = {}
+    for k in ("MOMX", "MOMY"):
+        I, E = faces(pv_[k])
+        t_uv[k] = -lift(-0.5 * Fs * alph * (E - I)) / Gv
+    if impl_fac != 0.0:
+        for k in ("MOMX", "MOMY"):
+            b = impl_fac * t_uv[k] - pv_[k] + qc[k]
+            for e2 in range(Ne2D):
+                for ij in range(Nfp):
+                    A = np.eye(NeZ * n1)
+                    for kz in range(NeZ):
+                        for side, (nb, pv1, pvn) in enumerate(((kz - 1, 0, n1 - 1), (kz + 1, n1 - 1, 0))):
+                            if nb < 0 or nb >= NeZ:
+                                continue
+                            t1 = 0.5 * impl_fac / Gv[kz, e2, :, ij] * lw[:, side] * Fs[kz, e2, side, ij] * alph[kz, e2, side, ij]
+                            A[kz * n1:(kz + 1) * n1, kz * n1 + pv1] += t1
+                            A[kz * n1:(kz + 1) * n1, nb * n1 + pvn] += -t1
+                    pv_[k][:, e2, :, ij] += np.linalg.solve(A, b[:, e2, :, ij].reshape(-1)).reshape(NeZ, n1)
+
+    # ---- eval_Ax (:224-262) + vi_cal_del_flux_dyn (:1262-1322) on PROG_VARS (the horizontal momenta already updated)
+    mw = pv_["MOMZ"] + Gv * G13 * pv_["MOMX"] + Gv * G23 * pv_["MOMY"]
+    dens = pv_["DDENS"] + dh
+    rhot = rhot_hyd + pv_["DRHOT"]
+    pot = rhot / dens
+    dpres_face = pres_of(dens * pot) - ph
+    mwI, mwE = faces(mw); mzI, mzE = faces(pv_["MOMZ"]); ddI, ddE = faces(pv_["DDENS"]); drI, drE = faces(pv_["DRHOT"])
+    ptI, ptE = faces(pot); dpI, dpE = faces(dpres_face)
+    gvI, _ = faces(Gv); g13I, _ = faces(G13); g23I, _ = faces(G23); mxI, _ = faces(pv_["MOMX"]); myI, _ = faces(pv_["MOMY"])
+    mzE = np.where(wall, -mzI - 2.0 * gvI * (g13I * mxI + g23I * myI), mzE)       # slip wall (:1292-1302)
+    mwE = np.where(wall, -mwI, mwE)
+    hf = 0.5 * Fs
+    df_d = hf * ((mwE - mwI) * nz - alph * (ddE - ddI))
+    df_w = hf * ((dpE - dpI) * nz - alph * (mzE - mzI))
+    df_t = hf * ((ptE * mwE - ptI * mwI) * nz - alph * (drE - drI))
+    t_d = -(E33 * Dz(mw) + lift(df_d)) / Gv
+    t_t = -(E33 * Dz(pot * mw) + lift(df_t)) / Gv
+    t_w = -(E33 * Dz(pres_of(rhot) - ph) + lift(df_w)) / Gv - grav * np.einsum("pl,zelj->zepj", VP, pv_["DDENS"])
+    out = {}
+    if impl_fac == 0.0:
+        res = {"DDENS": t_d, "MOMZ": t_w, "DRHOT": t_t, "MOMX": t_uv["MOMX"], "MOMY": t_uv["MOMY"]}
+        return {k: v.reshape(-1) for k, v in res.items()}
+
+    # ---- the Newton system of a column as ONE dense matrix: unknown index (kz, pv, var), var = DDENS, MOMZ, DRHOT (construct_matbnd :750-871)
+    wt = mw / dens
+    dpd = gamm * pres_of(rhot) / rhot
+    b3 = {"DDENS": impl_fac * t_d - pv_["DDENS"] + qc["DDENS"], "MOMZ": impl_fac * t_w - pv_["MOMZ"] + qc["MOMZ"],
+          "DRHOT": impl_fac * t_t - pv_["DRHOT"] + qc["DRHOT"]}
+    nb3 = 3 * n1
+    for e2 in range(Ne2D):
+        for ij in range(Nfp):
+            A = np.zeros((NeZ * nb3, NeZ * nb3))
+            rhs = np.zeros(NeZ * nb3)
+            ix = lambda kz, pv, v: kz * nb3 + 3 * pv + v
+            for kz in range(NeZ):
+                gv, po, wT, dp_ = Gv[kz, e2, :, ij], pot[kz, e2, :, ij], wt[kz, e2, :, ij], dpd[kz, e2, :, ij]
+                fdz = (E33[kz, e2, :, ij] / gv)[:, None] * (impl_fac * D)                     # [pv, pv2]
+                for pv in range(n1):
+                    for v, nm in enumerate(("DDENS", "MOMZ", "DRHOT")):
+                        rhs[ix(kz, pv, v)] = b3[nm][kz, e2, pv, ij]
+                    for p2 in range(n1):
+                        idn = 1.0 if pv == p2 else 0.0
+                        A[ix(kz, pv, 0), ix(kz, p2, 0)] += idn
+                        A[ix(kz, pv, 0), ix(kz, p2, 1)] += fdz[pv, p2]
+                        A[ix(kz, pv, 1), ix(kz, p2, 1)] += idn
+                        A[ix(kz, pv, 1), ix(kz, p2, 0)] += impl_fac * grav * VP[pv, p2]
+                        A[ix(kz, pv, 1), ix(kz, p2, 2)] += fdz[pv, p2] * dp_[p2]
+                        A[ix(kz, pv, 2), ix(kz, p2, 0)] += -fdz[pv, p2] * po[p2] * wT[p2]
+                        A[ix(kz, pv, 2), ix(kz, p2, 1)] += fdz[pv, p2] * po[p2]
+                        A[ix(kz, pv, 2), ix(kz, p2, 2)] += idn + fdz[pv, p2] * wT[p2]
+                for side, (nbz, pv1, pvn) in enumerate(((kz - 1, 0, n1 - 1), (kz + 1, n1 - 1, 0))):
+                    fac = 0.5 * impl_fac / gv * lw[:, side] * Fs[kz, e2, side, ij]             # [pv]
+                    t1 = fac * alph[kz, e2, side, ij]
+                    t2 = fac * (-1.0 if side == 0 else 1.0)
+                    for pv in range(n1):
+                        r0, r1, r2 = ix(kz, pv, 0), ix(kz, pv, 1), ix(kz, pv, 2)
+                        c0, c1, c2 = ix(kz, pv1, 0), ix(kz, pv1, 1), ix(kz, pv1, 2)
+                        if nbz < 0 or nbz >= NeZ:                                             # slip wall
+                            A[r2, c0] += 2.0 * t2[pv] * po[pv1] * wT[pv1]
+                            A[r0, c1] += -2.0 * t2[pv]
+                            A[r1, c1] += 2.0 * t1[pv]
+                            A[r2, c1] += -2.0 * t2[pv] * po[pv1]
+                            A[r2, c2] += -2.0 * t2[pv] * wT[pv1]
+                        else:
+                            A[r0, c0] += t1[pv]
+                            A[r2, c0] += t2[pv] * po[pv1] * wT[pv1]
+                            A[r0, c1] += -t2[pv]
+                            A[r1, c1] += t1[pv]
+                            A[r2, c1] += -t2[pv] * po[pv1]
+                            A[r1, c2] += -t2[pv] * dp_[pv1]
+                            A[r2, c2] += t1[pv] - t2[pv] * wT[pv1]
+                            pn, wn, dn = pot[nbz, e2, pvn, ij], wt[nbz, e2, pvn, ij], dpd[nbz, e2, pvn, ij]
+                            n0_, n1_, n2_ = ix(nbz, pvn, 0), ix(nbz, pvn, 1), ix(nbz, pvn, 2)
+                            A[r0, n0_] += -t1[pv]
+                            A[r2, n0_] += -t2[pv] * pn * wn
+                            A[r0, n1_] += t2[pv]
+                            A[r1, n1_] += -t1[pv]
+                            A[r2, n1_] += t2[pv] * pn
+                            A[r1, n2_] += t2[pv] * dn
+                            A[r2, n2_] += -t1[pv] + t2[pv] * wn
+            x = np.linalg.solve(A, rhs).reshape(NeZ, n1, 3)
+            pv_["DDENS"][:, e2, :, ij] += x[:, :, 0]
+            pv_["MOMZ"][:, e2, :, ij] += x[:, :, 1]
+            pv_["DRHOT"][:, e2, :, ij] += x[:, :, 2]
+    return {k: ((pv_[k] - qc[k]) / impl_fac).reshape(-1) for k in names}

@@ -77,3 +77,39 @@ def test_numpy_restatement_of_the_global_hevi_explicit_rows_equals_the_cpp_oracl
     for nm, iv in (("DENS_dt", 0), ("RHOT_dt", 1), ("MOMZ_dt", 2), ("MOMX_dt", 3), ("MOMY_dt", 4)):
         assert rel_l2(t[nm].reshape(-1), te[iv]) <= 1e-13, (panelID, nm)
     assert np.abs(te[3]).max() > 0.0 and np.abs(te[4]).max() > 0.0      # contravariant momenta: tendencies of order u / R per second
+
+
+@pytest.mark.parametrize("terrain", [False, True])
+@pytest.mark.parametrize("impl_fac", [0.0, 0.1])
+def test_numpy_restatement_of_cal_vi_equals_the_cpp_oracle(impl_fac, terrain):
+    """The vertical-implicit Newton step written a second time from the Fortran, with a different solver: the whole column (NeZ elements x
+    8 nodes x 3 variables) as ONE dense system handed to numpy.linalg.solve, where the reference and oracle/dyn_hevi.cpp run a block-Thomas
+    sweep with a partial-pivot LU per element.  Flat mesh and bell mountain (GsqrtV, G13, G23, the (MOMX, MOMY) pre-solve feeding the
+    vertical mass flux): the pin of the terrain-following HEVI row."""
+    from cases import terrain_case, terrain_oracle
+    kw = dict(eqs="NONHYDRO3D_HEVI", tinteg="IMEX_ARK232")
+    if terrain:
+        case = terrain_case(7, (2, 2, 3), **kw)
+        o = terrain_oracle(case)
+    else:
+        case = DensityCurrentCase(p=7, NeX=2, NeY=2, NeZ=3, perturb=2.0, periodic=(False, True, False), **kw)
+        o = case.make_oracle()
+    e, m, c = case.elem, case.mesh, case.consts
+    n = m.Ne * e.Np
+    ORD = ("DDENS", "DRHOT", "MOMZ", "MOMX", "MOMY")            # the oracle's variable order
+    cur = {k: o.arr(k).copy() for k in ORD}
+    rng = np.random.default_rng(4)
+    var0 = np.stack([o.arr(k).copy() for k in ORD])
+    if impl_fac != 0.0:
+        var0[:, :n] += 1e-3 * rng.standard_normal((5, n)) * np.abs(var0[:, :n]).max(axis=1, keepdims=True)
+    ref = o.cal_vi(impl_fac, case.dt, var0)[:, :n]
+    aux = {k: o.arr(k).copy() for k in ("DENS_hyd", "PRES_hyd")}
+    got = numpy_dyn.cal_vi(e, m, c, aux, cur, {k: var0[i] for i, k in enumerate(ORD)}, impl_fac)
+    for i, k in enumerate(ORD):
+        if impl_fac == 0.0:
+            # MOMZ_dt is the residual of the near-cancelling -dDPRES/dz and -g drho: 1e-12 of the terms is 1e-11 of their difference
+            assert rel_l2(got[k], ref[i]) <= (1e-11 if k == "MOMZ" else 1e-12), (k, terrain)
+        else:       # compare the Newton iterate (the tendency cancels to round-off where the vertical operator is inactive)
+            qs_ref, qs_got = cur[k][:n] + impl_fac * ref[i], cur[k][:n] + impl_fac * got[k]
+            assert rel_l2(qs_got, qs_ref) <= 1e-11, (k, terrain)
+            assert np.abs(got[k] - ref[i]).max() <= 1e-10 * max(np.abs(var0[i]).max(), np.abs(ref[i]).max()) / impl_fac, (k, terrain)
