@@ -113,3 +113,25 @@ def test_numpy_restatement_of_cal_vi_equals_the_cpp_oracle(impl_fac, terrain):
             qs_ref, qs_got = cur[k][:n] + impl_fac * ref[i], cur[k][:n] + impl_fac * got[k]
             assert rel_l2(qs_got, qs_ref) <= 1e-11, (k, terrain)
             assert np.abs(got[k] - ref[i]).max() <= 1e-10 * max(np.abs(var0[i]).max(), np.abs(ref[i]).max()) / impl_fac, (k, terrain)
+
+
+def test_numpy_cal_vi_on_a_cubed_sphere_panel():
+    """The global twin of cal_vi (globalnonhydro3d_rhot_hevi.F90:873-1066) is the regional column solve with GsqrtV = Gsqrt / (gam^2 GsqrtH)
+    (= 1 in the shallow atmosphere without topography): the NumPy restatement on a panel mesh against the oracle."""
+    from cases import GlobalPanelCase
+    case = GlobalPanelCase(p=7, panelID=1, NeX=2, NeY=2, NeZ=3, balanced=False)
+    o = case.make_oracle()
+    e, m, c = case.elem, case.mesh, case.consts
+    n = m.Ne * e.Np
+    ORD = ("DDENS", "DRHOT", "MOMZ", "MOMX", "MOMY")
+    cur = {k: o.arr(k).copy() for k in ORD}
+    rng = np.random.default_rng(5)
+    var0 = np.stack([o.arr(k).copy() for k in ORD])
+    var0[:, :n] += 1e-3 * rng.standard_normal((5, n)) * np.abs(var0[:, :n]).max(axis=1, keepdims=True)
+    impl_fac = 5.0
+    ref = o.cal_vi(impl_fac, case.dt, var0)[:, :n]
+    aux = {k: o.arr(k).copy() for k in ("DENS_hyd", "PRES_hyd")}
+    got = numpy_dyn.cal_vi(e, m, c, aux, cur, {k: var0[i] for i, k in enumerate(ORD)}, impl_fac)
+    for i, k in enumerate(ORD):
+        qs_ref, qs_got = cur[k][:n] + impl_fac * ref[i], cur[k][:n] + impl_fac * got[k]
+        assert rel_l2(qs_got, qs_ref) <= 1e-11, k
