@@ -4,11 +4,16 @@ the Fortran, not from oracle/dyn_heve.cpp, vectorised over elements with dense t
   numflux_heve   atm_dyn_dgm_nonhydro3d_rhot_heve_numflux_get_generalvc   fluid_dyn_solver/scale_atm_dyn_dgm_nonhydro3d_rhot_heve_numflux.F90:946-1138
   cal_tend_heve  atm_dyn_dgm_nonhydro3d_rhot_heve_cal_tend                fluid_dyn_solver/scale_atm_dyn_dgm_nonhydro3d_rhot_heve.F90:292-489
   drhot2pres     atm_dyn_dgm_nonhydro3d_common_DRHOT2PRES                 fluid_dyn_solver/scale_atm_dyn_dgm_nonhydro3d_common.F90:428-479
-  apply_bc       AtmDynBnd%ApplyBC_PROGVARS_lc (SLIP / NOSLIP, flat)      fluid_dyn_solver/scale_atm_dyn_dgm_bnd.F90:270-367
   numflux_hevi   atm_dyn_dgm_nonhydro3d_rhot_hevi_numflux_get_generalvc   fluid_dyn_solver/scale_atm_dyn_dgm_nonhydro3d_rhot_hevi_numflux.F90:232-416
   cal_tend_hevi  atm_dyn_dgm_nonhydro3d_rhot_hevi_cal_tend                fluid_dyn_solver/scale_atm_dyn_dgm_nonhydro3d_rhot_hevi.F90:289-482
   numflux_hevi_global    ..._rhot_hevi_numflux_get_generalhvc             fluid_dyn_solver/scale_atm_dyn_dgm_nonhydro3d_rhot_hevi_numflux.F90:606-834
   cal_tend_hevi_global   atm_dyn_dgm_globalnonhydro3d_rhot_hevi_cal_tend  fluid_dyn_solver/scale_atm_dyn_dgm_globalnonhydro3d_rhot_hevi.F90:337-583
+  apply_bc       AtmDynBnd%ApplyBC_PROGVARS_lc (slip / no-slip walls, regional mesh incl. the terrain-following metric)
+                                                                          fluid_dyn_solver/scale_atm_dyn_dgm_bnd.F90:270-367
+  modal_filter   atm_dyn_dgm_modalfilter_apply                            fluid_dyn_solver/scale_atm_dyn_dgm_modalfilter.F90:49-130
+  update         AtmDynDGMDriver_nonhydro3d%Update, the stage loop        fluid_dyn_solver/scale_atm_dyn_dgm_driver_nonhydro3d.F90:614-963
+                 with the Runge-Kutta stages in their Butcher form (the reference and the C++ restatement use the low-storage / one-buffer
+                 forms of scale_timeint_rk.F90: the same numbers up to round-off)
   cal_vi         atm_dyn_dgm_nonhydro3d_rhot_hevi_cal_vi (:772-965) with eval_Ax, eval_Ax_uv, vi_cal_del_flux_dyn(_uv), construct_matbnd(_uv)
                  of scale_atm_dyn_dgm_nonhydro3d_rhot_hevi_common_2.F90:111-1328 -- the column systems assembled as ONE dense matrix per column
                  and solved with numpy.linalg.solve (the reference and the C++ restatement run a block-Thomas sweep with a partial-pivot LU
@@ -440,3 +445,86 @@ def cal_vi(elem, mesh, c, aux, cur, var0, impl_fac):
             pv_["MOMZ"][:, e2, :, ij] += x[:, :, 1]
             pv_["DRHOT"][:, e2, :, ij] += x[:, :, 2]
     return {k: ((pv_[k] - qc[k]) / impl_fac).reshape(-1) for k in names}
+
+
+PROG = ("DDENS", "MOMX", "MOMY", "MOMZ", "DRHOT")
+
+
+def apply_bc(elem, mesh, q, bc6):
+    """ApplyBC_PROGVARS_lc (bnd.F90:326-362): the halo slots of a physical boundary get the mirrored (SLIP = 2) or negated (NOSLIP = 3)
+    momentum of the interior face node; regional mesh (G11 = G22 = 1, G12 = 0), terrain-following metric included.  bc6: boundary id per
+    tile face (mesh.halo_bc_types); q: dict of flat arrays incl. halo, modified in place."""
+    iM, iP = mesh.VMapM.reshape(-1), mesh.VMapP.reshape(-1)
+    nx, ny, nz = (a.reshape(-1) for a in mesh.normal_fn)
+    nint = mesh.Ne * elem.Np
+    slot = iP - nint
+    on = slot >= 0
+    face_of_slot = np.searchsorted(np.cumsum(mesh.halo_face_size), np.maximum(slot, 0), side="right")
+    bc = np.where(on, np.asarray(bc6)[np.minimum(face_of_slot, 5)], 0)
+    G = mesh.Gsqrt.reshape(-1)
+    G13, G23 = mesh.GI3[0].reshape(-1), mesh.GI3[1].reshape(-1)
+    ke2d = np.repeat(mesh.EMap3Dto2D, elem.NfpTot)
+    h2 = (iM % elem.Np) % elem.Nfp
+    sl = bc == 2
+    m_, p_ = iM[sl], iP[sl]
+    Gv = G[m_] / mesh.GsqrtH[ke2d[sl], h2[sl]]
+    momw = q["MOMZ"][m_] / Gv + G13[m_] * q["MOMX"][m_] + G23[m_] * q["MOMY"][m_]
+    fac = nz[sl] * Gv ** 2 / (1.0 + (Gv * G13[m_]) ** 2 + (Gv * G23[m_]) ** 2)
+    mn = q["MOMX"][m_] * nx[sl] + q["MOMY"][m_] * ny[sl] + momw * nz[sl]
+    q["MOMX"][p_] = q["MOMX"][m_] - 2.0 * mn * (nx[sl] + fac * G13[m_])
+    q["MOMY"][p_] = q["MOMY"][m_] - 2.0 * mn * (ny[sl] + fac * G23[m_])
+    q["MOMZ"][p_] = q["MOMZ"][m_] - 2.0 * mn * fac / Gv
+    ns = bc == 3
+    for k in ("MOMX", "MOMY", "MOMZ"):
+        q[k][iP[ns]] = -q[k][iM[ns]]
+
+
+def modal_filter(elem, mesh, q, Fh, Fv):
+    """q <- F3D(Gsqrt q) / Gsqrt with the 1D filter matrices Fh (x, y) and Fv (z) (modalfilter.F90:49-130), interior elements."""
+    Ne, n = mesh.Ne, elem.np1
+    ni = Ne * elem.Np
+    G = mesh.Gsqrt.reshape(-1)[:ni].reshape(Ne, n, n, n)
+    for k in PROG:
+        a = q[k][:ni].reshape(Ne, n, n, n) * G                     # [ke, k, j, i]
+        a = np.einsum("il,ekjl->ekji", Fh, a)
+        a = np.einsum("jl,ekli->ekji", Fh, a)
+        a = np.einsum("kl,elji->ekji", Fv, a)
+        q[k][:ni] = (a / G).reshape(-1)
+
+
+def update(elem, mesh, c, q, aux, rk, dt, bc6, hevi=False, filt=None, nsteps=1, DPhydDx=None, DPhydDy=None):
+    """nsteps dynamics steps of the regional dry model (driver_nonhydro3d.F90:703-951), q: dict of the five prognostic variables, flat
+    arrays incl. halo, advanced in place.  rk: Butcher tables (oracle_api.rk_tables); filt: (Fh, Fv) or None; DPhydDx / DPhydDy: the
+    horizontal gradient of the background pressure (set-up product; non-zero over topography).  Per stage: [HEVI: cal_vi about
+    the state at the start of the step, StoreImplicit], halo exchange, pressure, boundary condition, explicit tendency, then the stage
+    combination  q = q0 + dt sum_j (a_ex(s+1, j) k_ex_j + a_im(s+1, j) k_im_j)  (the weights b for the last stage)."""
+    ns = rk["nstage"]
+    ni = mesh.Ne * elem.Np
+    R, cv, cp = (np.full(mesh.NeA * elem.Np, c[k]) for k in ("Rdry", "CVdry", "CPdry"))
+    for _ in range(nsteps):
+        q0 = {k: q[k][:ni].copy() for k in PROG}
+        kex, kim = [], []
+        for st in range(ns):
+            if hevi:
+                t = cal_vi(elem, mesh, c, aux, q, q0, rk["a_im"][st, st] * dt)
+                kim.append(t)
+                for k in PROG:
+                    q[k][:ni] = q[k][:ni] + rk["a_im"][st, st] * dt * t[k]
+            for k in PROG:
+                mesh.exchange_halo_numpy(q[k])
+            _, dpres = drhot2pres(c, q["DRHOT"], aux["PRES_hyd"], aux["THERM_hyd"], R, cv, cp)
+            mesh.exchange_halo_numpy(dpres)
+            apply_bc(elem, mesh, q, bc6)
+            t = (cal_tend_hevi if hevi else cal_tend_heve)(elem, mesh, c, q, aux, dpres, DPhydDx, DPhydDy)
+            kex.append({"DDENS": t["DENS_dt"].reshape(-1), "MOMX": t["MOMX_dt"].reshape(-1), "MOMY": t["MOMY_dt"].reshape(-1),
+                        "MOMZ": t["MOMZ_dt"].reshape(-1), "DRHOT": t["RHOT_dt"].reshape(-1)})
+            last = st == ns - 1
+            for k in PROG:
+                acc = q0[k].copy()
+                for j in range(st + 1):
+                    acc = acc + dt * (rk["b_ex"][j] if last else rk["a_ex"][st + 1, j]) * kex[j][k]
+                    if hevi:
+                        acc = acc + dt * (rk["b_im"][j] if last else rk["a_im"][st + 1, j]) * kim[j][k]
+                q[k][:ni] = acc
+        if filt is not None:
+            modal_filter(elem, mesh, q, *filt)

@@ -135,3 +135,36 @@ def test_numpy_cal_vi_on_a_cubed_sphere_panel():
     for i, k in enumerate(ORD):
         qs_ref, qs_got = cur[k][:n] + impl_fac * ref[i], cur[k][:n] + impl_fac * got[k]
         assert rel_l2(qs_got, qs_ref) <= 1e-11, k
+
+
+@pytest.mark.parametrize("eqs,tinteg,dt,terrain,mf", [("NONHYDRO3D_HEVE", "ERK_SSP_4s3o", 0.05, False, True),
+                                                       ("NONHYDRO3D_HEVE", "ERK_SSP_3s3o", 0.05, True, False),
+                                                       ("NONHYDRO3D_HEVI", "IMEX_ARK232", 0.2, False, True),
+                                                       ("NONHYDRO3D_HEVI", "IMEX_ARK324", 0.2, True, False)])
+def test_numpy_restatement_of_the_full_step_equals_the_cpp_oracle(eqs, tinteg, dt, terrain, mf):
+    """The whole dynamics step a second time in NumPy: stage loop in Butcher form, halo exchange, pressure, slip-wall boundary
+    condition (with the terrain-following metric), explicit tendency, vertical-implicit Newton step as a dense column solve, modal
+    filter -- three steps against the C++ oracle's driver (low-storage / one-buffer Runge-Kutta forms, block-Thomas + LU)."""
+    import oracle_api
+    from cases import terrain_case, terrain_oracle
+    kw = dict(eqs=eqs, tinteg=tinteg, dt=dt, modalfilter=mf)
+    if terrain:
+        case = terrain_case(7, (2, 2, 3), **kw)
+        o = terrain_oracle(case)
+    else:
+        case = DensityCurrentCase(p=7, NeX=2, NeY=2, NeZ=3, perturb=2.0, periodic=(False, True, False), **kw)
+        o = case.make_oracle()
+    e, m, c = case.elem, case.mesh, case.consts
+    n = m.Ne * e.Np
+    q = {k: o.arr(k).copy() for k in numpy_dyn.PROG}
+    aux = {k: o.arr(k).copy() for k in ("DENS_hyd", "PRES_hyd", "THERM_hyd")}
+    filt = None
+    if mf:
+        from cases import MF
+        filt = (e.filter1d(MF["MF_ETAC_h"], MF["MF_ALPHA_h"], MF["MF_ORDER_h"]), e.filter1d(MF["MF_ETAC_v"], MF["MF_ALPHA_v"], MF["MF_ORDER_v"]))
+    bc6 = m.halo_bc_types({k: 2 for k in ("south", "east", "north", "west", "btm", "top")})
+    numpy_dyn.update(e, m, c, q, aux, oracle_api.rk_tables(tinteg), dt, bc6, hevi=eqs.endswith("HEVI"), filt=filt, nsteps=3,
+                     DPhydDx=o.arr("DPhydDx").copy(), DPhydDy=o.arr("DPhydDy").copy())
+    o.update(3)
+    for k in numpy_dyn.PROG:
+        assert rel_l2(q[k][:n], o.arr(k)[:n]) <= 1e-11, (k, eqs, terrain)
