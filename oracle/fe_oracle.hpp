@@ -7,10 +7,15 @@
 // compiled in this environment (no Fortran compiler, SCALE library not vendored), so this oracle
 // is pinned by (i) the reference's own known-answer unit tests restated in tests/ (element
 // operators on 4x^p+3y^p+2z^p, sparse-matrix 5x5 case, Butcher tableaux of SSP3s3o/SSP4s3o, RK
-// convergence orders, halo fill pattern) and (ii) an independent NumPy restatement of the set-up
-// code.  Numerical flux, tendency assembly, pressure, boundary conditions, the vertical-implicit
-// solver and the full step have NO golden vectors in the reference: for those rows parity is
-// UNPINNED beyond this restatement ("Oracle").
+// convergence orders, halo fill pattern, VMapM / VMapP and halo sources in closed form, LGL points) and
+// (ii) independent NumPy restatements: of the set-up code (fe_project_b200/element.py, mesh.py,
+// cubedsphere.py) and, since round 2, of the dynamics rows themselves (oracle/numpy_dyn.py: pressure,
+// flux + tendency of HEVE / HEVI / global HEVI, boundary condition, modal filter, the vertical-implicit
+// Newton step as a dense column solve, the whole step; tests/test_oracle_numpy_dyn.py: agreement to
+// round-off, flat and terrain-following).  Numerical flux, tendency assembly, pressure, boundary
+// conditions, the vertical-implicit solver and the full step have NO golden vectors in the reference:
+// for those rows parity is UNPINNED BY REFERENCE VECTORS -- two restatements written from the same
+// Fortran agree, nothing the reference itself produced was compared ("Oracle").
 //
 // Every function cites the reference file:line it restates.  Paths are relative to
 // /root/reference/FElib/src unless stated otherwise.
