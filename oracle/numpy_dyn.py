@@ -205,8 +205,10 @@ def _face_h2d(elem, mesh):
     return mesh.EMap3Dto2D[:, None], (mesh.VMapM % elem.Np) % elem.Nfp
 
 
-def numflux_hevi_global(elem, mesh, c, q, aux, DPRES):
-    """numflux_get_generalhvc (rhot_hevi_numflux.F90:702-830) on a cubed-sphere panel: the horizontal metric G11 / G12 / G22 and GsqrtH
+def numflux_hevi_global(elem, mesh, c, q, aux, DPRES, hevi=True):
+    """hevi = False: numflux_get_generalhvc of the HEVE set (rhot_heve_numflux.F90:1620-1770): full normal velocity for mass and theta, no
+    swV factor, vertical pressure jump in MOMZ.
+    numflux_get_generalhvc (rhot_hevi_numflux.F90:702-830) on a cubed-sphere panel: the horizontal metric G11 / G12 / G22 and GsqrtH
     of the OWN element's 2D node on both sides (iM2Dto3D), rgam2 = 1 / gam^2, Gnn with the metric of the face direction."""
     iM, iP = mesh.VMapM, mesh.VMapP
     nx, ny, nz = mesh.normal_fn
@@ -237,15 +239,17 @@ def numflux_hevi_global(elem, mesh, c, q, aux, DPRES):
         s["Gnn"] = rgam2 * (np.abs(G11 * nx) + np.abs(G22 * ny)) + (1.0 * s["RGv"] ** 2 + s["G13"] * s["Gxz"] + s["G23"] * s["Gyz"]) * np.abs(nz)
         side[tag] = s
     I, E = side["IN"], side["EX"]
-    swV = 1.0 - nz ** 2
+    swV = (1.0 - nz ** 2) if hevi else 1.0
     alpha = swV * np.maximum(np.sqrt(I["Gnn"] * gamm * (I["Phyd"] + I["dp"]) * I["Gs"] / I["Dens"]) + np.abs(I["Vel"]),
                              np.sqrt(E["Gnn"] * gamm * (E["Phyd"] + E["dp"]) * E["Gs"] / E["Dens"]) + np.abs(E["Vel"]))
     hf = mesh.Fscale * 0.5
-    out = {}
-    out["DENS"] = hf * (E["Dens"] * E["Velh"] - I["Dens"] * I["Velh"] + (-alpha * (E["DDENS"] - I["DDENS"])))
-    out["RHOT"] = hf * (E["Rhot"] * E["Velh"] - I["Rhot"] * I["Velh"] + (-alpha * (E["DRHOT"] - I["DRHOT"])))
-    out["MOMZ"] = hf * (E["MOMZ"] * E["Vel"] - I["MOMZ"] * I["Vel"] + (-alpha * (E["MOMZ"] - I["MOMZ"])))
+    vm = "Velh" if hevi else "Vel"
     t3, t4 = E["Gs"] * E["dp"], I["Gs"] * I["dp"]
+    pz = 0.0 if hevi else (t3 * E["RGv"] - t4 * I["RGv"]) * nz
+    out = {}
+    out["DENS"] = hf * (E["Dens"] * E[vm] - I["Dens"] * I[vm] + (-alpha * (E["DDENS"] - I["DDENS"])))
+    out["RHOT"] = hf * (E["Rhot"] * E[vm] - I["Rhot"] * I[vm] + (-alpha * (E["DRHOT"] - I["DRHOT"])))
+    out["MOMZ"] = hf * (E["MOMZ"] * E["Vel"] - I["MOMZ"] * I["Vel"] + pz + (-alpha * (E["MOMZ"] - I["MOMZ"])))
     mom1 = (E["G1n"] + E["Gxz"] * nz) * t3 - (I["G1n"] + I["Gxz"] * nz) * t4
     mom2 = (E["G2n"] + E["Gyz"] * nz) * t3 - (I["G2n"] + I["Gyz"] * nz) * t4
     out["MOMX"] = hf * (E["MOMX"] * E["Vel"] - I["MOMX"] * I["Vel"] + mom1 + (-alpha * (E["MOMX"] - I["MOMX"])))
@@ -253,13 +257,16 @@ def numflux_hevi_global(elem, mesh, c, q, aux, DPRES):
     return out
 
 
-def cal_tend_hevi_global(elem, mesh, c, q, aux, DPRES, DPhydDx, DPhydDy):
-    """Horizontally explicit tendency of GLOBALNONHYDRO3D_HEVI on one panel (globalnonhydro3d_rhot_hevi.F90:421-578): contravariant
+def cal_tend_hevi_global(elem, mesh, c, q, aux, DPRES, DPhydDx, DPhydDy, hevi=True):
+    """hevi = False: the full tendency of GLOBALNONHYDRO3D_HEVE in the shallow-atmosphere approximation
+    (globalnonhydro3d_rhot_heve.F90:338-600, cal_tend_shallow_atm): vertical mass / theta fluxes, vertical pressure gradient and buoyancy
+    included.
+    Horizontally explicit tendency of GLOBALNONHYDRO3D_HEVI on one panel (globalnonhydro3d_rhot_hevi.F90:421-578): contravariant
     pressure-gradient terms G11 / G12 / G22, the Christoffel terms of the equiangular gnomonic map and the Coriolis term (sign s = -1 on
     panel 6, the factor s Y on the equatorial panels)."""
     Ne, Np = mesh.Ne, elem.Np
     ni = Ne * Np
-    dfl = numflux_hevi_global(elem, mesh, c, q, aux, DPRES)
+    dfl = numflux_hevi_global(elem, mesh, c, q, aux, DPRES, hevi)
     sh = lambda a: np.asarray(a).reshape(-1)[:ni].reshape(Ne, Np)
     to3 = lambda a2: a2[mesh.EMap3Dto2D][:, elem.IndexH2Dto3D]              # (Ne2D, Nfp) -> (Ne, Np)
     G = sh(mesh.Gsqrt)
@@ -275,16 +282,19 @@ def cal_tend_hevi_global(elem, mesh, c, q, aux, DPRES, DPhydDx, DPhydDy):
     pt = (sh(aux["THERM_hyd"]) + dr) * RD
     w, u, v = mz * RD, mx * RD, my * RD
     zero = np.zeros_like(G)
-    F = {"DENS": (Fd[0], Fd[1], zero), "RHOT": (Fd[0] * pt, Fd[1] * pt, zero),
-         "MOMZ": (Fd[0] * w, Fd[1] * w, Fd[2] * w),
+    F = {"DENS": (Fd[0], Fd[1], zero if hevi else Fd[2]), "RHOT": (Fd[0] * pt, Fd[1] * pt, zero if hevi else Fd[2] * pt),
+         "MOMZ": (Fd[0] * w, Fd[1] * w, Fd[2] * w if hevi else Fd[2] * w + G * RGv * sh(DPRES)),
          "MOMX": (Fd[0] * u + G11 * gdp, Fd[1] * u + G12 * gdp, Fd[2] * u + gdp * (G11 * GI1 + G12 * GI2)),
          "MOMY": (Fd[0] * v + G12 * gdp, Fd[1] * v + G22 * gdp, Fd[2] * v + gdp * (G12 * GI1 + G22 * GI2))}
     E11, E22, E33 = mesh.Escale[0, 0], mesh.Escale[1, 1], mesh.Escale[2, 2]
     out = {}
     for nm in ("DENS", "RHOT", "MOMZ", "MOMX", "MOMY"):
         dx, dy, dz, lift = _div_lift(elem, *F[nm], dfl[nm], Ne)
-        vert = 0.0 if nm in ("DENS", "RHOT") else E33 * dz
+        vert = 0.0 if (hevi and nm in ("DENS", "RHOT")) else E33 * dz
         out[nm + "_dt"] = -(E11 * dx + E22 * dy + vert + lift) * RG
+    if not hevi:
+        n = elem.np1
+        out["MOMZ_dt"] = out["MOMZ_dt"] - c["GRAV"] * np.einsum("kl,elji->ekji", elem.VPOrdM1, dd.reshape(Ne, n, n, n)).reshape(Ne, Np)
     X, Y = to3(np.tan(mesh.pos2D[0])), to3(np.tan(mesh.pos2D[1]))
     two = 2.0 / (1.0 + X ** 2 + Y ** 2)
     sgn = -1.0 if mesh.panelID == 6 else 1.0

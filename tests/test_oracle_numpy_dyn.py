@@ -168,3 +168,25 @@ def test_numpy_restatement_of_the_full_step_equals_the_cpp_oracle(eqs, tinteg, d
     o.update(3)
     for k in numpy_dyn.PROG:
         assert rel_l2(q[k][:n], o.arr(k)[:n]) <= 1e-11, (k, eqs, terrain)
+
+
+@pytest.mark.parametrize("panelID", [2, 5, 6])
+def test_numpy_restatement_of_the_global_heve_rows_equals_the_cpp_oracle(panelID):
+    """GLOBALNONHYDRO3D_HEVE, shallow atmosphere: numflux_get_generalhvc of the HEVE set + cal_tend_shallow_atm in NumPy against
+    oracle/dyn_global.cpp."""
+    from cases import GlobalPanelCase
+    case = GlobalPanelCase(p=7, panelID=1, NeX=2, NeY=2, NeZ=3, balanced=False, eqs="GLOBALNONHYDRO3D_HEVE", tinteg="ERK_SSP_4s3o", dt=0.5)
+    case.panelID = panelID
+    case.mesh.panelID = panelID
+    o = case.make_oracle()
+    for w in ("exchange", "pressure", "bc", "tend_ex"):
+        o.piece(w)
+    e, m, c = case.elem, case.mesh, case.consts
+    n, N = m.Ne * e.Np, m.NeA * e.Np
+    q = {k: o.arr(k).copy() for k in ("DDENS", "MOMX", "MOMY", "MOMZ", "DRHOT")}
+    aux = {k: o.arr(k).copy() for k in ("DENS_hyd", "PRES_hyd", "THERM_hyd")}
+    t = numpy_dyn.cal_tend_hevi_global(e, m, c, q, aux, o.arr("DPRES"), o.arr("DPhydDx"), o.arr("DPhydDy"), hevi=False)
+    te = o.arr("tend_ex")[:5 * N].reshape(5, -1)[:, :n]
+    for nm, iv in (("DENS_dt", 0), ("RHOT_dt", 1), ("MOMZ_dt", 2), ("MOMX_dt", 3), ("MOMY_dt", 4)):
+        # MOMZ_dt: residual of the near-cancelling vertical pressure gradient and buoyancy (see the cal_vi test)
+        assert rel_l2(t[nm].reshape(-1), te[iv]) <= (1e-11 if nm == "MOMZ_dt" else 1e-13), (panelID, nm)
