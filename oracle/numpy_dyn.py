@@ -538,3 +538,49 @@ def update(elem, mesh, c, q, aux, rk, dt, bc6, hevi=False, filt=None, nsteps=1, 
                 q[k][:ni] = acc
         if filt is not None:
             modal_filter(elem, mesh, q, *filt)
+
+
+def update_sphere(elem, cs, c, qs, auxs, rk, dt, dphyd, filt=None, nsteps=1):
+    """nsteps steps of GLOBALNONHYDRO3D_HEVI on the whole cubed sphere (the six local meshes of one process, driver_nonhydro3d.F90:703-951 with
+    LOCAL_MESH_NUM = 6): per stage the vertical-implicit Newton step of every panel, the panel-edge exchange (cs.exchange_numpy: index reversal
+    and the change of basis of (MOMX, MOMY) across the edges) + the own top / bottom faces, pressure and its exchange, slip walls at the
+    bottom and the top, the explicit tendency of the global equations, the stage combination; then the modal filter.
+    qs / auxs: one dict per panel of flat arrays incl. halo; dphyd: per panel (DPhydDx, DPhydDy)."""
+    ns = rk["nstage"]
+    Np = elem.Np
+    nis = [m.Ne * Np for m in cs.panels]
+    bc6s = [m.halo_bc_types({"btm": 2, "top": 2}) for m in cs.panels]
+    for _ in range(nsteps):
+        q0 = [{k: q[k][:ni].copy() for k in PROG} for q, ni in zip(qs, nis)]
+        kex, kim = [[] for _ in qs], [[] for _ in qs]
+        for st in range(ns):
+            for P, (q, m, ni) in enumerate(zip(qs, cs.panels, nis)):
+                t = cal_vi(elem, m, c, auxs[P], q, q0[P], rk["a_im"][st, st] * dt)
+                kim[P].append(t)
+                for k in PROG:
+                    q[k][:ni] = q[k][:ni] + rk["a_im"][st, st] * dt * t[k]
+            dps = []
+            for P, (q, m) in enumerate(zip(qs, cs.panels)):
+                R, cv, cp = (np.full(m.NeA * Np, c[k]) for k in ("Rdry", "CVdry", "CPdry"))
+                _, dpres = drhot2pres(c, q["DRHOT"], auxs[P]["PRES_hyd"], auxs[P]["THERM_hyd"], R, cv, cp)
+                for k in PROG:
+                    m.exchange_halo_numpy(q[k])            # top / bottom faces (the lateral slots are overwritten by the panel-edge exchange)
+                m.exchange_halo_numpy(dpres)
+                dps.append(dpres)
+            cs.exchange_numpy([dict(q, DPRES=dp) for q, dp in zip(qs, dps)])
+            for P, (q, m, ni) in enumerate(zip(qs, cs.panels, nis)):
+                apply_bc(elem, m, q, bc6s[P])
+                t = cal_tend_hevi_global(elem, m, c, q, auxs[P], dps[P], dphyd[P][0], dphyd[P][1])
+                kex[P].append({"DDENS": t["DENS_dt"].reshape(-1), "MOMX": t["MOMX_dt"].reshape(-1), "MOMY": t["MOMY_dt"].reshape(-1),
+                               "MOMZ": t["MOMZ_dt"].reshape(-1), "DRHOT": t["RHOT_dt"].reshape(-1)})
+            last = st == ns - 1
+            for P, (q, ni) in enumerate(zip(qs, nis)):
+                for k in PROG:
+                    acc = q0[P][k].copy()
+                    for j in range(st + 1):
+                        acc = acc + dt * (rk["b_ex"][j] if last else rk["a_ex"][st + 1, j]) * kex[P][j][k]
+                        acc = acc + dt * (rk["b_im"][j] if last else rk["a_im"][st + 1, j]) * kim[P][j][k]
+                    q[k][:ni] = acc
+        if filt is not None:
+            for q, m in zip(qs, cs.panels):
+                modal_filter(elem, m, q, *filt)

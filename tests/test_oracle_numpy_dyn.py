@@ -190,3 +190,25 @@ def test_numpy_restatement_of_the_global_heve_rows_equals_the_cpp_oracle(panelID
     for nm, iv in (("DENS_dt", 0), ("RHOT_dt", 1), ("MOMZ_dt", 2), ("MOMX_dt", 3), ("MOMY_dt", 4)):
         # MOMZ_dt: residual of the near-cancelling vertical pressure gradient and buoyancy (see the cal_vi test)
         assert rel_l2(t[nm].reshape(-1), te[iv]) <= (1e-11 if nm == "MOMZ_dt" else 1e-13), (panelID, nm)
+
+
+def test_numpy_restatement_of_the_six_panel_step_equals_the_cpp_oracle():
+    """The whole cubed sphere stepped a second time in NumPy (panel-edge exchange by cubedsphere.exchange_numpy, the global explicit
+    tendency, the dense-column Newton step, modal filter) against the C++ oracle's six-panel driver: two steps of IMEX_ARK232."""
+    import oracle_api
+    from cases import GlobalSphereCase, MF
+    case = GlobalSphereCase(p=3, Ne=2, NeZ=2, dt=40.0, tinteg="IMEX_ARK232", modalfilter=True)
+    s = case.make_oracle()
+    e, c = case.elem, case.consts
+    qs = [{k: o.arr(k).copy() for k in numpy_dyn.PROG} for o in s.panels]
+    auxs = [{k: o.arr(k).copy() for k in ("DENS_hyd", "PRES_hyd", "THERM_hyd")} for o in s.panels]
+    dphyd = [(o.arr("DPhydDx").copy(), o.arr("DPhydDy").copy()) for o in s.panels]
+    filt = (e.filter1d(MF["MF_ETAC_h"], MF["MF_ALPHA_h"], MF["MF_ORDER_h"]), e.filter1d(MF["MF_ETAC_v"], MF["MF_ALPHA_v"], MF["MF_ORDER_v"]))
+    numpy_dyn.update_sphere(e, case.cs, c, qs, auxs, oracle_api.rk_tables("IMEX_ARK232"), case.dt, dphyd, filt=filt, nsteps=2)
+    s.update(2)
+    for P, (o, m) in enumerate(zip(s.panels, case.cs.panels)):
+        n = m.Ne * e.Np
+        for k in numpy_dyn.PROG:
+            ref = o.arr(k)[:n]
+            scale = max(np.abs(op.arr(k)[:n]).max() for op in s.panels)
+            assert np.linalg.norm(qs[P][k][:n] - ref) <= 1e-11 * max(np.linalg.norm(ref), 1e-3 * scale * np.sqrt(n)), (P, k)
